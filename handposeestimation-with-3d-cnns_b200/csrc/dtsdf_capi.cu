@@ -1,0 +1,474 @@
+// C ABI of the D-TSDF voxeliser (see include/dtsdf_b200.h for the contract and the
+// reference callables each entry point replaces).  Host-side runtime: argument
+// checking, error mapping, the per-process context with its streams and staging
+// buffers, and the chunked copy/compute pipeline behind the host entry points.
+#include "../../include/dtsdf_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "dtsdf_internal.h"
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorName(e),
+             cudaGetErrorString(e));
+    cudaGetLastError();   // clear the sticky-less error state
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return DTSDF_ERR_NO_DEVICE;
+    if (e == cudaErrorMemoryAllocation) return DTSDF_ERR_ALLOC;
+    return DTSDF_ERR_CUDA;
+}
+
+#define CK(call)                                        \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+int check_cfg(const dtsdf_config* cfg) {
+    if (!cfg) return DTSDF_ERR_INVALID_ARG;
+    if (cfg->voxel_res != 32 && cfg->voxel_res != 48 && cfg->voxel_res != 64) return DTSDF_ERR_UNSUPPORTED;
+    if (cfg->layout != DTSDF_LAYOUT_CXYZ && cfg->layout != DTSDF_LAYOUT_CZYX) return DTSDF_ERR_UNSUPPORTED;
+    if (cfg->bbox_mode < DTSDF_BBOX_PIXELS || cfg->bbox_mode > DTSDF_BBOX_GRID) return DTSDF_ERR_UNSUPPORTED;
+    if (!(cfg->focal > 0.0f) || !(cfg->trunc_mul > 0.0f)) return DTSDF_ERR_INVALID_ARG;
+    return DTSDF_OK;
+}
+
+int header_ok(const int32_t* h) {
+    const int64_t bw = (int64_t)h[4] - h[2], bh = (int64_t)h[5] - h[3];
+    const int64_t lim = 1 << 22;
+    if (bw <= 0 || bh <= 0 || bw > 32767 || bh > 32767) return 0;
+    if (h[2] <= -lim || h[3] <= -lim || h[4] >= lim || h[5] >= lim) return 0;
+    return 1;
+}
+
+// grow-only device / pinned buffers
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return DTSDF_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(bytes, (size_t)4096);
+        CK(cudaMalloc(&p, want));
+        cap = want;
+        return DTSDF_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct dtsdf_ctx {
+    int device = 0;
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    static const int NSLOT = 3;                 // chunks in flight
+    DevBuf d_depth[NSLOT], d_off[NSLOT], d_hdr[NSLOT], d_aux[NSLOT];
+    DevBuf d_vol[NSLOT], d_maxl[NSLOT], d_mid[NSLOT];
+    cudaEvent_t ev_in[NSLOT] = {}, ev_run[NSLOT] = {}, ev_out[NSLOT] = {};
+    // point-cloud path
+    DevBuf d_points, d_idx, d_pc, d_ext, d_misc;
+    int32_t last_n_valid = -1;
+    // joints
+    DevBuf d_j_in, d_j_out, d_j_ml, d_j_mp;
+};
+
+extern "C" {
+
+int dtsdf_abi_version(void) { return DTSDF_ABI_VERSION; }
+
+const char* dtsdf_error_string(int code) {
+    switch (code) {
+        case DTSDF_OK: return "ok";
+        case DTSDF_ERR_INVALID_ARG: return "invalid argument";
+        case DTSDF_ERR_UNSUPPORTED: return "unsupported voxel resolution, layout or bbox mode";
+        case DTSDF_ERR_CUDA: return "CUDA runtime error";
+        case DTSDF_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+        case DTSDF_ERR_ALLOC: return "out of memory";
+        case DTSDF_ERR_BAD_HEADER: return "frame header with empty or oversize bounding box";
+        default: return "unknown error";
+    }
+}
+
+const char* dtsdf_last_cuda_error(void) { return g_cuda_err; }
+
+void dtsdf_default_config(dtsdf_config* cfg) {
+    if (!cfg) return;
+    cfg->voxel_res = 32;
+    cfg->layout = DTSDF_LAYOUT_CXYZ;
+    cfg->bbox_mode = DTSDF_BBOX_PIXELS;
+    cfg->center_x = 160;
+    cfg->center_y = 120;
+    cfg->focal = 241.42f;
+    cfg->trunc_mul = 3.0f;
+}
+
+int dtsdf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int64_t dtsdf_launch_count(void) { return dtsdf::g_launch_count; }
+
+int dtsdf_pack_plan(int32_t n_frames, const int32_t* headers, int64_t* crop_offsets,
+                    int64_t* packed_len, int32_t* max_crop_px) {
+    if (n_frames < 0 || (n_frames > 0 && (!headers || !crop_offsets))) return DTSDF_ERR_INVALID_ARG;
+    int64_t off = 0;
+    int32_t mx = 0;
+    for (int32_t i = 0; i < n_frames; ++i) {
+        const int32_t* h = headers + 6 * (size_t)i;
+        if (!header_ok(h)) return DTSDF_ERR_BAD_HEADER;
+        const int64_t n = ((int64_t)h[4] - h[2]) * ((int64_t)h[5] - h[3]);
+        crop_offsets[i] = off;
+        off += (n + 3) & ~(int64_t)3;
+        if (n > mx) mx = (int32_t)n;
+    }
+    if (packed_len) *packed_len = off;
+    if (max_crop_px) *max_crop_px = mx;
+    return DTSDF_OK;
+}
+
+// ------------------------------------------------------------------ device entry points
+int dtsdf_voxelize_batch(const dtsdf_config* cfg, int32_t n_frames, const float* d_depth_packed,
+                         const int64_t* d_crop_offsets, const int32_t* d_headers,
+                         const float* d_aux, int32_t max_crop_px, float* d_out_vol,
+                         float* d_out_max_l, float* d_out_mid_p, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc != DTSDF_OK) return rc;
+    if (n_frames < 0) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!d_depth_packed || !d_crop_offsets || !d_headers || !d_out_vol) return DTSDF_ERR_INVALID_ARG;
+    if (cfg->bbox_mode != DTSDF_BBOX_PIXELS && !d_aux) return DTSDF_ERR_INVALID_ARG;
+    dtsdf::BatchArgs a;
+    a.depth = d_depth_packed;
+    a.offsets = reinterpret_cast<const long long*>(d_crop_offsets);
+    a.headers = d_headers;
+    a.aux = d_aux;
+    a.vol = d_out_vol;
+    a.max_l = d_out_max_l;
+    a.mid_p = d_out_mid_p;
+    a.n_frames = n_frames;
+    a.cap_floats = 0;
+    a.bbox_mode = cfg->bbox_mode;
+    a.center_x = cfg->center_x;
+    a.center_y = cfg->center_y;
+    a.focal = cfg->focal;
+    a.trunc_mul = cfg->trunc_mul;
+    CK(dtsdf::launch_voxelize(cfg->voxel_res, cfg->layout, a, max_crop_px, (cudaStream_t)stream));
+    return DTSDF_OK;
+}
+
+int dtsdf_point_cloud_batch(int32_t n_frames, double focal, const float* d_depth_packed,
+                            const int64_t* d_crop_offsets, const int32_t* d_headers,
+                            double* d_points, const int64_t* d_point_offsets, int32_t* d_n_valid,
+                            void* stream) {
+    if (n_frames < 0 || !(focal > 0.0)) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!d_depth_packed || !d_crop_offsets || !d_headers || !d_n_valid) return DTSDF_ERR_INVALID_ARG;
+    if (d_points && !d_point_offsets) return DTSDF_ERR_INVALID_ARG;
+    CK(dtsdf::launch_point_cloud(n_frames, focal, d_depth_packed,
+                                 reinterpret_cast<const long long*>(d_crop_offsets), d_headers, d_points,
+                                 reinterpret_cast<const long long*>(d_point_offsets), d_n_valid,
+                                 (cudaStream_t)stream));
+    return DTSDF_OK;
+}
+
+int dtsdf_resample_extrema_batch(int32_t n_frames, int32_t point_num, const double* d_points,
+                                 const int64_t* d_point_offsets, const int32_t* d_indices,
+                                 double* d_out_pc, float* d_out_extrema, void* stream) {
+    if (n_frames < 0 || point_num <= 0) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!d_points || !d_point_offsets || !d_out_extrema) return DTSDF_ERR_INVALID_ARG;
+    CK(dtsdf::launch_resample_extrema(n_frames, point_num, d_points,
+                                      reinterpret_cast<const long long*>(d_point_offsets), d_indices,
+                                      d_out_pc, d_out_extrema, (cudaStream_t)stream));
+    return DTSDF_OK;
+}
+
+int dtsdf_normalize_joints_batch(int32_t n_frames, const float* d_joints, const float* d_max_l,
+                                 const float* d_mid_p, int32_t clamp01, float* d_out, void* stream) {
+    if (n_frames < 0) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!d_joints || !d_max_l || !d_mid_p || !d_out) return DTSDF_ERR_INVALID_ARG;
+    CK(dtsdf::launch_normalize_joints(n_frames, d_joints, d_max_l, d_mid_p, clamp01, d_out,
+                                      (cudaStream_t)stream));
+    return DTSDF_OK;
+}
+
+// ------------------------------------------------------------------ context
+int dtsdf_ctx_create(int32_t device, dtsdf_ctx** out) {
+    if (!out) return DTSDF_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    if (n == 0) return DTSDF_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return DTSDF_ERR_INVALID_ARG;
+    CK(cudaSetDevice(device));
+    int major = 0;
+    CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d is sm_%d?, this library is built for sm_100a only",
+                 device, major * 10);
+        return DTSDF_ERR_NO_DEVICE;
+    }
+    dtsdf_ctx* c = new (std::nothrow) dtsdf_ctx();
+    if (!c) return DTSDF_ERR_ALLOC;
+    c->device = device;
+    cudaError_t err = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
+    for (int i = 0; i < dtsdf_ctx::NSLOT && err == cudaSuccess; ++i) {
+        err = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_run[i], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming);
+    }
+    if (err != cudaSuccess) {
+        dtsdf_ctx_destroy(c);
+        return cuda_fail(err, "context streams/events");
+    }
+    *out = c;
+    return DTSDF_OK;
+}
+
+void dtsdf_ctx_destroy(dtsdf_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < dtsdf_ctx::NSLOT; ++i) {
+        c->d_depth[i].release(); c->d_off[i].release(); c->d_hdr[i].release(); c->d_aux[i].release();
+        c->d_vol[i].release(); c->d_maxl[i].release(); c->d_mid[i].release();
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_run[i]) cudaEventDestroy(c->ev_run[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+    }
+    c->d_points.release(); c->d_idx.release(); c->d_pc.release(); c->d_ext.release(); c->d_misc.release();
+    c->d_j_in.release(); c->d_j_out.release(); c->d_j_ml.release(); c->d_j_mp.release();
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_run) cudaStreamDestroy(c->s_run);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    cudaGetLastError();
+    delete c;
+}
+
+int dtsdf_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return DTSDF_ERR_INVALID_ARG;
+    *ptr = nullptr;
+    if (bytes == 0) return DTSDF_OK;
+    CK(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    return DTSDF_OK;
+}
+
+void dtsdf_host_free(void* ptr) {
+    if (ptr) { cudaFreeHost(ptr); cudaGetLastError(); }
+}
+
+// ------------------------------------------------------------------ host pipeline
+// The batch is cut into chunks of whole frames; chunk k's host->device copy (s_in),
+// kernel (s_run) and device->host copy (s_out) run on their own streams with NSLOT
+// chunk buffers in flight, so for large batches the PCIe traffic in both directions
+// overlaps the kernel.
+int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
+                        const float* h_depth, int64_t packed_len, const int64_t* h_off,
+                        const int32_t* h_hdr, const float* h_aux, float* h_vol, float* h_maxl,
+                        float* h_mid) {
+    if (!c) return DTSDF_ERR_INVALID_ARG;
+    int rc = check_cfg(cfg);
+    if (rc != DTSDF_OK) return rc;
+    if (n_frames < 0 || packed_len < 0) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!h_depth || !h_off || !h_hdr || !h_vol) return DTSDF_ERR_INVALID_ARG;
+    if (cfg->bbox_mode != DTSDF_BBOX_PIXELS && !h_aux) return DTSDF_ERR_INVALID_ARG;
+    const int aux_w = cfg->bbox_mode == DTSDF_BBOX_EXTREMA ? 6 : (cfg->bbox_mode == DTSDF_BBOX_GRID ? 5 : 0);
+    const size_t R = (size_t)cfg->voxel_res;
+    const size_t vol_floats = 3 * R * R * R;
+
+    // validate headers / offsets on the host (the per-frame shims raise on these)
+    for (int32_t i = 0; i < n_frames; ++i) {
+        const int32_t* h = h_hdr + 6 * (size_t)i;
+        if (!header_ok(h)) return DTSDF_ERR_BAD_HEADER;
+        const int64_t n = ((int64_t)h[4] - h[2]) * ((int64_t)h[5] - h[3]);
+        if (h_off[i] < 0 || (h_off[i] & 3) || h_off[i] + ((n + 3) & ~(int64_t)3) > packed_len)
+            return DTSDF_ERR_INVALID_ARG;
+        if (i > 0 && h_off[i] < h_off[i - 1]) return DTSDF_ERR_INVALID_ARG;   // chunking needs ascending offsets
+    }
+    CK(cudaSetDevice(c->device));
+
+    // chunk size: about 64 MB of output per chunk, at least one frame
+    int32_t per_chunk = (int32_t)std::max<size_t>(1, ((size_t)64 << 20) / (vol_floats * 4));
+    if (per_chunk > n_frames) per_chunk = n_frames;
+    const int nchunk = (n_frames + per_chunk - 1) / per_chunk;
+    std::vector<int64_t> rebased;
+
+    for (int k = 0; k < nchunk; ++k) {
+        const int slot = k % dtsdf_ctx::NSLOT;
+        const int32_t f0 = k * per_chunk;
+        const int32_t nf = std::min(per_chunk, n_frames - f0);
+        const int64_t e0 = h_off[f0];
+        const int32_t* hl = h_hdr + 6 * (size_t)(f0 + nf - 1);
+        const int64_t nlast = ((int64_t)hl[4] - hl[2]) * ((int64_t)hl[5] - hl[3]);
+        const int64_t e1 = h_off[f0 + nf - 1] + ((nlast + 3) & ~(int64_t)3);
+        int32_t max_px = 0;
+        rebased.resize(nf);
+        for (int32_t i = 0; i < nf; ++i) {
+            const int32_t* h = h_hdr + 6 * (size_t)(f0 + i);
+            const int64_t n = ((int64_t)h[4] - h[2]) * ((int64_t)h[5] - h[3]);
+            max_px = std::max<int32_t>(max_px, (int32_t)n);
+            rebased[i] = h_off[f0 + i] - e0;
+        }
+        // the slot's buffers are free once its previous D2H has finished (which also implies
+        // that the kernel reading its input buffers has finished)
+        if (k >= dtsdf_ctx::NSLOT) CK(cudaEventSynchronize(c->ev_out[slot]));
+        if ((rc = c->d_depth[slot].reserve((size_t)(e1 - e0) * 4)) != DTSDF_OK) return rc;
+        if ((rc = c->d_off[slot].reserve((size_t)nf * 8)) != DTSDF_OK) return rc;
+        if ((rc = c->d_hdr[slot].reserve((size_t)nf * 24)) != DTSDF_OK) return rc;
+        if (aux_w && (rc = c->d_aux[slot].reserve((size_t)nf * aux_w * 4)) != DTSDF_OK) return rc;
+        if ((rc = c->d_vol[slot].reserve((size_t)nf * vol_floats * 4)) != DTSDF_OK) return rc;
+        if ((rc = c->d_maxl[slot].reserve((size_t)nf * 4)) != DTSDF_OK) return rc;
+        if ((rc = c->d_mid[slot].reserve((size_t)nf * 12)) != DTSDF_OK) return rc;
+
+        // H2D on s_in.  `rebased` is pageable host memory: cudaMemcpyAsync stages it before
+        // returning, so reusing the vector for the next chunk is safe.
+        CK(cudaMemcpyAsync(c->d_depth[slot].p, h_depth + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaMemcpyAsync(c->d_off[slot].p, rebased.data(), (size_t)nf * 8, cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaMemcpyAsync(c->d_hdr[slot].p, h_hdr + 6 * (size_t)f0, (size_t)nf * 24, cudaMemcpyHostToDevice, c->s_in));
+        if (aux_w)
+            CK(cudaMemcpyAsync(c->d_aux[slot].p, h_aux + (size_t)aux_w * f0, (size_t)nf * aux_w * 4,
+                               cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaEventRecord(c->ev_in[slot], c->s_in));
+
+        // kernel on s_run
+        CK(cudaStreamWaitEvent(c->s_run, c->ev_in[slot], 0));
+        rc = dtsdf_voxelize_batch(cfg, nf, (const float*)c->d_depth[slot].p, (const int64_t*)c->d_off[slot].p,
+                                  (const int32_t*)c->d_hdr[slot].p, aux_w ? (const float*)c->d_aux[slot].p : nullptr,
+                                  max_px, (float*)c->d_vol[slot].p, (float*)c->d_maxl[slot].p,
+                                  (float*)c->d_mid[slot].p, c->s_run);
+        if (rc != DTSDF_OK) return rc;
+        CK(cudaEventRecord(c->ev_run[slot], c->s_run));
+
+        // D2H on s_out
+        CK(cudaStreamWaitEvent(c->s_out, c->ev_run[slot], 0));
+        CK(cudaMemcpyAsync(h_vol + (size_t)f0 * vol_floats, c->d_vol[slot].p, (size_t)nf * vol_floats * 4,
+                           cudaMemcpyDeviceToHost, c->s_out));
+        if (h_maxl)
+            CK(cudaMemcpyAsync(h_maxl + f0, c->d_maxl[slot].p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->s_out));
+        if (h_mid)
+            CK(cudaMemcpyAsync(h_mid + 3 * (size_t)f0, c->d_mid[slot].p, (size_t)nf * 12, cudaMemcpyDeviceToHost, c->s_out));
+        CK(cudaEventRecord(c->ev_out[slot], c->s_out));
+    }
+    CK(cudaStreamSynchronize(c->s_out));
+    CK(cudaStreamSynchronize(c->s_run));
+    CK(cudaStreamSynchronize(c->s_in));
+    return DTSDF_OK;
+}
+
+int dtsdf_point_cloud_host(dtsdf_ctx* c, double focal, const int32_t* h_header, const float* h_depth,
+                           double* h_out_points, int32_t* n_valid) {
+    if (!c || !h_header || !h_depth || !n_valid || !(focal > 0.0)) return DTSDF_ERR_INVALID_ARG;
+    if (!header_ok(h_header)) return DTSDF_ERR_BAD_HEADER;
+    CK(cudaSetDevice(c->device));
+    const int64_t n = ((int64_t)h_header[4] - h_header[2]) * ((int64_t)h_header[5] - h_header[3]);
+    const int64_t n_pad = (n + 3) & ~(int64_t)3;
+    int rc;
+    if ((rc = c->d_depth[0].reserve((size_t)n_pad * 4)) != DTSDF_OK) return rc;
+    if ((rc = c->d_points.reserve((size_t)n * 24)) != DTSDF_OK) return rc;
+    // misc: [0..7] crop offset, [8..15] point offset, [16..39] header, [40..43] n_valid
+    if ((rc = c->d_misc.reserve(64)) != DTSDF_OK) return rc;
+    unsigned char misc[64];
+    memset(misc, 0, sizeof(misc));
+    memcpy(misc + 16, h_header, 24);
+    cudaStream_t s = c->s_run;
+    CK(cudaMemcpyAsync(c->d_depth[0].p, h_depth, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->d_misc.p, misc, 64, cudaMemcpyHostToDevice, s));
+    unsigned char* dm = (unsigned char*)c->d_misc.p;
+    rc = dtsdf_point_cloud_batch(1, focal, (const float*)c->d_depth[0].p, (const int64_t*)dm,
+                                 (const int32_t*)(dm + 16), (double*)c->d_points.p, (const int64_t*)(dm + 8),
+                                 (int32_t*)(dm + 40), s);
+    if (rc != DTSDF_OK) return rc;
+    CK(cudaMemcpyAsync(n_valid, dm + 40, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    c->last_n_valid = *n_valid;
+    if (h_out_points && *n_valid > 0) {
+        CK(cudaMemcpyAsync(h_out_points, c->d_points.p, (size_t)(*n_valid) * 24, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return DTSDF_OK;
+}
+
+int dtsdf_resample_extrema_host(dtsdf_ctx* c, int32_t point_num, const double* h_points, int32_t n_points,
+                                const int32_t* h_indices, double* h_out_pc, float* h_out_extrema) {
+    if (!c || point_num <= 0 || !h_out_extrema) return DTSDF_ERR_INVALID_ARG;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->s_run;
+    int rc;
+    int32_t avail;
+    if (h_points) {
+        if (n_points <= 0) return DTSDF_ERR_INVALID_ARG;
+        if ((rc = c->d_points.reserve((size_t)n_points * 24)) != DTSDF_OK) return rc;
+        CK(cudaMemcpyAsync(c->d_points.p, h_points, (size_t)n_points * 24, cudaMemcpyHostToDevice, s));
+        c->last_n_valid = n_points;
+        avail = n_points;
+    } else {
+        if (c->last_n_valid <= 0) return DTSDF_ERR_INVALID_ARG;   // no resident cloud
+        avail = c->last_n_valid;
+    }
+    if (h_indices) {
+        for (int32_t i = 0; i < point_num; ++i)
+            if (h_indices[i] < 0 || h_indices[i] >= avail) return DTSDF_ERR_INVALID_ARG;
+        if ((rc = c->d_idx.reserve((size_t)point_num * 4)) != DTSDF_OK) return rc;
+        CK(cudaMemcpyAsync(c->d_idx.p, h_indices, (size_t)point_num * 4, cudaMemcpyHostToDevice, s));
+    } else if (point_num > avail) {
+        return DTSDF_ERR_INVALID_ARG;
+    }
+    if ((rc = c->d_misc.reserve(64)) != DTSDF_OK) return rc;
+    if ((rc = c->d_ext.reserve(24)) != DTSDF_OK) return rc;
+    if (h_out_pc && (rc = c->d_pc.reserve((size_t)point_num * 24)) != DTSDF_OK) return rc;
+    CK(cudaMemsetAsync(c->d_misc.p, 0, 16, s));                   // point offset 0
+    rc = dtsdf_resample_extrema_batch(1, point_num, (const double*)c->d_points.p,
+                                      (const int64_t*)((unsigned char*)c->d_misc.p + 8),
+                                      h_indices ? (const int32_t*)c->d_idx.p : nullptr,
+                                      h_out_pc ? (double*)c->d_pc.p : nullptr, (float*)c->d_ext.p, s);
+    if (rc != DTSDF_OK) return rc;
+    CK(cudaMemcpyAsync(h_out_extrema, c->d_ext.p, 24, cudaMemcpyDeviceToHost, s));
+    if (h_out_pc)
+        CK(cudaMemcpyAsync(h_out_pc, c->d_pc.p, (size_t)point_num * 24, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return DTSDF_OK;
+}
+
+int dtsdf_normalize_joints_host(dtsdf_ctx* c, int32_t n_frames, const float* h_joints,
+                                const float* h_max_l, const float* h_mid_p, int32_t clamp01,
+                                float* h_out) {
+    if (!c || n_frames < 0) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!h_joints || !h_max_l || !h_mid_p || !h_out) return DTSDF_ERR_INVALID_ARG;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->s_run;
+    int rc;
+    const size_t nj = (size_t)n_frames * 63 * 4;
+    if ((rc = c->d_j_in.reserve(nj)) != DTSDF_OK) return rc;
+    if ((rc = c->d_j_out.reserve(nj)) != DTSDF_OK) return rc;
+    if ((rc = c->d_j_ml.reserve((size_t)n_frames * 4)) != DTSDF_OK) return rc;
+    if ((rc = c->d_j_mp.reserve((size_t)n_frames * 12)) != DTSDF_OK) return rc;
+    CK(cudaMemcpyAsync(c->d_j_in.p, h_joints, nj, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->d_j_ml.p, h_max_l, (size_t)n_frames * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->d_j_mp.p, h_mid_p, (size_t)n_frames * 12, cudaMemcpyHostToDevice, s));
+    rc = dtsdf_normalize_joints_batch(n_frames, (const float*)c->d_j_in.p, (const float*)c->d_j_ml.p,
+                                      (const float*)c->d_j_mp.p, clamp01, (float*)c->d_j_out.p, s);
+    if (rc != DTSDF_OK) return rc;
+    CK(cudaMemcpyAsync(h_out, c->d_j_out.p, nj, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return DTSDF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,46 @@
+// Internal interface between the C ABI (dtsdf_capi.cu) and the kernels (dtsdf_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dtsdf {
+
+// Arguments of the fused voxeliser, passed by value to the kernel.
+struct BatchArgs {
+    const float*     depth;      // packed crops
+    const long long* offsets;    // [n] start of crop i in floats (multiple of 4)
+    const int*       headers;    // [n][6]
+    const float*     aux;        // [n][6] extrema, [n][5] grid params, or nullptr
+    float*           vol;        // [n][3][R][R][R]
+    float*           max_l;      // [n] or nullptr
+    float*           mid_p;      // [n][3] or nullptr
+    int              n_frames;
+    int              cap_floats; // shared-memory staging capacity (floats, multiple of 4)
+    int              bbox_mode;
+    int              center_x;
+    int              center_y;
+    float            focal;
+    float            trunc_mul;
+};
+
+// Picks the staging capacity / grid and launches the fused kernel.  Returns a cudaError_t.
+cudaError_t launch_voxelize(int voxel_res, int layout, BatchArgs args, int max_crop_px,
+                            cudaStream_t stream);
+
+cudaError_t launch_point_cloud(int n_frames, double focal, const float* depth,
+                               const long long* offsets, const int* headers, double* points,
+                               const long long* point_offsets, int* n_valid,
+                               cudaStream_t stream);
+
+cudaError_t launch_resample_extrema(int n_frames, int point_num, const double* points,
+                                    const long long* point_offsets, const int* indices,
+                                    double* out_pc, float* out_extrema, cudaStream_t stream);
+
+cudaError_t launch_normalize_joints(int n_frames, const float* joints, const float* max_l,
+                                    const float* mid_p, int clamp01, float* out,
+                                    cudaStream_t stream);
+
+// kernels launched by this process (claimed in bench.py's gpu_launches)
+extern long long g_launch_count;
+
+}  // namespace dtsdf

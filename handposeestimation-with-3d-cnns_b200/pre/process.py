@@ -1,0 +1,134 @@
+"""Drop-in for the reference's ``pre/process.py``: same class, methods and return values,
+computed by the sm_100a CUDA library (include/dtsdf_b200.h).  No CPU fallback.
+
+Reference behaviour kept (paths relative to the reference root):
+  DataProcess(data, ground_truth, point_num=6000, aug=False) ....... pre/process.py:6-11
+  .process() -> [point_clouds, tsdf, max_l, mid_p] .................. pre/process.py:13-28
+  .point_cloud(), .set_length(), .tsdf_f(), .max_min_point(), .tsdf_cal()  pre/process.py:30-200
+  cut_version aliases: DataProcess(data, point_num=6000, aug=False), .get_points(),
+  .normalize(gt, max_l, mid_p) ..................................... cut_version/pre/process.py:6,52,251
+
+What runs where: back-projection + compaction, the gather by the resampling index vector,
+the per-axis extrema, the grid parameters and the voxel loop run on the GPU.  The index
+vector itself is drawn on the host from the *global* ``np.random`` stream with exactly
+the reference's calls (pre/process.py:75-80), so seeding ``np.random`` reproduces the
+reference's sampled cloud bit for bit.
+
+Differences, all deliberate:
+  * the volume is returned as float32 ``[3,32,32,32]`` (c,x,y,z); the reference returns the
+    same values in a float64 array (every value it stores is a float32 scalar);
+  * ``aug=True`` raises NotImplementedError: the reference's ``data_aug`` itself raises
+    ``AxisError`` (pre/process.py:252, ``np.mean(..., axis=2)`` on a 2-D cloud), so there is
+    no behaviour to reproduce.
+"""
+import numpy as np
+
+from _bind import package
+
+_pkg = package()
+
+
+class DataProcess(object):
+
+    def __init__(self, data, ground_truth=None, point_num=6000, aug=False):
+        # cut_version signature DataProcess(data, point_num=6000, aug=False)
+        # (cut_version/pre/process.py:6): the second positional argument is the point count
+        if isinstance(ground_truth, (int, np.integer)) and not isinstance(ground_truth, bool):
+            if isinstance(point_num, (bool, np.bool_)):
+                aug = bool(point_num)
+            point_num = int(ground_truth)
+            ground_truth = None
+        self.fFocal_msra = 241.42
+        self.data = data
+        self.ground_truth = ground_truth
+        self.point_num = point_num
+        self.aug = aug
+        self._vox = _pkg.default_voxelizer()
+        self._cloud = None          # last array returned by point_cloud() (resident on the device)
+        self._sampled = None        # (array returned by set_length, point_max, point_min)
+
+    # ------------------------------------------------------------------ pre/process.py:13-28
+    def process(self):
+        hand_points = self.point_cloud()
+        point_clouds = self.set_length(hand_points)
+        tsdf, max_l, mid_p = self.tsdf_f(point_clouds)
+        if self.aug:
+            hand_aug, ground_truth_aug = self.data_aug(hand_points)
+            point_clouds_aug = self.set_length(hand_aug)
+            tsdf_aug, max_l_aug, mid_p_aug = self.tsdf_f(point_clouds_aug)
+            return [point_clouds, tsdf, max_l, mid_p,
+                    point_clouds_aug, tsdf_aug, max_l_aug, mid_p_aug, ground_truth_aug]
+        return [point_clouds, tsdf, max_l, mid_p]
+
+    # ------------------------------------------------------------------ pre/process.py:30-68
+    def point_cloud(self):
+        "get point cloud from depth informations (float64[n_valid, 3])"
+        pts = self._vox.point_cloud(self.data)
+        self._cloud = pts
+        return pts
+
+    # ------------------------------------------------------------------ pre/process.py:70-84
+    def set_length(self, hand_points):
+        "set the point number"
+        point_num = self.point_num
+        point_shape = hand_points.shape[0]
+        if point_shape < point_num:
+            rand_idx = np.arange(0, point_num, 1, dtype=np.int32)
+            rand_idx[point_shape:] = np.random.randint(0, point_shape,
+                                                       size=point_num - point_shape)
+        else:
+            rand_idx = np.random.randint(0, point_shape, size=point_num)
+        resident = hand_points is self._cloud
+        pc, pmax, pmin = self._vox.resample_extrema(
+            point_num, rand_idx, points=None if resident else hand_points)
+        if not resident:
+            self._cloud = None      # the device now holds hand_points, not the last point_cloud()
+        self._sampled = (pc, pmax, pmin)
+        return pc
+
+    # cut_version/pre/process.py:52-67
+    def get_points(self):
+        return self.set_length(self.point_cloud())
+
+    # ------------------------------------------------------------------ pre/process.py:102-120
+    def max_min_point(self, point_cloud):
+        if self._sampled is not None and point_cloud is self._sampled[0]:
+            return self._sampled[1].copy(), self._sampled[2].copy()
+        pc = np.asarray(point_cloud, dtype=np.float64)
+        self._cloud = None
+        _, pmax, pmin = self._vox.resample_extrema(pc.shape[0], None, points=pc, want_points=False)
+        return pmax, pmin
+
+    # ------------------------------------------------------------------ pre/process.py:86-100
+    def tsdf_f(self, point_cloud):
+        point_max, point_min = self.max_min_point(point_cloud)
+        aux = np.concatenate([point_max, point_min]).astype(np.float32).reshape(1, 6)
+        vol, max_l, mid_p = self._vox.voxelize_frames(
+            [self.data], layout=_pkg.LAYOUT_CXYZ, bbox_mode=_pkg.BBOX_EXTREMA, aux=aux)
+        return vol[0], max_l[0], mid_p[0]
+
+    # ------------------------------------------------------------------ pre/process.py:122-200
+    def tsdf_cal(self, vox_ori, voxel_len, truncation):
+        aux = np.empty((1, 5), dtype=np.float32)
+        aux[0, :3] = np.asarray(vox_ori, dtype=np.float32)
+        aux[0, 3] = np.float32(voxel_len)
+        aux[0, 4] = np.float32(truncation)
+        vol, _, _ = self._vox.voxelize_frames(
+            [self.data], layout=_pkg.LAYOUT_CXYZ, bbox_mode=_pkg.BBOX_GRID, aux=aux)
+        return vol[0]
+
+    # ------------------------------------------------------------------ pre/process.py:202-261
+    def data_aug(self, *args):
+        raise NotImplementedError(
+            "data_aug: the reference implementation raises AxisError (pre/process.py:252) and the "
+            "cut_version variant voxelises the un-augmented depth map "
+            "(cut_version/pre/process.py:207); augmentation is specified separately "
+            "(SURVEY.md section 8f, N2)")
+
+    # ------------------------------------------------------------------ cut_version/pre/process.py:251-263
+    def normalize(self, ground_truth, max_l, mid_p):
+        gt = np.asarray(ground_truth, dtype=np.float32).reshape(-1, 63)
+        n = gt.shape[0]
+        ml = np.broadcast_to(np.asarray(max_l, dtype=np.float32).reshape(-1), (n,))
+        mp = np.broadcast_to(np.asarray(mid_p, dtype=np.float32).reshape(-1, 3), (n, 3))
+        return self._vox.normalize_joints(gt, ml, mp)

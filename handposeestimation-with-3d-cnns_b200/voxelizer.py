@@ -1,0 +1,270 @@
+"""Host-side API of the B200 D-TSDF voxeliser on top of the C ABI (capi.py).
+
+Two ways in:
+
+* ``Voxelizer`` - NumPy in, NumPy out, through the library's *host* entry points
+  (its own streams, chunked copy/compute overlap).  The drop-in modules in ``pre/``
+  (process.py, tsdf_for.py, tsdf_numba.py) are thin wrappers over this class.
+* ``voxelize_device`` and friends - torch CUDA tensors in and out through the
+  *device* entry points on torch's current stream; nothing leaves HBM.  torch is
+  only used for device memory and streams.
+"""
+import ctypes
+
+import numpy as np
+
+from . import capi
+from .capi import (BBOX_EXTREMA, BBOX_GRID, BBOX_PIXELS, LAYOUT_CXYZ, LAYOUT_CZYX, check,
+                   load_library)
+
+FOCAL = 241.42          # pre/process.py:7, pre/tsdf_numba.py:8
+CENTER_X = 160          # pre/process.py:133, pre/tsdf_numba.py:9
+CENTER_Y = 120          # pre/process.py:134, pre/tsdf_numba.py:10
+VOXEL_RES = 32          # pre/process.py:88
+
+
+def frame_depth(frame):
+    """Depth vector of a frame record: key 'depth' (process.py / tsdf_for.py) or 'data'
+    (pre/tsdf_numba.py:132-133)."""
+    if "depth" in frame:
+        return frame["depth"]
+    return frame["data"]
+
+
+def pack_frames(frames, pinned=False):
+    """Packs frame records into the batched input format of include/dtsdf_b200.h.
+
+    Returns ``(headers int32[n,6], offsets int64[n], packed float32[packed_len], max_crop_px)``;
+    crop starts are 16-byte aligned and the tail padding is zero.  With ``pinned=True`` the
+    packed buffer is page-locked and a fifth value, its owning ``PinnedBuffer``, is returned.
+    """
+    n = len(frames)
+    headers = np.empty((n, 6), dtype=np.int32)
+    for i, fr in enumerate(frames):
+        h = np.asarray(fr["header"]).reshape(-1)
+        if h.size < 6:
+            raise ValueError("frame %d: header needs 6 int32 values" % i)
+        headers[i] = h[:6]
+    offsets, packed_len, max_px = capi.pack_plan(headers)
+    if pinned:
+        buf = capi.PinnedBuffer(max(packed_len, 4), np.float32)
+        packed = buf.array
+        packed[:] = 0
+    else:
+        buf = None
+        packed = np.zeros(max(packed_len, 4), dtype=np.float32)
+    for i, fr in enumerate(frames):
+        d = np.asarray(frame_depth(fr), dtype=np.float32).reshape(-1)
+        n_px = int(headers[i, 4] - headers[i, 2]) * int(headers[i, 5] - headers[i, 3])
+        if d.size != n_px:
+            raise ValueError("frame %d: depth has %d values, bounding box has %d pixels" % (i, d.size, n_px))
+        packed[offsets[i]:offsets[i] + n_px] = d
+    if pinned:
+        return headers, offsets, packed, max_px, buf
+    return headers, offsets, packed, max_px
+
+
+class Voxelizer:
+    """NumPy-facing voxeliser bound to one CUDA device (host entry points of the C ABI)."""
+
+    def __init__(self, device=0, voxel_res=VOXEL_RES, focal=FOCAL, center_x=CENTER_X, center_y=CENTER_Y,
+                 trunc_mul=3.0):
+        self._lib = load_library()
+        self.voxel_res = int(voxel_res)
+        self.focal = float(focal)
+        self.center_x = int(center_x)
+        self.center_y = int(center_y)
+        self.trunc_mul = float(trunc_mul)
+        self._ctx = ctypes.c_void_p()
+        check(self._lib.dtsdf_ctx_create(int(device), ctypes.byref(self._ctx)))
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.dtsdf_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def config(self, layout=LAYOUT_CXYZ, bbox_mode=BBOX_PIXELS, voxel_res=None):
+        cfg = capi.default_config(voxel_res or self.voxel_res, layout, bbox_mode)
+        cfg.focal = self.focal
+        cfg.center_x = self.center_x
+        cfg.center_y = self.center_y
+        cfg.trunc_mul = self.trunc_mul
+        return cfg
+
+    # ------------------------------------------------------------------ voxelisation
+    def voxelize_packed(self, headers, offsets, packed, layout=LAYOUT_CXYZ, bbox_mode=BBOX_PIXELS,
+                        aux=None, voxel_res=None, out_vol=None, out_max_l=None, out_mid_p=None):
+        """``dtsdf_voxelize_host`` on an already packed batch (see pack_frames).
+
+        ``out_*`` may be preallocated (e.g. pinned) arrays.  Returns (vol, max_l, mid_p).
+        """
+        R = int(voxel_res or self.voxel_res)
+        headers = np.ascontiguousarray(headers, dtype=np.int32).reshape(-1, 6)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = headers.shape[0]
+        assert packed.dtype == np.float32 and packed.flags["C_CONTIGUOUS"]
+        if out_vol is None:
+            out_vol = np.empty((n, 3, R, R, R), dtype=np.float32)
+        if out_max_l is None:
+            out_max_l = np.empty(n, dtype=np.float32)
+        if out_mid_p is None:
+            out_mid_p = np.empty((n, 3), dtype=np.float32)
+        if aux is not None:
+            aux = np.ascontiguousarray(aux, dtype=np.float32)
+            width = 6 if bbox_mode == BBOX_EXTREMA else 5
+            if aux.shape != (n, width):
+                raise ValueError("aux must be float32[%d,%d]" % (n, width))
+        cfg = self.config(layout, bbox_mode, R)
+        check(self._lib.dtsdf_voxelize_host(
+            self._ctx, ctypes.byref(cfg), n, capi._ptr(packed), int(packed.size), capi._ptr(offsets),
+            capi._ptr(headers), capi._ptr(aux), capi._ptr(out_vol), capi._ptr(out_max_l),
+            capi._ptr(out_mid_p)))
+        return out_vol, out_max_l, out_mid_p
+
+    def voxelize_frames(self, frames, layout=LAYOUT_CXYZ, bbox_mode=BBOX_PIXELS, aux=None, voxel_res=None):
+        """Frame records -> (vol float32[n,3,R,R,R], max_l float32[n], mid_p float32[n,3])."""
+        headers, offsets, packed, _ = pack_frames(frames)
+        return self.voxelize_packed(headers, offsets, packed, layout, bbox_mode, aux, voxel_res)
+
+    # ------------------------------------------------------------------ process.py pieces
+    def point_cloud(self, frame):
+        """DataProcess.point_cloud (pre/process.py:30-68): float64[n_valid,3]; the cloud also
+        stays resident on the device for ``resample_extrema``."""
+        header = np.ascontiguousarray(np.asarray(frame["header"]).reshape(-1)[:6], dtype=np.int32)
+        depth = np.ascontiguousarray(frame_depth(frame), dtype=np.float32).reshape(-1)
+        n_px = int(header[4] - header[2]) * int(header[5] - header[3])
+        if depth.size != n_px:
+            raise ValueError("depth has %d values, bounding box has %d pixels" % (depth.size, n_px))
+        pts = np.empty((max(n_px, 1), 3), dtype=np.float64)
+        n_valid = ctypes.c_int32(0)
+        check(self._lib.dtsdf_point_cloud_host(self._ctx, ctypes.c_double(self.focal), capi._ptr(header),
+                                               capi._ptr(depth), capi._ptr(pts), ctypes.byref(n_valid)))
+        return pts[:n_valid.value].copy()
+
+    def resample_extrema(self, point_num, indices=None, points=None, want_points=True):
+        """Gather ``point_num`` rows by ``indices`` (pre/process.py:82) from ``points`` (or the cloud
+        left on the device by ``point_cloud``) and reduce (max, min) (pre/process.py:102-120).
+
+        Returns ``(pc float64[point_num,3] or None, point_max float32[3], point_min float32[3])``.
+        """
+        point_num = int(point_num)
+        idx = None if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
+        if idx is not None and idx.size != point_num:
+            raise ValueError("indices must have point_num entries")
+        pts = None
+        n_points = 0
+        if points is not None:
+            pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+            n_points = pts.shape[0]
+        out_pc = np.empty((point_num, 3), dtype=np.float64) if want_points else None
+        ext = np.empty(6, dtype=np.float32)
+        check(self._lib.dtsdf_resample_extrema_host(self._ctx, point_num, capi._ptr(pts), n_points,
+                                                    capi._ptr(idx), capi._ptr(out_pc), capi._ptr(ext)))
+        return out_pc, ext[:3].copy(), ext[3:].copy()
+
+    def normalize_joints(self, joints, max_l, mid_p, clamp01=False):
+        """(gt - mid_p)/max_l + 0.5 (pre/joint_nor.py:8-18), float32[n,63]."""
+        j = np.ascontiguousarray(joints, dtype=np.float32).reshape(-1, 63)
+        n = j.shape[0]
+        ml = np.ascontiguousarray(max_l, dtype=np.float32).reshape(n)
+        mp = np.ascontiguousarray(mid_p, dtype=np.float32).reshape(n, 3)
+        out = np.empty_like(j)
+        check(self._lib.dtsdf_normalize_joints_host(self._ctx, n, capi._ptr(j), capi._ptr(ml), capi._ptr(mp),
+                                                    1 if clamp01 else 0, capi._ptr(out)))
+        return out
+
+
+_default_voxelizers = {}
+
+
+def default_voxelizer(device=0):
+    """Process-wide Voxelizer used by the drop-in modules in ``pre/``."""
+    v = _default_voxelizers.get(device)
+    if v is None:
+        v = Voxelizer(device=device)
+        _default_voxelizers[device] = v
+    return v
+
+
+# ---------------------------------------------------------------------- device-resident path
+def _torch_stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def voxelize_device(depth_packed, offsets, headers, max_crop_px=0, cfg=None, aux=None,
+                    out_vol=None, out_max_l=None, out_mid_p=None, stream=None):
+    """``dtsdf_voxelize_batch`` on torch CUDA tensors, asynchronous on torch's current stream.
+
+    depth_packed float32[packed_len], offsets int64[n], headers int32[n,6] - all on the same
+    CUDA device.  Returns (vol float32[n,3,R,R,R], max_l float32[n], mid_p float32[n,3]).
+    """
+    import torch
+    if not (depth_packed.is_cuda and offsets.is_cuda and headers.is_cuda):
+        raise RuntimeError("voxelize_device needs CUDA tensors; there is no CPU fallback")
+    assert depth_packed.dtype == torch.float32 and offsets.dtype == torch.int64 and headers.dtype == torch.int32
+    assert depth_packed.is_contiguous() and offsets.is_contiguous() and headers.is_contiguous()
+    cfg = cfg or capi.default_config()
+    n = int(headers.shape[0])
+    R = int(cfg.voxel_res)
+    dev = depth_packed.device
+    if out_vol is None:
+        out_vol = torch.empty((n, 3, R, R, R), dtype=torch.float32, device=dev)
+    if out_max_l is None:
+        out_max_l = torch.empty((n,), dtype=torch.float32, device=dev)
+    if out_mid_p is None:
+        out_mid_p = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    aux_ptr = None
+    if aux is not None:
+        assert aux.is_cuda and aux.dtype == torch.float32 and aux.is_contiguous()
+        aux_ptr = aux.data_ptr()
+    with torch.cuda.device(dev):
+        check(load_library().dtsdf_voxelize_batch(
+            ctypes.byref(cfg), n, depth_packed.data_ptr(), offsets.data_ptr(), headers.data_ptr(), aux_ptr,
+            int(max_crop_px), out_vol.data_ptr(), out_max_l.data_ptr(), out_mid_p.data_ptr(),
+            _torch_stream_ptr(stream)))
+    return out_vol, out_max_l, out_mid_p
+
+
+def normalize_joints_device(joints, max_l, mid_p, clamp01=True, out=None, stream=None):
+    """``dtsdf_normalize_joints_batch`` on torch CUDA tensors (3D_CNN/train.py:236-244)."""
+    import torch
+    assert joints.is_cuda and joints.dtype == torch.float32 and joints.is_contiguous()
+    n = int(joints.shape[0])
+    if out is None:
+        out = torch.empty((n, 63), dtype=torch.float32, device=joints.device)
+    with torch.cuda.device(joints.device):
+        check(load_library().dtsdf_normalize_joints_batch(
+            n, joints.data_ptr(), max_l.contiguous().data_ptr(), mid_p.contiguous().data_ptr(),
+            1 if clamp01 else 0, out.data_ptr(), _torch_stream_ptr(stream)))
+    return out
+
+
+def shard_range(n_frames, rank, world_size):
+    """Contiguous frame range [lo, hi) of ``rank``: frames are independent, so
+    the batch is cut into ``world_size`` near-equal contiguous shards and nothing is exchanged
+    while voxelising."""
+    base, rem = divmod(int(n_frames), int(world_size))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def shard_packed(headers, offsets, packed, rank, world_size):
+    """Rank-local view of a packed batch: (headers, rebased offsets, packed slice)."""
+    n = headers.shape[0]
+    lo, hi = shard_range(n, rank, world_size)
+    if hi == lo:
+        return headers[lo:hi], offsets[lo:hi], packed[:0]
+    e0 = int(offsets[lo])
+    h = headers[hi - 1]
+    n_last = int(h[4] - h[2]) * int(h[5] - h[3])
+    e1 = int(offsets[hi - 1]) + ((n_last + 3) & ~3)
+    return headers[lo:hi], offsets[lo:hi] - e0, packed[e0:e1]

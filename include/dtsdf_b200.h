@@ -1,0 +1,202 @@
+/*
+ * dtsdf_b200.h — C ABI of the B200-native projective directional TSDF (D-TSDF)
+ * voxeliser: MSRA depth crop + bounding box -> 3 x R^3 float volume.
+ *
+ * This is the drop-in boundary for the hot path of
+ * Moon0shang/HandPoseEstimation-with-3D-CNNs.  The reference has no FFI of its
+ * own (it is pure Python); every entry point below names the reference callable
+ * it replaces (paths relative to the reference root).  The Python modules under
+ * handposeestimation-with-3d-cnns_b200/pre/ (process.py, tsdf_for.py,
+ * tsdf_numba.py) bind these symbols with ctypes and keep the reference's names
+ * and signatures; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C types only; no CUDA or torch types in any signature
+ *     (`void* stream` is a cudaStream_t, NULL = the legacy default stream);
+ *   - every function returns DTSDF_OK (0) or a negative DTSDF_ERR_* code and
+ *     never throws; dtsdf_error_string() / dtsdf_last_cuda_error() explain;
+ *   - "device" entry points take device pointers owned by the caller, enqueue
+ *     work on `stream` and return without synchronising;
+ *   - "host" entry points take host pointers, run on the context's own streams
+ *     and return when the outputs are complete;
+ *   - there is no CPU fallback: without a usable CUDA device every compute entry
+ *     point fails with DTSDF_ERR_NO_DEVICE / DTSDF_ERR_CUDA.
+ *
+ * Frame record (reference: pre/read_MSRA.py:155-164, pre/process.py:32-40)
+ *   header  int32[6] = {img_w, img_h, left, top, right, bottom}, right/bottom
+ *           exclusive: bw = right-left, bh = bottom-top
+ *   depth   float32[bw*bh], row-major over the crop, millimetres, 0 = background
+ *
+ * Packed batch
+ *   depth_packed  float32[packed_len]: the crops back to back; crop i starts at
+ *                 element crop_offsets[i], which must be a multiple of 4 (16-byte
+ *                 aligned, so the crop can be bulk-copied to shared memory by
+ *                 TMA), and the buffer must be readable up to the next multiple
+ *                 of 4 elements after each crop's end (dtsdf_pack_plan() does
+ *                 both);
+ *   crop_offsets  int64[n_frames];
+ *   headers       int32[n_frames][6].
+ */
+#ifndef DTSDF_B200_H
+#define DTSDF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTSDF_ABI_VERSION 1
+
+/* error codes */
+#define DTSDF_OK                 0
+#define DTSDF_ERR_INVALID_ARG   -1
+#define DTSDF_ERR_UNSUPPORTED   -2   /* voxel_res not in {32,48,64}, unknown layout/mode */
+#define DTSDF_ERR_CUDA          -3   /* a CUDA runtime call failed, see dtsdf_last_cuda_error() */
+#define DTSDF_ERR_NO_DEVICE     -4   /* no CUDA device / not an sm_100 device */
+#define DTSDF_ERR_ALLOC         -5
+#define DTSDF_ERR_BAD_HEADER    -6   /* a frame header has bw <= 0, bh <= 0 or a crop > 32767 px wide/high */
+
+/* volume layouts */
+#define DTSDF_LAYOUT_CXYZ 0   /* out[c][x][y][z]: pre/process.py:196-198, pre/tsdf_for.py:118-120,
+                                 the layout of the result/ tree and of 3D_CNN/dataset.py:35 */
+#define DTSDF_LAYOUT_CZYX 1   /* out[c][z][y][x]: pre/tsdf_numba.py:70-72 */
+
+/* where the per-frame bounding box comes from */
+#define DTSDF_BBOX_PIXELS  0  /* min/max over all pixels with |d| >= 1, back-projected with
+                                 q=d/f, X=q*(x-cx), Y=-q*(y-cy), Z=-d: pre/tsdf_numba.py:75-116,140-141 */
+#define DTSDF_BBOX_EXTREMA 1  /* caller gives aux[i] = {max_x,max_y,max_z,min_x,min_y,min_z}, the
+                                 result of max_min_point(): pre/process.py:102-120, pre/tsdf_for.py:23-41 */
+#define DTSDF_BBOX_GRID    2  /* caller gives aux[i] = {vox_ori_x,y,z, voxel_len, trunc}: the arguments
+                                 of DataProcess.tsdf_cal(): pre/process.py:122 */
+
+typedef struct dtsdf_config {
+    int32_t voxel_res;   /* R: 32 (pre/process.py:88), 48 or 64 */
+    int32_t layout;      /* DTSDF_LAYOUT_* */
+    int32_t bbox_mode;   /* DTSDF_BBOX_* */
+    int32_t center_x;    /* 160: pre/process.py:133, pre/tsdf_numba.py:9 */
+    int32_t center_y;    /* 120: pre/process.py:134, pre/tsdf_numba.py:10 */
+    float   focal;       /* 241.42: pre/process.py:7, pre/tsdf_numba.py:8 */
+    float   trunc_mul;   /* 3: pre/process.py:95, pre/tsdf_numba.py:146 */
+} dtsdf_config;
+
+/* ---- library / diagnostics -------------------------------------------------- */
+int         dtsdf_abi_version(void);
+const char* dtsdf_error_string(int code);
+const char* dtsdf_last_cuda_error(void);          /* thread-local text of the last CUDA failure */
+void        dtsdf_default_config(dtsdf_config* cfg);  /* R=32, CXYZ, PIXELS, 160, 120, 241.42, 3 */
+int         dtsdf_device_count(void);             /* number of CUDA devices, 0 if none */
+/* number of CUDA kernels this library has launched in the calling process */
+int64_t     dtsdf_launch_count(void);
+
+/* ---- packing helpers (host, no CUDA) ---------------------------------------- */
+/* Computes 16-byte-aligned crop offsets for n_frames headers.  crop_offsets[i] is
+ * the start (in floats) of crop i; returns the total packed length in floats
+ * (a multiple of 4) in *packed_len and the largest crop (pixels) in *max_crop_px.
+ * Replaces nothing in the reference (which handles one .bin file at a time,
+ * pre/read_MSRA.py:98-103); it defines the batched input format. */
+int dtsdf_pack_plan(int32_t n_frames, const int32_t* headers,
+                    int64_t* crop_offsets, int64_t* packed_len, int32_t* max_crop_px);
+
+/* ---- device entry points (caller-owned device memory, asynchronous) ---------- */
+
+/* Fused per-frame pipeline, one launch for the whole batch:
+ *   bounding box (per cfg->bbox_mode) -> grid parameters -> per-voxel D-TSDF.
+ * Replaces tsdf_numba.cal_tsdf_cuda (pre/tsdf_numba.py:119-161: min_max_kernel
+ * :75-116, host reduce + grid parameters :140-147, tsdf_kernel :15-72) and the
+ * CPU loop DataProcess.tsdf_f/tsdf_cal (pre/process.py:86-100,122-200 ==
+ * pre/tsdf_for.py:6-20,44-122).
+ *   d_aux        NULL for DTSDF_BBOX_PIXELS, float[n][6] for EXTREMA, float[n][5] for GRID
+ *   max_crop_px  upper bound of bw*bh over the batch (a tuning hint for the shared
+ *                memory staging buffer; 0 = unknown; results never depend on it)
+ *   d_out_vol    float[n][3][R][R][R] in cfg->layout
+ *   d_out_max_l  float[n]     (may be NULL)   side of the voxel cube, pre/process.py:93
+ *   d_out_mid_p  float[n][3]  (may be NULL)   centre of the bounding box, pre/process.py:91
+ */
+int dtsdf_voxelize_batch(const dtsdf_config* cfg, int32_t n_frames,
+                         const float* d_depth_packed, const int64_t* d_crop_offsets,
+                         const int32_t* d_headers, const float* d_aux, int32_t max_crop_px,
+                         float* d_out_vol, float* d_out_max_l, float* d_out_mid_p,
+                         void* stream);
+
+/* Back-projection of every pixel with d != 0 to a float64 point, compacted in
+ * row-major order.  Replaces DataProcess.point_cloud (pre/process.py:30-68).
+ *   focal           the Python float 241.42 as a double (the reference divides float64
+ *                   values by it, pre/process.py:53,59), not the float32 of dtsdf_config
+ *   d_points        double[..][3]; frame i's points start at row d_point_offsets[i]
+ *                   and need room for bw*bh rows
+ *   d_n_valid       int32[n]: number of points written per frame
+ */
+int dtsdf_point_cloud_batch(int32_t n_frames, double focal,
+                            const float* d_depth_packed, const int64_t* d_crop_offsets,
+                            const int32_t* d_headers,
+                            double* d_points, const int64_t* d_point_offsets,
+                            int32_t* d_n_valid, void* stream);
+
+/* Gathers point_num rows per frame by index and reduces the per-axis extrema.
+ * Replaces the gather of DataProcess.set_length (pre/process.py:82; the index
+ * vector itself comes from the caller's np.random stream, :75-80) and
+ * max_min_point (pre/process.py:102-120).
+ *   d_indices      int32[n][point_num], each in [0, n_valid_i)
+ *   d_out_pc       double[n][point_num][3]  (may be NULL)
+ *   d_out_extrema  float[n][6] = {max_x,max_y,max_z,min_x,min_y,min_z}; z ignores exact zeros
+ */
+int dtsdf_resample_extrema_batch(int32_t n_frames, int32_t point_num,
+                                 const double* d_points, const int64_t* d_point_offsets,
+                                 const int32_t* d_indices,
+                                 double* d_out_pc, float* d_out_extrema, void* stream);
+
+/* Joint normalisation (gt - mid_p)/max_l + 0.5 over n frames of 21 joints.
+ * Replaces joint_nor.normalize (pre/joint_nor.py:8-18) and DataProcess.normalize
+ * (cut_version/pre/process.py:251-263).  clamp01 != 0 also clamps to [0,1] as the
+ * trainer does (3D_CNN/train.py:236-244). */
+int dtsdf_normalize_joints_batch(int32_t n_frames, const float* d_joints /*[n][63]*/,
+                                 const float* d_max_l, const float* d_mid_p,
+                                 int32_t clamp01, float* d_out /*[n][63]*/, void* stream);
+
+/* ---- host entry points (host memory in and out, synchronous) ----------------- */
+typedef struct dtsdf_ctx dtsdf_ctx;
+
+int  dtsdf_ctx_create(int32_t device, dtsdf_ctx** out);
+void dtsdf_ctx_destroy(dtsdf_ctx* ctx);
+
+/* Page-locked host buffers for the host entry points (plain malloc'ed memory
+ * works too, only slower). */
+int  dtsdf_host_alloc(void** ptr, int64_t bytes);
+void dtsdf_host_free(void* ptr);
+
+/* Same computation as dtsdf_voxelize_batch with HOST buffers: the batch is cut
+ * into chunks and host->device copy, kernel and device->host copy of successive
+ * chunks overlap on three streams.  This is the call the NumPy-facing shims
+ * (tsdf_numba.cal_tsdf_cuda, tsdf_for.tsdf_f, DataProcess.tsdf_f/tsdf_cal) make. */
+int dtsdf_voxelize_host(dtsdf_ctx* ctx, const dtsdf_config* cfg, int32_t n_frames,
+                        const float* h_depth_packed, int64_t packed_len,
+                        const int64_t* h_crop_offsets, const int32_t* h_headers,
+                        const float* h_aux,
+                        float* h_out_vol, float* h_out_max_l, float* h_out_mid_p);
+
+/* DataProcess.point_cloud for one frame (pre/process.py:30-68).  The compacted
+ * cloud also stays resident in the context for dtsdf_resample_extrema_host.
+ *   h_out_points  double[bw*bh][3] capacity (may be NULL to only count)
+ */
+int dtsdf_point_cloud_host(dtsdf_ctx* ctx, double focal, const int32_t* h_header,
+                           const float* h_depth, double* h_out_points, int32_t* n_valid);
+
+/* DataProcess.set_length gather + max_min_point on the cloud left in the context
+ * by the last dtsdf_point_cloud_host call, or on h_points when it is not NULL
+ * (tsdf_for.tsdf_f / DataProcess.tsdf_f are handed an arbitrary cloud).
+ *   h_indices      int32[point_num] or NULL (= identity, point_num rows of h_points)
+ */
+int dtsdf_resample_extrema_host(dtsdf_ctx* ctx, int32_t point_num,
+                                const double* h_points, int32_t n_points,
+                                const int32_t* h_indices,
+                                double* h_out_pc, float* h_out_extrema);
+
+int dtsdf_normalize_joints_host(dtsdf_ctx* ctx, int32_t n_frames, const float* h_joints,
+                                const float* h_max_l, const float* h_mid_p,
+                                int32_t clamp01, float* h_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTSDF_B200_H */

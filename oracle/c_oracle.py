@@ -1,0 +1,61 @@
+"""ctypes wrapper of the C oracle (oracle/dtsdf_oracle.c).  Test infrastructure only:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs, never by the product package."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(_HERE, "dtsdf_oracle.c")
+LIB = os.path.join(_HERE, "_build", "libdtsdf_oracle.so")
+
+_lib = None
+
+
+def build(force=False):
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    subprocess.run(["gcc", "-O2", "-std=c11", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC",
+                    "-shared", SRC, "-o", LIB, "-lm"], check=True)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        l = ctypes.CDLL(LIB)
+        vp, i32, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+        l.oracle_bbox_from_pixels.argtypes = [vp, vp, f32, i32, i32, vp, vp]
+        l.oracle_bbox_from_pixels.restype = None
+        l.oracle_grid_params.argtypes = [vp, vp, i32, f32, vp, vp, vp, vp, vp]
+        l.oracle_grid_params.restype = None
+        l.oracle_tsdf_cal.argtypes = [vp, vp, vp, f32, f32, i32, i32, f32, i32, i32, vp]
+        l.oracle_tsdf_cal.restype = None
+        l.oracle_dtsdf_batch.argtypes = [i32, vp, vp, vp, i32, i32, i32, vp, f32, f32, i32, i32, vp, vp, vp, i32]
+        l.oracle_dtsdf_batch.restype = i32
+        _lib = l
+    return _lib
+
+
+def dtsdf_batch(headers, offsets, packed, R=32, layout=0, bbox_mode=0, aux=None, trunc_mul=3.0,
+                focal=241.42, cx=160, cy=120, nthreads=0, out=None):
+    """Whole path on a packed batch.  Returns (vol, max_l, mid_p, threads_used)."""
+    headers = np.ascontiguousarray(headers, dtype=np.int32).reshape(-1, 6)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    packed = np.ascontiguousarray(packed, dtype=np.float32)
+    n = headers.shape[0]
+    vol = out if out is not None else np.empty((n, 3, R, R, R), dtype=np.float32)
+    max_l = np.zeros(n, dtype=np.float32)
+    mid_p = np.zeros((n, 3), dtype=np.float32)
+    aux_p = None
+    if aux is not None:
+        aux = np.ascontiguousarray(aux, dtype=np.float32)
+        aux_p = aux.ctypes.data
+    used = lib().oracle_dtsdf_batch(n, headers.ctypes.data, packed.ctypes.data, offsets.ctypes.data, R, layout,
+                                    bbox_mode, aux_p, trunc_mul, focal, cx, cy, vol.ctypes.data,
+                                    max_l.ctypes.data, mid_p.ctypes.data, nthreads)
+    return vol, max_l, mid_p, used

@@ -1,0 +1,258 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the golden vectors
+of the unmodified reference.  Run on the B200 box: python -m pytest tests -m gpu.
+
+Bar: bounding box, grid parameters, voxel/pixel indexing, truncation and sign decisions and
+the TSDF values themselves are all BIT-EXACT against the f32 step-wise oracle (tolerance 0,
+sign of zero included)."""
+import numpy as np
+import pytest
+
+from helpers import import_pre, pack_simple, pkg, synth
+from oracle import c_oracle
+from oracle import dtsdf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vox():
+    return pkg.Voxelizer(device=0)
+
+
+def _same(a, b):
+    return np.array_equal(a, b) and np.array_equal(np.signbit(a), np.signbit(b))
+
+
+def test_library_loaded_and_device_present():
+    assert pkg.capi.device_count() >= 1
+    assert pkg.capi.load_library().dtsdf_abi_version() == 1
+
+
+# ----------------------------------------------------------------------------- golden vectors
+def test_extrema_mode_matches_reference_for_loop(vox, forloop_golden):
+    # tsdf_for.tsdf_f / DataProcess.tsdf_f: pre/tsdf_for.py:6-20,44-122
+    frames = [{"header": c["header"], "depth": c["depth"]} for c in forloop_golden]
+    aux = np.stack([np.concatenate([c["pmax"], c["pmin"]]) for c in forloop_golden]).astype(np.float32)
+    vol, max_l, mid_p = vox.voxelize_frames(frames, layout=pkg.LAYOUT_CXYZ, bbox_mode=pkg.BBOX_EXTREMA, aux=aux)
+    for i, c in enumerate(forloop_golden):
+        assert _same(vol[i], c["tsdf"]), "case %d" % i
+        assert max_l[i] == c["max_l"] and np.array_equal(mid_p[i], c["mid_p"])
+
+
+def test_pixels_mode_matches_reference_numba_kernels(vox, numba_golden):
+    # min_max_kernel + tsdf_kernel: pre/tsdf_numba.py:15-116,140-147, layout (c,z,y,x)
+    frames = [{"header": c["header"], "data": c["depth"]} for c in numba_golden]
+    vol, max_l, mid_p = vox.voxelize_frames(frames, layout=pkg.LAYOUT_CZYX, bbox_mode=pkg.BBOX_PIXELS)
+    for i, c in enumerate(numba_golden):
+        assert max_l[i] == c["max_l"] and np.array_equal(mid_p[i], c["mid_p"])
+    assert _same(vol[0], numba_golden[0]["tsdf"])
+
+
+def test_grid_mode_matches_reference_tsdf_cal(vox, forloop_golden):
+    # DataProcess.tsdf_cal(vox_ori, voxel_len, trunc): pre/process.py:122-200
+    c = forloop_golden[1]
+    vox_ori, voxel_len, trunc, _, _ = orc.grid_params(c["pmax"], c["pmin"])
+    aux = np.array([[vox_ori[0], vox_ori[1], vox_ori[2], voxel_len, trunc]], dtype=np.float32)
+    vol, _, _ = vox.voxelize_frames([{"header": c["header"], "depth": c["depth"]}],
+                                    bbox_mode=pkg.BBOX_GRID, aux=aux)
+    assert _same(vol[0], c["tsdf"])
+
+
+# ----------------------------------------------------------------------------- drop-in modules
+def test_dataprocess_process_matches_reference(forloop_golden):
+    # DataProcess(...).process(): pre/process.py:13-28 with the golden run's np.random seed
+    process = import_pre("process")
+    for c in forloop_golden:
+        frame = {"header": c["header"], "depth": c["depth"]}
+        np.random.seed(int(c["np_random_seed"]))
+        out = process.DataProcess(frame, np.zeros(63, np.float32), int(c["point_num"]), aug=False).process()
+        assert len(out) == 4
+        pc, tsdf, max_l, mid_p = out
+        assert pc.dtype == np.float64 and pc.shape == (int(c["point_num"]), 3)
+        assert np.array_equal(pc[:64], c["pc_head"])
+        if "pc" in c:
+            assert np.array_equal(pc, c["pc"])
+        assert tsdf.shape == (3, 32, 32, 32) and _same(tsdf, c["tsdf"])
+        assert max_l == c["max_l"] and np.array_equal(mid_p, c["mid_p"])
+
+
+def test_dataprocess_methods(forloop_golden):
+    process = import_pre("process")
+    c = forloop_golden[0]
+    frame = {"header": c["header"], "depth": c["depth"]}
+    dp = process.DataProcess(frame, None, 6000)
+    pts = dp.point_cloud()                                    # pre/process.py:30-68
+    assert pts.dtype == np.float64 and pts.shape == (int(c["n_valid"]), 3)
+    assert np.array_equal(pts[:64], c["pc_all_head"])
+    assert np.array_equal(pts, orc.point_cloud(c["header"], c["depth"]))
+    pmax, pmin = dp.max_min_point(c["pc"])                    # pre/process.py:102-120
+    assert pmax.dtype == np.float32
+    assert np.array_equal(pmax, c["pmax"]) and np.array_equal(pmin, c["pmin"])
+    tsdf, max_l, mid_p = dp.tsdf_f(c["pc"])                   # pre/process.py:86-100
+    assert _same(tsdf, c["tsdf"]) and max_l == c["max_l"]
+    vox_ori, voxel_len, trunc, _, _ = orc.grid_params(c["pmax"], c["pmin"])
+    assert _same(dp.tsdf_cal(vox_ori, voxel_len, trunc), c["tsdf"])   # pre/process.py:122
+    # cut_version signature and aliases (cut_version/pre/process.py:6,52)
+    np.random.seed(int(c["np_random_seed"]))
+    pc = process.DataProcess(frame, 6000, False).get_points()
+    assert np.array_equal(pc, c["pc"])
+    with pytest.raises(NotImplementedError):
+        process.DataProcess(frame, None, 6000, aug=True).process()
+
+
+def test_tsdf_for_module(forloop_golden):
+    tsdf_for = import_pre("tsdf_for")
+    c = forloop_golden[3]
+    frame = {"header": c["header"], "depth": c["depth"]}
+    tsdf, max_l, mid_p = tsdf_for.tsdf_f(frame, c["pc"])      # pre/tsdf_for.py:6-20
+    assert _same(tsdf, c["tsdf"]) and max_l == c["max_l"] and np.array_equal(mid_p, c["mid_p"])
+    pmax, pmin = tsdf_for.max_min_point(c["pc"])
+    assert np.array_equal(pmax, c["pmax"]) and np.array_equal(pmin, c["pmin"])
+
+
+def test_tsdf_numba_module(numba_golden):
+    tsdf_numba = import_pre("tsdf_numba")
+    assert (tsdf_numba.FOCAL, tsdf_numba.CENTER_X, tsdf_numba.CENTER_Y, tsdf_numba.VOXEL_RES) == (241.42, 160, 120, 32)
+    c = numba_golden[0]
+    tsdf, max_l, mid_p = tsdf_numba.cal_tsdf_cuda({"header": c["header"], "data": c["depth"]})
+    assert tsdf.dtype == np.float32 and _same(tsdf, c["tsdf"])
+    assert max_l == c["max_l"] and np.array_equal(mid_p, c["mid_p"])
+    # error convention: None (after printing) when there is no valid pixel, pre/tsdf_numba.py:162-171
+    empty = {"header": c["header"], "data": np.zeros_like(c["depth"])}
+    assert tsdf_numba.cal_tsdf_cuda(empty) is None
+    # anything else propagates as an exception
+    with pytest.raises(KeyError):
+        tsdf_numba.cal_tsdf_cuda({"header": c["header"], "depth": c["depth"]})
+
+
+# ----------------------------------------------------------------------------- oracle sweeps
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("R", [32, 48, 64])
+def test_ragged_batch_matches_oracle(vox, R, layout):
+    frames = synth.make_frames(range(200, 232))
+    vol, max_l, mid_p = vox.voxelize_frames(frames, layout=layout, voxel_res=R)
+    for i, fr in enumerate(frames[:8]):                       # NumPy oracle on a few
+        v, ml, mp = orc.dtsdf_from_pixels(fr, R=R, layout=layout)
+        assert _same(vol[i], v) and max_l[i] == ml and np.array_equal(mid_p[i], mp)
+    headers, offsets, packed = pack_simple(frames)            # C oracle on all
+    cv, cml, cmp_, _ = c_oracle.dtsdf_batch(headers, offsets, packed, R=R, layout=layout)
+    assert _same(vol, cv) and np.array_equal(max_l, cml) and np.array_equal(mid_p, cmp_)
+
+
+def test_batch_larger_than_grid(vox):
+    # more frames than resident CTAs: every CTA loops over several frames
+    frames = synth.make_frames(range(1000, 1000 + 1500))
+    headers, offsets, packed = pack_simple(frames)
+    vol, max_l, mid_p = vox.voxelize_packed(headers, offsets, packed)
+    cv, cml, cmp_, _ = c_oracle.dtsdf_batch(headers, offsets, packed)
+    assert _same(vol, cv) and np.array_equal(max_l, cml) and np.array_equal(mid_p, cmp_)
+
+
+def test_edge_crops(vox):
+    frames = [
+        synth.make_frame(1, box=(0, 0, 320, 240)),             # full image: larger than shared memory, direct path
+        synth.make_frame(2, box=(40, 20, 260, 230)),           # 220x210 = 185 KB: staged, one CTA per SM
+        synth.make_frame(3, box=(159, 119, 160, 120)),         # 1x1 crop
+        synth.make_frame(4, box=(100, 100, 103, 101)),         # 3x1 crop (padded to 4 floats)
+        synth.make_frame(5, box=(10, 10, 11, 200)),            # 1 px wide
+        synth.make_frame(6, box=(0, 0, 96, 80)),               # touching the image corner
+    ]
+    z = synth.make_frame(7)
+    z["depth"] = np.zeros_like(z["depth"])                     # no valid pixel at all
+    frames.append(z)
+    s = synth.make_frame(8)
+    s["depth"] = np.where(s["depth"] > 0, np.float32(0.5), np.float32(0))   # |d| < 1 everywhere
+    frames.append(s)
+    n = synth.make_frame(9)
+    n["depth"] = -n["depth"]                                   # negative depths are valid (abs() test)
+    frames.append(n)
+    headers, offsets, packed = pack_simple(frames)
+    for layout in (0, 1):
+        vol, max_l, mid_p = vox.voxelize_packed(headers, offsets, packed, layout=layout)
+        cv, cml, cmp_, _ = c_oracle.dtsdf_batch(headers, offsets, packed, layout=layout)
+        for i in range(len(frames)):
+            assert _same(vol[i], cv[i]), "frame %d layout %d" % (i, layout)
+        assert np.array_equal(max_l, cml) and np.array_equal(mid_p, cmp_)
+
+
+def test_empty_batch_and_bad_arguments(vox):
+    vol, max_l, mid_p = vox.voxelize_frames([])
+    assert vol.shape == (0, 3, 32, 32, 32) and max_l.shape == (0,)
+    fr = synth.make_frame(0)
+    with pytest.raises(pkg.DtsdfError) as e:
+        vox.voxelize_frames([fr], voxel_res=40)
+    assert e.value.code == pkg.capi.ERR_UNSUPPORTED
+    bad = {"header": np.array([320, 240, 100, 60, 100, 190], np.int32), "depth": np.zeros(0, np.float32)}
+    with pytest.raises(pkg.DtsdfError) as e:
+        vox.voxelize_frames([bad])
+    assert e.value.code == pkg.capi.ERR_BAD_HEADER
+    with pytest.raises(ValueError):
+        vox.voxelize_frames([{"header": fr["header"], "depth": fr["depth"][:-1]}])
+
+
+# ----------------------------------------------------------------------------- device-resident path
+def test_device_entry_point_matches_host_entry_point(vox):
+    import torch
+    frames = synth.make_frames(range(300, 340))
+    headers, offsets, packed, max_px = pkg.pack_frames(frames)
+    hv, hml, hmp = vox.voxelize_packed(headers, offsets, packed)
+    dev = torch.device("cuda:0")
+    d_vol, d_ml, d_mp = pkg.voxelize_device(torch.from_numpy(packed).to(dev), torch.from_numpy(offsets).to(dev),
+                                            torch.from_numpy(headers).to(dev), max_px)
+    torch.cuda.synchronize()
+    assert _same(d_vol.cpu().numpy(), hv)
+    assert np.array_equal(d_ml.cpu().numpy(), hml) and np.array_equal(d_mp.cpu().numpy(), hmp)
+    # the staging hint never changes results (0 = unknown, or too small -> direct path)
+    for hint in (0, 16):
+        v2, _, _ = pkg.voxelize_device(torch.from_numpy(packed).to(dev), torch.from_numpy(offsets).to(dev),
+                                       torch.from_numpy(headers).to(dev), hint)
+        torch.cuda.synchronize()
+        assert _same(v2.cpu().numpy(), hv)
+
+
+def test_full_size_batch_properties():
+    """BASELINE.json configs[1] size (8,500 frames): size-independent properties."""
+    import torch
+    n = 8500
+    headers, depth = synth.make_uniform_batch(n, seed0=7)
+    dev = torch.device("cuda:0")
+    offsets, packed_len, max_px = pkg.capi.pack_plan(headers)
+    assert packed_len == depth.size
+    d_depth = torch.from_numpy(depth.reshape(-1)).to(dev)
+    d_off = torch.from_numpy(offsets).to(dev)
+    d_hdr = torch.from_numpy(headers).to(dev)
+    cfg0 = pkg.capi.default_config(layout=pkg.LAYOUT_CXYZ)
+    cfg1 = pkg.capi.default_config(layout=pkg.LAYOUT_CZYX)
+    v0, ml0, mp0 = pkg.voxelize_device(d_depth, d_off, d_hdr, max_px, cfg0)
+    v0b, _, _ = pkg.voxelize_device(d_depth, d_off, d_hdr, max_px, cfg0)
+    v1, ml1, mp1 = pkg.voxelize_device(d_depth, d_off, d_hdr, max_px, cfg1)
+    torch.cuda.synchronize()
+    assert torch.equal(v0, v0b)                                    # deterministic / idempotent
+    assert torch.equal(v0, v1.permute(0, 1, 4, 3, 2))              # the two layouts are transposes
+    assert torch.equal(ml0, ml1) and torch.equal(mp0, mp1)
+    assert float(v0.abs().max()) <= 1.0 and not bool(torch.isnan(v0).any())
+    # a spot sample against the C oracle
+    pick = np.arange(0, n, 271)
+    cv, cml, _, _ = c_oracle.dtsdf_batch(headers[pick], offsets[: pick.size], depth[pick].reshape(-1))
+    assert _same(v0[torch.from_numpy(pick).to(dev)].cpu().numpy(), cv)
+    assert np.array_equal(ml0.cpu().numpy()[pick], cml)
+    # a frame's volume does not depend on its neighbours: permuting frames permutes volumes
+    perm = np.random.default_rng(0).permutation(n)
+    vp, _, _ = pkg.voxelize_device(torch.from_numpy(depth[perm].reshape(-1)).to(dev), d_off, d_hdr, max_px, cfg0)
+    torch.cuda.synchronize()
+    assert torch.equal(vp, v0[torch.from_numpy(perm).to(dev)])
+
+
+def test_normalize_joints(vox):
+    # (gt - mid_p)/max_l + 0.5: pre/joint_nor.py:8-18 (float64 there, float32 here: 1e-6)
+    rng = np.random.default_rng(3)
+    gt = rng.uniform(-150, 150, size=(50, 63)).astype(np.float32)
+    max_l = rng.uniform(100, 250, size=50).astype(np.float32)
+    mid_p = rng.uniform(-50, 50, size=(50, 3)).astype(np.float32)
+    out = vox.normalize_joints(gt, max_l, mid_p)
+    ref = orc.normalize_joints(gt, max_l, mid_p)
+    assert np.max(np.abs(out - ref)) <= 1e-6
+    f32 = (gt.reshape(50, 21, 3) - mid_p[:, None, :]) / max_l[:, None, None] + np.float32(0.5)
+    assert np.array_equal(out, f32.reshape(50, 63))
+    clamped = vox.normalize_joints(gt, max_l, mid_p, clamp01=True)   # 3D_CNN/train.py:241-242
+    assert np.array_equal(clamped, np.clip(f32.reshape(50, 63), 0, 1))

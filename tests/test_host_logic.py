@@ -1,0 +1,154 @@
+"""Host-side logic that needs no GPU: the library loads and exports the whole C ABI, argument
+checking, packing, frame sharding (incl. a world_size-2 gloo run) and the synthetic generator."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as graft
+from helpers import pack_simple, pkg, synth
+
+
+def test_library_exports_every_symbol_in_header():
+    graft.build_cuda()
+    lib = pkg.capi.load_library()
+    names = graft.header_symbols()
+    assert len(names) >= 19
+    for s in names:
+        assert hasattr(lib, s), s
+    assert set(names) == set(pkg.capi._SIGNATURES)          # the ctypes table covers the whole ABI
+    assert lib.dtsdf_abi_version() == 1
+    assert lib.dtsdf_error_string(-4).decode().startswith("no usable CUDA device")
+
+
+def test_default_config_matches_reference_constants():
+    cfg = pkg.capi.default_config()
+    assert (cfg.voxel_res, cfg.layout, cfg.bbox_mode) == (32, 0, 0)          # pre/process.py:88
+    assert (cfg.center_x, cfg.center_y) == (160, 120)                        # pre/tsdf_numba.py:9-10
+    assert cfg.focal == np.float32(241.42) and cfg.trunc_mul == 3.0          # :8, :146
+
+
+def test_argument_checks_need_no_device():
+    lib = pkg.capi.load_library()
+    cfg = pkg.capi.default_config()
+    assert lib.dtsdf_voxelize_batch(None, 1, None, None, None, None, 0, None, None, None, None) == pkg.capi.ERR_INVALID_ARG
+    cfg.voxel_res = 40
+    assert lib.dtsdf_voxelize_batch(ctypes.byref(cfg), 1, 8, 8, 8, None, 0, 8, None, None, None) == pkg.capi.ERR_UNSUPPORTED
+    cfg.voxel_res = 32
+    assert lib.dtsdf_voxelize_batch(ctypes.byref(cfg), 0, None, None, None, None, 0, None, None, None, None) == 0
+    assert lib.dtsdf_voxelize_batch(ctypes.byref(cfg), -1, 8, 8, 8, None, 0, 8, None, None, None) == pkg.capi.ERR_INVALID_ARG
+    cfg.bbox_mode = pkg.BBOX_EXTREMA       # aux is required
+    assert lib.dtsdf_voxelize_batch(ctypes.byref(cfg), 1, 8, 8, 8, None, 0, 8, None, None, None) == pkg.capi.ERR_INVALID_ARG
+
+
+def test_no_cpu_fallback_without_device():
+    if pkg.capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pkg.DtsdfError) as e:
+        pkg.Voxelizer(device=0)
+    assert e.value.code in (pkg.capi.ERR_NO_DEVICE, pkg.capi.ERR_CUDA)
+    if graft.PKG_DIR + "/pre" not in sys.path:
+        sys.path.insert(0, os.path.join(graft.PKG_DIR, "pre"))
+    import tsdf_numba
+    fr = synth.make_frame(0, key="data")
+    with pytest.raises(pkg.DtsdfError):
+        tsdf_numba.cal_tsdf_cuda(fr)
+
+
+def test_pack_plan_and_pack_frames():
+    frames = synth.make_frames(range(5)) + [synth.make_frame(9, box=(10, 10, 13, 11))]
+    headers, offsets, packed, max_px = pkg.pack_frames(frames)
+    h2, o2, p2 = pack_simple(frames)
+    assert np.array_equal(headers, h2) and np.array_equal(offsets, o2) and np.array_equal(packed, p2)
+    assert np.all(offsets % 4 == 0)
+    assert max_px == max(f["depth"].size for f in frames)
+    with pytest.raises(pkg.DtsdfError) as e:
+        pkg.capi.pack_plan(np.array([[320, 240, 10, 10, 10, 20]], np.int32))
+    assert e.value.code == pkg.capi.ERR_BAD_HEADER
+    with pytest.raises(ValueError):
+        pkg.pack_frames([{"header": frames[0]["header"], "depth": frames[0]["depth"][:-3]}])
+    o, total, mx = pkg.capi.pack_plan(np.zeros((0, 6), np.int32))
+    assert o.size == 0 and total == 0 and mx == 0
+
+
+def test_shard_range_partitions_frames():
+    for n in (0, 1, 7, 8, 8500, 76375):
+        for w in (1, 2, 4, 8):
+            parts = [pkg.shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_packed_rebases_offsets():
+    frames = synth.make_frames(range(11))
+    headers, offsets, packed, _ = pkg.pack_frames(frames)
+    seen = 0
+    for r in range(3):
+        h, o, p = pkg.shard_packed(headers, offsets, packed, r, 3)
+        assert o.size == h.shape[0] and (o.size == 0 or o[0] == 0)
+        for i in range(h.shape[0]):
+            n = frames[seen]["depth"].size
+            assert np.array_equal(p[o[i]:o[i] + n], frames[seen]["depth"])
+            seen += 1
+    assert seen == 11
+
+
+def test_synthetic_frames_are_deterministic_and_msra_shaped():
+    a, b = synth.make_frame(5), synth.make_frame(5)
+    assert np.array_equal(a["header"], b["header"]) and np.array_equal(a["depth"], b["depth"])
+    h = a["header"]
+    assert h.dtype == np.int32 and h[0] == 320 and h[1] == 240
+    assert a["depth"].dtype == np.float32 and a["depth"].size == (h[4] - h[2]) * (h[5] - h[3])
+    d = synth.make_frame(0, box=synth.DEFAULT_BOX)["depth"]
+    assert d.size == 15600 and 8000 < np.count_nonzero(d) < 9500
+    hdr, dep = synth.make_uniform_batch(10, seed0=1)
+    assert hdr.shape == (10, 6) and dep.shape == (10, 15600) and dep.dtype == np.float32
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch
+    from oracle import c_oracle
+    frames = synth.make_frames(range(40, 49))
+    headers, offsets, packed, _ = pkg.pack_frames(frames)
+    h, o, p = pkg.shard_packed(headers, offsets, packed, rank, world)
+    # the per-rank work of the sharded job, computed by the oracle here (no GPU in this test)
+    vol, max_l, _, _ = c_oracle.dtsdf_batch(h, o, p, nthreads=1)
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([h.shape[0]], dtype=torch.int64))
+    sizes = [int(c) for c in counts]
+    pad = max(sizes)
+    mine = torch.zeros((pad,) + vol.shape[1:])
+    mine[: vol.shape[0]] = torch.from_numpy(vol)
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    if rank == 0:
+        full = torch.cat([g[:s] for g, s in zip(gathered, sizes)]).numpy()
+        ref, _, _, _ = c_oracle.dtsdf_batch(headers, offsets, packed, nthreads=1)
+        q.put(bool(np.array_equal(full, ref)) and sum(sizes) == 9)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_gather_gloo():
+    """world_size 2 over gloo: contiguous shards, rebased offsets, all-gather of the volumes to
+    every rank reproduces the single-process result."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok

@@ -1,0 +1,50 @@
+"""The C oracle (oracle/dtsdf_oracle.c, also the CPU baseline of bench.py) against the golden
+vectors of the unmodified reference and against the NumPy oracle.  Bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from oracle import dtsdf_oracle as orc
+from helpers import pack_simple, synth
+
+
+def test_c_oracle_matches_for_loop_golden(forloop_golden):
+    frames = [{"header": c["header"], "depth": c["depth"]} for c in forloop_golden]
+    headers, offsets, packed = pack_simple(frames)
+    aux = np.stack([np.concatenate([c["pmax"], c["pmin"]]) for c in forloop_golden]).astype(np.float32)
+    vol, max_l, mid_p, _ = c_oracle.dtsdf_batch(headers, offsets, packed, bbox_mode=1, aux=aux, layout=0)
+    for i, c in enumerate(forloop_golden):
+        assert np.array_equal(vol[i], c["tsdf"])
+        assert np.array_equal(np.signbit(vol[i]), np.signbit(c["tsdf"]))
+        assert max_l[i] == c["max_l"] and np.array_equal(mid_p[i], c["mid_p"])
+
+
+def test_c_oracle_matches_numba_golden(numba_golden):
+    frames = [{"header": c["header"], "depth": c["depth"]} for c in numba_golden]
+    headers, offsets, packed = pack_simple(frames)
+    vol, max_l, mid_p, _ = c_oracle.dtsdf_batch(headers, offsets, packed, bbox_mode=0, layout=1)
+    for i, c in enumerate(numba_golden):
+        assert max_l[i] == c["max_l"] and np.array_equal(mid_p[i], c["mid_p"])
+    assert np.array_equal(vol[0], numba_golden[0]["tsdf"])
+
+
+@pytest.mark.parametrize("R", [32, 48, 64])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_c_oracle_matches_numpy_oracle(R, layout):
+    frames = synth.make_frames(range(20, 26))
+    headers, offsets, packed = pack_simple(frames)
+    vol, max_l, mid_p, _ = c_oracle.dtsdf_batch(headers, offsets, packed, R=R, layout=layout, nthreads=2)
+    for i, fr in enumerate(frames):
+        v, ml, mp = orc.dtsdf_from_pixels(fr, R=R, layout=layout)
+        assert np.array_equal(vol[i], v)
+        assert np.array_equal(np.signbit(vol[i]), np.signbit(v))
+        assert max_l[i] == ml and np.array_equal(mid_p[i], mp)
+
+
+def test_c_oracle_grid_mode(forloop_golden):
+    c = forloop_golden[0]
+    vox_ori, voxel_len, trunc, _, _ = orc.grid_params(c["pmax"], c["pmin"])
+    headers, offsets, packed = pack_simple([{"header": c["header"], "depth": c["depth"]}])
+    aux = np.array([[vox_ori[0], vox_ori[1], vox_ori[2], voxel_len, trunc]], dtype=np.float32)
+    vol, _, _, _ = c_oracle.dtsdf_batch(headers, offsets, packed, bbox_mode=2, aux=aux)
+    assert np.array_equal(vol[0], c["tsdf"])
