@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""Benchmark of the depth-crop -> D-TSDF hot path (BASELINE.json: D-TSDF volumes/s, 32^3 x 3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU reference arm (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W      # N > 1, one rank per GPU
+
+A "step" is one pass of the fused voxeliser over one batch of synthetic MSRA-shaped frames
+(BASELINE.json configs[1]: 8,500 frames of 120x130 px per GPU, R = 32).  Frames shard across
+ranks with no data-path collective (weak scaling: every rank voxelises its own 8,500 frames).
+
+Printed JSON (one line, rank 0):
+  value      volumes/s over all ranks, inputs resident in HBM, K launches timed with CUDA events
+             on the launching stream, max over ranks
+  e2e        the same metric through the host entry point of the C ABI (dtsdf_voxelize_host):
+             pinned HOST buffers in and out, H2D + kernel + D2H inside the timed region
+  roofline   HBM roofline of the fused kernel: algorithmic bytes per launch / measured launch time
+             against MEASURED_PEAKS.json
+  cpu_baseline  the C oracle port of the reference loop on the host cores (N = 1, rank 0 only)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "dtsdf_volumes_per_sec"
+UNIT = "volumes/s"
+FRAMES_PER_GPU = 8500          # BASELINE.json configs[1]
+BOX = (100, 60, 220, 190)      # 120 x 130 crop, BASELINE.md section 3
+
+
+def algorithmic_bytes(headers, R):
+    """24 (header) + 4*bw*bh (crop read once) + 12*R^3 (volume) + 16 (max_l, mid_p)."""
+    bw = (headers[:, 4] - headers[:, 2]).astype(np.int64)
+    bh = (headers[:, 5] - headers[:, 3]).astype(np.int64)
+    return int(np.sum(24 + 4 * bw * bh + 12 * R ** 3 + 16))
+
+
+def workload_config(args, world):
+    return {
+        "workload": "configs[1]: %d synthetic MSRA-shaped frames per GPU, crop %dx%d, R=%d -> 3x%d^3 f32"
+                    % (args.frames, BOX[2] - BOX[0], BOX[3] - BOX[1], args.res, args.res),
+        "frames_per_gpu": args.frames,
+        "frames_total": args.frames * world,
+        "voxel_res": args.res,
+        "layout": "cxyz" if args.layout == 0 else "czyx",
+        "bbox": "valid pixels (tsdf_numba.cal_tsdf_cuda semantics)",
+        "sharding": "frames, contiguous per rank, no data-path collective",
+        "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush"
+              % ((args.frames * (15600 * 4 + 12 * args.res ** 3)) / 1e9),
+    }
+
+
+class ClockSampler:
+    """Polls NVML for SM clock and throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        names = {
+            "nvmlClocksEventReasonSwPowerCap": "sw_power_cap",
+            "nvmlClocksThrottleReasonSwPowerCap": "sw_power_cap",
+            "nvmlClocksThrottleReasonHwSlowdown": "hw_slowdown",
+            "nvmlClocksThrottleReasonHwThermalSlowdown": "hw_thermal_slowdown",
+            "nvmlClocksThrottleReasonSwThermalSlowdown": "sw_thermal_slowdown",
+            "nvmlClocksThrottleReasonHwPowerBrakeSlowdown": "hw_power_brake",
+        }
+        masks = {getattr(nv, k): v for k, v in names.items() if hasattr(nv, k)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for m, name in masks.items():
+                    if r & m:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        self._stop = threading.Event()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(res, layout):
+    """dram bytes per launch of the fused kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        d = json.load(open(p))
+        return d.get("R%d_L%d" % (res, layout), {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm: the C oracle port of the reference's loop, all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_port_rate(headers, offsets, packed, R, layout, seconds, nthreads=0):
+    """Times oracle_dtsdf_batch on a bounded sample sized for about `seconds` of work."""
+    from oracle import c_oracle
+    n = headers.shape[0]
+    probe = min(n, 64)
+    px = int(offsets[probe]) if probe < n else packed.size
+    t0 = time.perf_counter()
+    _, _, _, used = c_oracle.dtsdf_batch(headers[:probe], offsets[:probe], packed[:px], R=R, layout=layout,
+                                         nthreads=nthreads)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    sample = int(min(n, max(probe, seconds * probe / dt)))
+    px = int(offsets[sample]) if sample < n else packed.size
+    out = np.empty((sample, 3, R, R, R), dtype=np.float32)
+    t0 = time.perf_counter()
+    c_oracle.dtsdf_batch(headers[:sample], offsets[:sample], packed[:px], R=R, layout=layout, nthreads=nthreads,
+                         out=out)
+    dt = time.perf_counter() - t0
+    return sample / dt, used, sample, dt
+
+
+def python_loop_rate(headers, offsets, packed, R):
+    """The reference's own form of the loop (interpreted Python over 32^3 voxels), one frame."""
+    from oracle import dtsdf_oracle as orc
+    h = headers[0]
+    n = int(h[4] - h[2]) * int(h[5] - h[3])
+    depth = packed[int(offsets[0]):int(offsets[0]) + n]
+    t0 = time.perf_counter()
+    pmin, pmax = orc.bbox_from_pixels(h, depth)
+    vox_ori, voxel_len, trunc, _, _ = orc.grid_params(pmax, pmin, R)
+    orc.tsdf_cal_loop(h, depth, vox_ori, voxel_len, trunc, R)
+    return 1.0 / (time.perf_counter() - t0)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from __graft_entry__ import build_oracle, load_package
+    build_oracle()
+    pkg = load_package()
+    headers, depth = pkg.synth.make_uniform_batch(min(args.frames, 4096), seed0=0, box=BOX)
+    offsets = (np.arange(headers.shape[0], dtype=np.int64) * depth.shape[1])
+    packed = depth.reshape(-1)
+    from oracle import c_oracle
+    # size one step for ~0.25 s
+    rate, used, _, _ = cpu_port_rate(headers, offsets, packed, args.res, args.layout, 0.5)
+    per_step = int(max(32, min(headers.shape[0], rate * 0.25)))
+    px = int(offsets[per_step]) if per_step < headers.shape[0] else packed.size
+    out = np.empty((per_step, 3, args.res, args.res, args.res), dtype=np.float32)
+
+    def step():
+        c_oracle.dtsdf_batch(headers[:per_step], offsets[:per_step], packed[:px], R=args.res,
+                             layout=args.layout, out=out)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, world),
+        "cpu_baseline": {
+            "value": value, "unit": UNIT, "cores": used, "kind": "port",
+            "sample": "%d frames per step x %d steps of the same workload; C restatement of the reference's "
+                      "Python voxel loop (oracle/dtsdf_oracle.c, gcc -O2, OpenMP over frames, %d threads); "
+                      "the reference itself is interpreted Python and cannot travel to this box"
+                      % (per_step, args.steps, used),
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import build_cuda, load_package
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the D-TSDF path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    build_cuda()
+    pkg = load_package()
+    capi = pkg.capi
+    R, F = args.res, args.frames
+
+    # ---- workload: F fixed-shape synthetic frames per rank, in pinned host memory
+    headers, depth = pkg.synth.make_uniform_batch(F, seed0=1234 + 7919 * rank, box=BOX)
+    offsets, packed_len, max_px = capi.pack_plan(headers)
+    assert packed_len == depth.size
+    h_packed = capi.PinnedBuffer(packed_len, np.float32)
+    h_packed.array[:] = depth.reshape(-1)
+    del depth
+    h_vol = capi.PinnedBuffer((F, 3, R, R, R), np.float32)
+    h_maxl = capi.PinnedBuffer(F, np.float32)
+    h_mid = capi.PinnedBuffer((F, 3), np.float32)
+    alg_bytes = algorithmic_bytes(headers, R)
+
+    d_packed = torch.from_numpy(h_packed.array).to(dev)
+    d_off = torch.from_numpy(offsets).to(dev)
+    d_hdr = torch.from_numpy(headers).to(dev)
+    d_vol = torch.empty((F, 3, R, R, R), dtype=torch.float32, device=dev)
+    d_maxl = torch.empty((F,), dtype=torch.float32, device=dev)
+    d_mid = torch.empty((F, 3), dtype=torch.float32, device=dev)
+    cfg = capi.default_config(R, args.layout, pkg.BBOX_PIXELS)
+
+    def step():
+        pkg.voxelize_device(d_packed, d_off, d_hdr, max_px, cfg, out_vol=d_vol, out_max_l=d_maxl,
+                            out_mid_p=d_mid)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+
+    # ---- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    launches = capi.launch_count() - launches0
+    local_ms = e0.elapsed_time(e1)
+    barrier()
+    ms = max_over_ranks(local_ms)
+    value = F * world * args.steps / (ms * 1e-3)
+
+    # ---- optional gather of the volumes to rank 0 (BASELINE.json configs[2])
+    gather = None
+    if args.gather and world > 1:
+        bufs = [torch.empty_like(d_vol) for _ in range(world)] if rank == 0 else None
+        dist.gather(d_vol, bufs, dst=0)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        step()
+        dist.gather(d_vol, bufs, dst=0)
+        g1.record()
+        torch.cuda.synchronize()
+        gms = max_over_ranks(g0.elapsed_time(g1))
+        gather = {"value": F * world / (gms * 1e-3), "unit": UNIT, "ms": gms,
+                  "bytes_to_rank0": int((world - 1) * d_vol.numel() * 4)}
+        del bufs
+
+    # ---- end to end through the host entry point (pinned host buffers, H2D + kernel + D2H)
+    vox = pkg.Voxelizer(device=local_rank, voxel_res=R)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def e2e_step():
+        vox.voxelize_packed(headers, offsets, h_packed.array, layout=args.layout, bbox_mode=pkg.BBOX_PIXELS,
+                            out_vol=h_vol.array, out_max_l=h_maxl.array, out_mid_p=h_mid.array)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    with sampler:
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = F * world * e2e_steps / e2e_s
+    # the e2e result is the real thing: compare with the device-resident run
+    ok = bool(np.array_equal(h_vol.array[:64], d_vol[:64].cpu().numpy()))
+    h2d = int(h_packed.array.nbytes + headers.nbytes + offsets.nbytes)
+    d2h = int(h_vol.array.nbytes + h_maxl.array.nbytes + h_mid.array.nbytes)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kernel_s = (local_ms * 1e-3) / args.steps
+        achieved = alg_bytes / kernel_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "dtsdf_voxelize_host (C ABI, pinned host buffers)",
+                    "matches_device_run": ok},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(R, args.layout),
+                         "peak_source": peak_src, "kernel": "dtsdf_fused_kernel<%d,%d>" % (R, args.layout),
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kernel_s * 1e3},
+            "clocks": sampler.summary(),
+        }
+        if gather is not None:
+            line["with_gather_to_rank0"] = gather
+        if world == 1 and not args.no_cpu_baseline:
+            from __graft_entry__ import build_oracle
+            build_oracle()
+            rate, used, sample, dt = cpu_port_rate(headers, offsets, h_packed.array, R, args.layout,
+                                                   args.cpu_seconds)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": used, "kind": "port",
+                "sample": "first %d frames of the same batch in %.1f s; C restatement of the reference's Python "
+                          "voxel loop (oracle/dtsdf_oracle.c, gcc -O2, OpenMP over frames)" % (sample, dt),
+                "python_loop_volumes_per_s_per_core": python_loop_rate(headers, offsets, h_packed.array, R),
+            }
+        print(json.dumps(line), flush=True)
+    barrier()
+    vox.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU")
+    ap.add_argument("--res", type=int, default=32, choices=[32, 48, 64])
+    ap.add_argument("--layout", type=int, default=0, choices=[0, 1], help="0 = (c,x,y,z), 1 = (c,z,y,x)")
+    ap.add_argument("--gather", action="store_true", help="also time voxelise + gather of volumes to rank 0")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

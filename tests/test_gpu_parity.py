@@ -20,7 +20,13 @@ def vox():
 
 
 def _same(a, b):
-    return np.array_equal(a, b) and np.array_equal(np.signbit(a), np.signbit(b))
+    """Bit-exact, sign of zero included; NaNs (0/0 when a bounding box degenerates to a point)
+    must sit in the same places, their payload is not compared."""
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape != b.shape or not np.array_equal(a, b, equal_nan=True):
+        return False
+    ok = ~np.isnan(a)
+    return bool(np.array_equal(np.signbit(a)[ok], np.signbit(b)[ok]))
 
 
 def test_library_loaded_and_device_present():
