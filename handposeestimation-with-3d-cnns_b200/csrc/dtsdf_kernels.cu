@@ -16,20 +16,34 @@
 // Design (one CTA works on one frame at a time, persistent over the batch):
 //   1. thread 0 starts a TMA bulk copy (cp.async.bulk, completion on an mbarrier) of
 //      the frame's depth crop global -> shared memory;
-//   2. all threads scan the crop in shared memory for the bounding box; warp
+//   2. one warp per crop row scans the crop in shared memory for the bounding box; warp
 //      reduction with redux.sync.{min,max}.f32 (CREDUX, new on sm_100a), block
 //      reduction through shared memory;
 //   3. every thread derives the grid parameters; the block fills two R x R tables of
 //      projected pixel columns / rows (the projection separates: pix_x depends on
 //      (x,z) only, pix_y on (y,z) only), so the voxel loop does no projection maths;
-//   4. voxel loop: each thread owns 4 consecutive voxels along the fastest output
-//      axis, gathers their depth pixels from shared memory, evaluates the truncated
-//      signed directional distances and writes three 16-byte streaming stores (one per
-//      channel); a warp store covers 512 contiguous bytes.
+//   4. voxel loop over tiles of 8 x 4 columns x 32 voxels along the fastest output
+//      axis.  A warp owns one group of 4 consecutive voxels along that axis for the
+//      32 columns of the tile, so all its lanes sit at (almost) the same depth:
+//      most warps are entirely far from the surface and take a ~10-instruction
+//      shortcut (|v_z - w_z| > trunc already forces the Euclidean truncation, the
+//      result is +-1), and only warps that straddle the surface run the full
+//      per-axis evaluation.  Results go to a 128B-swizzled shared-memory tile
+//      (conflict-free 16-byte stores) that one thread hands to the TMA engine
+//      (cp.async.bulk.tensor.5d, SWIZZLE_128B) for the global write, double-buffered,
+//      so the LSU never issues a global store.
+// Divisions: x/focal and x/trunc have per-launch / per-frame constant divisors; they
+// are evaluated as q = a*y, then one or two residual corrections q += fma(-b,q,a)*y
+// with y = rcp_rn(b) (Markstein).  With a correctly rounded reciprocal and a faithful
+// q the last correction is the correctly rounded quotient; for the default focal
+// 241.42f the one-correction form was checked exhaustively over all dividends
+// (tests/test_division.py).  Frames or pixels outside the proven exponent ranges
+// take the generic IEEE path (__fdiv_rn).  Results are bit-identical either way.
 // The path is a streaming, write-dominated map with a small gather: HBM-bound, no
 // tensor cores (there is no contraction to feed them).
 #include "dtsdf_internal.h"
 
+#include <cuda.h>
 #include <math.h>
 
 namespace dtsdf {
@@ -43,6 +57,10 @@ constexpr int NWARP = NT / 32;
 constexpr float SENTINEL = 99999.0f;    // pre/tsdf_numba.py:88-89
 constexpr int MAGIC_I = 0x4B400000;     // bit pattern of 12582912.0f = 1.5 * 2^23
 constexpr float MAGIC_F = 12582912.0f;  // int_as_float(MAGIC_I + k) == MAGIC_F + k for |k| < 2^22
+constexpr float THR_SQ = 1.00000011920928955078125f;   // nextafter(1,2): sqrt_rn(s) > 1 <=> s > THR_SQ
+constexpr float BIG_DEPTH = 1099511627776.0f;          // 2^40: depth range of the FMA division proof
+constexpr int TILE_BYTES = 3 * 32 * 128;               // 3 channels x 32 columns x 32 floats
+constexpr unsigned DEFAULT_FOCAL_BITS = 0x43716B85u;   // 241.42f
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -82,6 +100,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
             : "memory");
     } while (!done);
 }
+// 5-D TMA tensor store shared -> global (bulk async-group completion).
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tmap, const void* src, int c0, int c1,
+                                             int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+            reinterpret_cast<uint64_t>(tmap)),
+        "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ float warp_min(float v) {
     float r;
     asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
@@ -92,9 +124,16 @@ __device__ __forceinline__ float warp_max(float v) {
     asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
     return r;
 }
-__device__ __forceinline__ void st_stream_f4(float* p, float a, float b, float c, float d) {
-    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
-                 : "memory");
+
+// ---------------------------------------------------------------- exact division by a fixed divisor
+// a / b with y = rcp_rn(b): one (ONE=true) or two residual corrections.  Preconditions
+// (checked by the callers): b and a/b well inside the normal range, see file header.
+template <bool ONE>
+__device__ __forceinline__ float div_fixed(float a, float b, float y) {
+    float q = __fmul_rn(a, y);
+    q = __fmaf_rn(__fmaf_rn(-b, q, a), y, q);
+    if (!ONE) q = __fmaf_rn(__fmaf_rn(-b, q, a), y, q);
+    return q;
 }
 
 // ---------------------------------------------------------------- shared memory
@@ -102,132 +141,201 @@ template <int R>
 struct __align__(16) FrameShared {
     float red[NWARP][8];            // per-warp partial min xyz / max xyz (6 used)
     float vx[R], vy[R], vz[R];      // voxel centres per axis
-    short pxt[R * R];               // projected column - left, or -1 when outside the crop
-    short pyt[R * R];               // projected row - top,    or -1
-    unsigned long long bar;         // TMA completion barrier
+    float coef[R];                  // -focal / vz
+    int   xt[R * R];                // [s][f]: 4*(pix_x - left), negative when outside the crop
+    int   yt[R * R];                // CXYZ: [y][z], CZYX: [z][y]: pix_y - top, negative when outside
+    unsigned long long bar;         // crop TMA completion barrier
 };
 
 struct Frame {
-    int l, t, r, b, bw, n;
+    int l, t, r, b, bw, bh, n;
 };
 
-// ---------------------------------------------------------------- bounding box scan
-// pre/tsdf_numba.py:83-96.  `crop` is shared memory when STAGED, global otherwise.
-template <bool STAGED>
-__device__ __forceinline__ void bbox_scan(const float* __restrict__ crop, const Frame& fr,
-                                          float focal, int cx, int cy, float (&mn)[3],
-                                          float (&mx)[3]) {
-    // row = pos / bw via multiply-high; exact for pos*bw < 2^32 (bw, bh <= 32767 is
-    // checked by the caller and n = bw*bh < 2^30, so the error term pos*(m*bw - 2^32)
-    // stays below 2^32 as m*bw - 2^32 < bw).
-    const unsigned magic = fr.bw > 1 ? (unsigned)((0x100000000ull + (unsigned)fr.bw - 1) / (unsigned)fr.bw) : 0u;
-    const float kx = MAGIC_F + (float)cx;
-    const float ky = MAGIC_F + (float)cy;
-    for (int pos = threadIdx.x; pos < fr.n; pos += NT) {
-        const float d = STAGED ? crop[pos] : __ldg(crop + pos);
-        if (!(fabsf(d) < 1.0f)) {
-            const int row = fr.bw > 1 ? (int)__umulhi((unsigned)pos, magic) : pos;
-            const int col = pos - row * fr.bw;
-            const float q = __fdiv_rn(d, focal);
-            const float fx = __fsub_rn(__int_as_float(MAGIC_I + col + fr.l), kx);   // (x - cx), exact
-            const float fy = __fsub_rn(__int_as_float(MAGIC_I + row + fr.t), ky);   // (y - cy), exact
-            const float X = __fmul_rn(q, fx);
-            const float Y = __fmul_rn(-q, fy);
-            const float Z = -d;
-            mn[0] = fminf(mn[0], X); mx[0] = fmaxf(mx[0], X);
-            mn[1] = fminf(mn[1], Y); mx[1] = fmaxf(mx[1], Y);
-            mn[2] = fminf(mn[2], Z); mx[2] = fmaxf(mx[2], Z);
-        }
-    }
-}
-
-// ---------------------------------------------------------------- voxel evaluation
+// per-frame constants of the voxel evaluation
 struct VoxConst {
-    int   bw;
+    int   bw4;       // 4 * crop width (byte stride of a crop row)
     int   ix;        // MAGIC_I + left:  int_as_float(ix + (px-left)) == MAGIC_F + px
     int   iy;        // MAGIC_I + top
     float kx;        // MAGIC_F + cx
     float ky;        // MAGIC_F + cy
     float focal;
+    float yf;        // rcp_rn(focal)
     float trunc;
+    float yt;        // rcp_rn(trunc)
+    float t_far;     // |v_z - w_z| above this forces truncation; +inf disables the shortcut
 };
 
-// pre/process.py:163-194 == pre/tsdf_numba.py:38-68 for one voxel whose projection
-// (pa, pb) = (pix_x - left, pix_y - top) is inside the crop.
-template <bool STAGED>
-__device__ __forceinline__ void eval_voxel(const float* __restrict__ crop, const VoxConst& k,
-                                           int pa, int pb, float vx, float vy, float vz,
-                                           float& o0, float& o1, float& o2) {
-    const int idx = pb * k.bw + pa;
-    const float d = STAGED ? crop[idx] : __ldg(crop + idx);
-    if (fabsf(d) < 1.0f) return;
-    const float c1 = __fdiv_rn(d, k.focal);
-    const float fx = __fsub_rn(__int_as_float(k.ix + pa), k.kx);    //  (pix_x - cx)
-    const float fy = __fsub_rn(k.ky, __int_as_float(k.iy + pb));    // -(pix_y - cy)
-    const float wx = __fmul_rn(fx, c1);
-    const float wy = __fmul_rn(fy, c1);
-    const float wz = -d;
-    float tx = __fdiv_rn(fabsf(__fsub_rn(vx, wx)), k.trunc);
-    float ty = __fdiv_rn(fabsf(__fsub_rn(vy, wy)), k.trunc);
-    float tz = __fdiv_rn(fabsf(__fsub_rn(vz, wz)), k.trunc);
-    const float s = __fadd_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)), __fmul_rn(tz, tz));
-    // sqrt_rn(s) > 1  <=>  s > nextafter(1,2): the square root of pre/process.py:180 is
-    // only compared with 1 (tests/test_oracle_golden.py::test_sqrt_truncation_threshold).
-    // Below the threshold every component is already <= 1, so min(t,1) (:187-189) is
-    // the identity there.
-    if (s > 1.00000011920928955078125f) { tx = 1.0f; ty = 1.0f; tz = 1.0f; }
-    if (wz > vz) { tx = -tx; ty = -ty; tz = -tz; }
-    o0 = tx; o1 = ty; o2 = tz;
+// ---------------------------------------------------------------- bounding box scan
+// pre/tsdf_numba.py:83-96, one warp per crop row.  `crop` is shared memory when STAGED.
+template <bool STAGED, bool DEFF>
+__device__ __forceinline__ void bbox_scan(const float* __restrict__ crop, const Frame& fr, float focal,
+                                          float yf, bool focal_ok, int cx, int cy, float (&mn)[3],
+                                          float (&mx)[3]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float kx = MAGIC_F + (float)cx;
+    const float ky = MAGIC_F + (float)cy;
+    for (int row = warp; row < fr.bh; row += NWARP) {
+        const float fy = __fsub_rn(__int_as_float(MAGIC_I + row + fr.t), ky);        // (y - cy), exact
+        const float* p = crop + (size_t)row * fr.bw;
+        float fx = __fsub_rn(__int_as_float(MAGIC_I + lane + fr.l), kx);             // (x - cx), exact
+        for (int col = lane; col < fr.bw; col += 32, fx = __fadd_rn(fx, 32.0f)) {
+            const float d = STAGED ? p[col] : __ldg(p + col);
+            const float ad = fabsf(d);
+            if (!(ad < 1.0f)) {
+                float q;
+                if (ad < BIG_DEPTH && (DEFF || focal_ok)) q = div_fixed<DEFF>(d, focal, yf);
+                else q = __fdiv_rn(d, focal);
+                const float X = __fmul_rn(q, fx);
+                const float Y = __fmul_rn(-q, fy);
+                const float Z = -d;
+                mn[0] = fminf(mn[0], X); mx[0] = fmaxf(mx[0], X);
+                mn[1] = fminf(mn[1], Y); mx[1] = fmaxf(mx[1], Y);
+                mn[2] = fminf(mn[2], Z); mx[2] = fmaxf(mx[2], Z);
+            }
+        }
+    }
 }
 
-template <int R, int LAYOUT, bool STAGED>
-__device__ __forceinline__ void voxel_loop(const float* __restrict__ crop,
-                                           const FrameShared<R>* __restrict__ sh,
-                                           const VoxConst& k, float* __restrict__ out) {
-    constexpr int Q = R / 4;                 // 4-voxel groups along the fastest axis
-    constexpr int ITEMS = R * R * Q;
-    constexpr int CH = R * R * R;            // channel stride
+// ---------------------------------------------------------------- voxel evaluation
+struct Tsdf3 { float x, y, z; };
+
+// Generic IEEE evaluation of one valid voxel: pre/process.py:172-194 == pre/tsdf_numba.py:43-68.
+// sz = v_z + d (= v_z - w_z).
+__device__ __noinline__ Tsdf3 eval_generic(float d, float fx, float fy, float vx, float vy, float vz,
+                                           float sz, float focal, float trunc) {
+    const float c1 = __fdiv_rn(d, focal);
+    const float wx = __fmul_rn(fx, c1);
+    const float wy = __fmul_rn(fy, c1);
+    float tx = __fdiv_rn(fabsf(__fsub_rn(vx, wx)), trunc);
+    float ty = __fdiv_rn(fabsf(__fsub_rn(vy, wy)), trunc);
+    float tz = __fdiv_rn(fabsf(sz), trunc);
+    const float s = __fadd_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)), __fmul_rn(tz, tz));
+    // sqrt_rn(s) > 1 <=> s > nextafter(1,2); below it every component is <= 1 already, so
+    // min(t,1) (pre/process.py:187-189) is the identity there.
+    if (s > THR_SQ) { tx = 1.0f; ty = 1.0f; tz = 1.0f; }
+    if (-d > vz) { tx = -tx; ty = -ty; tz = -tz; }
+    Tsdf3 o; o.x = tx; o.y = ty; o.z = tz;
+    return o;
+}
+
+// Same evaluation with the fixed-divisor divisions (bit-identical inside the proven ranges).
+template <bool DEFF>
+__device__ __forceinline__ Tsdf3 eval_fast(float d, float fx, float fy, float vx, float vy, float sz,
+                                           const VoxConst& k) {
+    const float c1 = div_fixed<DEFF>(d, k.focal, k.yf);
+    const float wx = __fmul_rn(fx, c1);
+    const float wy = __fmul_rn(fy, c1);
+    float tx = div_fixed<false>(fabsf(__fsub_rn(vx, wx)), k.trunc, k.yt);
+    float ty = div_fixed<false>(fabsf(__fsub_rn(vy, wy)), k.trunc, k.yt);
+    float tz = div_fixed<false>(fabsf(sz), k.trunc, k.yt);
+    const float s = __fadd_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)), __fmul_rn(tz, tz));
+    if (s > THR_SQ) { tx = 1.0f; ty = 1.0f; tz = 1.0f; }
+    if (sz < 0.0f) { tx = -tx; ty = -ty; tz = -tz; }      // -d > v_z  <=>  v_z + d < 0
+    Tsdf3 o; o.x = tx; o.y = ty; o.z = tz;
+    return o;
+}
+
+// One frame's voxel loop.  F = fastest output axis (z for CXYZ, x for CZYX), S = slowest
+// (x / z), M = y.  A tile is 8 (S) x 4 (M) columns x 32 (F) voxels; warp w owns the 4 voxels
+// F = 32*chunk + 4*w .. +3 of the tile's 32 columns (lane = 4*s_local + m_local).
+template <int R, int LAYOUT, bool STAGED, bool FAST, bool DEFF>
+__device__ __forceinline__ void voxel_tiles(const float* __restrict__ crop,
+                                            const FrameShared<R>* __restrict__ sh, const VoxConst& k,
+                                            const CUtensorMap* tmap, unsigned char* tiles, int frame,
+                                            unsigned& gstep) {
+    constexpr int FCH = (R + 31) / 32;
+    constexpr int NM = R / 4;
+    constexpr int NSTEPS = (R / 8) * NM * FCH;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll 1
-    for (int it = threadIdx.x; it < ITEMS; it += NT) {
-        const int q4 = it % Q;
-        const int m = (it / Q) % R;          // middle axis: y in both layouts
-        const int o = it / (Q * R);          // slowest axis: x (CXYZ) or z (CZYX)
-        short4 pa4, pb4;
-        float4 va, vb, vc;                   // voxel centre x / y / z for the 4 voxels
-        if (LAYOUT == 0) {                   // out[c][x][y][z]: 4 consecutive z
-            pa4 = *reinterpret_cast<const short4*>(&sh->pxt[o * R + 4 * q4]);   // [x][z]
-            pb4 = *reinterpret_cast<const short4*>(&sh->pyt[m * R + 4 * q4]);   // [y][z]
-            const float x = sh->vx[o], y = sh->vy[m];
-            va = make_float4(x, x, x, x);
-            vb = make_float4(y, y, y, y);
-            vc = *reinterpret_cast<const float4*>(&sh->vz[4 * q4]);
-        } else {                             // out[c][z][y][x]: 4 consecutive x
-            pa4 = *reinterpret_cast<const short4*>(&sh->pxt[o * R + 4 * q4]);   // [z][x]
-            const short pb = sh->pyt[o * R + m];                                // [z][y]
-            pb4 = make_short4(pb, pb, pb, pb);
-            const float y = sh->vy[m], z = sh->vz[o];
-            va = *reinterpret_cast<const float4*>(&sh->vx[4 * q4]);
-            vb = make_float4(y, y, y, y);
-            vc = make_float4(z, z, z, z);
+    for (int ts = 0; ts < NSTEPS; ++ts) {
+        const int fch = ts % FCH;
+        const int mg = (ts / FCH) % NM;
+        const int sg = ts / (FCH * NM);
+        const int s = sg * 8 + (lane >> 2);
+        const int m = mg * 4 + (lane & 3);
+        const int f0 = fch * 32 + 4 * warp;
+        float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f}, o2[4] = {0.f, 0.f, 0.f, 0.f};
+        if (f0 < R) {
+            const int4 xa = *reinterpret_cast<const int4*>(&sh->xt[s * R + f0]);
+            int pa[4] = {xa.x, xa.y, xa.z, xa.w};
+            int pb[4];
+            float vxj[4], vyj[4], vzj[4];
+            if (LAYOUT == 0) {              // out[c][x][y][z]: S = x, F = z
+                const int4 yb = *reinterpret_cast<const int4*>(&sh->yt[m * R + f0]);
+                pb[0] = yb.x; pb[1] = yb.y; pb[2] = yb.z; pb[3] = yb.w;
+                const float4 vz4 = *reinterpret_cast<const float4*>(&sh->vz[f0]);
+                vzj[0] = vz4.x; vzj[1] = vz4.y; vzj[2] = vz4.z; vzj[3] = vz4.w;
+                const float x = sh->vx[s], y = sh->vy[m];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { vxj[j] = x; vyj[j] = y; }
+            } else {                        // out[c][z][y][x]: S = z, F = x
+                const int yb = sh->yt[s * R + m];
+                const float4 vx4 = *reinterpret_cast<const float4*>(&sh->vx[f0]);
+                vxj[0] = vx4.x; vxj[1] = vx4.y; vxj[2] = vx4.z; vxj[3] = vx4.w;
+                const float y = sh->vy[m], z = sh->vz[s];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { pb[j] = yb; vyj[j] = y; vzj[j] = z; }
+            }
+            float d[4], sz[4];
+            bool nearj[4];
+            bool any_near = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool inside = (pa[j] | pb[j]) >= 0;
+                const int off = inside ? pb[j] * k.bw4 + pa[j] : 0;
+                const float* q = reinterpret_cast<const float*>(reinterpret_cast<const char*>(crop) + off);
+                d[j] = STAGED ? *q : __ldg(q);
+                const bool ok = inside && !(fabsf(d[j]) < 1.0f);          // pre/process.py:159,167
+                sz[j] = __fadd_rn(vzj[j], d[j]);                          // v_z - w_z, w_z = -d
+                const bool far = fabsf(sz[j]) > k.t_far;
+                // far from the surface along z alone: t_z > 1, so the Euclidean truncation
+                // fires (pre/process.py:180-185) and the result is +-1 by the side of the surface
+                const float one = __int_as_float((__float_as_int(sz[j]) & 0x80000000) | 0x3F800000);
+                const float v = (ok && far) ? one : 0.0f;
+                o0[j] = v; o1[j] = v; o2[j] = v;
+                nearj[j] = ok && !far;
+                any_near |= nearj[j];
+            }
+            if (__any_sync(0xffffffffu, any_near)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (nearj[j]) {
+                        const float fx = __fsub_rn(__int_as_float(k.ix + (pa[j] >> 2)), k.kx);   //  (pix_x - cx)
+                        const float fy = __fsub_rn(k.ky, __int_as_float(k.iy + pb[j]));          // -(pix_y - cy)
+                        Tsdf3 t;
+                        if (FAST && fabsf(d[j]) < BIG_DEPTH) t = eval_fast<DEFF>(d[j], fx, fy, vxj[j], vyj[j], sz[j], k);
+                        else t = eval_generic(d[j], fx, fy, vxj[j], vyj[j], vzj[j], sz[j], k.focal, k.trunc);
+                        o0[j] = t.x; o1[j] = t.y; o2[j] = t.z;
+                    }
+                }
+            }
         }
-        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
-        if ((pa4.x | pb4.x) >= 0) eval_voxel<STAGED>(crop, k, pa4.x, pb4.x, va.x, vb.x, vc.x, r0.x, r1.x, r2.x);
-        if ((pa4.y | pb4.y) >= 0) eval_voxel<STAGED>(crop, k, pa4.y, pb4.y, va.y, vb.y, vc.y, r0.y, r1.y, r2.y);
-        if ((pa4.z | pb4.z) >= 0) eval_voxel<STAGED>(crop, k, pa4.z, pb4.z, va.z, vb.z, vc.z, r0.z, r1.z, r2.z);
-        if ((pa4.w | pb4.w) >= 0) eval_voxel<STAGED>(crop, k, pa4.w, pb4.w, va.w, vb.w, vc.w, r0.w, r1.w, r2.w);
-        float* p = out + 4 * it;
-        st_stream_f4(p, r0.x, r0.y, r0.z, r0.w);
-        st_stream_f4(p + CH, r1.x, r1.y, r1.z, r1.w);
-        st_stream_f4(p + 2 * CH, r2.x, r2.y, r2.z, r2.w);
+        // 128B-swizzled tile: row = lane (column of the tile), 16-byte chunk = warp ^ (row & 7)
+        unsigned char* buf = tiles + (gstep & 1u) * TILE_BYTES;
+        float4* dst = reinterpret_cast<float4*>(buf + lane * 128 + ((warp ^ (lane & 7)) << 4));
+        dst[0] = make_float4(o0[0], o0[1], o0[2], o0[3]);
+        dst[256] = make_float4(o1[0], o1[1], o1[2], o1[3]);      // + 4096 bytes: channel 1
+        dst[512] = make_float4(o2[0], o2[1], o2[2], o2[3]);      // + 8192 bytes: channel 2
+        fence_proxy_async();                  // generic-proxy writes -> visible to the TMA engine
+        if (tid == 0) bulk_wait_read_all();   // the other buffer's store has finished reading it
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_5d(tmap, buf, fch * 32, mg * 4, sg * 8, 0, frame);
+            bulk_commit();
+        }
+        ++gstep;
     }
 }
 
 // ---------------------------------------------------------------- fused kernel
-template <int R, int LAYOUT>
-__global__ void __launch_bounds__(NT) dtsdf_fused_kernel(const BatchArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FrameShared<R>* sh = reinterpret_cast<FrameShared<R>*>(smem_raw);
-    float* crop_s = reinterpret_cast<float*>(smem_raw + sizeof(FrameShared<R>));
+template <int R, int LAYOUT, bool DEFF>
+__global__ void __launch_bounds__(NT, 2) dtsdf_fused_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                            const BatchArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* tiles = smem_raw;                                           // 2 x TILE_BYTES, 1024-aligned
+    FrameShared<R>* sh = reinterpret_cast<FrameShared<R>*>(smem_raw + 2 * TILE_BYTES);
+    float* crop_s = reinterpret_cast<float*>(smem_raw + 2 * TILE_BYTES + sizeof(FrameShared<R>));
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 
@@ -237,6 +345,9 @@ __global__ void __launch_bounds__(NT) dtsdf_fused_kernel(const BatchArgs a) {
     }
     __syncthreads();
     uint32_t parity = 0;
+    unsigned gstep = 0;
+    const float yf = __frcp_rn(a.focal);
+    const bool focal_ok = a.focal >= 0x1p-30f && a.focal <= 0x1p30f;
 
     for (int f = blockIdx.x; f < a.n_frames; f += gridDim.x) {
         // ---- frame record (pre/tsdf_numba.py:122-129)
@@ -244,11 +355,12 @@ __global__ void __launch_bounds__(NT) dtsdf_fused_kernel(const BatchArgs a) {
         Frame fr;
         fr.l = __ldg(h + 2); fr.t = __ldg(h + 3); fr.r = __ldg(h + 4); fr.b = __ldg(h + 5);
         fr.bw = fr.r - fr.l;
-        const int bh = fr.b - fr.t;
+        fr.bh = fr.b - fr.t;
         const int lim = 1 << 22;
-        const bool bad = fr.bw <= 0 || bh <= 0 || fr.bw > 32767 || bh > 32767 ||
+        const bool bad = fr.bw <= 0 || fr.bh <= 0 || fr.bw > 32767 || fr.bh > 32767 ||
                          fr.l <= -lim || fr.t <= -lim || fr.r >= lim || fr.b >= lim;
-        fr.n = bad ? 0 : fr.bw * bh;
+        if (bad) { fr.bw = 0; fr.bh = 0; }
+        fr.n = fr.bw * fr.bh;
         const float* crop_g = a.depth + __ldg(a.offsets + f);
         const int n_pad = (fr.n + 3) & ~3;
         const bool staged = n_pad > 0 && n_pad <= a.cap_floats;     // CTA-uniform
@@ -285,9 +397,9 @@ __global__ void __launch_bounds__(NT) dtsdf_fused_kernel(const BatchArgs a) {
                 if (staged) {
                     mbar_wait(&sh->bar, parity);
                     landed = true;
-                    bbox_scan<true>(crop_s, fr, a.focal, a.center_x, a.center_y, mn, mx);
+                    bbox_scan<true, DEFF>(crop_s, fr, a.focal, yf, focal_ok, a.center_x, a.center_y, mn, mx);
                 } else {
-                    bbox_scan<false>(crop_g, fr, a.focal, a.center_x, a.center_y, mn, mx);
+                    bbox_scan<false, DEFF>(crop_g, fr, a.focal, yf, focal_ok, a.center_x, a.center_y, mn, mx);
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { mn[c] = warp_min(mn[c]); mx[c] = warp_max(mx[c]); }
@@ -331,52 +443,99 @@ __global__ void __launch_bounds__(NT) dtsdf_fused_kernel(const BatchArgs a) {
             }
         }
 
-        // ---- 3. per-axis voxel centres and the two projection tables
+        // ---- 3. per-axis voxel centres, -focal/v_z, and the two projection tables
         //         (pre/process.py:150-159 == pre/tsdf_numba.py:26-32,36)
         if (tid < R) {
-            const float s = __fmul_rn((float)tid, voxel_len);
-            sh->vx[tid] = __fadd_rn(ox, s);
-            sh->vy[tid] = __fadd_rn(oy, s);
-            sh->vz[tid] = __fadd_rn(oz, s);
+            const float sft = __fmul_rn((float)tid, voxel_len);
+            const float vz = __fadd_rn(oz, sft);
+            sh->vx[tid] = __fadd_rn(ox, sft);
+            sh->vy[tid] = __fadd_rn(oy, sft);
+            sh->vz[tid] = vz;
+            sh->coef[tid] = __fdiv_rn(-a.focal, vz);
         }
+        __syncthreads();
         for (int e = tid; e < R * R; e += NT) {
             const int ea = e / R, eb = e % R;
-            const int zi = (LAYOUT == 0) ? eb : ea;      // pxt: [x][z] / [z][x]; pyt: [y][z] / [z][y]
-            const int xi = (LAYOUT == 0) ? ea : eb;      // (also the y index for pyt)
-            const float vz = __fadd_rn(oz, __fmul_rn((float)zi, voxel_len));
-            const float vx = __fadd_rn(ox, __fmul_rn((float)xi, voxel_len));
-            const float vy = __fadd_rn(oy, __fmul_rn((float)xi, voxel_len));
-            const float coeff = __fdiv_rn(-a.focal, vz);
-            const float fpx = __fadd_rn(__fmul_rn(vx, coeff), (float)a.center_x);
-            const float fpy = __fadd_rn(__fmul_rn(-vy, coeff), (float)a.center_y);
+            // xt[s][f]: CXYZ (x = ea, z = eb), CZYX (z = ea, x = eb)
+            // yt:       CXYZ [y = ea][z = eb], CZYX [z = ea][y = eb]
+            const int zi = (LAYOUT == 0) ? eb : ea;
+            const int ti = (LAYOUT == 0) ? ea : eb;      // x index for xt, y index for yt
+            const float coeff = sh->coef[zi];
+            const float fpx = __fadd_rn(__fmul_rn(sh->vx[ti], coeff), (float)a.center_x);
+            const float fpy = __fadd_rn(__fmul_rn(-sh->vy[ti], coeff), (float)a.center_y);
             const int px = __float2int_rz(fpx);          // int(): truncation toward zero
             const int py = __float2int_rz(fpy);
-            const bool okx = !bad && fabsf(fpx) < 2e9f && px >= fr.l && px < fr.r;   // non-finite -> outside
-            const bool oky = !bad && fabsf(fpy) < 2e9f && py >= fr.t && py < fr.b;
-            sh->pxt[e] = okx ? (short)(px - fr.l) : (short)-1;
-            sh->pyt[e] = oky ? (short)(py - fr.t) : (short)-1;
+            const bool okx = fabsf(fpx) < 2e9f && px >= fr.l && px < fr.r;   // non-finite -> outside
+            const bool oky = fabsf(fpy) < 2e9f && py >= fr.t && py < fr.b;   // (bad header: empty ranges)
+            sh->xt[e] = okx ? 4 * (px - fr.l) : (int)0x80000000;
+            sh->yt[e] = oky ? (py - fr.t) : (int)0x80000000;
         }
         if (staged && !landed) mbar_wait(&sh->bar, parity);
         if (staged) parity ^= 1u;
         __syncthreads();
 
         // ---- 4. voxel loop
+        // the fixed-divisor divisions are proven for these ranges (file header); anything else
+        // takes the generic IEEE path
+        const float ax = fabsf(ox), ay = fabsf(oy), az = fabsf(oz);
+        const bool fast = (DEFF || focal_ok) && trunc >= 0x1p-30f && trunc <= 0x1p30f &&
+                          voxel_len >= 0x1p-30f && voxel_len <= 0x1p30f &&
+                          (ax == 0.0f || (ax >= 0x1p-60f && ax <= 0x1p30f)) &&
+                          (ay == 0.0f || (ay >= 0x1p-60f && ay <= 0x1p30f)) &&
+                          (az == 0.0f || (az >= 0x1p-60f && az <= 0x1p30f));
         VoxConst k;
-        k.bw = fr.bw;
+        k.bw4 = 4 * fr.bw;
         k.ix = MAGIC_I + fr.l;
         k.iy = MAGIC_I + fr.t;
         k.kx = MAGIC_F + (float)a.center_x;
         k.ky = MAGIC_F + (float)a.center_y;
         k.focal = a.focal;
+        k.yf = yf;
         k.trunc = trunc;
-        float* out = a.vol + (size_t)f * 3 * R * R * R;
-        if (staged) voxel_loop<R, LAYOUT, true>(crop_s, sh, k, out);
-        else        voxel_loop<R, LAYOUT, false>(crop_g, sh, k, out);
-        __syncthreads();              // crop_s and the tables are rewritten by the next frame
+        k.yt = __frcp_rn(trunc);
+        // margin 2^-10 on the far test: t_z = RN(|s_z|/trunc) > 1 + 2^-11, t_z^2 > THR_SQ
+        k.t_far = fast ? __fmul_rn(trunc, 1.0009765625f) : INFINITY;
+        if (fast) {
+            if (staged) voxel_tiles<R, LAYOUT, true, true, DEFF>(crop_s, sh, k, &tmap, tiles, f, gstep);
+            else        voxel_tiles<R, LAYOUT, false, true, DEFF>(crop_g, sh, k, &tmap, tiles, f, gstep);
+        } else {
+            if (staged) voxel_tiles<R, LAYOUT, true, false, DEFF>(crop_s, sh, k, &tmap, tiles, f, gstep);
+            else        voxel_tiles<R, LAYOUT, false, false, DEFF>(crop_g, sh, k, &tmap, tiles, f, gstep);
+        }
+        // the last tile's __syncthreads() also orders every read of crop_s / the tables before the
+        // next frame overwrites them
     }
+    if (tid == 0) bulk_wait_all();    // shared memory must outlive the TMA reads
 }
 
-template <int R, int LAYOUT>
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+cudaError_t encode_volume_map(CUtensorMap* tmap, float* vol, int R, int n_frames) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return e;
+        if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    // volume tensor, fastest dimension first: F (R), M (R), S (R), channel (3), frame (n)
+    const cuuint64_t r = (cuuint64_t)R;
+    cuuint64_t dims[5] = {r, r, r, 3, (cuuint64_t)n_frames};
+    cuuint64_t strides[4] = {r * 4, r * r * 4, r * r * r * 4, 3 * r * r * r * 4};
+    cuuint32_t box[5] = {32, 4, 8, 3, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult res = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, vol, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return res == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int R, int LAYOUT, bool DEFF>
 cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t stream) {
     BatchArgs args = args_in;
     int dev = 0;
@@ -387,9 +546,13 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    const int fixed = (int)sizeof(FrameShared<R>);
-    // staging capacity: the largest crop of the batch when known, capped so at least two
-    // CTAs fit per SM when that is enough for the crop; oversize crops take the direct path.
+    if ((reinterpret_cast<uintptr_t>(args.vol) & 15) != 0) return cudaErrorMisalignedAddress;
+    alignas(64) CUtensorMap tmap;
+    e = encode_volume_map(&tmap, args.vol, R, args.n_frames);
+    if (e != cudaSuccess) return e;
+    const int fixed = 2 * TILE_BYTES + (int)sizeof(FrameShared<R>);
+    // staging capacity: the largest crop of the batch when known (the occupancy then follows from
+    // it: two CTAs per SM up to ~85 KB crops, one above); oversize crops take the direct path.
     long long want = max_crop_px > 0 ? (((long long)max_crop_px + 3) & ~3ll) * 4 : (long long)smem_optin;
     long long avail = (long long)smem_optin - fixed - 1024;
     if (want > avail) want = avail;
@@ -397,7 +560,7 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     want &= ~15ll;
     args.cap_floats = (int)(want / 4);
     const size_t smem = (size_t)fixed + (size_t)want;
-    auto kern = dtsdf_fused_kernel<R, LAYOUT>;
+    auto kern = dtsdf_fused_kernel<R, LAYOUT, DEFF>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
@@ -406,7 +569,7 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     if (occ < 1) occ = 1;
     long long grid = (long long)occ * sms;        // persistent: a whole number of waves
     if (grid > args.n_frames) grid = args.n_frames;
-    kern<<<(unsigned)grid, NT, smem, stream>>>(args);
+    kern<<<(unsigned)grid, NT, smem, stream>>>(tmap, args);
     ++g_launch_count;
     return cudaGetLastError();
 }
@@ -527,10 +690,15 @@ __global__ void normalize_joints_kernel(int total, const float* __restrict__ joi
 cudaError_t launch_voxelize(int voxel_res, int layout, BatchArgs args, int max_crop_px,
                             cudaStream_t stream) {
     if (args.n_frames <= 0) return cudaSuccess;
-#define DTSDF_CASE(RR)                                                                   \
-    case RR:                                                                             \
-        return layout == 0 ? launch_fused<RR, 0>(args, max_crop_px, stream)              \
-                           : launch_fused<RR, 1>(args, max_crop_px, stream);
+    // the one-correction division by focal is proven for 241.42f only (exhaustive test)
+    const bool deff = __builtin_bit_cast(unsigned, args.focal) == DEFAULT_FOCAL_BITS;
+#define DTSDF_CASE(RR)                                                                              \
+    case RR:                                                                                        \
+        if (layout == 0)                                                                            \
+            return deff ? launch_fused<RR, 0, true>(args, max_crop_px, stream)                      \
+                        : launch_fused<RR, 0, false>(args, max_crop_px, stream);                    \
+        return deff ? launch_fused<RR, 1, true>(args, max_crop_px, stream)                          \
+                    : launch_fused<RR, 1, false>(args, max_crop_px, stream);
     switch (voxel_res) {
         DTSDF_CASE(32)
         DTSDF_CASE(48)

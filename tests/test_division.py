@@ -1,0 +1,31 @@
+"""The kernel replaces x/focal and x/trunc by FMA sequences with a precomputed reciprocal
+(csrc/dtsdf_kernels.cu: div_fixed).  This checks them against IEEE division on the CPU:
+exhaustively for the default focal over the dividend range the kernel uses, and on a large
+pseudo-random sample for variable divisors."""
+import os
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "native", "division_check.c")
+
+
+@pytest.fixture(scope="module")
+def checker(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("div") / "division_check")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-fopenmp", SRC, "-o", exe, "-lm"], check=True)
+    return exe
+
+
+def test_one_correction_division_by_default_focal_is_exact(checker):
+    # the kernel's range is 1 <= |d| < 2^40 (biased exponents 127..166); checked with margin
+    out = subprocess.run([checker, "focal", "120", "175"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "mismatches=0" in out.stdout
+
+
+def test_two_correction_division_random(checker):
+    out = subprocess.run([checker, "random", "400000000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "mismatches=0" in out.stdout
