@@ -45,7 +45,7 @@ int check_cfg(const dtsdf_config* cfg) {
 int header_ok(const int32_t* h) {
     const int64_t bw = (int64_t)h[4] - h[2], bh = (int64_t)h[5] - h[3];
     const int64_t lim = 1 << 22;
-    if (bw <= 0 || bh <= 0 || bw > 32767 || bh > 32767) return 0;
+    if (bw <= 0 || bh <= 0 || bw > 32767 || bh > 32767 || bw * bh > ((int64_t)1 << 26)) return 0;
     if (h[2] <= -lim || h[3] <= -lim || h[4] >= lim || h[5] >= lim) return 0;
     return 1;
 }

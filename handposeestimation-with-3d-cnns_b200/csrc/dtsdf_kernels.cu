@@ -13,25 +13,37 @@
 // with __fadd_rn/__fmul_rn/__fdiv_rn, which the compiler never contracts into FMAs.
 // The file is also compiled with -fmad=false.
 //
-// Design (one CTA works on one frame at a time, persistent over the batch):
-//   1. thread 0 starts a TMA bulk copy (cp.async.bulk, completion on an mbarrier) of
-//      the frame's depth crop global -> shared memory;
-//   2. one warp per crop row scans the crop in shared memory for the bounding box; warp
-//      reduction with redux.sync.{min,max}.f32 (CREDUX, new on sm_100a), block
-//      reduction through shared memory;
-//   3. every thread derives the grid parameters; the block fills two R x R tables of
-//      projected pixel columns / rows (the projection separates: pix_x depends on
-//      (x,z) only, pix_y on (y,z) only), so the voxel loop does no projection maths;
-//   4. voxel loop over tiles of 8 x 4 columns x 32 voxels along the fastest output
-//      axis.  A warp owns one group of 4 consecutive voxels along that axis for the
-//      32 columns of the tile, so all its lanes sit at (almost) the same depth:
-//      most warps are entirely far from the surface and take a ~10-instruction
-//      shortcut (|v_z - w_z| > trunc already forces the Euclidean truncation, the
-//      result is +-1), and only warps that straddle the surface run the full
-//      per-axis evaluation.  Results go to a 128B-swizzled shared-memory tile
-//      (conflict-free 16-byte stores) that one thread hands to the TMA engine
-//      (cp.async.bulk.tensor.5d, SWIZZLE_128B) for the global write, double-buffered,
-//      so the LSU never issues a global store.
+// Design (persistent CTAs; one CTA works on one frame at a time, 8 warps):
+//   per frame                                              who            sync
+//   ------------------------------------------------------------------------------------
+//   A  block-reduce the bbox partials, grid parameters     all threads    barrier before
+//   B  projection tables at[s][f], yt (the projection      all threads
+//      separates: pix_x depends on (x,z), pix_y on (y,z))
+//   C  voxel loop, two interleaved passes                  warps, free-   barrier before,
+//                                                          running        crop mbarrier
+//   D  "crop buffer free" arrival; the last warp to        lane 0 of
+//      arrive starts the TMA bulk copy of the NEXT crop    each warp
+//   E  bbox scan of the NEXT frame straight from global    warps, free-
+//      memory (L2), partials to shared memory              running
+//   so the crop copy (cp.async.bulk -> mbarrier) and the scan of frame f+1 overlap the
+//   stragglers of frame f, and nobody ever waits for a crop to land.
+//
+// Voxel loop.  A thread owns a group of 4 consecutive voxels along the fastest output
+// axis F (z for (c,x,y,z), x for (c,z,y,x)): one 16-byte store per channel.  Within a
+// warp, lane = (slow-axis row, F-group): R/4 lanes cover one full F-row (128 B for R=32)
+// and 32/(R/4) consecutive slow-axis rows share the warp; the warp then sweeps the middle
+// axis (y).  The lane's table row at[s][f0..f0+3] and its voxel z centres stay in
+// registers for the sweep; the per-iteration table read is a broadcast; the depth gather
+// of a warp touches neighbouring pixels of one or two crop rows (few bank conflicts); the
+// stores of a warp instruction are whole 128-byte lines.
+//   pass 1 classifies every voxel with ~10 instructions: outside the crop / no depth
+//     -> 0; farther than trunc from the surface along z -> +-1 (|v_z - w_z| > trunc
+//     alone forces the Euclidean truncation); otherwise "near".  Every group is stored
+//     at once (near voxels as 0 for now), groups with near voxels are also appended to a
+//     per-warp ring list in shared memory (ballot + popc).
+//   pass 2 runs whenever 32 entries are waiting: every lane takes one listed group, runs
+//     the full per-axis evaluation where needed and rewrites the group's 3 x 16 bytes.
+//     The rewrite hits lines that are still dirty in L2, so DRAM sees each line once.
 // Divisions: x/focal and x/trunc have per-launch / per-frame constant divisors; they
 // are evaluated as q = a*y, then one or two residual corrections q += fma(-b,q,a)*y
 // with y = rcp_rn(b) (Markstein).  With a correctly rounded reciprocal and a faithful
@@ -43,8 +55,8 @@
 // tensor cores (there is no contraction to feed them).
 #include "dtsdf_internal.h"
 
-#include <cuda.h>
 #include <math.h>
+#include <stddef.h>
 
 namespace dtsdf {
 
@@ -59,8 +71,10 @@ constexpr int MAGIC_I = 0x4B400000;     // bit pattern of 12582912.0f = 1.5 * 2^
 constexpr float MAGIC_F = 12582912.0f;  // int_as_float(MAGIC_I + k) == MAGIC_F + k for |k| < 2^22
 constexpr float THR_SQ = 1.00000011920928955078125f;   // nextafter(1,2): sqrt_rn(s) > 1 <=> s > THR_SQ
 constexpr float BIG_DEPTH = 1099511627776.0f;          // 2^40: depth range of the FMA division proof
-constexpr int TILE_BYTES = 3 * 32 * 128;               // 3 channels x 32 columns x 32 floats
+constexpr int LIST_CAP = 128;                          // per-warp ring of 16-bit work-list entries
+constexpr int OUTSIDE = -(1 << 30);                    // table sentinel: projection outside the crop
 constexpr unsigned DEFAULT_FOCAL_BITS = 0x43716B85u;   // 241.42f
+constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -88,6 +102,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// L2 prefetch of a byte range (multiple of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     uint32_t done;
     do {
@@ -100,20 +118,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
             : "memory");
     } while (!done);
 }
-// 5-D TMA tensor store shared -> global (bulk async-group completion).
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tmap, const void* src, int c0, int c1,
-                                             int c2, int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
-            reinterpret_cast<uint64_t>(tmap)),
-        "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
+__device__ __forceinline__ void st_f4(float* p, const float4& v) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
 }
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() {
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ float warp_min(float v) {
     float r;
     asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
@@ -137,23 +145,29 @@ __device__ __forceinline__ float div_fixed(float a, float b, float y) {
 }
 
 // ---------------------------------------------------------------- shared memory
-template <int R>
+template <int R, int LAYOUT>
 struct __align__(16) FrameShared {
-    float red[NWARP][8];            // per-warp partial min xyz / max xyz (6 used)
+    static constexpr int YS = (LAYOUT == 0) ? R : R + 1;   // (c,z,y,x): yt rows are read down a column
+    int   at[R * R];                // [s][f]: 4*(pix_x - left), OUTSIDE when not in the crop
+    int   yt[R * YS];               // CXYZ [y][z], CZYX [z][y]: 4*bw*(pix_y - top), or OUTSIDE
+    short yr[R * YS];               // same indexing: pix_y - top (pass 2 only)
     float vx[R], vy[R], vz[R];      // voxel centres per axis
-    float coef[R];                  // -focal / vz
-    int   xt[R * R];                // [s][f]: 4*(pix_x - left), negative when outside the crop
-    int   yt[R * R];                // CXYZ: [y][z], CZYX: [z][y]: pix_y - top, negative when outside
+    float red[NWARP][8];            // per-warp partial min xyz / max xyz (6 used)
+    unsigned short list[NWARP][LIST_CAP];   // per-warp ring lists: groups with near-surface voxels
     unsigned long long bar;         // crop TMA completion barrier
+    unsigned int done;              // warps that have finished reading the crop (running count)
+    unsigned int pad_;
+    float zero[4];                  // zero[3] sits right below the crop: target of "outside" gathers
 };
 
 struct Frame {
-    int l, t, r, b, bw, bh, n;
+    int l, t, r, b, bw, bh, n, n_pad;
+    const float* crop;
+    bool staged;
 };
 
 // per-frame constants of the voxel evaluation
 struct VoxConst {
-    int   bw4;       // 4 * crop width (byte stride of a crop row)
     int   ix;        // MAGIC_I + left:  int_as_float(ix + (px-left)) == MAGIC_F + px
     int   iy;        // MAGIC_I + top
     float kx;        // MAGIC_F + cx
@@ -165,34 +179,120 @@ struct VoxConst {
     float t_far;     // |v_z - w_z| above this forces truncation; +inf disables the shortcut
 };
 
+__device__ __forceinline__ Frame load_frame(const BatchArgs& a, int f) {
+    // frame record (pre/tsdf_numba.py:122-129)
+    const int* h = a.headers + 6 * (size_t)f;
+    Frame fr;
+    fr.l = __ldg(h + 2); fr.t = __ldg(h + 3); fr.r = __ldg(h + 4); fr.b = __ldg(h + 5);
+    fr.bw = fr.r - fr.l;
+    fr.bh = fr.b - fr.t;
+    const int lim = 1 << 22;
+    const bool bad = fr.bw <= 0 || fr.bh <= 0 || fr.bw > 32767 || fr.bh > 32767 ||
+                     (long long)fr.bw * fr.bh > (1ll << 26) ||      // byte offsets stay below 2^28
+                     fr.l <= -lim || fr.t <= -lim || fr.r >= lim || fr.b >= lim;
+    if (bad) { fr.bw = 0; fr.bh = 0; }
+    fr.n = fr.bw * fr.bh;
+    fr.n_pad = (fr.n + 3) & ~3;
+    fr.crop = a.depth + __ldg(a.offsets + f);
+    fr.staged = fr.n_pad > 0 && fr.n_pad <= a.cap_floats;     // CTA-uniform
+    return fr;
+}
+
 // ---------------------------------------------------------------- bounding box scan
-// pre/tsdf_numba.py:83-96, one warp per crop row.  `crop` is shared memory when STAGED.
-template <bool STAGED, bool DEFF>
-__device__ __forceinline__ void bbox_scan(const float* __restrict__ crop, const Frame& fr, float focal,
-                                          float yf, bool focal_ok, int cx, int cy, float (&mn)[3],
-                                          float (&mx)[3]) {
+// pre/tsdf_numba.py:83-96 without evaluating every pixel.  q = RN(d/f) is monotone in d,
+// X = RN(q*(x-cx)) is monotone in q for a fixed column and Y = RN(-q*(y-cy)) for a fixed row,
+// so the extremes of X (Y) over any set of pixels of one column (row) are attained at the
+// set's smallest and largest valid depth: the scan only tracks min/max valid depth per column
+// (in registers, 4 columns per lane and 128-column panel) and per lane and row, and
+// back-projects those.  The result is the same min/max the reference computes over all valid
+// pixels.  Invalid pixels (|d| < 1, pre/tsdf_numba.py:87) become NaN, which fminf/fmaxf skip.
+// One warp per crop row, four rows in flight per warp; reads global memory (L2) directly.
+template <bool DEFF>
+__device__ __forceinline__ float div_focal(float d, float focal, float yf, bool focal_ok) {
+    if (!(fabsf(d) >= BIG_DEPTH) && (DEFF || focal_ok)) return div_fixed<DEFF>(d, focal, yf);
+    return __fdiv_rn(d, focal);
+}
+
+template <bool DEFF>
+__device__ __forceinline__ void bbox_scan(const Frame& fr, float focal, float yf, bool focal_ok, int cx,
+                                          int cy, float (&mn)[3], float (&mx)[3]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float kx = MAGIC_F + (float)cx;
     const float ky = MAGIC_F + (float)cy;
-    for (int row = warp; row < fr.bh; row += NWARP) {
-        const float fy = __fsub_rn(__int_as_float(MAGIC_I + row + fr.t), ky);        // (y - cy), exact
-        const float* p = crop + (size_t)row * fr.bw;
-        float fx = __fsub_rn(__int_as_float(MAGIC_I + lane + fr.l), kx);             // (x - cx), exact
-        for (int col = lane; col < fr.bw; col += 32, fx = __fadd_rn(fx, 32.0f)) {
-            const float d = STAGED ? p[col] : __ldg(p + col);
-            const float ad = fabsf(d);
-            if (!(ad < 1.0f)) {
-                float q;
-                if (ad < BIG_DEPTH && (DEFF || focal_ok)) q = div_fixed<DEFF>(d, focal, yf);
-                else q = __fdiv_rn(d, focal);
-                const float X = __fmul_rn(q, fx);
-                const float Y = __fmul_rn(-q, fy);
-                const float Z = -d;
-                mn[0] = fminf(mn[0], X); mx[0] = fmaxf(mx[0], X);
-                mn[1] = fminf(mn[1], Y); mx[1] = fmaxf(mx[1], Y);
-                mn[2] = fminf(mn[2], Z); mx[2] = fmaxf(mx[2], Z);
+    const float* __restrict__ crop = fr.crop;
+    float dlo = INFINITY, dhi = -INFINITY;           // valid depth extremes (Z = -d)
+    for (int panel = 0; panel < fr.bw; panel += 128) {
+        bool inb[4];
+        float cmin[4], cmax[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            inb[j] = panel + lane + 32 * j < fr.bw;
+            cmin[j] = INFINITY; cmax[j] = -INFINITY;
+        }
+        // one row: this lane's (up to) 4 pixels
+        auto row_step = [&](int row, const float (&d)[4]) {
+            float rmin = INFINITY, rmax = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float v = fabsf(d[j]) < 1.0f ? __int_as_float(0x7fc00000) : d[j];
+                cmin[j] = fminf(cmin[j], v); cmax[j] = fmaxf(cmax[j], v);
+                rmin = fminf(rmin, v); rmax = fmaxf(rmax, v);
+            }
+            const bool has = rmin <= rmax;
+            const float a0 = has ? rmin : __int_as_float(0x7fc00000);
+            const float a1 = has ? rmax : __int_as_float(0x7fc00000);
+            const float fy = __fsub_rn(__int_as_float(MAGIC_I + row + fr.t), ky);   // (y - cy), exact
+            const float y1 = __fmul_rn(-div_focal<DEFF>(a0, focal, yf, focal_ok), fy);
+            const float y2 = __fmul_rn(-div_focal<DEFF>(a1, focal, yf, focal_ok), fy);
+            mn[1] = fminf(mn[1], fminf(y1, y2)); mx[1] = fmaxf(mx[1], fmaxf(y1, y2));
+        };
+        int row = warp;
+        for (; row + 3 * NWARP < fr.bh; row += 4 * NWARP) {
+            float d[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float* p = crop + (size_t)(row + u * NWARP) * fr.bw + panel + lane;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[u][j] = inb[j] ? __ldg(p + 32 * j) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) row_step(row + u * NWARP, d[u]);
+        }
+        for (; row < fr.bh; row += NWARP) {
+            float d[4];
+            const float* p = crop + (size_t)row * fr.bw + panel + lane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = inb[j] ? __ldg(p + 32 * j) : 0.0f;
+            row_step(row, d);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (cmin[j] <= cmax[j]) {                 // this lane's column has a valid pixel in its rows
+                const float fx = __fsub_rn(__int_as_float(MAGIC_I + panel + lane + 32 * j + fr.l), kx);   // (x - cx)
+                const float x1 = __fmul_rn(div_focal<DEFF>(cmin[j], focal, yf, focal_ok), fx);
+                const float x2 = __fmul_rn(div_focal<DEFF>(cmax[j], focal, yf, focal_ok), fx);
+                mn[0] = fminf(mn[0], fminf(x1, x2)); mx[0] = fmaxf(mx[0], fmaxf(x1, x2));
+                dlo = fminf(dlo, cmin[j]); dhi = fmaxf(dhi, cmax[j]);
             }
         }
+    }
+    if (dlo <= dhi) { mn[2] = fminf(mn[2], -dhi); mx[2] = fmaxf(mx[2], -dlo); }
+}
+
+// scan + warp reduction; lane 0 leaves the warp's partial in shared memory
+template <bool DEFF>
+__device__ __forceinline__ void bbox_partial(const Frame& fr, const BatchArgs& a, float yf, bool focal_ok,
+                                             float (*red)[8]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float mn[3], mx[3];
+    mn[0] = mn[1] = mn[2] = SENTINEL;
+    mx[0] = mx[1] = mx[2] = -SENTINEL;
+    bbox_scan<DEFF>(fr, a.focal, yf, focal_ok, a.center_x, a.center_y, mn, mx);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { mn[c] = warp_min(mn[c]); mx[c] = warp_max(mx[c]); }
+    if (lane == 0) {
+        *reinterpret_cast<float4*>(&red[warp][0]) = make_float4(mn[0], mn[1], mn[2], mx[0]);
+        *reinterpret_cast<float2*>(&red[warp][4]) = make_float2(mx[1], mx[2]);
     }
 }
 
@@ -230,150 +330,256 @@ __device__ __forceinline__ Tsdf3 eval_fast(float d, float fx, float fy, float vx
     float tz = div_fixed<false>(fabsf(sz), k.trunc, k.yt);
     const float s = __fadd_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)), __fmul_rn(tz, tz));
     if (s > THR_SQ) { tx = 1.0f; ty = 1.0f; tz = 1.0f; }
-    if (sz < 0.0f) { tx = -tx; ty = -ty; tz = -tz; }      // -d > v_z  <=>  v_z + d < 0
-    Tsdf3 o; o.x = tx; o.y = ty; o.z = tz;
+    // -d > v_z  <=>  v_z + d < 0: flip the sign bit with the one of sz
+    const int sg = __float_as_int(sz) & 0x80000000;
+    Tsdf3 o;
+    o.x = __int_as_float(__float_as_int(tx) ^ sg);
+    o.y = __int_as_float(__float_as_int(ty) ^ sg);
+    o.z = __int_as_float(__float_as_int(tz) ^ sg);
     return o;
 }
 
-// One frame's voxel loop.  F = fastest output axis (z for CXYZ, x for CZYX), S = slowest
-// (x / z), M = y.  A tile is 8 (S) x 4 (M) columns x 32 (F) voxels; warp w owns the 4 voxels
-// F = 32*chunk + 4*w .. +3 of the tile's 32 columns (lane = 4*s_local + m_local).
+// byte offset into the crop; negative <=> either table entry is OUTSIDE; reads as "no depth"
+template <bool STAGED>
+__device__ __forceinline__ float gather_depth(const float* __restrict__ crop, int off) {
+    if (STAGED) {
+        // the word right below the staged crop is 0.0f (FrameShared::zero[3])
+        off = max(off, -4);
+        return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(crop) + off);
+    }
+    if (off < 0) return 0.0f;
+    return __ldg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(crop) + off));
+}
+
+// Classification of one voxel (pass 1).
+//   value 0        : projection outside the crop or |depth| < 1 (pre/process.py:159,167)
+//   value +-1      : farther than trunc from the surface along z alone: t_z > 1, so the
+//                    Euclidean truncation fires (pre/process.py:180-185) and the result is +-1
+//                    by the side of the surface (:191-194)
+//   near           : needs the full evaluation (value 0 for now)
+#define DTSDF_CLASSIFY(D, VZ, OUT, NEAR)                                                          \
+    {                                                                                             \
+        const float sz_ = __fadd_rn(VZ, D);                     /* v_z - w_z, w_z = -d */         \
+        const bool ok_ = !(fabsf(D) < 1.0f);                                                      \
+        const bool far_ = fabsf(sz_) > t_far;                                                     \
+        const float one_ = __int_as_float((__float_as_int(sz_) & 0x80000000) | 0x3F800000);       \
+        OUT = (ok_ && far_) ? one_ : 0.0f;                                                        \
+        NEAR = NEAR || (ok_ && !far_);                                                            \
+    }
+
+// Lane geometry of the voxel loop for an R^3 grid
+template <int R>
+struct LaneMap {
+    static constexpr int LPR = R / 4;               // lanes per F-row (groups of 4 voxels)
+    static constexpr int ROWS = 32 / LPR;           // slow-axis rows per warp
+    static constexpr int ACTIVE = ROWS * LPR;       // 32 for R = 32, 64; 24 for R = 48
+    static constexpr int NSG = R / ROWS;            // slow-axis row groups per frame
+    static constexpr int MSTEPS = R / NWARP;        // middle-axis positions per warp and row group
+    static_assert(R % 4 == 0 && R % ROWS == 0 && R % NWARP == 0, "unsupported grid size");
+    static_assert(R <= 64 && NSG <= 32, "work-list entries are 5 + 6 + 5 bits");
+};
+
+// pass 2: full evaluation of n (<= 32) listed groups starting at ring position `head`
 template <int R, int LAYOUT, bool STAGED, bool FAST, bool DEFF>
-__device__ __forceinline__ void voxel_tiles(const float* __restrict__ crop,
-                                            const FrameShared<R>* __restrict__ sh, const VoxConst& k,
-                                            const CUtensorMap* tmap, unsigned char* tiles, int frame,
-                                            unsigned& gstep) {
-    constexpr int FCH = (R + 31) / 32;
-    constexpr int NM = R / 4;
-    constexpr int NSTEPS = (R / 8) * NM * FCH;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#pragma unroll 1
-    for (int ts = 0; ts < NSTEPS; ++ts) {
-        const int fch = ts % FCH;
-        const int mg = (ts / FCH) % NM;
-        const int sg = ts / (FCH * NM);
-        const int s = sg * 8 + (lane >> 2);
-        const int m = mg * 4 + (lane & 3);
-        const int f0 = fch * 32 + 4 * warp;
-        float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f}, o2[4] = {0.f, 0.f, 0.f, 0.f};
-        if (f0 < R) {
-            const int4 xa = *reinterpret_cast<const int4*>(&sh->xt[s * R + f0]);
-            int pa[4] = {xa.x, xa.y, xa.z, xa.w};
-            int pb[4];
-            float vxj[4], vyj[4], vzj[4];
-            if (LAYOUT == 0) {              // out[c][x][y][z]: S = x, F = z
-                const int4 yb = *reinterpret_cast<const int4*>(&sh->yt[m * R + f0]);
-                pb[0] = yb.x; pb[1] = yb.y; pb[2] = yb.z; pb[3] = yb.w;
-                const float4 vz4 = *reinterpret_cast<const float4*>(&sh->vz[f0]);
-                vzj[0] = vz4.x; vzj[1] = vz4.y; vzj[2] = vz4.z; vzj[3] = vz4.w;
-                const float x = sh->vx[s], y = sh->vy[m];
+__device__ __forceinline__ void eval_listed(const float* __restrict__ crop,
+                                            const FrameShared<R, LAYOUT>* __restrict__ sh, const VoxConst& k,
+                                            float* __restrict__ out, const unsigned short* list, int head, int n) {
+    using LM = LaneMap<R>;
+    constexpr int YS = FrameShared<R, LAYOUT>::YS;
+    constexpr int CH = R * R * R;
+    const int lane = threadIdx.x & 31;
+    if (lane < n) {
+        const int ent = list[(head + lane) & (LIST_CAP - 1)];
+        const int L = ent & 31, m = (ent >> 5) & 63, sg = ent >> 11;
+        const int s = sg * LM::ROWS + L / LM::LPR;
+        const int f0 = 4 * (L % LM::LPR);
+        const int4 A = *reinterpret_cast<const int4*>(&sh->at[s * R + f0]);
+        const int a4[4] = {A.x, A.y, A.z, A.w};
+        int b4[4], row4[4];
+        float vx4[4], vz4[4];
+        const float vy = sh->vy[m];
+        if (LAYOUT == 0) {
+            const int4 B = *reinterpret_cast<const int4*>(&sh->yt[m * YS + f0]);
+            b4[0] = B.x; b4[1] = B.y; b4[2] = B.z; b4[3] = B.w;
+            const short4 rr = *reinterpret_cast<const short4*>(&sh->yr[m * YS + f0]);
+            row4[0] = rr.x; row4[1] = rr.y; row4[2] = rr.z; row4[3] = rr.w;
+            const float4 z4 = *reinterpret_cast<const float4*>(&sh->vz[f0]);
+            vz4[0] = z4.x; vz4[1] = z4.y; vz4[2] = z4.z; vz4[3] = z4.w;
+            const float x1 = sh->vx[s];
+            vx4[0] = vx4[1] = vx4[2] = vx4[3] = x1;
+        } else {
+            const int b1 = sh->yt[s * YS + m];
+            const int r1 = sh->yr[s * YS + m];
+            const float z1 = sh->vz[s];
+            const float4 x4 = *reinterpret_cast<const float4*>(&sh->vx[f0]);
+            vx4[0] = x4.x; vx4[1] = x4.y; vx4[2] = x4.z; vx4[3] = x4.w;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { vxj[j] = x; vyj[j] = y; }
-            } else {                        // out[c][z][y][x]: S = z, F = x
-                const int yb = sh->yt[s * R + m];
-                const float4 vx4 = *reinterpret_cast<const float4*>(&sh->vx[f0]);
-                vxj[0] = vx4.x; vxj[1] = vx4.y; vxj[2] = vx4.z; vxj[3] = vx4.w;
-                const float y = sh->vy[m], z = sh->vz[s];
+            for (int j = 0; j < 4; ++j) { b4[j] = b1; row4[j] = r1; vz4[j] = z1; }
+        }
+        float o0[4], o1[4], o2[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { pb[j] = yb; vyj[j] = y; vzj[j] = z; }
-            }
-            float d[4], sz[4];
-            bool nearj[4];
-            bool any_near = false;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool inside = (pa[j] | pb[j]) >= 0;
-                const int off = inside ? pb[j] * k.bw4 + pa[j] : 0;
-                const float* q = reinterpret_cast<const float*>(reinterpret_cast<const char*>(crop) + off);
-                d[j] = STAGED ? *q : __ldg(q);
-                const bool ok = inside && !(fabsf(d[j]) < 1.0f);          // pre/process.py:159,167
-                sz[j] = __fadd_rn(vzj[j], d[j]);                          // v_z - w_z, w_z = -d
-                const bool far = fabsf(sz[j]) > k.t_far;
-                // far from the surface along z alone: t_z > 1, so the Euclidean truncation
-                // fires (pre/process.py:180-185) and the result is +-1 by the side of the surface
-                const float one = __int_as_float((__float_as_int(sz[j]) & 0x80000000) | 0x3F800000);
-                const float v = (ok && far) ? one : 0.0f;
-                o0[j] = v; o1[j] = v; o2[j] = v;
-                nearj[j] = ok && !far;
-                any_near |= nearj[j];
-            }
-            if (__any_sync(0xffffffffu, any_near)) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (nearj[j]) {
-                        const float fx = __fsub_rn(__int_as_float(k.ix + (pa[j] >> 2)), k.kx);   //  (pix_x - cx)
-                        const float fy = __fsub_rn(k.ky, __int_as_float(k.iy + pb[j]));          // -(pix_y - cy)
-                        Tsdf3 t;
-                        if (FAST && fabsf(d[j]) < BIG_DEPTH) t = eval_fast<DEFF>(d[j], fx, fy, vxj[j], vyj[j], sz[j], k);
-                        else t = eval_generic(d[j], fx, fy, vxj[j], vyj[j], vzj[j], sz[j], k.focal, k.trunc);
-                        o0[j] = t.x; o1[j] = t.y; o2[j] = t.z;
-                    }
+        for (int j = 0; j < 4; ++j) {
+            const float d = gather_depth<STAGED>(crop, a4[j] + b4[j]);
+            const float sz = __fadd_rn(vz4[j], d);
+            const bool ok = !(fabsf(d) < 1.0f);
+            const bool far = fabsf(sz) > k.t_far;
+            float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+            if (ok) {
+                if (far) {
+                    t0 = t1 = t2 = __int_as_float((__float_as_int(sz) & 0x80000000) | 0x3F800000);
+                } else {
+                    const float fx = __fsub_rn(__int_as_float(k.ix + (a4[j] >> 2)), k.kx);   //  (pix_x - cx)
+                    const float fy = __fsub_rn(k.ky, __int_as_float(k.iy + row4[j]));        // -(pix_y - cy)
+                    Tsdf3 t;
+                    if (FAST && fabsf(d) < BIG_DEPTH) t = eval_fast<DEFF>(d, fx, fy, vx4[j], vy, sz, k);
+                    else t = eval_generic(d, fx, fy, vx4[j], vy, vz4[j], sz, k.focal, k.trunc);
+                    t0 = t.x; t1 = t.y; t2 = t.z;
                 }
             }
+            o0[j] = t0; o1[j] = t1; o2[j] = t2;
         }
-        // 128B-swizzled tile: row = lane (column of the tile), 16-byte chunk = warp ^ (row & 7)
-        unsigned char* buf = tiles + (gstep & 1u) * TILE_BYTES;
-        float4* dst = reinterpret_cast<float4*>(buf + lane * 128 + ((warp ^ (lane & 7)) << 4));
-        dst[0] = make_float4(o0[0], o0[1], o0[2], o0[3]);
-        dst[256] = make_float4(o1[0], o1[1], o1[2], o1[3]);      // + 4096 bytes: channel 1
-        dst[512] = make_float4(o2[0], o2[1], o2[2], o2[3]);      // + 8192 bytes: channel 2
-        fence_proxy_async();                  // generic-proxy writes -> visible to the TMA engine
-        if (tid == 0) bulk_wait_read_all();   // the other buffer's store has finished reading it
-        __syncthreads();
-        if (tid == 0) {
-            tma_store_5d(tmap, buf, fch * 32, mg * 4, sg * 8, 0, frame);
-            bulk_commit();
-        }
-        ++gstep;
+        float* p = out + ((size_t)(s * R + m) * R + f0);
+        st_f4(p, make_float4(o0[0], o0[1], o0[2], o0[3]));
+        st_f4(p + CH, make_float4(o1[0], o1[1], o1[2], o1[3]));
+        st_f4(p + 2 * CH, make_float4(o2[0], o2[1], o2[2], o2[3]));
     }
 }
 
+// One frame's voxel loop (both passes).  The warps run independently.  Warp w handles the
+// middle-axis positions m = w, w + 8, ... of every slow-axis row group, so every warp sees every
+// part of the volume (balanced pass-2 work).
+template <int R, int LAYOUT, bool STAGED, bool FAST, bool DEFF>
+__device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
+                                             FrameShared<R, LAYOUT>* __restrict__ sh, const VoxConst& k,
+                                             float* __restrict__ out) {
+    using LM = LaneMap<R>;
+    constexpr int YS = FrameShared<R, LAYOUT>::YS;
+    constexpr int CH = R * R * R;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool active = lane < LM::ACTIVE;
+    const int fg = lane % LM::LPR;
+    const int sr = active ? lane / LM::LPR : LM::ROWS - 1;
+    const int f0 = 4 * fg;
+    const float t_far = k.t_far;
+    unsigned short* list = sh->list[warp];
+    const unsigned lt = (1u << lane) - 1u;
+    int head = 0, tail = 0;
+
+    float4 vzf = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (LAYOUT == 0) vzf = *reinterpret_cast<const float4*>(&sh->vz[f0]);
+
+#pragma unroll 1
+    for (int sg = 0; sg < LM::NSG; ++sg) {
+        const int s = sg * LM::ROWS + sr;
+        const int4 A = *reinterpret_cast<const int4*>(&sh->at[s * R + f0]);
+        if (LAYOUT != 0) {
+            const float z1 = sh->vz[s];
+            vzf = make_float4(z1, z1, z1, z1);
+        }
+        float* const obase = out + ((size_t)s * R * R + f0);
+        const int ebase = (sg << 11) | lane;
+#pragma unroll
+        for (int ks = 0; ks < LM::MSTEPS; ks += 2) {
+            const int m0 = warp + NWARP * ks, m1 = m0 + NWARP;
+            int4 B0, B1;
+            if (LAYOUT == 0) {
+                B0 = *reinterpret_cast<const int4*>(&sh->yt[m0 * YS + f0]);
+                B1 = *reinterpret_cast<const int4*>(&sh->yt[m1 * YS + f0]);
+            } else {
+                const int y0 = sh->yt[s * YS + m0], y1 = sh->yt[s * YS + m1];
+                B0 = make_int4(y0, y0, y0, y0);
+                B1 = make_int4(y1, y1, y1, y1);
+            }
+            const float d00 = gather_depth<STAGED>(crop, A.x + B0.x);
+            const float d01 = gather_depth<STAGED>(crop, A.y + B0.y);
+            const float d02 = gather_depth<STAGED>(crop, A.z + B0.z);
+            const float d03 = gather_depth<STAGED>(crop, A.w + B0.w);
+            const float d10 = gather_depth<STAGED>(crop, A.x + B1.x);
+            const float d11 = gather_depth<STAGED>(crop, A.y + B1.y);
+            const float d12 = gather_depth<STAGED>(crop, A.z + B1.z);
+            const float d13 = gather_depth<STAGED>(crop, A.w + B1.w);
+            float4 v0, v1;
+            bool n0 = false, n1 = false;
+            DTSDF_CLASSIFY(d00, vzf.x, v0.x, n0)
+            DTSDF_CLASSIFY(d01, vzf.y, v0.y, n0)
+            DTSDF_CLASSIFY(d02, vzf.z, v0.z, n0)
+            DTSDF_CLASSIFY(d03, vzf.w, v0.w, n0)
+            DTSDF_CLASSIFY(d10, vzf.x, v1.x, n1)
+            DTSDF_CLASSIFY(d11, vzf.y, v1.y, n1)
+            DTSDF_CLASSIFY(d12, vzf.z, v1.z, n1)
+            DTSDF_CLASSIFY(d13, vzf.w, v1.w, n1)
+            if (active) {
+                float* p0 = obase + m0 * R;
+                float* p1 = obase + m1 * R;
+                st_f4(p0, v0); st_f4(p0 + CH, v0); st_f4(p0 + 2 * CH, v0);
+                st_f4(p1, v1); st_f4(p1 + CH, v1); st_f4(p1 + 2 * CH, v1);
+            }
+            n0 = n0 && active;
+            n1 = n1 && active;
+            const unsigned bal0 = __ballot_sync(FULL, n0);
+            const unsigned bal1 = __ballot_sync(FULL, n1);
+            if (n0) list[(tail + __popc(bal0 & lt)) & (LIST_CAP - 1)] = (unsigned short)(ebase | (m0 << 5));
+            tail += __popc(bal0);
+            if (n1) list[(tail + __popc(bal1 & lt)) & (LIST_CAP - 1)] = (unsigned short)(ebase | (m1 << 5));
+            tail += __popc(bal1);
+            while (tail - head >= 32) {              // warp-uniform
+                __syncwarp();                        // list entries and the pass-1 stores are ordered before pass 2
+                eval_listed<R, LAYOUT, STAGED, FAST, DEFF>(crop, sh, k, out, list, head, 32);
+                head += 32;
+            }
+        }
+    }
+    __syncwarp();
+    eval_listed<R, LAYOUT, STAGED, FAST, DEFF>(crop, sh, k, out, list, head, tail - head);
+}
+#undef DTSDF_CLASSIFY
+
 // ---------------------------------------------------------------- fused kernel
 template <int R, int LAYOUT, bool DEFF>
-__global__ void __launch_bounds__(NT, 2) dtsdf_fused_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                            const BatchArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* tiles = smem_raw;                                           // 2 x TILE_BYTES, 1024-aligned
-    FrameShared<R>* sh = reinterpret_cast<FrameShared<R>*>(smem_raw + 2 * TILE_BYTES);
-    float* crop_s = reinterpret_cast<float*>(smem_raw + 2 * TILE_BYTES + sizeof(FrameShared<R>));
+__global__ void __launch_bounds__(NT, 3) dtsdf_fused_kernel(const BatchArgs a) {
+    using FS = FrameShared<R, LAYOUT>;
+    constexpr int YS = FS::YS;
+    static_assert(sizeof(FS) % 16 == 0 && offsetof(FS, zero) + 16 == sizeof(FS), "zero pad must touch the crop");
+    static_assert(LaneMap<R>::MSTEPS % 2 == 0, "the sweep is unrolled by two");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FS* sh = reinterpret_cast<FS*>(smem_raw);
+    float* crop_s = reinterpret_cast<float*>(smem_raw + sizeof(FS));
     const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31;
 
     if (tid == 0) {
         mbar_init(&sh->bar, 1);
         fence_mbar_init();
+        sh->done = 0u;
+        sh->zero[0] = sh->zero[1] = sh->zero[2] = sh->zero[3] = 0.0f;
     }
-    __syncthreads();
     uint32_t parity = 0;
-    unsigned gstep = 0;
     const float yf = __frcp_rn(a.focal);
     const bool focal_ok = a.focal >= 0x1p-30f && a.focal <= 0x1p30f;
+    const bool scan = a.bbox_mode == 0;              // DTSDF_BBOX_PIXELS
 
-    for (int f = blockIdx.x; f < a.n_frames; f += gridDim.x) {
-        // ---- frame record (pre/tsdf_numba.py:122-129)
-        const int* h = a.headers + 6 * (size_t)f;
-        Frame fr;
-        fr.l = __ldg(h + 2); fr.t = __ldg(h + 3); fr.r = __ldg(h + 4); fr.b = __ldg(h + 5);
-        fr.bw = fr.r - fr.l;
-        fr.bh = fr.b - fr.t;
-        const int lim = 1 << 22;
-        const bool bad = fr.bw <= 0 || fr.bh <= 0 || fr.bw > 32767 || fr.bh > 32767 ||
-                         fr.l <= -lim || fr.t <= -lim || fr.r >= lim || fr.b >= lim;
-        if (bad) { fr.bw = 0; fr.bh = 0; }
-        fr.n = fr.bw * fr.bh;
-        const float* crop_g = a.depth + __ldg(a.offsets + f);
-        const int n_pad = (fr.n + 3) & ~3;
-        const bool staged = n_pad > 0 && n_pad <= a.cap_floats;     // CTA-uniform
+    int f = blockIdx.x;
+    if (f >= a.n_frames) return;
+    Frame fr = load_frame(a, f);
+    __syncthreads();                                  // barrier initialised
+    if (fr.staged && tid == 0) {
+        mbar_expect_tx(&sh->bar, (uint32_t)fr.n_pad * 4u);
+        bulk_g2s(crop_s, fr.crop, (uint32_t)fr.n_pad * 4u, &sh->bar);
+    }
+    if (scan) bbox_partial<DEFF>(fr, a, yf, focal_ok, sh->red);
 
-        // ---- 1. TMA bulk copy of the crop into shared memory
-        if (staged && tid == 0) {
-            fence_proxy_async();      // earlier generic-proxy reads of crop_s happen-before the async write
-            mbar_expect_tx(&sh->bar, (uint32_t)n_pad * 4u);
-            bulk_g2s(crop_s, crop_g, (uint32_t)n_pad * 4u, &sh->bar);
+    for (;;) {
+        __syncthreads();      // (A) bbox partials are in; nobody reads the previous frame's tables any more
+
+        // ---- next frame's record early: its latency hides behind the table phase
+        const int fn = f + (int)gridDim.x;
+        const bool more = fn < a.n_frames;
+        Frame frn = fr;
+        if (more) {
+            frn = load_frame(a, fn);
         }
-        bool landed = false;
 
-        // ---- 2. bounding box (pre/tsdf_numba.py:75-116,140-141) or caller-supplied
+        // ---- bounding box (pre/tsdf_numba.py:75-116,140-141) or caller-supplied
         float ox, oy, oz, voxel_len, trunc;
         if (a.bbox_mode == 2) {       // DTSDF_BBOX_GRID: pre/process.py:122 arguments
             const float* g = a.aux + 5 * (size_t)f;
@@ -391,23 +597,9 @@ __global__ void __launch_bounds__(NT, 2) dtsdf_fused_kernel(const __grid_constan
             }
         } else {
             float mn[3], mx[3];
-            if (a.bbox_mode == 0) {   // DTSDF_BBOX_PIXELS
+            if (scan) {
                 mn[0] = mn[1] = mn[2] = SENTINEL;
                 mx[0] = mx[1] = mx[2] = -SENTINEL;
-                if (staged) {
-                    mbar_wait(&sh->bar, parity);
-                    landed = true;
-                    bbox_scan<true, DEFF>(crop_s, fr, a.focal, yf, focal_ok, a.center_x, a.center_y, mn, mx);
-                } else {
-                    bbox_scan<false, DEFF>(crop_g, fr, a.focal, yf, focal_ok, a.center_x, a.center_y, mn, mx);
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) { mn[c] = warp_min(mn[c]); mx[c] = warp_max(mx[c]); }
-                if (lane == 0) {
-                    *reinterpret_cast<float4*>(&sh->red[warp][0]) = make_float4(mn[0], mn[1], mn[2], mx[0]);
-                    *reinterpret_cast<float2*>(&sh->red[warp][4]) = make_float2(mx[1], mx[2]);
-                }
-                __syncthreads();
 #pragma unroll
                 for (int w = 0; w < NWARP; ++w) {
                     const float4 p = *reinterpret_cast<const float4*>(&sh->red[w][0]);
@@ -443,38 +635,42 @@ __global__ void __launch_bounds__(NT, 2) dtsdf_fused_kernel(const __grid_constan
             }
         }
 
-        // ---- 3. per-axis voxel centres, -focal/v_z, and the two projection tables
-        //         (pre/process.py:150-159 == pre/tsdf_numba.py:26-32,36)
+        // ---- per-axis voxel centres and the two projection tables
+        //      (pre/process.py:150-159 == pre/tsdf_numba.py:26-32,36)
         if (tid < R) {
             const float sft = __fmul_rn((float)tid, voxel_len);
-            const float vz = __fadd_rn(oz, sft);
             sh->vx[tid] = __fadd_rn(ox, sft);
             sh->vy[tid] = __fadd_rn(oy, sft);
-            sh->vz[tid] = vz;
-            sh->coef[tid] = __fdiv_rn(-a.focal, vz);
+            sh->vz[tid] = __fadd_rn(oz, sft);
         }
-        __syncthreads();
-        for (int e = tid; e < R * R; e += NT) {
-            const int ea = e / R, eb = e % R;
-            // xt[s][f]: CXYZ (x = ea, z = eb), CZYX (z = ea, x = eb)
-            // yt:       CXYZ [y = ea][z = eb], CZYX [z = ea][y = eb]
-            const int zi = (LAYOUT == 0) ? eb : ea;
-            const int ti = (LAYOUT == 0) ? ea : eb;      // x index for xt, y index for yt
-            const float coeff = sh->coef[zi];
-            const float fpx = __fadd_rn(__fmul_rn(sh->vx[ti], coeff), (float)a.center_x);
-            const float fpy = __fadd_rn(__fmul_rn(-sh->vy[ti], coeff), (float)a.center_y);
-            const int px = __float2int_rz(fpx);          // int(): truncation toward zero
-            const int py = __float2int_rz(fpy);
-            const bool okx = fabsf(fpx) < 2e9f && px >= fr.l && px < fr.r;   // non-finite -> outside
-            const bool oky = fabsf(fpy) < 2e9f && py >= fr.t && py < fr.b;   // (bad header: empty ranges)
-            sh->xt[e] = okx ? 4 * (px - fr.l) : (int)0x80000000;
-            sh->yt[e] = oky ? (py - fr.t) : (int)0x80000000;
+        {
+            // entry e: zi = e % R is the z index, ti = e / R the x (at) / y (yt) index.  With
+            // NT a multiple of R the z index, and with it the division, is the same for every
+            // entry of a thread.
+            constexpr bool HOIST = (NT % R) == 0;
+            float coeff_h = 0.0f;
+            if (HOIST) coeff_h = __fdiv_rn(-a.focal, __fadd_rn(oz, __fmul_rn((float)(tid % R), voxel_len)));
+#pragma unroll 2
+            for (int e = tid; e < R * R; e += NT) {
+                const int ti = e / R, zi = e % R;
+                const float coeff = HOIST ? coeff_h
+                                          : __fdiv_rn(-a.focal, __fadd_rn(oz, __fmul_rn((float)zi, voxel_len)));
+                const float sft = __fmul_rn((float)ti, voxel_len);
+                const float fpx = __fadd_rn(__fmul_rn(__fadd_rn(ox, sft), coeff), (float)a.center_x);
+                const float fpy = __fadd_rn(__fmul_rn(-__fadd_rn(oy, sft), coeff), (float)a.center_y);
+                const int px = __float2int_rz(fpx);          // int(): truncation toward zero
+                const int py = __float2int_rz(fpy);
+                const bool okx = fabsf(fpx) < 2e9f && px >= fr.l && px < fr.r;   // non-finite -> outside
+                const bool oky = fabsf(fpy) < 2e9f && py >= fr.t && py < fr.b;   // (bad header: empty ranges)
+                // at[s][f]: CXYZ s = x, f = z; CZYX s = z, f = x.   yt: CXYZ [y][z]; CZYX [z][y]
+                const int ia = (LAYOUT == 0) ? ti * R + zi : zi * R + ti;
+                const int iy = (LAYOUT == 0) ? ti * YS + zi : zi * YS + ti;
+                sh->at[ia] = okx ? 4 * (px - fr.l) : OUTSIDE;
+                sh->yt[iy] = oky ? 4 * fr.bw * (py - fr.t) : OUTSIDE;
+                sh->yr[iy] = oky ? (short)(py - fr.t) : (short)0;
+            }
         }
-        if (staged && !landed) mbar_wait(&sh->bar, parity);
-        if (staged) parity ^= 1u;
-        __syncthreads();
 
-        // ---- 4. voxel loop
         // the fixed-divisor divisions are proven for these ranges (file header); anything else
         // takes the generic IEEE path
         const float ax = fabsf(ox), ay = fabsf(oy), az = fabsf(oz);
@@ -484,7 +680,6 @@ __global__ void __launch_bounds__(NT, 2) dtsdf_fused_kernel(const __grid_constan
                           (ay == 0.0f || (ay >= 0x1p-60f && ay <= 0x1p30f)) &&
                           (az == 0.0f || (az >= 0x1p-60f && az <= 0x1p30f));
         VoxConst k;
-        k.bw4 = 4 * fr.bw;
         k.ix = MAGIC_I + fr.l;
         k.iy = MAGIC_I + fr.t;
         k.kx = MAGIC_F + (float)a.center_x;
@@ -495,44 +690,43 @@ __global__ void __launch_bounds__(NT, 2) dtsdf_fused_kernel(const __grid_constan
         k.yt = __frcp_rn(trunc);
         // margin 2^-10 on the far test: t_z = RN(|s_z|/trunc) > 1 + 2^-11, t_z^2 > THR_SQ
         k.t_far = fast ? __fmul_rn(trunc, 1.0009765625f) : INFINITY;
-        if (fast) {
-            if (staged) voxel_tiles<R, LAYOUT, true, true, DEFF>(crop_s, sh, k, &tmap, tiles, f, gstep);
-            else        voxel_tiles<R, LAYOUT, false, true, DEFF>(crop_g, sh, k, &tmap, tiles, f, gstep);
-        } else {
-            if (staged) voxel_tiles<R, LAYOUT, true, false, DEFF>(crop_s, sh, k, &tmap, tiles, f, gstep);
-            else        voxel_tiles<R, LAYOUT, false, false, DEFF>(crop_g, sh, k, &tmap, tiles, f, gstep);
+        float* out = a.vol + (size_t)f * 3 * R * R * R;
+
+        // the next crop goes to L2 now, so that the scan at the end of this frame finds it there
+        if (more && tid == 0 && frn.n_pad > 0) bulk_prefetch_l2(frn.crop, (uint32_t)frn.n_pad * 4u);
+        __syncthreads();      // (C) tables are complete
+        if (fr.staged) {
+            mbar_wait(&sh->bar, parity);
+            parity ^= 1u;
         }
-        // the last tile's __syncthreads() also orders every read of crop_s / the tables before the
-        // next frame overwrites them
-    }
-    if (tid == 0) bulk_wait_all();    // shared memory must outlive the TMA reads
-}
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
+        // ---- voxel loop
+        if (fast) {
+            if (fr.staged) voxel_passes<R, LAYOUT, true, true, DEFF>(crop_s, sh, k, out);
+            else           voxel_passes<R, LAYOUT, false, true, DEFF>(fr.crop, sh, k, out);
+        } else {
+            if (fr.staged) voxel_passes<R, LAYOUT, true, false, DEFF>(crop_s, sh, k, out);
+            else           voxel_passes<R, LAYOUT, false, false, DEFF>(fr.crop, sh, k, out);
+        }
+        if (!more) break;
 
-cudaError_t encode_volume_map(CUtensorMap* tmap, float* vol, int R, int n_frames) {
-    static EncodeTiledFn encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        if (e != cudaSuccess) return e;
-        if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
-        encode = reinterpret_cast<EncodeTiledFn>(fn);
+        // ---- this warp is done with the staged crop; the last warp to get here starts the
+        //      copy of the next one.  Every lane's reads were consumed before its stores were
+        //      issued, and the warp issues in order, so they are complete at this point.
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned prev = atomicAdd(&sh->done, 1u);
+            if ((prev % NWARP) == NWARP - 1 && frn.staged) {
+                fence_proxy_async();      // generic-proxy reads of crop_s happen-before the async write
+                mbar_expect_tx(&sh->bar, (uint32_t)frn.n_pad * 4u);
+                bulk_g2s(crop_s, frn.crop, (uint32_t)frn.n_pad * 4u, &sh->bar);
+            }
+        }
+        // ---- bounding-box scan of the next frame, from global memory
+        if (scan) bbox_partial<DEFF>(frn, a, yf, focal_ok, sh->red);
+        f = fn;
+        fr = frn;
     }
-    // volume tensor, fastest dimension first: F (R), M (R), S (R), channel (3), frame (n)
-    const cuuint64_t r = (cuuint64_t)R;
-    cuuint64_t dims[5] = {r, r, r, 3, (cuuint64_t)n_frames};
-    cuuint64_t strides[4] = {r * 4, r * r * 4, r * r * r * 4, 3 * r * r * r * 4};
-    cuuint32_t box[5] = {32, 4, 8, 3, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult res = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, vol, dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return res == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 template <int R, int LAYOUT, bool DEFF>
@@ -547,12 +741,9 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
     if ((reinterpret_cast<uintptr_t>(args.vol) & 15) != 0) return cudaErrorMisalignedAddress;
-    alignas(64) CUtensorMap tmap;
-    e = encode_volume_map(&tmap, args.vol, R, args.n_frames);
-    if (e != cudaSuccess) return e;
-    const int fixed = 2 * TILE_BYTES + (int)sizeof(FrameShared<R>);
+    const int fixed = (int)sizeof(FrameShared<R, LAYOUT>);
     // staging capacity: the largest crop of the batch when known (the occupancy then follows from
-    // it: two CTAs per SM up to ~85 KB crops, one above); oversize crops take the direct path.
+    // it: three CTAs per SM up to ~63 KB crops, two up to ~100 KB, one above); oversize crops take the direct path.
     long long want = max_crop_px > 0 ? (((long long)max_crop_px + 3) & ~3ll) * 4 : (long long)smem_optin;
     long long avail = (long long)smem_optin - fixed - 1024;
     if (want > avail) want = avail;
@@ -569,7 +760,7 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     if (occ < 1) occ = 1;
     long long grid = (long long)occ * sms;        // persistent: a whole number of waves
     if (grid > args.n_frames) grid = args.n_frames;
-    kern<<<(unsigned)grid, NT, smem, stream>>>(tmap, args);
+    kern<<<(unsigned)grid, NT, smem, stream>>>(args);
     ++g_launch_count;
     return cudaGetLastError();
 }
