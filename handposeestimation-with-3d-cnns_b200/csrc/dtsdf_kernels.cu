@@ -71,7 +71,6 @@ constexpr int MAGIC_I = 0x4B400000;     // bit pattern of 12582912.0f = 1.5 * 2^
 constexpr float MAGIC_F = 12582912.0f;  // int_as_float(MAGIC_I + k) == MAGIC_F + k for |k| < 2^22
 constexpr float THR_SQ = 1.00000011920928955078125f;   // nextafter(1,2): sqrt_rn(s) > 1 <=> s > THR_SQ
 constexpr float BIG_DEPTH = 1099511627776.0f;          // 2^40: depth range of the FMA division proof
-constexpr int LIST_CAP = 128;                          // per-warp ring of 16-bit work-list entries
 constexpr int OUTSIDE = -(1 << 30);                    // table sentinel: projection outside the crop
 constexpr unsigned DEFAULT_FOCAL_BITS = 0x43716B85u;   // 241.42f
 constexpr unsigned FULL = 0xffffffffu;
@@ -153,10 +152,15 @@ struct __align__(16) FrameShared {
     short yr[R * YS];               // same indexing: pix_y - top (pass 2 only)
     float vx[R], vy[R], vz[R];      // voxel centres per axis
     float red[NWARP][8];            // per-warp partial min xyz / max xyz (6 used)
-    unsigned short list[NWARP][LIST_CAP];   // per-warp ring lists: groups with near-surface voxels
+    // per-warp work lists (groups with near-surface voxels): what one slow-axis row group can
+    // add plus the remainder (< 32) carried over from the previous one
+    static constexpr int LIST_CAP = 32 + 32 * (R / NWARP);
+    unsigned short list[NWARP][LIST_CAP];
     unsigned long long bar;         // crop TMA completion barrier
+    const float* next_crop;         // the next frame's record (registers are scarce in the voxel loop)
+    int next_box[4];                // left, top, right, bottom
     unsigned int done;              // warps that have finished reading the crop (running count)
-    unsigned int pad_;
+    unsigned int pad_[3];
     float zero[4];                  // zero[3] sits right below the crop: target of "outside" gathers
 };
 
@@ -166,26 +170,21 @@ struct Frame {
     bool staged;
 };
 
-// per-frame constants of the voxel evaluation
+// per-frame constants of the voxel evaluation (everything else comes from the kernel parameters)
 struct VoxConst {
     int   ix;        // MAGIC_I + left:  int_as_float(ix + (px-left)) == MAGIC_F + px
     int   iy;        // MAGIC_I + top
-    float kx;        // MAGIC_F + cx
-    float ky;        // MAGIC_F + cy
-    float focal;
-    float yf;        // rcp_rn(focal)
     float trunc;
     float yt;        // rcp_rn(trunc)
     float t_far;     // |v_z - w_z| above this forces truncation; +inf disables the shortcut
 };
 
-__device__ __forceinline__ Frame load_frame(const BatchArgs& a, int f) {
-    // frame record (pre/tsdf_numba.py:122-129)
-    const int* h = a.headers + 6 * (size_t)f;
+// frame record (pre/tsdf_numba.py:122-129) from its bounding box and crop address
+__device__ __forceinline__ Frame make_frame(int l, int t, int r, int b, const float* crop, int cap_floats) {
     Frame fr;
-    fr.l = __ldg(h + 2); fr.t = __ldg(h + 3); fr.r = __ldg(h + 4); fr.b = __ldg(h + 5);
-    fr.bw = fr.r - fr.l;
-    fr.bh = fr.b - fr.t;
+    fr.l = l; fr.t = t; fr.r = r; fr.b = b;
+    fr.bw = r - l;
+    fr.bh = b - t;
     const int lim = 1 << 22;
     const bool bad = fr.bw <= 0 || fr.bh <= 0 || fr.bw > 32767 || fr.bh > 32767 ||
                      (long long)fr.bw * fr.bh > (1ll << 26) ||      // byte offsets stay below 2^28
@@ -193,9 +192,15 @@ __device__ __forceinline__ Frame load_frame(const BatchArgs& a, int f) {
     if (bad) { fr.bw = 0; fr.bh = 0; }
     fr.n = fr.bw * fr.bh;
     fr.n_pad = (fr.n + 3) & ~3;
-    fr.crop = a.depth + __ldg(a.offsets + f);
-    fr.staged = fr.n_pad > 0 && fr.n_pad <= a.cap_floats;     // CTA-uniform
+    fr.crop = crop;
+    fr.staged = fr.n_pad > 0 && fr.n_pad <= cap_floats;     // CTA-uniform
     return fr;
+}
+
+__device__ __forceinline__ Frame load_frame(const BatchArgs& a, int f) {
+    const int* h = a.headers + 6 * (size_t)f;
+    return make_frame(__ldg(h + 2), __ldg(h + 3), __ldg(h + 4), __ldg(h + 5), a.depth + __ldg(a.offsets + f),
+                      a.cap_floats);
 }
 
 // ---------------------------------------------------------------- bounding box scan
@@ -318,25 +323,46 @@ __device__ __noinline__ Tsdf3 eval_generic(float d, float fx, float fy, float vx
     return o;
 }
 
-// Same evaluation with the fixed-divisor divisions (bit-identical inside the proven ranges).
+// Two voxels at a time on the packed FP32 pipe of sm_100 (FFMA2 / FMUL2: two IEEE binary32
+// round-to-nearest operations per instruction), with the fixed-divisor divisions.  Same
+// operations in the same order as eval_generic, bit-identical inside the proven ranges.
+// The quotients keep the sign of their dividends (RN division is odd); |.| and the final sign
+// (-d > v_z  <=>  v_z + d < 0) are one LOP3 per output.
+template <bool ONE>
+__device__ __forceinline__ float2 div_fixed2(float2 a, float2 nb, float2 y) {      // nb = -b
+    float2 q = __fmul2_rn(a, y);
+    q = __ffma2_rn(__ffma2_rn(nb, q, a), y, q);
+    if (!ONE) q = __ffma2_rn(__ffma2_rn(nb, q, a), y, q);
+    return q;
+}
+
 template <bool DEFF>
-__device__ __forceinline__ Tsdf3 eval_fast(float d, float fx, float fy, float vx, float vy, float sz,
-                                           const VoxConst& k) {
-    const float c1 = div_fixed<DEFF>(d, k.focal, k.yf);
-    const float wx = __fmul_rn(fx, c1);
-    const float wy = __fmul_rn(fy, c1);
-    float tx = div_fixed<false>(fabsf(__fsub_rn(vx, wx)), k.trunc, k.yt);
-    float ty = div_fixed<false>(fabsf(__fsub_rn(vy, wy)), k.trunc, k.yt);
-    float tz = div_fixed<false>(fabsf(sz), k.trunc, k.yt);
-    const float s = __fadd_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)), __fmul_rn(tz, tz));
-    if (s > THR_SQ) { tx = 1.0f; ty = 1.0f; tz = 1.0f; }
-    // -d > v_z  <=>  v_z + d < 0: flip the sign bit with the one of sz
-    const int sg = __float_as_int(sz) & 0x80000000;
-    Tsdf3 o;
-    o.x = __int_as_float(__float_as_int(tx) ^ sg);
-    o.y = __int_as_float(__float_as_int(ty) ^ sg);
-    o.z = __int_as_float(__float_as_int(tz) ^ sg);
-    return o;
+__device__ __forceinline__ void eval_pair(float2 d, float2 fx, float2 fy, float2 vx, float2 vy, float2 sz,
+                                          float focal, float yf, float trunc, float ytr,
+                                          float (&o0)[2], float (&o1)[2], float (&o2)[2]) {
+    const float2 m1 = make_float2(-1.0f, -1.0f);
+    const float2 nf = make_float2(-focal, -focal), yf2 = make_float2(yf, yf);
+    const float2 nt = make_float2(-trunc, -trunc), yt2 = make_float2(ytr, ytr);
+    const float2 c1 = div_fixed2<DEFF>(d, nf, yf2);
+    const float2 wx = __fmul2_rn(fx, c1);
+    const float2 wy = __fmul2_rn(fy, c1);
+    const float2 dx = __ffma2_rn(wx, m1, vx);              // v_x - w_x: the product is exact, one rounding
+    const float2 dy = __ffma2_rn(wy, m1, vy);
+    const float2 tx = div_fixed2<false>(dx, nt, yt2);      // signed; |t| below
+    const float2 ty = div_fixed2<false>(dy, nt, yt2);
+    const float2 tz = div_fixed2<false>(sz, nt, yt2);
+    const float2 s = __fadd2_rn(__fadd2_rn(__fmul2_rn(tx, tx), __fmul2_rn(ty, ty)), __fmul2_rn(tz, tz));
+    const float ss[2] = {s.x, s.y}, szz[2] = {sz.x, sz.y};
+    const float txx[2] = {tx.x, tx.y}, tyy[2] = {ty.x, ty.y}, tzz[2] = {tz.x, tz.y};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int sg = __float_as_int(szz[i]) & 0x80000000;
+        const bool sat = ss[i] > THR_SQ;
+        const int one = 0x3F800000 | sg;
+        o0[i] = __int_as_float(sat ? one : ((__float_as_int(txx[i]) & 0x7fffffff) | sg));
+        o1[i] = __int_as_float(sat ? one : ((__float_as_int(tyy[i]) & 0x7fffffff) | sg));
+        o2[i] = __int_as_float(sat ? one : ((__float_as_int(tzz[i]) & 0x7fffffff) | sg));
+    }
 }
 
 // byte offset into the crop; negative <=> either table entry is OUTSIDE; reads as "no depth"
@@ -379,17 +405,18 @@ struct LaneMap {
     static_assert(R <= 64 && NSG <= 32, "work-list entries are 5 + 6 + 5 bits");
 };
 
-// pass 2: full evaluation of n (<= 32) listed groups starting at ring position `head`
+// pass 2: full evaluation of the n (<= 32) listed groups list[0..n)
 template <int R, int LAYOUT, bool STAGED, bool FAST, bool DEFF>
 __device__ __forceinline__ void eval_listed(const float* __restrict__ crop,
                                             const FrameShared<R, LAYOUT>* __restrict__ sh, const VoxConst& k,
-                                            float* __restrict__ out, const unsigned short* list, int head, int n) {
+                                            const BatchArgs& a, float yf, float* __restrict__ out,
+                                            const unsigned short* list, int n) {
     using LM = LaneMap<R>;
     constexpr int YS = FrameShared<R, LAYOUT>::YS;
     constexpr int CH = R * R * R;
     const int lane = threadIdx.x & 31;
     if (lane < n) {
-        const int ent = list[(head + lane) & (LIST_CAP - 1)];
+        const int ent = list[lane];
         const int L = ent & 31, m = (ent >> 5) & 63, sg = ent >> 11;
         const int s = sg * LM::ROWS + L / LM::LPR;
         const int f0 = 4 * (L % LM::LPR);
@@ -416,27 +443,51 @@ __device__ __forceinline__ void eval_listed(const float* __restrict__ crop,
 #pragma unroll
             for (int j = 0; j < 4; ++j) { b4[j] = b1; row4[j] = r1; vz4[j] = z1; }
         }
+        const float kx = MAGIC_F + (float)a.center_x, ky = MAGIC_F + (float)a.center_y;
+        float d4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d4[j] = gather_depth<STAGED>(crop, a4[j] + b4[j]);
         float o0[4], o1[4], o2[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float d = gather_depth<STAGED>(crop, a4[j] + b4[j]);
-            const float sz = __fadd_rn(vz4[j], d);
-            const bool ok = !(fabsf(d) < 1.0f);
-            const bool far = fabsf(sz) > k.t_far;
-            float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
-            if (ok) {
-                if (far) {
-                    t0 = t1 = t2 = __int_as_float((__float_as_int(sz) & 0x80000000) | 0x3F800000);
+        for (int h = 0; h < 4; h += 2) {
+            float sz[2], fx[2], fy[2];
+            bool ok[2], far[2], big[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int j = h + i;
+                sz[i] = __fadd_rn(vz4[j], d4[j]);
+                ok[i] = !(fabsf(d4[j]) < 1.0f);
+                far[i] = fabsf(sz[i]) > k.t_far;
+                big[i] = !(fabsf(d4[j]) < BIG_DEPTH);
+                fx[i] = __fsub_rn(__int_as_float(k.ix + (a4[j] >> 2)), kx);   //  (pix_x - cx)
+                fy[i] = __fsub_rn(ky, __int_as_float(k.iy + row4[j]));        // -(pix_y - cy)
+            }
+            const bool near0 = ok[0] && !far[0], near1 = ok[1] && !far[1];
+            float p0[2] = {0.0f, 0.0f}, p1[2] = {0.0f, 0.0f}, p2[2] = {0.0f, 0.0f};
+            if (near0 || near1) {
+                if (FAST && !big[0] && !big[1]) {
+                    eval_pair<DEFF>(make_float2(d4[h], d4[h + 1]), make_float2(fx[0], fx[1]),
+                                    make_float2(fy[0], fy[1]), make_float2(vx4[h], vx4[h + 1]),
+                                    make_float2(vy, vy), make_float2(sz[0], sz[1]), a.focal, yf, k.trunc, k.yt,
+                                    p0, p1, p2);
                 } else {
-                    const float fx = __fsub_rn(__int_as_float(k.ix + (a4[j] >> 2)), k.kx);   //  (pix_x - cx)
-                    const float fy = __fsub_rn(k.ky, __int_as_float(k.iy + row4[j]));        // -(pix_y - cy)
-                    Tsdf3 t;
-                    if (FAST && fabsf(d) < BIG_DEPTH) t = eval_fast<DEFF>(d, fx, fy, vx4[j], vy, sz, k);
-                    else t = eval_generic(d, fx, fy, vx4[j], vy, vz4[j], sz, k.focal, k.trunc);
-                    t0 = t.x; t1 = t.y; t2 = t.z;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const Tsdf3 t = eval_generic(d4[h + i], fx[i], fy[i], vx4[h + i], vy, vz4[h + i], sz[i],
+                                                     a.focal, k.trunc);
+                        p0[i] = t.x; p1[i] = t.y; p2[i] = t.z;
+                    }
                 }
             }
-            o0[j] = t0; o1[j] = t1; o2[j] = t2;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float one = __int_as_float((__float_as_int(sz[i]) & 0x80000000) | 0x3F800000);
+                const bool nr = ok[i] && !far[i];
+                const float rest = (ok[i] && far[i]) ? one : 0.0f;
+                o0[h + i] = nr ? p0[i] : rest;
+                o1[h + i] = nr ? p1[i] : rest;
+                o2[h + i] = nr ? p2[i] : rest;
+            }
         }
         float* p = out + ((size_t)(s * R + m) * R + f0);
         st_f4(p, make_float4(o0[0], o0[1], o0[2], o0[3]));
@@ -447,11 +498,13 @@ __device__ __forceinline__ void eval_listed(const float* __restrict__ crop,
 
 // One frame's voxel loop (both passes).  The warps run independently.  Warp w handles the
 // middle-axis positions m = w, w + 8, ... of every slow-axis row group, so every warp sees every
-// part of the volume (balanced pass-2 work).
+// part of the volume (balanced pass-2 work).  Pass 2 runs at the end of each row group on whole
+// batches of 32 listed groups; the remainder moves to the front of the list.
 template <int R, int LAYOUT, bool STAGED, bool FAST, bool DEFF>
 __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
                                              FrameShared<R, LAYOUT>* __restrict__ sh, const VoxConst& k,
-                                             float* __restrict__ out) {
+                                             const BatchArgs& a, float yf, float* __restrict__ out,
+                                             bool prefetch_next) {
     using LM = LaneMap<R>;
     constexpr int YS = FrameShared<R, LAYOUT>::YS;
     constexpr int CH = R * R * R;
@@ -463,7 +516,7 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
     const float t_far = k.t_far;
     unsigned short* list = sh->list[warp];
     const unsigned lt = (1u << lane) - 1u;
-    int head = 0, tail = 0;
+    int cnt = 0;
 
     float4 vzf = make_float4(0.f, 0.f, 0.f, 0.f);
     if (LAYOUT == 0) vzf = *reinterpret_cast<const float4*>(&sh->vz[f0]);
@@ -478,6 +531,11 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
         }
         float* const obase = out + ((size_t)s * R * R + f0);
         const int ebase = (sg << 11) | lane;
+        // the next crop goes to L2 shortly before its scan (earlier, the output stream evicts it)
+        if (prefetch_next && sg == LM::NSG - 2 && threadIdx.x == 0) {
+            const int nb = ((sh->next_box[2] - sh->next_box[0]) * (sh->next_box[3] - sh->next_box[1]) + 3) & ~3;
+            if (nb > 0) bulk_prefetch_l2(sh->next_crop, (uint32_t)nb * 4u);
+        }
 #pragma unroll
         for (int ks = 0; ks < LM::MSTEPS; ks += 2) {
             const int m0 = warp + NWARP * ks, m1 = m0 + NWARP;
@@ -518,25 +576,35 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
             n1 = n1 && active;
             const unsigned bal0 = __ballot_sync(FULL, n0);
             const unsigned bal1 = __ballot_sync(FULL, n1);
-            if (n0) list[(tail + __popc(bal0 & lt)) & (LIST_CAP - 1)] = (unsigned short)(ebase | (m0 << 5));
-            tail += __popc(bal0);
-            if (n1) list[(tail + __popc(bal1 & lt)) & (LIST_CAP - 1)] = (unsigned short)(ebase | (m1 << 5));
-            tail += __popc(bal1);
-            while (tail - head >= 32) {              // warp-uniform
-                __syncwarp();                        // list entries and the pass-1 stores are ordered before pass 2
-                eval_listed<R, LAYOUT, STAGED, FAST, DEFF>(crop, sh, k, out, list, head, 32);
-                head += 32;
-            }
+            if (n0) list[cnt + __popc(bal0 & lt)] = (unsigned short)(ebase | (m0 << 5));
+            cnt += __popc(bal0);
+            if (n1) list[cnt + __popc(bal1 & lt)] = (unsigned short)(ebase | (m1 << 5));
+            cnt += __popc(bal1);
+        }
+        // ---- pass 2 on whole batches (warp-uniform control flow)
+        if (cnt >= 32) {
+            __syncwarp();                 // list entries and the pass-1 stores are ordered before pass 2
+            int done = 0;
+            do {
+                eval_listed<R, LAYOUT, STAGED, FAST, DEFF>(crop, sh, k, a, yf, out, list + done, 32);
+                done += 32;
+            } while (cnt - done >= 32);
+            const int rem = cnt - done;
+            unsigned short carry = 0;
+            if (lane < rem) carry = list[done + lane];
+            __syncwarp();
+            if (lane < rem) list[lane] = carry;
+            cnt = rem;
         }
     }
     __syncwarp();
-    eval_listed<R, LAYOUT, STAGED, FAST, DEFF>(crop, sh, k, out, list, head, tail - head);
+    eval_listed<R, LAYOUT, STAGED, FAST, DEFF>(crop, sh, k, a, yf, out, list, cnt);
 }
 #undef DTSDF_CLASSIFY
 
 // ---------------------------------------------------------------- fused kernel
 template <int R, int LAYOUT, bool DEFF>
-__global__ void __launch_bounds__(NT, 3) dtsdf_fused_kernel(const BatchArgs a) {
+__global__ void __launch_bounds__(NT, 3) dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     using FS = FrameShared<R, LAYOUT>;
     constexpr int YS = FS::YS;
     static_assert(sizeof(FS) % 16 == 0 && offsetof(FS, zero) + 16 == sizeof(FS), "zero pad must touch the crop");
@@ -571,12 +639,15 @@ __global__ void __launch_bounds__(NT, 3) dtsdf_fused_kernel(const BatchArgs a) {
     for (;;) {
         __syncthreads();      // (A) bbox partials are in; nobody reads the previous frame's tables any more
 
-        // ---- next frame's record early: its latency hides behind the table phase
+        // ---- next frame's record: loaded now by one thread, parked in shared memory before (C)
         const int fn = f + (int)gridDim.x;
         const bool more = fn < a.n_frames;
-        Frame frn = fr;
-        if (more) {
-            frn = load_frame(a, fn);
+        int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0;
+        const float* ncrop = nullptr;
+        if (more && tid == 0) {
+            const int* h = a.headers + 6 * (size_t)fn;
+            nb0 = __ldg(h + 2); nb1 = __ldg(h + 3); nb2 = __ldg(h + 4); nb3 = __ldg(h + 5);
+            ncrop = a.depth + __ldg(a.offsets + fn);
         }
 
         // ---- bounding box (pre/tsdf_numba.py:75-116,140-141) or caller-supplied
@@ -682,50 +753,51 @@ __global__ void __launch_bounds__(NT, 3) dtsdf_fused_kernel(const BatchArgs a) {
         VoxConst k;
         k.ix = MAGIC_I + fr.l;
         k.iy = MAGIC_I + fr.t;
-        k.kx = MAGIC_F + (float)a.center_x;
-        k.ky = MAGIC_F + (float)a.center_y;
-        k.focal = a.focal;
-        k.yf = yf;
         k.trunc = trunc;
         k.yt = __frcp_rn(trunc);
         // margin 2^-10 on the far test: t_z = RN(|s_z|/trunc) > 1 + 2^-11, t_z^2 > THR_SQ
         k.t_far = fast ? __fmul_rn(trunc, 1.0009765625f) : INFINITY;
         float* out = a.vol + (size_t)f * 3 * R * R * R;
+        const bool staged = fr.staged;
+        const float* crop_g = fr.crop;
 
-        // the next crop goes to L2 now, so that the scan at the end of this frame finds it there
-        if (more && tid == 0 && frn.n_pad > 0) bulk_prefetch_l2(frn.crop, (uint32_t)frn.n_pad * 4u);
+        if (more && tid == 0) {
+            sh->next_crop = ncrop;
+            sh->next_box[0] = nb0; sh->next_box[1] = nb1; sh->next_box[2] = nb2; sh->next_box[3] = nb3;
+        }
         __syncthreads();      // (C) tables are complete
-        if (fr.staged) {
+        if (staged) {
             mbar_wait(&sh->bar, parity);
             parity ^= 1u;
         }
 
         // ---- voxel loop
         if (fast) {
-            if (fr.staged) voxel_passes<R, LAYOUT, true, true, DEFF>(crop_s, sh, k, out);
-            else           voxel_passes<R, LAYOUT, false, true, DEFF>(fr.crop, sh, k, out);
+            if (staged) voxel_passes<R, LAYOUT, true, true, DEFF>(crop_s, sh, k, a, yf, out, more);
+            else        voxel_passes<R, LAYOUT, false, true, DEFF>(crop_g, sh, k, a, yf, out, more);
         } else {
-            if (fr.staged) voxel_passes<R, LAYOUT, true, false, DEFF>(crop_s, sh, k, out);
-            else           voxel_passes<R, LAYOUT, false, false, DEFF>(fr.crop, sh, k, out);
+            if (staged) voxel_passes<R, LAYOUT, true, false, DEFF>(crop_s, sh, k, a, yf, out, more);
+            else        voxel_passes<R, LAYOUT, false, false, DEFF>(crop_g, sh, k, a, yf, out, more);
         }
         if (!more) break;
 
         // ---- this warp is done with the staged crop; the last warp to get here starts the
         //      copy of the next one.  Every lane's reads were consumed before its stores were
         //      issued, and the warp issues in order, so they are complete at this point.
+        fr = make_frame(sh->next_box[0], sh->next_box[1], sh->next_box[2], sh->next_box[3], sh->next_crop,
+                        a.cap_floats);
         __syncwarp();
         if (lane == 0) {
             const unsigned prev = atomicAdd(&sh->done, 1u);
-            if ((prev % NWARP) == NWARP - 1 && frn.staged) {
+            if ((prev % NWARP) == NWARP - 1 && fr.staged) {
                 fence_proxy_async();      // generic-proxy reads of crop_s happen-before the async write
-                mbar_expect_tx(&sh->bar, (uint32_t)frn.n_pad * 4u);
-                bulk_g2s(crop_s, frn.crop, (uint32_t)frn.n_pad * 4u, &sh->bar);
+                mbar_expect_tx(&sh->bar, (uint32_t)fr.n_pad * 4u);
+                bulk_g2s(crop_s, fr.crop, (uint32_t)fr.n_pad * 4u, &sh->bar);
             }
         }
         // ---- bounding-box scan of the next frame, from global memory
-        if (scan) bbox_partial<DEFF>(frn, a, yf, focal_ok, sh->red);
+        if (scan) bbox_partial<DEFF>(fr, a, yf, focal_ok, sh->red);
         f = fn;
-        fr = frn;
     }
 }
 
