@@ -121,6 +121,12 @@ __device__ __forceinline__ void st_f4(float* p, const float4& v) {
     asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
+// 1 if either operand is a NaN
+__device__ __forceinline__ int unordered(float a, float b) {
+    int r;
+    asm("{\n\t.reg .pred p;\n\tsetp.nan.f32 p, %1, %2;\n\tselp.s32 %0, 1, 0, p;\n\t}" : "=r"(r) : "f"(a), "f"(b));
+    return r;
+}
 __device__ __forceinline__ float warp_min(float v) {
     float r;
     asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
@@ -160,8 +166,9 @@ struct __align__(16) FrameShared {
     const float* next_crop;         // the next frame's record (registers are scarce in the voxel loop)
     int next_box[4];                // left, top, right, bottom
     unsigned int done;              // warps that have finished reading the crop (running count)
-    unsigned int pad_[3];
-    float zero[4];                  // zero[3] sits right below the crop: target of "outside" gathers
+    unsigned int nanflag[2];        // by frame parity: the staged crop holds a NaN (take the unstaged path)
+    unsigned int pad_;
+    float zero[4];                  // zero[3] sits right below the crop: target of "outside" gathers (NaN)
 };
 
 struct Frame {
@@ -210,94 +217,122 @@ __device__ __forceinline__ Frame load_frame(const BatchArgs& a, int f) {
 // set's smallest and largest valid depth: the scan only tracks min/max valid depth per column
 // (in registers, 4 columns per lane and 128-column panel) and per lane and row, and
 // back-projects those.  The result is the same min/max the reference computes over all valid
-// pixels.  Invalid pixels (|d| < 1, pre/tsdf_numba.py:87) become NaN, which fminf/fmaxf skip.
+// pixels.  Invalid pixels (|d| < 1, pre/tsdf_numba.py:87) become NaN, which fminf/fmaxf skip;
+// a row without valid pixels yields +-inf extremes whose quotient is NaN as well.
 // One warp per crop row, four rows in flight per warp; reads global memory (L2) directly.
-template <bool DEFF>
-__device__ __forceinline__ float div_focal(float d, float focal, float yf, bool focal_ok) {
-    if (!(fabsf(d) >= BIG_DEPTH) && (DEFF || focal_ok)) return div_fixed<DEFF>(d, focal, yf);
-    return __fdiv_rn(d, focal);
+// VEC: rows start 16-byte aligned (bw % 4 == 0): a lane owns 4 adjacent columns (one LDG.128);
+// otherwise columns lane, lane+32, lane+64, lane+96 of the panel (4 coalesced scalar loads).
+// EXACT: IEEE division; otherwise the fixed-divisor form, valid while |d| < BIG_DEPTH (the
+// caller checks the depth range afterwards and rescans with EXACT if needed).
+template <bool ONE, bool EXACT>
+__device__ __forceinline__ float div_focal(float d, float focal, float yf) {
+    return EXACT ? __fdiv_rn(d, focal) : div_fixed<ONE>(d, focal, yf);
 }
 
-template <bool DEFF>
-__device__ __forceinline__ void bbox_scan(const Frame& fr, float focal, float yf, bool focal_ok, int cx,
-                                          int cy, float (&mn)[3], float (&mx)[3]) {
+template <bool ONE, bool EXACT, bool VEC>
+__device__ __forceinline__ void bbox_scan(const Frame& fr, float focal, float yf, int cx, int cy,
+                                          float (&mn)[3], float (&mx)[3]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float kx = MAGIC_F + (float)cx;
     const float ky = MAGIC_F + (float)cy;
     const float* __restrict__ crop = fr.crop;
+    const float qnan = __int_as_float(0x7fc00000);
     float dlo = INFINITY, dhi = -INFINITY;           // valid depth extremes (Z = -d)
     for (int panel = 0; panel < fr.bw; panel += 128) {
+        const int c0 = panel + (VEC ? 4 * lane : lane);          // first column of this lane
+        constexpr int CS = VEC ? 1 : 32;                         // column stride of this lane
         bool inb[4];
         float cmin[4], cmax[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            inb[j] = panel + lane + 32 * j < fr.bw;
+            inb[j] = c0 + CS * j < fr.bw;
             cmin[j] = INFINITY; cmax[j] = -INFINITY;
         }
+        auto load_row = [&](int row, float (&d)[4]) {
+            const float* p = crop + (size_t)row * fr.bw + c0;
+            if (VEC) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (inb[0]) v = __ldg(reinterpret_cast<const float4*>(p));      // bw % 4 == 0: all four in range
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[j] = inb[j] ? __ldg(p + 32 * j) : 0.0f;
+            }
+        };
         // one row: this lane's (up to) 4 pixels
         auto row_step = [&](int row, const float (&d)[4]) {
-            float rmin = INFINITY, rmax = -INFINITY;
+            float v[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float v = fabsf(d[j]) < 1.0f ? __int_as_float(0x7fc00000) : d[j];
-                cmin[j] = fminf(cmin[j], v); cmax[j] = fmaxf(cmax[j], v);
-                rmin = fminf(rmin, v); rmax = fmaxf(rmax, v);
+                v[j] = fabsf(d[j]) < 1.0f ? qnan : d[j];
+                cmin[j] = fminf(cmin[j], v[j]); cmax[j] = fmaxf(cmax[j], v[j]);
             }
-            const bool has = rmin <= rmax;
-            const float a0 = has ? rmin : __int_as_float(0x7fc00000);
-            const float a1 = has ? rmax : __int_as_float(0x7fc00000);
+            const float rmin = fminf(fminf(fminf(v[0], INFINITY), v[1]), fminf(v[2], v[3]));
+            const float rmax = fmaxf(fmaxf(fmaxf(v[0], -INFINITY), v[1]), fmaxf(v[2], v[3]));
             const float fy = __fsub_rn(__int_as_float(MAGIC_I + row + fr.t), ky);   // (y - cy), exact
-            const float y1 = __fmul_rn(-div_focal<DEFF>(a0, focal, yf, focal_ok), fy);
-            const float y2 = __fmul_rn(-div_focal<DEFF>(a1, focal, yf, focal_ok), fy);
-            mn[1] = fminf(mn[1], fminf(y1, y2)); mx[1] = fmaxf(mx[1], fmaxf(y1, y2));
+            const float y1 = __fmul_rn(-div_focal<ONE, EXACT>(rmin, focal, yf), fy);
+            const float y2 = __fmul_rn(-div_focal<ONE, EXACT>(rmax, focal, yf), fy);
+            // a row without valid pixels: rmin = +inf, rmax = -inf.  EXACT: the products are
+            // +-inf or NaN; fixed-divisor form: NaN (inf - inf in the residual).  Mask the former.
+            const bool has = !EXACT || rmin <= rmax;
+            mn[1] = fminf(mn[1], has ? fminf(y1, y2) : qnan);
+            mx[1] = fmaxf(mx[1], has ? fmaxf(y1, y2) : qnan);
         };
         int row = warp;
         for (; row + 3 * NWARP < fr.bh; row += 4 * NWARP) {
             float d[4][4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float* p = crop + (size_t)(row + u * NWARP) * fr.bw + panel + lane;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) d[u][j] = inb[j] ? __ldg(p + 32 * j) : 0.0f;
-            }
+            for (int u = 0; u < 4; ++u) load_row(row + u * NWARP, d[u]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) row_step(row + u * NWARP, d[u]);
         }
         for (; row < fr.bh; row += NWARP) {
             float d[4];
-            const float* p = crop + (size_t)row * fr.bw + panel + lane;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) d[j] = inb[j] ? __ldg(p + 32 * j) : 0.0f;
+            load_row(row, d);
             row_step(row, d);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (cmin[j] <= cmax[j]) {                 // this lane's column has a valid pixel in its rows
-                const float fx = __fsub_rn(__int_as_float(MAGIC_I + panel + lane + 32 * j + fr.l), kx);   // (x - cx)
-                const float x1 = __fmul_rn(div_focal<DEFF>(cmin[j], focal, yf, focal_ok), fx);
-                const float x2 = __fmul_rn(div_focal<DEFF>(cmax[j], focal, yf, focal_ok), fx);
-                mn[0] = fminf(mn[0], fminf(x1, x2)); mx[0] = fmaxf(mx[0], fmaxf(x1, x2));
-                dlo = fminf(dlo, cmin[j]); dhi = fmaxf(dhi, cmax[j]);
-            }
+            // a column without valid pixels gives NaN products (see above), which min/max skip
+            const bool has = !EXACT || cmin[j] <= cmax[j];
+            const float fx = __fsub_rn(__int_as_float(MAGIC_I + c0 + CS * j + fr.l), kx);   // (x - cx)
+            const float x1 = __fmul_rn(div_focal<ONE, EXACT>(cmin[j], focal, yf), fx);
+            const float x2 = __fmul_rn(div_focal<ONE, EXACT>(cmax[j], focal, yf), fx);
+            mn[0] = fminf(mn[0], has ? fminf(x1, x2) : qnan);
+            mx[0] = fmaxf(mx[0], has ? fmaxf(x1, x2) : qnan);
+            dlo = fminf(dlo, cmin[j]); dhi = fmaxf(dhi, cmax[j]);
         }
     }
     if (dlo <= dhi) { mn[2] = fminf(mn[2], -dhi); mx[2] = fmaxf(mx[2], -dlo); }
 }
 
 // scan + warp reduction; lane 0 leaves the warp's partial in shared memory
-template <bool DEFF>
-__device__ __forceinline__ void bbox_partial(const Frame& fr, const BatchArgs& a, float yf, bool focal_ok,
-                                             float (*red)[8]) {
+template <bool ONE, bool EXACT>
+__device__ __forceinline__ void bbox_partial(const Frame& fr, const BatchArgs& a, float yf, float (*red)[8]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float mn[3], mx[3];
     mn[0] = mn[1] = mn[2] = SENTINEL;
     mx[0] = mx[1] = mx[2] = -SENTINEL;
-    bbox_scan<DEFF>(fr, a.focal, yf, focal_ok, a.center_x, a.center_y, mn, mx);
+    if ((fr.bw & 3) == 0) bbox_scan<ONE, EXACT, true>(fr, a.focal, yf, a.center_x, a.center_y, mn, mx);
+    else                  bbox_scan<ONE, EXACT, false>(fr, a.focal, yf, a.center_x, a.center_y, mn, mx);
 #pragma unroll
     for (int c = 0; c < 3; ++c) { mn[c] = warp_min(mn[c]); mx[c] = warp_max(mx[c]); }
     if (lane == 0) {
         *reinterpret_cast<float4*>(&red[warp][0]) = make_float4(mn[0], mn[1], mn[2], mx[0]);
         *reinterpret_cast<float2*>(&red[warp][4]) = make_float2(mx[1], mx[2]);
+    }
+}
+
+// block reduction of the partials (every thread gets the result)
+__device__ __forceinline__ void bbox_reduce(const float (*red)[8], float (&mn)[3], float (&mx)[3]) {
+    mn[0] = mn[1] = mn[2] = SENTINEL;
+    mx[0] = mx[1] = mx[2] = -SENTINEL;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) {
+        const float4 p = *reinterpret_cast<const float4*>(&red[w][0]);
+        const float2 q = *reinterpret_cast<const float2*>(&red[w][4]);
+        mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+        mx[0] = fmaxf(mx[0], p.w); mx[1] = fmaxf(mx[1], q.x); mx[2] = fmaxf(mx[2], q.y);
     }
 }
 
@@ -369,7 +404,7 @@ __device__ __forceinline__ void eval_pair(float2 d, float2 fx, float2 fy, float2
 template <bool STAGED>
 __device__ __forceinline__ float gather_depth(const float* __restrict__ crop, int off) {
     if (STAGED) {
-        // the word right below the staged crop is 0.0f (FrameShared::zero[3])
+        // the word right below the staged crop reads as "no depth" (FrameShared::zero[3])
         off = max(off, -4);
         return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(crop) + off);
     }
@@ -383,15 +418,22 @@ __device__ __forceinline__ float gather_depth(const float* __restrict__ crop, in
 //                    Euclidean truncation fires (pre/process.py:180-185) and the result is +-1
 //                    by the side of the surface (:191-194)
 //   near           : needs the full evaluation (value 0 for now)
-#define DTSDF_CLASSIFY(D, VZ, OUT, NEAR)                                                          \
-    {                                                                                             \
-        const float sz_ = __fadd_rn(VZ, D);                     /* v_z - w_z, w_z = -d */         \
-        const bool ok_ = !(fabsf(D) < 1.0f);                                                      \
-        const bool far_ = fabsf(sz_) > t_far;                                                     \
-        const float one_ = __int_as_float((__float_as_int(sz_) & 0x80000000) | 0x3F800000);       \
-        OUT = (ok_ && far_) ? one_ : 0.0f;                                                        \
-        NEAR = NEAR || (ok_ && !far_);                                                            \
+// SAN: the staged crop was sanitised (|d| < 1 -> NaN, FrameShared::zero[3] is NaN too), so
+// "no depth" makes both comparisons false and needs no test of its own.
+template <bool SAN>
+__device__ __forceinline__ void classify(float d, float vz, float t_far, float& out, bool& near) {
+    const float sz = __fadd_rn(vz, d);                      // v_z - w_z, w_z = -d
+    const float one = __int_as_float((__float_as_int(sz) & 0x80000000) | 0x3F800000);
+    if (SAN) {
+        out = fabsf(sz) > t_far ? one : 0.0f;
+        near = near || fabsf(sz) <= t_far;
+    } else {
+        const bool ok = !(fabsf(d) < 1.0f);
+        const bool far = fabsf(sz) > t_far;
+        out = (ok && far) ? one : 0.0f;
+        near = near || (ok && !far);
     }
+}
 
 // Lane geometry of the voxel loop for an R^3 grid
 template <int R>
@@ -456,9 +498,10 @@ __device__ __forceinline__ void eval_listed(const float* __restrict__ crop,
             for (int i = 0; i < 2; ++i) {
                 const int j = h + i;
                 sz[i] = __fadd_rn(vz4[j], d4[j]);
-                ok[i] = !(fabsf(d4[j]) < 1.0f);
+                // sanitised staged crop: "no depth" is NaN, and real NaNs never get here
+                ok[i] = STAGED ? (d4[j] == d4[j]) : !(fabsf(d4[j]) < 1.0f);
                 far[i] = fabsf(sz[i]) > k.t_far;
-                big[i] = !(fabsf(d4[j]) < BIG_DEPTH);
+                big[i] = fabsf(d4[j]) >= BIG_DEPTH;          // (NaN = no depth: not evaluated, not big)
                 fx[i] = __fsub_rn(__int_as_float(k.ix + (a4[j] >> 2)), kx);   //  (pix_x - cx)
                 fy[i] = __fsub_rn(ky, __int_as_float(k.iy + row4[j]));        // -(pix_y - cy)
             }
@@ -558,14 +601,14 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
             const float d13 = gather_depth<STAGED>(crop, A.w + B1.w);
             float4 v0, v1;
             bool n0 = false, n1 = false;
-            DTSDF_CLASSIFY(d00, vzf.x, v0.x, n0)
-            DTSDF_CLASSIFY(d01, vzf.y, v0.y, n0)
-            DTSDF_CLASSIFY(d02, vzf.z, v0.z, n0)
-            DTSDF_CLASSIFY(d03, vzf.w, v0.w, n0)
-            DTSDF_CLASSIFY(d10, vzf.x, v1.x, n1)
-            DTSDF_CLASSIFY(d11, vzf.y, v1.y, n1)
-            DTSDF_CLASSIFY(d12, vzf.z, v1.z, n1)
-            DTSDF_CLASSIFY(d13, vzf.w, v1.w, n1)
+            classify<STAGED>(d00, vzf.x, t_far, v0.x, n0);
+            classify<STAGED>(d01, vzf.y, t_far, v0.y, n0);
+            classify<STAGED>(d02, vzf.z, t_far, v0.z, n0);
+            classify<STAGED>(d03, vzf.w, t_far, v0.w, n0);
+            classify<STAGED>(d10, vzf.x, t_far, v1.x, n1);
+            classify<STAGED>(d11, vzf.y, t_far, v1.y, n1);
+            classify<STAGED>(d12, vzf.z, t_far, v1.z, n1);
+            classify<STAGED>(d13, vzf.w, t_far, v1.w, n1);
             if (active) {
                 float* p0 = obase + m0 * R;
                 float* p1 = obase + m1 * R;
@@ -600,7 +643,6 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
     __syncwarp();
     eval_listed<R, LAYOUT, STAGED, FAST, DEFF>(crop, sh, k, a, yf, out, list, cnt);
 }
-#undef DTSDF_CLASSIFY
 
 // ---------------------------------------------------------------- fused kernel
 template <int R, int LAYOUT, bool DEFF>
@@ -619,12 +661,14 @@ __global__ void __launch_bounds__(NT, 3) dtsdf_fused_kernel(const __grid_constan
         mbar_init(&sh->bar, 1);
         fence_mbar_init();
         sh->done = 0u;
-        sh->zero[0] = sh->zero[1] = sh->zero[2] = sh->zero[3] = 0.0f;
+        sh->nanflag[0] = sh->nanflag[1] = 0u;
+        sh->zero[0] = sh->zero[1] = sh->zero[2] = sh->zero[3] = __int_as_float(0x7fc00000);
     }
     uint32_t parity = 0;
     const float yf = __frcp_rn(a.focal);
     const bool focal_ok = a.focal >= 0x1p-30f && a.focal <= 0x1p30f;
     const bool scan = a.bbox_mode == 0;              // DTSDF_BBOX_PIXELS
+    const bool scan_exact = !(DEFF || focal_ok);     // no proven fixed-divisor form for this focal
 
     int f = blockIdx.x;
     if (f >= a.n_frames) return;
@@ -634,9 +678,12 @@ __global__ void __launch_bounds__(NT, 3) dtsdf_fused_kernel(const __grid_constan
         mbar_expect_tx(&sh->bar, (uint32_t)fr.n_pad * 4u);
         bulk_g2s(crop_s, fr.crop, (uint32_t)fr.n_pad * 4u, &sh->bar);
     }
-    if (scan) bbox_partial<DEFF>(fr, a, yf, focal_ok, sh->red);
+    if (scan) {
+        if (scan_exact) bbox_partial<DEFF, true>(fr, a, yf, sh->red);
+        else            bbox_partial<DEFF, false>(fr, a, yf, sh->red);
+    }
 
-    for (;;) {
+    for (unsigned fpar = 0;; fpar ^= 1u) {
         __syncthreads();      // (A) bbox partials are in; nobody reads the previous frame's tables any more
 
         // ---- next frame's record: loaded now by one thread, parked in shared memory before (C)
@@ -669,14 +716,14 @@ __global__ void __launch_bounds__(NT, 3) dtsdf_fused_kernel(const __grid_constan
         } else {
             float mn[3], mx[3];
             if (scan) {
-                mn[0] = mn[1] = mn[2] = SENTINEL;
-                mx[0] = mx[1] = mx[2] = -SENTINEL;
-#pragma unroll
-                for (int w = 0; w < NWARP; ++w) {
-                    const float4 p = *reinterpret_cast<const float4*>(&sh->red[w][0]);
-                    const float2 q = *reinterpret_cast<const float2*>(&sh->red[w][4]);
-                    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
-                    mx[0] = fmaxf(mx[0], p.w); mx[1] = fmaxf(mx[1], q.x); mx[2] = fmaxf(mx[2], q.y);
+                bbox_reduce(sh->red, mn, mx);
+                // the fixed-divisor scan is exact for |d| < 2^40 only: rescan with IEEE divisions
+                // if the frame holds anything larger (block-uniform, never on real data)
+                if (!scan_exact && !(fabsf(mn[2]) < BIG_DEPTH && fabsf(mx[2]) < BIG_DEPTH)) {
+                    __syncthreads();
+                    bbox_partial<DEFF, true>(fr, a, yf, sh->red);
+                    __syncthreads();
+                    bbox_reduce(sh->red, mn, mx);
                 }
             } else {                  // DTSDF_BBOX_EXTREMA: {max xyz, min xyz}, pre/process.py:120
                 const float* g = a.aux + 6 * (size_t)f;
@@ -705,6 +752,30 @@ __global__ void __launch_bounds__(NT, 3) dtsdf_fused_kernel(const __grid_constan
                 }
             }
         }
+
+        // ---- the staged crop has landed long ago (its copy started before the scan): replace
+        //      "no depth" (|d| < 1, pre/process.py:167) by NaN once, so that the voxel loop needs no
+        //      validity test.  A crop that holds NaNs itself takes the unstaged path.
+        if (fr.staged) {
+            mbar_wait(&sh->bar, parity);
+            parity ^= 1u;
+            float4* c4 = reinterpret_cast<float4*>(crop_s);
+            const int n4 = fr.n_pad >> 2;
+            const float qnan = __int_as_float(0x7fc00000);
+            int bad = 0;
+#pragma unroll 4
+            for (int i = tid; i < n4; i += NT) {
+                float4 v = c4[i];
+                bad |= unordered(v.x, v.y) | unordered(v.z, v.w);
+                v.x = fabsf(v.x) < 1.0f ? qnan : v.x;
+                v.y = fabsf(v.y) < 1.0f ? qnan : v.y;
+                v.z = fabsf(v.z) < 1.0f ? qnan : v.z;
+                v.w = fabsf(v.w) < 1.0f ? qnan : v.w;
+                c4[i] = v;
+            }
+            if (bad) sh->nanflag[fpar] = 1u;
+        }
+        if (tid == 0) sh->nanflag[fpar ^ 1u] = 0u;       // for the next frame
 
         // ---- per-axis voxel centres and the two projection tables
         //      (pre/process.py:150-159 == pre/tsdf_numba.py:26-32,36)
@@ -758,18 +829,14 @@ __global__ void __launch_bounds__(NT, 3) dtsdf_fused_kernel(const __grid_constan
         // margin 2^-10 on the far test: t_z = RN(|s_z|/trunc) > 1 + 2^-11, t_z^2 > THR_SQ
         k.t_far = fast ? __fmul_rn(trunc, 1.0009765625f) : INFINITY;
         float* out = a.vol + (size_t)f * 3 * R * R * R;
-        const bool staged = fr.staged;
         const float* crop_g = fr.crop;
 
         if (more && tid == 0) {
             sh->next_crop = ncrop;
             sh->next_box[0] = nb0; sh->next_box[1] = nb1; sh->next_box[2] = nb2; sh->next_box[3] = nb3;
         }
-        __syncthreads();      // (C) tables are complete
-        if (staged) {
-            mbar_wait(&sh->bar, parity);
-            parity ^= 1u;
-        }
+        __syncthreads();      // (C) tables and the sanitised crop are complete
+        const bool staged = fr.staged && sh->nanflag[fpar] == 0u;
 
         // ---- voxel loop
         if (fast) {
@@ -796,7 +863,10 @@ __global__ void __launch_bounds__(NT, 3) dtsdf_fused_kernel(const __grid_constan
             }
         }
         // ---- bounding-box scan of the next frame, from global memory
-        if (scan) bbox_partial<DEFF>(fr, a, yf, focal_ok, sh->red);
+        if (scan) {
+            if (scan_exact) bbox_partial<DEFF, true>(fr, a, yf, sh->red);
+            else            bbox_partial<DEFF, false>(fr, a, yf, sh->red);
+        }
         f = fn;
     }
 }

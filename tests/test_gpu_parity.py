@@ -181,6 +181,30 @@ def test_edge_crops(vox):
         assert np.array_equal(max_l, cml) and np.array_equal(mid_p, cmp_)
 
 
+def test_nan_and_huge_depths(vox):
+    """Pixels holding NaN are not 'no depth' in the reference (abs(d) < 1 is false for NaN,
+    pre/process.py:167): the voxels that project onto them come out NaN.  Such a crop leaves
+    the sanitised staged path; depths beyond 2^40 leave the fixed-divisor scan."""
+    a = synth.make_frame(11)
+    a["depth"] = a["depth"].copy()
+    valid = np.flatnonzero(a["depth"] > 0)
+    a["depth"][valid[::37]] = np.nan
+    b = synth.make_frame(12)
+    b["depth"] = b["depth"].copy()
+    valid = np.flatnonzero(b["depth"] > 0)
+    b["depth"][valid[5]] = np.float32(3e12)
+    b["depth"][valid[9]] = np.float32(-2e13)
+    c = synth.make_frame(13)                                   # an ordinary neighbour in the same batch
+    headers, offsets, packed = pack_simple([a, b, c, a])
+    for layout in (0, 1):
+        vol, max_l, mid_p = vox.voxelize_packed(headers, offsets, packed, layout=layout)
+        cv, cml, cmp_, _ = c_oracle.dtsdf_batch(headers, offsets, packed, layout=layout)
+        assert np.isnan(cv[0]).any() and not np.isnan(cv[2]).any()
+        for i in range(4):
+            assert _same(vol[i], cv[i]), "frame %d layout %d" % (i, layout)
+        assert np.array_equal(max_l, cml) and np.array_equal(mid_p, cmp_)
+
+
 def test_empty_batch_and_bad_arguments(vox):
     vol, max_l, mid_p = vox.voxelize_frames([])
     assert vol.shape == (0, 3, 32, 32, 32) and max_l.shape == (0,)
