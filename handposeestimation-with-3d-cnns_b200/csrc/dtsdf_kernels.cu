@@ -609,16 +609,23 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
             classify<STAGED>(d11, vzf.y, t_far, v1.y, n1);
             classify<STAGED>(d12, vzf.z, t_far, v1.z, n1);
             classify<STAGED>(d13, vzf.w, t_far, v1.w, n1);
-            if (active) {
+            // Sectors (32 bytes = the groups of an even/odd lane pair) with near voxels are written
+            // by pass 2 only, whole: every byte crosses the SM -> L2 write path once and no sector
+            // is ever written in halves (a half-written sector costs L2 a fill from DRAM).
+            unsigned bal0 = __ballot_sync(FULL, n0 && active);
+            unsigned bal1 = __ballot_sync(FULL, n1 && active);
+            bal0 |= ((bal0 & 0x55555555u) << 1) | ((bal0 & 0xAAAAAAAAu) >> 1);
+            bal1 |= ((bal1 & 0x55555555u) << 1) | ((bal1 & 0xAAAAAAAAu) >> 1);
+            n0 = (bal0 >> lane) & 1u;
+            n1 = (bal1 >> lane) & 1u;
+            if (active && !n0) {
                 float* p0 = obase + m0 * R;
-                float* p1 = obase + m1 * R;
                 st_f4(p0, v0); st_f4(p0 + CH, v0); st_f4(p0 + 2 * CH, v0);
+            }
+            if (active && !n1) {
+                float* p1 = obase + m1 * R;
                 st_f4(p1, v1); st_f4(p1 + CH, v1); st_f4(p1 + 2 * CH, v1);
             }
-            n0 = n0 && active;
-            n1 = n1 && active;
-            const unsigned bal0 = __ballot_sync(FULL, n0);
-            const unsigned bal1 = __ballot_sync(FULL, n1);
             if (n0) list[cnt + __popc(bal0 & lt)] = (unsigned short)(ebase | (m0 << 5));
             cnt += __popc(bal0);
             if (n1) list[cnt + __popc(bal1 & lt)] = (unsigned short)(ebase | (m1 << 5));
