@@ -13,20 +13,20 @@
 // with __fadd_rn/__fmul_rn/__fdiv_rn, which the compiler never contracts into FMAs.
 // The file is also compiled with -fmad=false.
 //
-// Design (persistent CTAs; one CTA works on one frame at a time, 8 warps):
-//   per frame                                              who            sync
-//   ------------------------------------------------------------------------------------
-//   A  block-reduce the bbox partials, grid parameters     all threads    barrier before
-//   B  projection tables at[s][f], yt (the projection      all threads
-//      separates: pix_x depends on (x,z), pix_y on (y,z))
-//   C  voxel loop, two interleaved passes                  warps, free-   barrier before,
-//                                                          running        crop mbarrier
-//   D  "crop buffer free" arrival; the last warp to        lane 0 of
-//      arrive starts the TMA bulk copy of the NEXT crop    each warp
-//   E  bbox scan of the NEXT frame straight from global    warps, free-
-//      memory (L2), partials to shared memory              running
-//   so the crop copy (cp.async.bulk -> mbarrier) and the scan of frame f+1 overlap the
-//   stragglers of frame f, and nobody ever waits for a crop to land.
+// Design: ONE CTA (8 warps) PER FRAME, grid = number of frames.  The hardware block
+// scheduler balances ragged batches, and - measured on B200 - CTAs that come and go keep the
+// HBM write stream 15-40 % faster than persistent CTAs marching in lock-step (a store-only
+// variant of this kernel: 0.46 ms one CTA per frame vs 0.73 ms persistent for 8,500 frames).
+// Three CTAs are resident per SM (76 KB of shared memory each for a 120x130 crop), so the
+// prologue of one frame hides behind the voxel loops of two others.
+//   0  thread 0: frame record, mbarrier init, ONE TMA bulk copy (cp.async.bulk) of the crop
+//      global -> shared memory
+//   1  bounding-box scan of the staged crop, one warp per crop row (LDS.128), which also
+//      rewrites "no depth" pixels (|d| < 1) as NaN in place; warp reduction with
+//      redux.sync.{min,max}.f32, block reduction through shared memory            [barrier]
+//   2  grid parameters (every thread); projection tables at[s][f], yt (the projection
+//      separates: pix_x depends on (x,z), pix_y on (y,z))                          [barrier]
+//   3  voxel loop, two interleaved passes, warps free-running
 //
 // Voxel loop.  A thread owns a group of 4 consecutive voxels along the fastest output
 // axis F (z for (c,x,y,z), x for (c,z,y,x)): one 16-byte store per channel.  Within a
@@ -34,16 +34,18 @@
 // and 32/(R/4) consecutive slow-axis rows share the warp; the warp then sweeps the middle
 // axis (y).  The lane's table row at[s][f0..f0+3] and its voxel z centres stay in
 // registers for the sweep; the per-iteration table read is a broadcast; the depth gather
-// of a warp touches neighbouring pixels of one or two crop rows (few bank conflicts); the
-// stores of a warp instruction are whole 128-byte lines.
-//   pass 1 classifies every voxel with ~10 instructions: outside the crop / no depth
+// of a warp is a random gather (2.7 wavefronts on average, independent of the row pitch);
+// the stores of a warp instruction are whole 128-byte lines.
+//   pass 1 classifies every voxel with ~6 instructions: outside the crop / no depth
 //     -> 0; farther than trunc from the surface along z -> +-1 (|v_z - w_z| > trunc
-//     alone forces the Euclidean truncation); otherwise "near".  Every group is stored
-//     at once (near voxels as 0 for now), groups with near voxels are also appended to a
-//     per-warp ring list in shared memory (ballot + popc).
-//   pass 2 runs whenever 32 entries are waiting: every lane takes one listed group, runs
-//     the full per-axis evaluation where needed and rewrites the group's 3 x 16 bytes.
-//     The rewrite hits lines that are still dirty in L2, so DRAM sees each line once.
+//     alone forces the Euclidean truncation); otherwise "near".  Sectors (32 B, an even/odd
+//     lane pair) without near voxels are stored at once; the others are appended to a
+//     per-warp list in shared memory (ballot + popc) and left to pass 2, so every byte
+//     crosses the SM -> L2 write path once and no sector is ever written in halves (a
+//     half-written sector costs L2 a fill from DRAM: measured 1.06 ms vs 0.76 ms).
+//   pass 2 runs at the end of a row group on whole batches of 32 listed groups: every lane
+//     takes one group, runs the full per-axis evaluation two voxels at a time on the packed
+//     FP32 pipe (FFMA2/FMUL2) and stores the group's 3 x 16 bytes.
 // Divisions: x/focal and x/trunc have per-launch / per-frame constant divisors; they
 // are evaluated as q = a*y, then one or two residual corrections q += fma(-b,q,a)*y
 // with y = rcp_rn(b) (Markstein).  With a correctly rounded reciprocal and a faithful
@@ -57,6 +59,7 @@
 
 #include <math.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 namespace dtsdf {
 
@@ -74,6 +77,7 @@ constexpr float BIG_DEPTH = 1099511627776.0f;          // 2^40: depth range of t
 constexpr int OUTSIDE = -(1 << 30);                    // table sentinel: projection outside the crop
 constexpr unsigned DEFAULT_FOCAL_BITS = 0x43716B85u;   // 241.42f
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int QNAN_BITS = 0x7fc00000;
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -84,9 +88,6 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 }
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
@@ -101,10 +102,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
-// L2 prefetch of a byte range (multiple of 16)
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     uint32_t done;
     do {
@@ -118,14 +115,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
     } while (!done);
 }
 __device__ __forceinline__ void st_f4(float* p, const float4& v) {
+#ifdef DTSDF_EXP_NOSTORE            /* dev ablation: everything but the stores */
+    if (v.x != 123456.0f) return;
+#endif
     asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
-}
-// 1 if either operand is a NaN
-__device__ __forceinline__ int unordered(float a, float b) {
-    int r;
-    asm("{\n\t.reg .pred p;\n\tsetp.nan.f32 p, %1, %2;\n\tselp.s32 %0, 1, 0, p;\n\t}" : "=r"(r) : "f"(a), "f"(b));
-    return r;
 }
 __device__ __forceinline__ float warp_min(float v) {
     float r;
@@ -163,12 +157,9 @@ struct __align__(16) FrameShared {
     static constexpr int LIST_CAP = 32 + 32 * (R / NWARP);
     unsigned short list[NWARP][LIST_CAP];
     unsigned long long bar;         // crop TMA completion barrier
-    const float* next_crop;         // the next frame's record (registers are scarce in the voxel loop)
-    int next_box[4];                // left, top, right, bottom
-    unsigned int done;              // warps that have finished reading the crop (running count)
-    unsigned int nanflag[2];        // by frame parity: the staged crop holds a NaN (take the unstaged path)
+    unsigned int nanflag;           // the staged crop holds a NaN: take the unstaged path
     unsigned int pad_;
-    float zero[4];                  // zero[3] sits right below the crop: target of "outside" gathers (NaN)
+    float nodepth[4];               // nodepth[3] sits right below the crop: target of "outside" gathers (NaN)
 };
 
 struct Frame {
@@ -186,12 +177,13 @@ struct VoxConst {
     float t_far;     // |v_z - w_z| above this forces truncation; +inf disables the shortcut
 };
 
-// frame record (pre/tsdf_numba.py:122-129) from its bounding box and crop address
-__device__ __forceinline__ Frame make_frame(int l, int t, int r, int b, const float* crop, int cap_floats) {
+// frame record (pre/tsdf_numba.py:122-129)
+__device__ __forceinline__ Frame load_frame(const BatchArgs& a, int f) {
+    const int* h = a.headers + 6 * (size_t)f;
     Frame fr;
-    fr.l = l; fr.t = t; fr.r = r; fr.b = b;
-    fr.bw = r - l;
-    fr.bh = b - t;
+    fr.l = __ldg(h + 2); fr.t = __ldg(h + 3); fr.r = __ldg(h + 4); fr.b = __ldg(h + 5);
+    fr.bw = fr.r - fr.l;
+    fr.bh = fr.b - fr.t;
     const int lim = 1 << 22;
     const bool bad = fr.bw <= 0 || fr.bh <= 0 || fr.bw > 32767 || fr.bh > 32767 ||
                      (long long)fr.bw * fr.bh > (1ll << 26) ||      // byte offsets stay below 2^28
@@ -199,15 +191,9 @@ __device__ __forceinline__ Frame make_frame(int l, int t, int r, int b, const fl
     if (bad) { fr.bw = 0; fr.bh = 0; }
     fr.n = fr.bw * fr.bh;
     fr.n_pad = (fr.n + 3) & ~3;
-    fr.crop = crop;
-    fr.staged = fr.n_pad > 0 && fr.n_pad <= cap_floats;     // CTA-uniform
+    fr.crop = a.depth + __ldg(a.offsets + f);
+    fr.staged = fr.n_pad > 0 && fr.n_pad <= a.cap_floats;     // CTA-uniform
     return fr;
-}
-
-__device__ __forceinline__ Frame load_frame(const BatchArgs& a, int f) {
-    const int* h = a.headers + 6 * (size_t)f;
-    return make_frame(__ldg(h + 2), __ldg(h + 3), __ldg(h + 4), __ldg(h + 5), a.depth + __ldg(a.offsets + f),
-                      a.cap_floats);
 }
 
 // ---------------------------------------------------------------- bounding box scan
@@ -219,24 +205,26 @@ __device__ __forceinline__ Frame load_frame(const BatchArgs& a, int f) {
 // back-projects those.  The result is the same min/max the reference computes over all valid
 // pixels.  Invalid pixels (|d| < 1, pre/tsdf_numba.py:87) become NaN, which fminf/fmaxf skip;
 // a row without valid pixels yields +-inf extremes whose quotient is NaN as well.
-// One warp per crop row, four rows in flight per warp; reads global memory (L2) directly.
-// VEC: rows start 16-byte aligned (bw % 4 == 0): a lane owns 4 adjacent columns (one LDG.128);
-// otherwise columns lane, lane+32, lane+64, lane+96 of the panel (4 coalesced scalar loads).
+// One warp per crop row, four rows in flight per warp.
+// SMEM: `crop` is the staged copy in shared memory; the scan writes the NaN-for-no-depth form
+//       back in place (the voxel loop then needs no validity test) and reports whether the crop
+//       holds NaNs of its own (`nansum`).  Otherwise `crop` is global memory, read-only.
+// VEC:  rows start 16-byte aligned (bw % 4 == 0): a lane owns 4 adjacent columns (one 128-bit
+//       access); otherwise columns lane, lane+32, lane+64, lane+96 of the panel.
 // EXACT: IEEE division; otherwise the fixed-divisor form, valid while |d| < BIG_DEPTH (the
-// caller checks the depth range afterwards and rescans with EXACT if needed).
+//       caller checks the depth range afterwards and rescans with EXACT if needed).
 template <bool ONE, bool EXACT>
 __device__ __forceinline__ float div_focal(float d, float focal, float yf) {
     return EXACT ? __fdiv_rn(d, focal) : div_fixed<ONE>(d, focal, yf);
 }
 
-template <bool ONE, bool EXACT, bool VEC>
-__device__ __forceinline__ void bbox_scan(const Frame& fr, float focal, float yf, int cx, int cy,
-                                          float (&mn)[3], float (&mx)[3]) {
+template <bool ONE, bool EXACT, bool VEC, bool SMEM>
+__device__ __forceinline__ void bbox_scan(const Frame& fr, float* crop, float focal, float yf, int cx, int cy,
+                                          float (&mn)[3], float (&mx)[3], float2& nansum) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float kx = MAGIC_F + (float)cx;
     const float ky = MAGIC_F + (float)cy;
-    const float* __restrict__ crop = fr.crop;
-    const float qnan = __int_as_float(0x7fc00000);
+    const float qnan = __int_as_float(QNAN_BITS);
     float dlo = INFINITY, dhi = -INFINITY;           // valid depth extremes (Z = -d)
     for (int panel = 0; panel < fr.bw; panel += 128) {
         const int c0 = panel + (VEC ? 4 * lane : lane);          // first column of this lane
@@ -252,11 +240,12 @@ __device__ __forceinline__ void bbox_scan(const Frame& fr, float focal, float yf
             const float* p = crop + (size_t)row * fr.bw + c0;
             if (VEC) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (inb[0]) v = __ldg(reinterpret_cast<const float4*>(p));      // bw % 4 == 0: all four in range
+                if (inb[0]) v = SMEM ? *reinterpret_cast<const float4*>(p)     // bw % 4 == 0: all four in range
+                                     : __ldg(reinterpret_cast<const float4*>(p));
                 d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) d[j] = inb[j] ? __ldg(p + 32 * j) : 0.0f;
+                for (int j = 0; j < 4; ++j) d[j] = inb[j] ? (SMEM ? p[32 * j] : __ldg(p + 32 * j)) : 0.0f;
             }
         };
         // one row: this lane's (up to) 4 pixels
@@ -266,6 +255,18 @@ __device__ __forceinline__ void bbox_scan(const Frame& fr, float focal, float yf
             for (int j = 0; j < 4; ++j) {
                 v[j] = fabsf(d[j]) < 1.0f ? qnan : d[j];
                 cmin[j] = fminf(cmin[j], v[j]); cmax[j] = fmaxf(cmax[j], v[j]);
+            }
+            if (SMEM) {
+                // NaNs of the crop itself poison the running sums (so may inf - inf: harmless,
+                // the frame then takes the general path)
+                nansum = __fadd2_rn(nansum, __fadd2_rn(make_float2(d[0], d[1]), make_float2(d[2], d[3])));
+                float* p = crop + (size_t)row * fr.bw + c0;
+                if (VEC) {
+                    if (inb[0]) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (inb[j]) p[32 * j] = v[j];
+                }
             }
             const float rmin = fminf(fminf(fminf(v[0], INFINITY), v[1]), fminf(v[2], v[3]));
             const float rmax = fmaxf(fmaxf(fmaxf(v[0], -INFINITY), v[1]), fmaxf(v[2], v[3]));
@@ -306,21 +307,26 @@ __device__ __forceinline__ void bbox_scan(const Frame& fr, float focal, float yf
     if (dlo <= dhi) { mn[2] = fminf(mn[2], -dhi); mx[2] = fmaxf(mx[2], -dlo); }
 }
 
-// scan + warp reduction; lane 0 leaves the warp's partial in shared memory
-template <bool ONE, bool EXACT>
-__device__ __forceinline__ void bbox_partial(const Frame& fr, const BatchArgs& a, float yf, float (*red)[8]) {
+// scan + warp reduction; lane 0 leaves the warp's partial in shared memory.  Returns true if
+// this thread saw a NaN in the staged crop (SMEM only).
+template <bool ONE, bool EXACT, bool SMEM>
+__device__ __forceinline__ bool bbox_partial(const Frame& fr, float* crop, const BatchArgs& a, float yf,
+                                             float (*red)[8]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float mn[3], mx[3];
+    float2 nansum = make_float2(0.f, 0.f);
     mn[0] = mn[1] = mn[2] = SENTINEL;
     mx[0] = mx[1] = mx[2] = -SENTINEL;
-    if ((fr.bw & 3) == 0) bbox_scan<ONE, EXACT, true>(fr, a.focal, yf, a.center_x, a.center_y, mn, mx);
-    else                  bbox_scan<ONE, EXACT, false>(fr, a.focal, yf, a.center_x, a.center_y, mn, mx);
+    if ((fr.bw & 3) == 0) bbox_scan<ONE, EXACT, true, SMEM>(fr, crop, a.focal, yf, a.center_x, a.center_y, mn, mx, nansum);
+    else                  bbox_scan<ONE, EXACT, false, SMEM>(fr, crop, a.focal, yf, a.center_x, a.center_y, mn, mx, nansum);
 #pragma unroll
     for (int c = 0; c < 3; ++c) { mn[c] = warp_min(mn[c]); mx[c] = warp_max(mx[c]); }
     if (lane == 0) {
         *reinterpret_cast<float4*>(&red[warp][0]) = make_float4(mn[0], mn[1], mn[2], mx[0]);
         *reinterpret_cast<float2*>(&red[warp][4]) = make_float2(mx[1], mx[2]);
     }
+    const float t = __fadd_rn(nansum.x, nansum.y);
+    return t != t;
 }
 
 // block reduction of the partials (every thread gets the result)
@@ -334,6 +340,27 @@ __device__ __forceinline__ void bbox_reduce(const float (*red)[8], float (&mn)[3
         mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
         mx[0] = fmaxf(mx[0], p.w); mx[1] = fmaxf(mx[1], q.x); mx[2] = fmaxf(mx[2], q.y);
     }
+}
+
+// "no depth" -> NaN over the staged crop, for the bounding-box modes that do not scan it.
+// Returns true if this thread saw a NaN of the crop's own.
+__device__ __forceinline__ bool sanitize_crop(float* crop_s, int n_pad) {
+    float4* c4 = reinterpret_cast<float4*>(crop_s);
+    const int n4 = n_pad >> 2;
+    const float qnan = __int_as_float(QNAN_BITS);
+    float2 nansum = make_float2(0.f, 0.f);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += NT) {
+        float4 v = c4[i];
+        nansum = __fadd2_rn(nansum, __fadd2_rn(make_float2(v.x, v.y), make_float2(v.z, v.w)));
+        v.x = fabsf(v.x) < 1.0f ? qnan : v.x;
+        v.y = fabsf(v.y) < 1.0f ? qnan : v.y;
+        v.z = fabsf(v.z) < 1.0f ? qnan : v.z;
+        v.w = fabsf(v.w) < 1.0f ? qnan : v.w;
+        c4[i] = v;
+    }
+    const float t = __fadd_rn(nansum.x, nansum.y);
+    return t != t;
 }
 
 // ---------------------------------------------------------------- voxel evaluation
@@ -404,7 +431,7 @@ __device__ __forceinline__ void eval_pair(float2 d, float2 fx, float2 fy, float2
 template <bool STAGED>
 __device__ __forceinline__ float gather_depth(const float* __restrict__ crop, int off) {
     if (STAGED) {
-        // the word right below the staged crop reads as "no depth" (FrameShared::zero[3])
+        // the word right below the staged crop reads as "no depth" (FrameShared::nodepth[3])
         off = max(off, -4);
         return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(crop) + off);
     }
@@ -418,7 +445,7 @@ __device__ __forceinline__ float gather_depth(const float* __restrict__ crop, in
 //                    Euclidean truncation fires (pre/process.py:180-185) and the result is +-1
 //                    by the side of the surface (:191-194)
 //   near           : needs the full evaluation (value 0 for now)
-// SAN: the staged crop was sanitised (|d| < 1 -> NaN, FrameShared::zero[3] is NaN too), so
+// SAN: the staged crop was sanitised (|d| < 1 -> NaN, FrameShared::nodepth[3] is NaN too), so
 // "no depth" makes both comparisons false and needs no test of its own.
 template <bool SAN>
 __device__ __forceinline__ void classify(float d, float vz, float t_far, float& out, bool& near) {
@@ -546,8 +573,7 @@ __device__ __forceinline__ void eval_listed(const float* __restrict__ crop,
 template <int R, int LAYOUT, bool STAGED, bool FAST, bool DEFF>
 __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
                                              FrameShared<R, LAYOUT>* __restrict__ sh, const VoxConst& k,
-                                             const BatchArgs& a, float yf, float* __restrict__ out,
-                                             bool prefetch_next) {
+                                             const BatchArgs& a, float yf, float* __restrict__ out) {
     using LM = LaneMap<R>;
     constexpr int YS = FrameShared<R, LAYOUT>::YS;
     constexpr int CH = R * R * R;
@@ -574,11 +600,6 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
         }
         float* const obase = out + ((size_t)s * R * R + f0);
         const int ebase = (sg << 11) | lane;
-        // the next crop goes to L2 shortly before its scan (earlier, the output stream evicts it)
-        if (prefetch_next && sg == LM::NSG - 2 && threadIdx.x == 0) {
-            const int nb = ((sh->next_box[2] - sh->next_box[0]) * (sh->next_box[3] - sh->next_box[1]) + 3) & ~3;
-            if (nb > 0) bulk_prefetch_l2(sh->next_crop, (uint32_t)nb * 4u);
-        }
 #pragma unroll
         for (int ks = 0; ks < LM::MSTEPS; ks += 2) {
             const int m0 = warp + NWARP * ks, m1 = m0 + NWARP;
@@ -591,6 +612,20 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
                 B0 = make_int4(y0, y0, y0, y0);
                 B1 = make_int4(y1, y1, y1, y1);
             }
+#ifdef DTSDF_EXP_STOREONLY      /* dev ablation: the store pattern alone */
+            {
+                const float c = __int_as_float(0x3F800000 | ((m0 & 1) << 31));
+                const float4 v0 = make_float4(c, c, c, c), v1 = v0;
+                if (active) {
+                    float* p0 = obase + m0 * R;
+                    float* p1 = obase + m1 * R;
+                    st_f4(p0, v0); st_f4(p0 + CH, v0); st_f4(p0 + 2 * CH, v0);
+                    st_f4(p1, v1); st_f4(p1 + CH, v1); st_f4(p1 + 2 * CH, v1);
+                }
+                (void)B0; (void)B1; (void)t_far; (void)lt; (void)ebase; (void)A;
+                continue;
+            }
+#endif
             const float d00 = gather_depth<STAGED>(crop, A.x + B0.x);
             const float d01 = gather_depth<STAGED>(crop, A.y + B0.y);
             const float d02 = gather_depth<STAGED>(crop, A.z + B0.z);
@@ -631,6 +666,9 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
             if (n1) list[cnt + __popc(bal1 & lt)] = (unsigned short)(ebase | (m1 << 5));
             cnt += __popc(bal1);
         }
+#ifdef DTSDF_EXP_NOPASS2
+        cnt = 0;
+#endif
         // ---- pass 2 on whole batches (warp-uniform control flow)
         if (cnt >= 32) {
             __syncwarp();                 // list entries and the pass-1 stores are ordered before pass 2
@@ -652,229 +690,177 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
 }
 
 // ---------------------------------------------------------------- fused kernel
+#ifndef DTSDF_MIN_CTAS
+#define DTSDF_MIN_CTAS 3
+#endif
 template <int R, int LAYOUT, bool DEFF>
-__global__ void __launch_bounds__(NT, 3) dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
+__global__ void __launch_bounds__(NT, DTSDF_MIN_CTAS) dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     using FS = FrameShared<R, LAYOUT>;
     constexpr int YS = FS::YS;
-    static_assert(sizeof(FS) % 16 == 0 && offsetof(FS, zero) + 16 == sizeof(FS), "zero pad must touch the crop");
+    static_assert(sizeof(FS) % 16 == 0 && offsetof(FS, nodepth) + 16 == sizeof(FS), "the pad must touch the crop");
     static_assert(LaneMap<R>::MSTEPS % 2 == 0, "the sweep is unrolled by two");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FS* sh = reinterpret_cast<FS*>(smem_raw);
     float* crop_s = reinterpret_cast<float*>(smem_raw + sizeof(FS));
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
+    const int f = blockIdx.x;
 
+    // ---- 0. frame record; thread 0 starts the TMA bulk copy of the crop into shared memory
+    const Frame fr = load_frame(a, f);
     if (tid == 0) {
         mbar_init(&sh->bar, 1);
         fence_mbar_init();
-        sh->done = 0u;
-        sh->nanflag[0] = sh->nanflag[1] = 0u;
-        sh->zero[0] = sh->zero[1] = sh->zero[2] = sh->zero[3] = __int_as_float(0x7fc00000);
+        if (fr.staged) {
+            mbar_expect_tx(&sh->bar, (uint32_t)fr.n_pad * 4u);
+            bulk_g2s(crop_s, fr.crop, (uint32_t)fr.n_pad * 4u, &sh->bar);
+        }
+        sh->nanflag = 0u;
+        sh->nodepth[0] = sh->nodepth[1] = sh->nodepth[2] = sh->nodepth[3] = __int_as_float(QNAN_BITS);
     }
-    uint32_t parity = 0;
     const float yf = __frcp_rn(a.focal);
     const bool focal_ok = a.focal >= 0x1p-30f && a.focal <= 0x1p30f;
     const bool scan = a.bbox_mode == 0;              // DTSDF_BBOX_PIXELS
     const bool scan_exact = !(DEFF || focal_ok);     // no proven fixed-divisor form for this focal
+    __syncthreads();                                  // the mbarrier is initialised
 
-    int f = blockIdx.x;
-    if (f >= a.n_frames) return;
-    Frame fr = load_frame(a, f);
-    __syncthreads();                                  // barrier initialised
-    if (fr.staged && tid == 0) {
-        mbar_expect_tx(&sh->bar, (uint32_t)fr.n_pad * 4u);
-        bulk_g2s(crop_s, fr.crop, (uint32_t)fr.n_pad * 4u, &sh->bar);
+    // ---- 1. bounding-box scan (pre/tsdf_numba.py:75-116) of the staged crop, which also turns
+    //         "no depth" into NaN in place; crops too large for shared memory are scanned in
+    //         global memory and left alone
+    bool sawnan = false;
+    if (fr.staged) {
+        mbar_wait(&sh->bar, 0);
+        if (!scan)           sawnan = sanitize_crop(crop_s, fr.n_pad);
+        else if (scan_exact) sawnan = bbox_partial<DEFF, true, true>(fr, crop_s, a, yf, sh->red);
+        else                 sawnan = bbox_partial<DEFF, false, true>(fr, crop_s, a, yf, sh->red);
+    } else if (scan) {
+        if (scan_exact) bbox_partial<DEFF, true, false>(fr, const_cast<float*>(fr.crop), a, yf, sh->red);
+        else            bbox_partial<DEFF, false, false>(fr, const_cast<float*>(fr.crop), a, yf, sh->red);
     }
-    if (scan) {
-        if (scan_exact) bbox_partial<DEFF, true>(fr, a, yf, sh->red);
-        else            bbox_partial<DEFF, false>(fr, a, yf, sh->red);
-    }
+    if (sawnan) sh->nanflag = 1u;
+    __syncthreads();      // (A) bbox partials, sanitised crop and the NaN flag are in
 
-    for (unsigned fpar = 0;; fpar ^= 1u) {
-        __syncthreads();      // (A) bbox partials are in; nobody reads the previous frame's tables any more
-
-        // ---- next frame's record: loaded now by one thread, parked in shared memory before (C)
-        const int fn = f + (int)gridDim.x;
-        const bool more = fn < a.n_frames;
-        int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0;
-        const float* ncrop = nullptr;
-        if (more && tid == 0) {
-            const int* h = a.headers + 6 * (size_t)fn;
-            nb0 = __ldg(h + 2); nb1 = __ldg(h + 3); nb2 = __ldg(h + 4); nb3 = __ldg(h + 5);
-            ncrop = a.depth + __ldg(a.offsets + fn);
-        }
-
-        // ---- bounding box (pre/tsdf_numba.py:75-116,140-141) or caller-supplied
-        float ox, oy, oz, voxel_len, trunc;
-        if (a.bbox_mode == 2) {       // DTSDF_BBOX_GRID: pre/process.py:122 arguments
-            const float* g = a.aux + 5 * (size_t)f;
-            ox = __ldg(g); oy = __ldg(g + 1); oz = __ldg(g + 2);
-            voxel_len = __ldg(g + 3); trunc = __ldg(g + 4);
-            if (tid == 0) {
-                if (a.max_l) a.max_l[f] = __fmul_rn(voxel_len, (float)R);
-                if (a.mid_p) {
-                    // centre of the cube: vox_ori + (R-1)/2 * voxel_len (informational only)
-                    const float hl = __fmul_rn(voxel_len, 0.5f * (float)(R - 1));
-                    a.mid_p[3 * (size_t)f + 0] = __fadd_rn(ox, hl);
-                    a.mid_p[3 * (size_t)f + 1] = __fadd_rn(oy, hl);
-                    a.mid_p[3 * (size_t)f + 2] = __fadd_rn(oz, hl);
-                }
-            }
-        } else {
-            float mn[3], mx[3];
-            if (scan) {
-                bbox_reduce(sh->red, mn, mx);
-                // the fixed-divisor scan is exact for |d| < 2^40 only: rescan with IEEE divisions
-                // if the frame holds anything larger (block-uniform, never on real data)
-                if (!scan_exact && !(fabsf(mn[2]) < BIG_DEPTH && fabsf(mx[2]) < BIG_DEPTH)) {
-                    __syncthreads();
-                    bbox_partial<DEFF, true>(fr, a, yf, sh->red);
-                    __syncthreads();
-                    bbox_reduce(sh->red, mn, mx);
-                }
-            } else {                  // DTSDF_BBOX_EXTREMA: {max xyz, min xyz}, pre/process.py:120
-                const float* g = a.aux + 6 * (size_t)f;
-                mx[0] = __ldg(g); mx[1] = __ldg(g + 1); mx[2] = __ldg(g + 2);
-                mn[0] = __ldg(g + 3); mn[1] = __ldg(g + 4); mn[2] = __ldg(g + 5);
-            }
-            // ---- grid parameters (pre/process.py:91-96 == pre/tsdf_numba.py:142-147)
-            const float mid0 = __fmul_rn(__fadd_rn(mx[0], mn[0]), 0.5f);
-            const float mid1 = __fmul_rn(__fadd_rn(mx[1], mn[1]), 0.5f);
-            const float mid2 = __fmul_rn(__fadd_rn(mx[2], mn[2]), 0.5f);
-            const float max_l = fmaxf(fmaxf(__fsub_rn(mx[0], mn[0]), __fsub_rn(mx[1], mn[1])),
-                                      __fsub_rn(mx[2], mn[2]));
-            voxel_len = __fdiv_rn(max_l, (float)R);
-            trunc = __fmul_rn(voxel_len, a.trunc_mul);
-            const float half_l = __fmul_rn(max_l, 0.5f);
-            const float half_v = __fmul_rn(voxel_len, 0.5f);
-            ox = __fadd_rn(__fsub_rn(mid0, half_l), half_v);
-            oy = __fadd_rn(__fsub_rn(mid1, half_l), half_v);
-            oz = __fadd_rn(__fsub_rn(mid2, half_l), half_v);
-            if (tid == 0) {
-                if (a.max_l) a.max_l[f] = max_l;
-                if (a.mid_p) {
-                    a.mid_p[3 * (size_t)f + 0] = mid0;
-                    a.mid_p[3 * (size_t)f + 1] = mid1;
-                    a.mid_p[3 * (size_t)f + 2] = mid2;
-                }
+    // ---- 2. bounding box -> grid parameters
+    float ox, oy, oz, voxel_len, trunc;
+    if (a.bbox_mode == 2) {       // DTSDF_BBOX_GRID: pre/process.py:122 arguments
+        const float* g = a.aux + 5 * (size_t)f;
+        ox = __ldg(g); oy = __ldg(g + 1); oz = __ldg(g + 2);
+        voxel_len = __ldg(g + 3); trunc = __ldg(g + 4);
+        if (tid == 0) {
+            if (a.max_l) a.max_l[f] = __fmul_rn(voxel_len, (float)R);
+            if (a.mid_p) {
+                // centre of the cube: vox_ori + (R-1)/2 * voxel_len (informational only)
+                const float hl = __fmul_rn(voxel_len, 0.5f * (float)(R - 1));
+                a.mid_p[3 * (size_t)f + 0] = __fadd_rn(ox, hl);
+                a.mid_p[3 * (size_t)f + 1] = __fadd_rn(oy, hl);
+                a.mid_p[3 * (size_t)f + 2] = __fadd_rn(oz, hl);
             }
         }
-
-        // ---- the staged crop has landed long ago (its copy started before the scan): replace
-        //      "no depth" (|d| < 1, pre/process.py:167) by NaN once, so that the voxel loop needs no
-        //      validity test.  A crop that holds NaNs itself takes the unstaged path.
-        if (fr.staged) {
-            mbar_wait(&sh->bar, parity);
-            parity ^= 1u;
-            float4* c4 = reinterpret_cast<float4*>(crop_s);
-            const int n4 = fr.n_pad >> 2;
-            const float qnan = __int_as_float(0x7fc00000);
-            int bad = 0;
-#pragma unroll 4
-            for (int i = tid; i < n4; i += NT) {
-                float4 v = c4[i];
-                bad |= unordered(v.x, v.y) | unordered(v.z, v.w);
-                v.x = fabsf(v.x) < 1.0f ? qnan : v.x;
-                v.y = fabsf(v.y) < 1.0f ? qnan : v.y;
-                v.z = fabsf(v.z) < 1.0f ? qnan : v.z;
-                v.w = fabsf(v.w) < 1.0f ? qnan : v.w;
-                c4[i] = v;
-            }
-            if (bad) sh->nanflag[fpar] = 1u;
-        }
-        if (tid == 0) sh->nanflag[fpar ^ 1u] = 0u;       // for the next frame
-
-        // ---- per-axis voxel centres and the two projection tables
-        //      (pre/process.py:150-159 == pre/tsdf_numba.py:26-32,36)
-        if (tid < R) {
-            const float sft = __fmul_rn((float)tid, voxel_len);
-            sh->vx[tid] = __fadd_rn(ox, sft);
-            sh->vy[tid] = __fadd_rn(oy, sft);
-            sh->vz[tid] = __fadd_rn(oz, sft);
-        }
-        {
-            // entry e: zi = e % R is the z index, ti = e / R the x (at) / y (yt) index.  With
-            // NT a multiple of R the z index, and with it the division, is the same for every
-            // entry of a thread.
-            constexpr bool HOIST = (NT % R) == 0;
-            float coeff_h = 0.0f;
-            if (HOIST) coeff_h = __fdiv_rn(-a.focal, __fadd_rn(oz, __fmul_rn((float)(tid % R), voxel_len)));
-#pragma unroll 2
-            for (int e = tid; e < R * R; e += NT) {
-                const int ti = e / R, zi = e % R;
-                const float coeff = HOIST ? coeff_h
-                                          : __fdiv_rn(-a.focal, __fadd_rn(oz, __fmul_rn((float)zi, voxel_len)));
-                const float sft = __fmul_rn((float)ti, voxel_len);
-                const float fpx = __fadd_rn(__fmul_rn(__fadd_rn(ox, sft), coeff), (float)a.center_x);
-                const float fpy = __fadd_rn(__fmul_rn(-__fadd_rn(oy, sft), coeff), (float)a.center_y);
-                const int px = __float2int_rz(fpx);          // int(): truncation toward zero
-                const int py = __float2int_rz(fpy);
-                const bool okx = fabsf(fpx) < 2e9f && px >= fr.l && px < fr.r;   // non-finite -> outside
-                const bool oky = fabsf(fpy) < 2e9f && py >= fr.t && py < fr.b;   // (bad header: empty ranges)
-                // at[s][f]: CXYZ s = x, f = z; CZYX s = z, f = x.   yt: CXYZ [y][z]; CZYX [z][y]
-                const int ia = (LAYOUT == 0) ? ti * R + zi : zi * R + ti;
-                const int iy = (LAYOUT == 0) ? ti * YS + zi : zi * YS + ti;
-                sh->at[ia] = okx ? 4 * (px - fr.l) : OUTSIDE;
-                sh->yt[iy] = oky ? 4 * fr.bw * (py - fr.t) : OUTSIDE;
-                sh->yr[iy] = oky ? (short)(py - fr.t) : (short)0;
-            }
-        }
-
-        // the fixed-divisor divisions are proven for these ranges (file header); anything else
-        // takes the generic IEEE path
-        const float ax = fabsf(ox), ay = fabsf(oy), az = fabsf(oz);
-        const bool fast = (DEFF || focal_ok) && trunc >= 0x1p-30f && trunc <= 0x1p30f &&
-                          voxel_len >= 0x1p-30f && voxel_len <= 0x1p30f &&
-                          (ax == 0.0f || (ax >= 0x1p-60f && ax <= 0x1p30f)) &&
-                          (ay == 0.0f || (ay >= 0x1p-60f && ay <= 0x1p30f)) &&
-                          (az == 0.0f || (az >= 0x1p-60f && az <= 0x1p30f));
-        VoxConst k;
-        k.ix = MAGIC_I + fr.l;
-        k.iy = MAGIC_I + fr.t;
-        k.trunc = trunc;
-        k.yt = __frcp_rn(trunc);
-        // margin 2^-10 on the far test: t_z = RN(|s_z|/trunc) > 1 + 2^-11, t_z^2 > THR_SQ
-        k.t_far = fast ? __fmul_rn(trunc, 1.0009765625f) : INFINITY;
-        float* out = a.vol + (size_t)f * 3 * R * R * R;
-        const float* crop_g = fr.crop;
-
-        if (more && tid == 0) {
-            sh->next_crop = ncrop;
-            sh->next_box[0] = nb0; sh->next_box[1] = nb1; sh->next_box[2] = nb2; sh->next_box[3] = nb3;
-        }
-        __syncthreads();      // (C) tables and the sanitised crop are complete
-        const bool staged = fr.staged && sh->nanflag[fpar] == 0u;
-
-        // ---- voxel loop
-        if (fast) {
-            if (staged) voxel_passes<R, LAYOUT, true, true, DEFF>(crop_s, sh, k, a, yf, out, more);
-            else        voxel_passes<R, LAYOUT, false, true, DEFF>(crop_g, sh, k, a, yf, out, more);
-        } else {
-            if (staged) voxel_passes<R, LAYOUT, true, false, DEFF>(crop_s, sh, k, a, yf, out, more);
-            else        voxel_passes<R, LAYOUT, false, false, DEFF>(crop_g, sh, k, a, yf, out, more);
-        }
-        if (!more) break;
-
-        // ---- this warp is done with the staged crop; the last warp to get here starts the
-        //      copy of the next one.  Every lane's reads were consumed before its stores were
-        //      issued, and the warp issues in order, so they are complete at this point.
-        fr = make_frame(sh->next_box[0], sh->next_box[1], sh->next_box[2], sh->next_box[3], sh->next_crop,
-                        a.cap_floats);
-        __syncwarp();
-        if (lane == 0) {
-            const unsigned prev = atomicAdd(&sh->done, 1u);
-            if ((prev % NWARP) == NWARP - 1 && fr.staged) {
-                fence_proxy_async();      // generic-proxy reads of crop_s happen-before the async write
-                mbar_expect_tx(&sh->bar, (uint32_t)fr.n_pad * 4u);
-                bulk_g2s(crop_s, fr.crop, (uint32_t)fr.n_pad * 4u, &sh->bar);
-            }
-        }
-        // ---- bounding-box scan of the next frame, from global memory
+    } else {
+        float mn[3], mx[3];
         if (scan) {
-            if (scan_exact) bbox_partial<DEFF, true>(fr, a, yf, sh->red);
-            else            bbox_partial<DEFF, false>(fr, a, yf, sh->red);
+            bbox_reduce(sh->red, mn, mx);
+            // the fixed-divisor scan is exact for |d| < 2^40 only: rescan with IEEE divisions
+            // if the frame holds anything larger (block-uniform, never on real data; the
+            // sanitised crop scans like the original)
+            if (!scan_exact && !(fabsf(mn[2]) < BIG_DEPTH && fabsf(mx[2]) < BIG_DEPTH)) {
+                __syncthreads();
+                if (fr.staged) bbox_partial<DEFF, true, true>(fr, crop_s, a, yf, sh->red);
+                else           bbox_partial<DEFF, true, false>(fr, const_cast<float*>(fr.crop), a, yf, sh->red);
+                __syncthreads();
+                bbox_reduce(sh->red, mn, mx);
+            }
+        } else {                  // DTSDF_BBOX_EXTREMA: {max xyz, min xyz}, pre/process.py:120
+            const float* g = a.aux + 6 * (size_t)f;
+            mx[0] = __ldg(g); mx[1] = __ldg(g + 1); mx[2] = __ldg(g + 2);
+            mn[0] = __ldg(g + 3); mn[1] = __ldg(g + 4); mn[2] = __ldg(g + 5);
         }
-        f = fn;
+        // grid parameters (pre/process.py:91-96 == pre/tsdf_numba.py:142-147)
+        const float mid0 = __fmul_rn(__fadd_rn(mx[0], mn[0]), 0.5f);
+        const float mid1 = __fmul_rn(__fadd_rn(mx[1], mn[1]), 0.5f);
+        const float mid2 = __fmul_rn(__fadd_rn(mx[2], mn[2]), 0.5f);
+        const float max_l = fmaxf(fmaxf(__fsub_rn(mx[0], mn[0]), __fsub_rn(mx[1], mn[1])),
+                                  __fsub_rn(mx[2], mn[2]));
+        voxel_len = __fdiv_rn(max_l, (float)R);
+        trunc = __fmul_rn(voxel_len, a.trunc_mul);
+        const float half_l = __fmul_rn(max_l, 0.5f);
+        const float half_v = __fmul_rn(voxel_len, 0.5f);
+        ox = __fadd_rn(__fsub_rn(mid0, half_l), half_v);
+        oy = __fadd_rn(__fsub_rn(mid1, half_l), half_v);
+        oz = __fadd_rn(__fsub_rn(mid2, half_l), half_v);
+        if (tid == 0) {
+            if (a.max_l) a.max_l[f] = max_l;
+            if (a.mid_p) {
+                a.mid_p[3 * (size_t)f + 0] = mid0;
+                a.mid_p[3 * (size_t)f + 1] = mid1;
+                a.mid_p[3 * (size_t)f + 2] = mid2;
+            }
+        }
+    }
+
+    // ---- per-axis voxel centres and the two projection tables
+    //      (pre/process.py:150-159 == pre/tsdf_numba.py:26-32,36)
+    if (tid < R) {
+        const float sft = __fmul_rn((float)tid, voxel_len);
+        sh->vx[tid] = __fadd_rn(ox, sft);
+        sh->vy[tid] = __fadd_rn(oy, sft);
+        sh->vz[tid] = __fadd_rn(oz, sft);
+    }
+    {
+        // entry e: zi = e % R is the z index, ti = e / R the x (at) / y (yt) index.  With
+        // NT a multiple of R the z index, and with it the division, is the same for every
+        // entry of a thread.
+        constexpr bool HOIST = (NT % R) == 0;
+        float coeff_h = 0.0f;
+        if (HOIST) coeff_h = __fdiv_rn(-a.focal, __fadd_rn(oz, __fmul_rn((float)(tid % R), voxel_len)));
+#pragma unroll 2
+        for (int e = tid; e < R * R; e += NT) {
+            const int ti = e / R, zi = e % R;
+            const float coeff = HOIST ? coeff_h
+                                      : __fdiv_rn(-a.focal, __fadd_rn(oz, __fmul_rn((float)zi, voxel_len)));
+            const float sft = __fmul_rn((float)ti, voxel_len);
+            const float fpx = __fadd_rn(__fmul_rn(__fadd_rn(ox, sft), coeff), (float)a.center_x);
+            const float fpy = __fadd_rn(__fmul_rn(-__fadd_rn(oy, sft), coeff), (float)a.center_y);
+            const int px = __float2int_rz(fpx);          // int(): truncation toward zero
+            const int py = __float2int_rz(fpy);
+            const bool okx = fabsf(fpx) < 2e9f && px >= fr.l && px < fr.r;   // non-finite -> outside
+            const bool oky = fabsf(fpy) < 2e9f && py >= fr.t && py < fr.b;   // (bad header: empty ranges)
+            // at[s][f]: CXYZ s = x, f = z; CZYX s = z, f = x.   yt: CXYZ [y][z]; CZYX [z][y]
+            const int ia = (LAYOUT == 0) ? ti * R + zi : zi * R + ti;
+            const int iy = (LAYOUT == 0) ? ti * YS + zi : zi * YS + ti;
+            sh->at[ia] = okx ? 4 * (px - fr.l) : OUTSIDE;
+            sh->yt[iy] = oky ? 4 * fr.bw * (py - fr.t) : OUTSIDE;
+            sh->yr[iy] = oky ? (short)(py - fr.t) : (short)0;
+        }
+    }
+
+    // the fixed-divisor divisions are proven for these ranges (file header); anything else
+    // takes the generic IEEE path
+    const float ax = fabsf(ox), ay = fabsf(oy), az = fabsf(oz);
+    const bool fast = (DEFF || focal_ok) && trunc >= 0x1p-30f && trunc <= 0x1p30f &&
+                      voxel_len >= 0x1p-30f && voxel_len <= 0x1p30f &&
+                      (ax == 0.0f || (ax >= 0x1p-60f && ax <= 0x1p30f)) &&
+                      (ay == 0.0f || (ay >= 0x1p-60f && ay <= 0x1p30f)) &&
+                      (az == 0.0f || (az >= 0x1p-60f && az <= 0x1p30f));
+    VoxConst k;
+    k.ix = MAGIC_I + fr.l;
+    k.iy = MAGIC_I + fr.t;
+    k.trunc = trunc;
+    k.yt = __frcp_rn(trunc);
+    // margin 2^-10 on the far test: t_z = RN(|s_z|/trunc) > 1 + 2^-11, t_z^2 > THR_SQ
+    k.t_far = fast ? __fmul_rn(trunc, 1.0009765625f) : INFINITY;
+    float* out = a.vol + (size_t)f * 3 * R * R * R;
+
+    __syncthreads();      // (C) tables are complete
+    // a staged crop that holds NaNs of its own was sanitised into ambiguity: read the original
+    const bool staged = fr.staged && sh->nanflag == 0u;
+
+    // ---- 3. voxel loop
+    if (fast) {
+        if (staged) voxel_passes<R, LAYOUT, true, true, DEFF>(crop_s, sh, k, a, yf, out);
+        else        voxel_passes<R, LAYOUT, false, true, DEFF>(fr.crop, sh, k, a, yf, out);
+    } else {
+        if (staged) voxel_passes<R, LAYOUT, true, false, DEFF>(crop_s, sh, k, a, yf, out);
+        else        voxel_passes<R, LAYOUT, false, false, DEFF>(fr.crop, sh, k, a, yf, out);
     }
 }
 
@@ -884,12 +870,11 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    int smem_optin = 0, sms = 0;
+    int smem_optin = 0;
     e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
     if ((reinterpret_cast<uintptr_t>(args.vol) & 15) != 0) return cudaErrorMisalignedAddress;
+    if ((reinterpret_cast<uintptr_t>(args.depth) & 15) != 0) return cudaErrorMisalignedAddress;
     const int fixed = (int)sizeof(FrameShared<R, LAYOUT>);
     // staging capacity: the largest crop of the batch when known (the occupancy then follows from
     // it: three CTAs per SM up to ~63 KB crops, two up to ~100 KB, one above); oversize crops take the direct path.
@@ -903,13 +888,7 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     auto kern = dtsdf_fused_kernel<R, LAYOUT, DEFF>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) occ = 1;
-    long long grid = (long long)occ * sms;        // persistent: a whole number of waves
-    if (grid > args.n_frames) grid = args.n_frames;
-    kern<<<(unsigned)grid, NT, smem, stream>>>(args);
+    kern<<<(unsigned)args.n_frames, NT, smem, stream>>>(args);      // one CTA per frame
     ++g_launch_count;
     return cudaGetLastError();
 }
@@ -1041,8 +1020,10 @@ cudaError_t launch_voxelize(int voxel_res, int layout, BatchArgs args, int max_c
                     : launch_fused<RR, 1, false>(args, max_crop_px, stream);
     switch (voxel_res) {
         DTSDF_CASE(32)
+#ifndef DTSDF_EXP_ONLY32
         DTSDF_CASE(48)
         DTSDF_CASE(64)
+#endif
         default:
             return cudaErrorInvalidValue;
     }

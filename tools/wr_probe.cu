@@ -1,0 +1,48 @@
+// Dev probe: DRAM write bandwidth of a few store patterns (constant vs incompressible data).
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+__device__ __forceinline__ float4 val(size_t i, int rnd) {
+    if (!rnd) return make_float4(1.f, 1.f, 1.f, 1.f);
+    unsigned h = (unsigned)i * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    return make_float4(__uint_as_float(0x3f000000u | (h & 0x7fffff)), __uint_as_float(0x3f000000u | ((h * 3u) & 0x7fffff)),
+                       __uint_as_float(0x3f000000u | ((h * 5u) & 0x7fffff)), __uint_as_float(0x3f000000u | ((h * 7u) & 0x7fffff)));
+}
+// K1: grid-stride, every thread one float4 per step, whole grid sweeps linearly
+__global__ void k_linear(float4* out, size_t n4, int rnd) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) out[i] = val(i, rnd);
+}
+// K3: persistent CTAs, each writes whole frames (frame = fb float4) sequentially
+__global__ void k_frames(float4* out, int nframes, int fb, int rnd) {
+    for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
+        float4* o = out + (size_t)f * fb;
+        for (int i = threadIdx.x; i < fb; i += blockDim.x) o[i] = val((size_t)f * fb + i, rnd);
+    }
+}
+int main() {
+    const int nframes = 8500, fb = 3 * 32 * 32 * 32 / 4;
+    const size_t n4 = (size_t)nframes * fb;
+    float4* out; CK(cudaMalloc(&out, n4 * 16));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    auto run = [&](const char* name, auto launch) {
+        for (int i = 0; i < 3; ++i) launch();
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < 20; ++i) launch();
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= 20;
+        printf("%-44s %.4f ms  %.0f GB/s\n", name, ms, n4 * 16 / ms / 1e6);
+        CK(cudaGetLastError());
+    };
+    for (int rnd = 0; rnd < 2; ++rnd) {
+        printf("-- data %s\n", rnd ? "incompressible" : "constant");
+        run("linear grid-stride 148*8 x 256", [&] { k_linear<<<148 * 8, 256>>>(out, n4, rnd); });
+        run("linear one-shot (n4/256 CTAs)", [&] { k_linear<<<(unsigned)((n4 + 255) / 256), 256>>>(out, n4, rnd); });
+        run("frames persistent 444 x 256", [&] { k_frames<<<444, 256>>>(out, nframes, fb, rnd); });
+        run("frames persistent 148 x 1024", [&] { k_frames<<<148, 1024>>>(out, nframes, fb, rnd); });
+        run("frames one CTA per frame 8500 x 256", [&] { k_frames<<<nframes, 256>>>(out, nframes, fb, rnd); });
+        run("frames one CTA per frame 8500 x 1024", [&] { k_frames<<<nframes, 1024>>>(out, nframes, fb, rnd); });
+    }
+    return 0;
+}
