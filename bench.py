@@ -300,9 +300,13 @@ def run_ours(args, rank, local_rank, world):
     ms = max_over_ranks(local_ms)
     value = F * world * args.steps / (ms * 1e-3)
 
-    # ---- optional gather of the volumes to rank 0 (BASELINE.json configs[2])
+    # ---- optional gather of the volumes to rank 0 (BASELINE.json configs[2]), two ways:
+    #      "nccl": kernel writes local HBM, then dist.gather;  "p2p": the kernel stores straight into
+    #      rank 0's buffer over NVLink (gather.PeerVolumeBuffer), only a barrier follows
     gather = None
     if args.gather and world > 1:
+        import importlib
+        gmod = importlib.import_module(pkg.__name__ + ".gather")
         bufs = [torch.empty_like(d_vol) for _ in range(world)] if rank == 0 else None
         dist.gather(d_vol, bufs, dst=0)
         barrier()
@@ -313,9 +317,32 @@ def run_ours(args, rank, local_rank, world):
         g1.record()
         torch.cuda.synchronize()
         gms = max_over_ranks(g0.elapsed_time(g1))
-        gather = {"value": F * world / (gms * 1e-3), "unit": UNIT, "ms": gms,
+        gather = {"nccl": {"value": F * world / (gms * 1e-3), "unit": UNIT, "ms": gms},
                   "bytes_to_rank0": int((world - 1) * d_vol.numel() * 4)}
         del bufs
+        peer = gmod.PeerVolumeBuffer(F * world, R, root=0)
+
+        def p2p_step():
+            pkg.voxelize_device(d_packed, d_off, d_hdr, max_px, cfg, out_vol=peer.mine, out_max_l=d_maxl,
+                                out_mid_p=d_mid)
+        for _ in range(2):
+            p2p_step()
+        peer.complete()
+        reps = 5
+        g0.record()
+        for _ in range(reps):
+            p2p_step()
+        g1.record()
+        torch.cuda.synchronize()
+        pms = max_over_ranks(g0.elapsed_time(g1)) / reps
+        peer.complete()
+        ok_t = torch.tensor([1.0 if torch.equal(peer.mine.to(dev), d_vol) else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        same = bool(ok_t.item() == 1.0)
+        gather["p2p"] = {"value": F * world / (pms * 1e-3), "unit": UNIT, "ms": pms,
+                         "matches_local_run": same,
+                         "how": "fused: kernel stores into rank 0's IPC-mapped buffer over NVLink, then a barrier"}
+        peer.close()
 
     # ---- end to end through the host entry point (pinned host buffers, H2D + kernel + D2H)
     vox = pkg.Voxelizer(device=local_rank, voxel_res=R)

@@ -64,6 +64,11 @@ _SIGNATURES = {
     "dtsdf_default_config": (None, [_cfgp]),
     "dtsdf_device_count": (ctypes.c_int, []),
     "dtsdf_launch_count": (_i64, []),
+    "dtsdf_enable_peer_access": (ctypes.c_int, [_i32, _i32]),
+    "dtsdf_shared_alloc": (ctypes.c_int, [_i32, _i64, ctypes.POINTER(_vp), _vp]),
+    "dtsdf_shared_free": (ctypes.c_int, [_i32, _vp]),
+    "dtsdf_shared_open": (ctypes.c_int, [_i32, _vp, ctypes.POINTER(_vp)]),
+    "dtsdf_shared_close": (ctypes.c_int, [_i32, _vp]),
     "dtsdf_pack_plan": (ctypes.c_int, [_i32, _vp, _vp, ctypes.POINTER(_i64), ctypes.POINTER(_i32)]),
     "dtsdf_voxelize_batch": (ctypes.c_int, [_cfgp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "dtsdf_point_cloud_batch": (ctypes.c_int, [_i32, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

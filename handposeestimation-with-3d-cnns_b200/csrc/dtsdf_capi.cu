@@ -120,6 +120,89 @@ int dtsdf_device_count(void) {
 
 int64_t dtsdf_launch_count(void) { return dtsdf::g_launch_count; }
 
+int dtsdf_enable_peer_access(int32_t device, int32_t peer_device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    if (n == 0) return DTSDF_ERR_NO_DEVICE;
+    if (device < 0 || device >= n || peer_device < 0 || peer_device >= n) return DTSDF_ERR_INVALID_ARG;
+    if (device == peer_device) return DTSDF_OK;
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, device, peer_device));
+    if (!can) return DTSDF_ERR_UNSUPPORTED;
+    int prev = 0;
+    CK(cudaGetDevice(&prev));
+    CK(cudaSetDevice(device));
+    e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    cudaSetDevice(prev);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return DTSDF_OK; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+    return DTSDF_OK;
+}
+
+static int with_device(int32_t device, int* prev) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    if (n == 0) return DTSDF_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return DTSDF_ERR_INVALID_ARG;
+    CK(cudaGetDevice(prev));
+    CK(cudaSetDevice(device));
+    return DTSDF_OK;
+}
+
+int dtsdf_shared_alloc(int32_t device, int64_t bytes, void** d_ptr, uint8_t handle[DTSDF_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == DTSDF_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!d_ptr || !handle || bytes <= 0) return DTSDF_ERR_INVALID_ARG;
+    *d_ptr = nullptr;
+    int prev = 0, rc = with_device(device, &prev);
+    if (rc != DTSDF_OK) return rc;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) { if (p) cudaFree(p); return cuda_fail(e, "cudaMalloc / cudaIpcGetMemHandle"); }
+    memcpy(handle, &h, sizeof(h));
+    *d_ptr = p;
+    return DTSDF_OK;
+}
+
+int dtsdf_shared_free(int32_t device, void* d_ptr) {
+    if (!d_ptr) return DTSDF_OK;
+    int prev = 0, rc = with_device(device, &prev);
+    if (rc != DTSDF_OK) return rc;
+    cudaError_t e = cudaFree(d_ptr);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFree");
+    return DTSDF_OK;
+}
+
+int dtsdf_shared_open(int32_t device, const uint8_t handle[DTSDF_IPC_HANDLE_BYTES], void** d_ptr) {
+    if (!d_ptr || !handle) return DTSDF_ERR_INVALID_ARG;
+    *d_ptr = nullptr;
+    int prev = 0, rc = with_device(device, &prev);
+    if (rc != DTSDF_OK) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+    *d_ptr = p;
+    return DTSDF_OK;
+}
+
+int dtsdf_shared_close(int32_t device, void* d_ptr) {
+    if (!d_ptr) return DTSDF_OK;
+    int prev = 0, rc = with_device(device, &prev);
+    if (rc != DTSDF_OK) return rc;
+    cudaError_t e = cudaIpcCloseMemHandle(d_ptr);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcCloseMemHandle");
+    return DTSDF_OK;
+}
+
 int dtsdf_pack_plan(int32_t n_frames, const int32_t* headers, int64_t* crop_offsets,
                     int64_t* packed_len, int32_t* max_crop_px) {
     if (n_frames < 0 || (n_frames > 0 && (!headers || !crop_offsets))) return DTSDF_ERR_INVALID_ARG;

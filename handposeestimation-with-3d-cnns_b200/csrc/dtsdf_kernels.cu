@@ -188,7 +188,7 @@ __device__ __forceinline__ Frame load_frame(const BatchArgs& a, int f) {
     const bool bad = fr.bw <= 0 || fr.bh <= 0 || fr.bw > 32767 || fr.bh > 32767 ||
                      (long long)fr.bw * fr.bh > (1ll << 26) ||      // byte offsets stay below 2^28
                      fr.l <= -lim || fr.t <= -lim || fr.r >= lim || fr.b >= lim;
-    if (bad) { fr.bw = 0; fr.bh = 0; }
+    if (bad) { fr.bw = 0; fr.bh = 0; fr.r = fr.l; fr.b = fr.t; }      // empty pixel ranges: every voxel is outside
     fr.n = fr.bw * fr.bh;
     fr.n_pad = (fr.n + 3) & ~3;
     fr.crop = a.depth + __ldg(a.offsets + f);

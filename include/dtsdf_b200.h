@@ -89,6 +89,23 @@ int         dtsdf_device_count(void);             /* number of CUDA devices, 0 i
 /* number of CUDA kernels this library has launched in the calling process */
 int64_t     dtsdf_launch_count(void);
 
+/* Lets kernels running on `device` address memory that lives on `peer_device` (NVLink /
+ * NVSwitch peer access), so that d_out_vol of dtsdf_voxelize_batch may point into another
+ * GPU's HBM: the volumes of a frame shard are then gathered into a training rank by the
+ * voxeliser's own stores (nothing to replace in the reference, which is
+ * single-GPU).  Idempotent.  DTSDF_ERR_UNSUPPORTED if the two devices have no peer path. */
+int dtsdf_enable_peer_access(int32_t device, int32_t peer_device);
+
+/* A device buffer that other PROCESSES on the same node can map (CUDA IPC), for the same purpose
+ * across ranks: the root rank allocates the buffer of all volumes and publishes the 64-byte
+ * handle; every other rank opens it with its own GPU current and passes a pointer into it as
+ * d_out_vol.  dtsdf_shared_open enables peer access to the owning GPU lazily. */
+#define DTSDF_IPC_HANDLE_BYTES 64
+int dtsdf_shared_alloc(int32_t device, int64_t bytes, void** d_ptr, uint8_t handle[DTSDF_IPC_HANDLE_BYTES]);
+int dtsdf_shared_free(int32_t device, void* d_ptr);
+int dtsdf_shared_open(int32_t device, const uint8_t handle[DTSDF_IPC_HANDLE_BYTES], void** d_ptr);
+int dtsdf_shared_close(int32_t device, void* d_ptr);
+
 /* ---- packing helpers (host, no CUDA) ---------------------------------------- */
 /* Computes 16-byte-aligned crop offsets for n_frames headers.  crop_offsets[i] is
  * the start (in floats) of crop i; returns the total packed length in floats

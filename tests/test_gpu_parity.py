@@ -286,3 +286,26 @@ def test_normalize_joints(vox):
     assert np.array_equal(out, f32.reshape(50, 63))
     clamped = vox.normalize_joints(gt, max_l, mid_p, clamp01=True)   # 3D_CNN/train.py:241-242
     assert np.array_equal(clamped, np.clip(f32.reshape(50, 63), 0, 1))
+
+
+# ----------------------------------------------------------------------------- peer stores (NVLink)
+def test_kernel_stores_into_peer_memory():
+    """the gather to a training rank is done by the voxeliser kernel itself,
+    storing into a buffer that lives in another GPU's HBM (gather.PeerVolumeBuffer does this across
+    processes with CUDA IPC; here both GPUs belong to this process)."""
+    import importlib
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    gmod = importlib.import_module(pkg.__name__ + ".gather")
+    frames = synth.make_frames(range(400, 464))
+    headers, offsets, packed, max_px = pkg.pack_frames(frames)
+    gmod.enable_peer_access(1, 0)
+    out0 = torch.zeros((len(frames), 3, 32, 32, 32), dtype=torch.float32, device="cuda:0")   # lives on GPU 0
+    d1 = torch.device("cuda:1")
+    with torch.cuda.device(d1):
+        pkg.voxelize_device(torch.from_numpy(packed).to(d1), torch.from_numpy(offsets).to(d1),
+                            torch.from_numpy(headers).to(d1), max_px, out_vol=out0)           # runs on GPU 1
+        torch.cuda.synchronize(d1)
+    cv, _, _, _ = c_oracle.dtsdf_batch(*pack_simple(frames))
+    assert _same(out0.cpu().numpy(), cv)
