@@ -81,6 +81,8 @@ _SIGNATURES = {
     "dtsdf_voxelize_host": (ctypes.c_int, [_vp, _cfgp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_point_cloud_host": (ctypes.c_int, [_vp, ctypes.c_double, _vp, _vp, _vp, ctypes.POINTER(_i32)]),
     "dtsdf_resample_extrema_host": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "dtsdf_process_begin_host": (ctypes.c_int, [_vp, ctypes.c_double, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "dtsdf_process_finish_host": (ctypes.c_int, [_vp, _cfgp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_normalize_joints_host": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp]),
 }
 

@@ -80,6 +80,11 @@ struct dtsdf_ctx {
     int32_t last_n_valid = -1;
     // joints
     DevBuf d_j_in, d_j_out, d_j_ml, d_j_mp;
+    // batched process(): resident crops, clouds and their tables between begin and finish
+    DevBuf b_depth, b_off, b_hdr, b_points, b_poff, b_nvalid, b_idx, b_pc, b_ext, b_vol, b_maxl, b_mid;
+    int32_t b_n = 0;
+    int32_t b_max_px = 0;
+    std::vector<int32_t> b_nvalid_h;
 };
 
 extern "C" {
@@ -337,6 +342,9 @@ void dtsdf_ctx_destroy(dtsdf_ctx* c) {
     }
     c->d_points.release(); c->d_idx.release(); c->d_pc.release(); c->d_ext.release(); c->d_misc.release();
     c->d_j_in.release(); c->d_j_out.release(); c->d_j_ml.release(); c->d_j_mp.release();
+    c->b_depth.release(); c->b_off.release(); c->b_hdr.release(); c->b_points.release(); c->b_poff.release();
+    c->b_nvalid.release(); c->b_idx.release(); c->b_pc.release(); c->b_ext.release(); c->b_vol.release();
+    c->b_maxl.release(); c->b_mid.release();
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_run) cudaStreamDestroy(c->s_run);
     if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -525,6 +533,94 @@ int dtsdf_resample_extrema_host(dtsdf_ctx* c, int32_t point_num, const double* h
     CK(cudaMemcpyAsync(h_out_extrema, c->d_ext.p, 24, cudaMemcpyDeviceToHost, s));
     if (h_out_pc)
         CK(cudaMemcpyAsync(h_out_pc, c->d_pc.p, (size_t)point_num * 24, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return DTSDF_OK;
+}
+
+int dtsdf_process_begin_host(dtsdf_ctx* c, double focal, int32_t n_frames, const float* h_depth,
+                             int64_t packed_len, const int64_t* h_off, const int32_t* h_hdr,
+                             int32_t* h_n_valid) {
+    if (!c || n_frames < 0 || packed_len < 0 || !(focal > 0.0)) return DTSDF_ERR_INVALID_ARG;
+    c->b_n = 0;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!h_depth || !h_off || !h_hdr || !h_n_valid) return DTSDF_ERR_INVALID_ARG;
+    std::vector<int64_t> poff(n_frames);
+    int64_t total_px = 0;
+    int32_t max_px = 0;
+    for (int32_t i = 0; i < n_frames; ++i) {
+        const int32_t* h = h_hdr + 6 * (size_t)i;
+        if (!header_ok(h)) return DTSDF_ERR_BAD_HEADER;
+        const int64_t n = ((int64_t)h[4] - h[2]) * ((int64_t)h[5] - h[3]);
+        if (h_off[i] < 0 || (h_off[i] & 3) || h_off[i] + ((n + 3) & ~(int64_t)3) > packed_len)
+            return DTSDF_ERR_INVALID_ARG;
+        poff[i] = total_px;                 // room for every pixel of the crop
+        total_px += n;
+        max_px = std::max<int32_t>(max_px, (int32_t)n);
+    }
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = c->b_depth.reserve((size_t)packed_len * 4)) != DTSDF_OK) return rc;
+    if ((rc = c->b_off.reserve((size_t)n_frames * 8)) != DTSDF_OK) return rc;
+    if ((rc = c->b_hdr.reserve((size_t)n_frames * 24)) != DTSDF_OK) return rc;
+    if ((rc = c->b_poff.reserve((size_t)n_frames * 8)) != DTSDF_OK) return rc;
+    if ((rc = c->b_nvalid.reserve((size_t)n_frames * 4)) != DTSDF_OK) return rc;
+    if ((rc = c->b_points.reserve((size_t)total_px * 24)) != DTSDF_OK) return rc;
+    cudaStream_t s = c->s_run;
+    CK(cudaMemcpyAsync(c->b_depth.p, h_depth, (size_t)packed_len * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->b_off.p, h_off, (size_t)n_frames * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->b_hdr.p, h_hdr, (size_t)n_frames * 24, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->b_poff.p, poff.data(), (size_t)n_frames * 8, cudaMemcpyHostToDevice, s));
+    rc = dtsdf_point_cloud_batch(n_frames, focal, (const float*)c->b_depth.p, (const int64_t*)c->b_off.p,
+                                 (const int32_t*)c->b_hdr.p, (double*)c->b_points.p, (const int64_t*)c->b_poff.p,
+                                 (int32_t*)c->b_nvalid.p, s);
+    if (rc != DTSDF_OK) return rc;
+    CK(cudaMemcpyAsync(h_n_valid, c->b_nvalid.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));           // also covers the pageable poff staging
+    c->b_nvalid_h.assign(h_n_valid, h_n_valid + n_frames);
+    c->b_n = n_frames;
+    c->b_max_px = max_px;
+    return DTSDF_OK;
+}
+
+int dtsdf_process_finish_host(dtsdf_ctx* c, const dtsdf_config* cfg_in, int32_t point_num,
+                              const int32_t* h_idx, double* h_pc, float* h_vol, float* h_maxl, float* h_mid) {
+    if (!c) return DTSDF_ERR_INVALID_ARG;
+    int rc = check_cfg(cfg_in);
+    if (rc != DTSDF_OK) return rc;
+    if (point_num <= 0) return DTSDF_ERR_INVALID_ARG;
+    const int32_t n = c->b_n;
+    if (n == 0) return DTSDF_OK;
+    if (!h_idx || !h_vol) return DTSDF_ERR_INVALID_ARG;
+    for (int32_t i = 0; i < n; ++i) {
+        const int32_t nv = c->b_nvalid_h[i];
+        const int32_t* idx = h_idx + (size_t)i * point_num;
+        for (int32_t k = 0; k < point_num; ++k)
+            if (idx[k] < 0 || idx[k] >= nv) return DTSDF_ERR_INVALID_ARG;      // also: a frame without points
+    }
+    dtsdf_config cfg = *cfg_in;
+    cfg.bbox_mode = DTSDF_BBOX_EXTREMA;
+    const size_t R = (size_t)cfg.voxel_res, vol_floats = 3 * R * R * R;
+    CK(cudaSetDevice(c->device));
+    if ((rc = c->b_idx.reserve((size_t)n * point_num * 4)) != DTSDF_OK) return rc;
+    if ((rc = c->b_ext.reserve((size_t)n * 24)) != DTSDF_OK) return rc;
+    if (h_pc && (rc = c->b_pc.reserve((size_t)n * point_num * 24)) != DTSDF_OK) return rc;
+    if ((rc = c->b_vol.reserve((size_t)n * vol_floats * 4)) != DTSDF_OK) return rc;
+    if ((rc = c->b_maxl.reserve((size_t)n * 4)) != DTSDF_OK) return rc;
+    if ((rc = c->b_mid.reserve((size_t)n * 12)) != DTSDF_OK) return rc;
+    cudaStream_t s = c->s_run;
+    CK(cudaMemcpyAsync(c->b_idx.p, h_idx, (size_t)n * point_num * 4, cudaMemcpyHostToDevice, s));
+    rc = dtsdf_resample_extrema_batch(n, point_num, (const double*)c->b_points.p, (const int64_t*)c->b_poff.p,
+                                      (const int32_t*)c->b_idx.p, h_pc ? (double*)c->b_pc.p : nullptr,
+                                      (float*)c->b_ext.p, s);
+    if (rc != DTSDF_OK) return rc;
+    rc = dtsdf_voxelize_batch(&cfg, n, (const float*)c->b_depth.p, (const int64_t*)c->b_off.p,
+                              (const int32_t*)c->b_hdr.p, (const float*)c->b_ext.p, c->b_max_px,
+                              (float*)c->b_vol.p, (float*)c->b_maxl.p, (float*)c->b_mid.p, s);
+    if (rc != DTSDF_OK) return rc;
+    if (h_pc) CK(cudaMemcpyAsync(h_pc, c->b_pc.p, (size_t)n * point_num * 24, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_vol, c->b_vol.p, (size_t)n * vol_floats * 4, cudaMemcpyDeviceToHost, s));
+    if (h_maxl) CK(cudaMemcpyAsync(h_maxl, c->b_maxl.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (h_mid) CK(cudaMemcpyAsync(h_mid, c->b_mid.p, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return DTSDF_OK;
 }

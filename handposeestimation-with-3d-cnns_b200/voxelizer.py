@@ -168,6 +168,42 @@ class Voxelizer:
                                                     capi._ptr(idx), capi._ptr(out_pc), capi._ptr(ext)))
         return out_pc, ext[:3].copy(), ext[3:].copy()
 
+    def process_frames(self, frames, point_num=6000, want_points=True, layout=LAYOUT_CXYZ, voxel_res=None):
+        """``DataProcess(frame, gt, point_num).process()`` (pre/process.py:13-28) for a list of frame
+        records in two device round trips instead of per-frame Python loops.  The resampling index
+        vectors are drawn here, frame by frame in order, from the *global* ``np.random`` stream with
+        the reference's own calls (pre/process.py:75-80), so a seeded run reproduces the reference's
+        frame loop (pre/read_MSRA.py:98-111) bit for bit.
+
+        Returns ``(point_clouds float64[n,point_num,3] or None, tsdf float32[n,3,R,R,R],
+        max_l float32[n], mid_p float32[n,3])``.
+        """
+        R = int(voxel_res or self.voxel_res)
+        point_num = int(point_num)
+        headers, offsets, packed, _ = pack_frames(frames)
+        n = headers.shape[0]
+        n_valid = np.zeros(n, dtype=np.int32)
+        check(self._lib.dtsdf_process_begin_host(self._ctx, ctypes.c_double(self.focal), n, capi._ptr(packed),
+                                                 int(packed.size), capi._ptr(offsets), capi._ptr(headers),
+                                                 capi._ptr(n_valid)))
+        idx = np.empty((n, point_num), dtype=np.int32)
+        for i in range(n):
+            point_shape = int(n_valid[i])
+            if point_shape < point_num:
+                idx[i] = np.arange(0, point_num, 1, dtype=np.int32)
+                idx[i, point_shape:] = np.random.randint(0, point_shape, size=point_num - point_shape)
+            else:
+                idx[i] = np.random.randint(0, point_shape, size=point_num)
+        pcs = np.empty((n, point_num, 3), dtype=np.float64) if want_points else None
+        vol = np.empty((n, 3, R, R, R), dtype=np.float32)
+        max_l = np.empty(n, dtype=np.float32)
+        mid_p = np.empty((n, 3), dtype=np.float32)
+        cfg = self.config(layout, BBOX_EXTREMA, R)
+        check(self._lib.dtsdf_process_finish_host(self._ctx, ctypes.byref(cfg), point_num, capi._ptr(idx),
+                                                  capi._ptr(pcs), capi._ptr(vol), capi._ptr(max_l),
+                                                  capi._ptr(mid_p)))
+        return pcs, vol, max_l, mid_p
+
     def normalize_joints(self, joints, max_l, mid_p, clamp01=False):
         """(gt - mid_p)/max_l + 0.5 (pre/joint_nor.py:8-18), float32[n,63]."""
         j = np.ascontiguousarray(joints, dtype=np.float32).reshape(-1, 63)

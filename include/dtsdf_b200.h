@@ -209,6 +209,28 @@ int dtsdf_resample_extrema_host(dtsdf_ctx* ctx, int32_t point_num,
                                 const int32_t* h_indices,
                                 double* h_out_pc, float* h_out_extrema);
 
+/* DataProcess.process() for a whole batch (pre/process.py:13-28; the frame loop of
+ * read_MSRA.main(), pre/read_MSRA.py:98-111), in two calls because the resampling index vectors
+ * are drawn by the caller from its np.random stream and depend on the number of valid points:
+ *
+ *   dtsdf_process_begin_host   uploads the packed crops, back-projects and compacts every
+ *                              frame's point cloud (pre/process.py:30-68; it stays resident in
+ *                              the context) and returns n_valid per frame;
+ *   dtsdf_process_finish_host  gathers point_num rows per frame by the caller's indices
+ *                              (pre/process.py:82), reduces the extrema (:102-120) and runs the
+ *                              fused voxeliser with them (tsdf_f, :86-100) on the resident crops.
+ *     h_indices     int32[n][point_num], each in [0, n_valid_i)
+ *     h_out_pc      double[n][point_num][3] (may be NULL)
+ *     h_out_vol     float[n][3][R][R][R] in cfg->layout; cfg->bbox_mode is ignored (EXTREMA)
+ */
+int dtsdf_process_begin_host(dtsdf_ctx* ctx, double focal, int32_t n_frames,
+                             const float* h_depth_packed, int64_t packed_len,
+                             const int64_t* h_crop_offsets, const int32_t* h_headers,
+                             int32_t* h_n_valid);
+int dtsdf_process_finish_host(dtsdf_ctx* ctx, const dtsdf_config* cfg, int32_t point_num,
+                              const int32_t* h_indices, double* h_out_pc,
+                              float* h_out_vol, float* h_out_max_l, float* h_out_mid_p);
+
 int dtsdf_normalize_joints_host(dtsdf_ctx* ctx, int32_t n_frames, const float* h_joints,
                                 const float* h_max_l, const float* h_mid_p,
                                 int32_t clamp01, float* h_out);

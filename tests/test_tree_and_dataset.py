@@ -1,0 +1,145 @@
+"""The callers either side of the hot path against the golden
+``result/`` tree written by the UNMODIFIED reference (tests/golden/make_golden_tree.py ->
+tests/golden/msra_tree.npz): the ``3D_CNN/dataset.py`` consumer (CPU) and the ``pre/read_MSRA.py``
+preprocessing driver (GPU)."""
+import hashlib
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import graft, pkg
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_golden_tree as mini  # noqa: E402   (only its data-base writer is used here)
+
+CNN_DIR = os.path.join(graft.PKG_DIR, "3D_CNN")
+PRE_DIR = os.path.join(graft.PKG_DIR, "pre")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(HERE, "golden", "msra_tree.npz"))
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _import(name, directory):
+    if directory not in sys.path:
+        sys.path.insert(0, directory)
+    return importlib.import_module(name)
+
+
+def _write_tree(golden, root, gt_3d):
+    """The reference's result/ tree (pre/read_MSRA.py:119-126), rebuilt from the fixture."""
+    for sub in mini.SUBJECTS:
+        for name in ("Point_Cloud", "TSDF", "ground_truth", "num"):
+            os.makedirs(os.path.join(root, sub, name))
+        for ges in mini.GESTURES:
+            k = "%s_%s_" % (sub, ges)
+            np.savez(os.path.join(root, sub, "TSDF", "%s.npz" % ges), tsdf=golden[k + "tsdf"].astype(np.float64),
+                     max_l=golden[k + "max_l"], mid_p=golden[k + "mid_p"])
+            gt = golden[k + "gt"]
+            np.save(os.path.join(root, sub, "ground_truth", "%s.npy" % ges), gt.reshape(-1, 21, 3) if gt_3d else gt)
+            np.save(os.path.join(root, sub, "num", "%s.npy" % ges), golden[k + "num"])
+        np.save(os.path.join(root, "data_num-%s.npy" % sub), golden["data_num_%s" % sub])
+
+
+# ----------------------------------------------------------------------------- consumer (CPU)
+@pytest.mark.parametrize("gt_3d", [True, False])
+def test_dataset_matches_reference_loader(golden, tmp_path, gt_3d):
+    """MSRA_Dataset: 3D_CNN/dataset.py:16-117.  gt_3d=False is the tree pre/read_MSRA.py really
+    writes ([n,63] ground truth), which the reference loader cannot read (NameError, :105-108)."""
+    dataset = _import("dataset", CNN_DIR)
+    root = str(tmp_path / "result")
+    _write_tree(golden, root, gt_3d)
+    for train, tag in ((True, "train"), (False, "test")):
+        ds = dataset.MSRA_Dataset(root, None, train=train, aug=False)
+        assert len(ds) == int(golden["ds_%s_len" % tag])
+        assert ds.tsdf.dtype == np.float32 and ds.tsdf.shape[1:] == (3, 32, 32, 32)
+        assert _sha(ds.tsdf) == str(golden["ds_%s_tsdf_sha256" % tag])          # same frames, same order
+        assert np.array_equal(ds.ground_truth, golden["ds_%s_gt" % tag])        # z flipped (:107)
+        assert np.array_equal(ds.max_l, golden["ds_%s_max_l" % tag])
+        assert np.array_equal(ds.mid_p, golden["ds_%s_mid_p" % tag])
+        item = ds[len(ds) - 1]
+        assert len(item) == int(golden["ds_%s_item_len" % tag]) == 4
+        assert item[0].shape == (3, 32, 32, 32) and item[1].shape == (63,) and item[3].shape == (3,)
+    # consumed by a DataLoader like 3D_CNN/train.py:87-91
+    import torch
+    loader = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=False, num_workers=0)
+    tsdf, gt, max_l, mid_p = next(iter(loader))
+    assert tuple(tsdf.shape) == (4, 3, 32, 32, 32) and tsdf.dtype == torch.float32
+    assert tuple(gt.shape) == (4, 63) and tuple(max_l.shape) == (4,) and tuple(mid_p.shape) == (4, 3)
+
+
+# ----------------------------------------------------------------------------- preprocessing driver (GPU)
+@pytest.mark.gpu
+def test_read_msra_main_writes_the_reference_tree(golden, tmp_path):
+    """pre/read_MSRA.py main(): same files, same arrays, bit for bit, as the unmodified reference on
+    the same synthetic MSRA data base and np.random seed."""
+    read_MSRA = _import("read_MSRA", PRE_DIR)
+    db = str(tmp_path / "db") + os.sep
+    os.makedirs(db)
+    mini.write_mini_db(db)
+    h, d = read_MSRA.read_bin(os.path.join(db, "P0", "1", "000000_depth.bin"))      # pre/read_MSRA.py:155-164
+    fr = pkg.synth.make_frame(mini.frames_of(0, 0)[0])
+    assert h.dtype == np.int32 and np.array_equal(h, fr["header"]) and np.array_equal(d, fr["depth"])
+    n, gt = read_MSRA.read_joint(os.path.join(db, "P0", "1"))                         # :143-152
+    assert n == len(mini.frames_of(0, 0)) and gt.dtype == np.float32 and gt.shape == (n, 63)
+
+    res = str(tmp_path / "result")
+    read_MSRA.DB_dir, read_MSRA.SAVE_dir, read_MSRA.AUG = db, res, False
+    np.random.seed(int(golden["seed"]))
+    read_MSRA.main()
+    for sub in mini.SUBJECTS:
+        assert np.array_equal(np.load(os.path.join(res, "data_num-%s.npy" % sub)), golden["data_num_%s" % sub])
+        for ges in mini.GESTURES:
+            k = "%s_%s_" % (sub, ges)
+            z = np.load(os.path.join(res, sub, "TSDF", "%s.npz" % ges))
+            assert z["tsdf"].dtype == np.float64 and z["max_l"].dtype == np.float64
+            assert np.array_equal(z["tsdf"], golden[k + "tsdf"].astype(np.float64)), k
+            assert np.array_equal(np.signbit(z["tsdf"]), np.signbit(golden[k + "tsdf"]))
+            assert np.array_equal(z["max_l"], golden[k + "max_l"]) and np.array_equal(z["mid_p"], golden[k + "mid_p"])
+            pc = np.load(os.path.join(res, sub, "Point_Cloud", "%s.npy" % ges))
+            assert pc.dtype == np.float64 and _sha(pc) == str(golden[k + "pc_sha256"]), k
+            assert np.array_equal(pc[:, :32, :], golden[k + "pc_head"])
+            assert np.array_equal(np.load(os.path.join(res, sub, "ground_truth", "%s.npy" % ges)), golden[k + "gt"])
+            assert np.array_equal(np.load(os.path.join(res, sub, "num", "%s.npy" % ges)), golden[k + "num"])
+    read_MSRA.AUG = True
+    with pytest.raises(NotImplementedError):
+        read_MSRA.main()
+    read_MSRA.AUG = False
+
+
+@pytest.mark.gpu
+def test_dataset_from_database_on_device(golden, tmp_path):
+    """MSRA_Dataset.from_database: data base -> GPU-resident dataset with no result/ tree in between;
+    with the reference's seed it holds exactly what the reference loader returns."""
+    import torch
+    dataset = _import("dataset", CNN_DIR)
+    db = str(tmp_path / "db") + os.sep
+    os.makedirs(db)
+    mini.write_mini_db(db)
+    # the reference preprocesses EVERY subject in order (pre/read_MSRA.py:51), so the np.random stream
+    # a subject sees depends on the ones before it: replay the full order, keep the test split
+    np.random.seed(int(golden["seed"]))
+    full = {}
+    for s, sub in enumerate(mini.SUBJECTS):
+        ds = dataset.MSRA_Dataset.from_database(db, train=False, device="cuda", test_idx=s)
+        full[s] = ds
+    ds = full[2]                                                          # the reference's test_idx (:21)
+    assert ds.tsdf.is_cuda and len(ds) == int(golden["ds_test_len"])
+    assert _sha(ds.tsdf.cpu().numpy()) == str(golden["ds_test_tsdf_sha256"])
+    assert np.array_equal(ds.ground_truth.cpu().numpy(), golden["ds_test_gt"])
+    assert np.array_equal(ds.max_l.cpu().numpy(), golden["ds_test_max_l"])
+    assert np.array_equal(ds.mid_p.cpu().numpy(), golden["ds_test_mid_p"])
+    tsdf, gt, max_l, mid_p = ds[torch.arange(0, 4, device="cuda")]        # a batch without a host round trip
+    assert tsdf.is_cuda and tuple(tsdf.shape) == (4, 3, 32, 32, 32)
+    # deterministic variant: grid from all valid pixels (pre/tsdf_numba.py semantics), one fused launch per gesture
+    dp = dataset.MSRA_Dataset.from_database(db, train=True, device="cuda", bbox="pixels")
+    assert len(dp) == int(golden["ds_train_len"]) and float(dp.tsdf.abs().max()) <= 1.0
