@@ -25,6 +25,9 @@ LAYOUT_CZYX = 1
 BBOX_PIXELS = 0
 BBOX_EXTREMA = 1
 BBOX_GRID = 2
+OPT_PACKED_D2H = 1
+OPT_HOST_THREADS = 2
+STAT_D2H_BYTES = 1
 
 
 class DtsdfError(RuntimeError):
@@ -76,6 +79,8 @@ _SIGNATURES = {
     "dtsdf_normalize_joints_batch": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "dtsdf_ctx_create": (ctypes.c_int, [_i32, ctypes.POINTER(_vp)]),
     "dtsdf_ctx_destroy": (None, [_vp]),
+    "dtsdf_ctx_set_option": (ctypes.c_int, [_vp, _i32, _i64]),
+    "dtsdf_ctx_get_stat": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_i64)]),
     "dtsdf_host_alloc": (ctypes.c_int, [ctypes.POINTER(_vp), _i64]),
     "dtsdf_host_free": (None, [_vp]),
     "dtsdf_voxelize_host": (ctypes.c_int, [_vp, _cfgp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

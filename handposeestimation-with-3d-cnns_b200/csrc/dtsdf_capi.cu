@@ -8,8 +8,16 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <emmintrin.h>
+
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "dtsdf_internal.h"
@@ -66,12 +74,163 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// mapped pinned host buffer: the GPU writes it over PCIe, the host threads read it
+struct MapBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return DTSDF_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(bytes, (size_t)4096);
+        CK(cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable));
+        cap = want;
+        return DTSDF_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// a small persistent thread pool for the host-side expansion of packed volumes
+class Pool {
+public:
+    ~Pool() { stop(); }
+    void ensure(int n) {
+        if ((int)th_.size() == n) return;
+        stop();
+        quit_ = false;
+        for (int i = 0; i < n; ++i) th_.emplace_back([this] { run(); });
+    }
+    void submit(std::function<void()> fn) {
+        { std::lock_guard<std::mutex> g(m_); q_.push_back(std::move(fn)); }
+        cv_.notify_one();
+    }
+    void stop() {
+        { std::lock_guard<std::mutex> g(m_); quit_ = true; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+        th_.clear();
+    }
+private:
+    void run() {
+        for (;;) {
+            std::function<void()> fn;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [this] { return quit_ || !q_.empty(); });
+                if (q_.empty()) return;
+                fn = std::move(q_.front());
+                q_.pop_front();
+            }
+            fn();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::deque<std::function<void()>> q_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool quit_ = false;
+};
+
+struct Latch {
+    std::mutex m;
+    std::condition_variable cv;
+    int pending = 0;
+    void add(int n) { std::lock_guard<std::mutex> g(m); pending += n; }
+    void done() {
+        std::lock_guard<std::mutex> g(m);
+        if (--pending == 0) cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> g(m);
+        cv.wait(g, [this] { return pending == 0; });
+    }
+};
+
+// Expansion of one packed frame (dtsdf_internal.h: launch_pack) into its three channel planes.
+// Streaming stores: the planes are written once and not read back by this code.
+struct DecodeTables {
+    float val[256][4];          // the four voxel values of a code byte without literals
+    unsigned char nlit[256];    // number of literals in the byte
+    DecodeTables() {
+        const float v[4] = {0.0f, 1.0f, -1.0f, 0.0f};
+        for (int b = 0; b < 256; ++b) {
+            int n = 0;
+            for (int j = 0; j < 4; ++j) {
+                const int c = (b >> (2 * j)) & 3;
+                val[b][j] = v[c];
+                n += c == 3;
+            }
+            nlit[b] = (unsigned char)n;
+        }
+    }
+};
+const DecodeTables g_dec;
+
+template <bool ALIGNED>
+inline void put4(float* p, __m128 v) {
+    if (ALIGNED) _mm_stream_ps(p, v);
+    else _mm_storeu_ps(p, v);
+}
+
+template <bool ALIGNED>
+void decode_frame_t(const unsigned char* codes, const float* lits, size_t r3, float* out) {
+    float* o0 = out;
+    float* o1 = out + r3;
+    float* o2 = out + 2 * r3;
+    const size_t nb = r3 / 4;                 // code bytes; a multiple of 8 (r3 is a multiple of 1024)
+    const __m128 zero = _mm_setzero_ps(), pone = _mm_set1_ps(1.0f), mone = _mm_set1_ps(-1.0f);
+    for (size_t k = 0; k < nb; k += 8) {
+        unsigned long long w;
+        memcpy(&w, codes + k, 8);
+        // 32 voxels with one value (most of a volume): no table, no literals
+        const bool run0 = w == 0ull, run1 = w == 0x5555555555555555ull, run2 = w == 0xAAAAAAAAAAAAAAAAull;
+        if (run0 || run1 || run2) {
+            const __m128 v = run0 ? zero : (run1 ? pone : mone);
+            for (int j = 0; j < 8; ++j) {
+                put4<ALIGNED>(o0 + 4 * (k + j), v); put4<ALIGNED>(o1 + 4 * (k + j), v); put4<ALIGNED>(o2 + 4 * (k + j), v);
+            }
+            continue;
+        }
+        for (int j = 0; j < 8; ++j) {
+            const unsigned b = codes[k + j];
+            __m128 v0, v1, v2;
+            if (g_dec.nlit[b] == 0) {
+                v0 = v1 = v2 = _mm_loadu_ps(g_dec.val[b]);
+            } else {
+                alignas(16) float t0[4], t1[4], t2[4];
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned c = (b >> (2 * q)) & 3u;
+                    if (c == 3u) { t0[q] = lits[0]; t1[q] = lits[1]; t2[q] = lits[2]; lits += 3; }
+                    else { t0[q] = t1[q] = t2[q] = g_dec.val[b][q]; }
+                }
+                v0 = _mm_load_ps(t0); v1 = _mm_load_ps(t1); v2 = _mm_load_ps(t2);
+            }
+            put4<ALIGNED>(o0 + 4 * (k + j), v0); put4<ALIGNED>(o1 + 4 * (k + j), v1); put4<ALIGNED>(o2 + 4 * (k + j), v2);
+        }
+    }
+    if (ALIGNED) _mm_sfence();
+}
+
+void decode_frame(const unsigned char* codes, const float* lits, size_t r3, float* out) {
+    // streaming stores need 16-byte alignment: the three planes of a frame share it (r3 % 4 == 0)
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) decode_frame_t<true>(codes, lits, r3, out);
+    else decode_frame_t<false>(codes, lits, r3, out);
+}
+
 }  // namespace
 
 struct dtsdf_ctx {
     int device = 0;
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
-    static const int NSLOT = 3;                 // chunks in flight
+    static const int NSLOT = 4;                 // chunks in flight
+    // packed device -> host transfer
+    int opt_packed = 1;
+    int opt_threads = 0;                        // 0 = hardware concurrency
+    Pool pool;
+    DevBuf d_cnt[NSLOT], d_loff[NSLOT], d_codes[NSLOT], d_lits[NSLOT];
+    MapBuf m_codes[NSLOT], m_loff[NSLOT], m_lits[NSLOT];
+    Latch latch[NSLOT];
+    int64_t stat_d2h_bytes = 0;
     DevBuf d_depth[NSLOT], d_off[NSLOT], d_hdr[NSLOT], d_aux[NSLOT];
     DevBuf d_vol[NSLOT], d_maxl[NSLOT], d_mid[NSLOT];
     cudaEvent_t ev_in[NSLOT] = {}, ev_run[NSLOT] = {}, ev_out[NSLOT] = {};
@@ -336,6 +495,8 @@ void dtsdf_ctx_destroy(dtsdf_ctx* c) {
     for (int i = 0; i < dtsdf_ctx::NSLOT; ++i) {
         c->d_depth[i].release(); c->d_off[i].release(); c->d_hdr[i].release(); c->d_aux[i].release();
         c->d_vol[i].release(); c->d_maxl[i].release(); c->d_mid[i].release();
+        c->d_cnt[i].release(); c->d_loff[i].release(); c->d_codes[i].release(); c->d_lits[i].release();
+        c->m_codes[i].release(); c->m_loff[i].release(); c->m_lits[i].release();
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
         if (c->ev_run[i]) cudaEventDestroy(c->ev_run[i]);
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
@@ -350,6 +511,28 @@ void dtsdf_ctx_destroy(dtsdf_ctx* c) {
     if (c->s_out) cudaStreamDestroy(c->s_out);
     cudaGetLastError();
     delete c;
+}
+
+int dtsdf_ctx_set_option(dtsdf_ctx* c, int32_t option, int64_t value) {
+    if (!c) return DTSDF_ERR_INVALID_ARG;
+    switch (option) {
+        case DTSDF_OPT_PACKED_D2H:
+            c->opt_packed = value != 0;
+            return DTSDF_OK;
+        case DTSDF_OPT_HOST_THREADS:
+            if (value < 0 || value > 256) return DTSDF_ERR_INVALID_ARG;
+            c->opt_threads = (int)value;
+            return DTSDF_OK;
+        default:
+            return DTSDF_ERR_UNSUPPORTED;
+    }
+}
+
+int dtsdf_ctx_get_stat(dtsdf_ctx* c, int32_t stat, int64_t* value) {
+    if (!c || !value) return DTSDF_ERR_INVALID_ARG;
+    if (stat != DTSDF_STAT_D2H_BYTES) return DTSDF_ERR_UNSUPPORTED;
+    *value = c->stat_d2h_bytes;
+    return DTSDF_OK;
 }
 
 int dtsdf_host_alloc(void** ptr, int64_t bytes) {
@@ -401,6 +584,44 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
     const int nchunk = (n_frames + per_chunk - 1) / per_chunk;
     std::vector<int64_t> rebased;
 
+    // packed device -> host transfer: the GPU packs each chunk into mapped pinned memory, host
+    // threads expand it into h_vol while the next chunks are in flight
+    const bool packed = c->opt_packed != 0;
+    const size_t r3 = R * R * R;
+    c->stat_d2h_bytes = packed ? 0 : (int64_t)n_frames * (int64_t)(vol_floats * 4 + (h_maxl ? 4 : 0) + (h_mid ? 12 : 0));
+    int nthreads = 1;
+    if (packed) {
+        nthreads = c->opt_threads > 0 ? c->opt_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+        c->pool.ensure(nthreads);
+    }
+    struct Pending { int slot; int32_t f0, nf; };
+    Pending pend = {-1, 0, 0};
+    auto finalize = [&](const Pending& pd) -> int {
+        // the chunk's kernels have written the packed form: hand it to the host threads
+        CK(cudaEventSynchronize(c->ev_run[pd.slot]));
+        const unsigned char* codes = (const unsigned char*)c->m_codes[pd.slot].p;
+        const unsigned long long* loff = (const unsigned long long*)c->m_loff[pd.slot].p;
+        const float* lits = (const float*)c->m_lits[pd.slot].p;
+        c->stat_d2h_bytes += (int64_t)pd.nf * (int64_t)(r3 / 4) + (int64_t)(pd.nf + 1) * 8 + 12 * (int64_t)loff[pd.nf] +
+                             (h_maxl ? 4 * (int64_t)pd.nf : 0) + (h_mid ? 12 * (int64_t)pd.nf : 0);
+        const int jobs = std::min<int>(pd.nf, nthreads);
+        Latch* latch = &c->latch[pd.slot];
+        latch->add(jobs);
+        for (int j = 0; j < jobs; ++j) {
+            const int32_t a0 = (int32_t)((int64_t)pd.nf * j / jobs), a1 = (int32_t)((int64_t)pd.nf * (j + 1) / jobs);
+            float* dst = h_vol + (size_t)pd.f0 * vol_floats;
+            c->pool.submit([=] {
+                for (int32_t f = a0; f < a1; ++f)
+                    decode_frame(codes + (size_t)f * (r3 / 4), lits + 3 * loff[f], r3, dst + (size_t)f * vol_floats);
+                latch->done();
+            });
+        }
+        return DTSDF_OK;
+    };
+    auto drain = [&]() {
+        for (int i = 0; i < dtsdf_ctx::NSLOT; ++i) c->latch[i].wait();
+    };
+
     for (int k = 0; k < nchunk; ++k) {
         const int slot = k % dtsdf_ctx::NSLOT;
         const int32_t f0 = k * per_chunk;
@@ -417,16 +638,28 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
             max_px = std::max<int32_t>(max_px, (int32_t)n);
             rebased[i] = h_off[f0 + i] - e0;
         }
-        // the slot's buffers are free once its previous D2H has finished (which also implies
-        // that the kernel reading its input buffers has finished)
-        if (k >= dtsdf_ctx::NSLOT) CK(cudaEventSynchronize(c->ev_out[slot]));
-        if ((rc = c->d_depth[slot].reserve((size_t)(e1 - e0) * 4)) != DTSDF_OK) return rc;
-        if ((rc = c->d_off[slot].reserve((size_t)nf * 8)) != DTSDF_OK) return rc;
-        if ((rc = c->d_hdr[slot].reserve((size_t)nf * 24)) != DTSDF_OK) return rc;
-        if (aux_w && (rc = c->d_aux[slot].reserve((size_t)nf * aux_w * 4)) != DTSDF_OK) return rc;
-        if ((rc = c->d_vol[slot].reserve((size_t)nf * vol_floats * 4)) != DTSDF_OK) return rc;
-        if ((rc = c->d_maxl[slot].reserve((size_t)nf * 4)) != DTSDF_OK) return rc;
-        if ((rc = c->d_mid[slot].reserve((size_t)nf * 12)) != DTSDF_OK) return rc;
+        // the slot's buffers are free once its previous chunk has left them: plain mode, its D2H
+        // has finished (which implies its kernel has); packed mode, the host threads are done
+        // expanding it (its kernels were waited for before they started)
+        if (packed) c->latch[slot].wait();
+        else if (k >= dtsdf_ctx::NSLOT) CK(cudaEventSynchronize(c->ev_out[slot]));
+        auto fail = [&](int code) { if (packed) drain(); return code; };
+        if ((rc = c->d_depth[slot].reserve((size_t)(e1 - e0) * 4)) != DTSDF_OK) return fail(rc);
+        if ((rc = c->d_off[slot].reserve((size_t)nf * 8)) != DTSDF_OK) return fail(rc);
+        if ((rc = c->d_hdr[slot].reserve((size_t)nf * 24)) != DTSDF_OK) return fail(rc);
+        if (aux_w && (rc = c->d_aux[slot].reserve((size_t)nf * aux_w * 4)) != DTSDF_OK) return fail(rc);
+        if ((rc = c->d_vol[slot].reserve((size_t)nf * vol_floats * 4)) != DTSDF_OK) return fail(rc);
+        if ((rc = c->d_maxl[slot].reserve((size_t)nf * 4)) != DTSDF_OK) return fail(rc);
+        if ((rc = c->d_mid[slot].reserve((size_t)nf * 12)) != DTSDF_OK) return fail(rc);
+        if (packed) {
+            if ((rc = c->d_cnt[slot].reserve((size_t)nf * 4)) != DTSDF_OK) return fail(rc);
+            if ((rc = c->d_loff[slot].reserve((size_t)(nf + 1) * 8)) != DTSDF_OK) return fail(rc);
+            if ((rc = c->m_codes[slot].reserve((size_t)nf * (r3 / 4))) != DTSDF_OK) return fail(rc);
+            if ((rc = c->m_loff[slot].reserve((size_t)(nf + 1) * 8)) != DTSDF_OK) return fail(rc);
+            if ((rc = c->m_lits[slot].reserve((size_t)nf * vol_floats * 4 + 16)) != DTSDF_OK) return fail(rc);   // worst case
+            if ((rc = c->d_codes[slot].reserve((size_t)nf * (r3 / 4))) != DTSDF_OK) return fail(rc);
+            if ((rc = c->d_lits[slot].reserve((size_t)nf * vol_floats * 4 + 16)) != DTSDF_OK) return fail(rc);
+        }
 
         // H2D on s_in.  `rebased` is pageable host memory: cudaMemcpyAsync stages it before
         // returning, so reusing the vector for the next chunk is safe.
@@ -444,7 +677,32 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
                                   (const int32_t*)c->d_hdr[slot].p, aux_w ? (const float*)c->d_aux[slot].p : nullptr,
                                   max_px, (float*)c->d_vol[slot].p, (float*)c->d_maxl[slot].p,
                                   (float*)c->d_mid[slot].p, c->s_run);
-        if (rc != DTSDF_OK) return rc;
+        if (rc != DTSDF_OK) return fail(rc);
+
+        if (packed) {
+            // pack into device memory, then: codes and offsets (fixed size) by the copy engine, the
+            // literal stream (device-known size) by a copy kernel into mapped pinned memory
+            void* dv_lits = nullptr;
+            CK(cudaHostGetDevicePointer(&dv_lits, c->m_lits[slot].p, 0));
+            cudaError_t pe = dtsdf::launch_pack(nf, (int)r3, (const float*)c->d_vol[slot].p, (unsigned*)c->d_cnt[slot].p,
+                                                (unsigned long long*)c->d_loff[slot].p, nullptr,
+                                                (unsigned char*)c->d_codes[slot].p, (float*)c->d_lits[slot].p, c->s_run);
+            if (pe == cudaSuccess)
+                pe = dtsdf::launch_pack_push(nf, (const float*)c->d_lits[slot].p,
+                                             (const unsigned long long*)c->d_loff[slot].p, (float*)dv_lits, c->s_run);
+            if (pe != cudaSuccess) { drain(); return cuda_fail(pe, "launch_pack"); }
+            CK(cudaMemcpyAsync(c->m_codes[slot].p, c->d_codes[slot].p, (size_t)nf * (r3 / 4), cudaMemcpyDeviceToHost, c->s_run));
+            CK(cudaMemcpyAsync(c->m_loff[slot].p, c->d_loff[slot].p, (size_t)(nf + 1) * 8, cudaMemcpyDeviceToHost, c->s_run));
+            if (h_maxl)
+                CK(cudaMemcpyAsync(h_maxl + f0, c->d_maxl[slot].p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->s_run));
+            if (h_mid)
+                CK(cudaMemcpyAsync(h_mid + 3 * (size_t)f0, c->d_mid[slot].p, (size_t)nf * 12, cudaMemcpyDeviceToHost, c->s_run));
+            CK(cudaEventRecord(c->ev_run[slot], c->s_run));
+            // while this chunk runs on the GPU, hand the previous one to the host threads
+            if (pend.slot >= 0 && (rc = finalize(pend)) != DTSDF_OK) { drain(); return rc; }
+            pend = {slot, f0, nf};
+            continue;
+        }
         CK(cudaEventRecord(c->ev_run[slot], c->s_run));
 
         // D2H on s_out
@@ -456,6 +714,11 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
         if (h_mid)
             CK(cudaMemcpyAsync(h_mid + 3 * (size_t)f0, c->d_mid[slot].p, (size_t)nf * 12, cudaMemcpyDeviceToHost, c->s_out));
         CK(cudaEventRecord(c->ev_out[slot], c->s_out));
+    }
+    if (packed) {
+        if (pend.slot >= 0) rc = finalize(pend);
+        drain();
+        if (rc != DTSDF_OK) return rc;
     }
     CK(cudaStreamSynchronize(c->s_out));
     CK(cudaStreamSynchronize(c->s_run));

@@ -1003,6 +1003,146 @@ __global__ void normalize_joints_kernel(int total, const float* __restrict__ joi
     out[i] = v;
 }
 
+// ---------------------------------------------------------------- volume codec (device -> host transfer)
+// See dtsdf_internal.h.  One CTA per frame; a thread handles 4 consecutive voxels (one LDG.128
+// per channel plane, one code byte).
+__device__ __forceinline__ unsigned voxel_code(unsigned a, unsigned b, unsigned c) {
+    const bool same = a == b && b == c;
+    return (same && a == 0u) ? 0u : (same && a == 0x3F800000u) ? 1u : (same && a == 0xBF800000u) ? 2u : 3u;
+}
+
+__device__ __forceinline__ unsigned group_codes(const float* __restrict__ vol, int r3, int g, uint4& a,
+                                                uint4& b, uint4& c) {
+    a = __ldg(reinterpret_cast<const uint4*>(vol) + g);
+    b = __ldg(reinterpret_cast<const uint4*>(vol + r3) + g);
+    c = __ldg(reinterpret_cast<const uint4*>(vol + 2 * (size_t)r3) + g);
+    return voxel_code(a.x, b.x, c.x) | (voxel_code(a.y, b.y, c.y) << 2) | (voxel_code(a.z, b.z, c.z) << 4) |
+           (voxel_code(a.w, b.w, c.w) << 6);
+}
+
+__device__ __forceinline__ unsigned literals_in(unsigned byte) {      // number of 2-bit fields equal to 3
+    return __popc(byte & (byte >> 1) & 0x55u);
+}
+
+__global__ void __launch_bounds__(NT) pack_count_kernel(const float* __restrict__ vol, int r3,
+                                                        unsigned* __restrict__ counts) {
+    __shared__ unsigned wsum[NWARP];
+    const float* v = vol + (size_t)blockIdx.x * 3 * r3;
+    unsigned n = 0;
+    for (int g = threadIdx.x; g < r3 / 4; g += NT) {
+        uint4 a, b, c;
+        n += literals_in(group_codes(v, r3, g, a, b, c));
+    }
+    n = __reduce_add_sync(FULL, n);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int w = 0; w < NWARP; ++w) t += wsum[w];
+        counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void pack_scan_kernel(const unsigned* __restrict__ counts, int n, unsigned long long* __restrict__ off,
+                                 unsigned long long* __restrict__ off_copy) {
+    // batches are a few hundred frames: one thread is plenty
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < n; ++i) {
+            off[i] = run;
+            if (off_copy) off_copy[i] = run;
+            run += counts[i];
+        }
+        off[n] = run;
+        if (off_copy) off_copy[n] = run;
+    }
+}
+
+__global__ void __launch_bounds__(NT) pack_write_kernel(const float* __restrict__ vol, int r3,
+                                                        const unsigned* __restrict__ counts,
+                                                        const unsigned long long* __restrict__ off_dev,
+                                                        unsigned char* __restrict__ codes, float* __restrict__ lits) {
+    __shared__ unsigned wsum[NWARP];
+    const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* v = vol + (size_t)f * 3 * r3;
+    unsigned char* cd = codes + (size_t)f * (r3 / 4);
+    float* lt = lits + 3 * off_dev[f];
+    unsigned base = 0;
+    for (int g0 = 0; g0 < r3 / 4; g0 += NT) {            // r3/4 is a multiple of NT for R = 32, 48, 64
+        const int g = g0 + threadIdx.x;
+        uint4 a, b, c;
+        const unsigned byte = group_codes(v, r3, g, a, b, c);
+        cd[g] = (unsigned char)byte;
+        const unsigned n = literals_in(byte);
+        // block-wide exclusive prefix of n in voxel order
+        unsigned incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) {
+            const unsigned t = wsum[w];
+            if (w < warp) before += t;
+            total += t;
+        }
+        unsigned pos = base + before + incl - n;
+        if (n) {
+            const unsigned av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (((byte >> (2 * j)) & 3u) == 3u) {
+                    float* q = lt + 3 * (size_t)pos;
+                    q[0] = __uint_as_float(av[j]); q[1] = __uint_as_float(bv[j]); q[2] = __uint_as_float(cv[j]);
+                    ++pos;
+                }
+            }
+        }
+        base += total;
+        __syncthreads();
+    }
+    (void)counts;
+}
+
+// Copies the literal stream (3 * lit_off[n] floats, a count only the device knows) from device memory
+// to host-mapped memory with whole 16-byte, fully coalesced stores: PCIe likes 128-byte writes, the
+// scattered 4-byte stores of pack_write_kernel it does not.
+__global__ void __launch_bounds__(NT) pack_push_kernel(const float* __restrict__ lits, const unsigned long long* __restrict__ off,
+                                                       int n, float* __restrict__ host_lits) {
+    const unsigned long long n16 = (3ull * off[n] + 3ull) / 4ull;          // uint4 units (buffers are padded)
+    const uint4* src = reinterpret_cast<const uint4*>(lits);
+    uint4* dst = reinterpret_cast<uint4*>(host_lits);
+    for (unsigned long long i = blockIdx.x * (unsigned long long)NT + threadIdx.x; i < n16;
+         i += (unsigned long long)gridDim.x * NT)
+        dst[i] = src[i];
+}
+
+}  // namespace
+
+cudaError_t launch_pack_push(int n_frames, const float* lits, const unsigned long long* lit_off, float* host_lits,
+                             cudaStream_t stream) {
+    if (n_frames <= 0) return cudaSuccess;
+    pack_push_kernel<<<96, NT, 0, stream>>>(lits, lit_off, n_frames, host_lits);
+    ++g_launch_count;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack(int n_frames, int r3, const float* vol, unsigned* counts, unsigned long long* lit_off,
+                        unsigned long long* lit_off_copy, unsigned char* codes, float* lits, cudaStream_t stream) {
+    if (n_frames <= 0) return cudaSuccess;
+    if (r3 % (4 * NT) != 0) return cudaErrorInvalidValue;
+    pack_count_kernel<<<n_frames, NT, 0, stream>>>(vol, r3, counts);
+    pack_scan_kernel<<<1, 32, 0, stream>>>(counts, n_frames, lit_off, lit_off_copy);
+    pack_write_kernel<<<n_frames, NT, 0, stream>>>(vol, r3, counts, lit_off, codes, lits);
+    g_launch_count += 3;
+    return cudaGetLastError();
+}
+
+namespace {
 }  // namespace
 
 // ---------------------------------------------------------------- launchers

@@ -89,6 +89,17 @@ class Voxelizer:
         except Exception:
             pass
 
+    def set_option(self, option, value):
+        """``dtsdf_ctx_set_option``: capi.OPT_PACKED_D2H (packed device->host transfer of the volumes,
+        default on) and capi.OPT_HOST_THREADS (host threads that expand it)."""
+        check(self._lib.dtsdf_ctx_set_option(self._ctx, int(option), int(value)))
+
+    def stat(self, which=capi.STAT_D2H_BYTES):
+        """``dtsdf_ctx_get_stat`` of the last ``voxelize_packed`` call."""
+        v = ctypes.c_int64(0)
+        check(self._lib.dtsdf_ctx_get_stat(self._ctx, int(which), ctypes.byref(v)))
+        return int(v.value)
+
     def config(self, layout=LAYOUT_CXYZ, bbox_mode=BBOX_PIXELS, voxel_res=None):
         cfg = capi.default_config(voxel_res or self.voxel_res, layout, bbox_mode)
         cfg.focal = self.focal

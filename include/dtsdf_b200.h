@@ -177,6 +177,24 @@ typedef struct dtsdf_ctx dtsdf_ctx;
 int  dtsdf_ctx_create(int32_t device, dtsdf_ctx** out);
 void dtsdf_ctx_destroy(dtsdf_ctx* ctx);
 
+/* Context options.
+ *   DTSDF_OPT_PACKED_D2H   1 (default): dtsdf_voxelize_host brings the volumes back in a lossless
+ *                          packed form (2-bit codes for voxels that are 0 / +1 / -1 in all three
+ *                          channels, literals for the rest: ~8x fewer PCIe bytes) written by the
+ *                          GPU straight into mapped pinned memory, and expands them into the
+ *                          caller's buffer with the host threads below (streaming stores).
+ *                          0: plain device->host copies of the float volumes.
+ *   DTSDF_OPT_HOST_THREADS number of host threads for the expansion (default: all hardware
+ *                          threads, at most 32). */
+#define DTSDF_OPT_PACKED_D2H   1
+#define DTSDF_OPT_HOST_THREADS 2
+int dtsdf_ctx_set_option(dtsdf_ctx* ctx, int32_t option, int64_t value);
+/* Statistics of the last dtsdf_voxelize_host call.
+ *   DTSDF_STAT_D2H_BYTES   bytes that crossed PCIe device -> host (packed: codes + offsets +
+ *                          literals + max_l/mid_p; plain: the float volumes + max_l/mid_p) */
+#define DTSDF_STAT_D2H_BYTES 1
+int dtsdf_ctx_get_stat(dtsdf_ctx* ctx, int32_t stat, int64_t* value);
+
 /* Page-locked host buffers for the host entry points (plain malloc'ed memory
  * works too, only slower). */
 int  dtsdf_host_alloc(void** ptr, int64_t bytes);

@@ -220,6 +220,37 @@ def test_empty_batch_and_bad_arguments(vox):
         vox.voxelize_frames([{"header": fr["header"], "depth": fr["depth"][:-1]}])
 
 
+def test_packed_and_plain_host_transfer_agree():
+    """dtsdf_voxelize_host brings volumes back packed (2-bit codes + literals, expanded by host
+    threads) or as plain copies (DTSDF_OPT_PACKED_D2H): the same bits either way, several chunks,
+    every resolution and layout, odd thread counts, an unaligned destination."""
+    frames = synth.make_frames(range(500, 500 + 400))          # 400 x 393 KB = 2.4 chunks at R = 32
+    z = synth.make_frame(7)
+    z["depth"] = np.zeros_like(z["depth"])
+    frames[13] = z                                              # an all-zero volume: no literals at all
+    headers, offsets, packed = pack_simple(frames)
+    v = pkg.Voxelizer(device=0)
+    for R, layout, nthreads, nfr in ((32, 0, 0, 400), (32, 1, 3, 400), (48, 0, 5, 60), (64, 1, 1, 30)):
+        hdr, off = headers[:nfr], offsets[:nfr]
+        v.set_option(pkg.capi.OPT_PACKED_D2H, 0)
+        plain = v.voxelize_packed(hdr, off, packed, layout=layout, voxel_res=R)
+        v.set_option(pkg.capi.OPT_PACKED_D2H, 1)
+        v.set_option(pkg.capi.OPT_HOST_THREADS, nthreads)
+        got = v.voxelize_packed(hdr, off, packed, layout=layout, voxel_res=R)
+        for a, b in zip(plain, got):
+            assert _same(a, b)
+        raw = np.empty(nfr * 3 * R ** 3 + 1, dtype=np.float32)            # destination only 4-byte aligned
+        dst = raw[1:].reshape(nfr, 3, R, R, R)
+        v.voxelize_packed(hdr, off, packed, layout=layout, voxel_res=R, out_vol=dst)
+        assert _same(dst, plain[0])
+    cv, _, _, _ = c_oracle.dtsdf_batch(headers, offsets, packed)
+    v.set_option(pkg.capi.OPT_HOST_THREADS, 0)
+    assert _same(v.voxelize_packed(headers, offsets, packed)[0], cv)
+    with pytest.raises(pkg.DtsdfError):
+        v.set_option(99, 1)
+    v.close()
+
+
 # ----------------------------------------------------------------------------- device-resident path
 def test_device_entry_point_matches_host_entry_point(vox):
     import torch
