@@ -27,6 +27,7 @@ BBOX_EXTREMA = 1
 BBOX_GRID = 2
 OPT_PACKED_D2H = 1
 OPT_HOST_THREADS = 2
+OPT_CHUNK_MB = 3
 STAT_D2H_BYTES = 1
 
 

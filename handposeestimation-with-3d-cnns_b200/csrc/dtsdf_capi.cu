@@ -196,14 +196,9 @@ void decode_frame_t(const unsigned char* codes, const float* lits, size_t r3, fl
             __m128 v0, v1, v2;
             if (g_dec.nlit[b] == 0) {
                 v0 = v1 = v2 = _mm_loadu_ps(g_dec.val[b]);
-            } else {
-                alignas(16) float t0[4], t1[4], t2[4];
-                for (int q = 0; q < 4; ++q) {
-                    const unsigned c = (b >> (2 * q)) & 3u;
-                    if (c == 3u) { t0[q] = lits[0]; t1[q] = lits[1]; t2[q] = lits[2]; lits += 3; }
-                    else { t0[q] = t1[q] = t2[q] = g_dec.val[b][q]; }
-                }
-                v0 = _mm_load_ps(t0); v1 = _mm_load_ps(t1); v2 = _mm_load_ps(t2);
+            } else {                          // literal group: x[4], y[4], z[4] (16-byte aligned)
+                v0 = _mm_load_ps(lits); v1 = _mm_load_ps(lits + 4); v2 = _mm_load_ps(lits + 8);
+                lits += 12;
             }
             put4<ALIGNED>(o0 + 4 * (k + j), v0); put4<ALIGNED>(o1 + 4 * (k + j), v1); put4<ALIGNED>(o2 + 4 * (k + j), v2);
         }
@@ -226,6 +221,7 @@ struct dtsdf_ctx {
     // packed device -> host transfer
     int opt_packed = 1;
     int opt_threads = 0;                        // 0 = hardware concurrency
+    int opt_chunk_mb = 64;
     Pool pool;
     DevBuf d_cnt[NSLOT], d_loff[NSLOT], d_codes[NSLOT], d_lits[NSLOT];
     MapBuf m_codes[NSLOT], m_loff[NSLOT], m_lits[NSLOT];
@@ -523,6 +519,10 @@ int dtsdf_ctx_set_option(dtsdf_ctx* c, int32_t option, int64_t value) {
             if (value < 0 || value > 256) return DTSDF_ERR_INVALID_ARG;
             c->opt_threads = (int)value;
             return DTSDF_OK;
+        case DTSDF_OPT_CHUNK_MB:
+            if (value < 1 || value > 4096) return DTSDF_ERR_INVALID_ARG;
+            c->opt_chunk_mb = (int)value;
+            return DTSDF_OK;
         default:
             return DTSDF_ERR_UNSUPPORTED;
     }
@@ -578,8 +578,8 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
     }
     CK(cudaSetDevice(c->device));
 
-    // chunk size: about 64 MB of output per chunk, at least one frame
-    int32_t per_chunk = (int32_t)std::max<size_t>(1, ((size_t)64 << 20) / (vol_floats * 4));
+    // chunk size: about 64 MB of output per chunk by default, at least one frame
+    int32_t per_chunk = (int32_t)std::max<size_t>(1, ((size_t)c->opt_chunk_mb << 20) / (vol_floats * 4));
     if (per_chunk > n_frames) per_chunk = n_frames;
     const int nchunk = (n_frames + per_chunk - 1) / per_chunk;
     std::vector<int64_t> rebased;
@@ -602,7 +602,7 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
         const unsigned char* codes = (const unsigned char*)c->m_codes[pd.slot].p;
         const unsigned long long* loff = (const unsigned long long*)c->m_loff[pd.slot].p;
         const float* lits = (const float*)c->m_lits[pd.slot].p;
-        c->stat_d2h_bytes += (int64_t)pd.nf * (int64_t)(r3 / 4) + (int64_t)(pd.nf + 1) * 8 + 12 * (int64_t)loff[pd.nf] +
+        c->stat_d2h_bytes += (int64_t)pd.nf * (int64_t)(r3 / 4) + (int64_t)(pd.nf + 1) * 8 + 48 * (int64_t)loff[pd.nf] +
                              (h_maxl ? 4 * (int64_t)pd.nf : 0) + (h_mid ? 12 * (int64_t)pd.nf : 0);
         const int jobs = std::min<int>(pd.nf, nthreads);
         Latch* latch = &c->latch[pd.slot];
@@ -612,7 +612,7 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
             float* dst = h_vol + (size_t)pd.f0 * vol_floats;
             c->pool.submit([=] {
                 for (int32_t f = a0; f < a1; ++f)
-                    decode_frame(codes + (size_t)f * (r3 / 4), lits + 3 * loff[f], r3, dst + (size_t)f * vol_floats);
+                    decode_frame(codes + (size_t)f * (r3 / 4), lits + 12 * loff[f], r3, dst + (size_t)f * vol_floats);
                 latch->done();
             });
         }

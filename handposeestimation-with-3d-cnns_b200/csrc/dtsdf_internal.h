@@ -41,18 +41,18 @@ cudaError_t launch_normalize_joints(int n_frames, const float* joints, const flo
                                     cudaStream_t stream);
 
 // Volume codec for the device -> host transfer (host entry points).  A voxel whose three channels
-// are all +0.0, all +1.0 or all -1.0 (about 90 % of a D-TSDF volume) becomes a 2-bit code 0/1/2;
-// anything else is code 3 plus its three floats in a per-frame literal stream.  Lossless.
-//   counts   [n]     literals per frame (device scratch)
+// are all +0.0, all +1.0 or all -1.0 (about 90 % of a D-TSDF volume) becomes a 2-bit code 0/1/2,
+// anything else code 3.  A group of 4 consecutive voxels (one code byte) that holds a code 3 is a
+// "literal group": its 3 x 4 floats (x[4], y[4], z[4]) go to a per-frame literal stream.  Lossless.
+//   counts   [n]     literal groups per frame (device scratch)
 //   lit_off  [n+1]   exclusive prefix of counts (device); lit_off_copy: optional second copy
-//                    (host-mapped, for the decoder)
-//   codes    [n][R3/4] bytes: voxel 4k+j of the frame in bits 2j..2j+1 of byte k (may be host-mapped)
-//   lits     [3 * lit_off[n]] floats, frame after frame, voxel order, (c0,c1,c2) per literal
+//   codes    [n][R3/4] bytes: voxel 4k+j of the frame in bits 2j..2j+1 of byte k
+//   lits     [12 * lit_off[n]] floats, frame after frame, group order, 48 bytes per literal group
 cudaError_t launch_pack(int n_frames, int r3, const float* vol, unsigned* counts,
                         unsigned long long* lit_off, unsigned long long* lit_off_copy,
                         unsigned char* codes, float* lits, cudaStream_t stream);
 
-// literal stream device -> host-mapped memory, exactly 3 * lit_off[n] floats (rounded up to 16 bytes)
+// literal stream device -> host-mapped memory, exactly 12 * lit_off[n] floats
 cudaError_t launch_pack_push(int n_frames, const float* lits, const unsigned long long* lit_off,
                              float* host_lits, cudaStream_t stream);
 

@@ -1020,8 +1020,8 @@ __device__ __forceinline__ unsigned group_codes(const float* __restrict__ vol, i
            (voxel_code(a.w, b.w, c.w) << 6);
 }
 
-__device__ __forceinline__ unsigned literals_in(unsigned byte) {      // number of 2-bit fields equal to 3
-    return __popc(byte & (byte >> 1) & 0x55u);
+__device__ __forceinline__ unsigned has_literal(unsigned byte) {      // any 2-bit field equal to 3
+    return (byte & (byte >> 1) & 0x55u) != 0u;
 }
 
 __global__ void __launch_bounds__(NT) pack_count_kernel(const float* __restrict__ vol, int r3,
@@ -1031,7 +1031,7 @@ __global__ void __launch_bounds__(NT) pack_count_kernel(const float* __restrict_
     unsigned n = 0;
     for (int g = threadIdx.x; g < r3 / 4; g += NT) {
         uint4 a, b, c;
-        n += literals_in(group_codes(v, r3, g, a, b, c));
+        n += has_literal(group_codes(v, r3, g, a, b, c));
     }
     n = __reduce_add_sync(FULL, n);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = n;
@@ -1059,29 +1059,23 @@ __global__ void pack_scan_kernel(const unsigned* __restrict__ counts, int n, uns
 }
 
 __global__ void __launch_bounds__(NT) pack_write_kernel(const float* __restrict__ vol, int r3,
-                                                        const unsigned* __restrict__ counts,
                                                         const unsigned long long* __restrict__ off_dev,
                                                         unsigned char* __restrict__ codes, float* __restrict__ lits) {
     __shared__ unsigned wsum[NWARP];
     const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* v = vol + (size_t)f * 3 * r3;
     unsigned char* cd = codes + (size_t)f * (r3 / 4);
-    float* lt = lits + 3 * off_dev[f];
+    uint4* lt = reinterpret_cast<uint4*>(lits) + 3 * off_dev[f];
     unsigned base = 0;
     for (int g0 = 0; g0 < r3 / 4; g0 += NT) {            // r3/4 is a multiple of NT for R = 32, 48, 64
         const int g = g0 + threadIdx.x;
         uint4 a, b, c;
         const unsigned byte = group_codes(v, r3, g, a, b, c);
         cd[g] = (unsigned char)byte;
-        const unsigned n = literals_in(byte);
-        // block-wide exclusive prefix of n in voxel order
-        unsigned incl = n;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned t = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane == 31) wsum[warp] = incl;
+        const unsigned lit = has_literal(byte);
+        // block-wide exclusive prefix of the literal groups, in voxel order
+        const unsigned bal = __ballot_sync(FULL, lit);
+        if (lane == 0) wsum[warp] = __popc(bal);
         __syncthreads();
         unsigned before = 0, total = 0;
 #pragma unroll
@@ -1090,30 +1084,21 @@ __global__ void __launch_bounds__(NT) pack_write_kernel(const float* __restrict_
             if (w < warp) before += t;
             total += t;
         }
-        unsigned pos = base + before + incl - n;
-        if (n) {
-            const unsigned av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, cv[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (((byte >> (2 * j)) & 3u) == 3u) {
-                    float* q = lt + 3 * (size_t)pos;
-                    q[0] = __uint_as_float(av[j]); q[1] = __uint_as_float(bv[j]); q[2] = __uint_as_float(cv[j]);
-                    ++pos;
-                }
-            }
+        if (lit) {
+            uint4* q = lt + 3 * (size_t)(base + before + __popc(bal & ((1u << lane) - 1u)));
+            q[0] = a; q[1] = b; q[2] = c;
         }
         base += total;
         __syncthreads();
     }
-    (void)counts;
 }
 
-// Copies the literal stream (3 * lit_off[n] floats, a count only the device knows) from device memory
+// Copies the literal stream (12 * lit_off[n] floats, a count only the device knows) from device memory
 // to host-mapped memory with whole 16-byte, fully coalesced stores: PCIe likes 128-byte writes, the
 // scattered 4-byte stores of pack_write_kernel it does not.
 __global__ void __launch_bounds__(NT) pack_push_kernel(const float* __restrict__ lits, const unsigned long long* __restrict__ off,
                                                        int n, float* __restrict__ host_lits) {
-    const unsigned long long n16 = (3ull * off[n] + 3ull) / 4ull;          // uint4 units (buffers are padded)
+    const unsigned long long n16 = 3ull * off[n];                          // uint4 units
     const uint4* src = reinterpret_cast<const uint4*>(lits);
     uint4* dst = reinterpret_cast<uint4*>(host_lits);
     for (unsigned long long i = blockIdx.x * (unsigned long long)NT + threadIdx.x; i < n16;
@@ -1137,7 +1122,7 @@ cudaError_t launch_pack(int n_frames, int r3, const float* vol, unsigned* counts
     if (r3 % (4 * NT) != 0) return cudaErrorInvalidValue;
     pack_count_kernel<<<n_frames, NT, 0, stream>>>(vol, r3, counts);
     pack_scan_kernel<<<1, 32, 0, stream>>>(counts, n_frames, lit_off, lit_off_copy);
-    pack_write_kernel<<<n_frames, NT, 0, stream>>>(vol, r3, counts, lit_off, codes, lits);
+    pack_write_kernel<<<n_frames, NT, 0, stream>>>(vol, r3, lit_off, codes, lits);
     g_launch_count += 3;
     return cudaGetLastError();
 }

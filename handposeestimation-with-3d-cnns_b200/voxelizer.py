@@ -77,6 +77,15 @@ class Voxelizer:
         self.trunc_mul = float(trunc_mul)
         self._ctx = ctypes.c_void_p()
         check(self._lib.dtsdf_ctx_create(int(device), ctypes.byref(self._ctx)))
+        # one process per GPU (torchrun): the ranks of a node share its host cores, so each takes its
+        # share of them for the expansion of packed volumes
+        import os
+        try:
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        except ValueError:
+            local_world = 1
+        if local_world > 1:
+            self.set_option(capi.OPT_HOST_THREADS, max(1, (os.cpu_count() or 1) // local_world))
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:

@@ -188,6 +188,7 @@ void dtsdf_ctx_destroy(dtsdf_ctx* ctx);
  *                          threads, at most 32). */
 #define DTSDF_OPT_PACKED_D2H   1
 #define DTSDF_OPT_HOST_THREADS 2
+#define DTSDF_OPT_CHUNK_MB     3   /* output megabytes per pipeline chunk of dtsdf_voxelize_host (default 64) */
 int dtsdf_ctx_set_option(dtsdf_ctx* ctx, int32_t option, int64_t value);
 /* Statistics of the last dtsdf_voxelize_host call.
  *   DTSDF_STAT_D2H_BYTES   bytes that crossed PCIe device -> host (packed: codes + offsets +
