@@ -29,6 +29,8 @@ OPT_PACKED_D2H = 1
 OPT_HOST_THREADS = 2
 OPT_CHUNK_MB = 3
 STAT_D2H_BYTES = 1
+JOINT_CLAMP01 = 1
+JOINT_FLIP_Z = 2
 
 
 class DtsdfError(RuntimeError):
@@ -75,6 +77,8 @@ _SIGNATURES = {
     "dtsdf_shared_close": (ctypes.c_int, [_i32, _vp]),
     "dtsdf_pack_plan": (ctypes.c_int, [_i32, _vp, _vp, ctypes.POINTER(_i64), ctypes.POINTER(_i32)]),
     "dtsdf_voxelize_batch": (ctypes.c_int, [_cfgp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "dtsdf_voxelize_joints_batch": (ctypes.c_int, [_cfgp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp,
+                                                   _vp]),
     "dtsdf_point_cloud_batch": (ctypes.c_int, [_i32, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_resample_extrema_batch": (ctypes.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_normalize_joints_batch": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i32, _vp, _vp]),

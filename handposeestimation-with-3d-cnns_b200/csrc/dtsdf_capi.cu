@@ -386,7 +386,18 @@ int dtsdf_voxelize_batch(const dtsdf_config* cfg, int32_t n_frames, const float*
                          const int64_t* d_crop_offsets, const int32_t* d_headers,
                          const float* d_aux, int32_t max_crop_px, float* d_out_vol,
                          float* d_out_max_l, float* d_out_mid_p, void* stream) {
+    return dtsdf_voxelize_joints_batch(cfg, n_frames, d_depth_packed, d_crop_offsets, d_headers, d_aux, max_crop_px,
+                                       nullptr, 0, d_out_vol, d_out_max_l, d_out_mid_p, nullptr, stream);
+}
+
+int dtsdf_voxelize_joints_batch(const dtsdf_config* cfg, int32_t n_frames, const float* d_depth_packed,
+                                const int64_t* d_crop_offsets, const int32_t* d_headers,
+                                const float* d_aux, int32_t max_crop_px, const float* d_joints,
+                                int32_t joint_flags, float* d_out_vol, float* d_out_max_l,
+                                float* d_out_mid_p, float* d_out_joints, void* stream) {
     int rc = check_cfg(cfg);
+    if ((d_joints != nullptr) != (d_out_joints != nullptr)) return DTSDF_ERR_INVALID_ARG;
+    if (joint_flags & ~3) return DTSDF_ERR_INVALID_ARG;
     if (rc != DTSDF_OK) return rc;
     if (n_frames < 0) return DTSDF_ERR_INVALID_ARG;
     if (n_frames == 0) return DTSDF_OK;
@@ -407,6 +418,9 @@ int dtsdf_voxelize_batch(const dtsdf_config* cfg, int32_t n_frames, const float*
     a.center_y = cfg->center_y;
     a.focal = cfg->focal;
     a.trunc_mul = cfg->trunc_mul;
+    a.joints = d_joints;
+    a.out_joints = d_out_joints;
+    a.joint_flags = joint_flags;
     CK(dtsdf::launch_voxelize(cfg->voxel_res, cfg->layout, a, max_crop_px, (cudaStream_t)stream));
     return DTSDF_OK;
 }

@@ -21,6 +21,9 @@ struct BatchArgs {
     int              center_y;
     float            focal;
     float            trunc_mul;
+    const float*     joints;     // [n][63] ground-truth joints to normalise in the same launch, or nullptr
+    float*           out_joints; // [n][63]
+    int              joint_flags; // bit 0: clamp to [0,1]; bit 1: negate z first (3D_CNN/dataset.py:107)
 };
 
 // Picks the staging capacity / grid and launches the fused kernel.  Returns a cudaError_t.

@@ -741,18 +741,21 @@ __global__ void __launch_bounds__(NT, DTSDF_MIN_CTAS) dtsdf_fused_kernel(const _
 
     // ---- 2. bounding box -> grid parameters
     float ox, oy, oz, voxel_len, trunc;
+    float jmid0, jmid1, jmid2, jmax_l;      // what the joint normalisation uses
     if (a.bbox_mode == 2) {       // DTSDF_BBOX_GRID: pre/process.py:122 arguments
         const float* g = a.aux + 5 * (size_t)f;
         ox = __ldg(g); oy = __ldg(g + 1); oz = __ldg(g + 2);
         voxel_len = __ldg(g + 3); trunc = __ldg(g + 4);
+        // centre of the cube: vox_ori + (R-1)/2 * voxel_len (informational only)
+        const float hl = __fmul_rn(voxel_len, 0.5f * (float)(R - 1));
+        jmax_l = __fmul_rn(voxel_len, (float)R);
+        jmid0 = __fadd_rn(ox, hl); jmid1 = __fadd_rn(oy, hl); jmid2 = __fadd_rn(oz, hl);
         if (tid == 0) {
-            if (a.max_l) a.max_l[f] = __fmul_rn(voxel_len, (float)R);
+            if (a.max_l) a.max_l[f] = jmax_l;
             if (a.mid_p) {
-                // centre of the cube: vox_ori + (R-1)/2 * voxel_len (informational only)
-                const float hl = __fmul_rn(voxel_len, 0.5f * (float)(R - 1));
-                a.mid_p[3 * (size_t)f + 0] = __fadd_rn(ox, hl);
-                a.mid_p[3 * (size_t)f + 1] = __fadd_rn(oy, hl);
-                a.mid_p[3 * (size_t)f + 2] = __fadd_rn(oz, hl);
+                a.mid_p[3 * (size_t)f + 0] = jmid0;
+                a.mid_p[3 * (size_t)f + 1] = jmid1;
+                a.mid_p[3 * (size_t)f + 2] = jmid2;
             }
         }
     } else {
@@ -787,6 +790,7 @@ __global__ void __launch_bounds__(NT, DTSDF_MIN_CTAS) dtsdf_fused_kernel(const _
         ox = __fadd_rn(__fsub_rn(mid0, half_l), half_v);
         oy = __fadd_rn(__fsub_rn(mid1, half_l), half_v);
         oz = __fadd_rn(__fsub_rn(mid2, half_l), half_v);
+        jmax_l = max_l; jmid0 = mid0; jmid1 = mid1; jmid2 = mid2;
         if (tid == 0) {
             if (a.max_l) a.max_l[f] = max_l;
             if (a.mid_p) {
@@ -795,6 +799,18 @@ __global__ void __launch_bounds__(NT, DTSDF_MIN_CTAS) dtsdf_fused_kernel(const _
                 a.mid_p[3 * (size_t)f + 2] = mid2;
             }
         }
+    }
+
+    // ---- joint normalisation in the same launch: (gt - mid_p)/max_l + 0.5 in float32
+    //      (pre/joint_nor.py:8-18; 3D_CNN/train.py:236-244 with the clamp)
+    if (a.joints != nullptr && tid < 63) {
+        const int c = tid % 3;
+        float g = __ldg(a.joints + 63 * (size_t)f + tid);
+        if ((a.joint_flags & 2) && c == 2) g = -g;
+        const float m = c == 0 ? jmid0 : (c == 1 ? jmid1 : jmid2);
+        float v = __fadd_rn(__fdiv_rn(__fsub_rn(g, m), jmax_l), 0.5f);
+        if (a.joint_flags & 1) v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+        a.out_joints[63 * (size_t)f + tid] = v;
     }
 
     // ---- per-axis voxel centres and the two projection tables

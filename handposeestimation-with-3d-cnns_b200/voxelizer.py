@@ -256,11 +256,14 @@ def _torch_stream_ptr(stream=None):
 
 
 def voxelize_device(depth_packed, offsets, headers, max_crop_px=0, cfg=None, aux=None,
-                    out_vol=None, out_max_l=None, out_mid_p=None, stream=None):
+                    out_vol=None, out_max_l=None, out_mid_p=None, stream=None, joints=None, joint_flags=0,
+                    out_joints=None):
     """``dtsdf_voxelize_batch`` on torch CUDA tensors, asynchronous on torch's current stream.
 
     depth_packed float32[packed_len], offsets int64[n], headers int32[n,6] - all on the same
     CUDA device.  Returns (vol float32[n,3,R,R,R], max_l float32[n], mid_p float32[n,3]).
+    With ``joints`` (float32[n,63]) the joint normalisation runs in the same launch
+    (``dtsdf_voxelize_joints_batch``) and a fourth value, float32[n,63], is returned.
     """
     import torch
     if not (depth_packed.is_cuda and offsets.is_cuda and headers.is_cuda):
@@ -281,6 +284,16 @@ def voxelize_device(depth_packed, offsets, headers, max_crop_px=0, cfg=None, aux
     if aux is not None:
         assert aux.is_cuda and aux.dtype == torch.float32 and aux.is_contiguous()
         aux_ptr = aux.data_ptr()
+    if joints is not None:
+        assert joints.is_cuda and joints.dtype == torch.float32 and joints.is_contiguous() and joints.numel() == n * 63
+        if out_joints is None:
+            out_joints = torch.empty((n, 63), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(load_library().dtsdf_voxelize_joints_batch(
+                ctypes.byref(cfg), n, depth_packed.data_ptr(), offsets.data_ptr(), headers.data_ptr(), aux_ptr,
+                int(max_crop_px), joints.data_ptr(), int(joint_flags), out_vol.data_ptr(), out_max_l.data_ptr(),
+                out_mid_p.data_ptr(), out_joints.data_ptr(), _torch_stream_ptr(stream)))
+        return out_vol, out_max_l, out_mid_p, out_joints
     with torch.cuda.device(dev):
         check(load_library().dtsdf_voxelize_batch(
             ctypes.byref(cfg), n, depth_packed.data_ptr(), offsets.data_ptr(), headers.data_ptr(), aux_ptr,

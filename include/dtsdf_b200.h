@@ -136,6 +136,22 @@ int dtsdf_voxelize_batch(const dtsdf_config* cfg, int32_t n_frames,
                          float* d_out_vol, float* d_out_max_l, float* d_out_mid_p,
                          void* stream);
 
+/* dtsdf_voxelize_batch plus the joint normalisation of the same frames in the same launch:
+ * out = (gt - mid_p)/max_l + 0.5 with the frame's own mid_p / max_l (pre/joint_nor.py:8-18), which
+ * the trainer recomputes per sample in a Python loop on GPU tensors (3D_CNN/train.py:236-244).
+ *   d_joints      float[n][63] ground truth (21 joints x 3)
+ *   joint_flags   DTSDF_JOINT_CLAMP01: clamp to [0,1] (3D_CNN/train.py:241-242);
+ *                 DTSDF_JOINT_FLIP_Z: negate every z first (3D_CNN/dataset.py:107)
+ *   d_out_joints  float[n][63] */
+#define DTSDF_JOINT_CLAMP01 1
+#define DTSDF_JOINT_FLIP_Z  2
+int dtsdf_voxelize_joints_batch(const dtsdf_config* cfg, int32_t n_frames,
+                                const float* d_depth_packed, const int64_t* d_crop_offsets,
+                                const int32_t* d_headers, const float* d_aux, int32_t max_crop_px,
+                                const float* d_joints, int32_t joint_flags,
+                                float* d_out_vol, float* d_out_max_l, float* d_out_mid_p,
+                                float* d_out_joints, void* stream);
+
 /* Back-projection of every pixel with d != 0 to a float64 point, compacted in
  * row-major order.  Replaces DataProcess.point_cloud (pre/process.py:30-68).
  *   focal           the Python float 241.42 as a double (the reference divides float64

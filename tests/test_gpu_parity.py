@@ -340,3 +340,54 @@ def test_kernel_stores_into_peer_memory():
         torch.cuda.synchronize(d1)
     cv, _, _, _ = c_oracle.dtsdf_batch(*pack_simple(frames))
     assert _same(out0.cpu().numpy(), cv)
+
+
+def test_joint_normalisation_fused_into_the_voxeliser_launch(vox):
+    """dtsdf_voxelize_joints_batch: the joints come out normalised with the frame's own mid_p / max_l
+    (pre/joint_nor.py:8-18), bit-identical to the stand-alone kernel, with the trainer's clamp
+    (3D_CNN/train.py:241-242) and the loader's z flip (3D_CNN/dataset.py:107) as flags."""
+    import torch
+    frames = synth.make_frames(range(600, 640))
+    headers, offsets, packed, max_px = pkg.pack_frames(frames)
+    dev = torch.device("cuda:0")
+    gt = np.random.default_rng(5).uniform(-150, 150, size=(len(frames), 63)).astype(np.float32)
+    args = (torch.from_numpy(packed).to(dev), torch.from_numpy(offsets).to(dev), torch.from_numpy(headers).to(dev), max_px)
+    vol0, ml0, mp0 = pkg.voxelize_device(*args)
+    for flags in (0, pkg.capi.JOINT_CLAMP01, pkg.capi.JOINT_FLIP_Z, pkg.capi.JOINT_CLAMP01 | pkg.capi.JOINT_FLIP_Z):
+        vol, ml, mp, jn = pkg.voxelize_device(*args, joints=torch.from_numpy(gt).to(dev), joint_flags=flags)
+        torch.cuda.synchronize()
+        assert torch.equal(vol, vol0) and torch.equal(ml, ml0) and torch.equal(mp, mp0)
+        g = gt.reshape(-1, 21, 3).copy()
+        if flags & pkg.capi.JOINT_FLIP_Z:
+            g[:, :, 2] = -g[:, :, 2]
+        ref = vox.normalize_joints(g.reshape(-1, 63), ml.cpu().numpy(), mp.cpu().numpy(),
+                                   clamp01=bool(flags & pkg.capi.JOINT_CLAMP01))
+        assert np.array_equal(jn.cpu().numpy(), ref)
+
+
+def test_on_the_fly_loader_overlapped_batches(vox):
+    """loader.OnTheFlyLoader (BASELINE.json configs[4]): batches voxelised on a side stream from frames
+    resident in HBM, joint normalisation fused; every batch equals the direct result, in order and shuffled."""
+    import importlib
+    import torch
+    lmod = importlib.import_module(pkg.__name__ + ".loader")
+    frames = synth.make_frames(range(700, 700 + 70))
+    gt = np.random.default_rng(9).uniform(-150, 150, size=(len(frames), 63)).astype(np.float32)
+    res = lmod.ResidentFrames.from_frames(frames, joints=gt)
+    want_vol, want_ml, want_mp = vox.voxelize_frames(frames)
+    want_jn = vox.normalize_joints(gt, want_ml, want_mp, clamp01=True)
+    for shuffle in (False, True):
+        loader = lmod.OnTheFlyLoader(res, batch_size=16, shuffle=shuffle, seed=3)
+        assert len(loader) == 5
+        order = loader._order().cpu().numpy()
+        seen = 0
+        acc = torch.zeros((), device="cuda")
+        for tsdf, jn, max_l, mid_p in loader:
+            m = tsdf.shape[0]
+            idx = order[seen:seen + m]
+            acc += tsdf.abs().sum()                   # consumer work on the current stream
+            assert _same(tsdf.cpu().numpy(), want_vol[idx])
+            assert np.array_equal(jn.cpu().numpy(), want_jn[idx])
+            assert np.array_equal(max_l.cpu().numpy(), want_ml[idx]) and np.array_equal(mid_p.cpu().numpy(), want_mp[idx])
+            seen += m
+        assert seen == len(frames) and float(acc) > 0
