@@ -79,6 +79,8 @@ _SIGNATURES = {
     "dtsdf_voxelize_batch": (ctypes.c_int, [_cfgp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "dtsdf_voxelize_joints_batch": (ctypes.c_int, [_cfgp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp,
                                                    _vp]),
+    "dtsdf_voxelize_aug_batch": (ctypes.c_int, [_cfgp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp,
+                                                _vp]),
     "dtsdf_point_cloud_batch": (ctypes.c_int, [_i32, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_resample_extrema_batch": (ctypes.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_normalize_joints_batch": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i32, _vp, _vp]),

@@ -425,6 +425,39 @@ int dtsdf_voxelize_joints_batch(const dtsdf_config* cfg, int32_t n_frames, const
     return DTSDF_OK;
 }
 
+int dtsdf_voxelize_aug_batch(const dtsdf_config* cfg, int32_t n_frames, const float* d_depth_packed,
+                             const int64_t* d_crop_offsets, const int32_t* d_headers, const float* d_aug,
+                             int32_t max_crop_px, const float* d_joints, int32_t joint_flags,
+                             float* d_out_vol, float* d_out_max_l, float* d_out_mid_p, float* d_out_joints,
+                             void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc != DTSDF_OK) return rc;
+    if (n_frames < 0) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!d_depth_packed || !d_crop_offsets || !d_headers || !d_out_vol || !d_aug) return DTSDF_ERR_INVALID_ARG;
+    if ((d_joints != nullptr) != (d_out_joints != nullptr) || (joint_flags & ~3)) return DTSDF_ERR_INVALID_ARG;
+    dtsdf::BatchArgs a;
+    a.depth = d_depth_packed;
+    a.offsets = reinterpret_cast<const long long*>(d_crop_offsets);
+    a.headers = d_headers;
+    a.aux = nullptr;
+    a.vol = d_out_vol;
+    a.max_l = d_out_max_l;
+    a.mid_p = d_out_mid_p;
+    a.n_frames = n_frames;
+    a.cap_floats = 0;
+    a.bbox_mode = DTSDF_BBOX_PIXELS;
+    a.center_x = cfg->center_x;
+    a.center_y = cfg->center_y;
+    a.focal = cfg->focal;
+    a.trunc_mul = cfg->trunc_mul;
+    a.joints = d_joints;
+    a.out_joints = d_out_joints;
+    a.joint_flags = joint_flags;
+    CK(dtsdf::launch_voxelize_aug(cfg->voxel_res, cfg->layout, a, d_aug, max_crop_px, (cudaStream_t)stream));
+    return DTSDF_OK;
+}
+
 int dtsdf_point_cloud_batch(int32_t n_frames, double focal, const float* d_depth_packed,
                             const int64_t* d_crop_offsets, const int32_t* d_headers,
                             double* d_points, const int64_t* d_point_offsets, int32_t* d_n_valid,

@@ -30,6 +30,11 @@ struct BatchArgs {
 cudaError_t launch_voxelize(int voxel_res, int layout, BatchArgs args, int max_crop_px,
                             cudaStream_t stream);
 
+// Augmented D-TSDF (oracle/dtsdf_oracle.c: oracle_dtsdf_aug_frame is the specification).
+// aug: [n][21] = A (3x3 row-major), Ainv, c.
+cudaError_t launch_voxelize_aug(int voxel_res, int layout, BatchArgs args, const float* aug, int max_crop_px,
+                                cudaStream_t stream);
+
 cudaError_t launch_point_cloud(int n_frames, double focal, const float* depth,
                                const long long* offsets, const int* headers, double* points,
                                const long long* point_offsets, int* n_valid,

@@ -1019,6 +1019,180 @@ __global__ void normalize_joints_kernel(int total, const float* __restrict__ joi
     out[i] = v;
 }
 
+// ---------------------------------------------------------------- augmented D-TSDF
+// Specification: oracle/dtsdf_oracle.c, oracle_dtsdf_aug_frame (the
+// reference's own augmentation cannot run, pre/process.py:252).  p' = (p - c) . A + c; the grid is
+// laid over the augmented hand, every voxel centre is taken back to the camera frame with Ainv,
+// projected and looked up as in pre/process.py:150-175, and the distances are measured in the
+// augmented frame.  The projection no longer separates per axis, so this kernel evaluates every
+// voxel directly (IEEE divisions, one pass); it is the training-time path, not the bench's.
+__device__ __forceinline__ void xform(float px, float py, float pz, const float* __restrict__ M,
+                                      const float* __restrict__ c, float (&q)[3]) {
+    const float dx = __fsub_rn(px, c[0]), dy = __fsub_rn(py, c[1]), dz = __fsub_rn(pz, c[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float t = __fmul_rn(dx, M[k]);
+        t = __fmaf_rn(dy, M[3 + k], t);
+        t = __fmaf_rn(dz, M[6 + k], t);
+        q[k] = __fadd_rn(t, c[k]);
+    }
+}
+
+template <int R, int LAYOUT>
+__global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ BatchArgs a,
+                                                       const float* __restrict__ aug_all) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float red[NWARP][8];
+    __shared__ float aug[21];
+    __shared__ unsigned long long bar;
+    float* crop_s = reinterpret_cast<float*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.x;
+    const Frame fr = load_frame(a, f);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        if (fr.staged) {
+            mbar_expect_tx(&bar, (uint32_t)fr.n_pad * 4u);
+            bulk_g2s(crop_s, fr.crop, (uint32_t)fr.n_pad * 4u, &bar);
+        }
+    }
+    if (tid < 21) aug[tid] = __ldg(aug_all + 21 * (size_t)f + tid);
+    __syncthreads();
+    if (fr.staged) mbar_wait(&bar, 0);
+    const float* __restrict__ crop = fr.staged ? crop_s : fr.crop;
+    const float *A = aug, *Ainv = aug + 9, *c = aug + 18;
+    const float focal = a.focal;
+
+    // ---- 1. bounding box of the augmented points of all valid pixels
+    float mn[3] = {SENTINEL, SENTINEL, SENTINEL}, mx[3] = {-SENTINEL, -SENTINEL, -SENTINEL};
+    for (int pos = tid; pos < fr.n; pos += NT) {
+        const float d = crop[pos];
+        if (fabsf(d) < 1.0f) continue;
+        const int row = pos / fr.bw, col = pos - row * fr.bw;
+        const float q = __fdiv_rn(d, focal);
+        const float X = __fmul_rn(q, (float)(col + fr.l - a.center_x));
+        const float Y = __fmul_rn(-q, (float)(row + fr.t - a.center_y));
+        float pa[3];
+        xform(X, Y, -d, A, c, pa);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { mn[k] = pa[k] < mn[k] ? pa[k] : mn[k]; mx[k] = pa[k] > mx[k] ? pa[k] : mx[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
+    if (lane == 0) {
+        *reinterpret_cast<float4*>(&red[warp][0]) = make_float4(mn[0], mn[1], mn[2], mx[0]);
+        *reinterpret_cast<float2*>(&red[warp][4]) = make_float2(mx[1], mx[2]);
+    }
+    __syncthreads();
+    bbox_reduce(red, mn, mx);
+
+    // ---- 2. grid parameters (pre/process.py:91-96)
+    const float mid0 = __fmul_rn(__fadd_rn(mx[0], mn[0]), 0.5f);
+    const float mid1 = __fmul_rn(__fadd_rn(mx[1], mn[1]), 0.5f);
+    const float mid2 = __fmul_rn(__fadd_rn(mx[2], mn[2]), 0.5f);
+    const float max_l = fmaxf(fmaxf(__fsub_rn(mx[0], mn[0]), __fsub_rn(mx[1], mn[1])), __fsub_rn(mx[2], mn[2]));
+    const float voxel_len = __fdiv_rn(max_l, (float)R);
+    const float trunc = __fmul_rn(voxel_len, a.trunc_mul);
+    const float half_l = __fmul_rn(max_l, 0.5f), half_v = __fmul_rn(voxel_len, 0.5f);
+    const float ox = __fadd_rn(__fsub_rn(mid0, half_l), half_v);
+    const float oy = __fadd_rn(__fsub_rn(mid1, half_l), half_v);
+    const float oz = __fadd_rn(__fsub_rn(mid2, half_l), half_v);
+    if (tid == 0) {
+        if (a.max_l) a.max_l[f] = max_l;
+        if (a.mid_p) {
+            a.mid_p[3 * (size_t)f + 0] = mid0; a.mid_p[3 * (size_t)f + 1] = mid1; a.mid_p[3 * (size_t)f + 2] = mid2;
+        }
+    }
+    // augmented, normalised joints: (T(gt; A, c) - mid_p)/max_l + 0.5
+    if (a.joints != nullptr && tid < 21) {
+        const float* g = a.joints + 63 * (size_t)f + 3 * tid;
+        float gz = __ldg(g + 2);
+        if (a.joint_flags & 2) gz = -gz;
+        float ga[3];
+        xform(__ldg(g), __ldg(g + 1), gz, A, c, ga);
+        const float m[3] = {mid0, mid1, mid2};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float v = __fadd_rn(__fdiv_rn(__fsub_rn(ga[k], m[k]), max_l), 0.5f);
+            if (a.joint_flags & 1) v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+            a.out_joints[63 * (size_t)f + 3 * tid + k] = v;
+        }
+    }
+
+    // ---- 3. voxel loop: a thread owns 4 consecutive voxels along the fastest output axis
+    constexpr int Q = R / 4, CH = R * R * R;
+    float* out = a.vol + (size_t)f * 3 * CH;
+    for (int g = tid; g < CH / 4; g += NT) {
+        const int f0 = 4 * (g % Q), m = (g / Q) % R, s = g / (Q * R);
+        float o0[4], o1[4], o2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int xi = LAYOUT == 0 ? s : f0 + j, yi = m, zi = LAYOUT == 0 ? f0 + j : s;
+            const float vax = __fadd_rn(ox, __fmul_rn((float)xi, voxel_len));
+            const float vay = __fadd_rn(oy, __fmul_rn((float)yi, voxel_len));
+            const float vaz = __fadd_rn(oz, __fmul_rn((float)zi, voxel_len));
+            float v[3];
+            xform(vax, vay, vaz, Ainv, c, v);
+            const float coeff = __fdiv_rn(-focal, v[2]);
+            const float fpx = __fadd_rn(__fmul_rn(v[0], coeff), (float)a.center_x);
+            const float fpy = __fadd_rn(__fmul_rn(-v[1], coeff), (float)a.center_y);
+            float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+            if (fabsf(fpx) < 2e9f && fabsf(fpy) < 2e9f) {
+                const int px = __float2int_rz(fpx), py = __float2int_rz(fpy);
+                if (px >= fr.l && px < fr.r && py >= fr.t && py < fr.b) {
+                    const float d = crop[(size_t)(py - fr.t) * fr.bw + (px - fr.l)];
+                    if (!(fabsf(d) < 1.0f)) {
+                        const float c1 = __fdiv_rn(d, focal);
+                        float wa[3];
+                        xform(__fmul_rn((float)(px - a.center_x), c1), __fmul_rn((float)(-(py - a.center_y)), c1), -d, A, c, wa);
+                        t0 = __fdiv_rn(fabsf(__fsub_rn(vax, wa[0])), trunc);
+                        t1 = __fdiv_rn(fabsf(__fsub_rn(vay, wa[1])), trunc);
+                        t2 = __fdiv_rn(fabsf(__fsub_rn(vaz, wa[2])), trunc);
+                        const float ss = __fadd_rn(__fadd_rn(__fmul_rn(t0, t0), __fmul_rn(t1, t1)), __fmul_rn(t2, t2));
+                        // sqrt_rn(ss) > 1 <=> ss > nextafter(1,2); then min(t,1) is the identity below it,
+                        // except for NaN (kept) - same as the specification's comparisons
+                        if (ss > THR_SQ) { t0 = 1.0f; t1 = 1.0f; t2 = 1.0f; }
+                        if (1.0f < t0) t0 = 1.0f;
+                        if (1.0f < t1) t1 = 1.0f;
+                        if (1.0f < t2) t2 = 1.0f;
+                        if (-d > v[2]) { t0 = -t0; t1 = -t1; t2 = -t2; }
+                    }
+                }
+            }
+            o0[j] = t0; o1[j] = t1; o2[j] = t2;
+        }
+        float* p = out + 4 * (size_t)g;
+        st_f4(p, make_float4(o0[0], o0[1], o0[2], o0[3]));
+        st_f4(p + CH, make_float4(o1[0], o1[1], o1[2], o1[3]));
+        st_f4(p + 2 * CH, make_float4(o2[0], o2[1], o2[2], o2[3]));
+    }
+}
+
+template <int R, int LAYOUT>
+cudaError_t launch_aug_t(const BatchArgs& args_in, const float* aug, int max_crop_px, cudaStream_t stream) {
+    BatchArgs args = args_in;
+    int dev = 0, smem_optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    if ((reinterpret_cast<uintptr_t>(args.vol) & 15) != 0 || (reinterpret_cast<uintptr_t>(args.depth) & 15) != 0)
+        return cudaErrorMisalignedAddress;
+    long long want = max_crop_px > 0 ? (((long long)max_crop_px + 3) & ~3ll) * 4 : (long long)smem_optin;
+    const long long avail = (long long)smem_optin - 2048;
+    if (want > avail) want = avail;
+    if (want < 16) want = 16;
+    want &= ~15ll;
+    args.cap_floats = (int)(want / 4);
+    auto kern = dtsdf_aug_kernel<R, LAYOUT>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)args.n_frames, NT, (size_t)want, stream>>>(args, aug);
+    ++g_launch_count;
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- volume codec (device -> host transfer)
 // See dtsdf_internal.h.  One CTA per frame; a thread handles 4 consecutive voxels (one LDG.128
 // per channel plane, one code byte).
@@ -1169,6 +1343,19 @@ cudaError_t launch_voxelize(int voxel_res, int layout, BatchArgs args, int max_c
             return cudaErrorInvalidValue;
     }
 #undef DTSDF_CASE
+}
+
+cudaError_t launch_voxelize_aug(int voxel_res, int layout, BatchArgs args, const float* aug, int max_crop_px,
+                                cudaStream_t stream) {
+    if (args.n_frames <= 0) return cudaSuccess;
+    switch (voxel_res) {
+        case 32: return layout == 0 ? launch_aug_t<32, 0>(args, aug, max_crop_px, stream) : launch_aug_t<32, 1>(args, aug, max_crop_px, stream);
+#ifndef DTSDF_EXP_ONLY32
+        case 48: return layout == 0 ? launch_aug_t<48, 0>(args, aug, max_crop_px, stream) : launch_aug_t<48, 1>(args, aug, max_crop_px, stream);
+        case 64: return layout == 0 ? launch_aug_t<64, 0>(args, aug, max_crop_px, stream) : launch_aug_t<64, 1>(args, aug, max_crop_px, stream);
+#endif
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_point_cloud(int n_frames, double focal, const float* depth,

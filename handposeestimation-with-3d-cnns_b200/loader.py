@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import capi
+from .augment import make_augmentations, voxelize_aug_device
 from .voxelizer import pack_frames, voxelize_device
 
 
@@ -44,12 +45,18 @@ class ResidentFrames:
     def __len__(self):
         return int(self.headers.shape[0])
 
-    def voxelize(self, index, cfg=None, joint_flags=capi.JOINT_CLAMP01, out=None, stream=None):
+    def voxelize(self, index, cfg=None, joint_flags=capi.JOINT_CLAMP01, out=None, stream=None, aug=None):
         """Volumes (and normalised joints) of the frames ``index`` (int64 tensor on the device), on
-        ``stream`` (default: the current one).  ``out`` = preallocated (vol, max_l, mid_p[, joints])."""
+        ``stream`` (default: the current one).  ``out`` = preallocated (vol, max_l, mid_p[, joints]).
+        ``aug`` float32[len(index),21] on the device: augmented volumes and joints (augment.py)."""
         hdr = self.headers.index_select(0, index)
         off = self.offsets.index_select(0, index)
         o = out or (None, None, None, None)
+        if aug is not None:
+            j = self.joints.index_select(0, index) if self.joints is not None else None
+            return voxelize_aug_device(self.packed, off, hdr, aug, self.max_crop_px, cfg, out_vol=o[0], out_max_l=o[1],
+                                       out_mid_p=o[2], stream=stream, joints=j, joint_flags=joint_flags,
+                                       out_joints=o[3] if (j is not None and len(o) > 3) else None)
         if self.joints is not None:
             return voxelize_device(self.packed, off, hdr, self.max_crop_px, cfg, out_vol=o[0], out_max_l=o[1],
                                    out_mid_p=o[2], stream=stream, joints=self.joints.index_select(0, index),
@@ -63,7 +70,9 @@ class OnTheFlyLoader:
     iteration after the next one (two buffers).  ``joints_nor`` is None without ground truth."""
 
     def __init__(self, frames, batch_size=16, shuffle=False, seed=0, voxel_res=32, layout=capi.LAYOUT_CXYZ,
-                 joint_flags=capi.JOINT_CLAMP01, drop_last=False):
+                 joint_flags=capi.JOINT_CLAMP01, drop_last=False, augment=False, augment_center=None):
+        """``augment=True``: every batch gets fresh random stretch + rotation (augment.make_augmentations,
+        the reference's parameter ranges) about ``augment_center`` (3 floats, default the origin)."""
         self.frames = frames
         self.batch_size = int(batch_size)
         self.shuffle = shuffle
@@ -72,6 +81,10 @@ class OnTheFlyLoader:
         self.cfg = capi.default_config(voxel_res, layout, capi.BBOX_PIXELS)
         self.joint_flags = int(joint_flags)
         self.drop_last = drop_last
+        self.augment = bool(augment)
+        self.augment_center = None if augment_center is None else np.asarray(augment_center, np.float32).reshape(1, 3)
+        self._aug_rng = np.random.default_rng(self.seed + 7919)
+        self.last_aug = [None, None]
         R, B, dev = int(voxel_res), self.batch_size, frames.device
         self._bufs = []
         for _ in range(2):
@@ -109,11 +122,18 @@ class OnTheFlyLoader:
             slot = k % 2
             idx = order[k * B:(k + 1) * B]
             m = int(idx.numel())
+            aug = None
+            if self.augment:
+                centers = None if self.augment_center is None else np.repeat(self.augment_center, m, axis=0)
+                aug_h = make_augmentations(m, self._aug_rng, centers=centers)
+                self.last_aug[slot] = aug_h
             with torch.cuda.stream(side):
                 side.wait_event(consumed[slot])      # the consumer is done with this buffer
+                if self.augment:
+                    aug = torch.from_numpy(aug_h).to(fr.device, non_blocking=True)
                 buf = self._bufs[slot]
                 out = tuple(t[:m] for t in buf)
-                fr.voxelize(idx, self.cfg, self.joint_flags, out=out, stream=side)
+                fr.voxelize(idx, self.cfg, self.joint_flags, out=out, stream=side, aug=aug)
                 ready[slot].record(side)
             return m
 

@@ -152,6 +152,24 @@ int dtsdf_voxelize_joints_batch(const dtsdf_config* cfg, int32_t n_frames,
                                 float* d_out_vol, float* d_out_max_l, float* d_out_mid_p,
                                 float* d_out_joints, void* stream);
 
+/* Augmented D-TSDF for training-time augmentation.  Every frame gets its
+ * own affine map p' = (p - c) . A + c (row vector times matrix, A = stretch . rotation as in
+ * show/visualize.py:106-114): the grid is laid over the AUGMENTED hand, voxel centres are taken back
+ * to the camera frame with Ainv, projected and looked up as usual, distances are measured in the
+ * augmented frame.  There is no reference behaviour to reproduce (data_aug raises AxisError,
+ * pre/process.py:252; cut_version voxelises the un-augmented depth, cut_version/pre/process.py:207):
+ * the specification is oracle/dtsdf_oracle.c:oracle_dtsdf_aug_frame, matched bit for bit.
+ *   d_aug         float[n][21] = A[3][3], Ainv[3][3], c[3]
+ *   d_joints / joint_flags / d_out_joints   optional: the ground truth mapped by the same
+ *                 augmentation and normalised, (T(gt) - mid_p)/max_l + 0.5
+ * cfg->bbox_mode is ignored (the box is over the augmented valid pixels). */
+int dtsdf_voxelize_aug_batch(const dtsdf_config* cfg, int32_t n_frames,
+                             const float* d_depth_packed, const int64_t* d_crop_offsets,
+                             const int32_t* d_headers, const float* d_aug, int32_t max_crop_px,
+                             const float* d_joints, int32_t joint_flags,
+                             float* d_out_vol, float* d_out_max_l, float* d_out_mid_p,
+                             float* d_out_joints, void* stream);
+
 /* Back-projection of every pixel with d != 0 to a float64 point, compacted in
  * row-major order.  Replaces DataProcess.point_cloud (pre/process.py:30-68).
  *   focal           the Python float 241.42 as a double (the reference divides float64

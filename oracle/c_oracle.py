@@ -37,6 +37,8 @@ def lib():
         l.oracle_tsdf_cal.restype = None
         l.oracle_dtsdf_batch.argtypes = [i32, vp, vp, vp, i32, i32, i32, vp, f32, f32, i32, i32, vp, vp, vp, i32]
         l.oracle_dtsdf_batch.restype = i32
+        l.oracle_dtsdf_aug_batch.argtypes = [i32, vp, vp, vp, vp, i32, i32, f32, f32, i32, i32, vp, vp, vp]
+        l.oracle_dtsdf_aug_batch.restype = i32
         _lib = l
     return _lib
 
@@ -59,3 +61,20 @@ def dtsdf_batch(headers, offsets, packed, R=32, layout=0, bbox_mode=0, aux=None,
                                     bbox_mode, aux_p, trunc_mul, focal, cx, cy, vol.ctypes.data,
                                     max_l.ctypes.data, mid_p.ctypes.data, nthreads)
     return vol, max_l, mid_p, used
+
+
+def dtsdf_aug_batch(headers, offsets, packed, aug, R=32, layout=0, trunc_mul=3.0, focal=241.42, cx=160, cy=120):
+    """Augmented D-TSDF (the specification in dtsdf_oracle.c; parity unpinned).
+    aug float32[n,21] = A (3x3), Ainv (3x3), c (3).  Returns (vol, max_l, mid_p)."""
+    headers = np.ascontiguousarray(headers, dtype=np.int32).reshape(-1, 6)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    packed = np.ascontiguousarray(packed, dtype=np.float32)
+    aug = np.ascontiguousarray(aug, dtype=np.float32).reshape(-1, 21)
+    n = headers.shape[0]
+    vol = np.empty((n, 3, R, R, R), dtype=np.float32)
+    max_l = np.zeros(n, dtype=np.float32)
+    mid_p = np.zeros((n, 3), dtype=np.float32)
+    lib().oracle_dtsdf_aug_batch(n, headers.ctypes.data, packed.ctypes.data, offsets.ctypes.data, aug.ctypes.data,
+                                 R, layout, trunc_mul, focal, cx, cy, vol.ctypes.data, max_l.ctypes.data,
+                                 mid_p.ctypes.data)
+    return vol, max_l, mid_p

@@ -162,3 +162,111 @@ int oracle_dtsdf_batch(int n_frames, const int32_t* headers, const float* packed
     }
     return used;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Augmented D-TSDF.  PARITY UNPINNED: the reference's data_aug raises
+ * AxisError (pre/process.py:252) and the cut_version variant voxelises the un-augmented depth map
+ * (cut_version/pre/process.py:207), so there is no reference behaviour to pin to.  This function IS
+ * the specification the CUDA kernel (dtsdf_voxelize_aug_batch) is checked against, bit for bit:
+ *
+ *   p' = T(p; A, c) = (p - c) . A + c     row vector times matrix, as show/visualize.py:106-114
+ *                                          (A = S . R: stretch then rotation), about the centre c
+ *   each component: t = dx*A[0][k]; t = fmaf(dy, A[1][k], t); t = fmaf(dz, A[2][k], t); q_k = t + c_k
+ *
+ *   1. bounding box over the AUGMENTED points of all valid pixels (|d| >= 1; back-projection as
+ *      pre/tsdf_numba.py:91-96), sentinels as pre/tsdf_numba.py:88-89;
+ *   2. grid parameters from it, pre/process.py:91-96;
+ *   3. per voxel centre v' of that grid (augmented space): v = T(v'; Ainv, c) back in the camera
+ *      frame; project v (pre/process.py:155-157), look the depth up (:159-167), back-project the
+ *      pixel to the surface point w (:172-175), augment it: w' = T(w; A, c); per-axis distances
+ *      |v'_k - w'_k| / trunc, Euclidean truncation and min(t,1) (:177-189); negative behind the
+ *      surface as seen from the camera: w_z > v_z (:191-194, in the camera frame).
+ * With A = Ainv = identity and any finite c the result equals oracle_dtsdf_batch with bbox_mode 0
+ * whenever (p - c) + c == p exactly, in particular for c = 0.
+ * aug[f] = { A[3][3], Ainv[3][3], c[3] } (21 floats, row-major matrices).
+ */
+static inline void xform(const float* p, const float* M, const float* c, float* q) {
+    const float dx = p[0] - c[0], dy = p[1] - c[1], dz = p[2] - c[2];
+    for (int k = 0; k < 3; ++k) {
+        float t = dx * M[k];
+        t = fmaf(dy, M[3 + k], t);
+        t = fmaf(dz, M[6 + k], t);
+        q[k] = t + c[k];
+    }
+}
+
+void oracle_dtsdf_aug_frame(const int32_t* header, const float* depth, const float* aug, int R, int layout,
+                            float trunc_mul, float focal, int cx, int cy, float* out, float* max_l_out,
+                            float* mid_out) {
+    const float *A = aug, *Ainv = aug + 9, *c = aug + 18;
+    const int l = header[2], t = header[3], r = header[4], b = header[5];
+    const int bw = r - l, bh = b - t;
+    const long ch = (long)R * R * R;
+    memset(out, 0, sizeof(float) * 3 * ch);
+    float mn[3] = {SENTINEL, SENTINEL, SENTINEL}, mx[3] = {-SENTINEL, -SENTINEL, -SENTINEL};
+    const long n = (bw > 0 && bh > 0) ? (long)bw * bh : 0;
+    for (long pos = 0; pos < n; ++pos) {
+        const float d = depth[pos];
+        if (fabsf(d) < 1.0f) continue;
+        const int x = (int)(pos % bw) + l, y = (int)(pos / bw) + t;
+        const float q = d / focal;
+        const float p[3] = {q * (float)(x - cx), -q * (float)(y - cy), -d};
+        float pa[3];
+        xform(p, A, c, pa);
+        for (int k = 0; k < 3; ++k) {
+            if (pa[k] < mn[k]) mn[k] = pa[k];
+            if (pa[k] > mx[k]) mx[k] = pa[k];
+        }
+    }
+    float vox_ori[3], voxel_len, trunc, ml, mid[3];
+    oracle_grid_params(mx, mn, R, trunc_mul, vox_ori, &voxel_len, &trunc, &ml, mid);
+    if (max_l_out) *max_l_out = ml;
+    if (mid_out) { mid_out[0] = mid[0]; mid_out[1] = mid[1]; mid_out[2] = mid[2]; }
+    if (n == 0) return;
+    for (int x = 0; x < R; ++x)
+        for (int y = 0; y < R; ++y)
+            for (int z = 0; z < R; ++z) {
+                const float va[3] = {vox_ori[0] + (float)x * voxel_len, vox_ori[1] + (float)y * voxel_len,
+                                     vox_ori[2] + (float)z * voxel_len};
+                float v[3];
+                xform(va, Ainv, c, v);
+                const float coeff = -focal / v[2];
+                const float fpx = v[0] * coeff + (float)cx;
+                const float fpy = -v[1] * coeff + (float)cy;
+                if (!(fabsf(fpx) < 2e9f) || !(fabsf(fpy) < 2e9f)) continue;
+                const int px = (int)fpx, py = (int)fpy;
+                if (px < l || px >= r || py < t || py >= b) continue;
+                const float d = depth[(long)(py - t) * bw + px - l];
+                if (fabsf(d) < 1.0f) continue;
+                const float c1 = d / focal;
+                const float w[3] = {(float)(px - cx) * c1, (float)(-(py - cy)) * c1, -d};
+                float wa[3];
+                xform(w, A, c, wa);
+                float tx = fabsf(va[0] - wa[0]) / trunc;
+                float ty = fabsf(va[1] - wa[1]) / trunc;
+                float tz = fabsf(va[2] - wa[2]) / trunc;
+                const float dis = sqrtf(tx * tx + ty * ty + tz * tz);
+                if (dis > 1.0f) { tx = 1.0f; ty = 1.0f; tz = 1.0f; }
+                if (1.0f < tx) tx = 1.0f;
+                if (1.0f < ty) ty = 1.0f;
+                if (1.0f < tz) tz = 1.0f;
+                if (w[2] > v[2]) { tx = -tx; ty = -ty; tz = -tz; }
+                const long o = layout == 0 ? ((long)x * R + y) * R + z : ((long)z * R + y) * R + x;
+                out[o] = tx;
+                out[ch + o] = ty;
+                out[2 * ch + o] = tz;
+            }
+}
+
+int oracle_dtsdf_aug_batch(int n_frames, const int32_t* headers, const float* packed, const int64_t* offsets,
+                           const float* aug, int R, int layout, float trunc_mul, float focal, int cx, int cy,
+                           float* vol, float* max_l, float* mid_p) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int f = 0; f < n_frames; ++f)
+        oracle_dtsdf_aug_frame(headers + 6 * (long)f, packed + offsets[f], aug + 21 * (long)f, R, layout, trunc_mul,
+                               focal, cx, cy, vol + (long)f * 3 * R * R * R, max_l ? max_l + f : 0,
+                               mid_p ? mid_p + 3 * (long)f : 0);
+    return 0;
+}

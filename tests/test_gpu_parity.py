@@ -391,3 +391,74 @@ def test_on_the_fly_loader_overlapped_batches(vox):
             assert np.array_equal(max_l.cpu().numpy(), want_ml[idx]) and np.array_equal(mid_p.cpu().numpy(), want_mp[idx])
             seen += m
         assert seen == len(frames) and float(acc) > 0
+
+
+# ----------------------------------------------------------------------------- augmentation (N2)
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("R", [32, 48])
+def test_augmented_dtsdf_matches_its_specification(R, layout):
+    """dtsdf_voxelize_aug_batch vs oracle/dtsdf_oracle.c:oracle_dtsdf_aug_frame (the specification;
+    parity with the reference is unpinned: its data_aug raises, pre/process.py:252), bit for bit, on
+    random stretch + rotation about the origin and about a point inside the hand."""
+    import importlib
+    import torch
+    amod = importlib.import_module(pkg.__name__ + ".augment")
+    frames = synth.make_frames(range(800, 824)) + [synth.make_frame(1, box=(0, 0, 320, 240))]   # last: unstaged
+    headers, offsets, packed = pack_simple(frames)
+    n = len(frames)
+    centers = np.zeros((n, 3), np.float32)
+    centers[n // 2:] = [5.0, -12.0, -370.0]
+    aug = amod.make_augmentations(n, np.random.default_rng(R + layout), centers=centers)
+    dev = torch.device("cuda:0")
+    cfg = pkg.capi.default_config(R, layout, pkg.BBOX_PIXELS)
+    vol, ml, mp = amod.voxelize_aug_device(torch.from_numpy(packed).to(dev), torch.from_numpy(offsets).to(dev),
+                                           torch.from_numpy(headers).to(dev), torch.from_numpy(aug).to(dev), 130 * 150, cfg)
+    torch.cuda.synchronize()
+    cv, cml, cmp_ = c_oracle.dtsdf_aug_batch(headers, offsets, packed, aug, R=R, layout=layout)
+    assert np.array_equal(ml.cpu().numpy(), cml) and np.array_equal(mp.cpu().numpy(), cmp_)
+    got = vol.cpu().numpy()
+    for i in range(n):
+        assert _same(got[i], cv[i]), "frame %d" % i
+    assert 0.02 < float(np.mean((got != 0) & (np.abs(got) < 1))) < 0.5       # a real surface band is in there
+
+
+def test_identity_augmentation_is_the_plain_path(vox):
+    import importlib
+    import torch
+    amod = importlib.import_module(pkg.__name__ + ".augment")
+    frames = synth.make_frames(range(900, 916))
+    headers, offsets, packed, max_px = pkg.pack_frames(frames)
+    dev = torch.device("cuda:0")
+    gt = np.random.default_rng(2).uniform(-150, 150, size=(len(frames), 63)).astype(np.float32)
+    args = (torch.from_numpy(packed).to(dev), torch.from_numpy(offsets).to(dev), torch.from_numpy(headers).to(dev))
+    vol, ml, mp, jn = amod.voxelize_aug_device(*args, torch.from_numpy(amod.identity_augmentations(len(frames))).to(dev),
+                                               max_px, joints=torch.from_numpy(gt).to(dev),
+                                               joint_flags=pkg.capi.JOINT_CLAMP01)
+    want = pkg.voxelize_device(*args, max_px, joints=torch.from_numpy(gt).to(dev), joint_flags=pkg.capi.JOINT_CLAMP01)
+    torch.cuda.synchronize()
+    assert _same(vol.cpu().numpy(), want[0].cpu().numpy())
+    assert torch.equal(ml, want[1]) and torch.equal(mp, want[2]) and torch.equal(jn, want[3])
+
+
+def test_on_the_fly_loader_with_augmentation():
+    """BASELINE.json configs[4]: on-the-fly D-TSDF + 3-D augmentation on a side stream; every batch equals
+    the augmentation specification for the matrices the loader drew."""
+    import importlib
+    lmod = importlib.import_module(pkg.__name__ + ".loader")
+    frames = synth.make_frames(range(950, 950 + 20))
+    headers, offsets, packed = pack_simple(frames)
+    gt = np.random.default_rng(4).uniform(-100, 100, size=(len(frames), 63)).astype(np.float32)
+    res = lmod.ResidentFrames.from_frames(frames, joints=gt)
+    loader = lmod.OnTheFlyLoader(res, batch_size=8, shuffle=False, augment=True, augment_center=(0.0, 0.0, -380.0))
+    seen = 0
+    for k, (tsdf, jn, max_l, mid_p) in enumerate(loader):
+        m = tsdf.shape[0]
+        aug = loader.last_aug[k % 2]
+        sel = np.arange(seen, seen + m)
+        sub = [frames[i] for i in sel]
+        h, o, p = pack_simple(sub)
+        cv, cml, cmp_ = c_oracle.dtsdf_aug_batch(h, o, p, aug)
+        assert _same(tsdf.cpu().numpy(), cv) and np.array_equal(max_l.cpu().numpy(), cml)
+        assert jn.shape == (m, 63) and float(jn.min()) >= 0.0 and float(jn.max()) <= 1.0
+        seen += m
+    assert seen == len(frames)

@@ -48,3 +48,18 @@ def test_c_oracle_grid_mode(forloop_golden):
     aux = np.array([[vox_ori[0], vox_ori[1], vox_ori[2], voxel_len, trunc]], dtype=np.float32)
     vol, _, _, _ = c_oracle.dtsdf_batch(headers, offsets, packed, bbox_mode=2, aux=aux)
     assert np.array_equal(vol[0], c["tsdf"])
+
+
+def test_identity_augmentation_specification_reduces_to_the_reference_path():
+    """oracle_dtsdf_aug_frame (the specification of the augmented D-TSDF; parity with the reference
+    unpinned) with A = identity, c = 0 is the pinned pixel-bbox path, bit for bit."""
+    import helpers
+    frames = helpers.synth.make_frames(range(40, 44))
+    headers, offsets, packed = helpers.pack_simple(frames)
+    ident = np.zeros((len(frames), 21), np.float32)
+    ident[:, [0, 4, 8, 9, 13, 17]] = 1.0
+    for layout in (0, 1):
+        v, ml, mp = c_oracle.dtsdf_aug_batch(headers, offsets, packed, ident, layout=layout)
+        v0, ml0, mp0, _ = c_oracle.dtsdf_batch(headers, offsets, packed, layout=layout)
+        assert np.array_equal(v, v0) and np.array_equal(np.signbit(v), np.signbit(v0))
+        assert np.array_equal(ml, ml0) and np.array_equal(mp, mp0)

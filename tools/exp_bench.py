@@ -21,7 +21,10 @@ def run(names, frames=8500, steps=20):
     import numpy as np, torch
     import __graft_entry__ as g
     pkg = g.load_package()
-    headers, depth = pkg.synth.make_uniform_batch(frames, seed0=1234, box=(100, 60, 220, 190))
+    box = tuple(int(v) for v in os.environ.get("EXP_BOX", "100,60,220,190").split(","))
+    headers, depth = pkg.synth.make_uniform_batch(frames, seed0=1234, box=box)
+    bw, bh = box[2] - box[0], box[3] - box[1]
+    alg = frames * (24 + 4 * bw * bh + 12 * 32 ** 3 + 16)
     offsets, packed_len, max_px = pkg.capi.pack_plan(headers)
     dev = torch.device("cuda:0")
     d_packed = torch.from_numpy(depth.reshape(-1)).to(dev)
@@ -55,7 +58,7 @@ def run(names, frames=8500, steps=20):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        print("%-28s %.4f ms/launch  %.2f M volumes/s" % (name, ms, frames / ms / 1e3), flush=True)
+        print("%-28s %.4f ms/launch  %.2f M volumes/s  %.0f GB/s algorithmic (crop %dx%d)" % (name, ms, frames / ms / 1e3, alg / ms / 1e6, bw, bh), flush=True)
 
 
 if __name__ == "__main__":
