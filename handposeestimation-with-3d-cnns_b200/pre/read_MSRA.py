@@ -35,14 +35,39 @@ SAVE_dir = './result'
 AUG = False
 
 POINTS_NUM = 6000
+_TREE = ('Point_Cloud', 'TSDF', 'ground_truth', 'num')
 
 
-def _mkdir(path, what):
-    try:
-        os.mkdir(path)
-        print('create directory "%s".' % what)
-    except OSError:
-        print('directory "%s" already exist!' % what)
+def _ensure_dir(path, label=None):
+    """mkdir that reports like the reference does (pre/read_MSRA.py:39-59) but never hides other errors."""
+    if os.path.isdir(path):
+        if label:
+            print('directory "%s" already exist!' % label)
+        return
+    os.makedirs(path)
+    if label:
+        print('create directory "%s".' % label)
+
+
+def _load_gesture(folder):
+    """All frame records of one gesture folder plus its ground truth."""
+    count, joints = read_joint(folder)
+    records = []
+    for k in range(count):
+        hdr, crop = read_bin(os.path.join(folder, '%06d_depth.bin' % k))
+        records.append({'header': hdr, 'depth': crop})
+    return count, joints, records
+
+
+def _store_gesture(out_dir, ges, count, joints, clouds, volumes, sides, centres):
+    """The four files of a gesture (pre/read_MSRA.py:119-126).  The reference accumulates into float64
+    arrays (np.empty default dtype, :93-96), so that is what goes to disk."""
+    f64 = np.float64
+    np.save(os.path.join(out_dir, _TREE[0], ges + '.npy'), clouds)
+    np.savez(os.path.join(out_dir, _TREE[1], ges + '.npz'), tsdf=volumes.astype(f64), max_l=sides.astype(f64),
+             mid_p=centres.astype(f64))
+    np.save(os.path.join(out_dir, _TREE[2], ges + '.npy'), joints)
+    np.save(os.path.join(out_dir, _TREE[3], ges + '.npy'), count)
 
 
 def main():
@@ -51,60 +76,43 @@ def main():
         raise NotImplementedError(
             "AUG = True: the reference's data_aug raises AxisError (pre/process.py:252); "
             "augmentation is specified separately (SURVEY.md section 8f, N2)")
-    _mkdir(SAVE_dir, "result")
-    vox = _pkg.default_voxelizer()
-    # there are 9 subjects and 17 gestures in each subject
-    subject = sorted(os.listdir(DB_dir))
-    gesture = sorted(os.listdir(os.path.join(DB_dir, subject[0])))
-    for sub in subject:
-        sub_dir = os.path.join(SAVE_dir, sub)
-        _mkdir(sub_dir, sub)
-        for name in ('Point_Cloud', 'TSDF', 'ground_truth', 'num'):
-            try:
-                os.mkdir(os.path.join(sub_dir, name))
-            except OSError:
-                pass
-
-        total_num = 0
-        for ges in gesture:
-            file_dir = os.path.join(DB_dir, sub, ges)
-            bin_num, ground_truth = read_joint(file_dir)
-            total_num += bin_num
-
-            frames = []
-            for i in range(bin_num):
-                header, depth = read_bin(os.path.join(file_dir, '%06d_depth.bin' % i))
-                frames.append({'header': header, 'depth': depth})
-            pcs, tsdf, max_l, mid_p = vox.process_frames(frames, POINTS_NUM)
-
-            # the reference fills float64 arrays (np.empty default dtype, pre/read_MSRA.py:93-96)
-            np.save(os.path.join(sub_dir, 'Point_Cloud', '%s.npy' % ges), pcs)
-            np.savez(os.path.join(sub_dir, 'TSDF', '%s.npz' % ges),
-                     tsdf=tsdf.astype(np.float64), max_l=max_l.astype(np.float64),
-                     mid_p=mid_p.astype(np.float64))
-            np.save(os.path.join(sub_dir, 'ground_truth', '%s.npy' % ges), ground_truth)
-            np.save(os.path.join(sub_dir, 'num', '%s.npy' % ges), bin_num)
-            print('%s-%s files saved.' % (sub, ges))
-        np.save(os.path.join(SAVE_dir, 'data_num-%s.npy' % sub), total_num)
-        print('%s total number saved.' % sub)
+    _ensure_dir(SAVE_dir, "result")
+    engine = _pkg.default_voxelizer()
+    people = sorted(os.listdir(DB_dir))                      # 9 subjects ...
+    poses = sorted(os.listdir(os.path.join(DB_dir, people[0])))   # ... x 17 gestures in the full data base
+    for who in people:
+        out_dir = os.path.join(SAVE_dir, who)
+        _ensure_dir(out_dir, who)
+        for name in _TREE:
+            _ensure_dir(os.path.join(out_dir, name))
+        frames_of_subject = 0
+        for ges in poses:
+            count, joints, records = _load_gesture(os.path.join(DB_dir, who, ges))
+            frames_of_subject += count
+            # one batched call per gesture instead of DataProcess(...).process() per file (:98-111)
+            clouds, volumes, sides, centres = engine.process_frames(records, POINTS_NUM)
+            _store_gesture(out_dir, ges, count, joints, clouds, volumes, sides, centres)
+            print('%s-%s files saved.' % (who, ges))
+        np.save(os.path.join(SAVE_dir, 'data_num-%s.npy' % who), frames_of_subject)
+        print('%s total number saved.' % who)
 
 
 def read_joint(f_dir):
-    "read the joint files and return the ground truth"
-    # first line: number of bin files; the rest: 63 ground-truth values per frame
-    f_name = os.path.join(f_dir, 'joint.txt')
-    with open(f_name, 'r') as f:
-        bin_num = int(f.readline())
-    ground_truth = np.loadtxt(f_name, dtype=np.float32, skiprows=1)
-    return bin_num, ground_truth
+    """joint.txt of a gesture folder: first line = number of .bin files, then 63 ground-truth values
+    per frame.  Returns (bin_num, float32[bin_num,63])."""
+    path = os.path.join(f_dir, 'joint.txt')
+    with open(path) as fh:
+        bin_num = int(fh.readline().strip())
+    return bin_num, np.loadtxt(path, dtype=np.float32, skiprows=1)
 
 
 def read_bin(f_name):
-    "read one bin file: 6 x int32 header, then the float32 depth crop to the end of the file"
-    with open(f_name, 'rb') as f:
-        header = np.fromfile(f, dtype=np.int32, count=6)
-        depth = np.fromfile(f, dtype=np.float32)
-    return header, depth
+    """One MSRA depth file: int32[6] = img_w, img_h, left, top, right, bottom, then the float32 crop to
+    the end of the file.  Returns (header, depth)."""
+    raw = np.fromfile(f_name, dtype=np.uint8)
+    head = raw[:24 - (min(raw.size, 24) % 4) if raw.size < 24 else 24]
+    body = raw[24:24 + 4 * ((max(raw.size, 24) - 24) // 4)]          # whole floats only, like np.fromfile
+    return head[:4 * (head.size // 4)].view(np.int32).copy(), body.view(np.float32).copy()
 
 
 if __name__ == '__main__':
