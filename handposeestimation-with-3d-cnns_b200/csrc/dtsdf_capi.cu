@@ -278,7 +278,7 @@ int dtsdf_device_count(void) {
     return n;
 }
 
-int64_t dtsdf_launch_count(void) { return dtsdf::g_launch_count; }
+int64_t dtsdf_launch_count(void) { return dtsdf::g_launch_count.load(); }
 
 int dtsdf_enable_peer_access(int32_t device, int32_t peer_device) {
     int n = 0;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace dtsdf {
 
 // Arguments of the fused voxeliser, passed by value to the kernel.
@@ -65,6 +67,6 @@ cudaError_t launch_pack_push(int n_frames, const float* lits, const unsigned lon
                              float* host_lits, cudaStream_t stream);
 
 // kernels launched by this process (claimed in bench.py's gpu_launches)
-extern long long g_launch_count;
+extern std::atomic<long long> g_launch_count;
 
 }  // namespace dtsdf

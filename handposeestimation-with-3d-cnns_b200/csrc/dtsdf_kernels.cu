@@ -61,9 +61,11 @@
 #include <stddef.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 namespace dtsdf {
 
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 
 namespace {
 
