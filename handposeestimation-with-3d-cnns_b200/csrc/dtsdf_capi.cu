@@ -520,7 +520,8 @@ int dtsdf_ctx_create(int32_t device, dtsdf_ctx** out) {
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
     for (int i = 0; i < dtsdf_ctx::NSLOT && err == cudaSuccess; ++i) {
         err = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming);
-        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_run[i], cudaEventDisableTiming);
+        // the host waits on ev_run while its cores expand packed volumes: sleep, do not spin
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_run[i], cudaEventDisableTiming | cudaEventBlockingSync);
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming);
     }
     if (err != cudaSuccess) {
@@ -638,7 +639,10 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
     c->stat_d2h_bytes = packed ? 0 : (int64_t)n_frames * (int64_t)(vol_floats * 4 + (h_maxl ? 4 : 0) + (h_mid ? 12 : 0));
     int nthreads = 1;
     if (packed) {
-        nthreads = c->opt_threads > 0 ? c->opt_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+        // default: three quarters of the hardware threads (the expansion is memory-bound well before
+        // all cores are busy, and the calling thread and the CUDA driver need some too)
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        nthreads = c->opt_threads > 0 ? c->opt_threads : (int)std::min(32u, std::max(1u, hw - hw / 4));
         c->pool.ensure(nthreads);
     }
     struct Pending { int slot; int32_t f0, nf; };

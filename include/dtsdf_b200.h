@@ -218,8 +218,8 @@ void dtsdf_ctx_destroy(dtsdf_ctx* ctx);
  *                          GPU straight into mapped pinned memory, and expands them into the
  *                          caller's buffer with the host threads below (streaming stores).
  *                          0: plain device->host copies of the float volumes.
- *   DTSDF_OPT_HOST_THREADS number of host threads for the expansion (default: all hardware
- *                          threads, at most 32). */
+ *   DTSDF_OPT_HOST_THREADS number of host threads for the expansion (default 0 = three quarters of
+ *                          the hardware threads, at most 32). */
 #define DTSDF_OPT_PACKED_D2H   1
 #define DTSDF_OPT_HOST_THREADS 2
 #define DTSDF_OPT_CHUNK_MB     3   /* output megabytes per pipeline chunk of dtsdf_voxelize_host (default 64) */

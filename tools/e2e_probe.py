@@ -23,7 +23,6 @@ def run(label):
     print("%-24s %.1f ms  %.0f volumes/s" % (label, dt * 1e3, F / dt), flush=True)
 vox.set_option(capi.OPT_PACKED_D2H, 0); run("plain")
 vox.set_option(capi.OPT_PACKED_D2H, 1)
-for nt in (8, 12, 16):
-    for mb in (32, 64, 128, 256):
-        vox.set_option(capi.OPT_HOST_THREADS, nt); vox.set_option(capi.OPT_CHUNK_MB, mb)
-        run("packed, %d threads, %d MB" % (nt, mb))
+for nt in (12, 14, 15, 16):
+    vox.set_option(capi.OPT_HOST_THREADS, nt)
+    run("packed, %d threads" % nt)
