@@ -462,3 +462,63 @@ def test_on_the_fly_loader_with_augmentation():
         assert jn.shape == (m, 63) and float(jn.min()) >= 0.0 and float(jn.max()) <= 1.0
         seen += m
     assert seen == len(frames)
+
+
+# ----------------------------------------------------------------------------- randomised stress
+def _random_frames(rng, n):
+    """Frames that look nothing like a hand: random boxes anywhere in (and partly outside) the image,
+    depth fields mixing planes, noise, holes, values straddling the |d| = 1 validity threshold and
+    negative depths."""
+    frames = []
+    for _ in range(n):
+        bw, bh = int(rng.integers(1, 180)), int(rng.integers(1, 160))
+        l, t = int(rng.integers(-20, 300)), int(rng.integers(-20, 220))
+        yy, xx = np.mgrid[0:bh, 0:bw].astype(np.float32)
+        kind = int(rng.integers(0, 5))
+        base = np.float32(rng.uniform(150, 900))
+        if kind == 0:
+            d = base + rng.uniform(-2, 2) * xx + rng.uniform(-2, 2) * yy
+        elif kind == 1:
+            d = base + rng.normal(0, 40, size=(bh, bw))
+        elif kind == 2:
+            d = rng.uniform(0.0, 2.0, size=(bh, bw))                       # straddles |d| < 1
+        elif kind == 3:
+            d = -(base + 30 * np.sin(xx / 7.0) * np.cos(yy / 5.0))         # negative depths are valid
+        else:
+            d = base + 80 * ((xx // 8 + yy // 8) % 2)                      # steps
+        d = d.astype(np.float32)
+        d[rng.random((bh, bw)) < rng.uniform(0, 0.7)] = 0.0                # holes
+        frames.append({"header": np.array([320, 240, l, t, l + bw, t + bh], np.int32), "depth": d.reshape(-1)})
+    return frames
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_randomised_frames_all_bbox_modes(vox, seed):
+    rng = np.random.default_rng(seed)
+    frames = _random_frames(rng, 300)
+    headers, offsets, packed = pack_simple(frames)
+    n = len(frames)
+    for layout in (0, 1):
+        # bbox over valid pixels
+        vol, ml, mp = vox.voxelize_packed(headers, offsets, packed, layout=layout)
+        cv, cml, cmp_, _ = c_oracle.dtsdf_batch(headers, offsets, packed, layout=layout)
+        for i in range(n):
+            assert _same(vol[i], cv[i]), "pixels frame %d layout %d" % (i, layout)
+        assert _same(ml, cml) and _same(mp, cmp_)
+        # caller-supplied extrema: random boxes around a random point, from tiny to huge
+        centre = rng.uniform(-300, 300, size=(n, 3)).astype(np.float32)
+        centre[:, 2] = -rng.uniform(100, 1000, size=n).astype(np.float32)
+        half = (10.0 ** rng.uniform(-3, 3.5, size=(n, 3))).astype(np.float32)
+        aux = np.concatenate([centre + half, centre - half], axis=1).astype(np.float32)
+        vol, ml, mp = vox.voxelize_packed(headers, offsets, packed, layout=layout, bbox_mode=pkg.BBOX_EXTREMA, aux=aux)
+        cv, cml, cmp_, _ = c_oracle.dtsdf_batch(headers, offsets, packed, layout=layout, bbox_mode=1, aux=aux)
+        for i in range(n):
+            assert _same(vol[i], cv[i]), "extrema frame %d layout %d" % (i, layout)
+        assert _same(ml, cml) and _same(mp, cmp_)
+        # caller-supplied grid: voxel_len from 1e-4 to 1e3 mm, trunc not tied to it
+        grid = np.concatenate([centre - half, (10.0 ** rng.uniform(-4, 3, size=(n, 1))),
+                               (10.0 ** rng.uniform(-3, 3, size=(n, 1)))], axis=1).astype(np.float32)
+        vol, _, _ = vox.voxelize_packed(headers, offsets, packed, layout=layout, bbox_mode=pkg.BBOX_GRID, aux=grid)
+        cv, _, _, _ = c_oracle.dtsdf_batch(headers, offsets, packed, layout=layout, bbox_mode=2, aux=grid)
+        for i in range(n):
+            assert _same(vol[i], cv[i]), "grid frame %d layout %d" % (i, layout)
