@@ -50,8 +50,8 @@
 // are evaluated as q = a*y, then one or two residual corrections q += fma(-b,q,a)*y
 // with y = rcp_rn(b) (Markstein).  With a correctly rounded reciprocal and a faithful
 // q the last correction is the correctly rounded quotient; for the default focal
-// 241.42f the one-correction form was checked exhaustively over all dividends
-// (tests/test_division.py).  Frames or pixels outside the proven exponent ranges
+// 241.42f the one-correction form was checked exhaustively over every dividend with a
+// biased exponent of 120..175 (the kernel uses 127..166; tests/test_division.py).  Frames or pixels outside the proven exponent ranges
 // take the generic IEEE path (__fdiv_rn).  Results are bit-identical either way.
 // The path is a streaming, write-dominated map with a small gather: HBM-bound, no
 // tensor cores (there is no contraction to feed them).
