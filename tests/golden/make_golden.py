@@ -117,7 +117,8 @@ def numba_sim_golden():
         return _Py2Int(orig_grid(self, n))
 
     out = {}
-    mm_cases = [(10, (140, 100, 180, 136)), (11, (150, 90, 197, 131))]   # 40x36, 47x41 (ragged tail)
+    mm_cases = [(10, (140, 100, 180, 136)), (11, (150, 90, 197, 131)),   # 40x36, 47x41 (ragged tail)
+                (12, (96, 70, 160, 125))]                               # 64x55, off-centre
     for k, (seed, box) in enumerate(mm_cases):
         frame = synth.make_frame(seed, box=box, key="data")
         l, t, r, b = (int(v) for v in frame["header"][2:6])
@@ -151,7 +152,7 @@ def numba_sim_golden():
         out[p + "trunc"] = np.float32(trunc_dis)
         out[p + "vox_ori"] = vox_ori
         print("min_max case", k, min_p, max_p, type(voxel_len), vox_ori.dtype)
-        if k == 0:
+        if True:     # every case also goes through tsdf_kernel (about 12 s each in the simulator)
             tsdf = np.zeros([3, 32, 32, 32], dtype=np.float32)
             tsdf_numba.tsdf_kernel[[32, 32], tsdf_numba.threadsperblock](
                 vox_ori, voxel_len, l, r, t, b, trunc_dis, frame["data"], tsdf)
