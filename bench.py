@@ -47,8 +47,11 @@ def algorithmic_bytes(headers, R):
 
 def workload_config(args, world):
     return {
-        "workload": "configs[1]: %d synthetic MSRA-shaped frames per GPU, crop %dx%d, R=%d -> 3x%d^3 f32"
-                    % (args.frames, BOX[2] - BOX[0], BOX[3] - BOX[1], args.res, args.res),
+        "workload": "%s: %d synthetic MSRA-shaped frames per GPU, crop %dx%d, R=%d -> 3x%d^3 f32"
+                    % ("configs[1]" if (args.frames == FRAMES_PER_GPU and args.res == 32) else
+                       ("configs[2] (full MSRA-sized set)" if args.frames * world >= 76000 else
+                        ("configs[3] (resolution sweep)" if args.res != 32 else "custom size")),
+                       args.frames, BOX[2] - BOX[0], BOX[3] - BOX[1], args.res, args.res),
         "frames_per_gpu": args.frames,
         "frames_total": args.frames * world,
         "voxel_res": args.res,
