@@ -13,12 +13,12 @@
 // with __fadd_rn/__fmul_rn/__fdiv_rn, which the compiler never contracts into FMAs.
 // The file is also compiled with -fmad=false.
 //
-// Design: ONE CTA (8 warps) PER FRAME, grid = number of frames.  The hardware block
+// Design: ONE CTA (16 or 8 warps, CtaShape) PER FRAME, grid = number of frames.  The hardware block
 // scheduler balances ragged batches, and - measured on B200 - CTAs that come and go keep the
 // HBM write stream 15-40 % faster than persistent CTAs marching in lock-step (a store-only
 // variant of this kernel: 0.46 ms one CTA per frame vs 0.73 ms persistent for 8,500 frames).
-// Three CTAs are resident per SM (76 KB of shared memory each for a 120x130 crop), so the
-// prologue of one frame hides behind the voxel loops of two others.
+// Two or three CTAs are resident per SM (76 KB of shared memory each for a 120x130 crop), so the
+// prologue of one frame hides behind the voxel loops of the others.
 //   0  thread 0: frame record, mbarrier init, ONE TMA bulk copy (cp.async.bulk) of the crop
 //      global -> shared memory
 //   1  bounding-box scan of the staged crop, one warp per crop row (LDS.128), which also
@@ -146,18 +146,18 @@ __device__ __forceinline__ float div_fixed(float a, float b, float y) {
 }
 
 // ---------------------------------------------------------------- shared memory
-template <int R, int LAYOUT>
+template <int R, int LAYOUT, int NW>
 struct __align__(16) FrameShared {
     static constexpr int YS = (LAYOUT == 0) ? R : R + 1;   // (c,z,y,x): yt rows are read down a column
     int   at[R * R];                // [s][f]: 4*(pix_x - left), OUTSIDE when not in the crop
     int   yt[R * YS];               // CXYZ [y][z], CZYX [z][y]: 4*bw*(pix_y - top), or OUTSIDE
     short yr[R * YS];               // same indexing: pix_y - top (pass 2 only)
     float vx[R], vy[R], vz[R];      // voxel centres per axis
-    float red[NWARP][8];            // per-warp partial min xyz / max xyz (6 used)
+    float red[NW][8];            // per-warp partial min xyz / max xyz (6 used)
     // per-warp work lists (groups with near-surface voxels): what one slow-axis row group can
     // add plus the remainder (< 32) carried over from the previous one
-    static constexpr int LIST_CAP = 32 + 32 * (R / NWARP);
-    unsigned short list[NWARP][LIST_CAP];
+    static constexpr int LIST_CAP = 32 + 32 * (R / NW);
+    unsigned short list[NW][LIST_CAP];
     unsigned long long bar;         // crop TMA completion barrier
     unsigned int nanflag;           // the staged crop holds a NaN: take the unstaged path
     unsigned int pad_;
@@ -220,7 +220,7 @@ __device__ __forceinline__ float div_focal(float d, float focal, float yf) {
     return EXACT ? __fdiv_rn(d, focal) : div_fixed<ONE>(d, focal, yf);
 }
 
-template <bool ONE, bool EXACT, bool VEC, bool SMEM>
+template <bool ONE, bool EXACT, bool VEC, bool SMEM, int NW>
 __device__ __forceinline__ void bbox_scan(const Frame& fr, float* crop, float focal, float yf, int cx, int cy,
                                           float (&mn)[3], float (&mx)[3], float2& nansum) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -282,14 +282,14 @@ __device__ __forceinline__ void bbox_scan(const Frame& fr, float* crop, float fo
             mx[1] = fmaxf(mx[1], has ? fmaxf(y1, y2) : qnan);
         };
         int row = warp;
-        for (; row + 3 * NWARP < fr.bh; row += 4 * NWARP) {
+        for (; row + 3 * NW < fr.bh; row += 4 * NW) {
             float d[4][4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) load_row(row + u * NWARP, d[u]);
+            for (int u = 0; u < 4; ++u) load_row(row + u * NW, d[u]);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) row_step(row + u * NWARP, d[u]);
+            for (int u = 0; u < 4; ++u) row_step(row + u * NW, d[u]);
         }
-        for (; row < fr.bh; row += NWARP) {
+        for (; row < fr.bh; row += NW) {
             float d[4];
             load_row(row, d);
             row_step(row, d);
@@ -311,7 +311,7 @@ __device__ __forceinline__ void bbox_scan(const Frame& fr, float* crop, float fo
 
 // scan + warp reduction; lane 0 leaves the warp's partial in shared memory.  Returns true if
 // this thread saw a NaN in the staged crop (SMEM only).
-template <bool ONE, bool EXACT, bool SMEM>
+template <bool ONE, bool EXACT, bool SMEM, int NW>
 __device__ __forceinline__ bool bbox_partial(const Frame& fr, float* crop, const BatchArgs& a, float yf,
                                              float (*red)[8]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -319,8 +319,8 @@ __device__ __forceinline__ bool bbox_partial(const Frame& fr, float* crop, const
     float2 nansum = make_float2(0.f, 0.f);
     mn[0] = mn[1] = mn[2] = SENTINEL;
     mx[0] = mx[1] = mx[2] = -SENTINEL;
-    if ((fr.bw & 3) == 0) bbox_scan<ONE, EXACT, true, SMEM>(fr, crop, a.focal, yf, a.center_x, a.center_y, mn, mx, nansum);
-    else                  bbox_scan<ONE, EXACT, false, SMEM>(fr, crop, a.focal, yf, a.center_x, a.center_y, mn, mx, nansum);
+    if ((fr.bw & 3) == 0) bbox_scan<ONE, EXACT, true, SMEM, NW>(fr, crop, a.focal, yf, a.center_x, a.center_y, mn, mx, nansum);
+    else                  bbox_scan<ONE, EXACT, false, SMEM, NW>(fr, crop, a.focal, yf, a.center_x, a.center_y, mn, mx, nansum);
 #pragma unroll
     for (int c = 0; c < 3; ++c) { mn[c] = warp_min(mn[c]); mx[c] = warp_max(mx[c]); }
     if (lane == 0) {
@@ -332,11 +332,12 @@ __device__ __forceinline__ bool bbox_partial(const Frame& fr, float* crop, const
 }
 
 // block reduction of the partials (every thread gets the result)
+template <int NW>
 __device__ __forceinline__ void bbox_reduce(const float (*red)[8], float (&mn)[3], float (&mx)[3]) {
     mn[0] = mn[1] = mn[2] = SENTINEL;
     mx[0] = mx[1] = mx[2] = -SENTINEL;
 #pragma unroll
-    for (int w = 0; w < NWARP; ++w) {
+    for (int w = 0; w < NW; ++w) {
         const float4 p = *reinterpret_cast<const float4*>(&red[w][0]);
         const float2 q = *reinterpret_cast<const float2*>(&red[w][4]);
         mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
@@ -346,13 +347,14 @@ __device__ __forceinline__ void bbox_reduce(const float (*red)[8], float (&mn)[3
 
 // "no depth" -> NaN over the staged crop, for the bounding-box modes that do not scan it.
 // Returns true if this thread saw a NaN of the crop's own.
+template <int NW>
 __device__ __forceinline__ bool sanitize_crop(float* crop_s, int n_pad) {
     float4* c4 = reinterpret_cast<float4*>(crop_s);
     const int n4 = n_pad >> 2;
     const float qnan = __int_as_float(QNAN_BITS);
     float2 nansum = make_float2(0.f, 0.f);
 #pragma unroll 4
-    for (int i = threadIdx.x; i < n4; i += NT) {
+    for (int i = threadIdx.x; i < n4; i += (32 * NW)) {
         float4 v = c4[i];
         nansum = __fadd2_rn(nansum, __fadd2_rn(make_float2(v.x, v.y), make_float2(v.z, v.w)));
         v.x = fabsf(v.x) < 1.0f ? qnan : v.x;
@@ -465,25 +467,25 @@ __device__ __forceinline__ void classify(float d, float vz, float t_far, float& 
 }
 
 // Lane geometry of the voxel loop for an R^3 grid
-template <int R>
+template <int R, int NW>
 struct LaneMap {
     static constexpr int LPR = R / 4;               // lanes per F-row (groups of 4 voxels)
     static constexpr int ROWS = 32 / LPR;           // slow-axis rows per warp
     static constexpr int ACTIVE = ROWS * LPR;       // 32 for R = 32, 64; 24 for R = 48
     static constexpr int NSG = R / ROWS;            // slow-axis row groups per frame
-    static constexpr int MSTEPS = R / NWARP;        // middle-axis positions per warp and row group
-    static_assert(R % 4 == 0 && R % ROWS == 0 && R % NWARP == 0, "unsupported grid size");
+    static constexpr int MSTEPS = R / NW;        // middle-axis positions per warp and row group
+    static_assert(R % 4 == 0 && R % ROWS == 0 && R % NW == 0, "unsupported grid size");
     static_assert(R <= 64 && NSG <= 32, "work-list entries are 5 + 6 + 5 bits");
 };
 
 // pass 2: full evaluation of the n (<= 32) listed groups list[0..n)
-template <int R, int LAYOUT, bool STAGED, bool FAST, bool DEFF>
+template <int R, int LAYOUT, int NW, bool STAGED, bool FAST, bool DEFF>
 __device__ __forceinline__ void eval_listed(const float* __restrict__ crop,
-                                            const FrameShared<R, LAYOUT>* __restrict__ sh, const VoxConst& k,
+                                            const FrameShared<R, LAYOUT, NW>* __restrict__ sh, const VoxConst& k,
                                             const BatchArgs& a, float yf, float* __restrict__ out,
                                             const unsigned short* list, int n) {
-    using LM = LaneMap<R>;
-    constexpr int YS = FrameShared<R, LAYOUT>::YS;
+    using LM = LaneMap<R, NW>;
+    constexpr int YS = FrameShared<R, LAYOUT, NW>::YS;
     constexpr int CH = R * R * R;
     const int lane = threadIdx.x & 31;
     if (lane < n) {
@@ -572,12 +574,12 @@ __device__ __forceinline__ void eval_listed(const float* __restrict__ crop,
 // middle-axis positions m = w, w + 8, ... of every slow-axis row group, so every warp sees every
 // part of the volume (balanced pass-2 work).  Pass 2 runs at the end of each row group on whole
 // batches of 32 listed groups; the remainder moves to the front of the list.
-template <int R, int LAYOUT, bool STAGED, bool FAST, bool DEFF>
+template <int R, int LAYOUT, int NW, bool STAGED, bool FAST, bool DEFF>
 __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
-                                             FrameShared<R, LAYOUT>* __restrict__ sh, const VoxConst& k,
+                                             FrameShared<R, LAYOUT, NW>* __restrict__ sh, const VoxConst& k,
                                              const BatchArgs& a, float yf, float* __restrict__ out) {
-    using LM = LaneMap<R>;
-    constexpr int YS = FrameShared<R, LAYOUT>::YS;
+    using LM = LaneMap<R, NW>;
+    constexpr int YS = FrameShared<R, LAYOUT, NW>::YS;
     constexpr int CH = R * R * R;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool active = lane < LM::ACTIVE;
@@ -604,7 +606,7 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
         const int ebase = (sg << 11) | lane;
 #pragma unroll
         for (int ks = 0; ks < LM::MSTEPS; ks += 2) {
-            const int m0 = warp + NWARP * ks, m1 = m0 + NWARP;
+            const int m0 = warp + NW * ks, m1 = m0 + NW;
             int4 B0, B1;
             if (LAYOUT == 0) {
                 B0 = *reinterpret_cast<const int4*>(&sh->yt[m0 * YS + f0]);
@@ -676,7 +678,7 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
             __syncwarp();                 // list entries and the pass-1 stores are ordered before pass 2
             int done = 0;
             do {
-                eval_listed<R, LAYOUT, STAGED, FAST, DEFF>(crop, sh, k, a, yf, out, list + done, 32);
+                eval_listed<R, LAYOUT, NW, STAGED, FAST, DEFF>(crop, sh, k, a, yf, out, list + done, 32);
                 done += 32;
             } while (cnt - done >= 32);
             const int rem = cnt - done;
@@ -688,19 +690,32 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
         }
     }
     __syncwarp();
-    eval_listed<R, LAYOUT, STAGED, FAST, DEFF>(crop, sh, k, a, yf, out, list, cnt);
+    eval_listed<R, LAYOUT, NW, STAGED, FAST, DEFF>(crop, sh, k, a, yf, out, list, cnt);
 }
 
 // ---------------------------------------------------------------- fused kernel
-#ifndef DTSDF_MIN_CTAS
-#define DTSDF_MIN_CTAS 3
-#endif
+// CTA shape per grid size and layout.  16 warps with two CTAs per SM (64 registers) or 8 warps with
+// three (80 registers); both keep the SM's shared memory full of crops.  Fewer, wider CTAs get through
+// a frame's read phase faster (the same shows in a no-arithmetic kernel with this traffic,
+// tools/wr_probe.cu) but lose a little to the tighter register budget; measured on the 120x130
+// workload (fraction of the HBM copy peak, 16 warps vs 8): R=32 (c,x,y,z) 0.97 vs 0.93, R=32 (c,z,y,x)
+// 0.91 vs 0.93, R=64 (c,x,y,z) 0.80 vs 0.86, R=64 (c,z,y,x) 0.98 vs 0.97.  R = 48 needs 8 warps
+// (the sweep is unrolled by two).
+template <int R, int LAYOUT>
+struct CtaShape {
+    static constexpr bool WIDE = (R == 32 && LAYOUT == 0) || (R == 64 && LAYOUT == 1);
+    static constexpr int NW = WIDE ? 16 : 8;
+    static constexpr int MIN_CTAS = WIDE ? 2 : 3;
+};
+
 template <int R, int LAYOUT, bool DEFF>
-__global__ void __launch_bounds__(NT, DTSDF_MIN_CTAS) dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
-    using FS = FrameShared<R, LAYOUT>;
+__global__ void __launch_bounds__(32 * CtaShape<R, LAYOUT>::NW, CtaShape<R, LAYOUT>::MIN_CTAS)
+dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
+    constexpr int NW = CtaShape<R, LAYOUT>::NW;
+    using FS = FrameShared<R, LAYOUT, NW>;
     constexpr int YS = FS::YS;
     static_assert(sizeof(FS) % 16 == 0 && offsetof(FS, nodepth) + 16 == sizeof(FS), "the pad must touch the crop");
-    static_assert(LaneMap<R>::MSTEPS % 2 == 0, "the sweep is unrolled by two");
+    static_assert(LaneMap<R, NW>::MSTEPS % 2 == 0, "the sweep is unrolled by two");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FS* sh = reinterpret_cast<FS*>(smem_raw);
     float* crop_s = reinterpret_cast<float*>(smem_raw + sizeof(FS));
@@ -731,12 +746,12 @@ __global__ void __launch_bounds__(NT, DTSDF_MIN_CTAS) dtsdf_fused_kernel(const _
     bool sawnan = false;
     if (fr.staged) {
         mbar_wait(&sh->bar, 0);
-        if (!scan)           sawnan = sanitize_crop(crop_s, fr.n_pad);
-        else if (scan_exact) sawnan = bbox_partial<DEFF, true, true>(fr, crop_s, a, yf, sh->red);
-        else                 sawnan = bbox_partial<DEFF, false, true>(fr, crop_s, a, yf, sh->red);
+        if (!scan)           sawnan = sanitize_crop<NW>(crop_s, fr.n_pad);
+        else if (scan_exact) sawnan = bbox_partial<DEFF, true, true, NW>(fr, crop_s, a, yf, sh->red);
+        else                 sawnan = bbox_partial<DEFF, false, true, NW>(fr, crop_s, a, yf, sh->red);
     } else if (scan) {
-        if (scan_exact) bbox_partial<DEFF, true, false>(fr, const_cast<float*>(fr.crop), a, yf, sh->red);
-        else            bbox_partial<DEFF, false, false>(fr, const_cast<float*>(fr.crop), a, yf, sh->red);
+        if (scan_exact) bbox_partial<DEFF, true, false, NW>(fr, const_cast<float*>(fr.crop), a, yf, sh->red);
+        else            bbox_partial<DEFF, false, false, NW>(fr, const_cast<float*>(fr.crop), a, yf, sh->red);
     }
     if (sawnan) sh->nanflag = 1u;
     __syncthreads();      // (A) bbox partials, sanitised crop and the NaN flag are in
@@ -763,16 +778,16 @@ __global__ void __launch_bounds__(NT, DTSDF_MIN_CTAS) dtsdf_fused_kernel(const _
     } else {
         float mn[3], mx[3];
         if (scan) {
-            bbox_reduce(sh->red, mn, mx);
+            bbox_reduce<NW>(sh->red, mn, mx);
             // the fixed-divisor scan is exact for |d| < 2^40 only: rescan with IEEE divisions
             // if the frame holds anything larger (block-uniform, never on real data; the
             // sanitised crop scans like the original)
             if (!scan_exact && !(fabsf(mn[2]) < BIG_DEPTH && fabsf(mx[2]) < BIG_DEPTH)) {
                 __syncthreads();
-                if (fr.staged) bbox_partial<DEFF, true, true>(fr, crop_s, a, yf, sh->red);
-                else           bbox_partial<DEFF, true, false>(fr, const_cast<float*>(fr.crop), a, yf, sh->red);
+                if (fr.staged) bbox_partial<DEFF, true, true, NW>(fr, crop_s, a, yf, sh->red);
+                else           bbox_partial<DEFF, true, false, NW>(fr, const_cast<float*>(fr.crop), a, yf, sh->red);
                 __syncthreads();
-                bbox_reduce(sh->red, mn, mx);
+                bbox_reduce<NW>(sh->red, mn, mx);
             }
         } else {                  // DTSDF_BBOX_EXTREMA: {max xyz, min xyz}, pre/process.py:120
             const float* g = a.aux + 6 * (size_t)f;
@@ -825,13 +840,13 @@ __global__ void __launch_bounds__(NT, DTSDF_MIN_CTAS) dtsdf_fused_kernel(const _
     }
     {
         // entry e: zi = e % R is the z index, ti = e / R the x (at) / y (yt) index.  With
-        // NT a multiple of R the z index, and with it the division, is the same for every
+        // (32 * NW) a multiple of R the z index, and with it the division, is the same for every
         // entry of a thread.
-        constexpr bool HOIST = (NT % R) == 0;
+        constexpr bool HOIST = ((32 * NW) % R) == 0;
         float coeff_h = 0.0f;
         if (HOIST) coeff_h = __fdiv_rn(-a.focal, __fadd_rn(oz, __fmul_rn((float)(tid % R), voxel_len)));
 #pragma unroll 2
-        for (int e = tid; e < R * R; e += NT) {
+        for (int e = tid; e < R * R; e += (32 * NW)) {
             const int ti = e / R, zi = e % R;
             const float coeff = HOIST ? coeff_h
                                       : __fdiv_rn(-a.focal, __fadd_rn(oz, __fmul_rn((float)zi, voxel_len)));
@@ -874,11 +889,11 @@ __global__ void __launch_bounds__(NT, DTSDF_MIN_CTAS) dtsdf_fused_kernel(const _
 
     // ---- 3. voxel loop
     if (fast) {
-        if (staged) voxel_passes<R, LAYOUT, true, true, DEFF>(crop_s, sh, k, a, yf, out);
-        else        voxel_passes<R, LAYOUT, false, true, DEFF>(fr.crop, sh, k, a, yf, out);
+        if (staged) voxel_passes<R, LAYOUT, NW, true, true, DEFF>(crop_s, sh, k, a, yf, out);
+        else        voxel_passes<R, LAYOUT, NW, false, true, DEFF>(fr.crop, sh, k, a, yf, out);
     } else {
-        if (staged) voxel_passes<R, LAYOUT, true, false, DEFF>(crop_s, sh, k, a, yf, out);
-        else        voxel_passes<R, LAYOUT, false, false, DEFF>(fr.crop, sh, k, a, yf, out);
+        if (staged) voxel_passes<R, LAYOUT, NW, true, false, DEFF>(crop_s, sh, k, a, yf, out);
+        else        voxel_passes<R, LAYOUT, NW, false, false, DEFF>(fr.crop, sh, k, a, yf, out);
     }
 }
 
@@ -893,7 +908,8 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     if (e != cudaSuccess) return e;
     if ((reinterpret_cast<uintptr_t>(args.vol) & 15) != 0) return cudaErrorMisalignedAddress;
     if ((reinterpret_cast<uintptr_t>(args.depth) & 15) != 0) return cudaErrorMisalignedAddress;
-    const int fixed = (int)sizeof(FrameShared<R, LAYOUT>);
+    constexpr int NW = CtaShape<R, LAYOUT>::NW;
+    const int fixed = (int)sizeof(FrameShared<R, LAYOUT, NW>);
     // staging capacity: the largest crop of the batch when known (the occupancy then follows from
     // it: three CTAs per SM up to ~63 KB crops, two up to ~100 KB, one above); oversize crops take the direct path.
     long long want = max_crop_px > 0 ? (((long long)max_crop_px + 3) & ~3ll) * 4 : (long long)smem_optin;
@@ -906,7 +922,7 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     auto kern = dtsdf_fused_kernel<R, LAYOUT, DEFF>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)args.n_frames, NT, smem, stream>>>(args);      // one CTA per frame
+    kern<<<(unsigned)args.n_frames, (32 * NW), smem, stream>>>(args);      // one CTA per frame
     ++g_launch_count;
     return cudaGetLastError();
 }
@@ -1087,7 +1103,7 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
         *reinterpret_cast<float2*>(&red[warp][4]) = make_float2(mx[1], mx[2]);
     }
     __syncthreads();
-    bbox_reduce(red, mn, mx);
+    bbox_reduce<NWARP>(red, mn, mx);
 
     // ---- 2. grid parameters (pre/process.py:91-96)
     const float mid0 = __fmul_rn(__fadd_rn(mx[0], mn[0]), 0.5f);
