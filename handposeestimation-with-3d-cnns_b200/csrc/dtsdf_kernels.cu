@@ -897,6 +897,18 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     }
 }
 
+// The opt-in dynamic shared memory limit of a kernel is a per-device function attribute: raise it to the
+// device maximum once per (instantiation, device), not per launch (launches may come from several host
+// threads with different crop sizes).
+template <typename K>
+cudaError_t allow_max_smem(K kern, int dev, int smem_optin, std::atomic<unsigned>& done_mask) {
+    const unsigned bit = 1u << (dev & 31);
+    if (done_mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    if (e == cudaSuccess) done_mask.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
 template <int R, int LAYOUT, bool DEFF>
 cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t stream) {
     BatchArgs args = args_in;
@@ -920,7 +932,8 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     args.cap_floats = (int)(want / 4);
     const size_t smem = (size_t)fixed + (size_t)want;
     auto kern = dtsdf_fused_kernel<R, LAYOUT, DEFF>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static std::atomic<unsigned> smem_ok{0u};
+    e = allow_max_smem(kern, dev, smem_optin, smem_ok);
     if (e != cudaSuccess) return e;
     kern<<<(unsigned)args.n_frames, (32 * NW), smem, stream>>>(args);      // one CTA per frame
     ++g_launch_count;
@@ -1204,7 +1217,8 @@ cudaError_t launch_aug_t(const BatchArgs& args_in, const float* aug, int max_cro
     want &= ~15ll;
     args.cap_floats = (int)(want / 4);
     auto kern = dtsdf_aug_kernel<R, LAYOUT>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    static std::atomic<unsigned> smem_ok{0u};
+    e = allow_max_smem(kern, dev, smem_optin, smem_ok);
     if (e != cudaSuccess) return e;
     kern<<<(unsigned)args.n_frames, NT, (size_t)want, stream>>>(args, aug);
     ++g_launch_count;

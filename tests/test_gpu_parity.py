@@ -523,3 +523,34 @@ def test_randomised_frames_all_bbox_modes(vox, seed):
         cv, _, _, _ = c_oracle.dtsdf_batch(headers, offsets, packed, layout=layout, bbox_mode=2, aux=grid)
         for i in range(n):
             assert _same(vol[i], cv[i]), "grid frame %d layout %d" % (i, layout)
+
+
+def test_concurrent_host_threads_with_their_own_contexts():
+    """The library is re-entrant: several host threads, each with its own context (own streams, staging
+    buffers and expansion pool), voxelise different batches at the same time (ctypes drops the GIL)."""
+    import threading
+    jobs = []
+    for t in range(4):
+        frames = synth.make_frames(range(1200 + 100 * t, 1200 + 100 * t + 60 + 7 * t))
+        jobs.append(pack_simple(frames))
+    want = [c_oracle.dtsdf_batch(h, o, p, layout=t % 2)[0] for t, (h, o, p) in enumerate(jobs)]
+    got, errs = [None] * 4, []
+
+    def work(t):
+        try:
+            v = pkg.Voxelizer(device=0)
+            h, o, p = jobs[t]
+            for _ in range(3):
+                got[t] = v.voxelize_packed(h, o, p, layout=t % 2)[0]
+            v.close()
+        except Exception as e:          # noqa: BLE001
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errs, errs
+    for t in range(4):
+        assert _same(got[t], want[t]), "thread %d" % t
