@@ -13,12 +13,12 @@
 // with __fadd_rn/__fmul_rn/__fdiv_rn, which the compiler never contracts into FMAs.
 // The file is also compiled with -fmad=false.
 //
-// Design: ONE CTA (16 or 8 warps, CtaShape) PER FRAME, grid = number of frames.  The hardware block
+// Design: ONE CTA (8 warps) PER FRAME, grid = number of frames.  The hardware block
 // scheduler balances ragged batches, and - measured on B200 - CTAs that come and go keep the
 // HBM write stream 15-40 % faster than persistent CTAs marching in lock-step (a store-only
 // variant of this kernel: 0.46 ms one CTA per frame vs 0.73 ms persistent for 8,500 frames).
-// Two or three CTAs are resident per SM (76 KB of shared memory each for a 120x130 crop), so the
-// prologue of one frame hides behind the voxel loops of the others.
+// Two or three CTAs are resident per SM - as many as keep the volumes under construction inside the
+// L2 (launch_fused) - so the prologue of one frame hides behind the voxel loops of the others.
 //   0  thread 0: frame record, mbarrier init, ONE TMA bulk copy (cp.async.bulk) of the crop
 //      global -> shared memory
 //   1  bounding-box scan of the staged crop, one warp per crop row (LDS.128), which also
@@ -61,6 +61,7 @@
 #include <stddef.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <atomic>
 
 namespace dtsdf {
@@ -694,18 +695,13 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
 }
 
 // ---------------------------------------------------------------- fused kernel
-// CTA shape per grid size and layout.  16 warps with two CTAs per SM (64 registers) or 8 warps with
-// three (80 registers); both keep the SM's shared memory full of crops.  Fewer, wider CTAs get through
-// a frame's read phase faster (the same shows in a no-arithmetic kernel with this traffic,
-// tools/wr_probe.cu) but lose a little to the tighter register budget; measured on the 120x130
-// workload (fraction of the HBM copy peak, 16 warps vs 8): R=32 (c,x,y,z) 0.97 vs 0.93, R=32 (c,z,y,x)
-// 0.91 vs 0.93, R=64 (c,x,y,z) 0.80 vs 0.86, R=64 (c,z,y,x) 0.98 vs 0.97.  R = 48 needs 8 warps
-// (the sweep is unrolled by two).
+// CTA shape: 8 warps, up to three CTAs per SM (80 registers, no spills).  16 warps x 2 CTAs/SM (64
+// registers) was measured as well: the same speed as 8 warps x 2 CTAs/SM - what counts is how many
+// frames are in flight, see launch_fused.
 template <int R, int LAYOUT>
 struct CtaShape {
-    static constexpr bool WIDE = (R == 32 && LAYOUT == 0) || (R == 64 && LAYOUT == 1);
-    static constexpr int NW = WIDE ? 16 : 8;
-    static constexpr int MIN_CTAS = WIDE ? 2 : 3;
+    static constexpr int NW = 8;
+    static constexpr int MIN_CTAS = 3;
 };
 
 template <int R, int LAYOUT, bool DEFF>
@@ -904,7 +900,10 @@ template <typename K>
 cudaError_t allow_max_smem(K kern, int dev, int smem_optin, std::atomic<unsigned>& done_mask) {
     const unsigned bit = 1u << (dev & 31);
     if (done_mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
-    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)fa.sharedSizeBytes);
     if (e == cudaSuccess) done_mask.fetch_or(bit, std::memory_order_release);
     return e;
 }
@@ -930,11 +929,39 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     if (want < 16) want = 16;
     want &= ~15ll;
     args.cap_floats = (int)(want / 4);
-    const size_t smem = (size_t)fixed + (size_t)want;
+    size_t smem = (size_t)fixed + (size_t)want;
     auto kern = dtsdf_fused_kernel<R, LAYOUT, DEFF>;
     static std::atomic<unsigned> smem_ok{0u};
     e = allow_max_smem(kern, dev, smem_optin, smem_ok);
     if (e != cudaSuccess) return e;
+    // Frames in flight.  Every resident CTA has a volume (12 R^3 bytes) under construction; the stores
+    // of all of them sit in L2 until they are written back.  While that footprint fits in L2 the write
+    // stream reaches DRAM in long runs; beyond it, it does not: measured for R = 32 on B200 (126 MB L2),
+    // 2 CTAs/SM = 296 volumes = 116 MB -> 0.618 ms per 8,500 frames, 3 CTAs/SM = 174 MB -> 0.642 ms,
+    // 1 CTA/SM -> 0.78 ms (nothing left to hide a frame's prologue).  So: at most as many CTAs per SM as
+    // keep the footprint inside L2, but never fewer than two; the limit is imposed by padding the
+    // dynamic shared memory request.
+    {
+        int occ = 0, sms = 0, l2 = 0, smem_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * NW, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        if (e != cudaSuccess) return e;
+        const long long vol_bytes = 12ll * R * R * R;
+        const int fit = (int)((long long)l2 / ((long long)sms * vol_bytes));
+        const int target = fit >= 2 ? std::min(occ, fit) : occ;
+        if (target >= 1 && target < occ) {
+            // the largest request that still lets `target` CTAs share an SM (1 KB per CTA is reserved)
+            long long padded = ((long long)smem_sm / target - 1024) & ~15ll;
+            if (padded > smem_optin) padded = smem_optin;
+            if (padded > (long long)smem) smem = (size_t)padded;
+        }
+        args.cap_floats = (int)((smem - (size_t)fixed) / 4) & ~3;      // the padding stages larger crops for free
+    }
     kern<<<(unsigned)args.n_frames, (32 * NW), smem, stream>>>(args);      // one CTA per frame
     ++g_launch_count;
     return cudaGetLastError();
