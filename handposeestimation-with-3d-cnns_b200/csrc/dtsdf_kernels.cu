@@ -936,7 +936,8 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     if (e != cudaSuccess) return e;
     // Frames in flight.  Every resident CTA has a volume (12 R^3 bytes) under construction; the stores
     // of all of them sit in L2 until they are written back.  While that footprint fits in L2 the write
-    // stream reaches DRAM in long runs; beyond it, it does not: measured for R = 32 on B200 (126 MB L2),
+    // stream reaches DRAM more efficiently (fewer concurrent streams, longer runs - the exact mechanism
+    // was not isolated; the policy rests on the measurement): for R = 32 on B200 (126 MB L2),
     // 2 CTAs/SM = 296 volumes = 116 MB -> 0.618 ms per 8,500 frames, 3 CTAs/SM = 174 MB -> 0.642 ms,
     // 1 CTA/SM -> 0.78 ms (nothing left to hide a frame's prologue).  So: at most as many CTAs per SM as
     // keep the footprint inside L2, but never fewer than two; the limit is imposed by padding the
