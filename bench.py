@@ -17,7 +17,8 @@ Printed JSON (one line, rank 0):
              pinned HOST buffers in and out, H2D + kernel + D2H inside the timed region
   roofline   HBM roofline of the fused kernel: algorithmic bytes per launch / measured launch time
              against MEASURED_PEAKS.json
-  cpu_baseline  the C oracle port of the reference loop on the host cores (N = 1, rank 0 only)
+  cpu_baseline  the C oracle port of the reference loop on the host cores (N = 1, rank 0 only); beside it
+             the reference's own numba.cuda kernels driven per frame on this GPU (oracle/_ref)
 """
 import argparse
 import json
@@ -181,6 +182,38 @@ def python_loop_rate(headers, offsets, packed, R):
     vox_ori, voxel_len, trunc, _, _ = orc.grid_params(pmax, pmin, R)
     orc.tsdf_cal_loop(h, depth, vox_ori, voxel_len, trunc, R)
     return 1.0 / (time.perf_counter() - t0)
+
+
+def numba_gpu_rate(headers, offsets, packed, frames=256):
+    """The reference's own GPU path on this box: its two numba kernels (compiled from the unmodified
+    pre/tsdf_numba.py into oracle/_ref by oracle/make_numba_ptx.py) driven per frame exactly as
+    cal_tsdf_cuda does (pre/tsdf_numba.py:119-161: 2 launches, 2 H2D, 2 D2H, a host reduction).
+    Only R = 32, layout (c,z,y,x): the kernel is hard-wired to both."""
+    try:
+        from oracle import numba_ptx_ref
+        if not numba_ptx_ref.available():
+            return {"unavailable": "oracle/_ref PTX not built"}
+        import torch
+        ref = numba_ptx_ref.NumbaPtxReference(device=torch.cuda.current_device())
+        n = min(frames, headers.shape[0])
+        recs = []
+        for i in range(n):
+            h = headers[i]
+            px = int(h[4] - h[2]) * int(h[5] - h[3])
+            recs.append({"header": h, "data": np.array(packed[int(offsets[i]):int(offsets[i]) + px])})
+        for r in recs[:8]:
+            ref.cal_tsdf_cuda(r)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for r in recs:
+            ref.cal_tsdf_cuda(r)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": UNIT, "frames": n,
+                "how": "reference numba kernels (numba %s PTX of the unmodified source, driver-JITed for this GPU), "
+                       "one frame per call through the steps of cal_tsdf_cuda, 1 host thread" % ref.manifest["numba"]}
+    except Exception as e:  # a comparator, never fatal
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
 
 
 def run_reference(args, rank, world):
@@ -416,6 +449,9 @@ def run_ours(args, rank, local_rank, world):
                           "%d threads)" % (passes, sample, dt, used),
                 "python_loop_volumes_per_s_per_core": python_loop_rate(headers, offsets, h_packed.array, R),
             }
+            if R == 32:
+                line["cpu_baseline"]["reference_numba_kernels_on_this_gpu"] = numba_gpu_rate(
+                    headers, offsets, h_packed.array)
         print(json.dumps(line), flush=True)
     barrier()
     vox.close()

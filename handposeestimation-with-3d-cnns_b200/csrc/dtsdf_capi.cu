@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -138,7 +139,12 @@ struct Latch {
     void add(int n) { std::lock_guard<std::mutex> g(m); pending += n; }
     void done() {
         std::lock_guard<std::mutex> g(m);
-        if (--pending == 0) cv.notify_all();
+        if (pending > 0 && --pending == 0) cv.notify_all();
+    }
+    void reset() {                               // after a failed stream: nothing more will arrive
+        std::lock_guard<std::mutex> g(m);
+        pending = 0;
+        cv.notify_all();
     }
     void wait() {
         std::unique_lock<std::mutex> g(m);
@@ -146,71 +152,7 @@ struct Latch {
     }
 };
 
-// Expansion of one packed frame (dtsdf_internal.h: launch_pack) into its three channel planes.
-// Streaming stores: the planes are written once and not read back by this code.
-struct DecodeTables {
-    float val[256][4];          // the four voxel values of a code byte without literals
-    unsigned char nlit[256];    // number of literals in the byte
-    DecodeTables() {
-        const float v[4] = {0.0f, 1.0f, -1.0f, 0.0f};
-        for (int b = 0; b < 256; ++b) {
-            int n = 0;
-            for (int j = 0; j < 4; ++j) {
-                const int c = (b >> (2 * j)) & 3;
-                val[b][j] = v[c];
-                n += c == 3;
-            }
-            nlit[b] = (unsigned char)n;
-        }
-    }
-};
-const DecodeTables g_dec;
-
-template <bool ALIGNED>
-inline void put4(float* p, __m128 v) {
-    if (ALIGNED) _mm_stream_ps(p, v);
-    else _mm_storeu_ps(p, v);
-}
-
-template <bool ALIGNED>
-void decode_frame_t(const unsigned char* codes, const float* lits, size_t r3, float* out) {
-    float* o0 = out;
-    float* o1 = out + r3;
-    float* o2 = out + 2 * r3;
-    const size_t nb = r3 / 4;                 // code bytes; a multiple of 8 (r3 is a multiple of 1024)
-    const __m128 zero = _mm_setzero_ps(), pone = _mm_set1_ps(1.0f), mone = _mm_set1_ps(-1.0f);
-    for (size_t k = 0; k < nb; k += 8) {
-        unsigned long long w;
-        memcpy(&w, codes + k, 8);
-        // 32 voxels with one value (most of a volume): no table, no literals
-        const bool run0 = w == 0ull, run1 = w == 0x5555555555555555ull, run2 = w == 0xAAAAAAAAAAAAAAAAull;
-        if (run0 || run1 || run2) {
-            const __m128 v = run0 ? zero : (run1 ? pone : mone);
-            for (int j = 0; j < 8; ++j) {
-                put4<ALIGNED>(o0 + 4 * (k + j), v); put4<ALIGNED>(o1 + 4 * (k + j), v); put4<ALIGNED>(o2 + 4 * (k + j), v);
-            }
-            continue;
-        }
-        for (int j = 0; j < 8; ++j) {
-            const unsigned b = codes[k + j];
-            __m128 v0, v1, v2;
-            if (g_dec.nlit[b] == 0) {
-                v0 = v1 = v2 = _mm_loadu_ps(g_dec.val[b]);
-            } else {                          // literal group: x[4], y[4], z[4] (16-byte aligned)
-                v0 = _mm_load_ps(lits); v1 = _mm_load_ps(lits + 4); v2 = _mm_load_ps(lits + 8);
-                lits += 12;
-            }
-            put4<ALIGNED>(o0 + 4 * (k + j), v0); put4<ALIGNED>(o1 + 4 * (k + j), v1); put4<ALIGNED>(o2 + 4 * (k + j), v2);
-        }
-    }
-    if (ALIGNED) _mm_sfence();
-}
-
-void decode_frame(const unsigned char* codes, const float* lits, size_t r3, float* out) {
-    // streaming stores need 16-byte alignment: the three planes of a frame share it (r3 % 4 == 0)
-    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) decode_frame_t<true>(codes, lits, r3, out);
-    else decode_frame_t<false>(codes, lits, r3, out);
-}
+// (the expansion of a packed frame on the host lives in dtsdf_decode.cpp: dtsdf::decode_frame)
 
 }  // namespace
 
@@ -226,7 +168,17 @@ struct dtsdf_ctx {
     DevBuf d_cnt[NSLOT], d_loff[NSLOT], d_codes[NSLOT], d_lits[NSLOT];
     MapBuf m_codes[NSLOT], m_loff[NSLOT], m_lits[NSLOT];
     Latch latch[NSLOT];
-    int64_t stat_d2h_bytes = 0;
+    std::atomic<long long> stat_d2h_bytes{0};
+    // what the host function enqueued behind a chunk's device -> host copies needs to hand the
+    // chunk to the expansion threads (owned by the slot: rewritten only after latch[slot].wait())
+    struct ChunkRecord {
+        dtsdf_ctx* ctx;
+        int slot, jobs;
+        int32_t nf;
+        size_t r3, vol_floats;
+        float* dst;                              // h_vol + f0 * vol_floats
+        long long fixed_bytes;                   // PCIe bytes of the chunk apart from the literal stream
+    } chunk[NSLOT];
     DevBuf d_depth[NSLOT], d_off[NSLOT], d_hdr[NSLOT], d_aux[NSLOT];
     DevBuf d_vol[NSLOT], d_maxl[NSLOT], d_mid[NSLOT];
     cudaEvent_t ev_in[NSLOT] = {}, ev_run[NSLOT] = {}, ev_out[NSLOT] = {};
@@ -579,7 +531,7 @@ int dtsdf_ctx_set_option(dtsdf_ctx* c, int32_t option, int64_t value) {
 int dtsdf_ctx_get_stat(dtsdf_ctx* c, int32_t stat, int64_t* value) {
     if (!c || !value) return DTSDF_ERR_INVALID_ARG;
     if (stat != DTSDF_STAT_D2H_BYTES) return DTSDF_ERR_UNSUPPORTED;
-    *value = c->stat_d2h_bytes;
+    *value = (int64_t)c->stat_d2h_bytes.load();
     return DTSDF_OK;
 }
 
@@ -593,6 +545,32 @@ int dtsdf_host_alloc(void** ptr, int64_t bytes) {
 
 void dtsdf_host_free(void* ptr) {
     if (ptr) { cudaFreeHost(ptr); cudaGetLastError(); }
+}
+
+// Host function behind a chunk's device -> host copies (packed mode): split the chunk's frames over the
+// expansion threads.  Runs on a CUDA-internal thread: no CUDA calls here.
+static void CUDART_CB expand_chunk_cb(void* p) {
+    const dtsdf_ctx::ChunkRecord* r = static_cast<const dtsdf_ctx::ChunkRecord*>(p);
+    dtsdf_ctx* c = r->ctx;
+    const unsigned char* codes = (const unsigned char*)c->m_codes[r->slot].p;
+    const unsigned long long* loff = (const unsigned long long*)c->m_loff[r->slot].p;
+    const float* lits = (const float*)c->m_lits[r->slot].p;
+    c->stat_d2h_bytes += r->fixed_bytes + 48ll * (long long)loff[r->nf];
+    Latch* latch = &c->latch[r->slot];
+    const int32_t nf = r->nf;
+    const int jobs = r->jobs;
+    const size_t r3 = r->r3, vol_floats = r->vol_floats;
+    float* dst = r->dst;
+    for (int j = 0; j < jobs; ++j) {
+        const int32_t a0 = (int32_t)((int64_t)nf * j / jobs), a1 = (int32_t)((int64_t)nf * (j + 1) / jobs);
+        c->pool.submit([=] {
+#ifndef DTSDF_EXP_SKIP_DECODE   /* dev ablation: the pipeline without the host expansion */
+            for (int32_t f = a0; f < a1; ++f)
+                dtsdf::decode_frame(codes + (size_t)f * (r3 / 4), lits + 12 * loff[f], r3, dst + (size_t)f * vol_floats);
+#endif
+            latch->done();
+        });
+    }
 }
 
 // ------------------------------------------------------------------ host pipeline
@@ -636,7 +614,7 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
     // threads expand it into h_vol while the next chunks are in flight
     const bool packed = c->opt_packed != 0;
     const size_t r3 = R * R * R;
-    c->stat_d2h_bytes = packed ? 0 : (int64_t)n_frames * (int64_t)(vol_floats * 4 + (h_maxl ? 4 : 0) + (h_mid ? 12 : 0));
+    c->stat_d2h_bytes = packed ? 0ll : (long long)n_frames * (long long)(vol_floats * 4 + (h_maxl ? 4 : 0) + (h_mid ? 12 : 0));
     int nthreads = 1;
     if (packed) {
         // default: three quarters of the hardware threads (the expansion is memory-bound well before
@@ -645,35 +623,33 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
         nthreads = c->opt_threads > 0 ? c->opt_threads : (int)std::min(32u, std::max(1u, hw - hw / 4));
         c->pool.ensure(nthreads);
     }
-    struct Pending { int slot; int32_t f0, nf; };
-    Pending pend = {-1, 0, 0};
-    auto finalize = [&](const Pending& pd) -> int {
-        // the chunk's kernels have written the packed form: hand it to the host threads
-        CK(cudaEventSynchronize(c->ev_run[pd.slot]));
-        const unsigned char* codes = (const unsigned char*)c->m_codes[pd.slot].p;
-        const unsigned long long* loff = (const unsigned long long*)c->m_loff[pd.slot].p;
-        const float* lits = (const float*)c->m_lits[pd.slot].p;
-        c->stat_d2h_bytes += (int64_t)pd.nf * (int64_t)(r3 / 4) + (int64_t)(pd.nf + 1) * 8 + 48 * (int64_t)loff[pd.nf] +
-                             (h_maxl ? 4 * (int64_t)pd.nf : 0) + (h_mid ? 12 * (int64_t)pd.nf : 0);
-        const int jobs = std::min<int>(pd.nf, nthreads);
-        Latch* latch = &c->latch[pd.slot];
-        latch->add(jobs);
-        for (int j = 0; j < jobs; ++j) {
-            const int32_t a0 = (int32_t)((int64_t)pd.nf * j / jobs), a1 = (int32_t)((int64_t)pd.nf * (j + 1) / jobs);
-            float* dst = h_vol + (size_t)pd.f0 * vol_floats;
-            c->pool.submit([=] {
-                for (int32_t f = a0; f < a1; ++f)
-                    decode_frame(codes + (size_t)f * (r3 / 4), lits + 12 * loff[f], r3, dst + (size_t)f * vol_floats);
-                latch->done();
-            });
-        }
-        return DTSDF_OK;
-    };
+    // A chunk is handed to the expansion threads by a host function enqueued on s_out behind its
+    // device -> host copies (expand_chunk_cb below): the submitting thread never waits for the GPU, so
+    // up to NSLOT chunks are in flight on the three streams; it only waits, before reusing a slot,
+    // for the host threads to be done with the chunk that used it last (latch[slot]).
     auto drain = [&]() {
-        for (int i = 0; i < dtsdf_ctx::NSLOT; ++i) c->latch[i].wait();
+        // host functions do not run once a stream has failed: do not wait for them then
+        const bool ok = cudaStreamSynchronize(c->s_out) == cudaSuccess;
+        for (int i = 0; i < dtsdf_ctx::NSLOT; ++i) {
+            if (ok) c->latch[i].wait();
+            else c->latch[i].reset();
+        }
     };
 
+#ifdef DTSDF_EXP_TIMELINE       /* dev instrumentation: where a chunk's time goes on each stream */
+    struct TL { cudaEvent_t e[8]; };
+    std::vector<TL> tl(nchunk);
+    for (auto& t : tl) for (auto& e : t.e) cudaEventCreate(&e);
+    const auto host_t0 = std::chrono::steady_clock::now();
+    std::vector<double> host_submit(nchunk), host_wait(nchunk);
+#define TLREC(i, st) cudaEventRecord(tl[k].e[i], st)
+#else
+#define TLREC(i, st) ((void)0)
+#endif
     for (int k = 0; k < nchunk; ++k) {
+#ifdef DTSDF_EXP_TIMELINE
+        const auto hk0 = std::chrono::steady_clock::now();
+#endif
         const int slot = k % dtsdf_ctx::NSLOT;
         const int32_t f0 = k * per_chunk;
         const int32_t nf = std::min(per_chunk, n_frames - f0);
@@ -714,16 +690,19 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
 
         // H2D on s_in.  `rebased` is pageable host memory: cudaMemcpyAsync stages it before
         // returning, so reusing the vector for the next chunk is safe.
+        TLREC(0, c->s_in);
         CK(cudaMemcpyAsync(c->d_depth[slot].p, h_depth + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, c->s_in));
         CK(cudaMemcpyAsync(c->d_off[slot].p, rebased.data(), (size_t)nf * 8, cudaMemcpyHostToDevice, c->s_in));
         CK(cudaMemcpyAsync(c->d_hdr[slot].p, h_hdr + 6 * (size_t)f0, (size_t)nf * 24, cudaMemcpyHostToDevice, c->s_in));
         if (aux_w)
             CK(cudaMemcpyAsync(c->d_aux[slot].p, h_aux + (size_t)aux_w * f0, (size_t)nf * aux_w * 4,
                                cudaMemcpyHostToDevice, c->s_in));
+        TLREC(1, c->s_in);
         CK(cudaEventRecord(c->ev_in[slot], c->s_in));
 
         // kernel on s_run
         CK(cudaStreamWaitEvent(c->s_run, c->ev_in[slot], 0));
+        TLREC(2, c->s_run);
         rc = dtsdf_voxelize_batch(cfg, nf, (const float*)c->d_depth[slot].p, (const int64_t*)c->d_off[slot].p,
                                   (const int32_t*)c->d_hdr[slot].p, aux_w ? (const float*)c->d_aux[slot].p : nullptr,
                                   max_px, (float*)c->d_vol[slot].p, (float*)c->d_maxl[slot].p,
@@ -731,27 +710,49 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
         if (rc != DTSDF_OK) return fail(rc);
 
         if (packed) {
-            // pack into device memory, then: codes and offsets (fixed size) by the copy engine, the
-            // literal stream (device-known size) by a copy kernel into mapped pinned memory
+            // pack into device memory on the kernel stream; then, on s_out so that the next chunk's
+            // kernels are not held up by PCIe: the literal stream (device-known size) by a copy kernel
+            // into mapped pinned memory, codes and offsets (fixed size) by the copy engine.  (With
+            // everything on one stream the transfers were 60 % of that stream's time.)
+            TLREC(3, c->s_run);
             void* dv_lits = nullptr;
             CK(cudaHostGetDevicePointer(&dv_lits, c->m_lits[slot].p, 0));
             cudaError_t pe = dtsdf::launch_pack(nf, (int)r3, (const float*)c->d_vol[slot].p, (unsigned*)c->d_cnt[slot].p,
                                                 (unsigned long long*)c->d_loff[slot].p, nullptr,
                                                 (unsigned char*)c->d_codes[slot].p, (float*)c->d_lits[slot].p, c->s_run);
-            if (pe == cudaSuccess)
-                pe = dtsdf::launch_pack_push(nf, (const float*)c->d_lits[slot].p,
-                                             (const unsigned long long*)c->d_loff[slot].p, (float*)dv_lits, c->s_run);
+            TLREC(4, c->s_run);
             if (pe != cudaSuccess) { drain(); return cuda_fail(pe, "launch_pack"); }
-            CK(cudaMemcpyAsync(c->m_codes[slot].p, c->d_codes[slot].p, (size_t)nf * (r3 / 4), cudaMemcpyDeviceToHost, c->s_run));
-            CK(cudaMemcpyAsync(c->m_loff[slot].p, c->d_loff[slot].p, (size_t)(nf + 1) * 8, cudaMemcpyDeviceToHost, c->s_run));
+            CK(cudaEventRecord(c->ev_out[slot], c->s_run));          // packed mode: "chunk packed"
+            CK(cudaStreamWaitEvent(c->s_out, c->ev_out[slot], 0));
+            TLREC(7, c->s_out);
+#ifndef DTSDF_EXP_SKIP_PUSH     /* dev ablation: the literal stream stays on the device */
+            pe = dtsdf::launch_pack_push(nf, (const float*)c->d_lits[slot].p,
+                                         (const unsigned long long*)c->d_loff[slot].p, (float*)dv_lits, c->s_out);
+            if (pe != cudaSuccess) { drain(); return cuda_fail(pe, "launch_pack_push"); }
+#endif
+            TLREC(5, c->s_out);
+            CK(cudaMemcpyAsync(c->m_codes[slot].p, c->d_codes[slot].p, (size_t)nf * (r3 / 4), cudaMemcpyDeviceToHost, c->s_out));
+            CK(cudaMemcpyAsync(c->m_loff[slot].p, c->d_loff[slot].p, (size_t)(nf + 1) * 8, cudaMemcpyDeviceToHost, c->s_out));
             if (h_maxl)
-                CK(cudaMemcpyAsync(h_maxl + f0, c->d_maxl[slot].p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->s_run));
+                CK(cudaMemcpyAsync(h_maxl + f0, c->d_maxl[slot].p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->s_out));
             if (h_mid)
-                CK(cudaMemcpyAsync(h_mid + 3 * (size_t)f0, c->d_mid[slot].p, (size_t)nf * 12, cudaMemcpyDeviceToHost, c->s_run));
-            CK(cudaEventRecord(c->ev_run[slot], c->s_run));
-            // while this chunk runs on the GPU, hand the previous one to the host threads
-            if (pend.slot >= 0 && (rc = finalize(pend)) != DTSDF_OK) { drain(); return rc; }
-            pend = {slot, f0, nf};
+                CK(cudaMemcpyAsync(h_mid + 3 * (size_t)f0, c->d_mid[slot].p, (size_t)nf * 12, cudaMemcpyDeviceToHost, c->s_out));
+            TLREC(6, c->s_out);
+            // behind the copies: hand the chunk to the expansion threads
+            {
+                dtsdf_ctx::ChunkRecord& r = c->chunk[slot];
+                r.ctx = c; r.slot = slot; r.jobs = std::min<int>(nf, nthreads); r.nf = nf;
+                r.r3 = r3; r.vol_floats = vol_floats; r.dst = h_vol + (size_t)f0 * vol_floats;
+                r.fixed_bytes = (long long)nf * (long long)(r3 / 4) + (long long)(nf + 1) * 8 +
+                                (h_maxl ? 4ll * nf : 0ll) + (h_mid ? 12ll * nf : 0ll);
+                c->latch[slot].add(r.jobs);
+                const cudaError_t he = cudaLaunchHostFunc(c->s_out, expand_chunk_cb, &r);
+                if (he != cudaSuccess) { c->latch[slot].reset(); drain(); return cuda_fail(he, "cudaLaunchHostFunc"); }
+            }
+#ifdef DTSDF_EXP_TIMELINE
+            host_submit[k] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hk0).count();
+            host_wait[k] = 0.0;
+#endif
             continue;
         }
         CK(cudaEventRecord(c->ev_run[slot], c->s_run));
@@ -766,11 +767,31 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
             CK(cudaMemcpyAsync(h_mid + 3 * (size_t)f0, c->d_mid[slot].p, (size_t)nf * 12, cudaMemcpyDeviceToHost, c->s_out));
         CK(cudaEventRecord(c->ev_out[slot], c->s_out));
     }
+#ifdef DTSDF_EXP_TIMELINE
     if (packed) {
-        if (pend.slot >= 0) rc = finalize(pend);
-        drain();
-        if (rc != DTSDF_OK) return rc;
+        cudaDeviceSynchronize();
+        double sum[8] = {0}, hs = 0, hw = 0;
+        float ms;
+        for (int k = 0; k < nchunk; ++k) {
+            cudaEventElapsedTime(&ms, tl[k].e[0], tl[k].e[1]); sum[0] += ms;      // H2D
+            cudaEventElapsedTime(&ms, tl[k].e[2], tl[k].e[3]); sum[1] += ms;      // fused kernel
+            cudaEventElapsedTime(&ms, tl[k].e[3], tl[k].e[4]); sum[2] += ms;      // pack kernels
+            cudaEventElapsedTime(&ms, tl[k].e[7], tl[k].e[5]); sum[3] += ms;      // push kernel (s_out)
+            cudaEventElapsedTime(&ms, tl[k].e[5], tl[k].e[6]); sum[4] += ms;      // copy-engine D2H (s_out)
+            hs += host_submit[k]; hw += host_wait[k];
+        }
+        cudaEventElapsedTime(&ms, tl[0].e[0], tl[nchunk - 1].e[6]);
+        const double host_loop = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+        fprintf(stderr, "[timeline] chunks %d  first H2D..last D2H %.2f ms | sums: h2d %.2f  fused %.2f  pack %.2f  push %.2f  d2h %.2f | "
+                "host: submit %.2f  finalize-wait %.2f  loop %.2f\n", nchunk, ms, sum[0], sum[1], sum[2], sum[3], sum[4], hs, hw, host_loop);
+        // gaps on s_run between chunks
+        double gap = 0;
+        for (int k = 1; k < nchunk; ++k) { cudaEventElapsedTime(&ms, tl[k - 1].e[4], tl[k].e[2]); gap += ms; }
+        fprintf(stderr, "[timeline] idle on the kernel stream between chunks: %.2f ms\n", gap);
     }
+    for (auto& t : tl) for (auto& e : t.e) cudaEventDestroy(e);
+#endif
+    if (packed) drain();
     CK(cudaStreamSynchronize(c->s_out));
     CK(cudaStreamSynchronize(c->s_run));
     CK(cudaStreamSynchronize(c->s_in));

@@ -66,6 +66,12 @@ cudaError_t launch_pack(int n_frames, int r3, const float* vol, unsigned* counts
 cudaError_t launch_pack_push(int n_frames, const float* lits, const unsigned long long* lit_off,
                              float* host_lits, cudaStream_t stream);
 
+// Host side of the codec (dtsdf_decode.cpp, plain C++): expands one packed frame (its r3/4 code bytes and
+// its slice of the literal stream) into the three channel planes at `out` (any 4-byte alignment;
+// whole-line non-temporal stores when `out` is 16-byte aligned).
+void decode_frame(const unsigned char* codes, const float* lits, size_t r3, float* out);
+const char* decode_isa();
+
 // kernels launched by this process (claimed in bench.py's gpu_launches)
 extern std::atomic<long long> g_launch_count;
 

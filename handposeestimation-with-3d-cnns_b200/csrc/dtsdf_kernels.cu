@@ -704,6 +704,14 @@ struct CtaShape {
     static constexpr int MIN_CTAS = 3;
 };
 
+#ifdef DTSDF_EXP_NW64             /* dev experiment: CTA shape of the R = 64 instantiations */
+template <int LAYOUT>
+struct CtaShape<64, LAYOUT> {
+    static constexpr int NW = DTSDF_EXP_NW64;
+    static constexpr int MIN_CTAS = 1;
+};
+#endif
+
 template <int R, int LAYOUT, bool DEFF>
 __global__ void __launch_bounds__(32 * CtaShape<R, LAYOUT>::NW, CtaShape<R, LAYOUT>::MIN_CTAS)
 dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
@@ -941,7 +949,11 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     // 2 CTAs/SM = 296 volumes = 116 MB -> 0.618 ms per 8,500 frames, 3 CTAs/SM = 174 MB -> 0.642 ms,
     // 1 CTA/SM -> 0.78 ms (nothing left to hide a frame's prologue).  So: at most as many CTAs per SM as
     // keep the footprint inside L2, but never fewer than two; the limit is imposed by padding the
-    // dynamic shared memory request.
+    // dynamic shared memory request.  Where not even two volumes per SM fit (R = 48, 64) the occupancy
+    // is whatever shared memory allows, except at R = 64: a frame's voxel loop is then so long (3.1 MB
+    // of stores) that its prologue no longer needs hiding and ONE CTA per SM is fastest - 4,000
+    // frames: 2.04 ms vs 2.26-2.30 ms with two or three (16 warps x 1: 2.14 ms; R = 48: 0.99 ms with
+    // one, two or three alike).
     {
         int occ = 0, sms = 0, l2 = 0, smem_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * NW, smem);
@@ -954,7 +966,11 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
         if (e != cudaSuccess) return e;
         const long long vol_bytes = 12ll * R * R * R;
         const int fit = (int)((long long)l2 / ((long long)sms * vol_bytes));
-        const int target = fit >= 2 ? std::min(occ, fit) : occ;
+#ifdef DTSDF_EXP_TARGET         /* dev experiment: force the number of CTAs per SM */
+        const int target = std::min(occ, DTSDF_EXP_TARGET);
+#else
+        const int target = fit >= 2 ? std::min(occ, fit) : (R >= 64 ? 1 : occ);
+#endif
         if (target >= 1 && target < occ) {
             // the largest request that still lets `target` CTAs share an SM (1 KB per CTA is reserved)
             long long padded = ((long long)smem_sm / target - 1024) & ~15ll;

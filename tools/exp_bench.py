@@ -12,28 +12,33 @@ EXP = os.path.join(ROOT, "tools", "_exp")
 def build(name, flags):
     import __graft_entry__ as g
     os.makedirs(EXP, exist_ok=True)
-    srcs = [os.path.join(g.CSRC, "dtsdf_kernels.cu"), os.path.join(g.CSRC, "dtsdf_capi.cu")]
-    cmd = [g._find("nvcc")] + g.NVCC_FLAGS + ["-DDTSDF_EXP_ONLY32"] + flags + srcs + ["-o", os.path.join(EXP, name + ".so")]
+    srcs = [os.path.join(g.CSRC, "dtsdf_kernels.cu"), os.path.join(g.CSRC, "dtsdf_capi.cu"),
+            os.path.join(g.CSRC, "dtsdf_decode.cpp")]
+    only32 = [] if "--all-res" in flags else ["-DDTSDF_EXP_ONLY32"]
+    flags = [f for f in flags if f != "--all-res"]
+    cmd = [g._find("nvcc")] + g.NVCC_FLAGS + only32 + flags + srcs + ["-o", os.path.join(EXP, name + ".so")]
     subprocess.run(cmd, check=True, cwd=ROOT)
 
 
 def run(names, frames=8500, steps=20):
     import numpy as np, torch
+    R = int(os.environ.get("EXP_RES", "32"))
+    frames = int(os.environ.get("EXP_FRAMES", frames))
     import __graft_entry__ as g
     pkg = g.load_package()
     box = tuple(int(v) for v in os.environ.get("EXP_BOX", "100,60,220,190").split(","))
     headers, depth = pkg.synth.make_uniform_batch(frames, seed0=1234, box=box)
     bw, bh = box[2] - box[0], box[3] - box[1]
-    alg = frames * (24 + 4 * bw * bh + 12 * 32 ** 3 + 16)
+    alg = frames * (24 + 4 * bw * bh + 12 * R ** 3 + 16)
     offsets, packed_len, max_px = pkg.capi.pack_plan(headers)
     dev = torch.device("cuda:0")
     d_packed = torch.from_numpy(depth.reshape(-1)).to(dev)
     d_off = torch.from_numpy(offsets).to(dev)
     d_hdr = torch.from_numpy(headers).to(dev)
-    d_vol = torch.empty((frames, 3, 32, 32, 32), dtype=torch.float32, device=dev)
+    d_vol = torch.empty((frames, 3, R, R, R), dtype=torch.float32, device=dev)
     d_ml = torch.empty((frames,), dtype=torch.float32, device=dev)
     d_mp = torch.empty((frames, 3), dtype=torch.float32, device=dev)
-    cfg = pkg.capi.default_config(32, 0, 0)
+    cfg = pkg.capi.default_config(R, 0, 0)
     max_px = int(os.environ.get('EXP_MAXPX', max_px))
     for name in names:
         path = os.path.join(EXP, name + ".so") if name != "main" else pkg.capi.LIB_PATH
@@ -58,7 +63,7 @@ def run(names, frames=8500, steps=20):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        print("%-28s %.4f ms/launch  %.2f M volumes/s  %.0f GB/s algorithmic (crop %dx%d)" % (name, ms, frames / ms / 1e3, alg / ms / 1e6, bw, bh), flush=True)
+        print("R=%d %-28s %.4f ms/launch  %.2f M volumes/s  %.0f GB/s algorithmic (crop %dx%d)" % (R, name, ms, frames / ms / 1e3, alg / ms / 1e6, bw, bh), flush=True)
 
 
 if __name__ == "__main__":
