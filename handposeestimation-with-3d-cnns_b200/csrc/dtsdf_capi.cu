@@ -549,6 +549,9 @@ void dtsdf_host_free(void* ptr) {
 
 // Host function behind a chunk's device -> host copies (packed mode): split the chunk's frames over the
 // expansion threads.  Runs on a CUDA-internal thread: no CUDA calls here.
+#ifdef DTSDF_EXP_TIMELINE
+static std::atomic<long long> g_tl_decode_us{0};
+#endif
 static void CUDART_CB expand_chunk_cb(void* p) {
     const dtsdf_ctx::ChunkRecord* r = static_cast<const dtsdf_ctx::ChunkRecord*>(p);
     dtsdf_ctx* c = r->ctx;
@@ -564,9 +567,15 @@ static void CUDART_CB expand_chunk_cb(void* p) {
     for (int j = 0; j < jobs; ++j) {
         const int32_t a0 = (int32_t)((int64_t)nf * j / jobs), a1 = (int32_t)((int64_t)nf * (j + 1) / jobs);
         c->pool.submit([=] {
+#ifdef DTSDF_EXP_TIMELINE
+            const auto j0 = std::chrono::steady_clock::now();
+#endif
 #ifndef DTSDF_EXP_SKIP_DECODE   /* dev ablation: the pipeline without the host expansion */
             for (int32_t f = a0; f < a1; ++f)
                 dtsdf::decode_frame(codes + (size_t)f * (r3 / 4), lits + 12 * loff[f], r3, dst + (size_t)f * vol_floats);
+#endif
+#ifdef DTSDF_EXP_TIMELINE
+            g_tl_decode_us += (long long)std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - j0).count();
 #endif
             latch->done();
         });
@@ -650,7 +659,11 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
 #ifdef DTSDF_EXP_TIMELINE
         const auto hk0 = std::chrono::steady_clock::now();
 #endif
+#ifdef DTSDF_EXP_DEPTH          /* dev experiment: fewer chunks in flight */
+        const int slot = k % DTSDF_EXP_DEPTH;
+#else
         const int slot = k % dtsdf_ctx::NSLOT;
+#endif
         const int32_t f0 = k * per_chunk;
         const int32_t nf = std::min(per_chunk, n_frames - f0);
         const int64_t e0 = h_off[f0];
@@ -668,8 +681,14 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
         // the slot's buffers are free once its previous chunk has left them: plain mode, its D2H
         // has finished (which implies its kernel has); packed mode, the host threads are done
         // expanding it (its kernels were waited for before they started)
+#ifdef DTSDF_EXP_TIMELINE
+        const auto hl0 = std::chrono::steady_clock::now();
+#endif
         if (packed) c->latch[slot].wait();
         else if (k >= dtsdf_ctx::NSLOT) CK(cudaEventSynchronize(c->ev_out[slot]));
+#ifdef DTSDF_EXP_TIMELINE
+        host_wait[k] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hl0).count();
+#endif
         auto fail = [&](int code) { if (packed) drain(); return code; };
         if ((rc = c->d_depth[slot].reserve((size_t)(e1 - e0) * 4)) != DTSDF_OK) return fail(rc);
         if ((rc = c->d_off[slot].reserve((size_t)nf * 8)) != DTSDF_OK) return fail(rc);
@@ -751,7 +770,6 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
             }
 #ifdef DTSDF_EXP_TIMELINE
             host_submit[k] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hk0).count();
-            host_wait[k] = 0.0;
 #endif
             continue;
         }
@@ -783,7 +801,7 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
         cudaEventElapsedTime(&ms, tl[0].e[0], tl[nchunk - 1].e[6]);
         const double host_loop = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
         fprintf(stderr, "[timeline] chunks %d  first H2D..last D2H %.2f ms | sums: h2d %.2f  fused %.2f  pack %.2f  push %.2f  d2h %.2f | "
-                "host: submit %.2f  finalize-wait %.2f  loop %.2f\n", nchunk, ms, sum[0], sum[1], sum[2], sum[3], sum[4], hs, hw, host_loop);
+                "host: submit (incl. slot wait) %.2f  slot wait %.2f  loop %.2f | expansion thread-time %.2f ms over %d threads\n", nchunk, ms, sum[0], sum[1], sum[2], sum[3], sum[4], hs, hw, host_loop, g_tl_decode_us.exchange(0) * 1e-3, nthreads);
         // gaps on s_run between chunks
         double gap = 0;
         for (int k = 1; k < nchunk; ++k) { cudaEventElapsedTime(&ms, tl[k - 1].e[4], tl[k].e[2]); gap += ms; }

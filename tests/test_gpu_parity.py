@@ -252,6 +252,31 @@ def test_packed_and_plain_host_transfer_agree():
     v.close()
 
 
+def test_host_pipeline_many_small_chunks_and_destination_alignments():
+    """The host pipeline hands chunks to the expansion threads from a stream host function and
+    reuses its NSLOT chunk buffers: 1 MB chunks (2 frames each, ~150 chunks through 4 slots),
+    repeated calls on one context, destinations at every 16-byte phase of a 64-byte line (the
+    AVX-512 expansion peels code bytes up to the line boundary) - always the device run's bits."""
+    frames = synth.make_frames(range(900, 900 + 301))
+    headers, offsets, packed = pack_simple(frames)
+    v = pkg.Voxelizer(device=0)
+    want = c_oracle.dtsdf_batch(headers, offsets, packed)[0]
+    v.set_option(pkg.capi.OPT_CHUNK_MB, 1)
+    n, vf = len(frames), 3 * 32 ** 3
+    raw = np.empty(n * vf + 64, dtype=np.float32)
+    base = (-raw.ctypes.data // 4) % 16                     # index of a 64-byte aligned float
+    for nthreads, phase in ((0, 0), (1, 4), (7, 8), (16, 12), (3, 0)):
+        v.set_option(pkg.capi.OPT_HOST_THREADS, nthreads)
+        dst = raw[base + phase: base + phase + n * vf].reshape(n, 3, 32, 32, 32)
+        assert dst.ctypes.data % 64 == 4 * phase
+        dst[...] = np.float32(7.0)
+        _, max_l, mid_p = v.voxelize_packed(headers, offsets, packed, out_vol=dst)
+        assert _same(dst, want)
+    v.set_option(pkg.capi.OPT_CHUNK_MB, 64)
+    assert _same(v.voxelize_packed(headers, offsets, packed)[0], want)
+    v.close()
+
+
 # ----------------------------------------------------------------------------- device-resident path
 def test_device_entry_point_matches_host_entry_point(vox):
     import torch
