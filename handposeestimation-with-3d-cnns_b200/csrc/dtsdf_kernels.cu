@@ -467,16 +467,27 @@ __device__ __forceinline__ void classify(float d, float vz, float t_far, float& 
     }
 }
 
-// Lane geometry of the voxel loop for an R^3 grid
+// Lane geometry of the voxel loop for an R^3 grid.  A warp's 32 / LPR rows lie along the slow axis
+// (SROWS of them) - except where an F-row is not a whole number of 128-byte lines (R = 48: 192 B):
+// there they are MROWS = 2 consecutive MIDDLE-axis rows, which are adjacent in memory, so that a warp
+// store still covers whole lines (2 x 192 B = 3 lines) and a row group is one contiguous slab.
+// (Measured: no faster than two slow-axis rows per warp - 2.09 ms per 8,500 frames either way, 0.88
+// of the copy peak at one, two or three CTAs per SM; the form is kept for the store rule alone.)
 template <int R, int NW>
 struct LaneMap {
     static constexpr int LPR = R / 4;               // lanes per F-row (groups of 4 voxels)
-    static constexpr int ROWS = 32 / LPR;           // slow-axis rows per warp
+    static constexpr int ROWS = 32 / LPR;           // rows per warp
+    static constexpr int MROWS = ((16 * LPR) % 128 != 0) ? ROWS : 1;   // of which along the middle axis
+    static constexpr int SROWS = ROWS / MROWS;      // and along the slow axis
     static constexpr int ACTIVE = ROWS * LPR;       // 32 for R = 32, 64; 24 for R = 48
-    static constexpr int NSG = R / ROWS;            // slow-axis row groups per frame
-    static constexpr int MSTEPS = R / NW;        // middle-axis positions per warp and row group
-    static_assert(R % 4 == 0 && R % ROWS == 0 && R % NW == 0, "unsupported grid size");
-    static_assert(R <= 64 && NSG <= 32, "work-list entries are 5 + 6 + 5 bits");
+    static constexpr int NSG = R / SROWS;           // slow-axis row groups per frame
+    static constexpr int MSTEPS = R / (NW * MROWS); // middle-axis steps per warp and row group
+    // work-list entry: lane (5 bits) | middle-axis step index mq = m / MROWS | row group sg
+    static constexpr int SG_SHIFT = (MROWS == 1) ? 11 : 10;
+    static constexpr int MQ_MASK = (1 << (SG_SHIFT - 5)) - 1;
+    static_assert(R % 4 == 0 && R % ROWS == 0 && R % (NW * MROWS) == 0, "unsupported grid size");
+    static_assert(R / MROWS <= MQ_MASK + 1 && NSG <= (1 << (16 - SG_SHIFT)), "work-list entries are 16 bits");
+    static_assert(R <= 64, "table and list sizes");
 };
 
 // pass 2: full evaluation of the n (<= 32) listed groups list[0..n)
@@ -491,8 +502,10 @@ __device__ __forceinline__ void eval_listed(const float* __restrict__ crop,
     const int lane = threadIdx.x & 31;
     if (lane < n) {
         const int ent = list[lane];
-        const int L = ent & 31, m = (ent >> 5) & 63, sg = ent >> 11;
-        const int s = sg * LM::ROWS + L / LM::LPR;
+        const int L = ent & 31, mq = (ent >> 5) & LM::MQ_MASK, sg = ent >> LM::SG_SHIFT;
+        const int r = L / LM::LPR;
+        const int s = sg * LM::SROWS + r / LM::MROWS;
+        const int m = mq * LM::MROWS + r % LM::MROWS;
         const int f0 = 4 * (L % LM::LPR);
         const int4 A = *reinterpret_cast<const int4*>(&sh->at[s * R + f0]);
         const int a4[4] = {A.x, A.y, A.z, A.w};
@@ -585,7 +598,8 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool active = lane < LM::ACTIVE;
     const int fg = lane % LM::LPR;
-    const int sr = active ? lane / LM::LPR : LM::ROWS - 1;
+    const int row = active ? lane / LM::LPR : LM::ROWS - 1;
+    const int sr = row / LM::MROWS, mr = row % LM::MROWS;
     const int f0 = 4 * fg;
     const float t_far = k.t_far;
     unsigned short* list = sh->list[warp];
@@ -597,17 +611,18 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
 
 #pragma unroll 1
     for (int sg = 0; sg < LM::NSG; ++sg) {
-        const int s = sg * LM::ROWS + sr;
+        const int s = sg * LM::SROWS + sr;
         const int4 A = *reinterpret_cast<const int4*>(&sh->at[s * R + f0]);
         if (LAYOUT != 0) {
             const float z1 = sh->vz[s];
             vzf = make_float4(z1, z1, z1, z1);
         }
         float* const obase = out + ((size_t)s * R * R + f0);
-        const int ebase = (sg << 11) | lane;
+        const int ebase = (sg << LM::SG_SHIFT) | lane;
 #pragma unroll
         for (int ks = 0; ks < LM::MSTEPS; ks += 2) {
-            const int m0 = warp + NW * ks, m1 = m0 + NW;
+            const int mq0 = warp + NW * ks, mq1 = mq0 + NW;                 // middle-axis steps
+            const int m0 = mq0 * LM::MROWS + mr, m1 = mq1 * LM::MROWS + mr;   // this lane's rows
             int4 B0, B1;
             if (LAYOUT == 0) {
                 B0 = *reinterpret_cast<const int4*>(&sh->yt[m0 * YS + f0]);
@@ -666,9 +681,9 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
                 float* p1 = obase + m1 * R;
                 st_f4(p1, v1); st_f4(p1 + CH, v1); st_f4(p1 + 2 * CH, v1);
             }
-            if (n0) list[cnt + __popc(bal0 & lt)] = (unsigned short)(ebase | (m0 << 5));
+            if (n0) list[cnt + __popc(bal0 & lt)] = (unsigned short)(ebase | (mq0 << 5));
             cnt += __popc(bal0);
-            if (n1) list[cnt + __popc(bal1 & lt)] = (unsigned short)(ebase | (m1 << 5));
+            if (n1) list[cnt + __popc(bal1 & lt)] = (unsigned short)(ebase | (mq1 << 5));
             cnt += __popc(bal1);
         }
 #ifdef DTSDF_EXP_NOPASS2
@@ -702,6 +717,13 @@ template <int R, int LAYOUT>
 struct CtaShape {
     static constexpr int NW = 8;
     static constexpr int MIN_CTAS = 3;
+};
+
+// R = 48: 24 middle-axis row pairs per row group; 12 warps take two each (the sweep is unrolled by two)
+template <int LAYOUT>
+struct CtaShape<48, LAYOUT> {
+    static constexpr int NW = 12;
+    static constexpr int MIN_CTAS = 2;
 };
 
 #ifdef DTSDF_EXP_NW64             /* dev experiment: CTA shape of the R = 64 instantiations */
