@@ -621,7 +621,14 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
 
     // packed device -> host transfer: the GPU packs each chunk into mapped pinned memory, host
     // threads expand it into h_vol while the next chunks are in flight
-    const bool packed = c->opt_packed != 0;
+    // Small batches go back as plain copies even when the packed transfer is on: its extra kernels,
+    // stream hand-offs and thread wake-ups cost more than they save below ~32 frames (one frame:
+    // 350 us packed, 110 us plain; 64 frames: 26 us per frame packed, 33 us plain).
+    const bool packed = c->opt_packed != 0 && (size_t)n_frames * vol_floats * 4 >= ((size_t)16 << 20);
+    // A single plain chunk needs no pipeline: everything on one stream, one synchronisation.
+    const bool single = !packed && nchunk == 1;
+    cudaStream_t const st_in = single ? c->s_run : c->s_in;
+    cudaStream_t const st_out = single ? c->s_run : c->s_out;
     const size_t r3 = R * R * R;
     c->stat_d2h_bytes = packed ? 0ll : (long long)n_frames * (long long)(vol_floats * 4 + (h_maxl ? 4 : 0) + (h_mid ? 12 : 0));
     int nthreads = 1;
@@ -710,17 +717,19 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
         // H2D on s_in.  `rebased` is pageable host memory: cudaMemcpyAsync stages it before
         // returning, so reusing the vector for the next chunk is safe.
         TLREC(0, c->s_in);
-        CK(cudaMemcpyAsync(c->d_depth[slot].p, h_depth + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, c->s_in));
-        CK(cudaMemcpyAsync(c->d_off[slot].p, rebased.data(), (size_t)nf * 8, cudaMemcpyHostToDevice, c->s_in));
-        CK(cudaMemcpyAsync(c->d_hdr[slot].p, h_hdr + 6 * (size_t)f0, (size_t)nf * 24, cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaMemcpyAsync(c->d_depth[slot].p, h_depth + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, st_in));
+        CK(cudaMemcpyAsync(c->d_off[slot].p, rebased.data(), (size_t)nf * 8, cudaMemcpyHostToDevice, st_in));
+        CK(cudaMemcpyAsync(c->d_hdr[slot].p, h_hdr + 6 * (size_t)f0, (size_t)nf * 24, cudaMemcpyHostToDevice, st_in));
         if (aux_w)
             CK(cudaMemcpyAsync(c->d_aux[slot].p, h_aux + (size_t)aux_w * f0, (size_t)nf * aux_w * 4,
-                               cudaMemcpyHostToDevice, c->s_in));
+                               cudaMemcpyHostToDevice, st_in));
         TLREC(1, c->s_in);
-        CK(cudaEventRecord(c->ev_in[slot], c->s_in));
+        if (!single) {
+            CK(cudaEventRecord(c->ev_in[slot], c->s_in));
+            CK(cudaStreamWaitEvent(c->s_run, c->ev_in[slot], 0));
+        }
 
         // kernel on s_run
-        CK(cudaStreamWaitEvent(c->s_run, c->ev_in[slot], 0));
         TLREC(2, c->s_run);
         rc = dtsdf_voxelize_batch(cfg, nf, (const float*)c->d_depth[slot].p, (const int64_t*)c->d_off[slot].p,
                                   (const int32_t*)c->d_hdr[slot].p, aux_w ? (const float*)c->d_aux[slot].p : nullptr,
@@ -773,17 +782,18 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
 #endif
             continue;
         }
-        CK(cudaEventRecord(c->ev_run[slot], c->s_run));
-
         // D2H on s_out
-        CK(cudaStreamWaitEvent(c->s_out, c->ev_run[slot], 0));
+        if (!single) {
+            CK(cudaEventRecord(c->ev_run[slot], c->s_run));
+            CK(cudaStreamWaitEvent(c->s_out, c->ev_run[slot], 0));
+        }
         CK(cudaMemcpyAsync(h_vol + (size_t)f0 * vol_floats, c->d_vol[slot].p, (size_t)nf * vol_floats * 4,
-                           cudaMemcpyDeviceToHost, c->s_out));
+                           cudaMemcpyDeviceToHost, st_out));
         if (h_maxl)
-            CK(cudaMemcpyAsync(h_maxl + f0, c->d_maxl[slot].p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->s_out));
+            CK(cudaMemcpyAsync(h_maxl + f0, c->d_maxl[slot].p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st_out));
         if (h_mid)
-            CK(cudaMemcpyAsync(h_mid + 3 * (size_t)f0, c->d_mid[slot].p, (size_t)nf * 12, cudaMemcpyDeviceToHost, c->s_out));
-        CK(cudaEventRecord(c->ev_out[slot], c->s_out));
+            CK(cudaMemcpyAsync(h_mid + 3 * (size_t)f0, c->d_mid[slot].p, (size_t)nf * 12, cudaMemcpyDeviceToHost, st_out));
+        if (!single) CK(cudaEventRecord(c->ev_out[slot], c->s_out));
     }
 #ifdef DTSDF_EXP_TIMELINE
     if (packed) {
@@ -810,9 +820,9 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
     for (auto& t : tl) for (auto& e : t.e) cudaEventDestroy(e);
 #endif
     if (packed) drain();
-    CK(cudaStreamSynchronize(c->s_out));
+    if (!single) CK(cudaStreamSynchronize(c->s_out));
     CK(cudaStreamSynchronize(c->s_run));
-    CK(cudaStreamSynchronize(c->s_in));
+    if (!single) CK(cudaStreamSynchronize(c->s_in));
     return DTSDF_OK;
 }
 

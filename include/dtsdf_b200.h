@@ -217,6 +217,8 @@ void dtsdf_ctx_destroy(dtsdf_ctx* ctx);
  *                          channels, literals for the rest: ~8x fewer PCIe bytes) written by the
  *                          GPU straight into mapped pinned memory, and expands them into the
  *                          caller's buffer with the host threads below (streaming stores).
+ *                          Batches whose volumes are under 16 MB always come back as plain
+ *                          copies (the packed route costs more than it saves there).
  *                          0: plain device->host copies of the float volumes.
  *   DTSDF_OPT_HOST_THREADS number of host threads for the expansion (default 0 = three quarters of
  *                          the hardware threads, at most 32). */

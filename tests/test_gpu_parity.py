@@ -277,6 +277,46 @@ def test_host_pipeline_many_small_chunks_and_destination_alignments():
     v.close()
 
 
+def test_joint_nor_module(tmp_path, monkeypatch):
+    # pre/joint_nor.py:8-18 (float64 there): normalize() and the result-tree walk of read_joint()
+    jn = import_pre("joint_nor")
+    rng = np.random.default_rng(11)
+    n = 37
+    gt = (rng.normal(size=(n, 21, 3)) * 60 + np.array([10, -20, -400])).astype(np.float32)
+    max_l = rng.uniform(120, 260, size=n)
+    mid_p = rng.normal(size=(n, 3)) * 30 + np.array([0, 0, -400.0])
+    want = np.stack([(gt[i].astype(np.float64) - mid_p[i]) / max_l[i] + 0.5 for i in range(n)])
+    got = jn.normalize(gt, max_l, mid_p)
+    assert got.shape == (n, 21, 3) and got.dtype == np.float64
+    assert np.abs(got - want).max() <= 1e-6
+    assert np.abs(jn.normalize(gt.reshape(n, 63), max_l, mid_p) - want.reshape(n, 63)).max() <= 1e-6
+    # read_joint(): <subject>/joint_nor/<gesture>.npy next to ground_truth/ and TSDF/
+    sub = tmp_path / "P0"
+    (sub / "ground_truth").mkdir(parents=True)
+    (sub / "TSDF").mkdir()
+    np.save(sub / "ground_truth" / "1.npy", gt)
+    np.savez(sub / "TSDF" / "1.npz", tsdf=np.zeros((n, 3, 2, 2, 2)), max_l=max_l, mid_p=mid_p)
+    monkeypatch.setattr(jn, "DATA_dir", str(tmp_path))
+    jn.read_joint()
+    assert np.abs(np.load(sub / "joint_nor" / "1.npy") - want).max() <= 1e-6
+
+
+def test_time_test_module(tmp_path, forloop_golden, capsys):
+    # pre/time_test.py:13-30: both entry points on one .bin frame, the reference's two printed lines
+    tt = import_pre("time_test")
+    c = forloop_golden[0]
+    raw = tmp_path / "000000_depth.bin"
+    with open(raw, "wb") as f:
+        f.write(np.asarray(c["header"], dtype=np.int32).tobytes())
+        f.write(np.asarray(c["depth"], dtype=np.float32).tobytes())
+    np.save(tmp_path / "pc.npy", c["pc"][None])
+    (t1, ml1, mp1), (t2, ml2, mp2) = tt.read_data(str(raw), str(tmp_path / "pc.npy"))
+    out = capsys.readouterr().out
+    assert "for loop time:" in out and "numba time:" in out
+    assert _same(t1, c["tsdf"]) and ml1 == c["max_l"]
+    assert t2.shape == (3, 32, 32, 32) and ml2 > 0
+
+
 # ----------------------------------------------------------------------------- device-resident path
 def test_device_entry_point_matches_host_entry_point(vox):
     import torch

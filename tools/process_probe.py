@@ -26,4 +26,20 @@ def draw():
     for _ in range(n):
         np.random.randint(0, 8811, size=6000)
 res["index_draw_only_per_s"] = rate(draw)
+# the per-frame drop-in calls, as the reference's own frame loop makes them (pre/read_MSRA.py:98-111, pre/time_test.py:27)
+sys.path.insert(0, os.path.join(g.PKG_DIR, "pre"))
+import process as dp_mod, tsdf_numba as tn_mod
+k = 300
+recs = [{"header": f["header"], "data": f["depth"]} for f in frames[:k]]
+tn_mod.cal_tsdf_cuda(recs[0])
+t0 = time.perf_counter()
+for r in recs:
+    tn_mod.cal_tsdf_cuda(r)
+res["cal_tsdf_cuda_single_frame_calls_per_s"] = k / (time.perf_counter() - t0)
+gt = np.zeros(63, dtype=np.float32)
+dp_mod.DataProcess(frames[0], gt, 6000, aug=False).process()
+t0 = time.perf_counter()
+for f in frames[:k]:
+    dp_mod.DataProcess(f, gt, 6000, aug=False).process()
+res["DataProcess_process_single_frame_calls_per_s"] = k / (time.perf_counter() - t0)
 print(json.dumps(res))
