@@ -1135,6 +1135,172 @@ __device__ __forceinline__ void xform(float px, float py, float pz, const float*
     }
 }
 
+// Per-frame constants of the augmented voxel loop.
+struct AugFrame {
+    const float* crop;            // staged (shared) or global crop
+    int l, t, bw, bh;
+    int cx, cy;
+    float focal, trunc, voxel_len, ox, oy, oz;
+    float t_far;                  // |v_z - w_z| above this forces the Euclidean truncation; +inf: no shortcut
+};
+
+template <int R, int LAYOUT>
+__device__ __forceinline__ void aug_group_index(int g, int& f0, int& m, int& s) {
+    constexpr int Q = R / 4;
+    f0 = 4 * (g % Q); m = (g / Q) % R; s = g / (Q * R);
+}
+
+// Voxel j of a group: augmented-frame centre va, camera-frame centre v, pixel, depth.
+// Returns false when the voxel stays 0 (projection not finite, outside the crop, |d| < 1).
+template <int R, int LAYOUT>
+__device__ __forceinline__ bool aug_lookup(const AugFrame& k, const float* __restrict__ Ainv,
+                                           const float* __restrict__ c, int f0, int m, int s, int j,
+                                           float (&va)[3], float (&v)[3], int& px, int& py, float& d) {
+    const int xi = LAYOUT == 0 ? s : f0 + j, yi = m, zi = LAYOUT == 0 ? f0 + j : s;
+    va[0] = __fadd_rn(k.ox, __fmul_rn((float)xi, k.voxel_len));
+    va[1] = __fadd_rn(k.oy, __fmul_rn((float)yi, k.voxel_len));
+    va[2] = __fadd_rn(k.oz, __fmul_rn((float)zi, k.voxel_len));
+    xform(va[0], va[1], va[2], Ainv, c, v);
+    const float coeff = __fdiv_rn(-k.focal, v[2]);
+    const float fpx = __fadd_rn(__fmul_rn(v[0], coeff), (float)k.cx);
+    const float fpy = __fadd_rn(__fmul_rn(-v[1], coeff), (float)k.cy);
+    // the specification drops |fp| >= 2e9 (or NaN) before int(): the conversion saturates, so anything
+    // that large falls outside the crop by itself; only NaN (which converts to 0) needs its own test
+    px = __float2int_rz(fpx);
+    py = __float2int_rz(fpy);
+    const unsigned ux = (unsigned)(px - k.l), uy = (unsigned)(py - k.t);
+    const float fs = __fadd_rn(fpx, fpy);
+    if (!(ux < (unsigned)k.bw && uy < (unsigned)k.bh && fs == fs)) return false;
+    d = k.crop[(int)uy * k.bw + (int)ux];
+    return !(fabsf(d) < 1.0f);
+}
+
+// Pass 1: every voxel of the group is 0, +-1 by the far-surface shortcut, or "near".
+template <int R, int LAYOUT>
+__device__ __forceinline__ bool aug_classify_group(const AugFrame& k, const float* __restrict__ Ainv,
+                                                   const float* __restrict__ c, int g, float4& val) {
+    int f0, m, s;
+    aug_group_index<R, LAYOUT>(g, f0, m, s);
+    float o[4];
+    bool near = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float va[3], v[3], d = 0.0f;
+        int px = 0, py = 0;
+        o[j] = 0.0f;
+        if (aug_lookup<R, LAYOUT>(k, Ainv, c, f0, m, s, j, va, v, px, py, d)) {
+            const float sz = __fadd_rn(v[2], d);                       // v_z - w_z, w_z = -d
+            if (fabsf(sz) > k.t_far && fabsf(d) < BIG_DEPTH)
+                o[j] = __int_as_float((__float_as_int(sz) & 0x80000000) | 0x3F800000);
+            else
+                near = true;
+        }
+    }
+    val = make_float4(o[0], o[1], o[2], o[3]);
+    return near;
+}
+
+// Pass 2: the specification's evaluation of all four voxels of a listed group, IEEE divisions.
+template <int R, int LAYOUT>
+__device__ __forceinline__ void aug_eval_group(const AugFrame& k, const float* __restrict__ A,
+                                               const float* __restrict__ Ainv, const float* __restrict__ c,
+                                               int g, float* __restrict__ out) {
+    constexpr int CH = R * R * R;
+    int f0, m, s;
+    aug_group_index<R, LAYOUT>(g, f0, m, s);
+    float o0[4], o1[4], o2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float va[3], v[3], d = 0.0f;
+        int px = 0, py = 0;
+        float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+        if (aug_lookup<R, LAYOUT>(k, Ainv, c, f0, m, s, j, va, v, px, py, d)) {
+            const float c1 = __fdiv_rn(d, k.focal);
+            float wa[3];
+            xform(__fmul_rn((float)(px - k.cx), c1), __fmul_rn((float)(-(py - k.cy)), c1), -d, A, c, wa);
+            t0 = __fdiv_rn(fabsf(__fsub_rn(va[0], wa[0])), k.trunc);
+            t1 = __fdiv_rn(fabsf(__fsub_rn(va[1], wa[1])), k.trunc);
+            t2 = __fdiv_rn(fabsf(__fsub_rn(va[2], wa[2])), k.trunc);
+            const float ss = __fadd_rn(__fadd_rn(__fmul_rn(t0, t0), __fmul_rn(t1, t1)), __fmul_rn(t2, t2));
+            // sqrt_rn(ss) > 1 <=> ss > nextafter(1,2); then min(t,1) is the identity below it,
+            // except for NaN (kept) - same as the specification's comparisons
+            if (ss > THR_SQ) { t0 = 1.0f; t1 = 1.0f; t2 = 1.0f; }
+            if (1.0f < t0) t0 = 1.0f;
+            if (1.0f < t1) t1 = 1.0f;
+            if (1.0f < t2) t2 = 1.0f;
+            if (-d > v[2]) { t0 = -t0; t1 = -t1; t2 = -t2; }
+        }
+        o0[j] = t0; o1[j] = t1; o2[j] = t2;
+    }
+    float* p = out + 4 * (size_t)g;
+    st_f4(p, make_float4(o0[0], o0[1], o0[2], o0[3]));
+    st_f4(p + CH, make_float4(o1[0], o1[1], o1[2], o1[3]));
+    st_f4(p + 2 * CH, make_float4(o2[0], o2[1], o2[2], o2[3]));
+}
+
+// Far-surface shortcut of the augmented path.  In exact arithmetic v' - w' = (v* - w) . A with v* the
+// exact preimage of the voxel centre v' under p -> (p - c).A + c, so |v' - w'| >= smin(A) |v* - w| >=
+// smin(A) (|v_z - w_z| - |v - v*|), where v = (v' - c).Ainv + c is what the specification projects and
+// |v - v*| <= |v' - c| |Ainv.A - I| / smin(A) accounts for a caller's Ainv that is not exactly A^-1.
+// Lower bound for smin(A): |det A| / (s1 s2) >= 2 |det A| / |A|_F^2.  If
+//     |v_z - w_z| > t_far = (trunc (1 + 2^-8) + slack) / smin_lo + drift
+// then |v' - w'| / trunc > 1 with a margin far above the float32 rounding of the specification's own
+// evaluation (slack: absolute rounding of coordinates of the frame's magnitude, 2^-17 relative; the
+// part of the rounding that grows with |d| is relative to |v_z - w_z| itself and below 2^-12 while
+// smin_lo > 2^-6 |A|_F, required here), so the Euclidean truncation fires and the voxel is +-1 by the
+// sign of v_z - w_z (pre/process.py:180-194).  Anything unusual (non-finite or huge entries, a nearly
+// singular A, tiny or huge trunc) switches the shortcut off: t_far = +inf.
+__device__ __forceinline__ float aug_far_threshold(const float* __restrict__ A, const float* __restrict__ Ainv,
+                                                   const float* __restrict__ c, float trunc, float max_l,
+                                                   float mid0, float mid1, float mid2) {
+    const float det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) +
+                      A[2] * (A[3] * A[7] - A[4] * A[6]);
+    float fa = 0.0f, fi = 0.0f, e = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { fa += A[i] * A[i]; fi += Ainv[i] * Ainv[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float p = Ainv[3 * i] * A[j] + Ainv[3 * i + 1] * A[3 + j] + Ainv[3 * i + 2] * A[6 + j];
+            e = fmaxf(e, fabsf(p - (i == j ? 1.0f : 0.0f)));
+        }
+    const float na = sqrtf(fa), ni = sqrtf(fi);
+    float smin_lo = 2.0f * fabsf(det) / fa * 0.999f;
+    {
+        // smallest eigenvalue of B = A^T A in closed form (trigonometric solution of the cubic); its
+        // float32 error is ~1e-6 of the LARGEST eigenvalue, so it is used only when it is at least
+        // 2^-6 of the trace (relative error then < 1e-4, covered by the factor 0.998)
+        const float b00 = A[0] * A[0] + A[3] * A[3] + A[6] * A[6], b11 = A[1] * A[1] + A[4] * A[4] + A[7] * A[7];
+        const float b22 = A[2] * A[2] + A[5] * A[5] + A[8] * A[8];
+        const float b01 = A[0] * A[1] + A[3] * A[4] + A[6] * A[7], b02 = A[0] * A[2] + A[3] * A[5] + A[6] * A[8];
+        const float b12 = A[1] * A[2] + A[4] * A[5] + A[7] * A[8];
+        const float q = (b00 + b11 + b22) * (1.0f / 3.0f);
+        const float p1 = b01 * b01 + b02 * b02 + b12 * b12;
+        const float p2 = (b00 - q) * (b00 - q) + (b11 - q) * (b11 - q) + (b22 - q) * (b22 - q) + 2.0f * p1;
+        float emin = q;
+        if (p2 > 1e-12f * q * q) {
+            const float pp = sqrtf(p2 * (1.0f / 6.0f)), ip = 1.0f / pp;
+            const float c00 = (b00 - q) * ip, c11 = (b11 - q) * ip, c22 = (b22 - q) * ip;
+            const float c01 = b01 * ip, c02 = b02 * ip, c12 = b12 * ip;
+            float r = 0.5f * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
+            r = fminf(1.0f, fmaxf(-1.0f, r));
+            const float phi = acosf(r) * (1.0f / 3.0f);
+            emin = q + 2.0f * pp * cosf(phi + 2.0943951023931953f);
+        }
+        if (emin > 0x1p-6f * 3.0f * q) smin_lo = fmaxf(smin_lo, sqrtf(emin) * 0.998f);
+    }
+    const float size = fabsf(c[0]) + fabsf(c[1]) + fabsf(c[2]) + fabsf(mid0) + fabsf(mid1) + fabsf(mid2) +
+                       2.0f * max_l + 1.0f;
+    const float reach = fabsf(mid0 - c[0]) + fabsf(mid1 - c[1]) + fabsf(mid2 - c[2]) + max_l;
+    const float drift = 3.0f * e * reach / smin_lo;
+    const float slack = 0x1p-17f * (1.0f + na) * (1.0f + ni) * size;
+    const float t_far = ((trunc * 1.00390625f + slack) / smin_lo + drift) * 1.001f;
+    const bool ok = smin_lo > 0x1p-6f * na && na < 0x1p10f && ni < 0x1p10f && size < 0x1p20f &&
+                    trunc >= 0x1p-20f && trunc <= 0x1p20f && e < 0x1p-10f && t_far < 0x1p30f;   // NaN -> false
+    return ok ? t_far : INFINITY;
+}
+
 template <int R, int LAYOUT>
 __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ BatchArgs a,
                                                        const float* __restrict__ aug_all) {
@@ -1163,10 +1329,10 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
 
     // ---- 1. bounding box of the augmented points of all valid pixels
     float mn[3] = {SENTINEL, SENTINEL, SENTINEL}, mx[3] = {-SENTINEL, -SENTINEL, -SENTINEL};
-    for (int pos = tid; pos < fr.n; pos += NT) {
-        const float d = crop[pos];
+    for (int row = warp; row < fr.bh; row += NWARP)
+    for (int col = lane; col < fr.bw; col += 32) {
+        const float d = crop[row * fr.bw + col];
         if (fabsf(d) < 1.0f) continue;
-        const int row = pos / fr.bw, col = pos - row * fr.bw;
         const float q = __fdiv_rn(d, focal);
         const float X = __fmul_rn(q, (float)(col + fr.l - a.center_x));
         const float Y = __fmul_rn(-q, (float)(row + fr.t - a.center_y));
@@ -1217,53 +1383,51 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
         }
     }
 
-    // ---- 3. voxel loop: a thread owns 4 consecutive voxels along the fastest output axis
-    constexpr int Q = R / 4, CH = R * R * R;
+    // ---- 3. voxel loop: a thread owns 4 consecutive voxels along the fastest output axis (a warp: 512
+    //      contiguous bytes per channel).  Two passes per warp as in the fused kernel: pass 1 classifies
+    //      (projection, lookup, far-surface shortcut) and stores the sectors that hold only 0 / +-1; groups
+    //      in sectors with near-surface voxels go to a per-warp list and are evaluated 32 at a time by
+    //      pass 2 with all lanes busy (the specification's arithmetic, IEEE divisions).
+    constexpr int CH = R * R * R;
+    static_assert((CH / 4) % NT == 0 && CH / 4 <= 65536, "groups per frame: whole warps, 16-bit list entries");
+    __shared__ unsigned short glist[NWARP][64];
+    AugFrame k;
+    k.crop = crop; k.l = fr.l; k.t = fr.t; k.bw = max(fr.bw, 0); k.bh = max(fr.bh, 0);   // bad header: empty crop
+    k.cx = a.center_x; k.cy = a.center_y; k.focal = focal; k.trunc = trunc; k.voxel_len = voxel_len;
+    k.ox = ox; k.oy = oy; k.oz = oz;
+    k.t_far = aug_far_threshold(A, Ainv, c, trunc, max_l, mid0, mid1, mid2);
     float* out = a.vol + (size_t)f * 3 * CH;
+    unsigned short* list = glist[warp];
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt = 0;
+#pragma unroll 1
     for (int g = tid; g < CH / 4; g += NT) {
-        const int f0 = 4 * (g % Q), m = (g / Q) % R, s = g / (Q * R);
-        float o0[4], o1[4], o2[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int xi = LAYOUT == 0 ? s : f0 + j, yi = m, zi = LAYOUT == 0 ? f0 + j : s;
-            const float vax = __fadd_rn(ox, __fmul_rn((float)xi, voxel_len));
-            const float vay = __fadd_rn(oy, __fmul_rn((float)yi, voxel_len));
-            const float vaz = __fadd_rn(oz, __fmul_rn((float)zi, voxel_len));
-            float v[3];
-            xform(vax, vay, vaz, Ainv, c, v);
-            const float coeff = __fdiv_rn(-focal, v[2]);
-            const float fpx = __fadd_rn(__fmul_rn(v[0], coeff), (float)a.center_x);
-            const float fpy = __fadd_rn(__fmul_rn(-v[1], coeff), (float)a.center_y);
-            float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
-            if (fabsf(fpx) < 2e9f && fabsf(fpy) < 2e9f) {
-                const int px = __float2int_rz(fpx), py = __float2int_rz(fpy);
-                if (px >= fr.l && px < fr.r && py >= fr.t && py < fr.b) {
-                    const float d = crop[(size_t)(py - fr.t) * fr.bw + (px - fr.l)];
-                    if (!(fabsf(d) < 1.0f)) {
-                        const float c1 = __fdiv_rn(d, focal);
-                        float wa[3];
-                        xform(__fmul_rn((float)(px - a.center_x), c1), __fmul_rn((float)(-(py - a.center_y)), c1), -d, A, c, wa);
-                        t0 = __fdiv_rn(fabsf(__fsub_rn(vax, wa[0])), trunc);
-                        t1 = __fdiv_rn(fabsf(__fsub_rn(vay, wa[1])), trunc);
-                        t2 = __fdiv_rn(fabsf(__fsub_rn(vaz, wa[2])), trunc);
-                        const float ss = __fadd_rn(__fadd_rn(__fmul_rn(t0, t0), __fmul_rn(t1, t1)), __fmul_rn(t2, t2));
-                        // sqrt_rn(ss) > 1 <=> ss > nextafter(1,2); then min(t,1) is the identity below it,
-                        // except for NaN (kept) - same as the specification's comparisons
-                        if (ss > THR_SQ) { t0 = 1.0f; t1 = 1.0f; t2 = 1.0f; }
-                        if (1.0f < t0) t0 = 1.0f;
-                        if (1.0f < t1) t1 = 1.0f;
-                        if (1.0f < t2) t2 = 1.0f;
-                        if (-d > v[2]) { t0 = -t0; t1 = -t1; t2 = -t2; }
-                    }
-                }
-            }
-            o0[j] = t0; o1[j] = t1; o2[j] = t2;
+        float4 val;
+        bool near = aug_classify_group<R, LAYOUT>(k, Ainv, c, g, val);
+        // a 32-byte sector (an even/odd lane pair) is written once, whole: by pass 1 or by pass 2
+        unsigned bal = __ballot_sync(FULL, near);
+        bal |= ((bal & 0x55555555u) << 1) | ((bal & 0xAAAAAAAAu) >> 1);
+        near = (bal >> lane) & 1u;
+        if (!near) {
+            float* p = out + 4 * (size_t)g;
+            st_f4(p, val); st_f4(p + CH, val); st_f4(p + 2 * CH, val);
+        } else {
+            list[cnt + __popc(bal & lt)] = (unsigned short)g;
         }
-        float* p = out + 4 * (size_t)g;
-        st_f4(p, make_float4(o0[0], o0[1], o0[2], o0[3]));
-        st_f4(p + CH, make_float4(o1[0], o1[1], o1[2], o1[3]));
-        st_f4(p + 2 * CH, make_float4(o2[0], o2[1], o2[2], o2[3]));
+        cnt += __popc(bal);
+        if (cnt >= 32) {
+            __syncwarp();
+            aug_eval_group<R, LAYOUT>(k, A, Ainv, c, (int)list[lane], out);
+            const int rem = cnt - 32;
+            unsigned short carry = 0;
+            if (lane < rem) carry = list[32 + lane];
+            __syncwarp();
+            if (lane < rem) list[lane] = carry;
+            cnt = rem;
+        }
     }
+    __syncwarp();
+    if (lane < cnt) aug_eval_group<R, LAYOUT>(k, A, Ainv, c, (int)list[lane], out);
 }
 
 template <int R, int LAYOUT>

@@ -488,6 +488,70 @@ def test_augmented_dtsdf_matches_its_specification(R, layout):
     assert 0.02 < float(np.mean((got != 0) & (np.abs(got) < 1))) < 0.5       # a real surface band is in there
 
 
+def test_augmented_dtsdf_unusual_transforms():
+    """The augmented kernel's far-surface shortcut must never change a result: transforms it was not
+    meant for - strong anisotropic stretch, a nearly singular A, an Ainv that is not the inverse of A,
+    a centre far from the hand, huge / tiny scales, NaN entries - and crops with huge, negative and
+    NaN depths, all bit for bit against the specification."""
+    import importlib
+    import torch
+    amod = importlib.import_module(pkg.__name__ + ".augment")
+    rng = np.random.default_rng(77)
+    base = synth.make_frames(range(1200, 1212))
+    mats = []
+
+    def rec(A, Ainv=None, c=(0, 0, 0)):
+        A = np.asarray(A, dtype=np.float64).reshape(3, 3)
+        Ainv = np.linalg.inv(A) if Ainv is None else np.asarray(Ainv, dtype=np.float64).reshape(3, 3)
+        return np.concatenate([A.reshape(-1), Ainv.reshape(-1), np.asarray(c, dtype=np.float64)]).astype(np.float32)
+
+    def rot(ax, deg):
+        t = np.deg2rad(deg)
+        cs, sn = np.cos(t), np.sin(t)
+        i, j = [(1, 2), (0, 2), (0, 1)][ax]
+        M = np.eye(3)
+        M[i, i], M[i, j], M[j, i], M[j, j] = cs, -sn, sn, cs
+        return M
+
+    mats.append(rec(np.diag([3.0, 0.3, 1.0]) @ rot(2, 50) @ rot(0, 35)))                 # strong stretch
+    mats.append(rec(np.diag([1.0, 1.0, 1e-3]) @ rot(1, 20)))                             # nearly singular
+    mats.append(rec(np.diag([1e-4, 1.0, 1.0])))                                          # nearly singular, axis-aligned
+    mats.append(rec(rot(2, 30), Ainv=rot(2, -25)))                                       # Ainv is not A^-1
+    mats.append(rec(np.diag([1.2, 0.8, 1.0]), Ainv=np.eye(3) * 1.5))                     # Ainv unrelated to A
+    mats.append(rec(rot(0, 20) @ rot(1, -15), c=(4000.0, -9000.0, 20000.0)))             # centre far away
+    mats.append(rec(rot(2, 10), c=(3e6, 0, -2e6)))                                       # centre beyond the guard
+    mats.append(rec(np.eye(3) * 900.0))                                                  # huge scale
+    mats.append(rec(np.eye(3) * 2e-3))                                                   # tiny scale
+    nanA = rec(rot(2, 15)); nanA[4] = np.nan
+    mats.append(nanA)                                                                    # NaN entry
+    mats.append(rec(np.diag([-1.0, 1.0, 1.0]) @ rot(2, 33), c=(5, -12, -370)))           # reflection
+    mats.append(rec(rot(0, 90) @ rot(2, 45), c=(5, -12, -370)))                          # depth axis swapped
+    frames = []
+    for i, f in enumerate(base):
+        d = f["depth"].copy()
+        if i % 4 == 1:
+            d[rng.integers(0, d.size, 40)] = 3e12                                        # beyond 2^40
+            d[rng.integers(0, d.size, 40)] = -500.0
+        if i % 4 == 2:
+            d[rng.integers(0, d.size, 25)] = np.nan
+        frames.append({"header": f["header"], "depth": d})
+    headers, offsets, packed = pack_simple(frames)
+    aug = np.stack(mats).astype(np.float32)
+    assert aug.shape == (len(frames), 21)
+    dev = torch.device("cuda:0")
+    for layout in (0, 1):
+        cfg = pkg.capi.default_config(32, layout, pkg.BBOX_PIXELS)
+        vol, ml, mp = amod.voxelize_aug_device(torch.from_numpy(packed).to(dev), torch.from_numpy(offsets).to(dev),
+                                               torch.from_numpy(headers).to(dev), torch.from_numpy(aug).to(dev),
+                                               130 * 150, cfg)
+        torch.cuda.synchronize()
+        cv, cml, cmp_ = c_oracle.dtsdf_aug_batch(headers, offsets, packed, aug, R=32, layout=layout)
+        assert _same(ml.cpu().numpy(), cml) and _same(mp.cpu().numpy(), cmp_)
+        got = vol.cpu().numpy()
+        for i in range(len(frames)):
+            assert _same(got[i], cv[i]), "frame %d layout %d" % (i, layout)
+
+
 def test_identity_augmentation_is_the_plain_path(vox):
     import importlib
     import torch
