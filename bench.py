@@ -49,7 +49,8 @@ def algorithmic_bytes(headers, R):
 def workload_config(args, world):
     return {
         "workload": "%s: %d synthetic MSRA-shaped frames per GPU, crop %dx%d, R=%d -> 3x%d^3 f32"
-                    % ("configs[1]" if (args.frames == FRAMES_PER_GPU and args.res == 32) else
+                    % ("ragged crops (80-150 x 80-140 px; the size below is the default, not used)" if args.ragged else
+                       "configs[1]" if (args.frames == FRAMES_PER_GPU and args.res == 32) else
                        ("configs[2] (full MSRA-sized set)" if args.frames * world >= 76000 else
                         ("configs[3] (resolution sweep)" if args.res != 32 else "custom size")),
                        args.frames, BOX[2] - BOX[0], BOX[3] - BOX[1], args.res, args.res),
@@ -281,13 +282,21 @@ def run_ours(args, rank, local_rank, world):
     R, F = args.res, args.frames
 
     # ---- workload: F fixed-shape synthetic frames per rank, in pinned host memory
-    headers, depth = pkg.synth.make_uniform_batch(F, seed0=1234 + 7919 * rank, box=BOX)
-    offsets, packed_len, max_px = capi.pack_plan(headers)
-    assert packed_len == depth.size
+    if args.ragged:
+        # every frame its own bounding box (80-150 x 80-140 px)
+        frames = pkg.synth.make_frames(range(100000 + F * rank, 100000 + F * (rank + 1)))
+        headers, offsets, depth, max_px = pkg.pack_frames(frames)
+        packed_len = depth.size
+        del frames
+    else:
+        headers, depth = pkg.synth.make_uniform_batch(F, seed0=1234 + 7919 * rank, box=BOX)
+        offsets, packed_len, max_px = capi.pack_plan(headers)
+        assert packed_len == depth.size
     h_packed = capi.PinnedBuffer(packed_len, np.float32)
     h_packed.array[:] = depth.reshape(-1)
     del depth
-    h_vol = capi.PinnedBuffer((F, 3, R, R, R), np.float32)
+    do_e2e = args.e2e_steps > 0
+    h_vol = capi.PinnedBuffer((F, 3, R, R, R), np.float32) if do_e2e else None
     h_maxl = capi.PinnedBuffer(F, np.float32)
     h_mid = capi.PinnedBuffer((F, 3), np.float32)
     alg_bytes = algorithmic_bytes(headers, R)
@@ -382,7 +391,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- end to end through the host entry point (pinned host buffers, H2D + kernel + D2H)
     vox = pkg.Voxelizer(device=local_rank, voxel_res=R)
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))       # (--e2e-steps 0 skips the end-to-end leg)
 
     def e2e_step():
         vox.voxelize_packed(headers, offsets, h_packed.array, layout=args.layout, bbox_mode=pkg.BBOX_PIXELS,
@@ -403,15 +412,17 @@ def run_ours(args, rank, local_rank, world):
 
     # plain device->host copies of the float volumes first (PCIe-bound), then the library's default:
     # volumes cross PCIe packed and are expanded into the host buffer by the host threads
-    vox.set_option(capi.OPT_PACKED_D2H, 0)
-    e2e_plain = time_e2e()
-    vox.set_option(capi.OPT_PACKED_D2H, 1)
-    e2e_value = time_e2e()
-    pcie_d2h = vox.stat(capi.STAT_D2H_BYTES)
-    # the e2e result is the real thing: compare with the device-resident run
-    ok = bool(np.array_equal(h_vol.array[:64], d_vol[:64].cpu().numpy()))
+    e2e_plain = e2e_value = pcie_d2h = ok = None
     h2d = int(h_packed.array.nbytes + headers.nbytes + offsets.nbytes)
-    d2h = int(h_vol.array.nbytes + h_maxl.array.nbytes + h_mid.array.nbytes)
+    d2h = int(F * 3 * R ** 3 * 4 + h_maxl.array.nbytes + h_mid.array.nbytes)
+    if do_e2e:
+        vox.set_option(capi.OPT_PACKED_D2H, 0)
+        e2e_plain = time_e2e()
+        vox.set_option(capi.OPT_PACKED_D2H, 1)
+        e2e_value = time_e2e()
+        pcie_d2h = vox.stat(capi.STAT_D2H_BYTES)
+        # the e2e result is the real thing: compare with the device-resident run
+        ok = bool(np.array_equal(h_vol.array[:64], d_vol[:64].cpu().numpy()))
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -423,7 +434,7 @@ def run_ours(args, rank, local_rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "dtsdf_voxelize_host (C ABI, pinned host buffers)",
+                    "steps": e2e_steps if do_e2e else 0, "api": "dtsdf_voxelize_host (C ABI, pinned host buffers)",
                     "matches_device_run": ok,
                     "transfer": "volumes packed on the GPU (2-bit codes + literals, lossless), written to mapped "
                                 "pinned memory, expanded into the caller's buffer by host threads",
@@ -469,7 +480,8 @@ def main():
     ap.add_argument("--res", type=int, default=32, choices=[32, 48, 64])
     ap.add_argument("--layout", type=int, default=0, choices=[0, 1], help="0 = (c,x,y,z), 1 = (c,z,y,x)")
     ap.add_argument("--gather", action="store_true", help="also time voxelise + gather of volumes to rank 0")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=10, help="0 skips the end-to-end leg (sizes beyond host memory)")
+    ap.add_argument("--ragged", action="store_true", help="every frame its own bounding box instead of 120x130")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
