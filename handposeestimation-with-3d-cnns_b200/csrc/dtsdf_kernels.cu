@@ -157,7 +157,7 @@ struct __align__(16) FrameShared {
     float red[NW][8];            // per-warp partial min xyz / max xyz (6 used)
     // per-warp work lists (groups with near-surface voxels): what one slow-axis row group can
     // add plus the remainder (< 32) carried over from the previous one
-    static constexpr int LIST_CAP = 32 + 32 * (R / NW);
+    static constexpr int LIST_CAP = 32 + ((32 % (R / 4)) != 0 ? 96 : 32 * (R / NW));   // 32 + LaneMap::BURST
     unsigned short list[NW][LIST_CAP];
     unsigned long long bar;         // crop TMA completion barrier
     unsigned int nanflag;           // the staged crop holds a NaN: take the unstaged path
@@ -467,27 +467,40 @@ __device__ __forceinline__ void classify(float d, float vz, float t_far, float& 
     }
 }
 
-// Lane geometry of the voxel loop for an R^3 grid.  A warp's 32 / LPR rows lie along the slow axis
-// (SROWS of them) - except where an F-row is not a whole number of 128-byte lines (R = 48: 192 B):
-// there they are MROWS = 2 consecutive MIDDLE-axis rows, which are adjacent in memory, so that a warp
-// store still covers whole lines (2 x 192 B = 3 lines) and a row group is one contiguous slab.
-// (Measured: no faster than two slow-axis rows per warp - 2.09 ms per 8,500 frames either way, 0.88
-// of the copy peak at one, two or three CTAs per SM; the form is kept for the store rule alone.)
+// Lane geometry of the voxel loop for an R^3 grid.
+//   Row map (R = 32, 64): lane = (slow-axis row, F-group); R/4 lanes cover one F-row, 32/(R/4) consecutive
+//   slow-axis rows share the warp, which sweeps the middle axis.
+//   Block map (R = 48, where an F-row is 12 groups and 32 lanes would cover 2.67 rows): the unit of work
+//   is a block of MB = 8 consecutive middle-axis rows of one slow-axis row = 96 groups = 1,536 contiguous
+//   bytes per channel, swept in T = 3 warp steps of 32 consecutive groups (512 B: whole lines, all lanes
+//   busy).  With the row map only 24 of 32 lanes work and pass 1 costs 1.33x the instructions per voxel:
+//   the R = 48 kernel was then SM-bound (0.88 of the copy peak at any occupancy, while its store-only
+//   ablation ran at 0.99), see DESIGN.md.
 template <int R, int NW>
 struct LaneMap {
     static constexpr int LPR = R / 4;               // lanes per F-row (groups of 4 voxels)
-    static constexpr int ROWS = 32 / LPR;           // rows per warp
-    static constexpr int MROWS = ((16 * LPR) % 128 != 0) ? ROWS : 1;   // of which along the middle axis
-    static constexpr int SROWS = ROWS / MROWS;      // and along the slow axis
-    static constexpr int ACTIVE = ROWS * LPR;       // 32 for R = 32, 64; 24 for R = 48
-    static constexpr int NSG = R / SROWS;           // slow-axis row groups per frame
-    static constexpr int MSTEPS = R / (NW * MROWS); // middle-axis steps per warp and row group
-    // work-list entry: lane (5 bits) | middle-axis step index mq = m / MROWS | row group sg
-    static constexpr int SG_SHIFT = (MROWS == 1) ? 11 : 10;
-    static constexpr int MQ_MASK = (1 << (SG_SHIFT - 5)) - 1;
-    static_assert(R % 4 == 0 && R % ROWS == 0 && R % (NW * MROWS) == 0, "unsupported grid size");
-    static_assert(R / MROWS <= MQ_MASK + 1 && NSG <= (1 << (16 - SG_SHIFT)), "work-list entries are 16 bits");
-    static_assert(R <= 64, "table and list sizes");
+    static constexpr bool BLOCKED = (32 % LPR) != 0;
+    static constexpr int ROWS = BLOCKED ? 1 : 32 / LPR;   // slow-axis rows per warp (row map)
+    static constexpr int ACTIVE = BLOCKED ? 32 : ROWS * LPR;
+    static constexpr int NSG = R / ROWS;            // slow-axis row groups per frame
+    static constexpr int MSTEPS = R / NW;           // middle-axis positions per warp and row group (row map)
+    static constexpr int MB = 8, T = (MB * LPR) / 32, NMB = R / MB;      // block map
+    // most list entries one step of the sweep can add
+    static constexpr int BURST = BLOCKED ? 32 * T : 32 * (R / NW);
+    static_assert(R % 4 == 0 && R % ROWS == 0 && R <= 64, "unsupported grid size");
+    static_assert(BLOCKED ? ((MB * LPR) % 32 == 0 && R % MB == 0 && LPR % 2 == 0 && LPR <= 16)
+                          : (R % NW == 0 && NSG <= 32), "work-list entries are 16 bits");
+    // work-list entry -> (slow-axis index s, middle-axis index m, first voxel f0 of the group)
+    __device__ static __forceinline__ void decode(int ent, int& s, int& m, int& f0) {
+        if (BLOCKED) {                              // s (6 bits) | m (6 bits) | F-group (4 bits)
+            s = ent >> 10; m = (ent >> 4) & 63; f0 = 4 * (ent & 15);
+        } else {                                    // row group (5 bits) | m (6 bits) | lane (5 bits)
+            const int L = ent & 31;
+            m = (ent >> 5) & 63;
+            s = (ent >> 11) * ROWS + L / LPR;
+            f0 = 4 * (L % LPR);
+        }
+    }
 };
 
 // pass 2: full evaluation of the n (<= 32) listed groups list[0..n)
@@ -502,11 +515,8 @@ __device__ __forceinline__ void eval_listed(const float* __restrict__ crop,
     const int lane = threadIdx.x & 31;
     if (lane < n) {
         const int ent = list[lane];
-        const int L = ent & 31, mq = (ent >> 5) & LM::MQ_MASK, sg = ent >> LM::SG_SHIFT;
-        const int r = L / LM::LPR;
-        const int s = sg * LM::SROWS + r / LM::MROWS;
-        const int m = mq * LM::MROWS + r % LM::MROWS;
-        const int f0 = 4 * (L % LM::LPR);
+        int s, m, f0;
+        LM::decode(ent, s, m, f0);
         const int4 A = *reinterpret_cast<const int4*>(&sh->at[s * R + f0]);
         const int a4[4] = {A.x, A.y, A.z, A.w};
         int b4[4], row4[4];
@@ -595,11 +605,11 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
     using LM = LaneMap<R, NW>;
     constexpr int YS = FrameShared<R, LAYOUT, NW>::YS;
     constexpr int CH = R * R * R;
+    static_assert(!LM::BLOCKED, "the block map has its own sweep (voxel_passes_blocked)");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool active = lane < LM::ACTIVE;
     const int fg = lane % LM::LPR;
-    const int row = active ? lane / LM::LPR : LM::ROWS - 1;
-    const int sr = row / LM::MROWS, mr = row % LM::MROWS;
+    const int sr = active ? lane / LM::LPR : LM::ROWS - 1;
     const int f0 = 4 * fg;
     const float t_far = k.t_far;
     unsigned short* list = sh->list[warp];
@@ -611,18 +621,17 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
 
 #pragma unroll 1
     for (int sg = 0; sg < LM::NSG; ++sg) {
-        const int s = sg * LM::SROWS + sr;
+        const int s = sg * LM::ROWS + sr;
         const int4 A = *reinterpret_cast<const int4*>(&sh->at[s * R + f0]);
         if (LAYOUT != 0) {
             const float z1 = sh->vz[s];
             vzf = make_float4(z1, z1, z1, z1);
         }
         float* const obase = out + ((size_t)s * R * R + f0);
-        const int ebase = (sg << LM::SG_SHIFT) | lane;
+        const int ebase = (sg << 11) | lane;
 #pragma unroll
         for (int ks = 0; ks < LM::MSTEPS; ks += 2) {
-            const int mq0 = warp + NW * ks, mq1 = mq0 + NW;                 // middle-axis steps
-            const int m0 = mq0 * LM::MROWS + mr, m1 = mq1 * LM::MROWS + mr;   // this lane's rows
+            const int m0 = warp + NW * ks, m1 = m0 + NW;
             int4 B0, B1;
             if (LAYOUT == 0) {
                 B0 = *reinterpret_cast<const int4*>(&sh->yt[m0 * YS + f0]);
@@ -681,9 +690,9 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
                 float* p1 = obase + m1 * R;
                 st_f4(p1, v1); st_f4(p1 + CH, v1); st_f4(p1 + 2 * CH, v1);
             }
-            if (n0) list[cnt + __popc(bal0 & lt)] = (unsigned short)(ebase | (mq0 << 5));
+            if (n0) list[cnt + __popc(bal0 & lt)] = (unsigned short)(ebase | (m0 << 5));
             cnt += __popc(bal0);
-            if (n1) list[cnt + __popc(bal1 & lt)] = (unsigned short)(ebase | (mq1 << 5));
+            if (n1) list[cnt + __popc(bal1 & lt)] = (unsigned short)(ebase | (m1 << 5));
             cnt += __popc(bal1);
         }
 #ifdef DTSDF_EXP_NOPASS2
@@ -692,6 +701,95 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
         // ---- pass 2 on whole batches (warp-uniform control flow)
         if (cnt >= 32) {
             __syncwarp();                 // list entries and the pass-1 stores are ordered before pass 2
+            int done = 0;
+            do {
+                eval_listed<R, LAYOUT, NW, STAGED, FAST, DEFF>(crop, sh, k, a, yf, out, list + done, 32);
+                done += 32;
+            } while (cnt - done >= 32);
+            const int rem = cnt - done;
+            unsigned short carry = 0;
+            if (lane < rem) carry = list[done + lane];
+            __syncwarp();
+            if (lane < rem) list[lane] = carry;
+            cnt = rem;
+        }
+    }
+    __syncwarp();
+    eval_listed<R, LAYOUT, NW, STAGED, FAST, DEFF>(crop, sh, k, a, yf, out, list, cnt);
+}
+
+// The same two passes with the block map (LaneMap::BLOCKED, R = 48).  Warp w takes the units
+// u = w, w + NW, ... with u = s * NMB + (block of 8 middle-axis rows); in step t of a unit lane l owns
+// group 32 t + l of the block: row (32 t + l) / LPR, F-group (32 t + l) % LPR - fixed per lane and step,
+// so the table rows at[s][f0..f0+3] are loaded once per unit and step.  Pass 2 runs at the end of a unit.
+template <int R, int LAYOUT, int NW, bool STAGED, bool FAST, bool DEFF>
+__device__ __forceinline__ void voxel_passes_blocked(const float* __restrict__ crop,
+                                                     FrameShared<R, LAYOUT, NW>* __restrict__ sh, const VoxConst& k,
+                                                     const BatchArgs& a, float yf, float* __restrict__ out) {
+    using LM = LaneMap<R, NW>;
+    constexpr int YS = FrameShared<R, LAYOUT, NW>::YS;
+    constexpr int CH = R * R * R;
+    constexpr int T = LM::T;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float t_far = k.t_far;
+    unsigned short* list = sh->list[warp];
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt = 0;
+    int rt[T], f0t[T];
+    float4 vzt[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const int gi = 32 * t + lane;
+        rt[t] = gi / LM::LPR;
+        f0t[t] = 4 * (gi % LM::LPR);
+        vzt[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (LAYOUT == 0) vzt[t] = *reinterpret_cast<const float4*>(&sh->vz[f0t[t]]);
+    }
+#pragma unroll 1
+    for (int u = warp; u < R * LM::NMB; u += NW) {
+        const int s = u / LM::NMB, m_base = (u - s * LM::NMB) * LM::MB;
+        float* const obase = out + (size_t)s * R * R;
+        float zs = 0.0f;
+        if (LAYOUT != 0) zs = sh->vz[s];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int m = m_base + rt[t], f0 = f0t[t];
+            const int4 A = *reinterpret_cast<const int4*>(&sh->at[s * R + f0]);
+            int4 B;
+            float4 vzf;
+            if (LAYOUT == 0) {
+                B = *reinterpret_cast<const int4*>(&sh->yt[m * YS + f0]);
+                vzf = vzt[t];
+            } else {
+                const int y0 = sh->yt[s * YS + m];
+                B = make_int4(y0, y0, y0, y0);
+                vzf = make_float4(zs, zs, zs, zs);
+            }
+            const float d0 = gather_depth<STAGED>(crop, A.x + B.x);
+            const float d1 = gather_depth<STAGED>(crop, A.y + B.y);
+            const float d2 = gather_depth<STAGED>(crop, A.z + B.z);
+            const float d3 = gather_depth<STAGED>(crop, A.w + B.w);
+            float4 v;
+            bool n = false;
+            classify<STAGED>(d0, vzf.x, t_far, v.x, n);
+            classify<STAGED>(d1, vzf.y, t_far, v.y, n);
+            classify<STAGED>(d2, vzf.z, t_far, v.z, n);
+            classify<STAGED>(d3, vzf.w, t_far, v.w, n);
+            // sectors (even/odd lane pairs: LPR is even, a pair never straddles rows) with near voxels
+            // are written by pass 2 only, whole
+            unsigned bal = __ballot_sync(FULL, n);
+            bal |= ((bal & 0x55555555u) << 1) | ((bal & 0xAAAAAAAAu) >> 1);
+            n = (bal >> lane) & 1u;
+            if (!n) {
+                float* p = obase + m * R + f0;
+                st_f4(p, v); st_f4(p + CH, v); st_f4(p + 2 * CH, v);
+            } else {
+                list[cnt + __popc(bal & lt)] = (unsigned short)((s << 10) | (m << 4) | (f0 >> 2));
+            }
+            cnt += __popc(bal);
+        }
+        if (cnt >= 32) {
+            __syncwarp();
             int done = 0;
             do {
                 eval_listed<R, LAYOUT, NW, STAGED, FAST, DEFF>(crop, sh, k, a, yf, out, list + done, 32);
@@ -719,10 +817,10 @@ struct CtaShape {
     static constexpr int MIN_CTAS = 3;
 };
 
-// R = 48: 24 middle-axis row pairs per row group; 12 warps take two each (the sweep is unrolled by two)
+// R = 48 (block map): 288 units of 8 middle-axis rows per frame, 36 per warp
 template <int LAYOUT>
 struct CtaShape<48, LAYOUT> {
-    static constexpr int NW = 12;
+    static constexpr int NW = 8;
     static constexpr int MIN_CTAS = 2;
 };
 
@@ -741,7 +839,7 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     using FS = FrameShared<R, LAYOUT, NW>;
     constexpr int YS = FS::YS;
     static_assert(sizeof(FS) % 16 == 0 && offsetof(FS, nodepth) + 16 == sizeof(FS), "the pad must touch the crop");
-    static_assert(LaneMap<R, NW>::MSTEPS % 2 == 0, "the sweep is unrolled by two");
+    static_assert(LaneMap<R, NW>::BLOCKED || LaneMap<R, NW>::MSTEPS % 2 == 0, "the sweep is unrolled by two");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FS* sh = reinterpret_cast<FS*>(smem_raw);
     float* crop_s = reinterpret_cast<float*>(smem_raw + sizeof(FS));
@@ -914,12 +1012,22 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     const bool staged = fr.staged && sh->nanflag == 0u;
 
     // ---- 3. voxel loop
-    if (fast) {
-        if (staged) voxel_passes<R, LAYOUT, NW, true, true, DEFF>(crop_s, sh, k, a, yf, out);
-        else        voxel_passes<R, LAYOUT, NW, false, true, DEFF>(fr.crop, sh, k, a, yf, out);
+    if constexpr (LaneMap<R, NW>::BLOCKED) {
+        if (fast) {
+            if (staged) voxel_passes_blocked<R, LAYOUT, NW, true, true, DEFF>(crop_s, sh, k, a, yf, out);
+            else        voxel_passes_blocked<R, LAYOUT, NW, false, true, DEFF>(fr.crop, sh, k, a, yf, out);
+        } else {
+            if (staged) voxel_passes_blocked<R, LAYOUT, NW, true, false, DEFF>(crop_s, sh, k, a, yf, out);
+            else        voxel_passes_blocked<R, LAYOUT, NW, false, false, DEFF>(fr.crop, sh, k, a, yf, out);
+        }
     } else {
-        if (staged) voxel_passes<R, LAYOUT, NW, true, false, DEFF>(crop_s, sh, k, a, yf, out);
-        else        voxel_passes<R, LAYOUT, NW, false, false, DEFF>(fr.crop, sh, k, a, yf, out);
+        if (fast) {
+            if (staged) voxel_passes<R, LAYOUT, NW, true, true, DEFF>(crop_s, sh, k, a, yf, out);
+            else        voxel_passes<R, LAYOUT, NW, false, true, DEFF>(fr.crop, sh, k, a, yf, out);
+        } else {
+            if (staged) voxel_passes<R, LAYOUT, NW, true, false, DEFF>(crop_s, sh, k, a, yf, out);
+            else        voxel_passes<R, LAYOUT, NW, false, false, DEFF>(fr.crop, sh, k, a, yf, out);
+        }
     }
 }
 
