@@ -601,7 +601,8 @@ __device__ __forceinline__ void eval_listed(const float* __restrict__ crop,
 template <int R, int LAYOUT, int NW, bool STAGED, bool FAST, bool DEFF>
 __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
                                              FrameShared<R, LAYOUT, NW>* __restrict__ sh, const VoxConst& k,
-                                             const BatchArgs& a, float yf, float* __restrict__ out) {
+                                             const BatchArgs& a, float yf, float* __restrict__ out,
+                                             int part, int nparts) {
     using LM = LaneMap<R, NW>;
     constexpr int YS = FrameShared<R, LAYOUT, NW>::YS;
     constexpr int CH = R * R * R;
@@ -620,7 +621,7 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
     if (LAYOUT == 0) vzf = *reinterpret_cast<const float4*>(&sh->vz[f0]);
 
 #pragma unroll 1
-    for (int sg = 0; sg < LM::NSG; ++sg) {
+    for (int sg = part * (LM::NSG / nparts), sg_end = sg + LM::NSG / nparts; sg < sg_end; ++sg) {
         const int s = sg * LM::ROWS + sr;
         const int4 A = *reinterpret_cast<const int4*>(&sh->at[s * R + f0]);
         if (LAYOUT != 0) {
@@ -725,7 +726,8 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
 template <int R, int LAYOUT, int NW, bool STAGED, bool FAST, bool DEFF>
 __device__ __forceinline__ void voxel_passes_blocked(const float* __restrict__ crop,
                                                      FrameShared<R, LAYOUT, NW>* __restrict__ sh, const VoxConst& k,
-                                                     const BatchArgs& a, float yf, float* __restrict__ out) {
+                                                     const BatchArgs& a, float yf, float* __restrict__ out,
+                                                     int part, int nparts) {
     using LM = LaneMap<R, NW>;
     constexpr int YS = FrameShared<R, LAYOUT, NW>::YS;
     constexpr int CH = R * R * R;
@@ -746,7 +748,8 @@ __device__ __forceinline__ void voxel_passes_blocked(const float* __restrict__ c
         if (LAYOUT == 0) vzt[t] = *reinterpret_cast<const float4*>(&sh->vz[f0t[t]]);
     }
 #pragma unroll 1
-    for (int u = warp; u < R * LM::NMB; u += NW) {
+    const int u_per_part = (R / nparts) * LM::NMB;       // whole slow-axis rows per part
+    for (int u = part * u_per_part + warp, u_end = (part + 1) * u_per_part; u < u_end; u += NW) {
         const int s = u / LM::NMB, m_base = (u - s * LM::NMB) * LM::MB;
         float* const obase = out + (size_t)s * R * R;
         float zs = 0.0f;
@@ -811,10 +814,22 @@ __device__ __forceinline__ void voxel_passes_blocked(const float* __restrict__ c
 // CTA shape: 8 warps, up to three CTAs per SM (80 registers, no spills).  16 warps x 2 CTAs/SM (64
 // registers) was measured as well: the same speed as 8 warps x 2 CTAs/SM - what counts is how many
 // frames are in flight, see launch_fused.
+// SPLIT: CTAs per frame.  A frame can be cut in SPLIT slabs along the slow axis, one CTA each (adjacent
+// block indices: the second crop load hits L2); every CTA redoes the cheap prologue (crop, bounding box,
+// tables), nothing is exchanged.  Measured per 4,000 frames: R = 48: 0.929 ms unsplit, 0.903 ms with
+// two or three CTAs per frame (kept: 2); R = 64: 2.04 ms unsplit at one CTA per SM, 2.22 ms with two
+// CTAs per frame, 2.10 ms with four (kept: 1 - fewer concurrent write streams win there).
+#ifndef DTSDF_EXP_SPLIT48
+#define DTSDF_EXP_SPLIT48 2
+#endif
+#ifndef DTSDF_EXP_SPLIT64
+#define DTSDF_EXP_SPLIT64 1
+#endif
 template <int R, int LAYOUT>
 struct CtaShape {
     static constexpr int NW = 8;
     static constexpr int MIN_CTAS = 3;
+    static constexpr int SPLIT = R == 64 ? DTSDF_EXP_SPLIT64 : 1;
 };
 
 // R = 48 (block map): 288 units of 8 middle-axis rows per frame, 36 per warp
@@ -822,6 +837,7 @@ template <int LAYOUT>
 struct CtaShape<48, LAYOUT> {
     static constexpr int NW = 8;
     static constexpr int MIN_CTAS = 2;
+    static constexpr int SPLIT = DTSDF_EXP_SPLIT48;
 };
 
 #ifdef DTSDF_EXP_NW64             /* dev experiment: CTA shape of the R = 64 instantiations */
@@ -829,6 +845,7 @@ template <int LAYOUT>
 struct CtaShape<64, LAYOUT> {
     static constexpr int NW = DTSDF_EXP_NW64;
     static constexpr int MIN_CTAS = 1;
+    static constexpr int SPLIT = DTSDF_EXP_SPLIT64;
 };
 #endif
 
@@ -840,11 +857,15 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     constexpr int YS = FS::YS;
     static_assert(sizeof(FS) % 16 == 0 && offsetof(FS, nodepth) + 16 == sizeof(FS), "the pad must touch the crop");
     static_assert(LaneMap<R, NW>::BLOCKED || LaneMap<R, NW>::MSTEPS % 2 == 0, "the sweep is unrolled by two");
+    static_assert(LaneMap<R, NW>::NSG % CtaShape<R, LAYOUT>::SPLIT == 0 && R % CtaShape<R, LAYOUT>::SPLIT == 0,
+                  "a frame splits into whole row groups");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FS* sh = reinterpret_cast<FS*>(smem_raw);
     float* crop_s = reinterpret_cast<float*>(smem_raw + sizeof(FS));
+    constexpr int SPLIT = CtaShape<R, LAYOUT>::SPLIT;
     const int tid = threadIdx.x;
-    const int f = blockIdx.x;
+    const int f = blockIdx.x / SPLIT, part = blockIdx.x % SPLIT;
+    const bool writer = part == 0;                    // max_l, mid_p, joints: once per frame
 
     // ---- 0. frame record; thread 0 starts the TMA bulk copy of the crop into shared memory
     const Frame fr = load_frame(a, f);
@@ -891,7 +912,7 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
         const float hl = __fmul_rn(voxel_len, 0.5f * (float)(R - 1));
         jmax_l = __fmul_rn(voxel_len, (float)R);
         jmid0 = __fadd_rn(ox, hl); jmid1 = __fadd_rn(oy, hl); jmid2 = __fadd_rn(oz, hl);
-        if (tid == 0) {
+        if (tid == 0 && writer) {
             if (a.max_l) a.max_l[f] = jmax_l;
             if (a.mid_p) {
                 a.mid_p[3 * (size_t)f + 0] = jmid0;
@@ -932,7 +953,7 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
         oy = __fadd_rn(__fsub_rn(mid1, half_l), half_v);
         oz = __fadd_rn(__fsub_rn(mid2, half_l), half_v);
         jmax_l = max_l; jmid0 = mid0; jmid1 = mid1; jmid2 = mid2;
-        if (tid == 0) {
+        if (tid == 0 && writer) {
             if (a.max_l) a.max_l[f] = max_l;
             if (a.mid_p) {
                 a.mid_p[3 * (size_t)f + 0] = mid0;
@@ -944,7 +965,7 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
 
     // ---- joint normalisation in the same launch: (gt - mid_p)/max_l + 0.5 in float32
     //      (pre/joint_nor.py:8-18; 3D_CNN/train.py:236-244 with the clamp)
-    if (a.joints != nullptr && tid < 63) {
+    if (a.joints != nullptr && tid < 63 && writer) {
         const int c = tid % 3;
         float g = __ldg(a.joints + 63 * (size_t)f + tid);
         if ((a.joint_flags & 2) && c == 2) g = -g;
@@ -1014,19 +1035,19 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     // ---- 3. voxel loop
     if constexpr (LaneMap<R, NW>::BLOCKED) {
         if (fast) {
-            if (staged) voxel_passes_blocked<R, LAYOUT, NW, true, true, DEFF>(crop_s, sh, k, a, yf, out);
-            else        voxel_passes_blocked<R, LAYOUT, NW, false, true, DEFF>(fr.crop, sh, k, a, yf, out);
+            if (staged) voxel_passes_blocked<R, LAYOUT, NW, true, true, DEFF>(crop_s, sh, k, a, yf, out, part, SPLIT);
+            else        voxel_passes_blocked<R, LAYOUT, NW, false, true, DEFF>(fr.crop, sh, k, a, yf, out, part, SPLIT);
         } else {
-            if (staged) voxel_passes_blocked<R, LAYOUT, NW, true, false, DEFF>(crop_s, sh, k, a, yf, out);
-            else        voxel_passes_blocked<R, LAYOUT, NW, false, false, DEFF>(fr.crop, sh, k, a, yf, out);
+            if (staged) voxel_passes_blocked<R, LAYOUT, NW, true, false, DEFF>(crop_s, sh, k, a, yf, out, part, SPLIT);
+            else        voxel_passes_blocked<R, LAYOUT, NW, false, false, DEFF>(fr.crop, sh, k, a, yf, out, part, SPLIT);
         }
     } else {
         if (fast) {
-            if (staged) voxel_passes<R, LAYOUT, NW, true, true, DEFF>(crop_s, sh, k, a, yf, out);
-            else        voxel_passes<R, LAYOUT, NW, false, true, DEFF>(fr.crop, sh, k, a, yf, out);
+            if (staged) voxel_passes<R, LAYOUT, NW, true, true, DEFF>(crop_s, sh, k, a, yf, out, part, SPLIT);
+            else        voxel_passes<R, LAYOUT, NW, false, true, DEFF>(fr.crop, sh, k, a, yf, out, part, SPLIT);
         } else {
-            if (staged) voxel_passes<R, LAYOUT, NW, true, false, DEFF>(crop_s, sh, k, a, yf, out);
-            else        voxel_passes<R, LAYOUT, NW, false, false, DEFF>(fr.crop, sh, k, a, yf, out);
+            if (staged) voxel_passes<R, LAYOUT, NW, true, false, DEFF>(crop_s, sh, k, a, yf, out, part, SPLIT);
+            else        voxel_passes<R, LAYOUT, NW, false, false, DEFF>(fr.crop, sh, k, a, yf, out, part, SPLIT);
         }
     }
 }
@@ -1099,7 +1120,9 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
 #ifdef DTSDF_EXP_TARGET         /* dev experiment: force the number of CTAs per SM */
         const int target = std::min(occ, DTSDF_EXP_TARGET);
 #else
-        const int target = fit >= 2 ? std::min(occ, fit) : (R >= 64 ? 1 : occ);
+        constexpr int SPLIT = CtaShape<R, LAYOUT>::SPLIT;
+        // (with SPLIT CTAs per frame, SPLIT CTAs per SM are one volume per SM under construction)
+        const int target = fit >= 2 ? std::min(occ, fit) : (R >= 64 ? std::min(occ, SPLIT) : occ);
 #endif
         if (target >= 1 && target < occ) {
             // the largest request that still lets `target` CTAs share an SM (1 KB per CTA is reserved)
@@ -1109,7 +1132,7 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
         }
         args.cap_floats = (int)((smem - (size_t)fixed) / 4) & ~3;      // the padding stages larger crops for free
     }
-    kern<<<(unsigned)args.n_frames, (32 * NW), smem, stream>>>(args);      // one CTA per frame
+    kern<<<(unsigned)args.n_frames * CtaShape<R, LAYOUT>::SPLIT, (32 * NW), smem, stream>>>(args);   // SPLIT CTAs per frame
     ++g_launch_count;
     return cudaGetLastError();
 }
