@@ -133,12 +133,15 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(res, layout):
-    """dram bytes per launch of the fused kernel from the committed ncu capture, if any."""
+def ncu_traffic(res, layout, frames):
+    """dram bytes per launch of the fused kernel from the committed ncu capture, if any, scaled from the
+    capture's frame count to this run's (the traffic is per frame: fixed-shape crops)."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
-        d = json.load(open(p))
-        return d.get("R%d_L%d" % (res, layout), {}).get("dram_bytes_per_launch")
+        e = json.load(open(p)).get("R%d_L%d" % (res, layout))
+        if not e:
+            return None
+        return e["dram_bytes_per_launch"] * frames / float(e.get("frames", frames))
     except Exception:
         return None
 
@@ -441,7 +444,7 @@ def run_ours(args, rank, local_rank, world):
                     "d2h_bytes_on_pcie_per_step": pcie_d2h, "plain_copy_value": e2e_plain},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(R, args.layout),
+                         "frac": achieved / peak, "traffic": None if args.ragged else ncu_traffic(R, args.layout, F),
                          "peak_source": peak_src, "kernel": "dtsdf_fused_kernel<%d,%d>" % (R, args.layout),
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kernel_s * 1e3},
             "clocks": sampler.summary(),
