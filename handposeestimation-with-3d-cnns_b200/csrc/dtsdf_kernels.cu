@@ -157,7 +157,9 @@ struct __align__(16) FrameShared {
     float red[NW][8];            // per-warp partial min xyz / max xyz (6 used)
     // per-warp work lists (groups with near-surface voxels): what one slow-axis row group can
     // add plus the remainder (< 32) carried over from the previous one
-    static constexpr int LIST_CAP = 32 + ((32 % (R / 4)) != 0 ? 96 : 32 * (R / NW));   // 32 + LaneMap::BURST
+    // a carried remainder (< 32) plus what one step of the sweep can add: a unit of the block map
+    // (96 groups) or one slow-axis row group of the row map
+    static constexpr int LIST_CAP = 32 + ((32 % (R / 4)) != 0 ? 96 : 32 * (R / NW));
     unsigned short list[NW][LIST_CAP];
     unsigned long long bar;         // crop TMA completion barrier
     unsigned int nanflag;           // the staged crop holds a NaN: take the unstaged path
@@ -485,8 +487,6 @@ struct LaneMap {
     static constexpr int NSG = R / ROWS;            // slow-axis row groups per frame
     static constexpr int MSTEPS = R / NW;           // middle-axis positions per warp and row group (row map)
     static constexpr int MB = 8, T = (MB * LPR) / 32, NMB = R / MB;      // block map
-    // most list entries one step of the sweep can add
-    static constexpr int BURST = BLOCKED ? 32 * T : 32 * (R / NW);
     static_assert(R % 4 == 0 && R % ROWS == 0 && R <= 64, "unsupported grid size");
     static_assert(BLOCKED ? ((MB * LPR) % 32 == 0 && R % MB == 0 && LPR % 2 == 0 && LPR <= 16)
                           : (R % NW == 0 && NSG <= 32), "work-list entries are 16 bits");
@@ -747,8 +747,8 @@ __device__ __forceinline__ void voxel_passes_blocked(const float* __restrict__ c
         vzt[t] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (LAYOUT == 0) vzt[t] = *reinterpret_cast<const float4*>(&sh->vz[f0t[t]]);
     }
-#pragma unroll 1
     const int u_per_part = (R / nparts) * LM::NMB;       // whole slow-axis rows per part
+#pragma unroll 1
     for (int u = part * u_per_part + warp, u_end = (part + 1) * u_per_part; u < u_end; u += NW) {
         const int s = u / LM::NMB, m_base = (u - s * LM::NMB) * LM::MB;
         float* const obase = out + (size_t)s * R * R;
