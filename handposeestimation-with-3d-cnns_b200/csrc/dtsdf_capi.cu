@@ -558,7 +558,7 @@ static void CUDART_CB expand_chunk_cb(void* p) {
     const unsigned char* codes = (const unsigned char*)c->m_codes[r->slot].p;
     const unsigned long long* loff = (const unsigned long long*)c->m_loff[r->slot].p;
     const float* lits = (const float*)c->m_lits[r->slot].p;
-    c->stat_d2h_bytes += r->fixed_bytes + 48ll * (long long)loff[r->nf];
+    c->stat_d2h_bytes += r->fixed_bytes + 12ll * (long long)loff[r->nf];
     Latch* latch = &c->latch[r->slot];
     const int32_t nf = r->nf;
     const int jobs = r->jobs;
@@ -572,7 +572,8 @@ static void CUDART_CB expand_chunk_cb(void* p) {
 #endif
 #ifndef DTSDF_EXP_SKIP_DECODE   /* dev ablation: the pipeline without the host expansion */
             for (int32_t f = a0; f < a1; ++f)
-                dtsdf::decode_frame(codes + (size_t)f * (r3 / 4), lits + 12 * loff[f], r3, dst + (size_t)f * vol_floats);
+                dtsdf::decode_frame(codes + (size_t)f * (r3 / 4), lits + 3 * loff[f], (size_t)(loff[f + 1] - loff[f]), r3,
+                                    dst + (size_t)f * vol_floats);
 #endif
 #ifdef DTSDF_EXP_TIMELINE
             g_tl_decode_us += (long long)std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - j0).count();

@@ -8,8 +8,8 @@
 // write-combining buffers never hold a partial line when the next plane's line is opened.
 //
 // Codes: voxel 4k+j of the frame sits in bits 2j..2j+1 of byte k: 0 = (+0,+0,+0), 1 = (+1,+1,+1),
-// 2 = (-1,-1,-1), 3 = literal.  A byte that holds a 3 is a literal group: its 3 x 4 floats
-// (x[4], y[4], z[4]) are the next 48 bytes of the frame's literal stream (16-byte aligned).
+// 2 = (-1,-1,-1), 3 = literal.  The frame's literal block holds, for its nlit literal voxels in voxel
+// order, x[nlit], then y[nlit], then z[nlit] (floats, 4-byte aligned).
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
@@ -30,26 +30,38 @@ struct DecodeTables {
 };
 const DecodeTables g_dec;
 
-inline bool has_literal(unsigned byte) { return (byte & (byte >> 1) & 0x55u) != 0u; }
+inline unsigned literal_mask(unsigned byte) { return byte & (byte >> 1) & 0x55u; }   // bit 2j: voxel j is a literal
+
+// the three running literal streams of a frame
+struct Lits {
+    const float* x;
+    const float* y;
+    const float* z;
+};
+
+// one code byte (4 voxels) -> one 128-bit vector per plane
+inline void expand_byte(unsigned b, Lits& l, __m128& x, __m128& y, __m128& z) {
+    x = y = z = _mm_load_ps(g_dec.val[b]);
+    const unsigned m = literal_mask(b);
+    if (m) {
+        alignas(16) float xv[4], yv[4], zv[4];
+        _mm_store_ps(xv, x); _mm_store_ps(yv, x); _mm_store_ps(zv, x);
+        for (int j = 0; j < 4; ++j)
+            if ((m >> (2 * j)) & 1u) { xv[j] = *l.x++; yv[j] = *l.y++; zv[j] = *l.z++; }
+        x = _mm_load_ps(xv); y = _mm_load_ps(yv); z = _mm_load_ps(zv);
+    }
+}
 
 // ---- baseline x86-64 (SSE2), 64-byte aligned output: 16 voxels (4 code bytes) -> one line per
 // plane, plane after plane
 template <bool NT>
-void decode_sse2(const unsigned char* codes, const float* lits, size_t r3, float* out) {
+void decode_sse2(const unsigned char* codes, Lits l, size_t r3, float* out) {
     float* o0 = out;
     float* o1 = out + r3;
     float* o2 = out + 2 * r3;
     for (size_t k = 0; k < r3 / 4; k += 4) {
         __m128 x[4], y[4], z[4];
-        for (int j = 0; j < 4; ++j) {
-            const unsigned b = codes[k + j];
-            if (!has_literal(b)) {
-                x[j] = y[j] = z[j] = _mm_load_ps(g_dec.val[b]);
-            } else {
-                x[j] = _mm_load_ps(lits); y[j] = _mm_load_ps(lits + 4); z[j] = _mm_load_ps(lits + 8);
-                lits += 12;
-            }
-        }
+        for (int j = 0; j < 4; ++j) expand_byte(codes[k + j], l, x[j], y[j], z[j]);
         if (NT) {
             for (int j = 0; j < 4; ++j) _mm_stream_ps(o0 + 4 * (k + j), x[j]);
             for (int j = 0; j < 4; ++j) _mm_stream_ps(o1 + 4 * (k + j), y[j]);
@@ -65,43 +77,37 @@ void decode_sse2(const unsigned char* codes, const float* lits, size_t r3, float
 
 // one code byte (4 voxels) -> 16 bytes per plane; for outputs whose lines cannot be written whole
 template <bool NT>
-inline const float* decode_byte(unsigned b, const float* lits, float* o0, float* o1, float* o2) {
+inline void decode_byte(unsigned b, Lits& l, float* o0, float* o1, float* o2) {
     __m128 x, y, z;
-    if (!has_literal(b)) {
-        x = y = z = _mm_load_ps(g_dec.val[b]);
-    } else {
-        x = _mm_load_ps(lits); y = _mm_load_ps(lits + 4); z = _mm_load_ps(lits + 8);
-        lits += 12;
-    }
+    expand_byte(b, l, x, y, z);
     if (NT) { _mm_stream_ps(o0, x); _mm_stream_ps(o1, y); _mm_stream_ps(o2, z); }
     else { _mm_storeu_ps(o0, x); _mm_storeu_ps(o1, y); _mm_storeu_ps(o2, z); }
-    return lits;
 }
 
 template <bool NT>
-void decode_bytes(const unsigned char* codes, const float* lits, size_t r3, float* out) {
+void decode_bytes(const unsigned char* codes, Lits l, size_t r3, float* out) {
     for (size_t k = 0; k < r3 / 4; ++k)
-        lits = decode_byte<NT>(codes[k], lits, out + 4 * k, out + r3 + 4 * k, out + 2 * r3 + 4 * k);
+        decode_byte<NT>(codes[k], l, out + 4 * k, out + r3 + 4 * k, out + 2 * r3 + 4 * k);
     if (NT) _mm_sfence();
 }
 
-// ---- AVX-512F: 16 two-bit codes -> 16 floats with one variable shift + one permute; literal groups
-// are inserted as 128-bit lanes; one 512-bit store per plane and line
+// ---- AVX-512F: 16 two-bit codes -> 16 floats with one variable shift + one permute; the literal
+// voxels of the line are filled in by a masked expand-load per plane; one 512-bit store per plane and line
 template <bool NT>
 __attribute__((target("avx512f")))
-void decode_avx512(const unsigned char* codes, const float* lits, size_t r3, float* out) {
+void decode_avx512(const unsigned char* codes, Lits l, size_t r3, float* out) {
     float* o0 = out;
     float* o1 = out + r3;
     float* o2 = out + 2 * r3;
     const __m512 table = _mm512_setr_ps(0.0f, 1.0f, -1.0f, 0.0f, 0.0f, 1.0f, -1.0f, 0.0f,
                                         0.0f, 1.0f, -1.0f, 0.0f, 0.0f, 1.0f, -1.0f, 0.0f);
     const __m512i shifts = _mm512_setr_epi32(0, 2, 4, 6, 8, 10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30);
+    const __m512i three = _mm512_set1_epi32(3);
     const size_t nb = r3 / 4;                    // code bytes: 4 voxels, 16 output bytes per plane each
     // NT: `out` is 16-byte aligned; peel code bytes until the planes reach a 64-byte boundary (all
     // three at once: a plane is a multiple of 64 bytes), the 32-bit code words are then read unaligned
     size_t k0 = NT ? (((64 - (reinterpret_cast<uintptr_t>(out) & 63)) & 63) / 16) : 0;
-    for (size_t b = 0; b < k0; ++b)
-        lits = decode_byte<NT>(codes[b], lits, o0 + 4 * b, o1 + 4 * b, o2 + 4 * b);
+    for (size_t b = 0; b < k0; ++b) decode_byte<NT>(codes[b], l, o0 + 4 * b, o1 + 4 * b, o2 + 4 * b);
     const size_t nw = (nb - k0) / 4;             // whole 32-bit code words: 16 voxels = one line per plane
     codes += k0; o0 += 4 * k0; o1 += 4 * k0; o2 += 4 * k0;
     for (size_t k = 0; k < nw; ++k) {
@@ -112,22 +118,12 @@ void decode_avx512(const unsigned char* codes, const float* lits, size_t r3, flo
         __m512 y = x, z = x;
         const uint32_t lit = w & (w >> 1) & 0x55555555u;
         if (lit) {
-            if (lit & 0x000000FFu) {
-                x = _mm512_insertf32x4(x, _mm_load_ps(lits), 0); y = _mm512_insertf32x4(y, _mm_load_ps(lits + 4), 0);
-                z = _mm512_insertf32x4(z, _mm_load_ps(lits + 8), 0); lits += 12;
-            }
-            if (lit & 0x0000FF00u) {
-                x = _mm512_insertf32x4(x, _mm_load_ps(lits), 1); y = _mm512_insertf32x4(y, _mm_load_ps(lits + 4), 1);
-                z = _mm512_insertf32x4(z, _mm_load_ps(lits + 8), 1); lits += 12;
-            }
-            if (lit & 0x00FF0000u) {
-                x = _mm512_insertf32x4(x, _mm_load_ps(lits), 2); y = _mm512_insertf32x4(y, _mm_load_ps(lits + 4), 2);
-                z = _mm512_insertf32x4(z, _mm_load_ps(lits + 8), 2); lits += 12;
-            }
-            if (lit & 0xFF000000u) {
-                x = _mm512_insertf32x4(x, _mm_load_ps(lits), 3); y = _mm512_insertf32x4(y, _mm_load_ps(lits + 4), 3);
-                z = _mm512_insertf32x4(z, _mm_load_ps(lits + 8), 3); lits += 12;
-            }
+            const __mmask16 m = _mm512_cmpeq_epi32_mask(_mm512_and_si512(idx, three), three);
+            x = _mm512_mask_expandloadu_ps(x, m, l.x);
+            y = _mm512_mask_expandloadu_ps(y, m, l.y);
+            z = _mm512_mask_expandloadu_ps(z, m, l.z);
+            const int n = __builtin_popcount(lit);
+            l.x += n; l.y += n; l.z += n;
         }
         if (NT) {
             _mm512_stream_ps(o0 + 16 * k, x); _mm512_stream_ps(o1 + 16 * k, y); _mm512_stream_ps(o2 + 16 * k, z);
@@ -136,7 +132,7 @@ void decode_avx512(const unsigned char* codes, const float* lits, size_t r3, flo
         }
     }
     for (size_t b = 4 * nw; b < nb - k0; ++b)     // the bytes after the last whole word (k0 != 0 only)
-        lits = decode_byte<NT>(codes[b], lits, o0 + 4 * b, o1 + 4 * b, o2 + 4 * b);
+        decode_byte<NT>(codes[b], l, o0 + 4 * b, o1 + 4 * b, o2 + 4 * b);
     if (NT) _mm_sfence();
 }
 
@@ -156,17 +152,18 @@ const char* decode_isa() { return cpu_has_avx512f() ? "avx512f" : "sse2"; }
 
 // r3 = R^3 is a multiple of 16 (R is a multiple of 4... 32, 48, 64), so the planes of a frame share
 // the alignment of `out`.
-void decode_frame(const unsigned char* codes, const float* lits, size_t r3, float* out) {
+void decode_frame(const unsigned char* codes, const float* lits, size_t nlit, size_t r3, float* out) {
+    const Lits l = {lits, lits + nlit, lits + 2 * nlit};
     const uintptr_t a = reinterpret_cast<uintptr_t>(out);
     if (cpu_has_avx512f()) {
-        if ((a & 15) == 0) decode_avx512<true>(codes, lits, r3, out);
-        else decode_avx512<false>(codes, lits, r3, out);
+        if ((a & 15) == 0) decode_avx512<true>(codes, l, r3, out);
+        else decode_avx512<false>(codes, l, r3, out);
     } else if ((a & 63) == 0) {
-        decode_sse2<true>(codes, lits, r3, out);
+        decode_sse2<true>(codes, l, r3, out);
     } else if ((a & 15) == 0) {
-        decode_bytes<true>(codes, lits, r3, out);
+        decode_bytes<true>(codes, l, r3, out);
     } else {
-        decode_bytes<false>(codes, lits, r3, out);
+        decode_bytes<false>(codes, l, r3, out);
     }
 }
 

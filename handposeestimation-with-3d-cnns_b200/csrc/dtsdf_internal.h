@@ -52,24 +52,26 @@ cudaError_t launch_normalize_joints(int n_frames, const float* joints, const flo
 
 // Volume codec for the device -> host transfer (host entry points).  A voxel whose three channels
 // are all +0.0, all +1.0 or all -1.0 (about 90 % of a D-TSDF volume) becomes a 2-bit code 0/1/2,
-// anything else code 3.  A group of 4 consecutive voxels (one code byte) that holds a code 3 is a
-// "literal group": its 3 x 4 floats (x[4], y[4], z[4]) go to a per-frame literal stream.  Lossless.
-//   counts   [n]     literal groups per frame (device scratch)
+// anything else code 3 = "literal": its three floats go to the frame's literal block.  Lossless.
+//   counts   [n]     literal voxels per frame (device scratch)
 //   lit_off  [n+1]   exclusive prefix of counts (device); lit_off_copy: optional second copy
 //   codes    [n][R3/4] bytes: voxel 4k+j of the frame in bits 2j..2j+1 of byte k
-//   lits     [12 * lit_off[n]] floats, frame after frame, group order, 48 bytes per literal group
+//   lits     [3 * lit_off[n]] floats; frame f's block starts at float 3 * lit_off[f] and holds, for its
+//            nf = lit_off[f+1] - lit_off[f] literal voxels in voxel order, x[nf], y[nf], z[nf]
+//            (12 bytes per literal voxel; literals per GROUP of four voxels, the first form, were 64 %
+//            more bytes on real volumes).  Buffers need 3 * R3 floats per frame + 16 bytes.
 cudaError_t launch_pack(int n_frames, int r3, const float* vol, unsigned* counts,
                         unsigned long long* lit_off, unsigned long long* lit_off_copy,
                         unsigned char* codes, float* lits, cudaStream_t stream);
 
-// literal stream device -> host-mapped memory, exactly 12 * lit_off[n] floats
+// literal stream device -> host-mapped memory: 3 * lit_off[n] floats, rounded up to whole 16 bytes
 cudaError_t launch_pack_push(int n_frames, const float* lits, const unsigned long long* lit_off,
                              float* host_lits, cudaStream_t stream);
 
 // Host side of the codec (dtsdf_decode.cpp, plain C++): expands one packed frame (its r3/4 code bytes and
-// its slice of the literal stream) into the three channel planes at `out` (any 4-byte alignment;
-// whole-line non-temporal stores when `out` is 16-byte aligned).
-void decode_frame(const unsigned char* codes, const float* lits, size_t r3, float* out);
+// its literal block of nlit voxels: x[nlit], y[nlit], z[nlit]) into the three channel planes at `out`
+// (any 4-byte alignment; whole-line non-temporal stores when `out` is 16-byte aligned).
+void decode_frame(const unsigned char* codes, const float* lits, size_t nlit, size_t r3, float* out);
 const char* decode_isa();
 
 // kernels launched by this process (claimed in bench.py's gpu_launches)

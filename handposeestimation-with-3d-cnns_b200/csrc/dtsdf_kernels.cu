@@ -1603,8 +1603,8 @@ __device__ __forceinline__ unsigned group_codes(const float* __restrict__ vol, i
            (voxel_code(a.w, b.w, c.w) << 6);
 }
 
-__device__ __forceinline__ unsigned has_literal(unsigned byte) {      // any 2-bit field equal to 3
-    return (byte & (byte >> 1) & 0x55u) != 0u;
+__device__ __forceinline__ unsigned literal_mask(unsigned byte) {     // bit 2j set <=> voxel j has code 3
+    return byte & (byte >> 1) & 0x55u;
 }
 
 __global__ void __launch_bounds__(NT) pack_count_kernel(const float* __restrict__ vol, int r3,
@@ -1614,7 +1614,7 @@ __global__ void __launch_bounds__(NT) pack_count_kernel(const float* __restrict_
     unsigned n = 0;
     for (int g = threadIdx.x; g < r3 / 4; g += NT) {
         uint4 a, b, c;
-        n += has_literal(group_codes(v, r3, g, a, b, c));
+        n += __popc(literal_mask(group_codes(v, r3, g, a, b, c)));
     }
     n = __reduce_add_sync(FULL, n);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = n;
@@ -1648,17 +1648,28 @@ __global__ void __launch_bounds__(NT) pack_write_kernel(const float* __restrict_
     const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* v = vol + (size_t)f * 3 * r3;
     unsigned char* cd = codes + (size_t)f * (r3 / 4);
-    uint4* lt = reinterpret_cast<uint4*>(lits) + 3 * off_dev[f];
+    // the frame's literal block: x of its nf literal voxels, then y, then z, in voxel order
+    const unsigned long long o0 = off_dev[f];
+    const unsigned nf = (unsigned)(off_dev[f + 1] - o0);
+    unsigned* lx = reinterpret_cast<unsigned*>(lits) + 3 * o0;
+    unsigned* ly = lx + nf;
+    unsigned* lz = ly + nf;
     unsigned base = 0;
     for (int g0 = 0; g0 < r3 / 4; g0 += NT) {            // r3/4 is a multiple of NT for R = 32, 48, 64
         const int g = g0 + threadIdx.x;
         uint4 a, b, c;
         const unsigned byte = group_codes(v, r3, g, a, b, c);
         cd[g] = (unsigned char)byte;
-        const unsigned lit = has_literal(byte);
-        // block-wide exclusive prefix of the literal groups, in voxel order
-        const unsigned bal = __ballot_sync(FULL, lit);
-        if (lane == 0) wsum[warp] = __popc(bal);
+        const unsigned m2 = literal_mask(byte);
+        const unsigned nl = __popc(m2);
+        // block-wide exclusive prefix of the literal voxels, in voxel order
+        unsigned incl = nl;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
         __syncthreads();
         unsigned before = 0, total = 0;
 #pragma unroll
@@ -1667,21 +1678,24 @@ __global__ void __launch_bounds__(NT) pack_write_kernel(const float* __restrict_
             if (w < warp) before += t;
             total += t;
         }
-        if (lit) {
-            uint4* q = lt + 3 * (size_t)(base + before + __popc(bal & ((1u << lane) - 1u)));
-            q[0] = a; q[1] = b; q[2] = c;
+        if (nl) {
+            unsigned r = base + before + incl - nl;
+            const unsigned av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((m2 >> (2 * j)) & 1u) { lx[r] = av[j]; ly[r] = bv[j]; lz[r] = cv[j]; ++r; }
         }
         base += total;
         __syncthreads();
     }
 }
 
-// Copies the literal stream (12 * lit_off[n] floats, a count only the device knows) from device memory
+// Copies the literal stream (3 * lit_off[n] floats, a count only the device knows) from device memory
 // to host-mapped memory with whole 16-byte, fully coalesced stores: PCIe likes 128-byte writes, the
 // scattered 4-byte stores of pack_write_kernel it does not.
 __global__ void __launch_bounds__(NT) pack_push_kernel(const float* __restrict__ lits, const unsigned long long* __restrict__ off,
                                                        int n, float* __restrict__ host_lits) {
-    const unsigned long long n16 = 3ull * off[n];                          // uint4 units
+    const unsigned long long n16 = (3ull * off[n] + 3ull) / 4ull;          // uint4 units (the buffers are padded)
     const uint4* src = reinterpret_cast<const uint4*>(lits);
     uint4* dst = reinterpret_cast<uint4*>(host_lits);
     for (unsigned long long i = blockIdx.x * (unsigned long long)NT + threadIdx.x; i < n16;

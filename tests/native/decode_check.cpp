@@ -9,7 +9,7 @@
 #include <vector>
 
 namespace dtsdf {
-void decode_frame(const unsigned char*, const float*, size_t, float*);
+void decode_frame(const unsigned char*, const float*, size_t, size_t, float*);
 const char* decode_isa();
 }
 
@@ -25,9 +25,7 @@ int main() {
         const size_t r3 = R * R * R, nb = r3 / 4;
         for (int density = 0; density < 4; ++density) {          // literal density 0, sparse, medium, all
             std::vector<unsigned char> codes(nb);
-            float* lits = (float*)aligned_alloc(64, nb * 48 + 64);
-            std::vector<float> want(3 * r3);
-            size_t nl = 0;
+            std::vector<float> want(3 * r3), lx, ly, lz;
             const float val[4] = {0.0f, 1.0f, -1.0f, 0.0f};
             for (size_t k = 0; k < nb; ++k) {
                 unsigned b = 0;
@@ -39,25 +37,29 @@ int main() {
                 }
                 if (rnd() % 4 == 0) b = (rnd() % 3) * 0x55u;          // runs of one value
                 codes[k] = (unsigned char)b;
-                if (b & (b >> 1) & 0x55u) {
-                    for (int p = 0; p < 3; ++p)
-                        for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned c = (b >> (2 * j)) & 3;
+                    float v[3] = {val[c], val[c], val[c]};
+                    if (c == 3) {
+                        for (int p = 0; p < 3; ++p) {
                             uint32_t bits = rnd();                    // any bit pattern, NaNs and -0 included
-                            float f; memcpy(&f, &bits, 4);
-                            lits[12 * nl + 4 * p + j] = f;
-                            want[p * r3 + 4 * k + j] = f;
+                            memcpy(&v[p], &bits, 4);
                         }
-                    ++nl;
-                } else {
-                    for (int p = 0; p < 3; ++p)
-                        for (int j = 0; j < 4; ++j) want[p * r3 + 4 * k + j] = val[(b >> (2 * j)) & 3];
+                        lx.push_back(v[0]); ly.push_back(v[1]); lz.push_back(v[2]);
+                    }
+                    for (int p = 0; p < 3; ++p) want[p * r3 + 4 * k + j] = v[p];
                 }
             }
+            const size_t nl = lx.size();
+            // the literal block sits at an odd float offset: only 4-byte alignment is promised
+            float* litbuf = (float*)aligned_alloc(64, (3 * nl + 32) * 4);
+            float* lits = litbuf + 1;
+            memcpy(lits, lx.data(), nl * 4); memcpy(lits + nl, ly.data(), nl * 4); memcpy(lits + 2 * nl, lz.data(), nl * 4);
             for (size_t mis = 0; mis < 20; ++mis) {                   // output offset in floats: 0..19
                 float* raw = (float*)aligned_alloc(64, (3 * r3 + 64) * 4);
                 memset(raw, 0xCD, (3 * r3 + 64) * 4);
                 float* out = raw + 16 + mis;
-                dtsdf::decode_frame(codes.data(), lits, r3, out);
+                dtsdf::decode_frame(codes.data(), lits, nl, r3, out);
                 const bool body = memcmp(out, want.data(), 3 * r3 * 4) == 0;
                 bool guard = true;                                    // nothing written outside the frame
                 for (size_t i = 0; i < 16 + mis; ++i) { uint32_t u; memcpy(&u, raw + i, 4); guard = guard && u == 0xCDCDCDCDu; }
@@ -66,7 +68,7 @@ int main() {
                 if (!body || !guard) { ++bad; printf("FAIL R=%zu density=%d offset=%zu body=%d guard=%d\n", R, density, mis, body, guard); }
                 free(raw);
             }
-            free(lits);
+            free(litbuf);
         }
     }
     printf("isa=%s cases=%d mismatches=%d\n", dtsdf::decode_isa(), cases, bad);
