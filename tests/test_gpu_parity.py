@@ -370,6 +370,39 @@ def test_full_size_batch_properties():
     assert torch.equal(vp, v0[torch.from_numpy(perm).to(dev)])
 
 
+def test_full_msra_sized_set_on_one_gpu():
+    """BASELINE.json configs[2] size on one GPU: 76,375 frames (30 GB of volumes, resident).  The offset
+    table walks 8,500 distinct crops nine times over, so frame i must equal frame i mod 8,500 - a
+    frame's volume depends on nothing but its own record - and a sample is checked against the C oracle."""
+    import torch
+    dev = torch.device("cuda:0")
+    free, _ = torch.cuda.mem_get_info(dev)
+    n, base = 76375, 8500
+    if free < 40 * (1 << 30):
+        pytest.skip("needs 40 GB of free device memory")
+    headers, depth = synth.make_uniform_batch(base, seed0=21)
+    offsets, packed_len, max_px = pkg.capi.pack_plan(headers)
+    idx = np.arange(n) % base
+    d_depth = torch.from_numpy(depth.reshape(-1)).to(dev)
+    d_off = torch.from_numpy(offsets[idx]).to(dev)
+    d_hdr = torch.from_numpy(headers[idx]).to(dev)
+    cfg = pkg.capi.default_config(layout=pkg.LAYOUT_CXYZ)
+    vol, ml, mp = pkg.voxelize_device(d_depth, d_off, d_hdr, max_px, cfg)
+    torch.cuda.synchronize()
+    assert vol.shape == (n, 3, 32, 32, 32)
+    first = vol[:base]
+    for k in range(1, (n + base - 1) // base):
+        part = vol[k * base:(k + 1) * base]
+        assert torch.equal(part, first[:part.shape[0]]), "replica %d" % k
+    assert torch.equal(ml[base:2 * base], ml[:base]) and torch.equal(mp[-100:], mp[(n - 100) % base:(n - 100) % base + 100])
+    pick = np.arange(0, base, 97)
+    cv, cml, _, _ = c_oracle.dtsdf_batch(headers[pick], offsets[:pick.size], depth[pick].reshape(-1))
+    assert _same(first[torch.from_numpy(pick).to(dev)].cpu().numpy(), cv)
+    assert np.array_equal(ml.cpu().numpy()[pick + 7 * base], cml)
+    del vol, first
+    torch.cuda.empty_cache()
+
+
 def test_normalize_joints(vox):
     # (gt - mid_p)/max_l + 0.5: pre/joint_nor.py:8-18 (float64 there, float32 here: 1e-6)
     rng = np.random.default_rng(3)
