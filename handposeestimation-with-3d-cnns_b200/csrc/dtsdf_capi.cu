@@ -159,7 +159,11 @@ struct Latch {
 struct dtsdf_ctx {
     int device = 0;
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+#ifdef DTSDF_EXP_NSLOT          /* dev experiment */
+    static const int NSLOT = DTSDF_EXP_NSLOT;
+#else
     static const int NSLOT = 4;                 // chunks in flight
+#endif
     // packed device -> host transfer
     int opt_packed = 1;
     int opt_threads = 0;                        // 0 = hardware concurrency
