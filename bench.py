@@ -278,6 +278,8 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries the JSON line only: NCCL's own banner (NCCL_DEBUG=VERSION on some boxes) goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/dtsdf_bench_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
     build_cuda()
     pkg = load_package()

@@ -15,12 +15,14 @@ _lib = None
 
 
 def build(force=False):
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
-        return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    subprocess.run(["gcc", "-O2", "-std=c11", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC",
-                    "-shared", SRC, "-o", LIB, "-lm"], check=True)
-    return LIB
+    """Compiled by __graft_entry__.build_oracle (content-hashed, one process at a time)."""
+    import sys
+    root = os.path.dirname(_HERE)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import __graft_entry__ as graft
+    assert graft.ORACLE_LIB == LIB
+    return graft.build_oracle(force)
 
 
 def lib():
