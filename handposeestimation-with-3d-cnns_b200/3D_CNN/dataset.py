@@ -19,6 +19,8 @@ Deliberate differences from the reference:
     Both shapes get the z flip of :107;
   * CUDA_VISIBLE_DEVICES is not overwritten at import (:12-13);
   * the PCA side data of ``size == 'full'`` (:165-181) is loaded only if ``./PCA`` exists.
+``variant='cut'`` selects the behaviour of the later fork ``cut_version/3D_CNN/dataset.py`` (3 subjects,
+ground truth [21,3], a fifth tuple member ``joint_nor``); see ``__init__``.
 """
 import os
 import os.path
@@ -31,7 +33,8 @@ from _bind import package
 
 
 class MSRA_Dataset(data.Dataset):
-    def __init__(self, root_path, opt=None, train=True, aug=False, device=None, size='small', test_idx=2):
+    def __init__(self, root_path, opt=None, train=True, aug=False, device=None, size='small', test_idx=2,
+                 variant='full'):
         self.root_path = root_path
         self.train = train
         self.size = size            # the reference hard-codes 'small' (:20)
@@ -39,7 +42,19 @@ class MSRA_Dataset(data.Dataset):
         self.PCA_SZ = 63
         self.AUG = aug
         self.device = device
-        if self.size == 'full':
+        # variant='cut': the later, slimmed fork (cut_version/3D_CNN/dataset.py:16-66): size, test index
+        # and PCA size come from ``opt`` (:20-22), 3 subjects, ground truth stays [n,21,3] without the
+        # z flip (:95), and a fifth member joint_nor[63] (:66,100-103) - loaded from ``joint_nor<aug>/``
+        # when the tree has it, otherwise computed on the GPU from ground truth, max_l and mid_p
+        self.variant = variant
+        if variant == 'cut' and opt is not None:
+            self.size = getattr(opt, 'size', self.size)
+            self.test_idx = getattr(opt, 'test_index', self.test_idx)
+            self.PCA_SZ = getattr(opt, 'PCA_SZ', self.PCA_SZ)
+        if variant == 'cut':
+            self.SUBJECTS = 3
+            self.GESTURES = 17 if self.size == 'full' else 3
+        elif self.size == 'full':
             self.SUBJECTS = 9
             self.GESTURES = 17
         else:
@@ -60,7 +75,8 @@ class MSRA_Dataset(data.Dataset):
 
     def _load_tree(self):
         results = sorted(os.listdir(self.root_path))[:9]
-        tsdf, gt, max_l, mid_p = [], [], [], []
+        tsdf, gt, max_l, mid_p, jn = [], [], [], [], []
+        cut = self.variant == 'cut'
         passes = [(self._subjects(results), '')]
         if self.AUG:
             passes.append(([results[s] for s in range(self.SUBJECTS)], '_aug'))     # :55-60
@@ -76,11 +92,22 @@ class MSRA_Dataset(data.Dataset):
                     max_l.append(z['max_l'].astype(np.float32).reshape(-1))
                     mid_p.append(z['mid_p'].astype(np.float32).reshape(-1, 3))
                     g = np.load(os.path.join(data_dir, 'ground_truth%s' % suffix, g_file[ges])).astype(np.float32)
-                    gt.append(self._flip_z(g))
+                    if not cut:
+                        gt.append(self._flip_z(g))
+                        continue
+                    gt.append(g.reshape(-1, 21, 3))
+                    n_dir = os.path.join(data_dir, 'joint_nor%s' % suffix)
+                    if os.path.isdir(n_dir):
+                        n_file = sorted(os.listdir(n_dir))
+                        jn.append(np.load(os.path.join(n_dir, n_file[ges])).astype(np.float32).reshape(-1, 63))
+                    else:
+                        jn.append(package().default_voxelizer().normalize_joints(g.reshape(-1, 63), max_l[-1], mid_p[-1]))
         self.tsdf = np.concatenate(tsdf) if tsdf else np.empty((0, 3, 32, 32, 32), np.float32)
         self.ground_truth = np.concatenate(gt) if gt else np.empty((0, 63), np.float32)
         self.max_l = np.concatenate(max_l) if max_l else np.empty(0, np.float32)
         self.mid_p = np.concatenate(mid_p) if mid_p else np.empty((0, 3), np.float32)
+        if cut:
+            self.joint_nor = np.concatenate(jn) if jn else np.empty((0, 63), np.float32)
         self.total_num = self.tsdf.shape[0]
 
     @staticmethod
@@ -135,7 +162,7 @@ class MSRA_Dataset(data.Dataset):
         return self
 
     def _finish(self):
-        if self.size == 'full' and os.path.isdir('./PCA'):
+        if self.variant != 'cut' and self.size == 'full' and os.path.isdir('./PCA'):
             self.__loadPCA()
         if self.device is not None:
             dev = torch.device(self.device)
@@ -145,9 +172,14 @@ class MSRA_Dataset(data.Dataset):
             self.mid_p = torch.from_numpy(self.mid_p).to(dev)
             if hasattr(self, 'ground_truth_pca'):
                 self.ground_truth_pca = torch.from_numpy(self.ground_truth_pca).to(dev)
+            if hasattr(self, 'joint_nor'):
+                self.joint_nor = torch.from_numpy(self.joint_nor).to(dev)
 
     def __getitem__(self, index):
         """return index data"""
+        if self.variant == 'cut':         # cut_version/3D_CNN/dataset.py:66
+            return (self.tsdf[index], self.ground_truth[index], self.max_l[index], self.mid_p[index],
+                    self.joint_nor[index])
         if hasattr(self, 'ground_truth_pca'):
             return (self.tsdf[index], self.ground_truth[index], self.max_l[index], self.mid_p[index],
                     self.ground_truth_pca[index])

@@ -277,6 +277,28 @@ def test_host_pipeline_many_small_chunks_and_destination_alignments():
     v.close()
 
 
+def test_host_pipeline_random_configurations():
+    """Random batch sizes (plain and packed routes), chunk sizes and expansion thread counts on one
+    context, back to back: the host entry point always returns the oracle's bits."""
+    frames = synth.make_frames(range(3000, 3000 + 400))
+    headers, offsets, packed = pack_simple(frames)
+    want, wml, wmp, _ = c_oracle.dtsdf_batch(headers, offsets, packed)
+    v = pkg.Voxelizer(device=0)
+    rng = np.random.default_rng(5)
+    out = np.empty_like(want)
+    for it in range(60):
+        mb = int(rng.choice([1, 2, 3, 5, 8, 16, 33, 64, 200]))
+        nt = int(rng.integers(0, 17))
+        n = int(rng.integers(1, 401))
+        v.set_option(pkg.capi.OPT_CHUNK_MB, mb)
+        v.set_option(pkg.capi.OPT_HOST_THREADS, nt)
+        out[:n] = 5.0
+        _, ml, mp = v.voxelize_packed(headers[:n], offsets[:n], packed, out_vol=out[:n])
+        assert _same(out[:n], want[:n]), "call %d: chunk %d MB, %d threads, %d frames" % (it, mb, nt, n)
+        assert np.array_equal(ml, wml[:n]) and np.array_equal(mp, wmp[:n])
+    v.close()
+
+
 def test_joint_nor_module(tmp_path, monkeypatch):
     # pre/joint_nor.py:8-18 (float64 there): normalize() and the result-tree walk of read_joint()
     jn = import_pre("joint_nor")

@@ -4,6 +4,7 @@ tests/golden/msra_tree.npz): the ``3D_CNN/dataset.py`` consumer (CPU) and the ``
 preprocessing driver (GPU)."""
 import hashlib
 import importlib
+import importlib.util
 import os
 import sys
 
@@ -75,6 +76,56 @@ def test_dataset_matches_reference_loader(golden, tmp_path, gt_3d):
     tsdf, gt, max_l, mid_p = next(iter(loader))
     assert tuple(tsdf.shape) == (4, 3, 32, 32, 32) and tsdf.dtype == torch.float32
     assert tuple(gt.shape) == (4, 63) and tuple(max_l.shape) == (4,) and tuple(mid_p.shape) == (4, 3)
+
+
+def test_dataset_cut_version_variant(golden, tmp_path):
+    """variant='cut': the later fork's loader (cut_version/3D_CNN/dataset.py:16-108): 3 subjects x 3
+    gestures, ground truth [21,3] unflipped, joint_nor from the tree as a fifth member.  Where the
+    reference tree is mounted (the build container) the unmodified fork loads the same tree for
+    comparison; elsewhere the expectation is rebuilt from the fixture."""
+    import types
+    dataset = _import("dataset", CNN_DIR)
+    root = str(tmp_path / "result")
+    _write_tree(golden, root, True)
+    want_jn = {}
+    for sub in mini.SUBJECTS:
+        os.makedirs(os.path.join(root, sub, "joint_nor"))
+        for ges in mini.GESTURES:
+            k = "%s_%s_" % (sub, ges)
+            gt = golden[k + "gt"].reshape(-1, 21, 3).astype(np.float64)
+            jn = np.stack([(gt[i] - golden[k + "mid_p"][i]) / golden[k + "max_l"][i] + 0.5 for i in range(gt.shape[0])])
+            np.save(os.path.join(root, sub, "joint_nor", "%s.npy" % ges), jn.reshape(-1, 63))
+            want_jn[(sub, ges)] = jn.reshape(-1, 63).astype(np.float32)
+    opt = types.SimpleNamespace(size="small", test_index=1, PCA_SZ=63)
+    ref_mod = None
+    ref_dir = "/root/reference/cut_version/3D_CNN"
+    if os.path.isdir(ref_dir):
+        spec = importlib.util.spec_from_file_location("ref_cut_dataset", os.path.join(ref_dir, "dataset.py"))
+        ref_mod = importlib.util.module_from_spec(spec)
+        keep = {k: os.environ.get(k) for k in ("CUDA_DEVICE_ORDER", "CUDA_VISIBLE_DEVICES")}
+        spec.loader.exec_module(ref_mod)                       # (it overwrites CUDA_VISIBLE_DEVICES at import)
+        for k, v in keep.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    for train in (True, False):
+        ds = dataset.MSRA_Dataset(root, opt, train=train, aug=False, variant="cut")
+        subs = [s for i, s in enumerate(mini.SUBJECTS[:3]) if (i != 1) == train]
+        keys = [(s, g) for s in subs for g in mini.GESTURES[:3]]
+        assert len(ds) == sum(want_jn[k].shape[0] for k in keys)
+        assert np.array_equal(ds.joint_nor, np.concatenate([want_jn[k] for k in keys]))
+        want_gt = np.concatenate([golden["%s_%s_gt" % k].reshape(-1, 21, 3) for k in keys])
+        assert np.array_equal(ds.ground_truth, want_gt)                         # [n,21,3], no z flip
+        item = ds[0]
+        assert len(item) == 5 and item[1].shape == (21, 3) and item[4].shape == (63,)
+        if ref_mod is not None:
+            rd = ref_mod.MSRA_Dataset(root, opt, train=train, aug=False)
+            assert len(rd) == len(ds)
+            for name in ("tsdf", "ground_truth", "max_l", "mid_p", "joint_nor"):
+                assert np.array_equal(getattr(rd, name), getattr(ds, name)), name
+            for a, b in zip(rd[len(rd) - 1], ds[len(ds) - 1]):
+                assert np.array_equal(a, b)
 
 
 # ----------------------------------------------------------------------------- preprocessing driver (GPU)
