@@ -34,6 +34,12 @@ SAVE_dir = './result'
 # set whether to do data augmentation
 AUG = False
 
+# True: the tree of the later fork (cut_version/pre/read_MSRA.py:60-113): ground truth saved as
+# [n,21,3] (:63), an extra joint_nor/<ges>.npy = (gt - mid_p)/max_l + 0.5 per frame in float64
+# (cut_version/pre/process.py:251-263, 63 numbers per frame: NumPy on the host, so the file matches
+# the fork's float64 arithmetic), no data_num-<sub>.npy (:131)
+JOINT_NOR = False
+
 POINTS_NUM = 6000
 _TREE = ('Point_Cloud', 'TSDF', 'ground_truth', 'num')
 
@@ -66,6 +72,10 @@ def _store_gesture(out_dir, ges, count, joints, clouds, volumes, sides, centres)
     np.save(os.path.join(out_dir, _TREE[0], ges + '.npy'), clouds)
     np.savez(os.path.join(out_dir, _TREE[1], ges + '.npz'), tsdf=volumes.astype(f64), max_l=sides.astype(f64),
              mid_p=centres.astype(f64))
+    if JOINT_NOR:
+        joints = joints.reshape(count, 21, 3)
+        nor = (joints.astype(f64) - centres.astype(f64)[:, None, :]) / sides.astype(f64)[:, None, None] + 0.5
+        np.save(os.path.join(out_dir, 'joint_nor', ges + '.npy'), nor.reshape(count, 63))
     np.save(os.path.join(out_dir, _TREE[2], ges + '.npy'), joints)
     np.save(os.path.join(out_dir, _TREE[3], ges + '.npy'), count)
 
@@ -83,7 +93,7 @@ def main():
     for who in people:
         out_dir = os.path.join(SAVE_dir, who)
         _ensure_dir(out_dir, who)
-        for name in _TREE:
+        for name in _TREE + (('joint_nor',) if JOINT_NOR else ()):
             _ensure_dir(os.path.join(out_dir, name))
         frames_of_subject = 0
         for ges in poses:
@@ -93,7 +103,8 @@ def main():
             clouds, volumes, sides, centres = engine.process_frames(records, POINTS_NUM)
             _store_gesture(out_dir, ges, count, joints, clouds, volumes, sides, centres)
             print('%s-%s files saved.' % (who, ges))
-        np.save(os.path.join(SAVE_dir, 'data_num-%s.npy' % who), frames_of_subject)
+        if not JOINT_NOR:
+            np.save(os.path.join(SAVE_dir, 'data_num-%s.npy' % who), frames_of_subject)
         print('%s total number saved.' % who)
 
 

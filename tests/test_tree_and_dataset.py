@@ -166,6 +166,31 @@ def test_read_msra_main_writes_the_reference_tree(golden, tmp_path):
         read_MSRA.main()
     read_MSRA.AUG = False
 
+    # the later fork's tree (cut_version/pre/read_MSRA.py:60-113): same volumes, ground truth [n,21,3],
+    # joint_nor/<ges>.npy in float64, no data_num file; MSRA_Dataset(variant='cut') loads it
+    res2 = str(tmp_path / "result_cut")
+    read_MSRA.SAVE_dir, read_MSRA.JOINT_NOR = res2, True
+    np.random.seed(int(golden["seed"]))
+    try:
+        read_MSRA.main()
+    finally:
+        read_MSRA.JOINT_NOR = False
+    assert not os.path.exists(os.path.join(res2, "data_num-P0.npy"))
+    for sub in mini.SUBJECTS:
+        for ges in mini.GESTURES:
+            k = "%s_%s_" % (sub, ges)
+            z = np.load(os.path.join(res2, sub, "TSDF", "%s.npz" % ges))
+            assert np.array_equal(z["tsdf"], golden[k + "tsdf"].astype(np.float64))
+            gt = np.load(os.path.join(res2, sub, "ground_truth", "%s.npy" % ges))
+            assert gt.shape[1:] == (21, 3) and np.array_equal(gt.reshape(-1, 63), golden[k + "gt"])
+            jn = np.load(os.path.join(res2, sub, "joint_nor", "%s.npy" % ges))
+            want = np.stack([(gt[i].astype(np.float64) - z["mid_p"][i]) / z["max_l"][i] + 0.5 for i in range(gt.shape[0])])
+            assert jn.dtype == np.float64 and np.array_equal(jn, want.reshape(-1, 63))
+    import types
+    dataset = _import("dataset", CNN_DIR)
+    ds = dataset.MSRA_Dataset(res2, types.SimpleNamespace(size="small", test_index=1, PCA_SZ=63), train=True, variant="cut")
+    assert len(ds[0]) == 5 and ds.joint_nor.shape == (len(ds), 63)
+
 
 @pytest.mark.gpu
 def test_dataset_from_database_on_device(golden, tmp_path):
