@@ -24,17 +24,22 @@ def make_augmentations(n, rng=None, stretch=(2.0 / 3.0, 3.0 / 2.0), max_rot_xy_d
     as show/visualize.py).  ``Ainv`` is the inverse of the float32-rounded ``A``."""
     rng = np.random.default_rng(0) if rng is None else rng
     out = np.zeros((n, 21), dtype=np.float32)
-    for i in range(n):
-        sx, sy = rng.uniform(stretch[0], stretch[1], size=2)
-        ax, ay = np.deg2rad(rng.uniform(-max_rot_xy_deg, max_rot_xy_deg, size=2))
-        az = np.deg2rad(rng.uniform(-max_rot_z_deg, max_rot_z_deg))
-        S = np.diag([sx, sy, 1.0])
-        Rx = np.array([[1, 0, 0], [0, np.cos(ax), np.sin(ax)], [0, -np.sin(ax), np.cos(ax)]])
-        Ry = np.array([[np.cos(ay), 0, -np.sin(ay)], [0, 1, 0], [np.sin(ay), 0, np.cos(ay)]])
-        Rz = np.array([[np.cos(az), np.sin(az), 0], [-np.sin(az), np.cos(az), 0], [0, 0, 1]])
-        A = (S @ Rx @ Ry @ Rz).astype(np.float32)
-        out[i, :9] = A.reshape(-1)
-        out[i, 9:18] = np.linalg.inv(A.astype(np.float64)).astype(np.float32).reshape(-1)
+    # five uniform draws per frame, frame after frame (sx, sy, ax, ay, az), whole batch at once
+    u = rng.random((n, 5))
+    sx = stretch[0] + (stretch[1] - stretch[0]) * u[:, 0]
+    sy = stretch[0] + (stretch[1] - stretch[0]) * u[:, 1]
+    ax = np.deg2rad(-max_rot_xy_deg + 2.0 * max_rot_xy_deg * u[:, 2])
+    ay = np.deg2rad(-max_rot_xy_deg + 2.0 * max_rot_xy_deg * u[:, 3])
+    az = np.deg2rad(-max_rot_z_deg + 2.0 * max_rot_z_deg * u[:, 4])
+    S = np.zeros((n, 3, 3)); Rx = np.zeros((n, 3, 3)); Ry = np.zeros((n, 3, 3)); Rz = np.zeros((n, 3, 3))
+    S[:, 0, 0], S[:, 1, 1], S[:, 2, 2] = sx, sy, 1.0
+    Rx[:, 0, 0] = 1.0; Rx[:, 1, 1] = np.cos(ax); Rx[:, 1, 2] = np.sin(ax); Rx[:, 2, 1] = -np.sin(ax); Rx[:, 2, 2] = np.cos(ax)
+    Ry[:, 1, 1] = 1.0; Ry[:, 0, 0] = np.cos(ay); Ry[:, 0, 2] = -np.sin(ay); Ry[:, 2, 0] = np.sin(ay); Ry[:, 2, 2] = np.cos(ay)
+    Rz[:, 2, 2] = 1.0; Rz[:, 0, 0] = np.cos(az); Rz[:, 0, 1] = np.sin(az); Rz[:, 1, 0] = -np.sin(az); Rz[:, 1, 1] = np.cos(az)
+    A = (S @ Rx @ Ry @ Rz).astype(np.float32)
+    out[:, :9] = A.reshape(n, 9)
+    if n:
+        out[:, 9:18] = np.linalg.inv(A.astype(np.float64)).astype(np.float32).reshape(n, 9)
     if centers is not None:
         out[:, 18:] = np.asarray(centers, dtype=np.float32).reshape(n, 3)
     return out

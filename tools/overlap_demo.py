@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=4096)
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--steps", type=int, default=100)
+ap.add_argument("--augment", action="store_true", help="random stretch + rotation per batch (augmented voxeliser)")
 args = ap.parse_args()
 pkg = g.load_package()
 lmod = importlib.import_module(pkg.__name__ + ".loader")
@@ -46,7 +47,8 @@ def timed(fn, steps):
     return (time.perf_counter() - t0) / steps * 1e3
 
 # (a) the step alone, on a batch that is already there
-loader = lmod.OnTheFlyLoader(res, batch_size=args.batch, shuffle=True, seed=0, drop_last=True)
+loader = lmod.OnTheFlyLoader(res, batch_size=args.batch, shuffle=True, seed=0, drop_last=True, augment=args.augment,
+                             augment_center=(0.0, 0.0, -380.0))
 tsdf0, jn0, _, _ = next(iter(loader))
 tsdf0, jn0 = tsdf0.clone(), jn0.clone()
 def step_only(n):
@@ -76,6 +78,6 @@ def overlapped(n):
                 break
 overlapped(10)
 ms_overlap = timed(overlapped, args.steps)
-print(json.dumps({"batch": args.batch, "ms_step_alone": ms_step, "ms_voxelise_then_step": ms_serial,
+print(json.dumps({"batch": args.batch, "augment": bool(args.augment), "ms_step_alone": ms_step, "ms_voxelise_then_step": ms_serial,
                   "ms_overlapped_loader": ms_overlap,
                   "voxeliser_cost_serial_ms": ms_serial - ms_step, "voxeliser_cost_overlapped_ms": ms_overlap - ms_step}))
