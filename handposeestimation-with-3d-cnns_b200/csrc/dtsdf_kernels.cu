@@ -818,18 +818,22 @@ __device__ __forceinline__ void voxel_passes_blocked(const float* __restrict__ c
 // block indices: the second crop load hits L2); every CTA redoes the cheap prologue (crop, bounding box,
 // tables), nothing is exchanged.  Measured per 4,000 frames: R = 48: 0.929 ms unsplit, 0.903 ms with
 // two or three CTAs per frame (kept: 2); R = 64: 2.04 ms unsplit at one CTA per SM, 2.22 ms with two
-// CTAs per frame, 2.10 ms with four (kept: 1 - fewer concurrent write streams win there).
+// CTAs per frame, 2.10 ms with four (kept: 1 - fewer concurrent write streams win there); R = 32 (per
+// 8,500 frames): 0.616 ms unsplit at two CTAs per SM, 0.619 ms with two CTAs per frame at three per SM (kept: 1).
 #ifndef DTSDF_EXP_SPLIT48
 #define DTSDF_EXP_SPLIT48 2
 #endif
 #ifndef DTSDF_EXP_SPLIT64
 #define DTSDF_EXP_SPLIT64 1
 #endif
+#ifndef DTSDF_EXP_SPLIT32
+#define DTSDF_EXP_SPLIT32 1
+#endif
 template <int R, int LAYOUT>
 struct CtaShape {
     static constexpr int NW = 8;
     static constexpr int MIN_CTAS = 3;
-    static constexpr int SPLIT = R == 64 ? DTSDF_EXP_SPLIT64 : 1;
+    static constexpr int SPLIT = R == 64 ? DTSDF_EXP_SPLIT64 : (R == 32 ? DTSDF_EXP_SPLIT32 : 1);
 };
 
 // R = 48 (block map): 288 units of 8 middle-axis rows per frame, 36 per warp
@@ -1122,7 +1126,7 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
 #else
         constexpr int SPLIT = CtaShape<R, LAYOUT>::SPLIT;
         // (with SPLIT CTAs per frame, SPLIT CTAs per SM are one volume per SM under construction)
-        const int target = fit >= 2 ? std::min(occ, fit) : (R >= 64 ? std::min(occ, SPLIT) : occ);
+        const int target = fit >= 2 ? std::min(occ, fit * SPLIT) : (R >= 64 ? std::min(occ, SPLIT) : occ);
 #endif
         if (target >= 1 && target < occ) {
             // the largest request that still lets `target` CTAs share an SM (1 KB per CTA is reserved)
