@@ -149,10 +149,20 @@ def ncu_traffic(res, layout, frames):
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm: the C oracle port of the reference's loop, all host threads
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """Hardware threads this process may run on.  Passed to the oracle explicitly: torchrun exports
+    OMP_NUM_THREADS=1 to its ranks, which would leave the reference arm on one core for N > 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port_rate(headers, offsets, packed, R, layout, seconds, nthreads=0):
     """Times oracle_dtsdf_batch on a bounded sample of about `seconds` of CPU work: whole passes over
     (a prefix of) the batch, repeated.  Returns (volumes/s, threads, frames per pass, passes, seconds)."""
     from oracle import c_oracle
+    nthreads = nthreads or host_threads()
     n = headers.shape[0]
     probe = min(n, 64)
     px = int(offsets[probe]) if probe < n else packed.size
@@ -238,7 +248,7 @@ def run_reference(args, rank, world):
 
     def step():
         c_oracle.dtsdf_batch(headers[:per_step], offsets[:per_step], packed[:px], R=args.res,
-                             layout=args.layout, out=out)
+                             layout=args.layout, out=out, nthreads=host_threads())
 
     for _ in range(args.warmup):
         step()
