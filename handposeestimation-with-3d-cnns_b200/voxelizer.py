@@ -85,7 +85,7 @@ class Voxelizer:
         except ValueError:
             local_world = 1
         if local_world > 1:
-            self.set_option(capi.OPT_HOST_THREADS, max(1, (os.cpu_count() or 1) // local_world))
+            self.set_option(capi.OPT_HOST_THREADS, max(1, min(8, (os.cpu_count() or 1) // local_world)))
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:

@@ -221,7 +221,7 @@ void dtsdf_ctx_destroy(dtsdf_ctx* ctx);
  *                          copies (the packed route costs more than it saves there).
  *                          0: plain device->host copies of the float volumes.
  *   DTSDF_OPT_HOST_THREADS number of host threads for the expansion (default 0 = three quarters of
- *                          the hardware threads, at most 32). */
+ *                          the hardware threads, at most 8: more do not add memory bandwidth). */
 #define DTSDF_OPT_PACKED_D2H   1
 #define DTSDF_OPT_HOST_THREADS 2
 #define DTSDF_OPT_CHUNK_MB     3   /* output megabytes per pipeline chunk of dtsdf_voxelize_host (default 64) */
