@@ -173,8 +173,7 @@ struct dtsdf_ctx {
     MapBuf m_codes[NSLOT], m_loff[NSLOT], m_lits[NSLOT];
     Latch latch[NSLOT];
     std::atomic<long long> stat_d2h_bytes{0};
-    // what the host function enqueued behind a chunk's device -> host copies needs to hand the
-    // chunk to the expansion threads (owned by the slot: rewritten only after latch[slot].wait())
+    // what the finalizer thread needs to hand a chunk to the expansion threads (owned by the slot: rewritten only after latch[slot].wait())
     struct ChunkRecord {
         dtsdf_ctx* ctx;
         int slot, jobs;
@@ -551,12 +550,12 @@ void dtsdf_host_free(void* ptr) {
     if (ptr) { cudaFreeHost(ptr); cudaGetLastError(); }
 }
 
-// Host function behind a chunk's device -> host copies (packed mode): split the chunk's frames over the
-// expansion threads.  Runs on a CUDA-internal thread: no CUDA calls here.
+// A chunk's packed form has arrived in host memory: split its frames over the expansion threads
+// (called by the finalizer thread of dtsdf_voxelize_host).
 #ifdef DTSDF_EXP_TIMELINE
 static std::atomic<long long> g_tl_decode_us{0};
 #endif
-static void CUDART_CB expand_chunk_cb(void* p) {
+static void expand_chunk(void* p) {
     const dtsdf_ctx::ChunkRecord* r = static_cast<const dtsdf_ctx::ChunkRecord*>(p);
     dtsdf_ctx* c = r->ctx;
     const unsigned char* codes = (const unsigned char*)c->m_codes[r->slot].p;
@@ -645,17 +644,49 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
         nthreads = c->opt_threads > 0 ? c->opt_threads : (int)std::min(8u, std::max(1u, hw - hw / 4));
         c->pool.ensure(nthreads);
     }
-    // A chunk is handed to the expansion threads by a host function enqueued on s_out behind its
-    // device -> host copies (expand_chunk_cb below): the submitting thread never waits for the GPU, so
-    // up to NSLOT chunks are in flight on the three streams; it only waits, before reusing a slot,
-    // for the host threads to be done with the chunk that used it last (latch[slot]).
-    auto drain = [&]() {
-        // host functions do not run once a stream has failed: do not wait for them then
-        const bool ok = cudaStreamSynchronize(c->s_out) == cudaSuccess;
-        for (int i = 0; i < dtsdf_ctx::NSLOT; ++i) {
-            if (ok) c->latch[i].wait();
-            else c->latch[i].reset();
+    // A chunk is handed to the expansion threads as soon as its last device -> host copy has landed: a
+    // finalizer thread (alive for the duration of this call) takes the chunks in order and polls the
+    // event recorded behind each one's copies.  (A stream host function - cudaLaunchHostFunc - did the same
+    // job at first: it holds its stream until it returns and costs ~0.2 ms per chunk; polling took a
+    // call over 8,500 frames from 33.5 ms to 28.6 ms and made 16-32 MB chunks as fast as 64 MB ones.)
+    // The submitting thread never waits for the GPU; before reusing a slot it waits for the host
+    // threads to be done with the chunk that used it last (latch[slot]).
+    std::mutex qm;
+    std::condition_variable qcv;
+    std::deque<int> fq;
+    bool qdone = false;
+    std::thread fin;
+    if (packed) fin = std::thread([&] {
+        cudaSetDevice(c->device);
+        for (;;) {
+            int slot;
+            {
+                std::unique_lock<std::mutex> lk(qm);
+                qcv.wait(lk, [&] { return !fq.empty() || qdone; });
+                if (fq.empty()) return;
+                slot = fq.front();
+                fq.pop_front();
+            }
+            cudaError_t e;
+            while ((e = cudaEventQuery(c->ev_run[slot])) == cudaErrorNotReady) _mm_pause();
+            if (e != cudaSuccess) { c->latch[slot].reset(); continue; }    // a failed stream: nothing to expand
+            expand_chunk(&c->chunk[slot]);
         }
+    });
+    auto stop_finalizer = [&] {
+        if (fin.joinable()) {
+            { std::lock_guard<std::mutex> g(qm); qdone = true; }
+            qcv.notify_all();
+            fin.join();                  // it first works off what is queued
+        }
+    };
+    struct AtExit {                      // every return path joins the thread
+        std::function<void()> fn;
+        ~AtExit() { fn(); }
+    } at_exit{stop_finalizer};
+    auto drain = [&]() {
+        stop_finalizer();
+        for (int i = 0; i < dtsdf_ctx::NSLOT; ++i) c->latch[i].wait();
     };
 
 #ifdef DTSDF_EXP_TIMELINE       /* dev instrumentation: where a chunk's time goes on each stream */
@@ -772,7 +803,7 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
             if (h_mid)
                 CK(cudaMemcpyAsync(h_mid + 3 * (size_t)f0, c->d_mid[slot].p, (size_t)nf * 12, cudaMemcpyDeviceToHost, c->s_out));
             TLREC(6, c->s_out);
-            // behind the copies: hand the chunk to the expansion threads
+            // behind the copies: an event for the finalizer thread
             {
                 dtsdf_ctx::ChunkRecord& r = c->chunk[slot];
                 r.ctx = c; r.slot = slot; r.jobs = std::min<int>(nf, nthreads); r.nf = nf;
@@ -780,8 +811,10 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
                 r.fixed_bytes = (long long)nf * (long long)(r3 / 4) + (long long)(nf + 1) * 8 +
                                 (h_maxl ? 4ll * nf : 0ll) + (h_mid ? 12ll * nf : 0ll);
                 c->latch[slot].add(r.jobs);
-                const cudaError_t he = cudaLaunchHostFunc(c->s_out, expand_chunk_cb, &r);
-                if (he != cudaSuccess) { c->latch[slot].reset(); drain(); return cuda_fail(he, "cudaLaunchHostFunc"); }
+                const cudaError_t he = cudaEventRecord(c->ev_run[slot], c->s_out);
+                if (he != cudaSuccess) { c->latch[slot].reset(); drain(); return cuda_fail(he, "cudaEventRecord"); }
+                { std::lock_guard<std::mutex> g(qm); fq.push_back(slot); }
+                qcv.notify_one();
             }
 #ifdef DTSDF_EXP_TIMELINE
             host_submit[k] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hk0).count();
