@@ -668,7 +668,11 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
                 fq.pop_front();
             }
             cudaError_t e;
-            while ((e = cudaEventQuery(c->ev_run[slot])) == cudaErrorNotReady) _mm_pause();
+            int spins = 0;               // spin briefly, then yield: the ranks of a node share its cores
+            while ((e = cudaEventQuery(c->ev_run[slot])) == cudaErrorNotReady) {
+                if (++spins < 64) _mm_pause();
+                else std::this_thread::yield();
+            }
             if (e != cudaSuccess) { c->latch[slot].reset(); continue; }    // a failed stream: nothing to expand
             expand_chunk(&c->chunk[slot]);
         }
