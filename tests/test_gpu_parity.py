@@ -253,7 +253,7 @@ def test_packed_and_plain_host_transfer_agree():
 
 
 def test_host_pipeline_many_small_chunks_and_destination_alignments():
-    """The host pipeline hands chunks to the expansion threads from a stream host function and
+    """The host pipeline hands chunks to the expansion threads from a finalizer thread and
     reuses its NSLOT chunk buffers: 1 MB chunks (2 frames each, ~150 chunks through 4 slots),
     repeated calls on one context, destinations at every 16-byte phase of a 64-byte line (the
     AVX-512 expansion peels code bytes up to the line boundary) - always the device run's bits."""
