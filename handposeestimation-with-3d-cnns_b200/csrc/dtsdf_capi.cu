@@ -656,7 +656,7 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
     std::deque<int> fq;
     bool qdone = false;
     std::thread fin;
-    if (packed) fin = std::thread([&] {
+    if (packed) try { fin = std::thread([&] {
         cudaSetDevice(c->device);
         for (;;) {
             int slot;
@@ -676,7 +676,7 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
             if (e != cudaSuccess) { c->latch[slot].reset(); continue; }    // a failed stream: nothing to expand
             expand_chunk(&c->chunk[slot]);
         }
-    });
+    }); } catch (...) { return DTSDF_ERR_ALLOC; }      // no thread to be had: nothing was started yet
     auto stop_finalizer = [&] {
         if (fin.joinable()) {
             { std::lock_guard<std::mutex> g(qm); qdone = true; }
