@@ -23,6 +23,18 @@ def test_library_exports_every_symbol_in_header():
     assert lib.dtsdf_error_string(-4).decode().startswith("no usable CUDA device")
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/dtsdf_b200.h is the drop-in boundary: it must compile as C99 (and C++11) on its own -
+    extern "C", plain pointers and sizes, no CUDA or torch types."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "dtsdf_b200.h"\nint main(void) { return DTSDF_OK; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
+                   check=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
+
+
 def test_default_config_matches_reference_constants():
     cfg = pkg.capi.default_config()
     assert (cfg.voxel_res, cfg.layout, cfg.bbox_mode) == (32, 0, 0)          # pre/process.py:88
