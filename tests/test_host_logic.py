@@ -35,6 +35,28 @@ def test_header_is_plain_c(tmp_path):
     subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
 
 
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no module of the package imports, loads or executes anything
+    under oracle/ (comments may cite it)."""
+    import ast
+    pkg_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "handposeestimation-with-3d-cnns_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for name in files:
+            path = os.path.join(dirpath, name)
+            if name.endswith(".py"):
+                tree = ast.parse(open(path).read())
+                for node in ast.walk(tree):
+                    if isinstance(node, ast.Import):
+                        assert not any(a.name.split(".")[0] == "oracle" for a in node.names), path
+                    if isinstance(node, ast.ImportFrom):
+                        assert (node.module or "").split(".")[0] != "oracle", path
+                    if isinstance(node, ast.Constant) and isinstance(node.value, str) and "\n" not in node.value:
+                        assert "libdtsdf_oracle" not in node.value and "oracle/_" not in node.value, path
+            elif name.endswith((".cu", ".cpp", ".h")):
+                text = open(path).read()
+                assert "#include \"../../oracle" not in text and "dtsdf_oracle.c\"" not in text, path
+
+
 def test_default_config_matches_reference_constants():
     cfg = pkg.capi.default_config()
     assert (cfg.voxel_res, cfg.layout, cfg.bbox_mode) == (32, 0, 0)          # pre/process.py:88
