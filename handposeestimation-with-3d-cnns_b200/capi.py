@@ -19,6 +19,8 @@ ERR_CUDA = -3
 ERR_NO_DEVICE = -4
 ERR_ALLOC = -5
 ERR_BAD_HEADER = -6
+ERR_INTERNAL = -7
+ERR_EMPTY_CLOUD = -8
 
 LAYOUT_CXYZ = 0
 LAYOUT_CZYX = 1
@@ -28,6 +30,7 @@ BBOX_GRID = 2
 OPT_PACKED_D2H = 1
 OPT_HOST_THREADS = 2
 OPT_CHUNK_MB = 3
+OPT_TEST_FAIL_CHUNK = 100
 STAT_D2H_BYTES = 1
 JOINT_CLAMP01 = 1
 JOINT_FLIP_Z = 2
@@ -84,6 +87,8 @@ _SIGNATURES = {
     "dtsdf_point_cloud_batch": (ctypes.c_int, [_i32, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_resample_extrema_batch": (ctypes.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_normalize_joints_batch": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "dtsdf_pack_volumes_batch": (ctypes.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "dtsdf_unpack_volumes_batch": (ctypes.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_ctx_create": (ctypes.c_int, [_i32, ctypes.POINTER(_vp)]),
     "dtsdf_ctx_destroy": (None, [_vp]),
     "dtsdf_ctx_set_option": (ctypes.c_int, [_vp, _i32, _i64]),
@@ -96,6 +101,10 @@ _SIGNATURES = {
     "dtsdf_process_begin_host": (ctypes.c_int, [_vp, ctypes.c_double, _i32, _vp, _i64, _vp, _vp, _vp]),
     "dtsdf_process_finish_host": (ctypes.c_int, [_vp, _cfgp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_normalize_joints_host": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "dtsdf_np_randint": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), _i32, _i32, _vp]),
+    "dtsdf_resample_indices": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), _i32, _vp, _i32, _vp]),
+    "dtsdf_process_host": (ctypes.c_int, [_vp, _cfgp, ctypes.c_double, _i32, _vp, _i64, _vp, _vp, _i32, _vp,
+                                          ctypes.POINTER(_i32), _vp, _vp, _vp, _vp]),
 }
 
 
@@ -122,9 +131,11 @@ def load_library():
 def check(rc):
     if rc == OK:
         return
+    if rc == ERR_EMPTY_CLOUD:
+        raise ValueError("low >= high")          # what the reference's np.random.randint(0, 0) raises
     lib = load_library()
     detail = lib.dtsdf_error_string(rc).decode()
-    if rc in (ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC):
+    if rc in (ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC, ERR_INTERNAL):
         extra = lib.dtsdf_last_cuda_error().decode()
         if extra:
             detail += " [" + extra + "]"
@@ -191,3 +202,49 @@ class PinnedBuffer:
             self.free()
         except Exception:
             pass
+
+
+class NumpyGlobalStream:
+    """The caller's global ``np.random`` stream (legacy MT19937) handed to the library and back:
+
+        with NumpyGlobalStream() as st:
+            lib.dtsdf_...(st.key_ptr, st.pos_ref, ...)
+
+    On exit - also when the call raised - ``np.random.set_state`` receives the advanced state, so what
+    follows in the caller's program draws what it would have drawn after the reference's own
+    ``np.random.randint`` calls (pre/process.py:75-80)."""
+
+    def __enter__(self):
+        import numpy as _np
+        self._st = _np.random.get_state()
+        if self._st[0] != "MT19937":
+            raise RuntimeError("np.random is not the legacy MT19937 stream")
+        self.key = _np.ascontiguousarray(self._st[1], dtype=_np.uint32).copy()
+        self.pos = _i32(int(self._st[2]))
+        self.key_ptr = self.key.ctypes.data
+        self.pos_ref = ctypes.byref(self.pos)
+        return self
+
+    def __exit__(self, *exc):
+        import numpy as _np
+        _np.random.set_state((self._st[0], self.key, int(self.pos.value), self._st[3], self._st[4]))
+        return False
+
+
+def np_randint(high, count):
+    """``np.random.randint(0, high, size=count)`` drawn by the library from the global stream (int32)."""
+    out = np.empty(int(count), dtype=np.int32)
+    with NumpyGlobalStream() as st:
+        check(load_library().dtsdf_np_randint(st.key_ptr, st.pos_ref, int(high), int(count), _ptr(out)))
+    return out
+
+
+def resample_indices(n_valid, point_num):
+    """The index vectors of ``DataProcess.set_length`` (pre/process.py:70-84) for frames with ``n_valid``
+    points each, in order, from the global ``np.random`` stream: int32[n, point_num]."""
+    n_valid = np.ascontiguousarray(n_valid, dtype=np.int32).reshape(-1)
+    out = np.empty((n_valid.size, int(point_num)), dtype=np.int32)
+    with NumpyGlobalStream() as st:
+        check(load_library().dtsdf_resample_indices(st.key_ptr, st.pos_ref, n_valid.size, _ptr(n_valid),
+                                                    int(point_num), _ptr(out)))
+    return out

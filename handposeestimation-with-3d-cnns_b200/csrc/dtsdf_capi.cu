@@ -17,6 +17,7 @@
 #include <deque>
 #include <functional>
 #include <mutex>
+#include <exception>
 #include <new>
 #include <thread>
 #include <vector>
@@ -41,6 +42,44 @@ int cuda_fail(cudaError_t e, const char* what) {
         cudaError_t e__ = (call);                       \
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
+
+// The C ABI never throws: every entry point that can reach an allocation or a std::thread runs its body
+// through this.
+template <typename F>
+int guarded(F&& body) noexcept {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "out of host memory (std::bad_alloc)");
+        return DTSDF_ERR_ALLOC;
+    } catch (const std::exception& e) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "C++ exception: %s", e.what());
+        return DTSDF_ERR_INTERNAL;
+    } catch (...) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "unknown C++ exception");
+        return DTSDF_ERR_INTERNAL;
+    }
+}
+
+// Makes `device` current for the duration of a host entry point and puts the caller's device back on
+// every exit (a process that drives several GPUs must not find its current device changed).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        err = cudaSetDevice(device);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) { cudaSetDevice(prev); cudaGetLastError(); }
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define USE_DEVICE(dev)                                                   \
+    DeviceGuard device_guard__(dev);                                      \
+    if (device_guard__.err != cudaSuccess) return cuda_fail(device_guard__.err, "cudaSetDevice")
 
 int check_cfg(const dtsdf_config* cfg) {
     if (!cfg) return DTSDF_ERR_INVALID_ARG;
@@ -91,19 +130,35 @@ struct MapBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-// a small persistent thread pool for the host-side expansion of packed volumes
+// A small persistent thread pool for the host-side expansion of packed volumes.  Jobs are plain records in
+// a fixed ring (no allocation on submit: nothing here can throw once the threads run).
+struct ExpandJob {
+    const void* chunk;          // dtsdf_ctx::ChunkRecord
+    int32_t f0, f1;             // frames [f0, f1) of the chunk
+};
+void run_expand_job(const ExpandJob& j);
+
 class Pool {
 public:
+    static const int CAP = 4096;             // >= chunks in flight x threads
     ~Pool() { stop(); }
-    void ensure(int n) {
+    void ensure(int n) {                     // may throw (std::thread): called before anything is in flight
         if ((int)th_.size() == n) return;
         stop();
         quit_ = false;
+        th_.reserve(n);
         for (int i = 0; i < n; ++i) th_.emplace_back([this] { run(); });
     }
-    void submit(std::function<void()> fn) {
-        { std::lock_guard<std::mutex> g(m_); q_.push_back(std::move(fn)); }
+    // false: the ring is full (the caller runs the job itself)
+    bool submit(const ExpandJob& j) noexcept {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            if (count_ == CAP) return false;
+            ring_[(head_ + count_) % CAP] = j;
+            ++count_;
+        }
         cv_.notify_one();
+        return true;
     }
     void stop() {
         { std::lock_guard<std::mutex> g(m_); quit_ = true; }
@@ -114,19 +169,21 @@ public:
 private:
     void run() {
         for (;;) {
-            std::function<void()> fn;
+            ExpandJob j;
             {
                 std::unique_lock<std::mutex> g(m_);
-                cv_.wait(g, [this] { return quit_ || !q_.empty(); });
-                if (q_.empty()) return;
-                fn = std::move(q_.front());
-                q_.pop_front();
+                cv_.wait(g, [this] { return quit_ || count_ > 0; });
+                if (count_ == 0) return;
+                j = ring_[head_];
+                head_ = (head_ + 1) % CAP;
+                --count_;
             }
-            fn();
+            run_expand_job(j);
         }
     }
     std::vector<std::thread> th_;
-    std::deque<std::function<void()>> q_;
+    ExpandJob ring_[CAP];
+    int head_ = 0, count_ = 0;
     std::mutex m_;
     std::condition_variable cv_;
     bool quit_ = false;
@@ -159,18 +216,15 @@ struct Latch {
 struct dtsdf_ctx {
     int device = 0;
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
-#ifdef DTSDF_EXP_NSLOT          /* dev experiment */
-    static const int NSLOT = DTSDF_EXP_NSLOT;
-#else
     static const int NSLOT = 4;                 // chunks in flight
-#endif
     // packed device -> host transfer
     int opt_packed = 1;
     int opt_threads = 0;                        // 0 = hardware concurrency
     int opt_chunk_mb = 64;
+    int opt_fail_chunk = -1;                    // testing: the host pipeline fails before submitting this chunk
     Pool pool;
     DevBuf d_cnt[NSLOT], d_loff[NSLOT], d_codes[NSLOT], d_lits[NSLOT];
-    MapBuf m_codes[NSLOT], m_loff[NSLOT], m_lits[NSLOT];
+    MapBuf m_codes[NSLOT], m_loff[NSLOT], m_lits[NSLOT], m_maxl[NSLOT], m_mid[NSLOT];
     Latch latch[NSLOT];
     std::atomic<long long> stat_d2h_bytes{0};
     // what the finalizer thread needs to hand a chunk to the expansion threads (owned by the slot: rewritten only after latch[slot].wait())
@@ -180,9 +234,16 @@ struct dtsdf_ctx {
         int32_t nf;
         size_t r3, vol_floats;
         float* dst;                              // h_vol + f0 * vol_floats
+        float* dst_maxl;                         // h_maxl + f0 or null
+        float* dst_mid;                          // h_mid + 3 f0 or null
+        double* dst_pc;                          // process mode: h_pc + f0 * point_num * 3 or null
+        size_t pc_doubles;                       // point_num * 3
         long long fixed_bytes;                   // PCIe bytes of the chunk apart from the literal stream
     } chunk[NSLOT];
     DevBuf d_depth[NSLOT], d_off[NSLOT], d_hdr[NSLOT], d_aux[NSLOT];
+    // dtsdf_process_host: per-chunk resampling indices (pinned staging + device), gathered clouds, extrema
+    MapBuf m_idx[NSLOT], m_pc[NSLOT];
+    DevBuf p_idx[NSLOT], p_pc[NSLOT], p_ext[NSLOT];
     DevBuf d_vol[NSLOT], d_maxl[NSLOT], d_mid[NSLOT];
     cudaEvent_t ev_in[NSLOT] = {}, ev_run[NSLOT] = {}, ev_out[NSLOT] = {};
     // point-cloud path
@@ -210,6 +271,8 @@ const char* dtsdf_error_string(int code) {
         case DTSDF_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
         case DTSDF_ERR_ALLOC: return "out of memory";
         case DTSDF_ERR_BAD_HEADER: return "frame header with empty or oversize bounding box";
+        case DTSDF_ERR_INTERNAL: return "internal error (C++ exception caught at the C boundary)";
+        case DTSDF_ERR_EMPTY_CLOUD: return "a frame has no point to draw from (np.random.randint: low >= high)";
         default: return "unknown error";
     }
 }
@@ -450,6 +513,28 @@ int dtsdf_normalize_joints_batch(int32_t n_frames, const float* d_joints, const 
     return DTSDF_OK;
 }
 
+int dtsdf_pack_volumes_batch(int32_t voxel_res, int32_t n_frames, const float* d_vol, uint8_t* d_codes,
+                             uint32_t* d_lit_count, float* d_lits, void* stream) {
+    if (voxel_res != 32 && voxel_res != 48 && voxel_res != 64) return DTSDF_ERR_UNSUPPORTED;
+    if (n_frames < 0) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!d_vol || !d_codes || !d_lit_count || !d_lits) return DTSDF_ERR_INVALID_ARG;
+    const int r3 = voxel_res * voxel_res * voxel_res;
+    CK(dtsdf::launch_pack_strided(n_frames, r3, d_vol, 3ll * r3, d_codes, d_lit_count, d_lits, (cudaStream_t)stream));
+    return DTSDF_OK;
+}
+
+int dtsdf_unpack_volumes_batch(int32_t voxel_res, int32_t n_frames, const uint8_t* d_codes,
+                               const uint32_t* d_lit_count, const float* d_lits, float* d_out_vol, void* stream) {
+    if (voxel_res != 32 && voxel_res != 48 && voxel_res != 64) return DTSDF_ERR_UNSUPPORTED;
+    if (n_frames < 0) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!d_codes || !d_lit_count || !d_lits || !d_out_vol) return DTSDF_ERR_INVALID_ARG;
+    const int r3 = voxel_res * voxel_res * voxel_res;
+    CK(dtsdf::launch_unpack_strided(n_frames, r3, d_codes, d_lit_count, d_lits, 3ll * r3, d_out_vol, (cudaStream_t)stream));
+    return DTSDF_OK;
+}
+
 // ------------------------------------------------------------------ context
 int dtsdf_ctx_create(int32_t device, dtsdf_ctx** out) {
     if (!out) return DTSDF_ERR_INVALID_ARG;
@@ -459,7 +544,7 @@ int dtsdf_ctx_create(int32_t device, dtsdf_ctx** out) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
     if (n == 0) return DTSDF_ERR_NO_DEVICE;
     if (device < 0 || device >= n) return DTSDF_ERR_INVALID_ARG;
-    CK(cudaSetDevice(device));
+    USE_DEVICE(device);
     int major = 0;
     CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
     if (major != 10) {
@@ -489,13 +574,14 @@ int dtsdf_ctx_create(int32_t device, dtsdf_ctx** out) {
 
 void dtsdf_ctx_destroy(dtsdf_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < dtsdf_ctx::NSLOT; ++i) {
         c->d_depth[i].release(); c->d_off[i].release(); c->d_hdr[i].release(); c->d_aux[i].release();
         c->d_vol[i].release(); c->d_maxl[i].release(); c->d_mid[i].release();
         c->d_cnt[i].release(); c->d_loff[i].release(); c->d_codes[i].release(); c->d_lits[i].release();
-        c->m_codes[i].release(); c->m_loff[i].release(); c->m_lits[i].release();
+        c->m_codes[i].release(); c->m_loff[i].release(); c->m_lits[i].release(); c->m_maxl[i].release(); c->m_mid[i].release();
+        c->m_idx[i].release(); c->m_pc[i].release(); c->p_idx[i].release(); c->p_pc[i].release(); c->p_ext[i].release();
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
         if (c->ev_run[i]) cudaEventDestroy(c->ev_run[i]);
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
@@ -526,6 +612,9 @@ int dtsdf_ctx_set_option(dtsdf_ctx* c, int32_t option, int64_t value) {
             if (value < 1 || value > 4096) return DTSDF_ERR_INVALID_ARG;
             c->opt_chunk_mb = (int)value;
             return DTSDF_OK;
+        case DTSDF_OPT_TEST_FAIL_CHUNK:
+            c->opt_fail_chunk = value < 0 ? -1 : (int)std::min<int64_t>(value, 1 << 30);
+            return DTSDF_OK;
         default:
             return DTSDF_ERR_UNSUPPORTED;
     }
@@ -550,177 +639,171 @@ void dtsdf_host_free(void* ptr) {
     if (ptr) { cudaFreeHost(ptr); cudaGetLastError(); }
 }
 
+}  // extern "C"
+
 // A chunk's packed form has arrived in host memory: split its frames over the expansion threads
-// (called by the finalizer thread of dtsdf_voxelize_host).
-#ifdef DTSDF_EXP_TIMELINE
-static std::atomic<long long> g_tl_decode_us{0};
-#endif
-static void expand_chunk(void* p) {
-    const dtsdf_ctx::ChunkRecord* r = static_cast<const dtsdf_ctx::ChunkRecord*>(p);
+// (called by the finalizer thread of dtsdf_voxelize_host).  Never throws, never allocates.
+static void expand_chunk(const dtsdf_ctx::ChunkRecord* r) {
+    dtsdf_ctx* c = r->ctx;
+    const unsigned long long* loff = (const unsigned long long*)c->m_loff[r->slot].p;
+    c->stat_d2h_bytes += r->fixed_bytes + 12ll * (long long)loff[r->nf];
+    // max_l / mid_p came back through the slot's pinned staging buffers (the caller's arrays may be
+    // pageable: a device -> host copy straight into them would block the submitting thread)
+    if (r->dst_maxl) memcpy(r->dst_maxl, c->m_maxl[r->slot].p, (size_t)r->nf * 4);
+    if (r->dst_mid) memcpy(r->dst_mid, c->m_mid[r->slot].p, (size_t)r->nf * 12);
+    for (int j = 0; j < r->jobs; ++j) {
+        ExpandJob job;
+        job.chunk = r;
+        job.f0 = (int32_t)((int64_t)r->nf * j / r->jobs);
+        job.f1 = (int32_t)((int64_t)r->nf * (j + 1) / r->jobs);
+        if (!c->pool.submit(job)) run_expand_job(job);
+    }
+}
+
+namespace {
+void run_expand_job(const ExpandJob& j) {
+    const dtsdf_ctx::ChunkRecord* r = static_cast<const dtsdf_ctx::ChunkRecord*>(j.chunk);
     dtsdf_ctx* c = r->ctx;
     const unsigned char* codes = (const unsigned char*)c->m_codes[r->slot].p;
     const unsigned long long* loff = (const unsigned long long*)c->m_loff[r->slot].p;
     const float* lits = (const float*)c->m_lits[r->slot].p;
-    c->stat_d2h_bytes += r->fixed_bytes + 12ll * (long long)loff[r->nf];
-    Latch* latch = &c->latch[r->slot];
-    const int32_t nf = r->nf;
-    const int jobs = r->jobs;
-    const size_t r3 = r->r3, vol_floats = r->vol_floats;
-    float* dst = r->dst;
-    for (int j = 0; j < jobs; ++j) {
-        const int32_t a0 = (int32_t)((int64_t)nf * j / jobs), a1 = (int32_t)((int64_t)nf * (j + 1) / jobs);
-        c->pool.submit([=] {
-#ifdef DTSDF_EXP_TIMELINE
-            const auto j0 = std::chrono::steady_clock::now();
-#endif
-#ifndef DTSDF_EXP_SKIP_DECODE   /* dev ablation: the pipeline without the host expansion */
-            for (int32_t f = a0; f < a1; ++f)
-                dtsdf::decode_frame(codes + (size_t)f * (r3 / 4), lits + 3 * loff[f], (size_t)(loff[f + 1] - loff[f]), r3,
-                                    dst + (size_t)f * vol_floats);
-#endif
-#ifdef DTSDF_EXP_TIMELINE
-            g_tl_decode_us += (long long)std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - j0).count();
-#endif
-            latch->done();
-        });
-    }
+    if (r->dst_pc && j.f1 > j.f0)               // the sampled clouds came back through pinned staging
+        memcpy(r->dst_pc + (size_t)j.f0 * r->pc_doubles, (const double*)c->m_pc[r->slot].p + (size_t)j.f0 * r->pc_doubles,
+               (size_t)(j.f1 - j.f0) * r->pc_doubles * 8);
+    for (int32_t f = j.f0; f < j.f1; ++f)
+        dtsdf::decode_frame(codes + (size_t)f * (r->r3 / 4), lits + 3 * loff[f], (size_t)(loff[f + 1] - loff[f]), r->r3,
+                            r->dst + (size_t)f * r->vol_floats);
+    c->latch[r->slot].done();
 }
+}  // namespace
 
 // ------------------------------------------------------------------ host pipeline
 // The batch is cut into chunks of whole frames; chunk k's host->device copy (s_in),
 // kernel (s_run) and device->host copy (s_out) run on their own streams with NSLOT
 // chunk buffers in flight, so for large batches the PCIe traffic in both directions
 // overlaps the kernel.
-int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
-                        const float* h_depth, int64_t packed_len, const int64_t* h_off,
-                        const int32_t* h_hdr, const float* h_aux, float* h_vol, float* h_maxl,
-                        float* h_mid) {
-    if (!c) return DTSDF_ERR_INVALID_ARG;
-    int rc = check_cfg(cfg);
-    if (rc != DTSDF_OK) return rc;
-    if (n_frames < 0 || packed_len < 0) return DTSDF_ERR_INVALID_ARG;
-    if (n_frames == 0) return DTSDF_OK;
-    if (!h_depth || !h_off || !h_hdr || !h_vol) return DTSDF_ERR_INVALID_ARG;
-    if (cfg->bbox_mode != DTSDF_BBOX_PIXELS && !h_aux) return DTSDF_ERR_INVALID_ARG;
-    const int aux_w = cfg->bbox_mode == DTSDF_BBOX_EXTREMA ? 6 : (cfg->bbox_mode == DTSDF_BBOX_GRID ? 5 : 0);
-    const size_t R = (size_t)cfg->voxel_res;
-    const size_t vol_floats = 3 * R * R * R;
+//
+// Error handling: the submission loop is one function (submit_chunks) whose every failure returns a
+// code; its caller then takes the ONE exit path: cancel what has not been handed to the expansion threads,
+// join the finalizer, wait for every expansion job that did start, synchronise the three streams - so
+// that nothing, neither a DMA nor a host thread, writes into the caller's buffers after the call has
+// returned, whatever the outcome.
+namespace {
 
-    // validate headers / offsets on the host (the per-frame shims raise on these)
-    for (int32_t i = 0; i < n_frames; ++i) {
-        const int32_t* h = h_hdr + 6 * (size_t)i;
-        if (!header_ok(h)) return DTSDF_ERR_BAD_HEADER;
-        const int64_t n = ((int64_t)h[4] - h[2]) * ((int64_t)h[5] - h[3]);
-        if (h_off[i] < 0 || (h_off[i] & 3) || h_off[i] + ((n + 3) & ~(int64_t)3) > packed_len)
-            return DTSDF_ERR_INVALID_ARG;
-        if (i > 0 && h_off[i] < h_off[i - 1]) return DTSDF_ERR_INVALID_ARG;   // chunking needs ascending offsets
+// pre/process.py:70-84 for n frames in order: fewer points than point_num -> all of them once, then random
+// repeats; otherwise point_num draws with replacement.  A frame without points makes the reference's
+// np.random.randint(0, 0) raise ValueError ("low >= high"): DTSDF_ERR_EMPTY_CLOUD, the stream stays where the
+// reference's would (advanced by the frames before it).
+int resample_indices(uint32_t* key, int* pos, int32_t n, const int32_t* n_valid, int32_t point_num, int32_t* out) {
+    for (int32_t i = 0; i < n; ++i) {
+        const int32_t nv = n_valid[i];
+        int32_t* idx = out + (size_t)i * point_num;
+        if (nv <= 0) return DTSDF_ERR_EMPTY_CLOUD;
+        if (nv < point_num) {
+            for (int32_t k = 0; k < nv; ++k) idx[k] = k;
+            dtsdf::np_legacy_randint(key, pos, (uint32_t)nv, point_num - nv, idx + nv);
+        } else {
+            dtsdf::np_legacy_randint(key, pos, (uint32_t)nv, point_num, idx);
+        }
     }
-    CK(cudaSetDevice(c->device));
+    return DTSDF_OK;
+}
 
-    // chunk size: about 64 MB of output per chunk by default, at least one frame
-    int32_t per_chunk = (int32_t)std::max<size_t>(1, ((size_t)c->opt_chunk_mb << 20) / (vol_floats * 4));
-    if (per_chunk > n_frames) per_chunk = n_frames;
-    const int nchunk = (n_frames + per_chunk - 1) / per_chunk;
-    std::vector<int64_t> rebased;
-
-    // packed device -> host transfer: the GPU packs each chunk into mapped pinned memory, host
-    // threads expand it into h_vol while the next chunks are in flight
-    // Small batches go back as plain copies even when the packed transfer is on: its extra kernels,
-    // stream hand-offs and thread wake-ups cost more than they save below ~32 frames (one frame:
-    // 350 us packed, 110 us plain; 64 frames: 26 us per frame packed, 33 us plain).
-    const bool packed = c->opt_packed != 0 && (size_t)n_frames * vol_floats * 4 >= ((size_t)16 << 20);
-    // A single plain chunk needs no pipeline: everything on one stream, one synchronisation.
-    const bool single = !packed && nchunk == 1;
-    cudaStream_t const st_in = single ? c->s_run : c->s_in;
-    cudaStream_t const st_out = single ? c->s_run : c->s_out;
-    const size_t r3 = R * R * R;
-    c->stat_d2h_bytes = packed ? 0ll : (long long)n_frames * (long long)(vol_floats * 4 + (h_maxl ? 4 : 0) + (h_mid ? 12 : 0));
-    int nthreads = 1;
-    if (packed) {
-        // default: three quarters of the hardware threads, at most 8: the expansion saturates the host's
-        // memory system with 8 threads (16-core box: 8 and 12 threads alike; 32-core box: 286 k volumes/s
-        // with 8, 271 k with 12, 234 k with 16), and the calling thread and the CUDA driver need cores too
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        nthreads = c->opt_threads > 0 ? c->opt_threads : (int)std::min(8u, std::max(1u, hw - hw / 4));
-        c->pool.ensure(nthreads);
-    }
-    // A chunk is handed to the expansion threads as soon as its last device -> host copy has landed: a
-    // finalizer thread (alive for the duration of this call) takes the chunks in order and polls the
-    // event recorded behind each one's copies.  (A stream host function - cudaLaunchHostFunc - did the same
-    // job at first: it holds its stream until it returns and costs ~0.2 ms per chunk; polling took a
-    // call over 8,500 frames from 33.5 ms to 28.6 ms and made 16-32 MB chunks as fast as 64 MB ones.)
-    // The submitting thread never waits for the GPU; before reusing a slot it waits for the host
-    // threads to be done with the chunk that used it last (latch[slot]).
+struct HostPipeline {
+    dtsdf_ctx* c;
+    const dtsdf_config* cfg;
+    int32_t n_frames;
+    const float* h_depth;
+    const int64_t* h_off;
+    const int32_t* h_hdr;
+    const float* h_aux;
+    float* h_vol;
+    float* h_maxl;
+    float* h_mid;
+    int aux_w;
+    size_t r3, vol_floats;
+    int32_t per_chunk;
+    int nchunk;
+    bool packed, single;
+    int nthreads;
+    // DataProcess.process() mode (dtsdf_process_host): crops, tables and point clouds of the whole batch are
+    // resident in the context (b_*); per chunk the host draws the resampling indices from the caller's
+    // MT19937 state, the device gathers the sampled clouds and reduces the extrema that feed the voxeliser
+    bool process_mode = false;
+    int32_t point_num = 0;
+    uint32_t* mt_key = nullptr;
+    int* mt_pos = nullptr;
+    double* h_pc = nullptr;
+    // finalizer: takes the chunks in order, polls the event behind each one's last copy, hands the
+    // chunk to the expansion threads
     std::mutex qm;
     std::condition_variable qcv;
-    std::deque<int> fq;
+    int fq[dtsdf_ctx::NSLOT * 2];            // slots queued for the finalizer (at most NSLOT at a time)
+    int fq_head = 0, fq_count = 0;
     bool qdone = false;
+    std::atomic<bool> cancel{false};
     std::thread fin;
-    if (packed) try { fin = std::thread([&] {
+
+    void finalizer() {
         cudaSetDevice(c->device);
         for (;;) {
             int slot;
             {
                 std::unique_lock<std::mutex> lk(qm);
-                qcv.wait(lk, [&] { return !fq.empty() || qdone; });
-                if (fq.empty()) return;
-                slot = fq.front();
-                fq.pop_front();
+                qcv.wait(lk, [&] { return fq_count > 0 || qdone; });
+                if (fq_count == 0) return;
+                slot = fq[fq_head];
+                fq_head = (fq_head + 1) % (dtsdf_ctx::NSLOT * 2);
+                --fq_count;
             }
-            cudaError_t e;
+            cudaError_t e = cudaSuccess;
             int spins = 0;               // spin briefly, then yield: the ranks of a node share its cores
-            while ((e = cudaEventQuery(c->ev_run[slot])) == cudaErrorNotReady) {
+            while (!cancel.load(std::memory_order_relaxed) &&
+                   (e = cudaEventQuery(c->ev_run[slot])) == cudaErrorNotReady) {
                 if (++spins < 64) _mm_pause();
                 else std::this_thread::yield();
             }
-            if (e != cudaSuccess) { c->latch[slot].reset(); continue; }    // a failed stream: nothing to expand
+            // a failed stream or a cancelled call: nothing of this chunk reaches the caller's buffers
+            if (e != cudaSuccess || cancel.load()) { cudaGetLastError(); c->latch[slot].reset(); continue; }
             expand_chunk(&c->chunk[slot]);
         }
-    }); } catch (...) { return DTSDF_ERR_ALLOC; }      // no thread to be had: nothing was started yet
-    auto stop_finalizer = [&] {
+    }
+    void enqueue_for_finalizer(int slot) {
+        { std::lock_guard<std::mutex> g(qm); fq[(fq_head + fq_count) % (dtsdf_ctx::NSLOT * 2)] = slot; ++fq_count; }
+        qcv.notify_one();
+    }
+    void stop_finalizer() {
         if (fin.joinable()) {
             { std::lock_guard<std::mutex> g(qm); qdone = true; }
             qcv.notify_all();
-            fin.join();                  // it first works off what is queued
+            fin.join();                  // it first works off (or, cancelled, drops) what is queued
         }
-    };
-    struct AtExit {                      // every return path joins the thread
-        std::function<void()> fn;
-        ~AtExit() { fn(); }
-    } at_exit{stop_finalizer};
-    auto drain = [&]() {
-        stop_finalizer();
-        for (int i = 0; i < dtsdf_ctx::NSLOT; ++i) c->latch[i].wait();
-    };
+    }
 
-#ifdef DTSDF_EXP_TIMELINE       /* dev instrumentation: where a chunk's time goes on each stream */
-    struct TL { cudaEvent_t e[8]; };
-    std::vector<TL> tl(nchunk);
-    for (auto& t : tl) for (auto& e : t.e) cudaEventCreate(&e);
-    const auto host_t0 = std::chrono::steady_clock::now();
-    std::vector<double> host_submit(nchunk), host_wait(nchunk);
-#define TLREC(i, st) cudaEventRecord(tl[k].e[i], st)
-#else
-#define TLREC(i, st) ((void)0)
-#endif
+    void configure();          // chunking, transfer route and thread count from the context options
+    int submit_chunks();
+    int run();
+};
+
+int HostPipeline::submit_chunks() {
+    const cudaStream_t st_in = single ? c->s_run : c->s_in;
+    const cudaStream_t st_out = single ? c->s_run : c->s_out;
+    std::vector<int64_t> rebased;
+    int rc;
     for (int k = 0; k < nchunk; ++k) {
-#ifdef DTSDF_EXP_TIMELINE
-        const auto hk0 = std::chrono::steady_clock::now();
-#endif
-#ifdef DTSDF_EXP_DEPTH          /* dev experiment: fewer chunks in flight */
-        const int slot = k % DTSDF_EXP_DEPTH;
-#else
         const int slot = k % dtsdf_ctx::NSLOT;
-#endif
         const int32_t f0 = k * per_chunk;
         const int32_t nf = std::min(per_chunk, n_frames - f0);
-        const int64_t e0 = h_off[f0];
-        const int32_t* hl = h_hdr + 6 * (size_t)(f0 + nf - 1);
-        const int64_t nlast = ((int64_t)hl[4] - hl[2]) * ((int64_t)hl[5] - hl[3]);
-        const int64_t e1 = h_off[f0 + nf - 1] + ((nlast + 3) & ~(int64_t)3);
+        int64_t e0 = 0, e1 = 0;
         int32_t max_px = 0;
-        rebased.resize(nf);
-        for (int32_t i = 0; i < nf; ++i) {
+        if (!process_mode) {
+            const int32_t* hl = h_hdr + 6 * (size_t)(f0 + nf - 1);
+            const int64_t nlast = ((int64_t)hl[4] - hl[2]) * ((int64_t)hl[5] - hl[3]);
+            e0 = h_off[f0];
+            e1 = h_off[f0 + nf - 1] + ((nlast + 3) & ~(int64_t)3);
+            rebased.resize(nf);
+        }
+        for (int32_t i = 0; !process_mode && i < nf; ++i) {
             const int32_t* h = h_hdr + 6 * (size_t)(f0 + i);
             const int64_t n = ((int64_t)h[4] - h[2]) * ((int64_t)h[5] - h[3]);
             max_px = std::max<int32_t>(max_px, (int32_t)n);
@@ -729,100 +812,111 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
         // the slot's buffers are free once its previous chunk has left them: plain mode, its D2H
         // has finished (which implies its kernel has); packed mode, the host threads are done
         // expanding it (its kernels were waited for before they started)
-#ifdef DTSDF_EXP_TIMELINE
-        const auto hl0 = std::chrono::steady_clock::now();
-#endif
         if (packed) c->latch[slot].wait();
         else if (k >= dtsdf_ctx::NSLOT) CK(cudaEventSynchronize(c->ev_out[slot]));
-#ifdef DTSDF_EXP_TIMELINE
-        host_wait[k] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hl0).count();
-#endif
-        auto fail = [&](int code) { if (packed) drain(); return code; };
-        if ((rc = c->d_depth[slot].reserve((size_t)(e1 - e0) * 4)) != DTSDF_OK) return fail(rc);
-        if ((rc = c->d_off[slot].reserve((size_t)nf * 8)) != DTSDF_OK) return fail(rc);
-        if ((rc = c->d_hdr[slot].reserve((size_t)nf * 24)) != DTSDF_OK) return fail(rc);
-        if (aux_w && (rc = c->d_aux[slot].reserve((size_t)nf * aux_w * 4)) != DTSDF_OK) return fail(rc);
-        if ((rc = c->d_vol[slot].reserve((size_t)nf * vol_floats * 4)) != DTSDF_OK) return fail(rc);
-        if ((rc = c->d_maxl[slot].reserve((size_t)nf * 4)) != DTSDF_OK) return fail(rc);
-        if ((rc = c->d_mid[slot].reserve((size_t)nf * 12)) != DTSDF_OK) return fail(rc);
+        if (k == c->opt_fail_chunk) CK(cudaErrorUnknown);          // injected failure (DTSDF_OPT_TEST_FAIL_CHUNK)
+        if (!process_mode) {
+            if ((rc = c->d_depth[slot].reserve((size_t)(e1 - e0) * 4)) != DTSDF_OK) return rc;
+            if ((rc = c->d_off[slot].reserve((size_t)nf * 8)) != DTSDF_OK) return rc;
+            if ((rc = c->d_hdr[slot].reserve((size_t)nf * 24)) != DTSDF_OK) return rc;
+        }
+        if (aux_w && (rc = c->d_aux[slot].reserve((size_t)nf * aux_w * 4)) != DTSDF_OK) return rc;
+        if ((rc = c->d_vol[slot].reserve((size_t)nf * vol_floats * 4)) != DTSDF_OK) return rc;
+        if ((rc = c->d_maxl[slot].reserve((size_t)nf * 4)) != DTSDF_OK) return rc;
+        if ((rc = c->d_mid[slot].reserve((size_t)nf * 12)) != DTSDF_OK) return rc;
         if (packed) {
-            if ((rc = c->d_cnt[slot].reserve((size_t)nf * 4)) != DTSDF_OK) return fail(rc);
-            if ((rc = c->d_loff[slot].reserve((size_t)(nf + 1) * 8)) != DTSDF_OK) return fail(rc);
-            if ((rc = c->m_codes[slot].reserve((size_t)nf * (r3 / 4))) != DTSDF_OK) return fail(rc);
-            if ((rc = c->m_loff[slot].reserve((size_t)(nf + 1) * 8)) != DTSDF_OK) return fail(rc);
-            if ((rc = c->m_lits[slot].reserve((size_t)nf * vol_floats * 4 + 16)) != DTSDF_OK) return fail(rc);   // worst case
-            if ((rc = c->d_codes[slot].reserve((size_t)nf * (r3 / 4))) != DTSDF_OK) return fail(rc);
-            if ((rc = c->d_lits[slot].reserve((size_t)nf * vol_floats * 4 + 16)) != DTSDF_OK) return fail(rc);
+            if ((rc = c->d_cnt[slot].reserve((size_t)nf * 4)) != DTSDF_OK) return rc;
+            if ((rc = c->d_loff[slot].reserve((size_t)(nf + 1) * 8)) != DTSDF_OK) return rc;
+            if ((rc = c->m_codes[slot].reserve((size_t)nf * (r3 / 4))) != DTSDF_OK) return rc;
+            if ((rc = c->m_loff[slot].reserve((size_t)(nf + 1) * 8)) != DTSDF_OK) return rc;
+            if ((rc = c->m_lits[slot].reserve((size_t)nf * vol_floats * 4 + 16)) != DTSDF_OK) return rc;   // worst case
+            if ((rc = c->m_maxl[slot].reserve((size_t)nf * 4)) != DTSDF_OK) return rc;
+            if ((rc = c->m_mid[slot].reserve((size_t)nf * 12)) != DTSDF_OK) return rc;
+            if ((rc = c->d_codes[slot].reserve((size_t)nf * (r3 / 4))) != DTSDF_OK) return rc;
+            if ((rc = c->d_lits[slot].reserve((size_t)nf * vol_floats * 4 + 16)) != DTSDF_OK) return rc;
         }
 
-        // H2D on s_in.  `rebased` is pageable host memory: cudaMemcpyAsync stages it before
-        // returning, so reusing the vector for the next chunk is safe.
-        TLREC(0, c->s_in);
-        CK(cudaMemcpyAsync(c->d_depth[slot].p, h_depth + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, st_in));
-        CK(cudaMemcpyAsync(c->d_off[slot].p, rebased.data(), (size_t)nf * 8, cudaMemcpyHostToDevice, st_in));
-        CK(cudaMemcpyAsync(c->d_hdr[slot].p, h_hdr + 6 * (size_t)f0, (size_t)nf * 24, cudaMemcpyHostToDevice, st_in));
-        if (aux_w)
-            CK(cudaMemcpyAsync(c->d_aux[slot].p, h_aux + (size_t)aux_w * f0, (size_t)nf * aux_w * 4,
-                               cudaMemcpyHostToDevice, st_in));
-        TLREC(1, c->s_in);
+        if (!process_mode) {
+            // H2D on s_in.  `rebased` is pageable host memory: cudaMemcpyAsync stages it before
+            // returning, so reusing the vector for the next chunk is safe.
+            CK(cudaMemcpyAsync(c->d_depth[slot].p, h_depth + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, st_in));
+            CK(cudaMemcpyAsync(c->d_off[slot].p, rebased.data(), (size_t)nf * 8, cudaMemcpyHostToDevice, st_in));
+            CK(cudaMemcpyAsync(c->d_hdr[slot].p, h_hdr + 6 * (size_t)f0, (size_t)nf * 24, cudaMemcpyHostToDevice, st_in));
+            if (aux_w)
+                CK(cudaMemcpyAsync(c->d_aux[slot].p, h_aux + (size_t)aux_w * f0, (size_t)nf * aux_w * 4,
+                                   cudaMemcpyHostToDevice, st_in));
+        } else {
+            // pre/process.py:70-84 for the frames of this chunk, in frame order, on the caller's stream
+            const size_t ni = (size_t)nf * point_num;
+            if ((rc = c->m_idx[slot].reserve(ni * 4)) != DTSDF_OK) return rc;
+            if ((rc = c->p_idx[slot].reserve(ni * 4)) != DTSDF_OK) return rc;
+            if ((rc = c->p_ext[slot].reserve((size_t)nf * 24)) != DTSDF_OK) return rc;
+            if (h_pc) {
+                if ((rc = c->p_pc[slot].reserve(ni * 24)) != DTSDF_OK) return rc;
+                if (packed && (rc = c->m_pc[slot].reserve(ni * 24)) != DTSDF_OK) return rc;
+            }
+            rc = resample_indices(mt_key, mt_pos, nf, c->b_nvalid_h.data() + f0, point_num, (int32_t*)c->m_idx[slot].p);
+            if (rc != DTSDF_OK) return rc;
+            CK(cudaMemcpyAsync(c->p_idx[slot].p, c->m_idx[slot].p, ni * 4, cudaMemcpyHostToDevice, st_in));
+        }
         if (!single) {
             CK(cudaEventRecord(c->ev_in[slot], c->s_in));
             CK(cudaStreamWaitEvent(c->s_run, c->ev_in[slot], 0));
         }
 
-        // kernel on s_run
-        TLREC(2, c->s_run);
-        rc = dtsdf_voxelize_batch(cfg, nf, (const float*)c->d_depth[slot].p, (const int64_t*)c->d_off[slot].p,
-                                  (const int32_t*)c->d_hdr[slot].p, aux_w ? (const float*)c->d_aux[slot].p : nullptr,
-                                  max_px, (float*)c->d_vol[slot].p, (float*)c->d_maxl[slot].p,
-                                  (float*)c->d_mid[slot].p, c->s_run);
-        if (rc != DTSDF_OK) return fail(rc);
+        // kernel(s) on s_run
+        if (!process_mode) {
+            rc = dtsdf_voxelize_batch(cfg, nf, (const float*)c->d_depth[slot].p, (const int64_t*)c->d_off[slot].p,
+                                      (const int32_t*)c->d_hdr[slot].p, aux_w ? (const float*)c->d_aux[slot].p : nullptr,
+                                      max_px, (float*)c->d_vol[slot].p, (float*)c->d_maxl[slot].p,
+                                      (float*)c->d_mid[slot].p, c->s_run);
+        } else {
+            rc = dtsdf_resample_extrema_batch(nf, point_num, (const double*)c->b_points.p, (const int64_t*)c->b_poff.p + f0,
+                                              (const int32_t*)c->p_idx[slot].p, h_pc ? (double*)c->p_pc[slot].p : nullptr,
+                                              (float*)c->p_ext[slot].p, c->s_run);
+            if (rc == DTSDF_OK)
+                rc = dtsdf_voxelize_batch(cfg, nf, (const float*)c->b_depth.p, (const int64_t*)c->b_off.p + f0,
+                                          (const int32_t*)c->b_hdr.p + 6 * (size_t)f0, (const float*)c->p_ext[slot].p,
+                                          c->b_max_px, (float*)c->d_vol[slot].p, (float*)c->d_maxl[slot].p,
+                                          (float*)c->d_mid[slot].p, c->s_run);
+        }
+        if (rc != DTSDF_OK) return rc;
 
         if (packed) {
             // pack into device memory on the kernel stream; then, on s_out so that the next chunk's
             // kernels are not held up by PCIe: the literal stream (device-known size) by a copy kernel
             // into mapped pinned memory, codes and offsets (fixed size) by the copy engine.  (With
             // everything on one stream the transfers were 60 % of that stream's time.)
-            TLREC(3, c->s_run);
             void* dv_lits = nullptr;
             CK(cudaHostGetDevicePointer(&dv_lits, c->m_lits[slot].p, 0));
-            cudaError_t pe = dtsdf::launch_pack(nf, (int)r3, (const float*)c->d_vol[slot].p, (unsigned*)c->d_cnt[slot].p,
-                                                (unsigned long long*)c->d_loff[slot].p, nullptr,
-                                                (unsigned char*)c->d_codes[slot].p, (float*)c->d_lits[slot].p, c->s_run);
-            TLREC(4, c->s_run);
-            if (pe != cudaSuccess) { drain(); return cuda_fail(pe, "launch_pack"); }
+            CK(dtsdf::launch_pack(nf, (int)r3, (const float*)c->d_vol[slot].p, (unsigned*)c->d_cnt[slot].p,
+                                  (unsigned long long*)c->d_loff[slot].p, nullptr,
+                                  (unsigned char*)c->d_codes[slot].p, (float*)c->d_lits[slot].p, c->s_run));
             CK(cudaEventRecord(c->ev_out[slot], c->s_run));          // packed mode: "chunk packed"
             CK(cudaStreamWaitEvent(c->s_out, c->ev_out[slot], 0));
-            TLREC(7, c->s_out);
-#ifndef DTSDF_EXP_SKIP_PUSH     /* dev ablation: the literal stream stays on the device */
-            pe = dtsdf::launch_pack_push(nf, (const float*)c->d_lits[slot].p,
-                                         (const unsigned long long*)c->d_loff[slot].p, (float*)dv_lits, c->s_out);
-            if (pe != cudaSuccess) { drain(); return cuda_fail(pe, "launch_pack_push"); }
-#endif
-            TLREC(5, c->s_out);
+            CK(dtsdf::launch_pack_push(nf, (const float*)c->d_lits[slot].p,
+                                       (const unsigned long long*)c->d_loff[slot].p, (float*)dv_lits, c->s_out));
             CK(cudaMemcpyAsync(c->m_codes[slot].p, c->d_codes[slot].p, (size_t)nf * (r3 / 4), cudaMemcpyDeviceToHost, c->s_out));
             CK(cudaMemcpyAsync(c->m_loff[slot].p, c->d_loff[slot].p, (size_t)(nf + 1) * 8, cudaMemcpyDeviceToHost, c->s_out));
             if (h_maxl)
-                CK(cudaMemcpyAsync(h_maxl + f0, c->d_maxl[slot].p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->s_out));
+                CK(cudaMemcpyAsync(c->m_maxl[slot].p, c->d_maxl[slot].p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->s_out));
             if (h_mid)
-                CK(cudaMemcpyAsync(h_mid + 3 * (size_t)f0, c->d_mid[slot].p, (size_t)nf * 12, cudaMemcpyDeviceToHost, c->s_out));
-            TLREC(6, c->s_out);
+                CK(cudaMemcpyAsync(c->m_mid[slot].p, c->d_mid[slot].p, (size_t)nf * 12, cudaMemcpyDeviceToHost, c->s_out));
+            if (process_mode && h_pc)
+                CK(cudaMemcpyAsync(c->m_pc[slot].p, c->p_pc[slot].p, (size_t)nf * point_num * 24, cudaMemcpyDeviceToHost, c->s_out));
             // behind the copies: an event for the finalizer thread
-            {
-                dtsdf_ctx::ChunkRecord& r = c->chunk[slot];
-                r.ctx = c; r.slot = slot; r.jobs = std::min<int>(nf, nthreads); r.nf = nf;
-                r.r3 = r3; r.vol_floats = vol_floats; r.dst = h_vol + (size_t)f0 * vol_floats;
-                r.fixed_bytes = (long long)nf * (long long)(r3 / 4) + (long long)(nf + 1) * 8 +
-                                (h_maxl ? 4ll * nf : 0ll) + (h_mid ? 12ll * nf : 0ll);
-                c->latch[slot].add(r.jobs);
-                const cudaError_t he = cudaEventRecord(c->ev_run[slot], c->s_out);
-                if (he != cudaSuccess) { c->latch[slot].reset(); drain(); return cuda_fail(he, "cudaEventRecord"); }
-                { std::lock_guard<std::mutex> g(qm); fq.push_back(slot); }
-                qcv.notify_one();
-            }
-#ifdef DTSDF_EXP_TIMELINE
-            host_submit[k] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hk0).count();
-#endif
+            dtsdf_ctx::ChunkRecord& r = c->chunk[slot];
+            r.ctx = c; r.slot = slot; r.jobs = std::min<int>(nf, nthreads); r.nf = nf;
+            r.r3 = r3; r.vol_floats = vol_floats; r.dst = h_vol + (size_t)f0 * vol_floats;
+            r.dst_maxl = h_maxl ? h_maxl + f0 : nullptr;
+            r.dst_mid = h_mid ? h_mid + 3 * (size_t)f0 : nullptr;
+            r.pc_doubles = (size_t)point_num * 3;
+            r.dst_pc = (process_mode && h_pc) ? h_pc + (size_t)f0 * r.pc_doubles : nullptr;
+            r.fixed_bytes = (long long)nf * (long long)(r3 / 4) + (long long)(nf + 1) * 8 +
+                            (h_maxl ? 4ll * nf : 0ll) + (h_mid ? 12ll * nf : 0ll) + (r.dst_pc ? 24ll * nf * point_num : 0ll);
+            CK(cudaEventRecord(c->ev_run[slot], c->s_out));
+            c->latch[slot].add(r.jobs);
+            enqueue_for_finalizer(slot);
             continue;
         }
         // D2H on s_out
@@ -836,44 +930,109 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
             CK(cudaMemcpyAsync(h_maxl + f0, c->d_maxl[slot].p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st_out));
         if (h_mid)
             CK(cudaMemcpyAsync(h_mid + 3 * (size_t)f0, c->d_mid[slot].p, (size_t)nf * 12, cudaMemcpyDeviceToHost, st_out));
+        if (process_mode && h_pc)
+            CK(cudaMemcpyAsync(h_pc + (size_t)f0 * point_num * 3, c->p_pc[slot].p, (size_t)nf * point_num * 24,
+                               cudaMemcpyDeviceToHost, st_out));
         if (!single) CK(cudaEventRecord(c->ev_out[slot], c->s_out));
     }
-#ifdef DTSDF_EXP_TIMELINE
-    if (packed) {
-        cudaDeviceSynchronize();
-        double sum[8] = {0}, hs = 0, hw = 0;
-        float ms;
-        for (int k = 0; k < nchunk; ++k) {
-            cudaEventElapsedTime(&ms, tl[k].e[0], tl[k].e[1]); sum[0] += ms;      // H2D
-            cudaEventElapsedTime(&ms, tl[k].e[2], tl[k].e[3]); sum[1] += ms;      // fused kernel
-            cudaEventElapsedTime(&ms, tl[k].e[3], tl[k].e[4]); sum[2] += ms;      // pack kernels
-            cudaEventElapsedTime(&ms, tl[k].e[7], tl[k].e[5]); sum[3] += ms;      // push kernel (s_out)
-            cudaEventElapsedTime(&ms, tl[k].e[5], tl[k].e[6]); sum[4] += ms;      // copy-engine D2H (s_out)
-            hs += host_submit[k]; hw += host_wait[k];
-        }
-        cudaEventElapsedTime(&ms, tl[0].e[0], tl[nchunk - 1].e[6]);
-        const double host_loop = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
-        fprintf(stderr, "[timeline] chunks %d  first H2D..last D2H %.2f ms | sums: h2d %.2f  fused %.2f  pack %.2f  push %.2f  d2h %.2f | "
-                "host: submit (incl. slot wait) %.2f  slot wait %.2f  loop %.2f | expansion thread-time %.2f ms over %d threads\n", nchunk, ms, sum[0], sum[1], sum[2], sum[3], sum[4], hs, hw, host_loop, g_tl_decode_us.exchange(0) * 1e-3, nthreads);
-        // gaps on s_run between chunks
-        double gap = 0;
-        for (int k = 1; k < nchunk; ++k) { cudaEventElapsedTime(&ms, tl[k - 1].e[4], tl[k].e[2]); gap += ms; }
-        fprintf(stderr, "[timeline] idle on the kernel stream between chunks: %.2f ms\n", gap);
-    }
-    for (auto& t : tl) for (auto& e : t.e) cudaEventDestroy(e);
-#endif
-    if (packed) drain();
-    if (!single) CK(cudaStreamSynchronize(c->s_out));
-    CK(cudaStreamSynchronize(c->s_run));
-    if (!single) CK(cudaStreamSynchronize(c->s_in));
     return DTSDF_OK;
+}
+
+void HostPipeline::configure() {
+    const size_t R = (size_t)cfg->voxel_res;
+    r3 = R * R * R;
+    vol_floats = 3 * r3;
+    // chunk size: about 64 MB of output per chunk by default, at least one frame
+    per_chunk = (int32_t)std::max<size_t>(1, ((size_t)c->opt_chunk_mb << 20) / (vol_floats * 4));
+    if (per_chunk > n_frames) per_chunk = n_frames;
+    nchunk = (n_frames + per_chunk - 1) / per_chunk;
+    // packed device -> host transfer: the GPU packs each chunk into mapped pinned memory, host
+    // threads expand it into h_vol while the next chunks are in flight.  Small batches go back as
+    // plain copies even when the packed transfer is on: its extra kernels, stream hand-offs and
+    // thread wake-ups cost more than they save below ~32 frames (one frame: 350 us packed, 110 us
+    // plain; 64 frames: 26 us per frame packed, 33 us plain).
+    packed = c->opt_packed != 0 && (size_t)n_frames * vol_floats * 4 >= ((size_t)16 << 20);
+    // A single plain chunk needs no pipeline: everything on one stream, one synchronisation.
+    single = !packed && nchunk == 1;
+    c->stat_d2h_bytes = packed ? 0ll
+                                 : (long long)n_frames * (long long)(vol_floats * 4 + (h_maxl ? 4 : 0) + (h_mid ? 12 : 0));
+    nthreads = 1;
+    if (packed) {
+        // default: three quarters of the hardware threads, at most 8: the expansion saturates the host's
+        // memory system with 8 threads (16-core box: 8 and 12 threads alike; 32-core box: 286 k volumes/s
+        // with 8, 271 k with 12, 234 k with 16), and the calling thread and the CUDA driver need cores too
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        nthreads = c->opt_threads > 0 ? c->opt_threads : (int)std::min(8u, std::max(1u, hw - hw / 4));
+    }
+}
+
+int HostPipeline::run() {
+    if (packed) {
+        c->pool.ensure(nthreads);                                  // (may throw: nothing is in flight yet)
+        fin = std::thread([this] { finalizer(); });
+    }
+    int rc;
+    try {
+        rc = submit_chunks();
+    } catch (const std::bad_alloc&) {
+        rc = DTSDF_ERR_ALLOC;
+    } catch (...) {
+        rc = DTSDF_ERR_INTERNAL;
+    }
+    // ---- the one exit path
+    if (rc != DTSDF_OK) cancel.store(true);
+    stop_finalizer();
+    for (int i = 0; i < dtsdf_ctx::NSLOT; ++i) c->latch[i].wait();         // expansion jobs that did start
+    cudaError_t e_out = single ? cudaSuccess : cudaStreamSynchronize(c->s_out);
+    cudaError_t e_run = cudaStreamSynchronize(c->s_run);
+    cudaError_t e_in = single ? cudaSuccess : cudaStreamSynchronize(c->s_in);
+    if (rc != DTSDF_OK) { cudaGetLastError(); return rc; }
+    if (e_out != cudaSuccess) return cuda_fail(e_out, "cudaStreamSynchronize(s_out)");
+    if (e_run != cudaSuccess) return cuda_fail(e_run, "cudaStreamSynchronize(s_run)");
+    if (e_in != cudaSuccess) return cuda_fail(e_in, "cudaStreamSynchronize(s_in)");
+    return DTSDF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
+                        const float* h_depth, int64_t packed_len, const int64_t* h_off,
+                        const int32_t* h_hdr, const float* h_aux, float* h_vol, float* h_maxl,
+                        float* h_mid) {
+    if (!c) return DTSDF_ERR_INVALID_ARG;
+    int rc = check_cfg(cfg);
+    if (rc != DTSDF_OK) return rc;
+    if (n_frames < 0 || packed_len < 0) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!h_depth || !h_off || !h_hdr || !h_vol) return DTSDF_ERR_INVALID_ARG;
+    if (cfg->bbox_mode != DTSDF_BBOX_PIXELS && !h_aux) return DTSDF_ERR_INVALID_ARG;
+    // validate headers / offsets on the host (the per-frame shims raise on these)
+    for (int32_t i = 0; i < n_frames; ++i) {
+        const int32_t* h = h_hdr + 6 * (size_t)i;
+        if (!header_ok(h)) return DTSDF_ERR_BAD_HEADER;
+        const int64_t n = ((int64_t)h[4] - h[2]) * ((int64_t)h[5] - h[3]);
+        if (h_off[i] < 0 || (h_off[i] & 3) || h_off[i] + ((n + 3) & ~(int64_t)3) > packed_len)
+            return DTSDF_ERR_INVALID_ARG;
+        if (i > 0 && h_off[i] < h_off[i - 1]) return DTSDF_ERR_INVALID_ARG;   // chunking needs ascending offsets
+    }
+    USE_DEVICE(c->device);
+    return guarded([&]() -> int {
+        HostPipeline p;
+        p.c = c; p.cfg = cfg; p.n_frames = n_frames; p.h_depth = h_depth; p.h_off = h_off; p.h_hdr = h_hdr;
+        p.h_aux = h_aux; p.h_vol = h_vol; p.h_maxl = h_maxl; p.h_mid = h_mid;
+        p.aux_w = cfg->bbox_mode == DTSDF_BBOX_EXTREMA ? 6 : (cfg->bbox_mode == DTSDF_BBOX_GRID ? 5 : 0);
+        p.configure();
+        return p.run();
+    });
 }
 
 int dtsdf_point_cloud_host(dtsdf_ctx* c, double focal, const int32_t* h_header, const float* h_depth,
                            double* h_out_points, int32_t* n_valid) {
     if (!c || !h_header || !h_depth || !n_valid || !(focal > 0.0)) return DTSDF_ERR_INVALID_ARG;
     if (!header_ok(h_header)) return DTSDF_ERR_BAD_HEADER;
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     const int64_t n = ((int64_t)h_header[4] - h_header[2]) * ((int64_t)h_header[5] - h_header[3]);
     const int64_t n_pad = (n + 3) & ~(int64_t)3;
     int rc;
@@ -905,7 +1064,7 @@ int dtsdf_point_cloud_host(dtsdf_ctx* c, double focal, const int32_t* h_header, 
 int dtsdf_resample_extrema_host(dtsdf_ctx* c, int32_t point_num, const double* h_points, int32_t n_points,
                                 const int32_t* h_indices, double* h_out_pc, float* h_out_extrema) {
     if (!c || point_num <= 0 || !h_out_extrema) return DTSDF_ERR_INVALID_ARG;
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     cudaStream_t s = c->s_run;
     int rc;
     int32_t avail;
@@ -943,9 +1102,19 @@ int dtsdf_resample_extrema_host(dtsdf_ctx* c, int32_t point_num, const double* h
     return DTSDF_OK;
 }
 
+static int process_begin_impl(dtsdf_ctx* c, double focal, int32_t n_frames, const float* h_depth,
+                              int64_t packed_len, const int64_t* h_off, const int32_t* h_hdr,
+                              int32_t* h_n_valid);
+
 int dtsdf_process_begin_host(dtsdf_ctx* c, double focal, int32_t n_frames, const float* h_depth,
                              int64_t packed_len, const int64_t* h_off, const int32_t* h_hdr,
                              int32_t* h_n_valid) {
+    return guarded([&] { return process_begin_impl(c, focal, n_frames, h_depth, packed_len, h_off, h_hdr, h_n_valid); });
+}
+
+static int process_begin_impl(dtsdf_ctx* c, double focal, int32_t n_frames, const float* h_depth,
+                              int64_t packed_len, const int64_t* h_off, const int32_t* h_hdr,
+                              int32_t* h_n_valid) {
     if (!c || n_frames < 0 || packed_len < 0 || !(focal > 0.0)) return DTSDF_ERR_INVALID_ARG;
     c->b_n = 0;
     if (n_frames == 0) return DTSDF_OK;
@@ -963,7 +1132,7 @@ int dtsdf_process_begin_host(dtsdf_ctx* c, double focal, int32_t n_frames, const
         total_px += n;
         max_px = std::max<int32_t>(max_px, (int32_t)n);
     }
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     int rc;
     if ((rc = c->b_depth.reserve((size_t)packed_len * 4)) != DTSDF_OK) return rc;
     if ((rc = c->b_off.reserve((size_t)n_frames * 8)) != DTSDF_OK) return rc;
@@ -1006,7 +1175,7 @@ int dtsdf_process_finish_host(dtsdf_ctx* c, const dtsdf_config* cfg_in, int32_t 
     dtsdf_config cfg = *cfg_in;
     cfg.bbox_mode = DTSDF_BBOX_EXTREMA;
     const size_t R = (size_t)cfg.voxel_res, vol_floats = 3 * R * R * R;
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     if ((rc = c->b_idx.reserve((size_t)n * point_num * 4)) != DTSDF_OK) return rc;
     if ((rc = c->b_ext.reserve((size_t)n * 24)) != DTSDF_OK) return rc;
     if (h_pc && (rc = c->b_pc.reserve((size_t)n * point_num * 24)) != DTSDF_OK) return rc;
@@ -1031,13 +1200,67 @@ int dtsdf_process_finish_host(dtsdf_ctx* c, const dtsdf_config* cfg_in, int32_t 
     return DTSDF_OK;
 }
 
+int dtsdf_np_randint(uint32_t* mt_key, int32_t* mt_pos, int32_t high, int32_t count, int32_t* out) {
+    if (!mt_key || !mt_pos || count < 0 || (count > 0 && !out)) return DTSDF_ERR_INVALID_ARG;
+    if (*mt_pos < 0 || *mt_pos > 624) return DTSDF_ERR_INVALID_ARG;
+    if (high <= 0) return DTSDF_ERR_EMPTY_CLOUD;              // np.random.randint: "low >= high"
+    int pos = *mt_pos;
+    dtsdf::np_legacy_randint(mt_key, &pos, (uint32_t)high, count, out);
+    *mt_pos = pos;
+    return DTSDF_OK;
+}
+
+int dtsdf_resample_indices(uint32_t* mt_key, int32_t* mt_pos, int32_t n_frames, const int32_t* n_valid,
+                           int32_t point_num, int32_t* out_idx) {
+    if (!mt_key || !mt_pos || n_frames < 0 || point_num <= 0) return DTSDF_ERR_INVALID_ARG;
+    if (*mt_pos < 0 || *mt_pos > 624) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!n_valid || !out_idx) return DTSDF_ERR_INVALID_ARG;
+    int pos = *mt_pos;
+    const int rc = resample_indices(mt_key, &pos, n_frames, n_valid, point_num, out_idx);
+    *mt_pos = pos;
+    return rc;
+}
+
+int dtsdf_process_host(dtsdf_ctx* c, const dtsdf_config* cfg_in, double focal, int32_t n_frames,
+                       const float* h_depth, int64_t packed_len, const int64_t* h_off, const int32_t* h_hdr,
+                       int32_t point_num, uint32_t* mt_key, int32_t* mt_pos, double* h_out_pc,
+                       float* h_out_vol, float* h_out_max_l, float* h_out_mid_p) {
+    if (!c) return DTSDF_ERR_INVALID_ARG;
+    int rc = check_cfg(cfg_in);
+    if (rc != DTSDF_OK) return rc;
+    if (point_num <= 0 || !mt_key || !mt_pos || *mt_pos < 0 || *mt_pos > 624) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames < 0) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!h_out_vol) return DTSDF_ERR_INVALID_ARG;
+    return guarded([&]() -> int {
+        // back-projection + compaction of every frame; crops, tables and clouds stay resident (b_*)
+        std::vector<int32_t> n_valid((size_t)n_frames);
+        int rc2 = process_begin_impl(c, focal, n_frames, h_depth, packed_len, h_off, h_hdr, n_valid.data());
+        if (rc2 != DTSDF_OK) return rc2;
+        USE_DEVICE(c->device);
+        dtsdf_config cfg = *cfg_in;
+        cfg.bbox_mode = DTSDF_BBOX_EXTREMA;
+        int pos = *mt_pos;
+        HostPipeline p;
+        p.c = c; p.cfg = &cfg; p.n_frames = n_frames; p.h_depth = nullptr; p.h_off = nullptr; p.h_hdr = nullptr;
+        p.h_aux = nullptr; p.h_vol = h_out_vol; p.h_maxl = h_out_max_l; p.h_mid = h_out_mid_p;
+        p.aux_w = 6;
+        p.process_mode = true; p.point_num = point_num; p.mt_key = mt_key; p.mt_pos = &pos; p.h_pc = h_out_pc;
+        p.configure();
+        rc2 = p.run();
+        *mt_pos = pos;
+        return rc2;
+    });
+}
+
 int dtsdf_normalize_joints_host(dtsdf_ctx* c, int32_t n_frames, const float* h_joints,
                                 const float* h_max_l, const float* h_mid_p, int32_t clamp01,
                                 float* h_out) {
     if (!c || n_frames < 0) return DTSDF_ERR_INVALID_ARG;
     if (n_frames == 0) return DTSDF_OK;
     if (!h_joints || !h_max_l || !h_mid_p || !h_out) return DTSDF_ERR_INVALID_ARG;
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     cudaStream_t s = c->s_run;
     int rc;
     const size_t nj = (size_t)n_frames * 63 * 4;

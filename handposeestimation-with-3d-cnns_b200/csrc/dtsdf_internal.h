@@ -68,13 +68,43 @@ cudaError_t launch_pack(int n_frames, int r3, const float* vol, unsigned* counts
 cudaError_t launch_pack_push(int n_frames, const float* lits, const unsigned long long* lit_off,
                              float* host_lits, cudaStream_t stream);
 
+// The strided container of the same codes, for device -> device transfers (the gather of volumes to a
+// training rank over NVLink): frame f's literals are interleaved (x, y, z) triples in voxel order at
+// lits + f * lit_stride (floats; lit_stride >= 3 * R3, a multiple of 4), cnt[f] of them.  Written in one
+// pass over the volume; no prefix over frames, so every frame's region can be read on its own.
+cudaError_t launch_pack_strided(int n_frames, int r3, const float* vol, long long lit_stride, unsigned char* codes,
+                                unsigned* cnt, float* lits, cudaStream_t stream);
+// codes / cnt / lits may be peer memory: the kernel pulls each frame with TMA bulk copies.
+cudaError_t launch_unpack_strided(int n_frames, int r3, const unsigned char* codes, const unsigned* cnt,
+                                  const float* lits, long long lit_stride, float* out, cudaStream_t stream);
+
 // Host side of the codec (dtsdf_decode.cpp, plain C++): expands one packed frame (its r3/4 code bytes and
 // its literal block of nlit voxels: x[nlit], y[nlit], z[nlit]) into the three channel planes at `out`
 // (any 4-byte alignment; whole-line non-temporal stores when `out` is 16-byte aligned).
 void decode_frame(const unsigned char* codes, const float* lits, size_t nlit, size_t r3, float* out);
 const char* decode_isa();
 
+// NumPy's legacy global stream (dtsdf_rng.cpp): `count` draws of np.random.randint(0, high) from the MT19937
+// state (key[624], pos as in np.random.get_state()), written to out; the state advances as NumPy's would.
+void np_legacy_randint(uint32_t* key, int* pos, uint32_t high, int count, int32_t* out);
+
 // kernels launched by this process (claimed in bench.py's gpu_launches)
 extern std::atomic<long long> g_launch_count;
+
+// The opt-in dynamic shared memory limit of a kernel is a per-device function attribute: raise it to the
+// device maximum once per (instantiation, device), not per launch (launches may come from several host
+// threads with different crop sizes).
+template <typename K>
+inline cudaError_t allow_max_smem(K kern, int dev, int smem_optin, std::atomic<unsigned>& done_mask) {
+    const unsigned bit = 1u << (dev & 31);
+    if (done_mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)fa.sharedSizeBytes);
+    if (e == cudaSuccess) done_mask.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
 
 }  // namespace dtsdf

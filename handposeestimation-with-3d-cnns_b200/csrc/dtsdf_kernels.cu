@@ -56,6 +56,7 @@
 // The path is a streaming, write-dominated map with a small gather: HBM-bound, no
 // tensor cores (there is no contraction to feed them).
 #include "dtsdf_internal.h"
+#include "dtsdf_ptx.cuh"
 
 #include <math.h>
 #include <stddef.h>
@@ -70,6 +71,8 @@ std::atomic<long long> g_launch_count{0};
 
 namespace {
 
+using namespace ptx;
+
 constexpr int NT = 256;                 // threads per CTA
 constexpr int NWARP = NT / 32;
 constexpr float SENTINEL = 99999.0f;    // pre/tsdf_numba.py:88-89
@@ -81,59 +84,6 @@ constexpr int OUTSIDE = -(1 << 30);                    // table sentinel: projec
 constexpr unsigned DEFAULT_FOCAL_BITS = 0x43716B85u;   // 241.42f
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int QNAN_BITS = 0x7fc00000;
-
-// ---------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion counted in bytes on the mbarrier.
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
-                                         unsigned long long* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void st_f4(float* p, const float4& v) {
-#ifdef DTSDF_EXP_NOSTORE            /* dev ablation: everything but the stores */
-    if (v.x != 123456.0f) return;
-#endif
-    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
-}
-__device__ __forceinline__ float warp_min(float v) {
-    float r;
-    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-    return r;
-}
-__device__ __forceinline__ float warp_max(float v) {
-    float r;
-    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-    return r;
-}
 
 // ---------------------------------------------------------------- exact division by a fixed divisor
 // a / b with y = rcp_rn(b): one (ONE=true) or two residual corrections.  Preconditions
@@ -642,20 +592,6 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
                 B0 = make_int4(y0, y0, y0, y0);
                 B1 = make_int4(y1, y1, y1, y1);
             }
-#ifdef DTSDF_EXP_STOREONLY      /* dev ablation: the store pattern alone */
-            {
-                const float c = __int_as_float(0x3F800000 | ((m0 & 1) << 31));
-                const float4 v0 = make_float4(c, c, c, c), v1 = v0;
-                if (active) {
-                    float* p0 = obase + m0 * R;
-                    float* p1 = obase + m1 * R;
-                    st_f4(p0, v0); st_f4(p0 + CH, v0); st_f4(p0 + 2 * CH, v0);
-                    st_f4(p1, v1); st_f4(p1 + CH, v1); st_f4(p1 + 2 * CH, v1);
-                }
-                (void)B0; (void)B1; (void)t_far; (void)lt; (void)ebase; (void)A;
-                continue;
-            }
-#endif
             const float d00 = gather_depth<STAGED>(crop, A.x + B0.x);
             const float d01 = gather_depth<STAGED>(crop, A.y + B0.y);
             const float d02 = gather_depth<STAGED>(crop, A.z + B0.z);
@@ -696,9 +632,6 @@ __device__ __forceinline__ void voxel_passes(const float* __restrict__ crop,
             if (n1) list[cnt + __popc(bal1 & lt)] = (unsigned short)(ebase | (m1 << 5));
             cnt += __popc(bal1);
         }
-#ifdef DTSDF_EXP_NOPASS2
-        cnt = 0;
-#endif
         // ---- pass 2 on whole batches (warp-uniform control flow)
         if (cnt >= 32) {
             __syncwarp();                 // list entries and the pass-1 stores are ordered before pass 2
@@ -820,20 +753,11 @@ __device__ __forceinline__ void voxel_passes_blocked(const float* __restrict__ c
 // two or three CTAs per frame (kept: 2); R = 64: 2.04 ms unsplit at one CTA per SM, 2.22 ms with two
 // CTAs per frame, 2.10 ms with four (kept: 1 - fewer concurrent write streams win there); R = 32 (per
 // 8,500 frames): 0.616 ms unsplit at two CTAs per SM, 0.619 ms with two CTAs per frame at three per SM (kept: 1).
-#ifndef DTSDF_EXP_SPLIT48
-#define DTSDF_EXP_SPLIT48 2
-#endif
-#ifndef DTSDF_EXP_SPLIT64
-#define DTSDF_EXP_SPLIT64 1
-#endif
-#ifndef DTSDF_EXP_SPLIT32
-#define DTSDF_EXP_SPLIT32 1
-#endif
 template <int R, int LAYOUT>
 struct CtaShape {
     static constexpr int NW = 8;
     static constexpr int MIN_CTAS = 3;
-    static constexpr int SPLIT = R == 64 ? DTSDF_EXP_SPLIT64 : (R == 32 ? DTSDF_EXP_SPLIT32 : 1);
+    static constexpr int SPLIT = 1;
 };
 
 // R = 48 (block map): 288 units of 8 middle-axis rows per frame, 36 per warp
@@ -841,17 +765,8 @@ template <int LAYOUT>
 struct CtaShape<48, LAYOUT> {
     static constexpr int NW = 8;
     static constexpr int MIN_CTAS = 2;
-    static constexpr int SPLIT = DTSDF_EXP_SPLIT48;
+    static constexpr int SPLIT = 2;
 };
-
-#ifdef DTSDF_EXP_NW64             /* dev experiment: CTA shape of the R = 64 instantiations */
-template <int LAYOUT>
-struct CtaShape<64, LAYOUT> {
-    static constexpr int NW = DTSDF_EXP_NW64;
-    static constexpr int MIN_CTAS = 1;
-    static constexpr int SPLIT = DTSDF_EXP_SPLIT64;
-};
-#endif
 
 template <int R, int LAYOUT, bool DEFF>
 __global__ void __launch_bounds__(32 * CtaShape<R, LAYOUT>::NW, CtaShape<R, LAYOUT>::MIN_CTAS)
@@ -1056,21 +971,6 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     }
 }
 
-// The opt-in dynamic shared memory limit of a kernel is a per-device function attribute: raise it to the
-// device maximum once per (instantiation, device), not per launch (launches may come from several host
-// threads with different crop sizes).
-template <typename K>
-cudaError_t allow_max_smem(K kern, int dev, int smem_optin, std::atomic<unsigned>& done_mask) {
-    const unsigned bit = 1u << (dev & 31);
-    if (done_mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
-    cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)fa.sharedSizeBytes);
-    if (e == cudaSuccess) done_mask.fetch_or(bit, std::memory_order_release);
-    return e;
-}
-
 template <int R, int LAYOUT, bool DEFF>
 cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t stream) {
     BatchArgs args = args_in;
@@ -1121,13 +1021,9 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
         if (e != cudaSuccess) return e;
         const long long vol_bytes = 12ll * R * R * R;
         const int fit = (int)((long long)l2 / ((long long)sms * vol_bytes));
-#ifdef DTSDF_EXP_TARGET         /* dev experiment: force the number of CTAs per SM */
-        const int target = std::min(occ, DTSDF_EXP_TARGET);
-#else
         constexpr int SPLIT = CtaShape<R, LAYOUT>::SPLIT;
         // (with SPLIT CTAs per frame, SPLIT CTAs per SM are one volume per SM under construction)
         const int target = fit >= 2 ? std::min(occ, fit * SPLIT) : (R >= 64 ? std::min(occ, SPLIT) : occ);
-#endif
         if (target >= 1 && target < occ) {
             // the largest request that still lets `target` CTAs share an SM (1 KB per CTA is reserved)
             long long padded = ((long long)smem_sm / target - 1024) & ~15ll;
@@ -1590,145 +1486,6 @@ cudaError_t launch_aug_t(const BatchArgs& args_in, const float* aug, int max_cro
     return cudaGetLastError();
 }
 
-// ---------------------------------------------------------------- volume codec (device -> host transfer)
-// See dtsdf_internal.h.  One CTA per frame; a thread handles 4 consecutive voxels (one LDG.128
-// per channel plane, one code byte).
-__device__ __forceinline__ unsigned voxel_code(unsigned a, unsigned b, unsigned c) {
-    const bool same = a == b && b == c;
-    return (same && a == 0u) ? 0u : (same && a == 0x3F800000u) ? 1u : (same && a == 0xBF800000u) ? 2u : 3u;
-}
-
-__device__ __forceinline__ unsigned group_codes(const float* __restrict__ vol, int r3, int g, uint4& a,
-                                                uint4& b, uint4& c) {
-    a = __ldg(reinterpret_cast<const uint4*>(vol) + g);
-    b = __ldg(reinterpret_cast<const uint4*>(vol + r3) + g);
-    c = __ldg(reinterpret_cast<const uint4*>(vol + 2 * (size_t)r3) + g);
-    return voxel_code(a.x, b.x, c.x) | (voxel_code(a.y, b.y, c.y) << 2) | (voxel_code(a.z, b.z, c.z) << 4) |
-           (voxel_code(a.w, b.w, c.w) << 6);
-}
-
-__device__ __forceinline__ unsigned literal_mask(unsigned byte) {     // bit 2j set <=> voxel j has code 3
-    return byte & (byte >> 1) & 0x55u;
-}
-
-__global__ void __launch_bounds__(NT) pack_count_kernel(const float* __restrict__ vol, int r3,
-                                                        unsigned* __restrict__ counts) {
-    __shared__ unsigned wsum[NWARP];
-    const float* v = vol + (size_t)blockIdx.x * 3 * r3;
-    unsigned n = 0;
-    for (int g = threadIdx.x; g < r3 / 4; g += NT) {
-        uint4 a, b, c;
-        n += __popc(literal_mask(group_codes(v, r3, g, a, b, c)));
-    }
-    n = __reduce_add_sync(FULL, n);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = n;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned t = 0;
-        for (int w = 0; w < NWARP; ++w) t += wsum[w];
-        counts[blockIdx.x] = t;
-    }
-}
-
-__global__ void pack_scan_kernel(const unsigned* __restrict__ counts, int n, unsigned long long* __restrict__ off,
-                                 unsigned long long* __restrict__ off_copy) {
-    // batches are a few hundred frames: one thread is plenty
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned long long run = 0;
-        for (int i = 0; i < n; ++i) {
-            off[i] = run;
-            if (off_copy) off_copy[i] = run;
-            run += counts[i];
-        }
-        off[n] = run;
-        if (off_copy) off_copy[n] = run;
-    }
-}
-
-__global__ void __launch_bounds__(NT) pack_write_kernel(const float* __restrict__ vol, int r3,
-                                                        const unsigned long long* __restrict__ off_dev,
-                                                        unsigned char* __restrict__ codes, float* __restrict__ lits) {
-    __shared__ unsigned wsum[NWARP];
-    const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* v = vol + (size_t)f * 3 * r3;
-    unsigned char* cd = codes + (size_t)f * (r3 / 4);
-    // the frame's literal block: x of its nf literal voxels, then y, then z, in voxel order
-    const unsigned long long o0 = off_dev[f];
-    const unsigned nf = (unsigned)(off_dev[f + 1] - o0);
-    unsigned* lx = reinterpret_cast<unsigned*>(lits) + 3 * o0;
-    unsigned* ly = lx + nf;
-    unsigned* lz = ly + nf;
-    unsigned base = 0;
-    for (int g0 = 0; g0 < r3 / 4; g0 += NT) {            // r3/4 is a multiple of NT for R = 32, 48, 64
-        const int g = g0 + threadIdx.x;
-        uint4 a, b, c;
-        const unsigned byte = group_codes(v, r3, g, a, b, c);
-        cd[g] = (unsigned char)byte;
-        const unsigned m2 = literal_mask(byte);
-        const unsigned nl = __popc(m2);
-        // block-wide exclusive prefix of the literal voxels, in voxel order
-        unsigned incl = nl;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned t = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        unsigned before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < NWARP; ++w) {
-            const unsigned t = wsum[w];
-            if (w < warp) before += t;
-            total += t;
-        }
-        if (nl) {
-            unsigned r = base + before + incl - nl;
-            const unsigned av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, cv[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if ((m2 >> (2 * j)) & 1u) { lx[r] = av[j]; ly[r] = bv[j]; lz[r] = cv[j]; ++r; }
-        }
-        base += total;
-        __syncthreads();
-    }
-}
-
-// Copies the literal stream (3 * lit_off[n] floats, a count only the device knows) from device memory
-// to host-mapped memory with whole 16-byte, fully coalesced stores: PCIe likes 128-byte writes, the
-// scattered 4-byte stores of pack_write_kernel it does not.
-__global__ void __launch_bounds__(NT) pack_push_kernel(const float* __restrict__ lits, const unsigned long long* __restrict__ off,
-                                                       int n, float* __restrict__ host_lits) {
-    const unsigned long long n16 = (3ull * off[n] + 3ull) / 4ull;          // uint4 units (the buffers are padded)
-    const uint4* src = reinterpret_cast<const uint4*>(lits);
-    uint4* dst = reinterpret_cast<uint4*>(host_lits);
-    for (unsigned long long i = blockIdx.x * (unsigned long long)NT + threadIdx.x; i < n16;
-         i += (unsigned long long)gridDim.x * NT)
-        dst[i] = src[i];
-}
-
-}  // namespace
-
-cudaError_t launch_pack_push(int n_frames, const float* lits, const unsigned long long* lit_off, float* host_lits,
-                             cudaStream_t stream) {
-    if (n_frames <= 0) return cudaSuccess;
-    pack_push_kernel<<<96, NT, 0, stream>>>(lits, lit_off, n_frames, host_lits);
-    ++g_launch_count;
-    return cudaGetLastError();
-}
-
-cudaError_t launch_pack(int n_frames, int r3, const float* vol, unsigned* counts, unsigned long long* lit_off,
-                        unsigned long long* lit_off_copy, unsigned char* codes, float* lits, cudaStream_t stream) {
-    if (n_frames <= 0) return cudaSuccess;
-    if (r3 % (4 * NT) != 0) return cudaErrorInvalidValue;
-    pack_count_kernel<<<n_frames, NT, 0, stream>>>(vol, r3, counts);
-    pack_scan_kernel<<<1, 32, 0, stream>>>(counts, n_frames, lit_off, lit_off_copy);
-    pack_write_kernel<<<n_frames, NT, 0, stream>>>(vol, r3, lit_off, codes, lits);
-    g_launch_count += 3;
-    return cudaGetLastError();
-}
-
-namespace {
 }  // namespace
 
 // ---------------------------------------------------------------- launchers
@@ -1746,10 +1503,8 @@ cudaError_t launch_voxelize(int voxel_res, int layout, BatchArgs args, int max_c
                     : launch_fused<RR, 1, false>(args, max_crop_px, stream);
     switch (voxel_res) {
         DTSDF_CASE(32)
-#ifndef DTSDF_EXP_ONLY32
         DTSDF_CASE(48)
         DTSDF_CASE(64)
-#endif
         default:
             return cudaErrorInvalidValue;
     }
@@ -1761,10 +1516,8 @@ cudaError_t launch_voxelize_aug(int voxel_res, int layout, BatchArgs args, const
     if (args.n_frames <= 0) return cudaSuccess;
     switch (voxel_res) {
         case 32: return layout == 0 ? launch_aug_t<32, 0>(args, aug, max_crop_px, stream) : launch_aug_t<32, 1>(args, aug, max_crop_px, stream);
-#ifndef DTSDF_EXP_ONLY32
         case 48: return layout == 0 ? launch_aug_t<48, 0>(args, aug, max_crop_px, stream) : launch_aug_t<48, 1>(args, aug, max_crop_px, stream);
         case 64: return layout == 0 ? launch_aug_t<64, 0>(args, aug, max_crop_px, stream) : launch_aug_t<64, 1>(args, aug, max_crop_px, stream);
-#endif
         default: return cudaErrorInvalidValue;
     }
 }

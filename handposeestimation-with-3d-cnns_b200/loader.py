@@ -66,8 +66,15 @@ class ResidentFrames:
 
 
 class OnTheFlyLoader:
-    """``for tsdf, joints_nor, max_l, mid_p in loader:`` - the batch tensors stay valid until the
-    iteration after the next one (two buffers).  ``joints_nor`` is None without ground truth."""
+    """``for tsdf, joints_nor, max_l, mid_p in loader:`` - three output buffers: the tensors of batch k
+    stay valid (and may be used by work enqueued on the consumer's current stream) during iteration k
+    AND iteration k+1, i.e. until batch k+2 is requested; batch k+1 is voxelised on a side stream while
+    the consumer works on batch k.  Ordering is by CUDA events on whatever stream is current where the
+    consumer asks for a batch: that stream waits for the batch at yield time, and the buffer of batch
+    k-1 is released on it when the consumer comes back for batch k+1.  ``joints_nor`` is None without
+    ground truth."""
+
+    NBUF = 3
 
     def __init__(self, frames, batch_size=16, shuffle=False, seed=0, voxel_res=32, layout=capi.LAYOUT_CXYZ,
                  joint_flags=capi.JOINT_CLAMP01, drop_last=False, augment=False, augment_center=None):
@@ -84,10 +91,10 @@ class OnTheFlyLoader:
         self.augment = bool(augment)
         self.augment_center = None if augment_center is None else np.asarray(augment_center, np.float32).reshape(1, 3)
         self._aug_rng = np.random.default_rng(self.seed + 7919)
-        self.last_aug = [None, None]
+        self.last_aug = [None] * self.NBUF
         R, B, dev = int(voxel_res), self.batch_size, frames.device
         self._bufs = []
-        for _ in range(2):
+        for _ in range(self.NBUF):
             self._bufs.append((torch.empty((B, 3, R, R, R), dtype=torch.float32, device=dev),
                                torch.empty((B,), dtype=torch.float32, device=dev),
                                torch.empty((B, 3), dtype=torch.float32, device=dev),
@@ -111,15 +118,16 @@ class OnTheFlyLoader:
         order = self._order()
         self.epoch += 1
         nb = len(self)
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed = [torch.cuda.Event(), torch.cuda.Event()]
-        main = torch.cuda.current_stream(fr.device)
-        side.wait_stream(main)                       # `order` and the resident tables are ready
+        NB = self.NBUF
+        ready = [torch.cuda.Event() for _ in range(NB)]
+        consumed = [torch.cuda.Event() for _ in range(NB)]
+        start = torch.cuda.current_stream(fr.device)
+        side.wait_stream(start)                      # `order` and the resident tables are ready
         for e in consumed:
-            e.record(main)
+            e.record(start)
 
         def launch(k):
-            slot = k % 2
+            slot = k % NB
             idx = order[k * B:(k + 1) * B]
             m = int(idx.numel())
             aug = None
@@ -141,9 +149,12 @@ class OnTheFlyLoader:
         for k in range(nb):
             if k + 1 < nb:
                 sizes[k + 1] = launch(k + 1)         # overlaps the consumer's work on batch k
-            slot = k % 2
-            main.wait_event(ready[slot])
+            slot = k % NB
+            torch.cuda.current_stream(fr.device).wait_event(ready[slot])
             m = sizes.pop(k)
             vol, max_l, mid_p, jn = (t[:m] for t in self._bufs[slot])
             yield vol, (jn if fr.joints is not None else None), max_l, mid_p
-            consumed[slot].record(torch.cuda.current_stream(fr.device))
+            # the consumer is back for batch k+1: whatever it enqueued on batch k-1 (during iterations
+            # k-1 and k) precedes this point of its stream; batch k+2 will reuse that buffer
+            if k >= 1:
+                consumed[(k - 1) % NB].record(torch.cuda.current_stream(fr.device))

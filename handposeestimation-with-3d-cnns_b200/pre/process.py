@@ -44,8 +44,6 @@ class DataProcess(object):
         self.point_num = point_num
         self.aug = aug
         self._vox = _pkg.default_voxelizer()
-        self._cloud = None          # last array returned by point_cloud() (resident on the device)
-        self._sampled = None        # (array returned by set_length, point_max, point_min)
 
     # ------------------------------------------------------------------ pre/process.py:13-28
     def process(self):
@@ -63,9 +61,7 @@ class DataProcess(object):
     # ------------------------------------------------------------------ pre/process.py:30-68
     def point_cloud(self):
         "get point cloud from depth informations (float64[n_valid, 3])"
-        pts = self._vox.point_cloud(self.data)
-        self._cloud = pts
-        return pts
+        return self._vox.point_cloud(self.data)
 
     # ------------------------------------------------------------------ pre/process.py:70-84
     def set_length(self, hand_points):
@@ -78,12 +74,10 @@ class DataProcess(object):
                                                        size=point_num - point_shape)
         else:
             rand_idx = np.random.randint(0, point_shape, size=point_num)
-        resident = hand_points is self._cloud
-        pc, pmax, pmin = self._vox.resample_extrema(
-            point_num, rand_idx, points=None if resident else hand_points)
-        if not resident:
-            self._cloud = None      # the device now holds hand_points, not the last point_cloud()
-        self._sampled = (pc, pmax, pmin)
+        # the array handed in is what gets gathered, like the reference's hand_points[rand_idx, :]: the
+        # device context is shared by every DataProcess / tsdf_for call of the process, so nothing is
+        # assumed to be resident from an earlier call (and in-place edits of hand_points count)
+        pc, _, _ = self._vox.resample_extrema(point_num, rand_idx, points=hand_points)
         return pc
 
     # cut_version/pre/process.py:52-67
@@ -92,10 +86,7 @@ class DataProcess(object):
 
     # ------------------------------------------------------------------ pre/process.py:102-120
     def max_min_point(self, point_cloud):
-        if self._sampled is not None and point_cloud is self._sampled[0]:
-            return self._sampled[1].copy(), self._sampled[2].copy()
         pc = np.asarray(point_cloud, dtype=np.float64)
-        self._cloud = None
         _, pmax, pmin = self._vox.resample_extrema(pc.shape[0], None, points=pc, want_points=False)
         return pmax, pmin
 

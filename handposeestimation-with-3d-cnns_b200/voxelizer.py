@@ -10,6 +10,8 @@ Two ways in:
   only used for device memory and streams.
 """
 import ctypes
+import functools
+import threading
 
 import numpy as np
 
@@ -64,8 +66,18 @@ def pack_frames(frames, pinned=False):
     return headers, offsets, packed, max_px
 
 
+def _serialised(method):
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        with self._lock:
+            return method(self, *args, **kwargs)
+    return wrapper
+
+
 class Voxelizer:
-    """NumPy-facing voxeliser bound to one CUDA device (host entry points of the C ABI)."""
+    """NumPy-facing voxeliser bound to one CUDA device (host entry points of the C ABI).  Calls on one
+    instance are serialised by a lock; the process-wide ``default_voxelizer()`` is therefore safe to share
+    between threads, and no call depends on state left by an earlier one unless its docstring says so."""
 
     def __init__(self, device=0, voxel_res=VOXEL_RES, focal=FOCAL, center_x=CENTER_X, center_y=CENTER_Y,
                  trunc_mul=3.0):
@@ -76,6 +88,10 @@ class Voxelizer:
         self.center_y = int(center_y)
         self.trunc_mul = float(trunc_mul)
         self._ctx = ctypes.c_void_p()
+        # one call at a time per context (ctypes drops the GIL during a call; the context's streams,
+        # staging buffers and resident clouds are not re-entrant).  Threads that want to overlap use
+        # a Voxelizer each.
+        self._lock = threading.RLock()
         check(self._lib.dtsdf_ctx_create(int(device), ctypes.byref(self._ctx)))
         # one process per GPU (torchrun): the ranks of a node share its host cores, so each takes its
         # share of them for the expansion of packed volumes
@@ -98,11 +114,13 @@ class Voxelizer:
         except Exception:
             pass
 
+    @_serialised
     def set_option(self, option, value):
         """``dtsdf_ctx_set_option``: capi.OPT_PACKED_D2H (packed device->host transfer of the volumes,
         default on) and capi.OPT_HOST_THREADS (host threads that expand it)."""
         check(self._lib.dtsdf_ctx_set_option(self._ctx, int(option), int(value)))
 
+    @_serialised
     def stat(self, which=capi.STAT_D2H_BYTES):
         """``dtsdf_ctx_get_stat`` of the last ``voxelize_packed`` call."""
         v = ctypes.c_int64(0)
@@ -118,6 +136,7 @@ class Voxelizer:
         return cfg
 
     # ------------------------------------------------------------------ voxelisation
+    @_serialised
     def voxelize_packed(self, headers, offsets, packed, layout=LAYOUT_CXYZ, bbox_mode=BBOX_PIXELS,
                         aux=None, voxel_res=None, out_vol=None, out_max_l=None, out_mid_p=None):
         """``dtsdf_voxelize_host`` on an already packed batch (see pack_frames).
@@ -153,6 +172,7 @@ class Voxelizer:
         return self.voxelize_packed(headers, offsets, packed, layout, bbox_mode, aux, voxel_res)
 
     # ------------------------------------------------------------------ process.py pieces
+    @_serialised
     def point_cloud(self, frame):
         """DataProcess.point_cloud (pre/process.py:30-68): float64[n_valid,3]; the cloud also
         stays resident on the device for ``resample_extrema``."""
@@ -167,6 +187,7 @@ class Voxelizer:
                                                capi._ptr(depth), capi._ptr(pts), ctypes.byref(n_valid)))
         return pts[:n_valid.value].copy()
 
+    @_serialised
     def resample_extrema(self, point_num, indices=None, points=None, want_points=True):
         """Gather ``point_num`` rows by ``indices`` (pre/process.py:82) from ``points`` (or the cloud
         left on the device by ``point_cloud``) and reduce (max, min) (pre/process.py:102-120).
@@ -190,14 +211,48 @@ class Voxelizer:
 
     def process_frames(self, frames, point_num=6000, want_points=True, layout=LAYOUT_CXYZ, voxel_res=None):
         """``DataProcess(frame, gt, point_num).process()`` (pre/process.py:13-28) for a list of frame
-        records in two device round trips instead of per-frame Python loops.  The resampling index
-        vectors are drawn here, frame by frame in order, from the *global* ``np.random`` stream with
-        the reference's own calls (pre/process.py:75-80), so a seeded run reproduces the reference's
-        frame loop (pre/read_MSRA.py:98-111) bit for bit.
+        records: ``pack_frames`` + ``process_packed``."""
+        headers, offsets, packed, _ = pack_frames(frames)
+        return self.process_packed(headers, offsets, packed, point_num, want_points, layout, voxel_res)
+
+    @_serialised
+    def process_packed(self, headers, offsets, packed, point_num=6000, want_points=True, layout=LAYOUT_CXYZ,
+                       voxel_res=None, out_vol=None):
+        """``DataProcess.process()`` for a packed batch in ONE library call (``dtsdf_process_host``): point
+        clouds on the device, the resampling index vectors drawn frame by frame, in order, from the *global*
+        ``np.random`` stream - by the library, in C, with NumPy's own algorithm (MT19937 + masked
+        rejection; the stream is handed over with ``np.random.get_state()`` and given back advanced) - gather,
+        extrema, voxel loop on the GPU.  A seeded run therefore reproduces the reference's frame loop
+        (pre/read_MSRA.py:98-111) bit for bit, and whatever the caller draws afterwards too.
 
         Returns ``(point_clouds float64[n,point_num,3] or None, tsdf float32[n,3,R,R,R],
-        max_l float32[n], mid_p float32[n,3])``.
+        max_l float32[n], mid_p float32[n,3])``.  A frame without a single point raises ValueError like the
+        reference's ``np.random.randint(0, 0)``.
         """
+        R = int(voxel_res or self.voxel_res)
+        point_num = int(point_num)
+        headers = np.ascontiguousarray(headers, dtype=np.int32).reshape(-1, 6)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        assert packed.dtype == np.float32 and packed.flags["C_CONTIGUOUS"]
+        n = headers.shape[0]
+        pcs = np.empty((n, point_num, 3), dtype=np.float64) if want_points else None
+        vol = np.empty((n, 3, R, R, R), dtype=np.float32) if out_vol is None else out_vol
+        max_l = np.empty(n, dtype=np.float32)
+        mid_p = np.empty((n, 3), dtype=np.float32)
+        cfg = self.config(layout, BBOX_EXTREMA, R)
+        with capi.NumpyGlobalStream() as st:
+            check(self._lib.dtsdf_process_host(
+                self._ctx, ctypes.byref(cfg), ctypes.c_double(self.focal), n, capi._ptr(packed), int(packed.size),
+                capi._ptr(offsets), capi._ptr(headers), point_num, st.key_ptr, st.pos_ref, capi._ptr(pcs),
+                capi._ptr(vol), capi._ptr(max_l), capi._ptr(mid_p)))
+        return pcs, vol, max_l, mid_p
+
+    @_serialised
+    def process_frames_two_calls(self, frames, point_num=6000, want_points=True, layout=LAYOUT_CXYZ, voxel_res=None):
+        """The same result through ``dtsdf_process_begin_host`` / ``dtsdf_process_finish_host`` with the index
+        vectors drawn HERE by ``np.random.randint``, one call per frame as the reference does
+        (pre/process.py:75-80): the form that depends on nothing but NumPy's public API (``process_packed``
+        is checked against it)."""
         R = int(voxel_res or self.voxel_res)
         point_num = int(point_num)
         headers, offsets, packed, _ = pack_frames(frames)
@@ -224,6 +279,7 @@ class Voxelizer:
                                                   capi._ptr(mid_p)))
         return pcs, vol, max_l, mid_p
 
+    @_serialised
     def normalize_joints(self, joints, max_l, mid_p, clamp01=False):
         """(gt - mid_p)/max_l + 0.5 (pre/joint_nor.py:8-18), float32[n,63]."""
         j = np.ascontiguousarray(joints, dtype=np.float32).reshape(-1, 63)

@@ -18,7 +18,11 @@
  *   - "device" entry points take device pointers owned by the caller, enqueue
  *     work on `stream` and return without synchronising;
  *   - "host" entry points take host pointers, run on the context's own streams
- *     and return when the outputs are complete;
+ *     and return when the outputs are complete - on failure, too: no copy and no host
+ *     thread of the library touches the caller's buffers after an entry point has
+ *     returned, whatever it returned.  They leave the calling thread's current CUDA
+ *     device as they found it.  Page-locked buffers (dtsdf_host_alloc) let copies and
+ *     kernels overlap; pageable ones work, with the host -> device copies serialised;
  *   - there is no CPU fallback: without a usable CUDA device every compute entry
  *     point fails with DTSDF_ERR_NO_DEVICE / DTSDF_ERR_CUDA.
  *
@@ -56,6 +60,9 @@ extern "C" {
 #define DTSDF_ERR_NO_DEVICE     -4   /* no CUDA device / not an sm_100 device */
 #define DTSDF_ERR_ALLOC         -5
 #define DTSDF_ERR_BAD_HEADER    -6   /* a frame header has bw <= 0, bh <= 0 or a crop > 32767 px wide/high */
+#define DTSDF_ERR_INTERNAL      -7   /* a C++ exception inside the library (caught at the boundary) */
+#define DTSDF_ERR_EMPTY_CLOUD   -8   /* a frame without a single point where one must be drawn: the reference's
+                                        np.random.randint(0, 0) raises ValueError there (pre/process.py:77,80) */
 
 /* volume layouts */
 #define DTSDF_LAYOUT_CXYZ 0   /* out[c][x][y][z]: pre/process.py:196-198, pre/tsdf_for.py:118-120,
@@ -197,6 +204,32 @@ int dtsdf_resample_extrema_batch(int32_t n_frames, int32_t point_num,
                                  const int32_t* d_indices,
                                  double* d_out_pc, float* d_out_extrema, void* stream);
 
+/* ---- lossless volume codec on the device (gather of volumes to a training rank) ----------------
+ * A voxel whose three channels are all +0.0, all +1.0 or all -1.0 - outside the crop, no depth, or
+ * beyond the truncation distance (pre/process.py:159,167,180-194): about 90 % of a D-TSDF volume -
+ * becomes a 2-bit code (0, 1, 2); any other voxel is a "literal" (code 3) whose three floats are kept.
+ * The packed form of n frames of R^3 voxels is
+ *   d_codes      uint8[n][R^3/4]   voxel 4k+j of a frame in bits 2j..2j+1 of its byte k
+ *   d_lit_count  uint32[n]         literal voxels per frame
+ *   d_lits       float[n][3*R^3]   per frame, its literals in voxel order as (x, y, z) triples; only
+ *                                  the first 3*d_lit_count[f] floats of a frame's region are written
+ * (~47 KB in use per frame at R = 32 against 393 KB dense).  It replaces nothing in the reference,
+ * which is single-GPU; it exists so that the optional gather of volumes into
+ * one rank moves an eighth of the bytes over NVLink.  Both layouts (the codec works on channel planes).
+ *
+ * dtsdf_pack_volumes_batch     one pass over dense volumes in device memory.
+ * dtsdf_unpack_volumes_batch   the inverse, one CTA per frame.  The three packed arrays may live in
+ *                              ANOTHER GPU's memory (dtsdf_shared_open / dtsdf_enable_peer_access):
+ *                              the kernel pulls each frame's bytes in use over NVLink with TMA bulk
+ *                              copies and writes the dense volume into local memory, so transfer and
+ *                              expansion are one kernel on the receiving rank.
+ * All pointers 16-byte aligned. */
+int dtsdf_pack_volumes_batch(int32_t voxel_res, int32_t n_frames, const float* d_vol,
+                             uint8_t* d_codes, uint32_t* d_lit_count, float* d_lits, void* stream);
+int dtsdf_unpack_volumes_batch(int32_t voxel_res, int32_t n_frames, const uint8_t* d_codes,
+                               const uint32_t* d_lit_count, const float* d_lits,
+                               float* d_out_vol, void* stream);
+
 /* Joint normalisation (gt - mid_p)/max_l + 0.5 over n frames of 21 joints.
  * Replaces joint_nor.normalize (pre/joint_nor.py:8-18) and DataProcess.normalize
  * (cut_version/pre/process.py:251-263).  clamp01 != 0 also clamps to [0,1] as the
@@ -225,6 +258,8 @@ void dtsdf_ctx_destroy(dtsdf_ctx* ctx);
 #define DTSDF_OPT_PACKED_D2H   1
 #define DTSDF_OPT_HOST_THREADS 2
 #define DTSDF_OPT_CHUNK_MB     3   /* output megabytes per pipeline chunk of dtsdf_voxelize_host (default 64) */
+#define DTSDF_OPT_TEST_FAIL_CHUNK 100 /* testing only: dtsdf_voxelize_host fails with DTSDF_ERR_CUDA when it reaches
+                                         chunk `value`, with the chunks before it in flight (-1, the default: off) */
 int dtsdf_ctx_set_option(dtsdf_ctx* ctx, int32_t option, int64_t value);
 /* Statistics of the last dtsdf_voxelize_host call.
  *   DTSDF_STAT_D2H_BYTES   bytes that crossed PCIe device -> host (packed: codes + offsets +
@@ -285,6 +320,35 @@ int dtsdf_process_begin_host(dtsdf_ctx* ctx, double focal, int32_t n_frames,
 int dtsdf_process_finish_host(dtsdf_ctx* ctx, const dtsdf_config* cfg, int32_t point_num,
                               const int32_t* h_indices, double* h_out_pc,
                               float* h_out_vol, float* h_out_max_l, float* h_out_mid_p);
+
+/* The caller's global NumPy stream, in C.  DataProcess.set_length draws its resampling indices with
+ * np.random.randint on the GLOBAL legacy stream (pre/process.py:75-80), and those indices decide the
+ * bounding box and with it every voxel; to stay bit-compatible with a seeded reference run the library
+ * consumes exactly the same stream: MT19937 as NumPy steps it, bounded integers by masked rejection
+ * (numpy/random/src/distributions: random_bounded_uint64_fill, use_masked = True, 32-bit branch).
+ *   mt_key[624], *mt_pos   the state as np.random.get_state() returns it (key, pos); advanced in place, to be
+ *                          handed back with np.random.set_state().  (NumPy is a dependency of the reference,
+ *                          not part of it: tests pin this against np.random itself.)
+ * dtsdf_np_randint         out[0..count) = np.random.randint(0, high, size=count)
+ * dtsdf_resample_indices   out_idx[n][point_num]: the index vectors of set_length for n frames in order, given
+ *                          each frame's number of points (fewer than point_num: all of them once, then random
+ *                          repeats; otherwise point_num draws).  DTSDF_ERR_EMPTY_CLOUD where NumPy would raise. */
+int dtsdf_np_randint(uint32_t* mt_key, int32_t* mt_pos, int32_t high, int32_t count, int32_t* out);
+int dtsdf_resample_indices(uint32_t* mt_key, int32_t* mt_pos, int32_t n_frames, const int32_t* n_valid,
+                           int32_t point_num, int32_t* out_idx);
+
+/* DataProcess(frame, gt, point_num).process() for a whole batch in ONE call (pre/process.py:13-28 inside the
+ * frame loop of read_MSRA.main(), pre/read_MSRA.py:98-111): point clouds on the device, resampling indices
+ * drawn here from the caller's MT19937 state chunk by chunk while earlier chunks are on the GPU, gather +
+ * extrema + fused voxeliser per chunk, volumes back through the packed transfer of dtsdf_voxelize_host.
+ *   h_out_pc   double[n][point_num][3] or NULL (the sampled clouds are not brought back)
+ * cfg->bbox_mode is ignored (EXTREMA).  Equal to dtsdf_process_begin_host + np.random draws +
+ * dtsdf_process_finish_host, bit for bit, state of the stream included. */
+int dtsdf_process_host(dtsdf_ctx* ctx, const dtsdf_config* cfg, double focal, int32_t n_frames,
+                       const float* h_depth_packed, int64_t packed_len,
+                       const int64_t* h_crop_offsets, const int32_t* h_headers,
+                       int32_t point_num, uint32_t* mt_key, int32_t* mt_pos,
+                       double* h_out_pc, float* h_out_vol, float* h_out_max_l, float* h_out_mid_p);
 
 int dtsdf_normalize_joints_host(dtsdf_ctx* ctx, int32_t n_frames, const float* h_joints,
                                 const float* h_max_l, const float* h_mid_p,

@@ -107,6 +107,82 @@ def test_dataprocess_methods(forloop_golden):
         process.DataProcess(frame, None, 6000, aug=True).process()
 
 
+def test_dataprocess_instances_interleaved(forloop_golden):
+    """Two DataProcess objects (and a tsdf_for call) share the process-wide device context: calls of one
+    between point_cloud() and set_length() of the other, and in-place edits of the arrays handed back,
+    must not leak into a result - the reference always works on the array it is handed
+    (pre/process.py:70-84,102-120)."""
+    process, tsdf_for = import_pre("process"), import_pre("tsdf_for")
+    a, b = forloop_golden[0], forloop_golden[3]
+    fa = {"header": a["header"], "depth": a["depth"]}
+    fb = {"header": b["header"], "depth": b["depth"]}
+    dpa, dpb = process.DataProcess(fa, None, int(a["point_num"])), process.DataProcess(fb, None, int(b["point_num"]))
+    hpa = dpa.point_cloud()
+    hpb = dpb.point_cloud()                                   # overwrites the cloud resident in the context
+    tsdf_for.max_min_point(b["pc"])                           # and so does this
+    np.random.seed(int(a["np_random_seed"]))
+    pca = dpa.set_length(hpa)
+    assert np.array_equal(pca[:64], a["pc_head"])
+    if "pc" in a:
+        assert np.array_equal(pca, a["pc"])
+    np.random.seed(int(b["np_random_seed"]))
+    pcb = dpb.set_length(hpb)
+    ta = dpa.tsdf_f(pca)                                      # after another instance's set_length
+    assert _same(ta[0], a["tsdf"]) and ta[1] == a["max_l"]
+    assert _same(dpb.tsdf_f(pcb)[0], b["tsdf"])
+    # in-place edits count: the gather and the extrema follow the array's current content
+    hp2 = hpa.copy()
+    hp2[:, 0] += 5.0
+    np.random.seed(int(a["np_random_seed"]))
+    idx = np.random.randint(0, hp2.shape[0], size=dpa.point_num) if hp2.shape[0] >= dpa.point_num else None
+    hpa[:, 0] += 5.0
+    np.random.seed(int(a["np_random_seed"]))
+    moved = dpa.set_length(hpa)
+    if idx is not None:
+        assert np.array_equal(moved, hp2[idx])
+    pca[:, 2] -= 3.0
+    pmax, pmin = dpa.max_min_point(pca)
+    z = pca[:, 2][pca[:, 2] != 0]
+    assert pmax[2] == np.float32(z.max()) and pmin[2] == np.float32(z.min())
+
+
+def test_process_host_one_call_equals_per_frame_numpy_draws():
+    """dtsdf_process_host (index vectors drawn by the library from the caller's MT19937 state, chunk by chunk,
+    pipelined) against dtsdf_process_begin_host + one np.random.randint call per frame +
+    dtsdf_process_finish_host: the same clouds, volumes, max_l, mid_p and the same np.random state afterwards.
+    Packed and plain routes, several chunks, frames with fewer points than point_num."""
+    frames = synth.make_frames(range(1200, 1200 + 150))
+    small = synth.make_frame(3, box=(150, 100, 190, 140))              # 1,600 px: fewer points than 6000
+    frames[5] = small
+    frames[77] = small
+    v = pkg.Voxelizer(device=0)
+    for chunk_mb, n, want_points, packed_route in ((64, 150, True, 1), (2, 150, False, 1), (1, 150, True, 1),
+                                                   (64, 30, True, 1), (1, 60, True, 0)):
+        v.set_option(pkg.capi.OPT_CHUNK_MB, chunk_mb)
+        v.set_option(pkg.capi.OPT_PACKED_D2H, packed_route)
+        np.random.seed(99)
+        a = v.process_frames_two_calls(frames[:n], 6000, want_points=want_points)
+        tail_a = np.random.randint(0, 1 << 30, size=4)
+        np.random.seed(99)
+        b = v.process_frames(frames[:n], 6000, want_points=want_points)
+        tail_b = np.random.randint(0, 1 << 30, size=4)
+        assert np.array_equal(tail_a, tail_b)
+        assert (a[0] is None) == (b[0] is None) == (not want_points)
+        if want_points:
+            assert np.array_equal(a[0], b[0])
+        assert _same(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    # a frame without a single point: the reference's np.random.randint(0, 0) raises ValueError
+    empty = synth.make_frame(4)
+    empty["depth"] = np.zeros_like(empty["depth"])
+    with pytest.raises(ValueError):
+        v.process_frames(frames[:3] + [empty] + frames[3:6], 6000)
+    np.random.seed(1)
+    out = v.process_frames(frames[:4], 6000)                              # the context works afterwards
+    np.random.seed(1)
+    assert _same(out[1], v.process_frames_two_calls(frames[:4], 6000)[1])
+    v.close()
+
+
 def test_tsdf_for_module(forloop_golden):
     tsdf_for = import_pre("tsdf_for")
     c = forloop_golden[3]
@@ -275,6 +351,57 @@ def test_host_pipeline_many_small_chunks_and_destination_alignments():
     v.set_option(pkg.capi.OPT_CHUNK_MB, 64)
     assert _same(v.voxelize_packed(headers, offsets, packed)[0], want)
     v.close()
+
+
+def test_host_pipeline_failure_leaves_no_writer_behind():
+    """A failure in the middle of the chunk loop (injected: DTSDF_OPT_TEST_FAIL_CHUNK) with earlier chunks in
+    flight: the call returns the error only after every copy and expansion thread is done or cancelled -
+    nothing writes into the caller's buffers after the return - and the context works afterwards.  Packed
+    and plain routes, pageable max_l / mid_p."""
+    import time
+    frames = synth.make_frames(range(7000, 7000 + 240))
+    headers, offsets, packed = pack_simple(frames)
+    want, wml, wmp, _ = c_oracle.dtsdf_batch(headers, offsets, packed)
+    v = pkg.Voxelizer(device=0)
+    v.set_option(pkg.capi.OPT_CHUNK_MB, 4)                       # 10 frames per chunk, 24 chunks
+    out = np.empty_like(want)
+    ml, mp = np.empty(len(frames), np.float32), np.empty((len(frames), 3), np.float32)
+    for packed_route in (1, 0):
+        v.set_option(pkg.capi.OPT_PACKED_D2H, packed_route)
+        for fail_at in (0, 3, 7, 23):
+            v.set_option(pkg.capi.OPT_TEST_FAIL_CHUNK, fail_at)
+            with pytest.raises(pkg.DtsdfError) as ei:
+                v.voxelize_packed(headers, offsets, packed, out_vol=out, out_max_l=ml, out_mid_p=mp)
+            assert ei.value.code == pkg.capi.ERR_CUDA
+            out[...] = np.float32(-7.0)
+            ml[...] = -7.0
+            mp[...] = -7.0
+            time.sleep(0.05)
+            assert (out == np.float32(-7.0)).all() and (ml == -7.0).all() and (mp == -7.0).all()
+        v.set_option(pkg.capi.OPT_TEST_FAIL_CHUNK, -1)
+        v.voxelize_packed(headers, offsets, packed, out_vol=out, out_max_l=ml, out_mid_p=mp)
+        assert _same(out, want) and np.array_equal(ml, wml) and np.array_equal(mp, wmp)
+    v.close()
+
+
+def test_host_entry_points_restore_the_current_device():
+    """A process that drives several GPUs: the library's host entry points run on the context's device
+    and put the caller's current device back."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    frames = synth.make_frames(range(10, 14))
+    torch.cuda.set_device(0)
+    v1 = pkg.Voxelizer(device=1)
+    assert torch.cuda.current_device() == 0
+    got = v1.voxelize_frames(frames)[0]
+    v1.point_cloud(frames[0])
+    assert torch.cuda.current_device() == 0
+    x = torch.zeros(4, device="cuda")
+    assert x.device.index == 0
+    assert _same(got, c_oracle.dtsdf_batch(*pack_simple(frames))[0])
+    v1.close()
+    assert torch.cuda.current_device() == 0
 
 
 def test_host_pipeline_random_configurations():
@@ -514,6 +641,34 @@ def test_on_the_fly_loader_overlapped_batches(vox):
         assert seen == len(frames) and float(acc) > 0
 
 
+def test_on_the_fly_loader_consumer_stream_and_previous_batch(vox):
+    """The loader's contract: a batch stays valid during the iteration that received it and the next one,
+    ordered on whatever stream is current in the consumer - here a stream of its own, with the previous
+    batch used (delayed) together with the current one and no host synchronisation in the loop."""
+    import importlib
+    import torch
+    lmod = importlib.import_module(pkg.__name__ + ".loader")
+    frames = synth.make_frames(range(1700, 1700 + 96))
+    res = lmod.ResidentFrames.from_frames(frames)
+    want_vol = torch.from_numpy(vox.voxelize_frames(frames)[0]).cuda()
+    loader = lmod.OnTheFlyLoader(res, batch_size=8)
+    mine = torch.cuda.Stream()
+    spin = torch.empty(1 << 24, device="cuda")
+    sums, prev = [], None
+    with torch.cuda.stream(mine):
+        for tsdf, jn, max_l, mid_p in loader:
+            for _ in range(4):
+                spin.add_(1.0)                            # keeps the consumer's stream behind the side stream
+            cur = tsdf.double().abs().sum()
+            sums.append(cur if prev is None else cur + prev.double().abs().sum())   # previous batch, one iteration late
+            prev = tsdf
+    mine.synchronize()
+    ref = [want_vol[8 * k:8 * k + 8].double().abs().sum() for k in range(12)]
+    for k in range(12):
+        w = ref[k] if k == 0 else ref[k] + ref[k - 1]
+        assert float(sums[k]) == float(w), k
+
+
 # ----------------------------------------------------------------------------- augmentation (N2)
 @pytest.mark.parametrize("layout", [0, 1])
 @pytest.mark.parametrize("R", [32, 48])
@@ -638,7 +793,7 @@ def test_on_the_fly_loader_with_augmentation():
     seen = 0
     for k, (tsdf, jn, max_l, mid_p) in enumerate(loader):
         m = tsdf.shape[0]
-        aug = loader.last_aug[k % 2]
+        aug = loader.last_aug[k % loader.NBUF]
         sel = np.arange(seen, seen + m)
         sub = [frames[i] for i in sel]
         h, o, p = pack_simple(sub)

@@ -2,13 +2,14 @@
 checking, packing, frame sharding (incl. a world_size-2 gloo run) and the synthetic generator."""
 import ctypes
 import os
+import subprocess
 import sys
 
 import numpy as np
 import pytest
 
 import __graft_entry__ as graft
-from helpers import pack_simple, pkg, synth
+from helpers import ROOT, pack_simple, pkg, synth
 
 
 def test_library_exports_every_symbol_in_header():
@@ -186,3 +187,71 @@ def test_two_rank_sharding_and_gather_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+# ------------------------------------------------------------------ the caller's np.random stream, in C
+_RNG_CHECK = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import __graft_entry__ as g
+capi = g.load_package().capi
+rng = np.random.default_rng(7)
+n = %d
+# numbers of valid points as MSRA crops have them, plus the corners: 1 point, powers of two and their
+# neighbours (the rejection mask changes there), fewer points than point_num
+n_valid = rng.integers(1, 30000, size=n).astype(np.int32)
+corner = np.array([1, 2, 3, 4, 5, 255, 256, 257, 4095, 4096, 4097, 5999, 6000, 6001, 8191, 8192, 8193, 65535, 65536,
+                   65537, (1 << 20) - 1, 1 << 20], dtype=np.int32)
+n_valid[:corner.size] = corner
+point_num = 6000
+np.random.seed(20181)
+np.random.random(777)                                   # not at a block boundary of the generator
+state = np.random.get_state()
+bad = 0
+CH = 2000
+for i0 in range(0, n, CH):                              # the library, a chunk of frames per call
+    np.random.set_state(state)
+    want = np.empty((min(CH, n - i0), point_num), dtype=np.int32)
+    for i in range(want.shape[0]):                      # pre/process.py:70-84, verbatim calls
+        ps = int(n_valid[i0 + i])
+        if ps < point_num:
+            want[i] = np.arange(0, point_num, 1, dtype=np.int32)
+            want[i, ps:] = np.random.randint(0, ps, size=point_num - ps)
+        else:
+            want[i] = np.random.randint(0, ps, size=point_num)
+    after = np.random.get_state()
+    np.random.set_state(state)
+    got = capi.resample_indices(n_valid[i0:i0 + want.shape[0]], point_num)
+    mine = np.random.get_state()
+    bad += int(not np.array_equal(got, want))
+    bad += int(not (np.array_equal(mine[1], after[1]) and mine[2] == after[2]))
+    state = after
+# single calls incl. count 0 and high 1 (which consumes nothing)
+np.random.seed(5)
+a = [np.random.randint(0, h, size=c) for h, c in ((1, 10), (7, 0), (2, 33), (1 << 30, 5), (3, 1000))]
+np.random.seed(5)
+b = [capi.np_randint(h, c) for h, c in ((1, 10), (7, 0), (2, 33), (1 << 30, 5), (3, 1000))]
+bad += int(not all(np.array_equal(x, y) for x, y in zip(a, b)))
+bad += int(np.random.randint(0, 1 << 20) != (np.random.seed(5), [np.random.randint(0, h, size=c) for h, c in
+            ((1, 10), (7, 0), (2, 33), (1 << 30, 5), (3, 1000))], np.random.randint(0, 1 << 20))[2])
+try:
+    capi.np_randint(0, 3)
+    bad += 1
+except ValueError:
+    pass
+print("RNG_CHECK", bad)
+'''
+
+
+@pytest.mark.parametrize("isa,frames", [("native", 100000), ("scalar", 6000)])
+def test_resampling_indices_equal_numpy_global_stream(isa, frames):
+    """dtsdf_resample_indices / dtsdf_np_randint consume the caller's legacy np.random stream exactly as
+    the reference's own np.random.randint calls do (pre/process.py:75-80): equal index vectors and equal
+    generator state afterwards, over 10^5 frames of random point counts (both instruction-set paths)."""
+    env = dict(os.environ)
+    if isa == "scalar":
+        env["DTSDF_RNG_ISA"] = "scalar"
+    r = subprocess.run([sys.executable, "-c", _RNG_CHECK % (ROOT, frames)], capture_output=True, text=True, env=env,
+                       timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "RNG_CHECK 0" in r.stdout, r.stdout[-500:]
