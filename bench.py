@@ -236,7 +236,7 @@ def run_reference(args, rank, world):
     from __graft_entry__ import build_oracle, load_package
     build_oracle()
     pkg = load_package()
-    headers, depth = pkg.synth.make_uniform_batch(min(args.frames, 4096), seed0=0, box=BOX)
+    headers, depth = pkg.synth.make_uniform_batch(min(args.frames, 4096), seed0=1234, box=BOX)    # the first frames of rank 0's batch
     offsets = (np.arange(headers.shape[0], dtype=np.int64) * depth.shape[1])
     packed = depth.reshape(-1)
     from oracle import c_oracle
@@ -261,7 +261,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args, world),
+        "data": "synthetic", "config": dict(workload_config(args, world), frames_timed_per_step=per_step,
+                                            note="the CPU arm times a bounded sample of the workload: %d frames per step "
+                                                 "(the first frames of the same batch), not all %d" % (per_step, args.frames)),
         "cpu_baseline": {
             "value": value, "unit": UNIT, "cores": used, "kind": "port",
             "sample": "%d frames per step x %d steps of the same workload; C restatement of the reference's "
@@ -273,6 +275,252 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+
+# ------------------------------------------------------------------------------------------------
+# gather of every rank's volumes into rank 0 (BASELINE.json configs[2]) - three ways
+# ------------------------------------------------------------------------------------------------
+NVLINK_PEER_GBS = 770.0        # measured peer copy per direction on this pool (B200_PROFILING.md)
+
+
+def run_gather_legs(pkg, dist, dev, rank, world, F, R, cfg, inputs, d_vol, d_maxl, d_mid, barrier, max_over_ranks):
+    """voxelise + gather, timed per step with CUDA events on every rank, max over ranks.
+      nccl    kernel into local HBM, then dist.gather of the dense volumes (ncclSend/Recv into rank 0)
+      p2p     the voxeliser's own stores land in rank 0's IPC-mapped buffer over NVLink, then a barrier
+      packed  every rank packs its volumes (2-bit codes + literal triples, lossless) in its own HBM; rank 0's
+              expansion kernel pulls the bytes in use over NVLink with TMA bulk copies while it writes the dense
+              volumes (gather.PackedVolumeGather): transfer and expansion are one kernel
+    Every leg's result on rank 0 is compared with the dense NCCL gather over ALL frames."""
+    import importlib
+    import torch
+    gmod = importlib.import_module(pkg.__name__ + ".gather")
+    d_packed, d_off, d_hdr, max_px = inputs
+    vol_bytes = F * 3 * R ** 3 * 4
+    dense_bytes = (world - 1) * vol_bytes
+    peak, _ = measured_peak()
+
+    def voxelise(out):
+        pkg.voxelize_device(d_packed, d_off, d_hdr, max_px, cfg, out_vol=out, out_max_l=d_maxl, out_mid_p=d_mid)
+
+    def timed(fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(reps):
+            fn()
+        g1.record()
+        torch.cuda.synchronize()
+        ms = max_over_ranks(g0.elapsed_time(g1)) / reps
+        barrier()
+        return ms
+
+    def all_ok(flag):
+        t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() == 1.0)
+
+    res = {"frames_total": F * world, "dense_bytes_to_rank0": int(dense_bytes),
+           "timed": "one step = voxelise every rank's %d frames + gather to rank 0; CUDA events, max over ranks" % F}
+    # ---- nccl: the dense gather; its result is the reference for the two others
+    bufs = [torch.empty_like(d_vol) for _ in range(world)] if rank == 0 else None
+
+    def nccl_step():
+        voxelise(d_vol)
+        dist.gather(d_vol, bufs, dst=0)
+    ms = timed(nccl_step, reps=3, warm=1)
+    res["nccl"] = {"value": F * world / (ms * 1e-3), "unit": UNIT, "ms": ms,
+                   "rank0_ingress_gbs": dense_bytes / (ms * 1e-3) / 1e9}
+
+    # ---- p2p: fused peer stores
+    peer = gmod.PeerVolumeBuffer(F * world, R, root=0)
+
+    def p2p_step():
+        voxelise(peer.mine)
+    ms = timed(p2p_step, reps=3, warm=1)
+    peer.complete()
+    same = True
+    if rank == 0:
+        same = all(bool(torch.equal(peer.full[r * F:(r + 1) * F].view(torch.int32), bufs[r].view(torch.int32)))
+                   for r in range(world))
+    res["p2p"] = {"value": F * world / (ms * 1e-3), "unit": UNIT, "ms": ms, "matches_nccl_gather_all_frames": all_ok(same),
+                  "rank0_ingress_gbs": dense_bytes / (ms * 1e-3) / 1e9}
+    peer.close()
+    del peer
+    torch.cuda.empty_cache()
+
+    # ---- packed: pack on every rank, pull + expand on rank 0
+    g = gmod.PackedVolumeGather([F] * world, R, root=0)
+
+    def packed_step():
+        if rank == 0:
+            voxelise(g.mine)
+        else:
+            voxelise(d_vol)
+            g.pack(d_vol)
+        g.gather()
+    ms = timed(packed_step, reps=5, warm=2)
+    nvlink_bytes = g.bytes_on_nvlink()
+    same = True
+    if rank == 0:
+        same = all(bool(torch.equal(g.full[r * F:(r + 1) * F].view(torch.int32), bufs[r].view(torch.int32)))
+                   for r in range(world))
+    res["packed"] = {"value": F * world / (ms * 1e-3), "unit": UNIT, "ms": ms,
+                     "matches_nccl_gather_all_frames": all_ok(same), "bytes_pulled_over_nvlink": int(nvlink_bytes),
+                     "rank0_ingress_gbs": nvlink_bytes / (ms * 1e-3) / 1e9,
+                     "rank0_hbm_write_gbs": world * vol_bytes / (ms * 1e-3) / 1e9}
+    g.close()
+    del g, bufs
+    torch.cuda.empty_cache()
+    # what bounds a gather into ONE GPU: its NVLink ingress (dense) and, for any form, its own HBM writes
+    hbm_ms = world * vol_bytes / (peak * 1e9) * 1e3
+    res["bound"] = {
+        "rank0_hbm_write_ms": hbm_ms, "rank0_hbm_write_volumes_per_s": F * world / (hbm_ms * 1e-3),
+        "dense_nvlink_ingress_ms": dense_bytes / (NVLINK_PEER_GBS * 1e9) * 1e3,
+        "packed_nvlink_ingress_ms": nvlink_bytes / (NVLINK_PEER_GBS * 1e9) * 1e3,
+        "note": "every volume of every rank is written into rank 0's HBM once (%.1f GB at the measured copy peak of "
+                "%.0f GB/s): no gather into one GPU can beat ~%.1f M volumes/s, about one GPU's own voxelising rate; "
+                "NVLink ingress at the measured %.0f GB/s peer-copy rate bounds the dense forms far below that"
+                % (world * vol_bytes / 1e9, peak, F * world / hbm_ms / 1e3, NVLINK_PEER_GBS),
+        "packed_frac_of_hbm_write_bound": hbm_ms / res["packed"]["ms"]}
+    res["best"] = max(("nccl", "p2p", "packed"), key=lambda k: res[k]["value"])
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations, one short measurement each (device-resident, CUDA events)
+# ------------------------------------------------------------------------------------------------
+def run_secondary(pkg, dev, rank, world, args, max_over_ranks, barrier):
+    import importlib
+    import torch
+    capi = pkg.capi
+    amod = importlib.import_module(pkg.__name__ + ".augment")
+    peak, _ = measured_peak()
+    out = {}
+
+    def timed(fn, reps=5, warm=3):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+        barrier()
+        return ms
+
+    def entry(name, frames, ms, alg, extra=None):
+        e = {"frames_per_gpu": frames, "ms": ms, "value": frames * world / (ms * 1e-3), "unit": UNIT,
+             "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg}}
+        if extra:
+            e.update(extra)
+        out[name] = e
+
+    F = args.frames
+    headers, depth = pkg.synth.make_uniform_batch(F, seed0=4321 + 7919 * rank, box=BOX)
+    offsets, packed_len, max_px = capi.pack_plan(headers)
+    d_packed = torch.from_numpy(depth.reshape(-1)).to(dev)
+    d_off, d_hdr = torch.from_numpy(offsets).to(dev), torch.from_numpy(headers).to(dev)
+    d_maxl = torch.empty((F,), dtype=torch.float32, device=dev)
+    d_mid = torch.empty((F, 3), dtype=torch.float32, device=dev)
+
+    # ---- configs[3]: resolution sweep (same crops; B = 24 + 4 bw bh + 12 R^3 + 16 per frame)
+    for R, n in ((48, F), (64, min(F, 4000))):
+        cfg = capi.default_config(R, args.layout, pkg.BBOX_PIXELS)
+        vol = torch.empty((n, 3, R, R, R), dtype=torch.float32, device=dev)
+        ms = timed(lambda: pkg.voxelize_device(d_packed, d_off[:n], d_hdr[:n], max_px, cfg, out_vol=vol,
+                                               out_max_l=d_maxl[:n], out_mid_p=d_mid[:n]))
+        entry("R%d" % R, n, ms, algorithmic_bytes(headers[:n], R), {"config": "configs[3]: same crops, R=%d" % R})
+        del vol
+        torch.cuda.empty_cache()
+
+    R = 32
+    cfg = capi.default_config(R, args.layout, pkg.BBOX_PIXELS)
+    vol = torch.empty((F, 3, R, R, R), dtype=torch.float32, device=dev)
+
+    # ---- configs[4] kernel: augmented D-TSDF (per-frame stretch + rotation), joints mapped in the same launch
+    aug = torch.from_numpy(amod.make_augmentations(F, np.random.default_rng(rank), centers=np.tile([0, 0, -380.0], (F, 1)))).to(dev)
+    ms = timed(lambda: amod.voxelize_aug_device(d_packed, d_off, d_hdr, aug, max_px, cfg, out_vol=vol, out_max_l=d_maxl,
+                                                out_mid_p=d_mid))
+    entry("augmented", F, ms, algorithmic_bytes(headers, R) + 84 * F,
+          {"config": "configs[4] kernel: dtsdf_voxelize_aug_batch, random stretch [2/3,3/2] + rotation per frame"})
+    del aug
+
+    # ---- the semantics the reference runs in production: DataProcess.process() (bounding box from the
+    #      resampled 6000-point cloud, pre/process.py:13-28).  Device kernels alone, then the host call.
+    P = 6000
+    lib = capi.load_library()
+    import ctypes
+    n_px = int(headers[0, 4] - headers[0, 2]) * int(headers[0, 5] - headers[0, 3])
+    d_points = torch.empty((F * n_px, 3), dtype=torch.float64, device=dev)
+    d_poff = (torch.arange(F, dtype=torch.int64, device=dev) * n_px).contiguous()
+    d_nvalid = torch.empty((F,), dtype=torch.int32, device=dev)
+    d_ext = torch.empty((F, 6), dtype=torch.float32, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def point_clouds():
+        capi.check(lib.dtsdf_point_cloud_batch(F, ctypes.c_double(241.42), d_packed.data_ptr(), d_off.data_ptr(),
+                                               d_hdr.data_ptr(), d_points.data_ptr(), d_poff.data_ptr(),
+                                               d_nvalid.data_ptr(), stream))
+    point_clouds()
+    n_valid = d_nvalid.cpu().numpy()
+    np.random.seed(1 + rank)
+    d_idx = torch.from_numpy(capi.resample_indices(n_valid, P)).to(dev)
+    cfg_e = capi.default_config(R, args.layout, pkg.BBOX_EXTREMA)
+
+    def process_device():
+        point_clouds()
+        capi.check(lib.dtsdf_resample_extrema_batch(F, P, d_points.data_ptr(), d_poff.data_ptr(), d_idx.data_ptr(), None,
+                                                    d_ext.data_ptr(), stream))
+        pkg.voxelize_device(d_packed, d_off, d_hdr, max_px, cfg_e, aux=d_ext, out_vol=vol, out_max_l=d_maxl, out_mid_p=d_mid)
+    ms = timed(process_device)
+    alg = algorithmic_bytes(headers, R) + int(np.sum(4 * n_px + 24 * n_valid.astype(np.int64) + 28 * P + 24))
+    entry("process_semantics_device", F, ms, alg,
+          {"config": "bbox from the resampled 6000-point cloud: point_cloud_kernel (f64) + resample_extrema_kernel + "
+                     "fused kernel (extrema mode), index vectors resident",
+           "bytes": "fused 455,656 + crop 4 bw bh + cloud 24 n_valid written + gather 24+4 per sample + 24"})
+    del d_points, d_idx, vol
+    torch.cuda.empty_cache()
+
+    # the host call: crops in, volumes out, index vectors drawn from np.random's MT19937 by the library
+    vox = pkg.Voxelizer(device=dev.index, voxel_res=R)
+    n_host = min(F, 4000)
+    h_out = capi.PinnedBuffer((n_host, 3, R, R, R), np.float32)
+    packed_h = np.ascontiguousarray(depth.reshape(-1)[:int(offsets[n_host]) if n_host < F else depth.size])
+    np.random.seed(7 + rank)
+    vox.process_packed(headers[:n_host], offsets[:n_host], packed_h, P, want_points=False, out_vol=h_out.array)
+    barrier()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        vox.process_packed(headers[:n_host], offsets[:n_host], packed_h, P, want_points=False, out_vol=h_out.array)
+    dt = max_over_ranks(time.perf_counter() - t0) / reps
+    barrier()
+    out["process_semantics_host_call"] = {
+        "frames_per_gpu": n_host, "ms": dt * 1e3, "value": n_host * world / dt, "unit": "frames/s",
+        "config": "Voxelizer.process_packed(want_points=False) = dtsdf_process_host: host crops in, volumes out (pinned), "
+                  "resampling indices drawn in C from the caller's np.random MT19937 state (bit-compatible with the "
+                  "reference's per-frame np.random.randint calls, pre/process.py:75-80)"}
+    vox.close()
+    h_out.free()
+
+    # ---- ragged crops (SURVEY.md section 8d: every frame its own 80-150 x 80-140 px bounding box)
+    n_r = min(F, 4000)
+    frames = pkg.synth.make_frames(range(200000 + n_r * rank, 200000 + n_r * (rank + 1)))
+    rh, ro, rp, rmax = pkg.pack_frames(frames)
+    del frames
+    dr = (torch.from_numpy(rp).to(dev), torch.from_numpy(ro).to(dev), torch.from_numpy(rh).to(dev))
+    vol = torch.empty((n_r, 3, R, R, R), dtype=torch.float32, device=dev)
+    ms = timed(lambda: pkg.voxelize_device(dr[0], dr[1], dr[2], rmax, cfg, out_vol=vol, out_max_l=d_maxl[:n_r],
+                                           out_mid_p=d_mid[:n_r]))
+    entry("ragged", n_r, ms, algorithmic_bytes(rh, R), {"config": "every frame its own 80-150 x 80-140 px crop, R=32"})
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -360,49 +608,18 @@ def run_ours(args, rank, local_rank, world):
     ms = max_over_ranks(local_ms)
     value = F * world * args.steps / (ms * 1e-3)
 
-    # ---- optional gather of the volumes to rank 0 (BASELINE.json configs[2]), two ways:
-    #      "nccl": kernel writes local HBM, then dist.gather;  "p2p": the kernel stores straight into
-    #      rank 0's buffer over NVLink (gather.PeerVolumeBuffer), only a barrier follows
+    # ---- gather of the volumes to rank 0 (BASELINE.json configs[2]: "... with volume all-gather to rank 0")
     gather = None
-    if args.gather and world > 1:
-        import importlib
-        gmod = importlib.import_module(pkg.__name__ + ".gather")
-        bufs = [torch.empty_like(d_vol) for _ in range(world)] if rank == 0 else None
-        dist.gather(d_vol, bufs, dst=0)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        step()
-        dist.gather(d_vol, bufs, dst=0)
-        g1.record()
-        torch.cuda.synchronize()
-        gms = max_over_ranks(g0.elapsed_time(g1))
-        gather = {"nccl": {"value": F * world / (gms * 1e-3), "unit": UNIT, "ms": gms},
-                  "bytes_to_rank0": int((world - 1) * d_vol.numel() * 4)}
-        del bufs
-        peer = gmod.PeerVolumeBuffer(F * world, R, root=0)
-
-        def p2p_step():
-            pkg.voxelize_device(d_packed, d_off, d_hdr, max_px, cfg, out_vol=peer.mine, out_max_l=d_maxl,
-                                out_mid_p=d_mid)
-        for _ in range(2):
-            p2p_step()
-        peer.complete()
-        reps = 5
-        g0.record()
-        for _ in range(reps):
-            p2p_step()
-        g1.record()
-        torch.cuda.synchronize()
-        pms = max_over_ranks(g0.elapsed_time(g1)) / reps
-        peer.complete()
-        ok_t = torch.tensor([1.0 if torch.equal(peer.mine.to(dev), d_vol) else 0.0], dtype=torch.float64, device=dev)
-        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
-        same = bool(ok_t.item() == 1.0)
-        gather["p2p"] = {"value": F * world / (pms * 1e-3), "unit": UNIT, "ms": pms,
-                         "matches_local_run": same,
-                         "how": "fused: kernel stores into rank 0's IPC-mapped buffer over NVLink, then a barrier"}
-        peer.close()
+    if world > 1 and not args.no_gather:
+        gather = run_gather_legs(pkg, dist, dev, rank, world, F, R, cfg, (d_packed, d_off, d_hdr, max_px),
+                                 d_vol, d_maxl, d_mid, barrier, max_over_ranks)
+    secondary = None
+    if not args.no_secondary:
+        del d_vol
+        torch.cuda.empty_cache()
+        secondary = run_secondary(pkg, dev, rank, world, args, max_over_ranks, barrier)
+        d_vol = torch.empty((F, 3, R, R, R), dtype=torch.float32, device=dev)
+        step()                                              # the end-to-end leg compares against it
 
     # ---- end to end through the host entry point (pinned host buffers, H2D + kernel + D2H)
     vox = pkg.Voxelizer(device=local_rank, voxel_res=R)
@@ -428,16 +645,78 @@ def run_ours(args, rank, local_rank, world):
     # plain device->host copies of the float volumes first (PCIe-bound), then the library's default:
     # volumes cross PCIe packed and are expanded into the host buffer by the host threads
     e2e_plain = e2e_value = pcie_d2h = ok = None
+    e2e_extra = {}
     h2d = int(h_packed.array.nbytes + headers.nbytes + offsets.nbytes)
     d2h = int(F * 3 * R ** 3 * 4 + h_maxl.array.nbytes + h_mid.array.nbytes)
     if do_e2e:
         vox.set_option(capi.OPT_PACKED_D2H, 0)
         e2e_plain = time_e2e()
         vox.set_option(capi.OPT_PACKED_D2H, 1)
+        vox.set_option(capi.OPT_LITERAL_PUSH, 1)
+        e2e_push = time_e2e()
+        vox.set_option(capi.OPT_LITERAL_PUSH, 0)
         e2e_value = time_e2e()
         pcie_d2h = vox.stat(capi.STAT_D2H_BYTES)
-        # the e2e result is the real thing: compare with the device-resident run
-        ok = bool(np.array_equal(h_vol.array[:64], d_vol[:64].cpu().numpy()))
+        # the e2e result is the real thing: compare ALL of it with the device-resident run
+        ok = True
+        for i0 in range(0, F, 1000):
+            ok = ok and bool(torch.equal(torch.from_numpy(h_vol.array[i0:i0 + 1000]).to(dev).view(torch.int32),
+                                         d_vol[i0:i0 + 1000].view(torch.int32)))
+        # ---- what bounds it, measured in this run: (1) the host's stores of the dense volumes (the expansion
+        # alone, same threads, same destination, all ranks at once), (2) the crops over PCIe (host -> device alone)
+        lazy, _, _ = vox.voxelize_packed_lazy(headers, offsets, h_packed.array, layout=args.layout, bbox_mode=pkg.BBOX_PIXELS)
+        lazy.expand(out=h_vol.array)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            lazy.expand(out=h_vol.array)
+        expand_rate = F * world * 3 / max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        packed_host_bytes = lazy.nbytes
+        lazy.close()
+        torch.cuda.synchronize()
+        t_h = torch.from_numpy(h_packed.array)
+        d_tmp = torch.empty_like(d_packed)
+        d_tmp.copy_(t_h, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            d_tmp.copy_(t_h, non_blocking=True)          # (page-locked by dtsdf_host_alloc: a plain DMA)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_ms = max_over_ranks(c0.elapsed_time(c1)) / 3
+        barrier()
+        del d_tmp
+        h2d_rate = F * world / (h2d_ms * 1e-3)
+
+        def lazy_step():
+            lz, _, _ = vox.voxelize_packed_lazy(headers, offsets, h_packed.array, layout=args.layout, bbox_mode=pkg.BBOX_PIXELS)
+            lz.close()
+        for _ in range(2):
+            lazy_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            lazy_step()
+        packed_result_rate = F * world * e2e_steps / max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        bound_v = min(expand_rate, h2d_rate)
+        e2e_extra = {
+            "bound": {"value": bound_v, "unit": UNIT,
+                      "what": "host stores of the dense volumes" if expand_rate <= h2d_rate else "crops over PCIe (H2D)",
+                      "host_expansion_alone_value": expand_rate,
+                      "host_expansion_alone_gbs": expand_rate * 3 * R ** 3 * 4 / 1e9,
+                      "h2d_alone_value": h2d_rate, "h2d_alone_gbs": h_packed.array.nbytes * world / (h2d_ms * 1e-3) / 1e9,
+                      "how": "measured in this run on all %d rank(s) at once: dtsdf_expand_frames of the same %d packed volumes "
+                             "into the same pinned destination with the call's thread count; one pinned host -> device copy of "
+                             "the crops" % (world, F)},
+            "frac": e2e_value / bound_v,
+            "push_kernel_value": e2e_push,
+            "packed_result_value": packed_result_rate,
+            "packed_result": "dtsdf_voxelize_host_packed: the volumes stay packed in host memory (%.1f KB per volume instead of "
+                             "%.0f KB), expanded on demand by dtsdf_expand_frames" % (packed_host_bytes / F / 1e3, 3 * R ** 3 * 4 / 1e3),
+        }
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -450,19 +729,24 @@ def run_ours(args, rank, local_rank, world):
             "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps if do_e2e else 0, "api": "dtsdf_voxelize_host (C ABI, pinned host buffers)",
-                    "matches_device_run": ok,
-                    "transfer": "volumes packed on the GPU (2-bit codes + literals, lossless), written to mapped "
-                                "pinned memory, expanded into the caller's buffer by host threads",
-                    "d2h_bytes_on_pcie_per_step": pcie_d2h, "plain_copy_value": e2e_plain},
+                    "matches_device_run_all_frames": ok,
+                    "transfer": "volumes packed on the GPU (2-bit codes + literals, lossless), brought back by the copy "
+                                "engine, expanded into the caller's buffer by host threads",
+                    "d2h_bytes_on_pcie_per_step": pcie_d2h, "plain_copy_value": e2e_plain, **e2e_extra},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None if args.ragged else ncu_traffic(R, args.layout, F),
+                         "traffic_source": "profiles/roofline_traffic.json: ncu --set full capture of this kernel "
+                                           "(dram__bytes_read.sum + dram__bytes_write.sum per launch), scaled to this run's "
+                                           "frame count; not re-measured inside this run",
                          "peak_source": peak_src, "kernel": "dtsdf_fused_kernel<%d,%d>" % (R, args.layout),
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kernel_s * 1e3},
             "clocks": sampler.summary(),
         }
         if gather is not None:
             line["with_gather_to_rank0"] = gather
+        if secondary is not None:
+            line["secondary"] = secondary
         if world == 1 and not args.no_cpu_baseline:
             from __graft_entry__ import build_oracle
             build_oracle()
@@ -494,7 +778,8 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU")
     ap.add_argument("--res", type=int, default=32, choices=[32, 48, 64])
     ap.add_argument("--layout", type=int, default=0, choices=[0, 1], help="0 = (c,x,y,z), 1 = (c,z,y,x)")
-    ap.add_argument("--gather", action="store_true", help="also time voxelise + gather of volumes to rank 0")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the voxelise + gather-to-rank-0 legs")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short measurements of the other configurations")
     ap.add_argument("--e2e-steps", type=int, default=10, help="0 skips the end-to-end leg (sizes beyond host memory)")
     ap.add_argument("--ragged", action="store_true", help="every frame its own bounding box instead of 120x130")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

@@ -9,11 +9,11 @@ Python identifier; load it with ``__graft_entry__.load_package()`` (alias
 """
 from . import capi, synth
 from .capi import (BBOX_EXTREMA, BBOX_GRID, BBOX_PIXELS, LAYOUT_CXYZ, LAYOUT_CZYX, DtsdfError)
-from .voxelizer import (Voxelizer, default_voxelizer, normalize_joints_device, pack_frames,
+from .voxelizer import (PackedHostVolumeList, PackedHostVolumes, Voxelizer, default_voxelizer, normalize_joints_device, pack_frames,
                         shard_packed, shard_range, voxelize_device)
 
 __all__ = [
-    "capi", "synth", "Voxelizer", "default_voxelizer", "pack_frames", "voxelize_device",
+    "capi", "synth", "Voxelizer", "PackedHostVolumes", "PackedHostVolumeList", "default_voxelizer", "pack_frames", "voxelize_device",
     "normalize_joints_device", "shard_range", "shard_packed", "DtsdfError",
     "LAYOUT_CXYZ", "LAYOUT_CZYX", "BBOX_PIXELS", "BBOX_EXTREMA", "BBOX_GRID",
 ]

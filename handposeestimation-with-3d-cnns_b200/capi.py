@@ -30,6 +30,7 @@ BBOX_GRID = 2
 OPT_PACKED_D2H = 1
 OPT_HOST_THREADS = 2
 OPT_CHUNK_MB = 3
+OPT_LITERAL_PUSH = 4
 OPT_TEST_FAIL_CHUNK = 100
 STAT_D2H_BYTES = 1
 JOINT_CLAMP01 = 1
@@ -96,6 +97,10 @@ _SIGNATURES = {
     "dtsdf_host_alloc": (ctypes.c_int, [ctypes.POINTER(_vp), _i64]),
     "dtsdf_host_free": (None, [_vp]),
     "dtsdf_voxelize_host": (ctypes.c_int, [_vp, _cfgp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dtsdf_voxelize_host_packed": (ctypes.c_int, [_vp, _cfgp, _i32, _vp, _i64, _vp, _vp, _vp, ctypes.POINTER(_vp), _vp, _vp]),
+    "dtsdf_expand_frames": (ctypes.c_int, [_vp, _i32, _i32, _vp, _i32]),
+    "dtsdf_packed_host_info": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_i64)]),
+    "dtsdf_packed_host_free": (None, [_vp]),
     "dtsdf_point_cloud_host": (ctypes.c_int, [_vp, ctypes.c_double, _vp, _vp, _vp, ctypes.POINTER(_i32)]),
     "dtsdf_resample_extrema_host": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp]),
     "dtsdf_process_begin_host": (ctypes.c_int, [_vp, ctypes.c_double, _i32, _vp, _i64, _vp, _vp, _vp]),

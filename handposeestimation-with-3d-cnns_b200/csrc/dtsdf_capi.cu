@@ -16,6 +16,7 @@
 #include <condition_variable>
 #include <deque>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <exception>
 #include <new>
@@ -213,14 +214,30 @@ struct Latch {
 
 }  // namespace
 
+// Volumes left packed in host memory by dtsdf_voxelize_host_packed: per pipeline chunk its code bytes,
+// literal offsets and literal stream exactly as they crossed PCIe (dtsdf_internal.h, compact container).
+struct dtsdf_packed_host {
+    int32_t n_frames = 0, voxel_res = 0, per_chunk = 1;
+    size_t r3 = 0;
+    struct Chunk {
+        int32_t f0 = 0, nf = 0;
+        std::unique_ptr<unsigned char[]> codes;          // [nf][r3/4]
+        std::unique_ptr<unsigned long long[]> loff;      // [nf+1]
+        std::unique_ptr<float[]> lits;                   // [3 * loff[nf]]
+    };
+    std::vector<Chunk> chunks;
+    std::atomic<long long> bytes{0};
+};
+
 struct dtsdf_ctx {
     int device = 0;
-    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr, s_lit = nullptr;
     static const int NSLOT = 4;                 // chunks in flight
     // packed device -> host transfer
     int opt_packed = 1;
     int opt_threads = 0;                        // 0 = hardware concurrency
     int opt_chunk_mb = 64;
+    int opt_push = 0;                           // literal stream by a push kernel instead of the copy engine
     int opt_fail_chunk = -1;                    // testing: the host pipeline fails before submitting this chunk
     Pool pool;
     DevBuf d_cnt[NSLOT], d_loff[NSLOT], d_codes[NSLOT], d_lits[NSLOT];
@@ -236,6 +253,7 @@ struct dtsdf_ctx {
         float* dst;                              // h_vol + f0 * vol_floats
         float* dst_maxl;                         // h_maxl + f0 or null
         float* dst_mid;                          // h_mid + 3 f0 or null
+        dtsdf_packed_host::Chunk* keep;          // packed result: the chunk's storage (the volumes are not expanded)
         double* dst_pc;                          // process mode: h_pc + f0 * point_num * 3 or null
         size_t pc_doubles;                       // point_num * 3
         long long fixed_bytes;                   // PCIe bytes of the chunk apart from the literal stream
@@ -245,7 +263,7 @@ struct dtsdf_ctx {
     MapBuf m_idx[NSLOT], m_pc[NSLOT];
     DevBuf p_idx[NSLOT], p_pc[NSLOT], p_ext[NSLOT];
     DevBuf d_vol[NSLOT], d_maxl[NSLOT], d_mid[NSLOT];
-    cudaEvent_t ev_in[NSLOT] = {}, ev_run[NSLOT] = {}, ev_out[NSLOT] = {};
+    cudaEvent_t ev_in[NSLOT] = {}, ev_run[NSLOT] = {}, ev_out[NSLOT] = {}, ev_meta[NSLOT] = {};
     // point-cloud path
     DevBuf d_points, d_idx, d_pc, d_ext, d_misc;
     int32_t last_n_valid = -1;
@@ -558,11 +576,13 @@ int dtsdf_ctx_create(int32_t device, dtsdf_ctx** out) {
     cudaError_t err = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_lit, cudaStreamNonBlocking);
     for (int i = 0; i < dtsdf_ctx::NSLOT && err == cudaSuccess; ++i) {
         err = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming);
         // the host waits on ev_run while its cores expand packed volumes: sleep, do not spin
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_run[i], cudaEventDisableTiming | cudaEventBlockingSync);
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_meta[i], cudaEventDisableTiming);
     }
     if (err != cudaSuccess) {
         dtsdf_ctx_destroy(c);
@@ -585,6 +605,7 @@ void dtsdf_ctx_destroy(dtsdf_ctx* c) {
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
         if (c->ev_run[i]) cudaEventDestroy(c->ev_run[i]);
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+        if (c->ev_meta[i]) cudaEventDestroy(c->ev_meta[i]);
     }
     c->d_points.release(); c->d_idx.release(); c->d_pc.release(); c->d_ext.release(); c->d_misc.release();
     c->d_j_in.release(); c->d_j_out.release(); c->d_j_ml.release(); c->d_j_mp.release();
@@ -594,6 +615,7 @@ void dtsdf_ctx_destroy(dtsdf_ctx* c) {
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_run) cudaStreamDestroy(c->s_run);
     if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->s_lit) cudaStreamDestroy(c->s_lit);
     cudaGetLastError();
     delete c;
 }
@@ -611,6 +633,9 @@ int dtsdf_ctx_set_option(dtsdf_ctx* c, int32_t option, int64_t value) {
         case DTSDF_OPT_CHUNK_MB:
             if (value < 1 || value > 4096) return DTSDF_ERR_INVALID_ARG;
             c->opt_chunk_mb = (int)value;
+            return DTSDF_OK;
+        case DTSDF_OPT_LITERAL_PUSH:
+            c->opt_push = value != 0;
             return DTSDF_OK;
         case DTSDF_OPT_TEST_FAIL_CHUNK:
             c->opt_fail_chunk = value < 0 ? -1 : (int)std::min<int64_t>(value, 1 << 30);
@@ -667,6 +692,14 @@ void run_expand_job(const ExpandJob& j) {
     const unsigned char* codes = (const unsigned char*)c->m_codes[r->slot].p;
     const unsigned long long* loff = (const unsigned long long*)c->m_loff[r->slot].p;
     const float* lits = (const float*)c->m_lits[r->slot].p;
+    if (r->keep) {                               // packed result: this job's share of the chunk, as it is
+        const size_t cb = r->r3 / 4;
+        memcpy(r->keep->codes.get() + (size_t)j.f0 * cb, codes + (size_t)j.f0 * cb, (size_t)(j.f1 - j.f0) * cb);
+        memcpy(r->keep->lits.get() + 3 * loff[j.f0], lits + 3 * loff[j.f0], (size_t)(loff[j.f1] - loff[j.f0]) * 12);
+        if (j.f0 == 0) memcpy(r->keep->loff.get(), loff, (size_t)(r->nf + 1) * 8);
+        c->latch[r->slot].done();
+        return;
+    }
     if (r->dst_pc && j.f1 > j.f0)               // the sampled clouds came back through pinned staging
         memcpy(r->dst_pc + (size_t)j.f0 * r->pc_doubles, (const double*)c->m_pc[r->slot].p + (size_t)j.f0 * r->pc_doubles,
                (size_t)(j.f1 - j.f0) * r->pc_doubles * 8);
@@ -742,30 +775,80 @@ struct HostPipeline {
     int fq_head = 0, fq_count = 0;
     bool qdone = false;
     std::atomic<bool> cancel{false};
+    std::atomic<bool> failed{false};           // the finalizer saw a CUDA failure (a chunk was dropped)
+    std::atomic<bool> no_memory{false};
+    dtsdf_packed_host* result = nullptr;       // dtsdf_voxelize_host_packed: the chunks stay packed, in here
     std::thread fin;
 
+    // Two stages per chunk, chunks in order, one thread:
+    //   A  codes, literal offsets, max_l / mid_p have landed (ev_meta): the host now knows how many literals
+    //      the chunk holds and issues ONE copy-engine transfer of exactly that many bytes on s_lit (a kernel
+    //      pushing the device-sized stream into mapped memory with SM stores ran at 20-24 GB/s and was the
+    //      longest item on the device side; the copy engine moves it at PCIe speed, and with four chunks in
+    //      flight the host round trip in between costs nothing);
+    //   B  the literals have landed (ev_run): hand the chunk to the expansion threads.
     void finalizer() {
         cudaSetDevice(c->device);
+        constexpr int QN = dtsdf_ctx::NSLOT * 2;
+        int qa[QN], qb[QN], a_head = 0, a_n = 0, b_head = 0, b_n = 0;
+        int spins = 0;
         for (;;) {
-            int slot;
             {
                 std::unique_lock<std::mutex> lk(qm);
-                qcv.wait(lk, [&] { return fq_count > 0 || qdone; });
-                if (fq_count == 0) return;
-                slot = fq[fq_head];
-                fq_head = (fq_head + 1) % (dtsdf_ctx::NSLOT * 2);
-                --fq_count;
+                if (a_n == 0 && b_n == 0) qcv.wait(lk, [&] { return fq_count > 0 || qdone; });
+                while (fq_count > 0) {
+                    qa[(a_head + a_n++) % QN] = fq[fq_head];
+                    fq_head = (fq_head + 1) % QN;
+                    --fq_count;
+                }
+                if (a_n == 0 && b_n == 0 && qdone) return;
             }
-            cudaError_t e = cudaSuccess;
-            int spins = 0;               // spin briefly, then yield: the ranks of a node share its cores
-            while (!cancel.load(std::memory_order_relaxed) &&
-                   (e = cudaEventQuery(c->ev_run[slot])) == cudaErrorNotReady) {
-                if (++spins < 64) _mm_pause();
-                else std::this_thread::yield();
+            bool progress = false;
+            const bool dead = cancel.load(std::memory_order_relaxed);
+            if (a_n > 0) {
+                const int slot = qa[a_head];
+                const cudaError_t e = dead ? cudaErrorUnknown : cudaEventQuery(c->ev_meta[slot]);
+                if (e != cudaErrorNotReady) {
+                    a_head = (a_head + 1) % QN; --a_n; progress = true;
+                    bool ok = e == cudaSuccess;
+                    if (ok && c->chunk[slot].keep) {
+                        const dtsdf_ctx::ChunkRecord& r = c->chunk[slot];
+                        const unsigned long long total = ((const unsigned long long*)c->m_loff[slot].p)[r.nf];
+                        try {
+                            r.keep->codes.reset(new unsigned char[(size_t)r.nf * (r.r3 / 4)]);
+                            r.keep->loff.reset(new unsigned long long[(size_t)r.nf + 1]);
+                            r.keep->lits.reset(new float[3 * (size_t)total + 4]);
+                            result->bytes += (long long)r.nf * (long long)(r.r3 / 4) + 8ll * (r.nf + 1) + 12ll * (long long)total;
+                        } catch (...) {
+                            ok = false;
+                            no_memory.store(true);
+                        }
+                    }
+                    if (ok && !c->opt_push) {
+                        const dtsdf_ctx::ChunkRecord& r = c->chunk[slot];
+                        const unsigned long long total = ((const unsigned long long*)c->m_loff[slot].p)[r.nf];
+                        if (total > 0)
+                            ok = cudaMemcpyAsync(c->m_lits[slot].p, c->d_lits[slot].p, (size_t)total * 12, cudaMemcpyDeviceToHost,
+                                                 c->s_lit) == cudaSuccess;
+                        ok = ok && cudaEventRecord(c->ev_run[slot], c->s_lit) == cudaSuccess;
+                    }
+                    // a failed stream or a cancelled call: nothing of this chunk reaches the caller's buffers
+                    if (!ok) { cudaGetLastError(); failed.store(true); c->latch[slot].reset(); }
+                    else qb[(b_head + b_n++) % QN] = slot;
+                }
             }
-            // a failed stream or a cancelled call: nothing of this chunk reaches the caller's buffers
-            if (e != cudaSuccess || cancel.load()) { cudaGetLastError(); c->latch[slot].reset(); continue; }
-            expand_chunk(&c->chunk[slot]);
+            if (b_n > 0) {
+                const int slot = qb[b_head];
+                const cudaError_t e = dead ? cudaErrorUnknown : (c->opt_push ? cudaSuccess : cudaEventQuery(c->ev_run[slot]));
+                if (e != cudaErrorNotReady) {
+                    b_head = (b_head + 1) % QN; --b_n; progress = true;
+                    if (e != cudaSuccess) { cudaGetLastError(); failed.store(true); c->latch[slot].reset(); }
+                    else expand_chunk(&c->chunk[slot]);
+                }
+            }
+            if (progress) spins = 0;
+            else if (++spins < 64) _mm_pause();      // spin briefly, then yield: the ranks of a node share its cores
+            else std::this_thread::yield();
         }
     }
     void enqueue_for_finalizer(int slot) {
@@ -894,8 +977,9 @@ int HostPipeline::submit_chunks() {
                                   (unsigned char*)c->d_codes[slot].p, (float*)c->d_lits[slot].p, c->s_run));
             CK(cudaEventRecord(c->ev_out[slot], c->s_run));          // packed mode: "chunk packed"
             CK(cudaStreamWaitEvent(c->s_out, c->ev_out[slot], 0));
-            CK(dtsdf::launch_pack_push(nf, (const float*)c->d_lits[slot].p,
-                                       (const unsigned long long*)c->d_loff[slot].p, (float*)dv_lits, c->s_out));
+            if (c->opt_push)
+                CK(dtsdf::launch_pack_push(nf, (const float*)c->d_lits[slot].p,
+                                           (const unsigned long long*)c->d_loff[slot].p, (float*)dv_lits, c->s_out));
             CK(cudaMemcpyAsync(c->m_codes[slot].p, c->d_codes[slot].p, (size_t)nf * (r3 / 4), cudaMemcpyDeviceToHost, c->s_out));
             CK(cudaMemcpyAsync(c->m_loff[slot].p, c->d_loff[slot].p, (size_t)(nf + 1) * 8, cudaMemcpyDeviceToHost, c->s_out));
             if (h_maxl)
@@ -907,14 +991,16 @@ int HostPipeline::submit_chunks() {
             // behind the copies: an event for the finalizer thread
             dtsdf_ctx::ChunkRecord& r = c->chunk[slot];
             r.ctx = c; r.slot = slot; r.jobs = std::min<int>(nf, nthreads); r.nf = nf;
-            r.r3 = r3; r.vol_floats = vol_floats; r.dst = h_vol + (size_t)f0 * vol_floats;
+            r.r3 = r3; r.vol_floats = vol_floats; r.dst = h_vol ? h_vol + (size_t)f0 * vol_floats : nullptr;
             r.dst_maxl = h_maxl ? h_maxl + f0 : nullptr;
             r.dst_mid = h_mid ? h_mid + 3 * (size_t)f0 : nullptr;
+            r.keep = result ? &result->chunks[(size_t)k] : nullptr;
+            if (r.keep) { r.keep->f0 = f0; r.keep->nf = nf; }
             r.pc_doubles = (size_t)point_num * 3;
             r.dst_pc = (process_mode && h_pc) ? h_pc + (size_t)f0 * r.pc_doubles : nullptr;
             r.fixed_bytes = (long long)nf * (long long)(r3 / 4) + (long long)(nf + 1) * 8 +
                             (h_maxl ? 4ll * nf : 0ll) + (h_mid ? 12ll * nf : 0ll) + (r.dst_pc ? 24ll * nf * point_num : 0ll);
-            CK(cudaEventRecord(c->ev_run[slot], c->s_out));
+            CK(cudaEventRecord(c->ev_meta[slot], c->s_out));
             c->latch[slot].add(r.jobs);
             enqueue_for_finalizer(slot);
             continue;
@@ -951,7 +1037,13 @@ void HostPipeline::configure() {
     // plain copies even when the packed transfer is on: its extra kernels, stream hand-offs and
     // thread wake-ups cost more than they save below ~32 frames (one frame: 350 us packed, 110 us
     // plain; 64 frames: 26 us per frame packed, 33 us plain).
-    packed = c->opt_packed != 0 && (size_t)n_frames * vol_floats * 4 >= ((size_t)16 << 20);
+    packed = result != nullptr || (c->opt_packed != 0 && (size_t)n_frames * vol_floats * 4 >= ((size_t)16 << 20));
+    if (result) {
+        result->n_frames = n_frames; result->voxel_res = (int32_t)R; result->r3 = r3; result->per_chunk = per_chunk;
+        result->chunks.clear();
+        result->chunks.resize((size_t)nchunk);
+        result->bytes = 0;
+    }
     // A single plain chunk needs no pipeline: everything on one stream, one synchronisation.
     single = !packed && nchunk == 1;
     c->stat_d2h_bytes = packed ? 0ll
@@ -982,7 +1074,12 @@ int HostPipeline::run() {
     // ---- the one exit path
     if (rc != DTSDF_OK) cancel.store(true);
     stop_finalizer();
+    if (rc == DTSDF_OK && failed.load()) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "a device -> host transfer of the host pipeline failed");
+        rc = no_memory.load() ? DTSDF_ERR_ALLOC : DTSDF_ERR_CUDA;
+    }
     for (int i = 0; i < dtsdf_ctx::NSLOT; ++i) c->latch[i].wait();         // expansion jobs that did start
+    if (packed) { cudaStreamSynchronize(c->s_lit); cudaGetLastError(); }
     cudaError_t e_out = single ? cudaSuccess : cudaStreamSynchronize(c->s_out);
     cudaError_t e_run = cudaStreamSynchronize(c->s_run);
     cudaError_t e_in = single ? cudaSuccess : cudaStreamSynchronize(c->s_in);
@@ -997,16 +1094,16 @@ int HostPipeline::run() {
 
 extern "C" {
 
-int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
-                        const float* h_depth, int64_t packed_len, const int64_t* h_off,
-                        const int32_t* h_hdr, const float* h_aux, float* h_vol, float* h_maxl,
-                        float* h_mid) {
+static int voxelize_host_common(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
+                                const float* h_depth, int64_t packed_len, const int64_t* h_off,
+                                const int32_t* h_hdr, const float* h_aux, float* h_vol, float* h_maxl,
+                                float* h_mid, dtsdf_packed_host* result) {
     if (!c) return DTSDF_ERR_INVALID_ARG;
     int rc = check_cfg(cfg);
     if (rc != DTSDF_OK) return rc;
     if (n_frames < 0 || packed_len < 0) return DTSDF_ERR_INVALID_ARG;
     if (n_frames == 0) return DTSDF_OK;
-    if (!h_depth || !h_off || !h_hdr || !h_vol) return DTSDF_ERR_INVALID_ARG;
+    if (!h_depth || !h_off || !h_hdr || (!h_vol && !result)) return DTSDF_ERR_INVALID_ARG;
     if (cfg->bbox_mode != DTSDF_BBOX_PIXELS && !h_aux) return DTSDF_ERR_INVALID_ARG;
     // validate headers / offsets on the host (the per-frame shims raise on these)
     for (int32_t i = 0; i < n_frames; ++i) {
@@ -1023,8 +1120,76 @@ int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
         p.c = c; p.cfg = cfg; p.n_frames = n_frames; p.h_depth = h_depth; p.h_off = h_off; p.h_hdr = h_hdr;
         p.h_aux = h_aux; p.h_vol = h_vol; p.h_maxl = h_maxl; p.h_mid = h_mid;
         p.aux_w = cfg->bbox_mode == DTSDF_BBOX_EXTREMA ? 6 : (cfg->bbox_mode == DTSDF_BBOX_GRID ? 5 : 0);
+        p.result = result;
         p.configure();
         return p.run();
+    });
+}
+
+int dtsdf_voxelize_host(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
+                        const float* h_depth, int64_t packed_len, const int64_t* h_off,
+                        const int32_t* h_hdr, const float* h_aux, float* h_vol, float* h_maxl,
+                        float* h_mid) {
+    if (n_frames > 0 && !h_vol) return DTSDF_ERR_INVALID_ARG;
+    return voxelize_host_common(c, cfg, n_frames, h_depth, packed_len, h_off, h_hdr, h_aux, h_vol, h_maxl, h_mid, nullptr);
+}
+
+int dtsdf_voxelize_host_packed(dtsdf_ctx* c, const dtsdf_config* cfg, int32_t n_frames,
+                               const float* h_depth, int64_t packed_len, const int64_t* h_off,
+                               const int32_t* h_hdr, const float* h_aux, dtsdf_packed_host** out,
+                               float* h_maxl, float* h_mid) {
+    if (!out) return DTSDF_ERR_INVALID_ARG;
+    *out = nullptr;
+    dtsdf_packed_host* h = new (std::nothrow) dtsdf_packed_host();
+    if (!h) return DTSDF_ERR_ALLOC;
+    if (cfg) { h->voxel_res = cfg->voxel_res; h->r3 = (size_t)cfg->voxel_res * cfg->voxel_res * cfg->voxel_res; }
+    const int rc = voxelize_host_common(c, cfg, n_frames, h_depth, packed_len, h_off, h_hdr, h_aux, nullptr, h_maxl, h_mid, h);
+    if (rc != DTSDF_OK) { delete h; return rc; }
+    *out = h;
+    return DTSDF_OK;
+}
+
+void dtsdf_packed_host_free(dtsdf_packed_host* h) { delete h; }
+
+int dtsdf_packed_host_info(const dtsdf_packed_host* h, int32_t* n_frames, int32_t* voxel_res, int64_t* bytes) {
+    if (!h) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames) *n_frames = h->n_frames;
+    if (voxel_res) *voxel_res = h->voxel_res;
+    if (bytes) *bytes = (int64_t)h->bytes.load();
+    return DTSDF_OK;
+}
+
+int dtsdf_expand_frames(const dtsdf_packed_host* h, int32_t first, int32_t count, float* h_out, int32_t n_threads) {
+    if (!h || first < 0 || count < 0 || (int64_t)first + count > h->n_frames) return DTSDF_ERR_INVALID_ARG;
+    if (count == 0) return DTSDF_OK;
+    if (!h_out) return DTSDF_ERR_INVALID_ARG;
+    const size_t r3 = h->r3, vol_floats = 3 * r3;
+    auto expand = [=](int32_t a, int32_t b) {
+        for (int32_t f = a; f < b; ++f) {
+            const dtsdf_packed_host::Chunk& ch = h->chunks[(size_t)(f / h->per_chunk)];
+            const int32_t i = f - ch.f0;
+            dtsdf::decode_frame(ch.codes.get() + (size_t)i * (r3 / 4), ch.lits.get() + 3 * ch.loff[i],
+                                (size_t)(ch.loff[i + 1] - ch.loff[i]), r3, h_out + (size_t)(f - first) * vol_floats);
+        }
+    };
+    int nt = n_threads > 0 ? n_threads : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    nt = std::min<int>(nt, (count + 3) / 4);              // a thread is not worth fewer than four frames
+    if (nt <= 1) { expand(first, first + count); return DTSDF_OK; }
+    return guarded([&]() -> int {
+        std::vector<std::thread> th;
+        th.reserve((size_t)nt);
+        int started = 0;
+        try {
+            for (; started < nt - 1; ++started) {
+                const int32_t a = first + (int32_t)((int64_t)count * started / nt), b = first + (int32_t)((int64_t)count * (started + 1) / nt);
+                th.emplace_back(expand, a, b);
+            }
+        } catch (...) {
+            // no more threads to be had: this one does the rest
+        }
+        expand(first + (int32_t)((int64_t)count * started / nt), first + count);
+        for (auto& t : th) t.join();
+        return DTSDF_OK;
     });
 }
 

@@ -17,15 +17,55 @@ reference's sampled cloud bit for bit.
 Differences, all deliberate:
   * the volume is returned as float32 ``[3,32,32,32]`` (c,x,y,z); the reference returns the
     same values in a float64 array (every value it stores is a float32 scalar);
-  * ``aug=True`` raises NotImplementedError: the reference's ``data_aug`` itself raises
-    ``AxisError`` (pre/process.py:252, ``np.mean(..., axis=2)`` on a 2-D cloud), so there is
-    no behaviour to reproduce.
+  * ``process()`` with ``aug=True`` raises NotImplementedError: the original's ``data_aug(pc)``
+    itself raises ``AxisError`` (pre/process.py:252, ``np.mean(..., axis=2)`` on a 2-D cloud), so
+    there is no behaviour to reproduce.  The later fork's ``data_aug(joints, point_clouds)``
+    (cut_version/pre/process.py:69-134) does run and is reproduced bit for bit.
 """
 import numpy as np
 
 from _bind import package
 
 _pkg = package()
+
+
+def draw_aug():
+    """The five random parameters of the fork's ``data_aug`` from the global ``np.random`` stream, in its
+    order (cut_version/pre/process.py:76-94): stretch x, stretch y ~ U[2/3, 3/2), then whole degrees about
+    x and y from [-10, 10) and about z from [-30, 30)."""
+    sx, sy = np.random.uniform(2 / 3, 3 / 2), np.random.uniform(2 / 3, 3 / 2)
+    return sx, sy, np.random.randint(-10, 10), np.random.randint(-10, 10), np.random.randint(-30, 30)
+
+
+def _plane_rotation(i, j, c, s):
+    """3x3 identity with [[c, s], [-s, c]] in rows/columns (i, j)."""
+    m = np.eye(3)
+    m[i, i], m[i, j], m[j, i], m[j, j] = c, s, -s, c
+    return m
+
+
+def apply_aug(params, joints, point_clouds):
+    """The arithmetic of the fork's ``data_aug`` (cut_version/pre/process.py:79-134) for drawn parameters:
+    ``S = diag(sx, sy, 1)``; ``R = Rx . Ry . Rz`` with the x and y angles converted to radians and the z
+    angle NOT (``np.cos(rot_z)`` of a number of degrees, :95-96); every row ``p`` becomes
+    ``(p . S) . R + mean(p . S)`` - the "centre" that is added back is the mean of the row's own three
+    stretched coordinates (``np.mean(.., axis=1)``, :110,125), and it was never subtracted (:116,129 rotate the
+    un-centred array).  float64 throughout, the fork's np.dot calls on the fork's shapes."""
+    sx, sy, rot_x, rot_y, rot_z = params
+    S = np.diag(np.array([sx, sy, 1]))
+    ax, ay = np.pi * rot_x / 180, np.pi * rot_y / 180
+    R_x = _plane_rotation(1, 2, np.cos(ax), np.sin(ax))
+    R_y = _plane_rotation(2, 0, np.cos(ay), np.sin(ay))
+    R_z = _plane_rotation(0, 1, np.cos(rot_z), np.sin(rot_z))
+    R = np.dot(np.dot(R_x, R_y), R_z)
+    joints = np.asarray(joints)
+    if len(joints.shape) != 2:
+        joints = joints.reshape(21, 3)
+
+    def moved(rows):
+        stretched = np.dot(rows, S)
+        return np.dot(stretched, R) + np.mean(stretched, axis=1)[:, None]
+    return moved(point_clouds), moved(joints)
 
 
 class DataProcess(object):
@@ -108,13 +148,27 @@ class DataProcess(object):
             [self.data], layout=_pkg.LAYOUT_CXYZ, bbox_mode=_pkg.BBOX_GRID, aux=aux)
         return vol[0]
 
-    # ------------------------------------------------------------------ pre/process.py:202-261
+    # ------------------------------------------------------------------ pre/process.py:202-261,
+    #                                                                    cut_version/pre/process.py:69-134
     def data_aug(self, *args):
+        """``data_aug(joints, point_clouds)`` - the later fork's augmentation, the one variant of the
+        reference that runs (cut_version/pre/process.py:69-134): returns ``(point_clouds_aug, ground_truth_aug)``
+        in float64 with the fork's own NumPy calls in the fork's order, quirks included (see ``draw_aug`` /
+        ``apply_aug``), so a seeded run reproduces it bit for bit.  It is host float64 linear algebra on a
+        6000 x 3 cloud; the D-TSDF of the augmented cloud is then ``tsdf_f(point_clouds_aug)`` - the fused
+        kernel with the bounding box of the augmented points over the UN-augmented depth map, as the fork
+        does (its own note at :207).
+
+        ``data_aug(point_clouds)`` - the original's signature (pre/process.py:202): that implementation
+        raises ``AxisError`` (:252, ``np.mean(..., axis=2)`` of a 2-D array) before returning anything, so
+        there is no behaviour to reproduce: NotImplementedError."""
+        if len(args) == 2:
+            joints, point_clouds = args
+            return apply_aug(draw_aug(), joints, point_clouds)
         raise NotImplementedError(
-            "data_aug: the reference implementation raises AxisError (pre/process.py:252) and the "
-            "cut_version variant voxelises the un-augmented depth map "
-            "(cut_version/pre/process.py:207); augmentation is specified separately "
-            "(SURVEY.md section 8f, N2)")
+            "data_aug(point_clouds): the reference implementation raises AxisError (pre/process.py:252); "
+            "the fork's data_aug(joints, point_clouds) (cut_version/pre/process.py:69) is implemented, and a "
+            "consistent on-device augmentation is specified separately (SURVEY.md section 8f, N2)")
 
     # ------------------------------------------------------------------ cut_version/pre/process.py:251-263
     def normalize(self, ground_truth, max_l, mid_p):

@@ -166,6 +166,29 @@ class Voxelizer:
             capi._ptr(out_mid_p)))
         return out_vol, out_max_l, out_mid_p
 
+    @_serialised
+    def voxelize_packed_lazy(self, headers, offsets, packed, layout=LAYOUT_CXYZ, bbox_mode=BBOX_PIXELS,
+                             aux=None, voxel_res=None):
+        """``dtsdf_voxelize_host_packed``: like ``voxelize_packed`` but the volumes stay packed in host memory
+        (``PackedHostVolumes``, expanded on demand).  Returns (packed_volumes, max_l, mid_p)."""
+        R = int(voxel_res or self.voxel_res)
+        headers = np.ascontiguousarray(headers, dtype=np.int32).reshape(-1, 6)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = headers.shape[0]
+        assert packed.dtype == np.float32 and packed.flags["C_CONTIGUOUS"]
+        out_max_l = np.empty(n, dtype=np.float32)
+        out_mid_p = np.empty((n, 3), dtype=np.float32)
+        if aux is not None:
+            aux = np.ascontiguousarray(aux, dtype=np.float32)
+        cfg = self.config(layout, bbox_mode, R)
+        handle = ctypes.c_void_p()
+        check(self._lib.dtsdf_voxelize_host_packed(
+            self._ctx, ctypes.byref(cfg), n, capi._ptr(packed), int(packed.size), capi._ptr(offsets),
+            capi._ptr(headers), capi._ptr(aux), ctypes.byref(handle), capi._ptr(out_max_l), capi._ptr(out_mid_p)))
+        if not handle.value:                       # n == 0
+            return None, out_max_l, out_mid_p
+        return PackedHostVolumes(handle, self._lib), out_max_l, out_mid_p
+
     def voxelize_frames(self, frames, layout=LAYOUT_CXYZ, bbox_mode=BBOX_PIXELS, aux=None, voxel_res=None):
         """Frame records -> (vol float32[n,3,R,R,R], max_l float32[n], mid_p float32[n,3])."""
         headers, offsets, packed, _ = pack_frames(frames)
@@ -247,28 +270,48 @@ class Voxelizer:
                 capi._ptr(vol), capi._ptr(max_l), capi._ptr(mid_p)))
         return pcs, vol, max_l, mid_p
 
-    @_serialised
     def process_frames_two_calls(self, frames, point_num=6000, want_points=True, layout=LAYOUT_CXYZ, voxel_res=None):
         """The same result through ``dtsdf_process_begin_host`` / ``dtsdf_process_finish_host`` with the index
         vectors drawn HERE by ``np.random.randint``, one call per frame as the reference does
         (pre/process.py:75-80): the form that depends on nothing but NumPy's public API (``process_packed``
         is checked against it)."""
-        R = int(voxel_res or self.voxel_res)
         point_num = int(point_num)
+        with self._lock:
+            n_valid = self.process_begin(frames)
+            n = n_valid.size
+            idx = np.empty((n, point_num), dtype=np.int32)
+            for i in range(n):
+                point_shape = int(n_valid[i])
+                if point_shape < point_num:
+                    idx[i] = np.arange(0, point_num, 1, dtype=np.int32)
+                    idx[i, point_shape:] = np.random.randint(0, point_shape, size=point_num - point_shape)
+                else:
+                    idx[i] = np.random.randint(0, point_shape, size=point_num)
+            return self.process_finish(idx, point_num, want_points, layout, voxel_res)
+
+    @_serialised
+    def process_begin(self, frames):
+        """``dtsdf_process_begin_host``: uploads the frames, back-projects and compacts every point cloud
+        (pre/process.py:30-68; crops and clouds stay resident in the context until ``process_finish``) and
+        returns the number of points per frame, int32[n] - what the caller needs to draw the resampling
+        indices from its own random stream."""
         headers, offsets, packed, _ = pack_frames(frames)
         n = headers.shape[0]
         n_valid = np.zeros(n, dtype=np.int32)
         check(self._lib.dtsdf_process_begin_host(self._ctx, ctypes.c_double(self.focal), n, capi._ptr(packed),
                                                  int(packed.size), capi._ptr(offsets), capi._ptr(headers),
                                                  capi._ptr(n_valid)))
-        idx = np.empty((n, point_num), dtype=np.int32)
-        for i in range(n):
-            point_shape = int(n_valid[i])
-            if point_shape < point_num:
-                idx[i] = np.arange(0, point_num, 1, dtype=np.int32)
-                idx[i, point_shape:] = np.random.randint(0, point_shape, size=point_num - point_shape)
-            else:
-                idx[i] = np.random.randint(0, point_shape, size=point_num)
+        return n_valid
+
+    @_serialised
+    def process_finish(self, indices, point_num=6000, want_points=True, layout=LAYOUT_CXYZ, voxel_res=None):
+        """``dtsdf_process_finish_host`` on the frames of the last ``process_begin``: gather by ``indices``
+        int32[n, point_num] (pre/process.py:82), extrema (:102-120), voxel loop.  No other call on this
+        Voxelizer may come in between.  Returns ``(point_clouds or None, tsdf, max_l, mid_p)``."""
+        R = int(voxel_res or self.voxel_res)
+        point_num = int(point_num)
+        idx = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, point_num)
+        n = idx.shape[0]
         pcs = np.empty((n, point_num, 3), dtype=np.float64) if want_points else None
         vol = np.empty((n, 3, R, R, R), dtype=np.float32)
         max_l = np.empty(n, dtype=np.float32)
@@ -289,6 +332,112 @@ class Voxelizer:
         out = np.empty_like(j)
         check(self._lib.dtsdf_normalize_joints_host(self._ctx, n, capi._ptr(j), capi._ptr(ml), capi._ptr(mp),
                                                     1 if clamp01 else 0, capi._ptr(out)))
+        return out
+
+
+class PackedHostVolumes:
+    """Volumes left packed in host memory by ``Voxelizer.voxelize_packed_lazy`` (``dtsdf_voxelize_host_packed``):
+    ~47 KB per volume instead of 393 KB.  Sequence-like: ``len(p)``, ``p[i]`` -> float32[3,R,R,R], ``p[a:b]`` and
+    ``p[index array]`` -> float32[k,3,R,R,R], expanded on demand by ``dtsdf_expand_frames``; ``shape`` and
+    ``dtype`` as the dense array would have them, so a ``torch.utils.data.Dataset`` can hold it where it held
+    the dense array (3D_CNN/dataset.py:35,73-79)."""
+
+    dtype = np.dtype(np.float32)
+
+    def __init__(self, handle, lib):
+        self._h, self._lib = handle, lib
+        n, r, b = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int64(0)
+        check(lib.dtsdf_packed_host_info(handle, ctypes.byref(n), ctypes.byref(r), ctypes.byref(b)))
+        self.n_frames, self.voxel_res, self.nbytes = int(n.value), int(r.value), int(b.value)
+
+    @property
+    def shape(self):
+        R = self.voxel_res
+        return (self.n_frames, 3, R, R, R)
+
+    def __len__(self):
+        return self.n_frames
+
+    def expand(self, first=0, count=None, out=None, threads=0):
+        """Frames [first, first+count) as float32[count,3,R,R,R] (into ``out`` if given)."""
+        count = self.n_frames - first if count is None else int(count)
+        R = self.voxel_res
+        if out is None:
+            out = np.empty((count, 3, R, R, R), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"] and out.size == count * 3 * R ** 3
+        check(self._lib.dtsdf_expand_frames(self._h, int(first), count, capi._ptr(out), int(threads)))
+        return out
+
+    def __getitem__(self, index):
+        if isinstance(index, (int, np.integer)):
+            i = int(index)
+            if i < 0:
+                i += self.n_frames
+            if not 0 <= i < self.n_frames:
+                raise IndexError(index)
+            return self.expand(i, 1, threads=1)[0]
+        if isinstance(index, slice):
+            a, b, st = index.indices(self.n_frames)
+            if st == 1:
+                return self.expand(a, max(b - a, 0))
+            index = np.arange(a, b, st)
+        idx = np.asarray(index).reshape(-1)
+        R = self.voxel_res
+        out = np.empty((idx.size, 3, R, R, R), dtype=np.float32)
+        for k, i in enumerate(idx):
+            self.expand(int(i) % self.n_frames if i < 0 else int(i), 1, out=out[k:k + 1], threads=1)
+        return out
+
+    def close(self):
+        if self._h is not None:
+            self._lib.dtsdf_packed_host_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PackedHostVolumeList:
+    """Several ``PackedHostVolumes`` (e.g. one per gesture) behind one index space."""
+
+    dtype = np.dtype(np.float32)
+
+    def __init__(self, parts):
+        self.parts = list(parts)
+        self.starts = np.concatenate([[0], np.cumsum([len(p) for p in self.parts])]).astype(np.int64)
+        self.voxel_res = self.parts[0].voxel_res if self.parts else 32
+        self.nbytes = sum(p.nbytes for p in self.parts)
+
+    @property
+    def shape(self):
+        R = self.voxel_res
+        return (int(self.starts[-1]), 3, R, R, R)
+
+    def __len__(self):
+        return int(self.starts[-1])
+
+    def _one(self, i):
+        i = int(i)
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        k = int(np.searchsorted(self.starts, i, side="right")) - 1
+        return self.parts[k][i - int(self.starts[k])]
+
+    def __getitem__(self, index):
+        if isinstance(index, (int, np.integer)):
+            return self._one(index)
+        if isinstance(index, slice):
+            index = np.arange(*index.indices(len(self)))
+        idx = np.asarray(index).reshape(-1)
+        R = self.voxel_res
+        out = np.empty((idx.size, 3, R, R, R), dtype=np.float32)
+        for k, i in enumerate(idx):
+            out[k] = self._one(i)
         return out
 
 

@@ -258,6 +258,9 @@ void dtsdf_ctx_destroy(dtsdf_ctx* ctx);
 #define DTSDF_OPT_PACKED_D2H   1
 #define DTSDF_OPT_HOST_THREADS 2
 #define DTSDF_OPT_CHUNK_MB     3   /* output megabytes per pipeline chunk of dtsdf_voxelize_host (default 64) */
+#define DTSDF_OPT_LITERAL_PUSH 4   /* packed transfer: 0 (default) the literal stream of a chunk comes back with one copy-engine
+                                      transfer issued once the host knows its size; 1: pushed into mapped pinned
+                                      memory by a kernel (no host round trip, SM stores over PCIe) */
 #define DTSDF_OPT_TEST_FAIL_CHUNK 100 /* testing only: dtsdf_voxelize_host fails with DTSDF_ERR_CUDA when it reaches
                                          chunk `value`, with the chunks before it in flight (-1, the default: off) */
 int dtsdf_ctx_set_option(dtsdf_ctx* ctx, int32_t option, int64_t value);
@@ -281,6 +284,25 @@ int dtsdf_voxelize_host(dtsdf_ctx* ctx, const dtsdf_config* cfg, int32_t n_frame
                         const int64_t* h_crop_offsets, const int32_t* h_headers,
                         const float* h_aux,
                         float* h_out_vol, float* h_out_max_l, float* h_out_mid_p);
+
+/* dtsdf_voxelize_host that leaves the volumes PACKED in host memory (the lossless form in which they cross
+ * PCIe: 2-bit codes + literals, ~47 KB instead of 393 KB per volume at R = 32) behind an opaque handle, for
+ * callers that do not need every volume dense at once - a data set that expands the samples of a batch on
+ * demand (3D_CNN/dataset.py:35 keeps [N,3,32,32,32] float32 = 30 GB for the full MSRA set in host memory; the
+ * packed set is 3.6 GB), or a writer that converts gesture by gesture (pre/read_MSRA.py:119-126).
+ *   dtsdf_expand_frames   frames [first, first+count) of the handle -> float[count][3][R][R][R] in the layout
+ *                         the volumes were made in; n_threads host threads (0 = default, at most 8)
+ *   dtsdf_packed_host_info / _free   size of the handle, release */
+typedef struct dtsdf_packed_host dtsdf_packed_host;
+int  dtsdf_voxelize_host_packed(dtsdf_ctx* ctx, const dtsdf_config* cfg, int32_t n_frames,
+                                const float* h_depth_packed, int64_t packed_len,
+                                const int64_t* h_crop_offsets, const int32_t* h_headers,
+                                const float* h_aux, dtsdf_packed_host** out,
+                                float* h_out_max_l, float* h_out_mid_p);
+int  dtsdf_expand_frames(const dtsdf_packed_host* packed, int32_t first, int32_t count, float* h_out,
+                         int32_t n_threads);
+int  dtsdf_packed_host_info(const dtsdf_packed_host* packed, int32_t* n_frames, int32_t* voxel_res, int64_t* bytes);
+void dtsdf_packed_host_free(dtsdf_packed_host* packed);
 
 /* DataProcess.point_cloud for one frame (pre/process.py:30-68).  The compacted
  * cloud also stays resident in the context for dtsdf_resample_extrema_host.

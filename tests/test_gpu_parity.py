@@ -353,6 +353,34 @@ def test_host_pipeline_many_small_chunks_and_destination_alignments():
     v.close()
 
 
+def test_packed_host_result_expands_to_the_dense_result():
+    """dtsdf_voxelize_host_packed + dtsdf_expand_frames: the volumes stay packed in host memory and any frame
+    range expands to exactly what dtsdf_voxelize_host returns; small batches, several chunks, every
+    resolution, both literal transfer routes (copy engine / push kernel)."""
+    frames = synth.make_frames(range(4100, 4100 + 260))
+    headers, offsets, packed = pack_simple(frames)
+    v = pkg.Voxelizer(device=0)
+    for R, n, chunk_mb, push in ((32, 260, 8, 0), (32, 260, 64, 1), (32, 3, 64, 0), (48, 40, 16, 0), (64, 20, 64, 0)):
+        v.set_option(pkg.capi.OPT_CHUNK_MB, chunk_mb)
+        v.set_option(pkg.capi.OPT_LITERAL_PUSH, push)
+        want, wml, wmp = v.voxelize_packed(headers[:n], offsets[:n], packed, voxel_res=R)
+        lazy, ml, mp = v.voxelize_packed_lazy(headers[:n], offsets[:n], packed, voxel_res=R)
+        assert len(lazy) == n and lazy.shape == want.shape and lazy.nbytes < want.nbytes / 4
+        assert np.array_equal(ml, wml) and np.array_equal(mp, wmp)
+        assert _same(lazy.expand(), want)
+        assert _same(lazy.expand(threads=3), want)
+        a, b = n // 3, n // 3 + min(7, n - n // 3)
+        assert _same(lazy[a:b], want[a:b]) and _same(lazy[n - 1], want[n - 1]) and _same(lazy[-1], want[-1])
+        assert _same(lazy[np.array([0, n - 1, n // 2])], want[[0, n - 1, n // 2]])
+        with pytest.raises(pkg.DtsdfError):
+            lazy.expand(n - 1, 2)
+        lazy.close()
+    v.set_option(pkg.capi.OPT_LITERAL_PUSH, 1)                    # the push route of the dense result, too
+    v.set_option(pkg.capi.OPT_CHUNK_MB, 8)
+    assert _same(v.voxelize_packed(headers, offsets, packed)[0], c_oracle.dtsdf_batch(headers, offsets, packed)[0])
+    v.close()
+
+
 def test_host_pipeline_failure_leaves_no_writer_behind():
     """A failure in the middle of the chunk loop (injected: DTSDF_OPT_TEST_FAIL_CHUNK) with earlier chunks in
     flight: the call returns the error only after every copy and expansion thread is done or cancelled -

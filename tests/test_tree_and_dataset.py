@@ -162,12 +162,12 @@ def test_read_msra_main_writes_the_reference_tree(golden, tmp_path):
             assert np.array_equal(np.load(os.path.join(res, sub, "ground_truth", "%s.npy" % ges)), golden[k + "gt"])
             assert np.array_equal(np.load(os.path.join(res, sub, "num", "%s.npy" % ges)), golden[k + "num"])
     read_MSRA.AUG = True
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):        # the original's tree with AUG: the original raises too
         read_MSRA.main()
     read_MSRA.AUG = False
 
-    # the later fork's tree (cut_version/pre/read_MSRA.py:60-113): same volumes, ground truth [n,21,3],
-    # joint_nor/<ges>.npy in float64, no data_num file; MSRA_Dataset(variant='cut') loads it
+    # the later fork's tree (cut_version/pre/read_MSRA.py:60-113): first three subjects, same volumes, ground
+    # truth [n,21,3], joint_nor/<ges>.npy in float64, no data_num file; MSRA_Dataset(variant='cut') loads it
     res2 = str(tmp_path / "result_cut")
     read_MSRA.SAVE_dir, read_MSRA.JOINT_NOR = res2, True
     np.random.seed(int(golden["seed"]))
@@ -175,8 +175,8 @@ def test_read_msra_main_writes_the_reference_tree(golden, tmp_path):
         read_MSRA.main()
     finally:
         read_MSRA.JOINT_NOR = False
-    assert not os.path.exists(os.path.join(res2, "data_num-P0.npy"))
-    for sub in mini.SUBJECTS:
+    assert not os.path.exists(os.path.join(res2, "data_num-P0.npy")) and not os.path.exists(os.path.join(res2, "P3"))
+    for sub in mini.SUBJECTS[:3]:
         for ges in mini.GESTURES:
             k = "%s_%s_" % (sub, ges)
             z = np.load(os.path.join(res2, sub, "TSDF", "%s.npz" % ges))
@@ -219,3 +219,67 @@ def test_dataset_from_database_on_device(golden, tmp_path):
     # deterministic variant: grid from all valid pixels (pre/tsdf_numba.py semantics), one fused launch per gesture
     dp = dataset.MSRA_Dataset.from_database(db, train=True, device="cuda", bbox="pixels")
     assert len(dp) == int(golden["ds_train_len"]) and float(dp.tsdf.abs().max()) <= 1.0
+    # the same set kept PACKED in host memory (dtsdf_voxelize_host_packed), samples expanded on demand
+    lazy = dataset.MSRA_Dataset.from_database(db, train=True, device=None, bbox="pixels", packed_host=True)
+    assert len(lazy) == len(dp) and tuple(lazy.tsdf.shape) == tuple(dp.tsdf.shape)
+    assert lazy.tsdf.nbytes < dp.tsdf.numel() * 4 / 4
+    dense = dp.tsdf.cpu().numpy()
+    for i in (0, 1, len(lazy) // 2, len(lazy) - 1):
+        t, g, ml, mp = lazy[i]
+        assert t.dtype == np.float32 and np.array_equal(t.view(np.uint32), dense[i].view(np.uint32))
+        assert ml == dp.max_l[i].item() and np.array_equal(g, dp.ground_truth[i].cpu().numpy())
+    loader = torch.utils.data.DataLoader(lazy, batch_size=5, shuffle=False)
+    got = torch.cat([b[0] for b in loader])
+    assert torch.equal(got, dp.tsdf.cpu())
+
+
+@pytest.mark.gpu
+def test_read_msra_main_writes_the_forks_tree_with_augmentation(tmp_path):
+    """pre/read_MSRA.py with JOINT_NOR and AUG: every file of the later fork's result/ tree - plain half and
+    _aug half - bit-identical to the UNMODIFIED fork's (cut_version/pre/read_MSRA.py:17-140 with AUG = True,
+    cut_version/pre/process.py:52-134; tests/golden/make_golden_tree_cut.py), np.random stream position
+    afterwards included.  DataProcess.data_aug(joints, point_clouds) itself against the frozen clouds."""
+    gold = np.load(os.path.join(HERE, "golden", "msra_tree_cut.npz"))
+    read_MSRA = _import("read_MSRA", PRE_DIR)
+    process = _import("process", PRE_DIR)
+    db = str(tmp_path / "db") + os.sep
+    os.makedirs(db)
+    mini.write_mini_db(db)
+    res = str(tmp_path / "result")
+    read_MSRA.DB_dir, read_MSRA.SAVE_dir, read_MSRA.AUG, read_MSRA.JOINT_NOR = db, res, True, True
+    np.random.seed(int(gold["seed"]))
+    try:
+        read_MSRA.main()
+    finally:
+        read_MSRA.AUG, read_MSRA.JOINT_NOR = False, False
+    assert np.array_equal(np.random.randint(0, 1 << 30, size=4), gold["stream_tail"])
+    assert sorted(os.listdir(res)) == [str(s) for s in gold["subjects"]]
+    for sub in gold["subjects"]:
+        assert sorted(os.listdir(os.path.join(res, str(sub)))) == sorted(
+            n + sfx for n in ("Point_Cloud", "TSDF", "ground_truth", "num", "joint_nor") for sfx in ("", "_aug"))
+        for ges in gold["gestures"]:
+            for sfx in ("", "_aug"):
+                k = "%s_%s%s_" % (sub, ges, sfx)
+                z = np.load(os.path.join(res, str(sub), "TSDF" + sfx, "%s.npz" % ges))
+                assert z["tsdf"].dtype == np.float64 and np.array_equal(z["tsdf"], gold[k + "tsdf"].astype(np.float64)), k
+                assert np.array_equal(np.signbit(z["tsdf"]), np.signbit(gold[k + "tsdf"]))
+                assert z["max_l"].dtype == np.float64 and np.array_equal(z["max_l"], gold[k + "max_l"]), k
+                assert np.array_equal(z["mid_p"], gold[k + "mid_p"]), k
+                pc = np.load(os.path.join(res, str(sub), "Point_Cloud" + sfx, "%s.npy" % ges))
+                assert pc.dtype == np.float64 and np.array_equal(pc[:, :32, :], gold[k + "pc_head"]), k
+                assert _sha(pc) == str(gold[k + "pc_sha256"]), k
+                for name in ("ground_truth", "num", "joint_nor"):
+                    got = np.load(os.path.join(res, str(sub), name + sfx, "%s.npy" % ges))
+                    want = gold[k + {"ground_truth": "gt", "num": "num", "joint_nor": "joint_nor"}[name]]
+                    assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want), (k, name)
+    # the drop-in method itself: DataProcess(data, point_num, aug).data_aug(joints, point_clouds)
+    fr = pkg.synth.make_frame(5)
+    dp = process.DataProcess(fr, 6000, True)
+    np.random.seed(3)
+    pc = dp.get_points()
+    pc_aug, gt_aug = dp.data_aug(np.arange(63, dtype=np.float32), pc)
+    assert pc_aug.shape == (6000, 3) and pc_aug.dtype == np.float64 and gt_aug.shape == (21, 3)
+    tsdf_aug, max_l_aug, mid_p_aug = dp.tsdf_f(pc_aug)
+    assert tsdf_aug.shape == (3, 32, 32, 32) and max_l_aug > 0
+    with pytest.raises(NotImplementedError):
+        dp.data_aug(pc)                                     # the original's signature: the original raises AxisError

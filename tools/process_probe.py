@@ -20,6 +20,15 @@ def rate(fn, reps=3):
 np.random.seed(0)
 res["process_frames_with_point_clouds_per_s"] = rate(lambda: vox.process_frames(frames, 6000, want_points=True))
 res["process_frames_volumes_only_per_s"] = rate(lambda: vox.process_frames(frames, 6000, want_points=False))
+res["process_frames_two_calls_numpy_draws_volumes_only_per_s"] = rate(
+    lambda: vox.process_frames_two_calls(frames, 6000, want_points=False), reps=1)
+hdr, off, pk, _ = pkg.pack_frames(frames)
+out = pkg.capi.PinnedBuffer((n, 3, 32, 32, 32), np.float32)
+res["process_packed_volumes_only_pinned_out_per_s"] = rate(
+    lambda: vox.process_packed(hdr, off, pk, 6000, want_points=False, out_vol=out.array))
+t0 = time.perf_counter()
+pkg.capi.resample_indices(np.full(n, 8811, dtype=np.int32), 6000)
+res["index_draw_in_library_only_per_s"] = n / (time.perf_counter() - t0)
 res["voxelize_frames_pixel_bbox_per_s"] = rate(lambda: vox.voxelize_frames(frames))
 # where the time goes in process_frames: the np.random index draw alone
 def draw():
