@@ -355,23 +355,30 @@ __device__ __forceinline__ float2 div_fixed2(float2 a, float2 nb, float2 y) {   
     return q;
 }
 
+// A caution that cost a round: ptxas (12.9) CONTRACTS packed operations.  mul.rn.f32x2 followed by add.rn.f32x2
+// becomes one FFMA2 - the explicit .rn that protects the scalar forms does not protect the x2 forms, with
+// -fmad=false or without - and an fma.rn.f32x2 by +-1 is first simplified to an add and then contracted the same
+// way.  So the packed pipe is used only where no product can reach an addition: sums of values that are not
+// products, and fused multiply-adds that ARE fused in the specification (the residual corrections of
+// div_fixed2).  Every product that is then added or subtracted - w = f * c1 -> v - w, the squares -> their
+// sum - is a scalar mul.rn feeding a scalar add.rn, which PTX guarantees are kept apart
+// (tests/test_sass_contraction.py checks the compiled code for it).
 template <bool DEFF>
 __device__ __forceinline__ void eval_pair(float2 d, float2 fx, float2 fy, float2 vx, float2 vy, float2 sz,
                                           float focal, float yf, float trunc, float ytr,
                                           float (&o0)[2], float (&o1)[2], float (&o2)[2]) {
-    const float2 m1 = make_float2(-1.0f, -1.0f);
     const float2 nf = make_float2(-focal, -focal), yf2 = make_float2(yf, yf);
     const float2 nt = make_float2(-trunc, -trunc), yt2 = make_float2(ytr, ytr);
     const float2 c1 = div_fixed2<DEFF>(d, nf, yf2);
-    const float2 wx = __fmul2_rn(fx, c1);
-    const float2 wy = __fmul2_rn(fy, c1);
-    const float2 dx = __ffma2_rn(wx, m1, vx);              // v_x - w_x: the product is exact, one rounding
-    const float2 dy = __ffma2_rn(wy, m1, vy);
+    // v - w with w = f * c1: product and difference each rounded once
+    const float2 dx = make_float2(__fsub_rn(vx.x, __fmul_rn(fx.x, c1.x)), __fsub_rn(vx.y, __fmul_rn(fx.y, c1.y)));
+    const float2 dy = make_float2(__fsub_rn(vy.x, __fmul_rn(fy.x, c1.x)), __fsub_rn(vy.y, __fmul_rn(fy.y, c1.y)));
     const float2 tx = div_fixed2<false>(dx, nt, yt2);      // signed; |t| below
     const float2 ty = div_fixed2<false>(dy, nt, yt2);
     const float2 tz = div_fixed2<false>(sz, nt, yt2);
-    const float2 s = __fadd2_rn(__fadd2_rn(__fmul2_rn(tx, tx), __fmul2_rn(ty, ty)), __fmul2_rn(tz, tz));
-    const float ss[2] = {s.x, s.y}, szz[2] = {sz.x, sz.y};
+    const float ss[2] = {__fadd_rn(__fadd_rn(__fmul_rn(tx.x, tx.x), __fmul_rn(ty.x, ty.x)), __fmul_rn(tz.x, tz.x)),
+                         __fadd_rn(__fadd_rn(__fmul_rn(tx.y, tx.y), __fmul_rn(ty.y, ty.y)), __fmul_rn(tz.y, tz.y))};
+    const float szz[2] = {sz.x, sz.y};
     const float txx[2] = {tx.x, tx.y}, tyy[2] = {ty.x, ty.y}, tzz[2] = {tz.x, tz.y};
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -1171,8 +1178,19 @@ struct AugFrame {
     const float* crop;            // staged (shared) or global crop
     int l, t, bw, bh;
     int cx, cy;
-    float focal, trunc, voxel_len, ox, oy, oz;
+    float focal, trunc;
+    float yf, ytr;                // rcp_rn(focal), rcp_rn(trunc): the fixed-divisor divisions of pass 2
+    bool fast_f, fast_t;          // ... are proven for this focal (241.42f) / this trunc range
     float t_far;                  // |v_z - w_z| above this forces the Euclidean truncation; +inf: no shortcut
+};
+
+// Per-axis tables of the separable voxel -> camera map (specification: oracle/dtsdf_oracle.c, step 3):
+//   v_k = tx[x][k] + (ty[y][k] + tz[z][k]),   tx[i] = (va_x[i] - c_x) * Ainv[0][.],  ty likewise with row 1,
+//   tz[i][k] = fma(va_z[i] - c_z, Ainv[2][k], c_k);   va[axis][i]: the voxel centres in the augmented frame.
+template <int R>
+struct __align__(16) AugTables {
+    float4 tx[R], ty[R], tz[R];
+    float va[3][R];
 };
 
 template <int R, int LAYOUT>
@@ -1181,77 +1199,117 @@ __device__ __forceinline__ void aug_group_index(int g, int& f0, int& m, int& s) 
     f0 = 4 * (g % Q); m = (g / Q) % R; s = g / (Q * R);
 }
 
-// Voxel j of a group: augmented-frame centre va, camera-frame centre v, pixel, depth.
-// Returns false when the voxel stays 0 (projection not finite, outside the crop, |d| < 1).
+// Camera-frame centres of the four voxels of a group (two per instruction on the packed FP32 pipe).
 template <int R, int LAYOUT>
-__device__ __forceinline__ bool aug_lookup(const AugFrame& k, const float* __restrict__ Ainv,
-                                           const float* __restrict__ c, int f0, int m, int s, int j,
-                                           float (&va)[3], float (&v)[3], int& px, int& py, float& d) {
-    const int xi = LAYOUT == 0 ? s : f0 + j, yi = m, zi = LAYOUT == 0 ? f0 + j : s;
-    va[0] = __fadd_rn(k.ox, __fmul_rn((float)xi, k.voxel_len));
-    va[1] = __fadd_rn(k.oy, __fmul_rn((float)yi, k.voxel_len));
-    va[2] = __fadd_rn(k.oz, __fmul_rn((float)zi, k.voxel_len));
-    xform(va[0], va[1], va[2], Ainv, c, v);
-    const float coeff = __fdiv_rn(-k.focal, v[2]);
-    const float fpx = __fadd_rn(__fmul_rn(v[0], coeff), (float)k.cx);
-    const float fpy = __fadd_rn(__fmul_rn(-v[1], coeff), (float)k.cy);
+__device__ __forceinline__ void aug_camera4(const AugTables<R>* __restrict__ T, int f0, int m, int s,
+                                            float (&vx)[4], float (&vy)[4], float (&vz)[4]) {
+    if (LAYOUT == 0) {                       // x = s, y = m, z = f0 + j
+        const float4 a = T->tx[s], b = T->ty[m];
+        const float2 ax = make_float2(a.x, a.x), ay = make_float2(a.y, a.y), az = make_float2(a.z, a.z);
+        const float2 bx = make_float2(b.x, b.x), by = make_float2(b.y, b.y), bz = make_float2(b.z, b.z);
+#pragma unroll
+        for (int h = 0; h < 4; h += 2) {
+            const float4 c0 = T->tz[f0 + h], c1 = T->tz[f0 + h + 1];
+            const float2 qx = __fadd2_rn(ax, __fadd2_rn(bx, make_float2(c0.x, c1.x)));
+            const float2 qy = __fadd2_rn(ay, __fadd2_rn(by, make_float2(c0.y, c1.y)));
+            const float2 qz = __fadd2_rn(az, __fadd2_rn(bz, make_float2(c0.z, c1.z)));
+            vx[h] = qx.x; vx[h + 1] = qx.y; vy[h] = qy.x; vy[h + 1] = qy.y; vz[h] = qz.x; vz[h + 1] = qz.y;
+        }
+    } else {                                 // x = f0 + j, y = m, z = s
+        const float4 b = T->ty[m], c = T->tz[s];
+        const float px = __fadd_rn(b.x, c.x), py = __fadd_rn(b.y, c.y), pz = __fadd_rn(b.z, c.z);
+        const float2 qx = make_float2(px, px), qy = make_float2(py, py), qz = make_float2(pz, pz);
+#pragma unroll
+        for (int h = 0; h < 4; h += 2) {
+            const float4 a0 = T->tx[f0 + h], a1 = T->tx[f0 + h + 1];
+            const float2 rx = __fadd2_rn(make_float2(a0.x, a1.x), qx);
+            const float2 ry = __fadd2_rn(make_float2(a0.y, a1.y), qy);
+            const float2 rz = __fadd2_rn(make_float2(a0.z, a1.z), qz);
+            vx[h] = rx.x; vx[h + 1] = rx.y; vy[h] = ry.x; vy[h + 1] = ry.y; vz[h] = rz.x; vz[h + 1] = rz.y;
+        }
+    }
+}
+
+// Projection and depth lookup of one voxel (pre/process.py:154-167), branch-free.  Returns the depth, or a
+// value with |d| < 1 ("no depth": the voxel stays 0) when the projection is not finite or outside the crop.
+// STAGED: the crop is in shared memory and the word right below it is 0.0f - the target of "outside".
+template <bool STAGED>
+__device__ __forceinline__ float aug_lookup(const AugFrame& k, float vx, float vy, float vz, int& px, int& py) {
+    const float coeff = __fdiv_rn(-k.focal, vz);
+    const float fpx = __fadd_rn(__fmul_rn(vx, coeff), (float)k.cx);
+    const float fpy = __fadd_rn(__fmul_rn(-vy, coeff), (float)k.cy);
     // the specification drops |fp| >= 2e9 (or NaN) before int(): the conversion saturates, so anything
     // that large falls outside the crop by itself; only NaN (which converts to 0) needs its own test
     px = __float2int_rz(fpx);
     py = __float2int_rz(fpy);
     const unsigned ux = (unsigned)(px - k.l), uy = (unsigned)(py - k.t);
     const float fs = __fadd_rn(fpx, fpy);
-    if (!(ux < (unsigned)k.bw && uy < (unsigned)k.bh && fs == fs)) return false;
-    d = k.crop[(int)uy * k.bw + (int)ux];
-    return !(fabsf(d) < 1.0f);
+    const bool in = ux < (unsigned)k.bw && uy < (unsigned)k.bh && fs == fs;
+    const int idx = in ? (int)uy * k.bw + (int)ux : -1;
+    if (STAGED) return k.crop[idx];
+    return in ? __ldg(k.crop + idx) : 0.0f;
+}
+
+// a / trunc and d / focal of pass 2: the fixed-divisor forms (div_fixed, file header) inside their proven
+// ranges - dividend 0 or 2^-60 <= |a| <= 2^60 with trunc in [2^-20, 2^20]; 1 <= |d| < 2^40 with the default
+// focal - and IEEE division otherwise.  Bit-identical either way.
+__device__ __forceinline__ float aug_div_trunc(const AugFrame& k, float a) {
+    const float m = fabsf(a);
+    if (k.fast_t && (m == 0.0f || (m >= 0x1p-60f && m <= 0x1p60f))) return div_fixed<false>(a, k.trunc, k.ytr);
+    return __fdiv_rn(a, k.trunc);
+}
+__device__ __forceinline__ float aug_div_focal(const AugFrame& k, float d) {
+    if (k.fast_f && fabsf(d) < BIG_DEPTH) return div_fixed<true>(d, k.focal, k.yf);     // (|d| >= 1: valid depth)
+    return __fdiv_rn(d, k.focal);
 }
 
 // Pass 1: every voxel of the group is 0, +-1 by the far-surface shortcut, or "near".
-template <int R, int LAYOUT>
-__device__ __forceinline__ bool aug_classify_group(const AugFrame& k, const float* __restrict__ Ainv,
-                                                   const float* __restrict__ c, int g, float4& val) {
+template <int R, int LAYOUT, bool STAGED>
+__device__ __forceinline__ bool aug_classify_group(const AugFrame& k, const AugTables<R>* __restrict__ T, int g, float4& val) {
     int f0, m, s;
     aug_group_index<R, LAYOUT>(g, f0, m, s);
-    float o[4];
+    float vx[4], vy[4], vz[4], o[4];
+    aug_camera4<R, LAYOUT>(T, f0, m, s, vx, vy, vz);
     bool near = false;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float va[3], v[3], d = 0.0f;
-        int px = 0, py = 0;
-        o[j] = 0.0f;
-        if (aug_lookup<R, LAYOUT>(k, Ainv, c, f0, m, s, j, va, v, px, py, d)) {
-            const float sz = __fadd_rn(v[2], d);                       // v_z - w_z, w_z = -d
-            if (fabsf(sz) > k.t_far && fabsf(d) < BIG_DEPTH)
-                o[j] = __int_as_float((__float_as_int(sz) & 0x80000000) | 0x3F800000);
-            else
-                near = true;
-        }
+        int px, py;
+        const float d = aug_lookup<STAGED>(k, vx[j], vy[j], vz[j], px, py);
+        const float sz = __fadd_rn(vz[j], d);                      // v_z - w_z, w_z = -d
+        const bool valid = !(fabsf(d) < 1.0f);
+        const bool far = fabsf(sz) > k.t_far && fabsf(d) < BIG_DEPTH;
+        o[j] = (valid && far) ? __int_as_float((__float_as_int(sz) & 0x80000000) | 0x3F800000) : 0.0f;
+        near = near || (valid && !far);
     }
     val = make_float4(o[0], o[1], o[2], o[3]);
     return near;
 }
 
-// Pass 2: the specification's evaluation of all four voxels of a listed group, IEEE divisions.
-template <int R, int LAYOUT>
-__device__ __forceinline__ void aug_eval_group(const AugFrame& k, const float* __restrict__ A,
-                                               const float* __restrict__ Ainv, const float* __restrict__ c,
+// Pass 2: the specification's evaluation of all four voxels of a listed group.
+template <int R, int LAYOUT, bool STAGED>
+__device__ __forceinline__ void aug_eval_group(const AugFrame& k, const AugTables<R>* __restrict__ T,
+                                               const float* __restrict__ A, const float* __restrict__ c,
                                                int g, float* __restrict__ out) {
     constexpr int CH = R * R * R;
     int f0, m, s;
     aug_group_index<R, LAYOUT>(g, f0, m, s);
+    float vx[4], vy[4], vz[4];
+    aug_camera4<R, LAYOUT>(T, f0, m, s, vx, vy, vz);
     float o0[4], o1[4], o2[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float va[3], v[3], d = 0.0f;
-        int px = 0, py = 0;
+        int px, py;
+        const float d = aug_lookup<STAGED>(k, vx[j], vy[j], vz[j], px, py);
         float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
-        if (aug_lookup<R, LAYOUT>(k, Ainv, c, f0, m, s, j, va, v, px, py, d)) {
-            const float c1 = __fdiv_rn(d, k.focal);
+        if (!(fabsf(d) < 1.0f)) {
+            const int xi = LAYOUT == 0 ? s : f0 + j, zi = LAYOUT == 0 ? f0 + j : s;
+            const float va0 = T->va[0][xi], va1 = T->va[1][m], va2 = T->va[2][zi];
+            const float c1 = aug_div_focal(k, d);
             float wa[3];
             xform(__fmul_rn((float)(px - k.cx), c1), __fmul_rn((float)(-(py - k.cy)), c1), -d, A, c, wa);
-            t0 = __fdiv_rn(fabsf(__fsub_rn(va[0], wa[0])), k.trunc);
-            t1 = __fdiv_rn(fabsf(__fsub_rn(va[1], wa[1])), k.trunc);
-            t2 = __fdiv_rn(fabsf(__fsub_rn(va[2], wa[2])), k.trunc);
+            t0 = fabsf(aug_div_trunc(k, __fsub_rn(va0, wa[0])));          // |a| / b == |a / b| under RN
+            t1 = fabsf(aug_div_trunc(k, __fsub_rn(va1, wa[1])));
+            t2 = fabsf(aug_div_trunc(k, __fsub_rn(va2, wa[2])));
             const float ss = __fadd_rn(__fadd_rn(__fmul_rn(t0, t0), __fmul_rn(t1, t1)), __fmul_rn(t2, t2));
             // sqrt_rn(ss) > 1 <=> ss > nextafter(1,2); then min(t,1) is the identity below it,
             // except for NaN (kept) - same as the specification's comparisons
@@ -1259,7 +1317,7 @@ __device__ __forceinline__ void aug_eval_group(const AugFrame& k, const float* _
             if (1.0f < t0) t0 = 1.0f;
             if (1.0f < t1) t1 = 1.0f;
             if (1.0f < t2) t2 = 1.0f;
-            if (-d > v[2]) { t0 = -t0; t1 = -t1; t2 = -t2; }
+            if (-d > vz[j]) { t0 = -t0; t1 = -t1; t2 = -t2; }
         }
         o0[j] = t0; o1[j] = t1; o2[j] = t2;
     }
@@ -1267,6 +1325,45 @@ __device__ __forceinline__ void aug_eval_group(const AugFrame& k, const float* _
     st_f4(p, make_float4(o0[0], o0[1], o0[2], o0[3]));
     st_f4(p + CH, make_float4(o1[0], o1[1], o1[2], o1[3]));
     st_f4(p + 2 * CH, make_float4(o2[0], o2[1], o2[2], o2[3]));
+}
+
+// Both passes over one frame.
+template <int R, int LAYOUT, bool STAGED>
+__device__ __forceinline__ void aug_voxel_passes(const AugFrame& k, const AugTables<R>* __restrict__ T,
+                                                 const float* __restrict__ A, const float* __restrict__ c,
+                                                 unsigned short* __restrict__ list, float* __restrict__ out) {
+    constexpr int CH = R * R * R;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt = 0;
+#pragma unroll 1
+    for (int g = tid; g < CH / 4; g += NT) {
+        float4 val;
+        bool near = aug_classify_group<R, LAYOUT, STAGED>(k, T, g, val);
+        // a 32-byte sector (an even/odd lane pair) is written once, whole: by pass 1 or by pass 2
+        unsigned bal = __ballot_sync(FULL, near);
+        bal |= ((bal & 0x55555555u) << 1) | ((bal & 0xAAAAAAAAu) >> 1);
+        near = (bal >> lane) & 1u;
+        if (!near) {
+            float* p = out + 4 * (size_t)g;
+            st_f4(p, val); st_f4(p + CH, val); st_f4(p + 2 * CH, val);
+        } else {
+            list[cnt + __popc(bal & lt)] = (unsigned short)g;
+        }
+        cnt += __popc(bal);
+        if (cnt >= 32) {
+            __syncwarp();
+            aug_eval_group<R, LAYOUT, STAGED>(k, T, A, c, (int)list[lane], out);
+            const int rem = cnt - 32;
+            unsigned short carry = 0;
+            if (lane < rem) carry = list[32 + lane];
+            __syncwarp();
+            if (lane < rem) list[lane] = carry;
+            cnt = rem;
+        }
+    }
+    __syncwarp();
+    if (lane < cnt) aug_eval_group<R, LAYOUT, STAGED>(k, T, A, c, (int)list[lane], out);
 }
 
 // Far-surface shortcut of the augmented path.  In exact arithmetic v' - w' = (v* - w) . A with v* the
@@ -1321,12 +1418,25 @@ __device__ __forceinline__ float aug_far_threshold(const float* __restrict__ A, 
         }
         if (emin > 0x1p-6f * 3.0f * q) smin_lo = fmaxf(smin_lo, sqrtf(emin) * 0.998f);
     }
+    // What the shortcut tests is the z component alone, and for a vector u with a given u_z the smallest
+    // |u . A| is |u_z| / |column z of A^-1| (minimum of the quadratic form u (A A^T) u^T with one coordinate
+    // fixed) - never below smin(A), and exactly 1 for the stretch-in-x,y-then-rotate maps of the reference
+    // (show/visualize.py:106-114: A = diag(sx, sy, 1) . R), whose near band is then as narrow as the plain
+    // kernel's instead of 1/min(sx, sy) times wider.  Column z of A^-1 = (row 0 of A) x (row 1 of A) / det.
+    float kappa_lo = smin_lo;
+    {
+        const float k0 = A[1] * A[5] - A[2] * A[4], k1 = A[2] * A[3] - A[0] * A[5], k2 = A[0] * A[4] - A[1] * A[3];
+        const float cn = sqrtf(k0 * k0 + k1 * k1 + k2 * k2);
+        // (each cross-product term carries a float32 error of ~2^-22 |A|_F^2: used only when the result is
+        // well above it)
+        if (cn > 0x1p-8f * fa && fabsf(det) > 0x1p-12f * na * fa) kappa_lo = fmaxf(kappa_lo, fabsf(det) / cn * 0.998f);
+    }
     const float size = fabsf(c[0]) + fabsf(c[1]) + fabsf(c[2]) + fabsf(mid0) + fabsf(mid1) + fabsf(mid2) +
                        2.0f * max_l + 1.0f;
     const float reach = fabsf(mid0 - c[0]) + fabsf(mid1 - c[1]) + fabsf(mid2 - c[2]) + max_l;
     const float drift = 3.0f * e * reach / smin_lo;
     const float slack = 0x1p-17f * (1.0f + na) * (1.0f + ni) * size;
-    const float t_far = ((trunc * 1.00390625f + slack) / smin_lo + drift) * 1.001f;
+    const float t_far = ((trunc * 1.00390625f + slack) / kappa_lo + drift) * 1.001f;
     const bool ok = smin_lo > 0x1p-6f * na && na < 0x1p10f && ni < 0x1p10f && size < 0x1p20f &&
                     trunc >= 0x1p-20f && trunc <= 0x1p20f && e < 0x1p-10f && t_far < 0x1p30f;   // NaN -> false
     return ok ? t_far : INFINITY;
@@ -1339,7 +1449,10 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
     __shared__ float red[NWARP][8];
     __shared__ float aug[21];
     __shared__ unsigned long long bar;
-    float* crop_s = reinterpret_cast<float*>(smem_raw);
+    __shared__ AugTables<R> tab;
+    // the staged crop starts 16 bytes into the dynamic shared memory; the word right below it is 0.0f
+    // ("no depth"), where lookups that fall outside the crop are pointed
+    float* crop_s = reinterpret_cast<float*>(smem_raw + 16);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.x;
     const Frame fr = load_frame(a, f);
@@ -1350,6 +1463,7 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
             mbar_expect_tx(&bar, (uint32_t)fr.n_pad * 4u);
             bulk_g2s(crop_s, fr.crop, (uint32_t)fr.n_pad * 4u, &bar);
         }
+        *reinterpret_cast<float4*>(smem_raw) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (tid < 21) aug[tid] = __ldg(aug_all + 21 * (size_t)f + tid);
     __syncthreads();
@@ -1358,19 +1472,47 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
     const float *A = aug, *Ainv = aug + 9, *c = aug + 18;
     const float focal = a.focal;
 
-    // ---- 1. bounding box of the augmented points of all valid pixels
+    // ---- 1. bounding box of the augmented points of all valid pixels: two pixels of a row per thread and
+    //      step, back-projection and transform on the packed FP32 pipe (FMUL2 / FFMA2: the same IEEE
+    //      operations, two at a time)
     float mn[3] = {SENTINEL, SENTINEL, SENTINEL}, mx[3] = {-SENTINEL, -SENTINEL, -SENTINEL};
-    for (int row = warp; row < fr.bh; row += NWARP)
-    for (int col = lane; col < fr.bw; col += 32) {
-        const float d = crop[row * fr.bw + col];
-        if (fabsf(d) < 1.0f) continue;
-        const float q = __fdiv_rn(d, focal);
-        const float X = __fmul_rn(q, (float)(col + fr.l - a.center_x));
-        const float Y = __fmul_rn(-q, (float)(row + fr.t - a.center_y));
-        float pa[3];
-        xform(X, Y, -d, A, c, pa);
+    {
+        const float yf = __frcp_rn(focal);
+        const bool deff = __float_as_uint(focal) == DEFAULT_FOCAL_BITS;
+        const float2 nc2 = make_float2(-c[2], -c[2]);
+        for (int row = warp; row < fr.bh; row += NWARP) {
+            const float fy = (float)(row + fr.t - a.center_y);
+            for (int col = lane; col < fr.bw; col += 64) {
+                const float d0 = crop[row * fr.bw + col];
+                const float d1 = col + 32 < fr.bw ? crop[row * fr.bw + col + 32] : 0.0f;
+                const bool v0 = !(fabsf(d0) < 1.0f), v1 = !(fabsf(d1) < 1.0f);
+                if (!(v0 || v1)) continue;
+                float2 q;
+                if (deff && fabsf(d0) < BIG_DEPTH && fabsf(d1) < BIG_DEPTH)
+                    q = div_fixed2<true>(make_float2(d0, d1), make_float2(-focal, -focal), make_float2(yf, yf));
+                else
+                    q = make_float2(__fdiv_rn(d0, focal), __fdiv_rn(d1, focal));
+                // X, Y are products that are then added to: scalar mul.rn, scalar add.rn (ptxas contracts the
+                // packed forms, see eval_pair); from dx on, every product is inside a specified fma
+                const float fx0 = (float)(col + fr.l - a.center_x), fx1 = (float)(col + 32 + fr.l - a.center_x);
+                const float2 dx = make_float2(__fsub_rn(__fmul_rn(q.x, fx0), c[0]), __fsub_rn(__fmul_rn(q.y, fx1), c[0]));
+                const float2 dy = make_float2(__fsub_rn(__fmul_rn(-q.x, fy), c[1]), __fsub_rn(__fmul_rn(-q.y, fy), c[1]));
+                const float2 dz = __fadd2_rn(make_float2(-d0, -d1), nc2);
+                float2 pa[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { mn[k] = pa[k] < mn[k] ? pa[k] : mn[k]; mx[k] = pa[k] > mx[k] ? pa[k] : mx[k]; }
+                for (int k = 0; k < 3; ++k) {
+                    float2 t = __fmul2_rn(dx, make_float2(A[k], A[k]));
+                    t = __ffma2_rn(dy, make_float2(A[3 + k], A[3 + k]), t);
+                    t = __ffma2_rn(dz, make_float2(A[6 + k], A[6 + k]), t);
+                    pa[k] = __fadd2_rn(t, make_float2(c[k], c[k]));
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (v0) { mn[k] = pa[k].x < mn[k] ? pa[k].x : mn[k]; mx[k] = pa[k].x > mx[k] ? pa[k].x : mx[k]; }
+                    if (v1) { mn[k] = pa[k].y < mn[k] ? pa[k].y : mn[k]; mx[k] = pa[k].y > mx[k] ? pa[k].y : mx[k]; }
+                }
+            }
+        }
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
@@ -1414,51 +1556,37 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
         }
     }
 
-    // ---- 3. voxel loop: a thread owns 4 consecutive voxels along the fastest output axis (a warp: 512
-    //      contiguous bytes per channel).  Two passes per warp as in the fused kernel: pass 1 classifies
-    //      (projection, lookup, far-surface shortcut) and stores the sectors that hold only 0 / +-1; groups
-    //      in sectors with near-surface voxels go to a per-warp list and are evaluated 32 at a time by
-    //      pass 2 with all lanes busy (the specification's arithmetic, IEEE divisions).
+    // ---- 3. per-axis tables of the voxel -> camera map (the specification's step 3), then the voxel loop:
+    //      a thread owns 4 consecutive voxels along the fastest output axis (a warp: 512 contiguous bytes per
+    //      channel).  Two passes per warp as in the fused kernel: pass 1 classifies (table sum, projection,
+    //      lookup, far-surface shortcut) and stores the sectors that hold only 0 / +-1; groups in sectors with
+    //      near-surface voxels go to a per-warp list and are evaluated 32 at a time by pass 2 with all lanes
+    //      busy (the specification's arithmetic, IEEE divisions).
     constexpr int CH = R * R * R;
-    static_assert((CH / 4) % NT == 0 && CH / 4 <= 65536, "groups per frame: whole warps, 16-bit list entries");
+    static_assert((CH / 4) % NT == 0 && CH / 4 <= 65536 && 3 * R <= NT, "groups per frame: whole warps, 16-bit list entries");
+    if (tid < 3 * R) {
+        const int axis = tid / R, i = tid - axis * R;
+        const float o = axis == 0 ? ox : (axis == 1 ? oy : oz);
+        const float va = __fadd_rn(o, __fmul_rn((float)i, voxel_len));
+        const float dd = __fsub_rn(va, c[axis]);
+        tab.va[axis][i] = va;
+        if (axis == 0)      tab.tx[i] = make_float4(__fmul_rn(dd, Ainv[0]), __fmul_rn(dd, Ainv[1]), __fmul_rn(dd, Ainv[2]), 0.0f);
+        else if (axis == 1) tab.ty[i] = make_float4(__fmul_rn(dd, Ainv[3]), __fmul_rn(dd, Ainv[4]), __fmul_rn(dd, Ainv[5]), 0.0f);
+        else                tab.tz[i] = make_float4(__fmaf_rn(dd, Ainv[6], c[0]), __fmaf_rn(dd, Ainv[7], c[1]),
+                                                    __fmaf_rn(dd, Ainv[8], c[2]), 0.0f);
+    }
     __shared__ unsigned short glist[NWARP][64];
     AugFrame k;
     k.crop = crop; k.l = fr.l; k.t = fr.t; k.bw = max(fr.bw, 0); k.bh = max(fr.bh, 0);   // bad header: empty crop
-    k.cx = a.center_x; k.cy = a.center_y; k.focal = focal; k.trunc = trunc; k.voxel_len = voxel_len;
-    k.ox = ox; k.oy = oy; k.oz = oz;
+    k.cx = a.center_x; k.cy = a.center_y; k.focal = focal; k.trunc = trunc;
+    k.yf = __frcp_rn(focal); k.ytr = __frcp_rn(trunc);
+    k.fast_f = __float_as_uint(focal) == DEFAULT_FOCAL_BITS;
+    k.fast_t = trunc >= 0x1p-20f && trunc <= 0x1p20f;
     k.t_far = aug_far_threshold(A, Ainv, c, trunc, max_l, mid0, mid1, mid2);
+    __syncthreads();          // the tables are complete
     float* out = a.vol + (size_t)f * 3 * CH;
-    unsigned short* list = glist[warp];
-    const unsigned lt = (1u << lane) - 1u;
-    int cnt = 0;
-#pragma unroll 1
-    for (int g = tid; g < CH / 4; g += NT) {
-        float4 val;
-        bool near = aug_classify_group<R, LAYOUT>(k, Ainv, c, g, val);
-        // a 32-byte sector (an even/odd lane pair) is written once, whole: by pass 1 or by pass 2
-        unsigned bal = __ballot_sync(FULL, near);
-        bal |= ((bal & 0x55555555u) << 1) | ((bal & 0xAAAAAAAAu) >> 1);
-        near = (bal >> lane) & 1u;
-        if (!near) {
-            float* p = out + 4 * (size_t)g;
-            st_f4(p, val); st_f4(p + CH, val); st_f4(p + 2 * CH, val);
-        } else {
-            list[cnt + __popc(bal & lt)] = (unsigned short)g;
-        }
-        cnt += __popc(bal);
-        if (cnt >= 32) {
-            __syncwarp();
-            aug_eval_group<R, LAYOUT>(k, A, Ainv, c, (int)list[lane], out);
-            const int rem = cnt - 32;
-            unsigned short carry = 0;
-            if (lane < rem) carry = list[32 + lane];
-            __syncwarp();
-            if (lane < rem) list[lane] = carry;
-            cnt = rem;
-        }
-    }
-    __syncwarp();
-    if (lane < cnt) aug_eval_group<R, LAYOUT>(k, A, Ainv, c, (int)list[lane], out);
+    if (fr.staged) aug_voxel_passes<R, LAYOUT, true>(k, &tab, A, c, glist[warp], out);
+    else           aug_voxel_passes<R, LAYOUT, false>(k, &tab, A, c, glist[warp], out);
 }
 
 template <int R, int LAYOUT>
@@ -1481,7 +1609,7 @@ cudaError_t launch_aug_t(const BatchArgs& args_in, const float* aug, int max_cro
     static std::atomic<unsigned> smem_ok{0u};
     e = allow_max_smem(kern, dev, smem_optin, smem_ok);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)args.n_frames, NT, (size_t)want, stream>>>(args, aug);
+    kern<<<(unsigned)args.n_frames, NT, (size_t)want + 16, stream>>>(args, aug);          // + the zero word below the crop
     ++g_launch_count;
     return cudaGetLastError();
 }

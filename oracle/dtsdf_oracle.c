@@ -176,13 +176,21 @@ int oracle_dtsdf_batch(int n_frames, const int32_t* headers, const float* packed
  *   1. bounding box over the AUGMENTED points of all valid pixels (|d| >= 1; back-projection as
  *      pre/tsdf_numba.py:91-96), sentinels as pre/tsdf_numba.py:88-89;
  *   2. grid parameters from it, pre/process.py:91-96;
- *   3. per voxel centre v' of that grid (augmented space): v = T(v'; Ainv, c) back in the camera
- *      frame; project v (pre/process.py:155-157), look the depth up (:159-167), back-project the
- *      pixel to the surface point w (:172-175), augment it: w' = T(w; A, c); per-axis distances
- *      |v'_k - w'_k| / trunc, Euclidean truncation and min(t,1) (:177-189); negative behind the
- *      surface as seen from the camera: w_z > v_z (:191-194, in the camera frame).
+ *   3. per voxel centre v' = (v'_x[x], v'_y[y], v'_z[z]) of that grid (augmented space): back in the camera
+ *      frame v = (v' - c) . Ainv + c, evaluated SEPARABLY - one table per grid axis, three components each,
+ *      and a fixed order of the two additions (round 2: the map is linear in the three grid indices, so a
+ *      per-axis table sum costs 3-4 additions per voxel where the row-vector product cost 15 operations):
+ *          Tx[x][k] = (v'_x[x] - c_x) * Ainv[0][k]
+ *          Ty[y][k] = (v'_y[y] - c_y) * Ainv[1][k]
+ *          Tz[z][k] = fmaf(v'_z[z] - c_z, Ainv[2][k], c_k)
+ *          v_k      = Tx[x][k] + (Ty[y][k] + Tz[z][k])
+ *      then: project v (pre/process.py:155-157), look the depth up (:159-167), back-project the pixel to the
+ *      surface point w (:172-175), augment it: w' = T(w; A, c); per-axis distances |v'_k - w'_k| / trunc,
+ *      Euclidean truncation and min(t,1) (:177-189); negative behind the surface as seen from the camera:
+ *      w_z > v_z (:191-194, in the camera frame).
  * With A = Ainv = identity and any finite c the result equals oracle_dtsdf_batch with bbox_mode 0
- * whenever (p - c) + c == p exactly, in particular for c = 0.
+ * whenever (p - c) + c == p exactly, in particular for c = 0 (the table sum then adds signed zeros to the one
+ * non-zero term of each component).
  * aug[f] = { A[3][3], Ainv[3][3], c[3] } (21 floats, row-major matrices).
  */
 static inline void xform(const float* p, const float* M, const float* c, float* q) {
@@ -223,13 +231,24 @@ void oracle_dtsdf_aug_frame(const int32_t* header, const float* depth, const flo
     if (max_l_out) *max_l_out = ml;
     if (mid_out) { mid_out[0] = mid[0]; mid_out[1] = mid[1]; mid_out[2] = mid[2]; }
     if (n == 0) return;
+    float Tx[64][3], Ty[64][3], Tz[64][3];
+    for (int i = 0; i < R; ++i) {
+        const float dx = (vox_ori[0] + (float)i * voxel_len) - c[0];
+        const float dy = (vox_ori[1] + (float)i * voxel_len) - c[1];
+        const float dz = (vox_ori[2] + (float)i * voxel_len) - c[2];
+        for (int k = 0; k < 3; ++k) {
+            Tx[i][k] = dx * Ainv[k];
+            Ty[i][k] = dy * Ainv[3 + k];
+            Tz[i][k] = fmaf(dz, Ainv[6 + k], c[k]);
+        }
+    }
     for (int x = 0; x < R; ++x)
         for (int y = 0; y < R; ++y)
             for (int z = 0; z < R; ++z) {
                 const float va[3] = {vox_ori[0] + (float)x * voxel_len, vox_ori[1] + (float)y * voxel_len,
                                      vox_ori[2] + (float)z * voxel_len};
                 float v[3];
-                xform(va, Ainv, c, v);
+                for (int k = 0; k < 3; ++k) v[k] = Tx[x][k] + (Ty[y][k] + Tz[z][k]);
                 const float coeff = -focal / v[2];
                 const float fpx = v[0] * coeff + (float)cx;
                 const float fpy = -v[1] * coeff + (float)cy;
