@@ -1,8 +1,10 @@
-"""BASELINE.json configs[4]: on-the-fly D-TSDF feeding a training step, voxelisation overlapped with
-the step.  The consumer is a stand-in 3-D CNN (the reference's DenseNet, 3D_CNN/network.py, is out of
-scope: it is cuDNN work); what is measured is what the voxeliser adds to the step time.
+"""BASELINE.json configs[4]: on-the-fly D-TSDF feeding the training step of 3D_CNN/network.py, voxelisation
+overlapped with the step.  The consumer is the reference's DenseNet and optimiser step rebuilt in
+tools/consumer_net.py (harness, pinned to the unmodified 3D_CNN/network.py by tests/test_consumer_network.py; cuDNN
+work, not product code) or, with --net standin, a three-convolution stand-in; what is measured is what the
+voxeliser adds to the step time.
 
-    python tools/overlap_demo.py [--frames 4096] [--batch 32] [--steps 100]
+    python tools/overlap_demo.py [--frames 4096] [--batch 16] [--steps 100] [--augment] [--net densenet|standin]
 """
 import argparse, importlib, json, os, sys, time
 import numpy as np
@@ -13,7 +15,8 @@ import __graft_entry__ as g
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=4096)
-ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--batch", type=int, default=16, help="the reference trains with 16 (3D_CNN/train.py:36)")
+ap.add_argument("--net", choices=["densenet", "standin"], default="densenet")
 ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--augment", action="store_true", help="random stretch + rotation per batch (augmented voxeliser)")
 args = ap.parse_args()
@@ -25,19 +28,25 @@ offsets, packed_len, max_px = pkg.capi.pack_plan(headers)
 gt = np.random.default_rng(1).uniform(-150, 150, size=(args.frames, 63)).astype(np.float32)
 res = lmod.ResidentFrames(headers, offsets, depth.reshape(-1), gt, dev, max_px)
 
-net = torch.nn.Sequential(
-    torch.nn.Conv3d(3, 16, 3, padding=1), torch.nn.ReLU(), torch.nn.MaxPool3d(2),
-    torch.nn.Conv3d(16, 48, 3, padding=1), torch.nn.ReLU(), torch.nn.MaxPool3d(2),
-    torch.nn.Conv3d(48, 96, 3, padding=1), torch.nn.ReLU(), torch.nn.MaxPool3d(2),
-    torch.nn.Flatten(), torch.nn.Linear(96 * 64, 1024), torch.nn.ReLU(), torch.nn.Linear(1024, 63)).to(dev)
-opt = torch.optim.SGD(net.parameters(), lr=1e-3)
+if args.net == "densenet":
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import consumer_net
+    net = consumer_net.DenseNet().to(dev)
+    train_step = consumer_net.make_training_step(net, lr=0.005)
+else:
+    net = torch.nn.Sequential(
+        torch.nn.Conv3d(3, 16, 3, padding=1), torch.nn.ReLU(), torch.nn.MaxPool3d(2),
+        torch.nn.Conv3d(16, 48, 3, padding=1), torch.nn.ReLU(), torch.nn.MaxPool3d(2),
+        torch.nn.Conv3d(48, 96, 3, padding=1), torch.nn.ReLU(), torch.nn.MaxPool3d(2),
+        torch.nn.Flatten(), torch.nn.Linear(96 * 64, 1024), torch.nn.ReLU(), torch.nn.Linear(1024, 63)).to(dev)
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3)
 
-def train_step(tsdf, target):
-    opt.zero_grad(set_to_none=True)
-    loss = torch.nn.functional.mse_loss(net(tsdf), target)
-    loss.backward()
-    opt.step()
-    return loss
+    def train_step(tsdf, target):
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(net(tsdf), target)
+        loss.backward()
+        opt.step()
+        return loss
 
 def timed(fn, steps):
     torch.cuda.synchronize()
@@ -78,6 +87,6 @@ def overlapped(n):
                 break
 overlapped(10)
 ms_overlap = timed(overlapped, args.steps)
-print(json.dumps({"batch": args.batch, "augment": bool(args.augment), "ms_step_alone": ms_step, "ms_voxelise_then_step": ms_serial,
+print(json.dumps({"net": args.net, "batch": args.batch, "augment": bool(args.augment), "ms_step_alone": ms_step, "ms_voxelise_then_step": ms_serial,
                   "ms_overlapped_loader": ms_overlap,
                   "voxeliser_cost_serial_ms": ms_serial - ms_step, "voxeliser_cost_overlapped_ms": ms_overlap - ms_step}))
