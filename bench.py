@@ -481,11 +481,31 @@ def run_secondary(pkg, dev, rank, world, args, max_over_ranks, barrier):
         pkg.voxelize_device(d_packed, d_off, d_hdr, max_px, cfg_e, aux=d_ext, out_vol=vol, out_max_l=d_maxl, out_mid_p=d_mid)
     ms = timed(process_device)
     alg = algorithmic_bytes(headers, R) + int(np.sum(4 * n_px + 24 * n_valid.astype(np.int64) + 28 * P + 24))
-    entry("process_semantics_device", F, ms, alg,
-          {"config": "bbox from the resampled 6000-point cloud: point_cloud_kernel (f64) + resample_extrema_kernel + "
-                     "fused kernel (extrema mode), index vectors resident",
+    entry("process_semantics_device_with_clouds", F, ms, alg,
+          {"config": "bbox from the resampled 6000-point cloud, clouds materialised (what a caller that wants the "
+                     "sampled points pays): point_cloud_kernel (f64) + resample_extrema_kernel + fused kernel (extrema "
+                     "mode), index vectors resident",
            "bytes": "fused 455,656 + crop 4 bw bh + cloud 24 n_valid written + gather 24+4 per sample + 24"})
-    del d_points, d_idx, vol
+    del d_points
+    torch.cuda.empty_cache()
+
+    # the same semantics in ONE launch when the sampled cloud itself is not wanted (3D_CNN/dataset.py never
+    # reads it): ranks of the valid pixels, a bitmap of the sampled ranks and the extrema of the sample inside
+    # the voxeliser (DTSDF_BBOX_SAMPLED) - no cloud is ever written
+    cfg_s = capi.default_config(R, args.layout, pkg.BBOX_PIXELS)
+
+    def process_sampled():
+        pkg.voxelize_sampled_device(d_packed, d_off, d_hdr, d_idx, max_px, cfg_s, out_vol=vol, out_max_l=d_maxl,
+                                    out_mid_p=d_mid)
+    ms_count = timed(lambda: pkg.count_valid_device(d_packed, d_off, d_hdr, out=d_nvalid))
+    ms = timed(process_sampled)
+    entry("process_semantics_device", F, ms, algorithmic_bytes(headers, R) + 4 * P * F,
+          {"config": "bbox from the resampled 6000-point cloud inside the voxeliser launch "
+                     "(dtsdf_voxelize_sampled_batch), index vectors resident",
+           "bytes": "fused 455,656 + 4 x 6000 index bytes per frame",
+           "count_valid_ms": ms_count,
+           "count_valid": "dtsdf_count_valid_batch over the same frames (what the index draw needs first; reads the crops)"})
+    del d_idx, vol
     torch.cuda.empty_cache()
 
     # the host call: crops in, volumes out, index vectors drawn from np.random's MT19937 by the library
@@ -502,11 +522,23 @@ def run_secondary(pkg, dev, rank, world, args, max_over_ranks, barrier):
         vox.process_packed(headers[:n_host], offsets[:n_host], packed_h, P, want_points=False, out_vol=h_out.array)
     dt = max_over_ranks(time.perf_counter() - t0) / reps
     barrier()
+    # what bounds it: the caller's random stream is ONE sequential MT19937 (each frame's 6000 draws start where
+    # the previous frame's rejection sampling stopped), drawn by one thread whatever the GPU does meanwhile
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        capi.resample_indices(n_valid[:n_host], P)
+    dt_rng = max_over_ranks(time.perf_counter() - t0) / reps
+    barrier()
     out["process_semantics_host_call"] = {
         "frames_per_gpu": n_host, "ms": dt * 1e3, "value": n_host * world / dt, "unit": "frames/s",
         "config": "Voxelizer.process_packed(want_points=False) = dtsdf_process_host: host crops in, volumes out (pinned), "
                   "resampling indices drawn in C from the caller's np.random MT19937 state (bit-compatible with the "
-                  "reference's per-frame np.random.randint calls, pre/process.py:75-80)"}
+                  "reference's per-frame np.random.randint calls, pre/process.py:75-80); dtsdf_count_valid_batch + "
+                  "dtsdf_voxelize_sampled_batch per chunk",
+        "bound": {"what": "the index draw alone (dtsdf_resample_indices, one thread: the stream is sequential)",
+                  "ms": dt_rng * 1e3, "value": n_host * world / dt_rng, "unit": "frames/s",
+                  "ns_per_draw": dt_rng / (n_host * P) * 1e9},
+        "frac": dt_rng / dt}
     vox.close()
     h_out.free()
 

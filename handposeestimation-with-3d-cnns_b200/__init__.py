@@ -10,10 +10,10 @@ Python identifier; load it with ``__graft_entry__.load_package()`` (alias
 from . import capi, synth
 from .capi import (BBOX_EXTREMA, BBOX_GRID, BBOX_PIXELS, LAYOUT_CXYZ, LAYOUT_CZYX, DtsdfError)
 from .voxelizer import (PackedHostVolumeList, PackedHostVolumes, Voxelizer, default_voxelizer, normalize_joints_device, pack_frames,
-                        shard_packed, shard_range, voxelize_device)
+                        shard_packed, shard_range, voxelize_device, voxelize_sampled_device, count_valid_device)
 
 __all__ = [
     "capi", "synth", "Voxelizer", "PackedHostVolumes", "PackedHostVolumeList", "default_voxelizer", "pack_frames", "voxelize_device",
-    "normalize_joints_device", "shard_range", "shard_packed", "DtsdfError",
+    "normalize_joints_device", "voxelize_sampled_device", "count_valid_device", "shard_range", "shard_packed", "DtsdfError",
     "LAYOUT_CXYZ", "LAYOUT_CZYX", "BBOX_PIXELS", "BBOX_EXTREMA", "BBOX_GRID",
 ]

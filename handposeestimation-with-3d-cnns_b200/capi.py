@@ -85,6 +85,9 @@ _SIGNATURES = {
                                                    _vp]),
     "dtsdf_voxelize_aug_batch": (ctypes.c_int, [_cfgp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp,
                                                 _vp]),
+    "dtsdf_count_valid_batch": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _vp]),
+    "dtsdf_voxelize_sampled_batch": (ctypes.c_int, [_cfgp, ctypes.c_double, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp,
+                                                    _vp]),
     "dtsdf_point_cloud_batch": (ctypes.c_int, [_i32, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_resample_extrema_batch": (ctypes.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_normalize_joints_batch": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i32, _vp, _vp]),

@@ -461,6 +461,51 @@ int dtsdf_voxelize_joints_batch(const dtsdf_config* cfg, int32_t n_frames, const
     return DTSDF_OK;
 }
 
+int dtsdf_count_valid_batch(int32_t n_frames, const float* d_depth_packed, const int64_t* d_crop_offsets,
+                            const int32_t* d_headers, int32_t* d_out_n_valid, void* stream) {
+    if (n_frames < 0) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!d_depth_packed || !d_crop_offsets || !d_headers || !d_out_n_valid) return DTSDF_ERR_INVALID_ARG;
+    CK(dtsdf::launch_count_valid(n_frames, d_depth_packed, reinterpret_cast<const long long*>(d_crop_offsets), d_headers,
+                                 d_out_n_valid, (cudaStream_t)stream));
+    return DTSDF_OK;
+}
+
+int dtsdf_voxelize_sampled_batch(const dtsdf_config* cfg, double focal, int32_t n_frames,
+                                 const float* d_depth_packed, const int64_t* d_crop_offsets,
+                                 const int32_t* d_headers, const int32_t* d_sample_idx, int32_t point_num,
+                                 int32_t max_crop_px, float* d_out_vol, float* d_out_max_l,
+                                 float* d_out_mid_p, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc != DTSDF_OK) return rc;
+    if (n_frames < 0 || point_num <= 0 || !(focal > 0.0)) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!d_depth_packed || !d_crop_offsets || !d_headers || !d_sample_idx || !d_out_vol) return DTSDF_ERR_INVALID_ARG;
+    dtsdf::BatchArgs a;
+    a.depth = d_depth_packed;
+    a.offsets = reinterpret_cast<const long long*>(d_crop_offsets);
+    a.headers = d_headers;
+    a.aux = nullptr;
+    a.vol = d_out_vol;
+    a.max_l = d_out_max_l;
+    a.mid_p = d_out_mid_p;
+    a.n_frames = n_frames;
+    a.cap_floats = 0;
+    a.bbox_mode = DTSDF_BBOX_SAMPLED;
+    a.center_x = cfg->center_x;
+    a.center_y = cfg->center_y;
+    a.focal = cfg->focal;
+    a.trunc_mul = cfg->trunc_mul;
+    a.joints = nullptr;
+    a.out_joints = nullptr;
+    a.joint_flags = 0;
+    a.sample_idx = d_sample_idx;
+    a.point_num = point_num;
+    a.focal64 = focal;
+    CK(dtsdf::launch_voxelize(cfg->voxel_res, cfg->layout, a, max_crop_px, (cudaStream_t)stream));
+    return DTSDF_OK;
+}
+
 int dtsdf_voxelize_aug_batch(const dtsdf_config* cfg, int32_t n_frames, const float* d_depth_packed,
                              const int64_t* d_crop_offsets, const int32_t* d_headers, const float* d_aug,
                              int32_t max_crop_px, const float* d_joints, int32_t joint_flags,
@@ -767,6 +812,7 @@ struct HostPipeline {
     uint32_t* mt_key = nullptr;
     int* mt_pos = nullptr;
     double* h_pc = nullptr;
+    double focal64 = 0.0;
     // finalizer: takes the chunks in order, polls the event behind each one's last copy, hands the
     // chunk to the expansion threads
     std::mutex qm;
@@ -953,6 +999,12 @@ int HostPipeline::submit_chunks() {
                                       (const int32_t*)c->d_hdr[slot].p, aux_w ? (const float*)c->d_aux[slot].p : nullptr,
                                       max_px, (float*)c->d_vol[slot].p, (float*)c->d_maxl[slot].p,
                                       (float*)c->d_mid[slot].p, c->s_run);
+        } else if (!h_pc) {
+            // nobody wants the sampled clouds: ranks, sample bitmap and extrema inside the voxeliser launch
+            rc = dtsdf_voxelize_sampled_batch(cfg, focal64, nf, (const float*)c->b_depth.p, (const int64_t*)c->b_off.p + f0,
+                                              (const int32_t*)c->b_hdr.p + 6 * (size_t)f0, (const int32_t*)c->p_idx[slot].p,
+                                              point_num, c->b_max_px, (float*)c->d_vol[slot].p, (float*)c->d_maxl[slot].p,
+                                              (float*)c->d_mid[slot].p, c->s_run);
         } else {
             rc = dtsdf_resample_extrema_batch(nf, point_num, (const double*)c->b_points.p, (const int64_t*)c->b_poff.p + f0,
                                               (const int32_t*)c->p_idx[slot].p, h_pc ? (double*)c->p_pc[slot].p : nullptr,
@@ -1269,17 +1321,19 @@ int dtsdf_resample_extrema_host(dtsdf_ctx* c, int32_t point_num, const double* h
 
 static int process_begin_impl(dtsdf_ctx* c, double focal, int32_t n_frames, const float* h_depth,
                               int64_t packed_len, const int64_t* h_off, const int32_t* h_hdr,
-                              int32_t* h_n_valid);
+                              int32_t* h_n_valid, bool want_points);
 
 int dtsdf_process_begin_host(dtsdf_ctx* c, double focal, int32_t n_frames, const float* h_depth,
                              int64_t packed_len, const int64_t* h_off, const int32_t* h_hdr,
                              int32_t* h_n_valid) {
-    return guarded([&] { return process_begin_impl(c, focal, n_frames, h_depth, packed_len, h_off, h_hdr, h_n_valid); });
+    return guarded([&] { return process_begin_impl(c, focal, n_frames, h_depth, packed_len, h_off, h_hdr, h_n_valid, true); });
 }
 
+// want_points = false: only the valid-pixel counts are needed (the sampled voxeliser finds the box of the
+// resampled cloud from the depth map itself); no cloud is built and none of its memory reserved
 static int process_begin_impl(dtsdf_ctx* c, double focal, int32_t n_frames, const float* h_depth,
                               int64_t packed_len, const int64_t* h_off, const int32_t* h_hdr,
-                              int32_t* h_n_valid) {
+                              int32_t* h_n_valid, bool want_points) {
     if (!c || n_frames < 0 || packed_len < 0 || !(focal > 0.0)) return DTSDF_ERR_INVALID_ARG;
     c->b_n = 0;
     if (n_frames == 0) return DTSDF_OK;
@@ -1302,22 +1356,29 @@ static int process_begin_impl(dtsdf_ctx* c, double focal, int32_t n_frames, cons
     if ((rc = c->b_depth.reserve((size_t)packed_len * 4)) != DTSDF_OK) return rc;
     if ((rc = c->b_off.reserve((size_t)n_frames * 8)) != DTSDF_OK) return rc;
     if ((rc = c->b_hdr.reserve((size_t)n_frames * 24)) != DTSDF_OK) return rc;
-    if ((rc = c->b_poff.reserve((size_t)n_frames * 8)) != DTSDF_OK) return rc;
     if ((rc = c->b_nvalid.reserve((size_t)n_frames * 4)) != DTSDF_OK) return rc;
-    if ((rc = c->b_points.reserve((size_t)total_px * 24)) != DTSDF_OK) return rc;
+    if (want_points) {
+        if ((rc = c->b_poff.reserve((size_t)n_frames * 8)) != DTSDF_OK) return rc;
+        if ((rc = c->b_points.reserve((size_t)total_px * 24)) != DTSDF_OK) return rc;
+    }
     cudaStream_t s = c->s_run;
     CK(cudaMemcpyAsync(c->b_depth.p, h_depth, (size_t)packed_len * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c->b_off.p, h_off, (size_t)n_frames * 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c->b_hdr.p, h_hdr, (size_t)n_frames * 24, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(c->b_poff.p, poff.data(), (size_t)n_frames * 8, cudaMemcpyHostToDevice, s));
-    rc = dtsdf_point_cloud_batch(n_frames, focal, (const float*)c->b_depth.p, (const int64_t*)c->b_off.p,
-                                 (const int32_t*)c->b_hdr.p, (double*)c->b_points.p, (const int64_t*)c->b_poff.p,
-                                 (int32_t*)c->b_nvalid.p, s);
+    if (want_points) {
+        CK(cudaMemcpyAsync(c->b_poff.p, poff.data(), (size_t)n_frames * 8, cudaMemcpyHostToDevice, s));
+        rc = dtsdf_point_cloud_batch(n_frames, focal, (const float*)c->b_depth.p, (const int64_t*)c->b_off.p,
+                                     (const int32_t*)c->b_hdr.p, (double*)c->b_points.p, (const int64_t*)c->b_poff.p,
+                                     (int32_t*)c->b_nvalid.p, s);
+    } else {
+        rc = dtsdf_count_valid_batch(n_frames, (const float*)c->b_depth.p, (const int64_t*)c->b_off.p,
+                                     (const int32_t*)c->b_hdr.p, (int32_t*)c->b_nvalid.p, s);
+    }
     if (rc != DTSDF_OK) return rc;
     CK(cudaMemcpyAsync(h_n_valid, c->b_nvalid.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));           // also covers the pageable poff staging
     c->b_nvalid_h.assign(h_n_valid, h_n_valid + n_frames);
-    c->b_n = n_frames;
+    c->b_n = want_points ? n_frames : 0;       // dtsdf_process_finish_host needs the clouds
     c->b_max_px = max_px;
     return DTSDF_OK;
 }
@@ -1401,7 +1462,8 @@ int dtsdf_process_host(dtsdf_ctx* c, const dtsdf_config* cfg_in, double focal, i
     return guarded([&]() -> int {
         // back-projection + compaction of every frame; crops, tables and clouds stay resident (b_*)
         std::vector<int32_t> n_valid((size_t)n_frames);
-        int rc2 = process_begin_impl(c, focal, n_frames, h_depth, packed_len, h_off, h_hdr, n_valid.data());
+        int rc2 = process_begin_impl(c, focal, n_frames, h_depth, packed_len, h_off, h_hdr, n_valid.data(),
+                                     h_out_pc != nullptr);
         if (rc2 != DTSDF_OK) return rc2;
         USE_DEVICE(c->device);
         dtsdf_config cfg = *cfg_in;
@@ -1412,6 +1474,7 @@ int dtsdf_process_host(dtsdf_ctx* c, const dtsdf_config* cfg_in, double focal, i
         p.h_aux = nullptr; p.h_vol = h_out_vol; p.h_maxl = h_out_max_l; p.h_mid = h_out_mid_p;
         p.aux_w = 6;
         p.process_mode = true; p.point_num = point_num; p.mt_key = mt_key; p.mt_pos = &pos; p.h_pc = h_out_pc;
+        p.focal64 = focal;
         p.configure();
         rc2 = p.run();
         *mt_pos = pos;

@@ -26,6 +26,11 @@ struct BatchArgs {
     const float*     joints;     // [n][63] ground-truth joints to normalise in the same launch, or nullptr
     float*           out_joints; // [n][63]
     int              joint_flags; // bit 0: clamp to [0,1]; bit 1: negate z first (3D_CNN/dataset.py:107)
+    // bbox_mode 3 (DTSDF_BBOX_SAMPLED, DataProcess.process() in one launch): the bounding box is that of the
+    // point cloud resampled by the caller's index vectors (pre/process.py:30-84,102-120), float64
+    const int*       sample_idx = nullptr;   // [n][point_num] ranks into each frame's valid pixels (row-major order)
+    int              point_num = 0;
+    double           focal64 = 0.0;          // the focal length of the float64 back-projection (pre/process.py:9)
 };
 
 // Picks the staging capacity / grid and launches the fused kernel.  Returns a cudaError_t.
@@ -36,6 +41,10 @@ cudaError_t launch_voxelize(int voxel_res, int layout, BatchArgs args, int max_c
 // aug: [n][21] = A (3x3 row-major), Ainv, c.
 cudaError_t launch_voxelize_aug(int voxel_res, int layout, BatchArgs args, const float* aug, int max_crop_px,
                                 cudaStream_t stream);
+
+// n_valid[i] = pixels of crop i with d != 0 (the rows pre/process.py:61-66 keeps)
+cudaError_t launch_count_valid(int n_frames, const float* depth, const long long* offsets, const int* headers,
+                               int* n_valid, cudaStream_t stream);
 
 cudaError_t launch_point_cloud(int n_frames, double focal, const float* depth,
                                const long long* offsets, const int* headers, double* points,

@@ -320,6 +320,269 @@ __device__ __forceinline__ bool sanitize_crop(float* crop_s, int n_pad) {
     return t != t;
 }
 
+// ---------------------------------------------------------------- sampled bounding box (DTSDF_BBOX_SAMPLED)
+// DataProcess.process() without ever materialising a cloud (pre/process.py:13-28): the bounding box of
+// hand_points[rand_idx] where hand_points are the back-projected pixels with d != 0 in row-major order
+// (pre/process.py:30-68, float64) and rand_idx the caller's index vector (:70-84).
+//   * rank of a pixel = number of valid pixels before it: counts per contiguous piece of the crop, one block
+//     scan, then ballot / popc within a warp step;
+//   * the sampled ranks are a bitmap in shared memory (one atomicOr per index; ranks beyond the bitmap are
+//     handled by further windows over the same data - not needed below 43,008 valid pixels at R = 32);
+//   * X = RN64(P / f) with P = RN64(u * d), u = (col + left) - w/2, is monotone in P, Y = RN64(-Q / f) in
+//     Q = RN64(v * d), v = (row + top) - h/2, and float32 rounding is monotone too: the per-axis extremes over the
+//     sample (pre/process.py:102-120) are those of P, Q and d, compared as order-preserving integers (-0 < +0,
+//     like the FMNMX of resample_extrema_kernel); NaNs are skipped as fminf/fmaxf skip them.  FOUR float64
+//     divisions per frame remain.
+//   * sampled_bbox_fast: P is monotone in d within a column and Q within a row, so per sampled pixel only the
+//     depth is compared - four shared-memory atomics on its ordered bits (column min/max, row min/max), no
+//     float64 in the loop; u * d and v * d are formed for the column / row extremes only.  This needs finite
+//     depths (0 * inf = NaN would hide a column's finite pixels) and a crop of at most COLCAP x ROWCAP pixels
+//     (the MSRA image is 320 x 240);
+//   * sampled_bbox_general: any other frame; every sampled pixel is multiplied out in float64.
+// Result in shared memory (FrameShared::red[0]): {max x, y, z, min x, y, z} - what resample_extrema_kernel
+// produces from the materialised cloud, bit for bit.  Scratch is the projection-table area of FrameShared (not
+// yet in use).
+__device__ __forceinline__ long long dkey(double x) {
+    const long long b = __double_as_longlong(x);
+    return b ^ ((b >> 63) & 0x7fffffffffffffffll);            // an involution
+}
+__device__ __forceinline__ double dkey_inv(long long k) { return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffll)); }
+__device__ __forceinline__ int fkey(float x) {
+    const int b = __float_as_int(x);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float fkey_inv(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
+constexpr int COLCAP = 320, ROWCAP = 240;
+constexpr int KEY_MAX = 0x7fffffff, KEY_MIN = -0x7fffffff - 1;
+
+template <int NW>
+struct SampledScratch {
+    long long kred[NW][4];        // per warp: min P, max P, min Q, max Q
+    float     fred[NW][2];        // per warp: min d, max d
+    int       wsum[NW];
+    int       flag[NW];           // per warp: its piece holds an infinite depth
+    int       colmin[COLCAP], colmax[COLCAP];     // ordered bits of the smallest / largest sampled depth per column
+    int       rowmin[ROWCAP], rowmax[ROWCAP];     // ... per row
+    unsigned  bitmap[1];          // ... to the end of the scratch area
+};
+
+struct KeyRange {
+    long long pmin, pmax, qmin, qmax;
+    float dmin, dmax;
+    __device__ __forceinline__ void init() {
+        pmin = qmin = 0x7fffffffffffffffll;
+        pmax = qmax = -0x7fffffffffffffffll - 1;
+        dmin = INFINITY; dmax = -INFINITY;
+    }
+    __device__ __forceinline__ void p(double P) { if (P == P) { const long long k = dkey(P); pmin = min(pmin, k); pmax = max(pmax, k); } }
+    __device__ __forceinline__ void q(double Q) { if (Q == Q) { const long long k = dkey(Q); qmin = min(qmin, k); qmax = max(qmax, k); } }
+};
+
+// block reduction of the per-thread ranges and the four divisions; ends with a barrier
+template <int NW>
+__device__ __forceinline__ void sampled_finish(KeyRange kr, SampledScratch<NW>* sc, float* out6, double focal) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kr.pmin = min(kr.pmin, __shfl_xor_sync(FULL, kr.pmin, o)); kr.pmax = max(kr.pmax, __shfl_xor_sync(FULL, kr.pmax, o));
+        kr.qmin = min(kr.qmin, __shfl_xor_sync(FULL, kr.qmin, o)); kr.qmax = max(kr.qmax, __shfl_xor_sync(FULL, kr.qmax, o));
+    }
+    const float dmin = warp_min(kr.dmin), dmax = warp_max(kr.dmax);
+    if (lane == 0) {
+        sc->kred[warp][0] = kr.pmin; sc->kred[warp][1] = kr.pmax; sc->kred[warp][2] = kr.qmin; sc->kred[warp][3] = kr.qmax;
+        sc->fred[warp][0] = dmin; sc->fred[warp][1] = dmax;
+    }
+    __syncthreads();
+    if (tid < 4) {
+        // tid 0: max x (largest P)  1: min x (smallest P)  2: max y (smallest Q, negated)  3: min y (largest Q, negated)
+        const int pair = tid < 2 ? 0 : 2;
+        long long kmn = sc->kred[0][pair], kmx = sc->kred[0][pair + 1];
+        for (int i = 1; i < NW; ++i) { kmn = min(kmn, sc->kred[i][pair]); kmx = max(kmx, sc->kred[i][pair + 1]); }
+        const bool is_max = tid == 0 || tid == 2;
+        float v = is_max ? -INFINITY : INFINITY;             // an empty sample leaves the fminf / fmaxf identities
+        if (kmn <= kmx) {
+            const double num = tid == 0 ? dkey_inv(kmx) : (tid == 1 ? dkey_inv(kmn) : (tid == 2 ? -dkey_inv(kmn) : -dkey_inv(kmx)));
+            v = __double2float_rn(__ddiv_rn(num, focal));
+        }
+        out6[(is_max ? 0 : 3) + (tid >> 1)] = v;             // {max x, max y, max z, min x, min y, min z}
+    } else if (tid == 4) {
+        float lo = sc->fred[0][0], hi = sc->fred[0][1];
+        for (int i = 1; i < NW; ++i) { lo = fminf(lo, sc->fred[i][0]); hi = fmaxf(hi, sc->fred[i][1]); }
+        out6[2] = -lo;            // max z = -(min d)
+        out6[5] = -hi;
+    }
+    __syncthreads();
+}
+
+// marks the ranks [w0, w0 + wn) that the index vector holds; eight loads in flight per thread
+template <int NTH>
+__device__ __forceinline__ void mark_samples(const int* __restrict__ idx, int point_num, int w0, int wn, unsigned* bitmap) {
+    for (int k0 = threadIdx.x; k0 < point_num; k0 += 8 * NTH) {
+        int v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = k0 + j * NTH < point_num ? __ldg(idx + k0 + j * NTH) : -1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned r = (unsigned)(v[j] - w0);                    // out-of-range indices set nothing
+            if (v[j] >= 0 && r < (unsigned)wn) atomicOr(&bitmap[r >> 5], 1u << (r & 31));
+        }
+    }
+}
+
+// returns false (CTA-uniform, nothing written) when the crop holds an infinite depth
+template <int NW, bool SMEM, int CROP_OFF, int OUT6_OFF, int CAP_BITS>
+__device__ __noinline__ bool sampled_bbox_fast(const float* __restrict__ crop_g, int n, int bw, int bh,
+                                               int l, int t, int w, int h, double focal,
+                                               const int* __restrict__ idx, int point_num) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NTH = 32 * NW;
+    SampledScratch<NW>* sc = reinterpret_cast<SampledScratch<NW>*>(smem_raw);
+    const float* crop = SMEM ? reinterpret_cast<const float*>(smem_raw + CROP_OFF) : crop_g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int c = tid; c < COLCAP; c += NTH) { sc->colmin[c] = KEY_MAX; sc->colmax[c] = KEY_MIN; }
+    for (int c = tid; c < ROWCAP; c += NTH) { sc->rowmin[c] = KEY_MAX; sc->rowmax[c] = KEY_MIN; }
+    // a warp owns one contiguous piece of the crop, a whole number of 32-pixel steps
+    const int S = ((n + NTH - 1) / NTH) * 32;
+    const int s0 = min(n, warp * S), s1 = min(n, s0 + S);
+    int cnt = 0;
+    float amax = 0.0f;
+#pragma unroll 4
+    for (int q = s0; q < s1; q += 32) {
+        const int p = q + lane;
+        const float d = p < s1 ? (SMEM ? crop[p] : __ldg(crop + p)) : 0.0f;
+        cnt += d != 0.0f;
+        amax = fmaxf(amax, fabsf(d));                          // (skips NaN)
+    }
+    cnt = __reduce_add_sync(FULL, cnt);
+    const unsigned anyinf = __ballot_sync(FULL, amax == INFINITY);
+    if (lane == 0) { sc->wsum[warp] = cnt; sc->flag[warp] = anyinf != 0u; }
+    __syncthreads();
+    int base = 0, total = 0, inf = 0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const int c = sc->wsum[i];
+        if (i < warp) base += c;
+        total += c;
+        inf |= sc->flag[i];
+    }
+    if (inf) return false;
+    for (int w0 = 0; w0 < total; w0 += CAP_BITS) {
+        const int wn = min(CAP_BITS, total - w0);
+        for (int i = tid; i < (wn + 31) / 32; i += NTH) sc->bitmap[i] = 0u;
+        __syncthreads();
+        mark_samples<NTH>(idx, point_num, w0, wn, sc->bitmap);
+        __syncthreads();
+        if (base < w0 + wn && base + cnt > w0) {               // warp-uniform
+            int rb = base - w0;
+            int row = (s0 + lane) / bw, col = (s0 + lane) - row * bw;
+#pragma unroll 2
+            for (int q = s0; q < s1; q += 32) {
+                const int p = q + lane;
+                const float d = p < s1 ? (SMEM ? crop[p] : __ldg(crop + p)) : 0.0f;
+                const bool valid = d != 0.0f;
+                const unsigned bal = __ballot_sync(FULL, valid);
+                const int r = rb + __popc(bal & lt);
+                rb += __popc(bal);
+                const bool inwin = valid && (unsigned)r < (unsigned)wn;
+                const unsigned word = inwin ? sc->bitmap[r >> 5] : 0u;
+                if (((word >> (r & 31)) & 1u) && d == d) {
+                    const int k = fkey(d);
+                    atomicMin(&sc->colmin[col], k); atomicMax(&sc->colmax[col], k);
+                    atomicMin(&sc->rowmin[row], k); atomicMax(&sc->rowmax[row], k);
+                }
+                col += 32;
+                while (col >= bw) { col -= bw; ++row; }
+            }
+        }
+        __syncthreads();
+    }
+    KeyRange kr;
+    kr.init();
+    const double half_w = (double)w / 2.0, half_h = (double)h / 2.0;
+    for (int c = tid; c < bw; c += NTH) {
+        const int klo = sc->colmin[c], khi = sc->colmax[c];
+        if (klo <= khi) {
+            const double u = ((double)c + (double)l) - half_w;
+            kr.p(__dmul_rn(u, (double)fkey_inv(klo))); kr.p(__dmul_rn(u, (double)fkey_inv(khi)));
+        }
+    }
+    for (int c = tid; c < bh; c += NTH) {
+        const int klo = sc->rowmin[c], khi = sc->rowmax[c];
+        if (klo <= khi) {
+            const double v = ((double)c + (double)t) - half_h;
+            const float lo = fkey_inv(klo), hi = fkey_inv(khi);
+            kr.q(__dmul_rn(v, (double)lo)); kr.q(__dmul_rn(v, (double)hi));
+            kr.dmin = fminf(kr.dmin, lo); kr.dmax = fmaxf(kr.dmax, hi);
+        }
+    }
+    sampled_finish<NW>(kr, sc, reinterpret_cast<float*>(smem_raw + OUT6_OFF), focal);
+    return true;
+}
+
+// any shape, any depth: every thread owns one contiguous run of the crop (odd length: the strided shared-memory
+// reads are conflict-free) and multiplies its sampled pixels out
+template <int NW, bool SMEM, int CROP_OFF, int OUT6_OFF, int CAP_BITS>
+__device__ __noinline__ void sampled_bbox_general(const float* __restrict__ crop_g, int n, int bw,
+                                                  int l, int t, int w, int h, double focal,
+                                                  const int* __restrict__ idx, int point_num) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NTH = 32 * NW;
+    SampledScratch<NW>* sc = reinterpret_cast<SampledScratch<NW>*>(smem_raw);
+    const float* crop = SMEM ? reinterpret_cast<const float*>(smem_raw + CROP_OFF) : crop_g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = ((n + NTH - 1) / NTH) | 1;
+    const int p0 = min(n, tid * L), p1 = min(n, p0 + L);
+    int cnt = 0;
+    for (int p = p0; p < p1; ++p) cnt += (SMEM ? crop[p] : __ldg(crop + p)) != 0.0f;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += v;
+    }
+    __syncthreads();                                           // (the fast attempt's readers of wsum are done)
+    if (lane == 31) sc->wsum[warp] = inc;
+    __syncthreads();
+    int base = inc - cnt, total = 0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const int c = sc->wsum[i];
+        if (i < warp) base += c;
+        total += c;
+    }
+    KeyRange kr;
+    kr.init();
+    const double half_w = (double)w / 2.0, half_h = (double)h / 2.0;
+    for (int w0 = 0; w0 < total; w0 += CAP_BITS) {
+        const int wn = min(CAP_BITS, total - w0);
+        for (int i = tid; i < (wn + 31) / 32; i += NTH) sc->bitmap[i] = 0u;
+        __syncthreads();
+        mark_samples<NTH>(idx, point_num, w0, wn, sc->bitmap);
+        __syncthreads();
+        if (base < w0 + wn && base + cnt > w0) {
+            int r = base - w0;
+            int row = p0 / bw, col = p0 - row * bw;
+            for (int p = p0; p < p1; ++p) {
+                const float d = SMEM ? crop[p] : __ldg(crop + p);
+                if (d != 0.0f) {
+                    if ((unsigned)r < (unsigned)wn && ((sc->bitmap[r >> 5] >> (r & 31)) & 1u)) {
+                        const double dd = (double)d;
+                        kr.p(__dmul_rn(((double)col + (double)l) - half_w, dd));
+                        kr.q(__dmul_rn(((double)row + (double)t) - half_h, dd));
+                        kr.dmin = fminf(kr.dmin, d); kr.dmax = fmaxf(kr.dmax, d);
+                    }
+                    ++r;
+                }
+                if (++col == bw) { col = 0; ++row; }
+            }
+        }
+        __syncthreads();
+    }
+    sampled_finish<NW>(kr, sc, reinterpret_cast<float*>(smem_raw + OUT6_OFF), focal);
+}
+
 // ---------------------------------------------------------------- voxel evaluation
 struct Tsdf3 { float x, y, z; };
 
@@ -808,6 +1071,9 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     const float yf = __frcp_rn(a.focal);
     const bool focal_ok = a.focal >= 0x1p-30f && a.focal <= 0x1p30f;
     const bool scan = a.bbox_mode == 0;              // DTSDF_BBOX_PIXELS
+    const bool sampled = a.bbox_mode == 3;           // DTSDF_BBOX_SAMPLED
+    constexpr unsigned SCRATCH_BITS = (unsigned)((offsetof(FS, vx) - offsetof(SampledScratch<NW>, bitmap)) * 8);
+    static_assert(offsetof(FS, at) == 0 && offsetof(FS, vx) > offsetof(SampledScratch<NW>, bitmap) + 1024, "scratch overlays the tables");
     const bool scan_exact = !(DEFF || focal_ok);     // no proven fixed-divisor form for this focal
     __syncthreads();                                  // the mbarrier is initialised
 
@@ -817,12 +1083,33 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     bool sawnan = false;
     if (fr.staged) {
         mbar_wait(&sh->bar, 0);
+        if (sampled) {       // (ends with a barrier: every thread is done reading the crop before it is sanitised)
+            const int iw = __ldg(a.headers + 6 * (size_t)f), ih = __ldg(a.headers + 6 * (size_t)f + 1);
+            const int* idx = a.sample_idx + (size_t)f * a.point_num;
+            bool done = false;
+            if (fr.bw <= COLCAP && fr.bh <= ROWCAP)
+                done = sampled_bbox_fast<NW, true, (int)sizeof(FS), (int)offsetof(FS, red), (int)SCRATCH_BITS>(
+                    nullptr, fr.n, fr.bw, fr.bh, fr.l, fr.t, iw, ih, a.focal64, idx, a.point_num);
+            if (!done)
+                sampled_bbox_general<NW, true, (int)sizeof(FS), (int)offsetof(FS, red), (int)SCRATCH_BITS>(
+                    nullptr, fr.n, fr.bw, fr.l, fr.t, iw, ih, a.focal64, idx, a.point_num);
+        }
         if (!scan)           sawnan = sanitize_crop<NW>(crop_s, fr.n_pad);
         else if (scan_exact) sawnan = bbox_partial<DEFF, true, true, NW>(fr, crop_s, a, yf, sh->red);
         else                 sawnan = bbox_partial<DEFF, false, true, NW>(fr, crop_s, a, yf, sh->red);
     } else if (scan) {
         if (scan_exact) bbox_partial<DEFF, true, false, NW>(fr, const_cast<float*>(fr.crop), a, yf, sh->red);
         else            bbox_partial<DEFF, false, false, NW>(fr, const_cast<float*>(fr.crop), a, yf, sh->red);
+    } else if (sampled) {
+        const int iw = __ldg(a.headers + 6 * (size_t)f), ih = __ldg(a.headers + 6 * (size_t)f + 1);
+        const int* idx = a.sample_idx + (size_t)f * a.point_num;
+        bool done = false;
+        if (fr.bw <= COLCAP && fr.bh <= ROWCAP)
+            done = sampled_bbox_fast<NW, false, (int)sizeof(FS), (int)offsetof(FS, red), (int)SCRATCH_BITS>(
+                fr.crop, fr.n, fr.bw, fr.bh, fr.l, fr.t, iw, ih, a.focal64, idx, a.point_num);
+        if (!done)
+            sampled_bbox_general<NW, false, (int)sizeof(FS), (int)offsetof(FS, red), (int)SCRATCH_BITS>(
+                fr.crop, fr.n, fr.bw, fr.l, fr.t, iw, ih, a.focal64, idx, a.point_num);
     }
     if (sawnan) sh->nanflag = 1u;
     __syncthreads();      // (A) bbox partials, sanitised crop and the NaN flag are in
@@ -860,6 +1147,10 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
                 __syncthreads();
                 bbox_reduce<NW>(sh->red, mn, mx);
             }
+        } else if (sampled) {     // DTSDF_BBOX_SAMPLED: the same six numbers, just reduced in shared memory
+            const float* g = &sh->red[0][0];
+            mx[0] = g[0]; mx[1] = g[1]; mx[2] = g[2];
+            mn[0] = g[3]; mn[1] = g[4]; mn[2] = g[5];
         } else {                  // DTSDF_BBOX_EXTREMA: {max xyz, min xyz}, pre/process.py:120
             const float* g = a.aux + 6 * (size_t)f;
             mx[0] = __ldg(g); mx[1] = __ldg(g + 1); mx[2] = __ldg(g + 2);
@@ -1042,6 +1333,35 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     kern<<<(unsigned)args.n_frames * CtaShape<R, LAYOUT>::SPLIT, (32 * NW), smem, stream>>>(args);   // SPLIT CTAs per frame
     ++g_launch_count;
     return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- valid-pixel count
+// n_valid[f] = pixels with d != 0 (the rows pre/process.py:61-66 keeps): what the caller needs to draw the
+// resampling indices (pre/process.py:70-84) before the sampled launch.  One CTA per frame, 128-bit loads.
+__global__ void __launch_bounds__(NT) count_valid_kernel(const float* __restrict__ depth,
+                                                         const long long* __restrict__ offsets,
+                                                         const int* __restrict__ headers, int* __restrict__ n_valid) {
+    __shared__ int wsum[NWARP];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* h = headers + 6 * (size_t)f;
+    const int bw = h[4] - h[2], bh = h[5] - h[3];
+    const int n = (bw > 0 && bh > 0) ? bw * bh : 0;
+    const float* crop = depth + offsets[f];                  // 16-byte aligned (packed batch format)
+    int cnt = 0;
+    for (int i = tid; i < (n >> 2); i += NT) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(crop) + i);
+        cnt += (v.x != 0.0f) + (v.y != 0.0f) + (v.z != 0.0f) + (v.w != 0.0f);
+    }
+    if (tid < (n & 3)) cnt += __ldg(crop + (n & ~3) + tid) != 0.0f;
+    cnt = __reduce_add_sync(FULL, cnt);
+    if (lane == 0) wsum[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < NWARP; ++i) s += wsum[i];
+        n_valid[f] = s;
+    }
 }
 
 // ---------------------------------------------------------------- point cloud (f64)
@@ -1648,6 +1968,15 @@ cudaError_t launch_voxelize_aug(int voxel_res, int layout, BatchArgs args, const
         case 64: return layout == 0 ? launch_aug_t<64, 0>(args, aug, max_crop_px, stream) : launch_aug_t<64, 1>(args, aug, max_crop_px, stream);
         default: return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_count_valid(int n_frames, const float* depth, const long long* offsets, const int* headers,
+                               int* n_valid, cudaStream_t stream) {
+    if (n_frames <= 0) return cudaSuccess;
+    if ((reinterpret_cast<uintptr_t>(depth) & 15) != 0) return cudaErrorMisalignedAddress;
+    count_valid_kernel<<<n_frames, NT, 0, stream>>>(depth, offsets, headers, n_valid);
+    ++g_launch_count;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_point_cloud(int n_frames, double focal, const float* depth,

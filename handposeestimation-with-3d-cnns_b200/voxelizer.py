@@ -507,6 +507,49 @@ def voxelize_device(depth_packed, offsets, headers, max_crop_px=0, cfg=None, aux
     return out_vol, out_max_l, out_mid_p
 
 
+def count_valid_device(depth_packed, offsets, headers, out=None, stream=None):
+    """``dtsdf_count_valid_batch``: int32[n] pixels with d != 0 per frame (``hand_points.shape[0]`` of
+    pre/process.py:70-73), asynchronous on torch's current stream."""
+    import torch
+    assert depth_packed.is_cuda and offsets.dtype == torch.int64 and headers.dtype == torch.int32
+    n = int(headers.shape[0])
+    if out is None:
+        out = torch.empty((n,), dtype=torch.int32, device=depth_packed.device)
+    with torch.cuda.device(depth_packed.device):
+        check(load_library().dtsdf_count_valid_batch(n, depth_packed.data_ptr(), offsets.data_ptr(), headers.data_ptr(),
+                                                     out.data_ptr(), _torch_stream_ptr(stream)))
+    return out
+
+
+def voxelize_sampled_device(depth_packed, offsets, headers, sample_idx, max_crop_px=0, cfg=None, focal=FOCAL,
+                            out_vol=None, out_max_l=None, out_mid_p=None, stream=None):
+    """``dtsdf_voxelize_sampled_batch``: ``DataProcess.process()`` (pre/process.py:13-28) for a batch in one launch,
+    without the clouds.  ``sample_idx`` int32[n, point_num]: every frame's ``rand_idx`` (pre/process.py:75-80).
+    Returns (vol, max_l, mid_p) like ``voxelize_device``."""
+    import torch
+    if not (depth_packed.is_cuda and offsets.is_cuda and headers.is_cuda and sample_idx.is_cuda):
+        raise RuntimeError("voxelize_sampled_device needs CUDA tensors; there is no CPU fallback")
+    assert depth_packed.dtype == torch.float32 and offsets.dtype == torch.int64 and headers.dtype == torch.int32
+    assert sample_idx.dtype == torch.int32 and sample_idx.is_contiguous() and sample_idx.dim() == 2
+    cfg = cfg or capi.default_config()
+    n = int(headers.shape[0])
+    assert int(sample_idx.shape[0]) == n
+    R = int(cfg.voxel_res)
+    dev = depth_packed.device
+    if out_vol is None:
+        out_vol = torch.empty((n, 3, R, R, R), dtype=torch.float32, device=dev)
+    if out_max_l is None:
+        out_max_l = torch.empty((n,), dtype=torch.float32, device=dev)
+    if out_mid_p is None:
+        out_mid_p = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(load_library().dtsdf_voxelize_sampled_batch(
+            ctypes.byref(cfg), float(focal), n, depth_packed.data_ptr(), offsets.data_ptr(), headers.data_ptr(),
+            sample_idx.data_ptr(), int(sample_idx.shape[1]), int(max_crop_px), out_vol.data_ptr(), out_max_l.data_ptr(),
+            out_mid_p.data_ptr(), _torch_stream_ptr(stream)))
+    return out_vol, out_max_l, out_mid_p
+
+
 def normalize_joints_device(joints, max_l, mid_p, clamp01=True, out=None, stream=None):
     """``dtsdf_normalize_joints_batch`` on torch CUDA tensors (3D_CNN/train.py:236-244)."""
     import torch

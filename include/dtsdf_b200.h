@@ -76,6 +76,8 @@ extern "C" {
                                  result of max_min_point(): pre/process.py:102-120, pre/tsdf_for.py:23-41 */
 #define DTSDF_BBOX_GRID    2  /* caller gives aux[i] = {vox_ori_x,y,z, voxel_len, trunc}: the arguments
                                  of DataProcess.tsdf_cal(): pre/process.py:122 */
+#define DTSDF_BBOX_SAMPLED 3  /* the box of the point cloud resampled by the caller's index vectors, found inside the
+                                 voxeliser launch: only through dtsdf_voxelize_sampled_batch / dtsdf_process_host */
 
 typedef struct dtsdf_config {
     int32_t voxel_res;   /* R: 32 (pre/process.py:88), 48 or 64 */
@@ -158,6 +160,28 @@ int dtsdf_voxelize_joints_batch(const dtsdf_config* cfg, int32_t n_frames,
                                 const float* d_joints, int32_t joint_flags,
                                 float* d_out_vol, float* d_out_max_l, float* d_out_mid_p,
                                 float* d_out_joints, void* stream);
+
+/* DataProcess(frame, gt, point_num).process() of pre/process.py:13-28 in ONE launch, when the sampled point cloud
+ * itself is not wanted: hand_points = the back-projected pixels with d != 0 in row-major order (float64,
+ * point_cloud(), :30-68); point_clouds = hand_points[rand_idx] (set_length, :70-84); bounding box of
+ * point_clouds rounded to float32 (max_min_point, :102-120); grid parameters and voxel loop (tsdf_f / tsdf_cal,
+ * :86-100,122-200).  Neither cloud is ever written: the kernel ranks the valid pixels of the staged crop, marks
+ * the sampled ranks in a shared-memory bitmap and reduces the extrema of the sample from the depth map itself.
+ * Equal, bit for bit, to dtsdf_point_cloud_batch + dtsdf_resample_extrema_batch + dtsdf_voxelize_batch(EXTREMA).
+ *   focal          float64 focal length of the back-projection (241.42, pre/process.py:9); cfg->focal is the
+ *                  voxel loop's float32 one (pre/process.py:132)
+ *   d_sample_idx   int32[n][point_num]: rand_idx of every frame, each in [0, n_valid_i) (others select nothing)
+ * cfg->bbox_mode is ignored.  The image size w, h of the back-projection comes from each header.
+ *
+ * dtsdf_count_valid_batch: d_out_n_valid[i] = number of pixels with d != 0 - hand_points.shape[0], the upper
+ * bound of the draws of set_length - so that the caller can draw rand_idx before the launch. */
+int dtsdf_count_valid_batch(int32_t n_frames, const float* d_depth_packed, const int64_t* d_crop_offsets,
+                            const int32_t* d_headers, int32_t* d_out_n_valid, void* stream);
+int dtsdf_voxelize_sampled_batch(const dtsdf_config* cfg, double focal, int32_t n_frames,
+                                 const float* d_depth_packed, const int64_t* d_crop_offsets,
+                                 const int32_t* d_headers, const int32_t* d_sample_idx, int32_t point_num,
+                                 int32_t max_crop_px, float* d_out_vol, float* d_out_max_l,
+                                 float* d_out_mid_p, void* stream);
 
 /* Augmented D-TSDF for training-time augmentation.  Every frame gets its
  * own affine map p' = (p - c) . A + c (row vector times matrix, A = stretch . rotation as in
@@ -363,8 +387,9 @@ int dtsdf_resample_indices(uint32_t* mt_key, int32_t* mt_pos, int32_t n_frames, 
  * frame loop of read_MSRA.main(), pre/read_MSRA.py:98-111): point clouds on the device, resampling indices
  * drawn here from the caller's MT19937 state chunk by chunk while earlier chunks are on the GPU, gather +
  * extrema + fused voxeliser per chunk, volumes back through the packed transfer of dtsdf_voxelize_host.
- *   h_out_pc   double[n][point_num][3] or NULL (the sampled clouds are not brought back)
- * cfg->bbox_mode is ignored (EXTREMA).  Equal to dtsdf_process_begin_host + np.random draws +
+ *   h_out_pc   double[n][point_num][3] or NULL: the sampled clouds are not brought back - and then never built:
+ *              the batch goes through dtsdf_count_valid_batch + dtsdf_voxelize_sampled_batch
+ * cfg->bbox_mode is ignored.  Equal to dtsdf_process_begin_host + np.random draws +
  * dtsdf_process_finish_host, bit for bit, state of the stream included. */
 int dtsdf_process_host(dtsdf_ctx* ctx, const dtsdf_config* cfg, double focal, int32_t n_frames,
                        const float* h_depth_packed, int64_t packed_len,

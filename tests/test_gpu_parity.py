@@ -183,6 +183,88 @@ def test_process_host_one_call_equals_per_frame_numpy_draws():
     v.close()
 
 
+def _sampled_case_frames():
+    """Hands, frames that look nothing like a hand (boxes partly outside the image, holes, values straddling
+    |d| = 1, negative depths), NaN and huge depths, mixed signs in the centre column / row (products of either
+    zero), a full 320x240 frame (not staged in shared memory), 1-pixel crops and a 1-pixel-wide one."""
+    rng = np.random.default_rng(2024)
+    frames = synth.make_frames(range(1500, 1512)) + _random_frames(rng, 40)
+    f = synth.make_frame(7)
+    d = f["depth"].copy()
+    d[rng.integers(0, d.size, 30)] = np.nan
+    d[rng.integers(0, d.size, 30)] = 3e12
+    d[rng.integers(0, d.size, 30)] = -450.0
+    d[rng.integers(0, d.size, 30)] = 0.25                      # a point of the cloud, no depth for the voxel loop
+    frames.append({"header": f["header"], "depth": d})
+    yy, xx = np.mgrid[0:40, 0:60].astype(np.float32)           # box around the principal point, depth changing sign
+    d = np.where((xx + yy) % 3 == 0, -300.0 - xx, 280.0 + yy).astype(np.float32)
+    frames.append({"header": np.array([320, 240, 130, 100, 190, 140], np.int32), "depth": d.reshape(-1)})
+    frames.append(synth.make_frame(1, box=(0, 0, 320, 240)))
+    frames.append({"header": np.array([320, 240, 17, 33, 18, 34], np.int32), "depth": np.array([412.5], np.float32)})
+    frames.append({"header": np.array([320, 240, 200, 10, 201, 110], np.int32),
+                   "depth": rng.uniform(300, 500, size=100).astype(np.float32)})
+    frames.append({"header": np.array([321, 239, 100, 50, 160, 120], np.int32),      # odd image size: half-integer u, v
+                   "depth": rng.uniform(200, 600, size=60 * 70).astype(np.float32)})
+    return frames
+
+
+@pytest.mark.parametrize("R,layout", [(32, 0), (32, 1), (48, 0), (64, 1)])
+def test_sampled_voxeliser_equals_the_cloud_path(R, layout):
+    """DTSDF_BBOX_SAMPLED (dtsdf_count_valid_batch + dtsdf_voxelize_sampled_batch: ranks, sample bitmap and
+    extrema inside the voxeliser launch, no cloud in memory) against the three-kernel form that materialises
+    float64 clouds (dtsdf_process_begin_host / _finish_host) for the same index vectors, bit for bit; and,
+    on frames without NaN depths, against the NumPy restatement of point_cloud / set_length / max_min_point
+    (pre/process.py:30-84,102-120) followed by the C oracle's voxel loop."""
+    import torch
+    v = pkg.Voxelizer(device=0, voxel_res=R)
+    frames = _sampled_case_frames()
+    n_valid = v.process_begin(frames)
+    for f, nv in zip(frames, n_valid):
+        d = np.asarray(f["depth"])
+        assert nv == int(np.count_nonzero(d != 0))             # NaN != 0: a row any() keeps (pre/process.py:63)
+    frames = [f for f, nv in zip(frames, n_valid) if nv > 0]
+    n_valid = v.process_begin(frames)
+    n = len(frames)
+    rng = np.random.default_rng(R + layout)
+    for point_num in (6000, 37):
+        idx = np.empty((n, point_num), np.int32)
+        for i, nv in enumerate(n_valid):
+            if nv < point_num:                                  # pre/process.py:74-77
+                idx[i] = np.arange(point_num)
+                idx[i, nv:] = rng.integers(0, nv, size=point_num - nv)
+            else:
+                idx[i] = rng.integers(0, nv, size=point_num)
+        pcs, want_vol, want_ml, want_mp = v.process_finish(idx, point_num, True, layout, R)
+        headers, offsets, packed, max_px = pkg.pack_frames(frames)
+        dev = torch.device("cuda:0")
+        args = (torch.from_numpy(packed).to(dev), torch.from_numpy(offsets).to(dev), torch.from_numpy(headers).to(dev))
+        assert np.array_equal(pkg.count_valid_device(*args).cpu().numpy(), n_valid)
+        cfg = pkg.capi.default_config(R, layout, pkg.BBOX_PIXELS)
+        for hint in (max_px, 64):                               # 64: nothing fits the staging buffer
+            vol, ml, mp = pkg.voxelize_sampled_device(*args, torch.from_numpy(idx).to(dev), hint, cfg)
+            torch.cuda.synchronize()
+            assert _same(ml.cpu().numpy(), want_ml) and _same(mp.cpu().numpy(), want_mp)
+            got = vol.cpu().numpy()
+            for i in range(n):
+                assert _same(got[i], want_vol[i]), "frame %d hint %d" % (i, hint)
+        # the restatement of the reference's own steps
+        aux = np.zeros((n, 6), np.float32)
+        clean = []
+        for i, f in enumerate(frames):
+            d = np.asarray(f["depth"])
+            if np.isnan(d).any():
+                continue
+            pc = orc.point_cloud(f["header"], d)[idx[i]]
+            assert np.array_equal(pc, pcs[i])
+            pmax, pmin = orc.max_min_point(pc)
+            aux[i, :3], aux[i, 3:] = pmax, pmin
+            clean.append(i)
+        cv, cml, cmp_, _ = c_oracle.dtsdf_batch(headers, offsets, packed, R=R, layout=layout, bbox_mode=1, aux=aux)
+        for i in clean:
+            assert _same(got[i], cv[i]) and _same(want_ml[i], cml[i]) and _same(want_mp[i], cmp_[i]), "oracle frame %d" % i
+    v.close()
+
+
 def test_tsdf_for_module(forloop_golden):
     tsdf_for = import_pre("tsdf_for")
     c = forloop_golden[3]
