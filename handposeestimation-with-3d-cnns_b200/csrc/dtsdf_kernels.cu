@@ -417,11 +417,11 @@ __device__ __forceinline__ void sampled_finish(KeyRange kr, SampledScratch<NW>* 
 
 // marks the ranks [w0, w0 + wn) that the index vector holds; eight loads in flight per thread
 template <int NTH>
-__device__ __forceinline__ void mark_samples(const int* __restrict__ idx, int point_num, int w0, int wn, unsigned* bitmap) {
+__device__ __forceinline__ void mark_samples(const int* idx, int point_num, int w0, int wn, unsigned* bitmap) {
     for (int k0 = threadIdx.x; k0 < point_num; k0 += 8 * NTH) {
         int v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = k0 + j * NTH < point_num ? __ldg(idx + k0 + j * NTH) : -1;
+        for (int j = 0; j < 8; ++j) v[j] = k0 + j * NTH < point_num ? idx[k0 + j * NTH] : -1;      // (shared or global)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const unsigned r = (unsigned)(v[j] - w0);                    // out-of-range indices set nothing
@@ -430,19 +430,32 @@ __device__ __forceinline__ void mark_samples(const int* __restrict__ idx, int po
     }
 }
 
-// returns false (CTA-uniform, nothing written) when the crop holds an infinite depth
-template <int NW, bool SMEM, int CROP_OFF, int OUT6_OFF, int CAP_BITS>
+// what sampled_bbox_fast expects to find (the kernel does this while the crop is still on its way, ahead of a
+// barrier it has anyway): empty column / row extremes and a cleared bitmap for the n ranks a crop of n pixels can
+// have (+ two spare words)
+template <int NW>
+__device__ __forceinline__ void sampled_scratch_init(unsigned char* smem_raw, int n) {
+    constexpr int NTH = 32 * NW;
+    SampledScratch<NW>* sc = reinterpret_cast<SampledScratch<NW>*>(smem_raw);
+    for (int c = threadIdx.x; c < COLCAP; c += NTH) { sc->colmin[c] = KEY_MAX; sc->colmax[c] = KEY_MIN; }
+    for (int c = threadIdx.x; c < ROWCAP; c += NTH) { sc->rowmin[c] = KEY_MAX; sc->rowmax[c] = KEY_MIN; }
+    for (int i = threadIdx.x; i < (n + 31) / 32 + 2; i += NTH) sc->bitmap[i] = 0u;
+}
+
+// Needs bw <= COLCAP, bh <= ROWCAP, n + 64 <= CAP_BITS and sampled_scratch_init + a barrier before it.
+// Returns false (CTA-uniform, no result written) when the crop holds an infinite depth.
+template <int NW, bool SMEM, int CROP_OFF, int OUT6_OFF>
 __device__ __noinline__ bool sampled_bbox_fast(const float* __restrict__ crop_g, int n, int bw, int bh,
                                                int l, int t, int w, int h, double focal,
-                                               const int* __restrict__ idx, int point_num) {
+                                               const int* idx, int point_num) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NTH = 32 * NW;
     SampledScratch<NW>* sc = reinterpret_cast<SampledScratch<NW>*>(smem_raw);
     const float* crop = SMEM ? reinterpret_cast<const float*>(smem_raw + CROP_OFF) : crop_g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    for (int c = tid; c < COLCAP; c += NTH) { sc->colmin[c] = KEY_MAX; sc->colmax[c] = KEY_MIN; }
-    for (int c = tid; c < ROWCAP; c += NTH) { sc->rowmin[c] = KEY_MAX; sc->rowmax[c] = KEY_MIN; }
+    // the sampled ranks (all below the number of valid pixels, hence below n; anything else marks nothing)
+    mark_samples<NTH>(idx, point_num, 0, n, sc->bitmap);
     // a warp owns one contiguous piece of the crop, a whole number of 32-pixel steps
     const int S = ((n + NTH - 1) / NTH) * 32;
     const int s0 = min(n, warp * S), s1 = min(n, s0 + S);
@@ -459,41 +472,57 @@ __device__ __noinline__ bool sampled_bbox_fast(const float* __restrict__ crop_g,
     const unsigned anyinf = __ballot_sync(FULL, amax == INFINITY);
     if (lane == 0) { sc->wsum[warp] = cnt; sc->flag[warp] = anyinf != 0u; }
     __syncthreads();
-    int base = 0, total = 0, inf = 0;
+    int base = 0, inf = 0;
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
-        const int c = sc->wsum[i];
-        if (i < warp) base += c;
-        total += c;
+        if (i < warp) base += sc->wsum[i];
         inf |= sc->flag[i];
     }
     if (inf) return false;
-    for (int w0 = 0; w0 < total; w0 += CAP_BITS) {
-        const int wn = min(CAP_BITS, total - w0);
-        for (int i = tid; i < (wn + 31) / 32; i += NTH) sc->bitmap[i] = 0u;
-        __syncthreads();
-        mark_samples<NTH>(idx, point_num, w0, wn, sc->bitmap);
-        __syncthreads();
-        if (base < w0 + wn && base + cnt > w0) {               // warp-uniform
+    {
+        {
+            const int w0 = 0, wn = n;
             int rb = base - w0;
             int row = (s0 + lane) / bw, col = (s0 + lane) - row * bw;
-#pragma unroll 2
-            for (int q = s0; q < s1; q += 32) {
-                const int p = q + lane;
-                const float d = p < s1 ? (SMEM ? crop[p] : __ldg(crop + p)) : 0.0f;
-                const bool valid = d != 0.0f;
-                const unsigned bal = __ballot_sync(FULL, valid);
-                const int r = rb + __popc(bal & lt);
-                rb += __popc(bal);
-                const bool inwin = valid && (unsigned)r < (unsigned)wn;
-                const unsigned word = inwin ? sc->bitmap[r >> 5] : 0u;
-                if (((word >> (r & 31)) & 1u) && d == d) {
-                    const int k = fkey(d);
-                    atomicMin(&sc->colmin[col], k); atomicMax(&sc->colmax[col], k);
-                    atomicMin(&sc->rowmin[row], k); atomicMax(&sc->rowmax[row], k);
+            const bool wide = bw >= 32;                        // a 32-pixel step then crosses at most one row end
+            // four steps per iteration, every load ahead of the atomics that follow (the compiler cannot move
+            // a shared-memory load across them itself): depth, ballot and rank of all four, then the four
+            // bitmap words, then the updates
+            constexpr int U = 4;
+#pragma unroll 1
+            for (int q = s0; q < s1; q += 32 * U) {
+                float d[U];
+                int r[U];
+                unsigned word[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int p = q + 32 * u + lane;
+                    d[u] = p < s1 ? (SMEM ? crop[p] : __ldg(crop + p)) : 0.0f;
                 }
-                col += 32;
-                while (col >= bw) { col -= bw; ++row; }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned bal = __ballot_sync(FULL, d[u] != 0.0f);
+                    r[u] = rb + __popc(bal & lt);
+                    rb += __popc(bal);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool inwin = d[u] != 0.0f && (unsigned)r[u] < (unsigned)wn;
+                    word[u] = inwin ? sc->bitmap[r[u] >> 5] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (((word[u] >> (r[u] & 31)) & 1u) && d[u] == d[u]) {
+                        // (one reduction per row in the warp instead of 32 atomics on the same word was
+                        //  measured: slower, 1.30 vs 1.09 ms per 8,500 frames - same-address shared atomics are cheap)
+                        const int k = fkey(d[u]);
+                        atomicMin(&sc->colmin[col], k); atomicMax(&sc->colmax[col], k);
+                        atomicMin(&sc->rowmin[row], k); atomicMax(&sc->rowmax[row], k);
+                    }
+                    col += 32;
+                    if (wide) { if (col >= bw) { col -= bw; ++row; } }
+                    else      { while (col >= bw) { col -= bw; ++row; } }
+                }
             }
         }
         __syncthreads();
@@ -1038,7 +1067,10 @@ struct CtaShape<48, LAYOUT> {
     static constexpr int SPLIT = 2;
 };
 
-template <int R, int LAYOUT, bool DEFF>
+// SAMPLED: the instantiation that serves DTSDF_BBOX_SAMPLED (and only that mode).  A kernel of its own so that the
+// other modes compile exactly as they would without it - the extra live values and out-of-line calls of the
+// sampled prologue cost the R = 64 kernel 8 % through spills when they shared one.
+template <int R, int LAYOUT, bool DEFF, bool SAMPLED>
 __global__ void __launch_bounds__(32 * CtaShape<R, LAYOUT>::NW, CtaShape<R, LAYOUT>::MIN_CTAS)
 dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     constexpr int NW = CtaShape<R, LAYOUT>::NW;
@@ -1058,23 +1090,34 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
 
     // ---- 0. frame record; thread 0 starts the TMA bulk copy of the crop into shared memory
     const Frame fr = load_frame(a, f);
+    // DTSDF_BBOX_SAMPLED: the frame's index vector rides behind the crop on the same barrier when both fit
+    const int* idx_g = SAMPLED ? a.sample_idx + (size_t)f * a.point_num : nullptr;
+    const bool idx_staged = SAMPLED && fr.staged && (a.point_num & 3) == 0 &&
+                            fr.n_pad + a.point_num <= a.cap_floats && (reinterpret_cast<uintptr_t>(idx_g) & 15) == 0;
     if (tid == 0) {
         mbar_init(&sh->bar, 1);
         fence_mbar_init();
         if (fr.staged) {
-            mbar_expect_tx(&sh->bar, (uint32_t)fr.n_pad * 4u);
+            mbar_expect_tx(&sh->bar, (uint32_t)fr.n_pad * 4u + (idx_staged ? (uint32_t)a.point_num * 4u : 0u));
             bulk_g2s(crop_s, fr.crop, (uint32_t)fr.n_pad * 4u, &sh->bar);
+            if (idx_staged) bulk_g2s(crop_s + fr.n_pad, idx_g, (uint32_t)a.point_num * 4u, &sh->bar);
         }
         sh->nanflag = 0u;
         sh->nodepth[0] = sh->nodepth[1] = sh->nodepth[2] = sh->nodepth[3] = __int_as_float(QNAN_BITS);
     }
     const float yf = __frcp_rn(a.focal);
     const bool focal_ok = a.focal >= 0x1p-30f && a.focal <= 0x1p30f;
-    const bool scan = a.bbox_mode == 0;              // DTSDF_BBOX_PIXELS
-    const bool sampled = a.bbox_mode == 3;           // DTSDF_BBOX_SAMPLED
+    const bool scan = !SAMPLED && a.bbox_mode == 0;  // DTSDF_BBOX_PIXELS
+    constexpr bool sampled = SAMPLED;                // DTSDF_BBOX_SAMPLED
     constexpr unsigned SCRATCH_BITS = (unsigned)((offsetof(FS, vx) - offsetof(SampledScratch<NW>, bitmap)) * 8);
     static_assert(offsetof(FS, at) == 0 && offsetof(FS, vx) > offsetof(SampledScratch<NW>, bitmap) + 1024, "scratch overlays the tables");
     const bool scan_exact = !(DEFF || focal_ok);     // no proven fixed-divisor form for this focal
+    // the common shape of a sampled frame: per-column / per-row extremes and one bitmap window (prepared now,
+    // while the crop is on its way)
+    const bool sampled_fast = sampled && fr.bw <= COLCAP && fr.bh <= ROWCAP && fr.n + 64 <= (int)SCRATCH_BITS;
+    if constexpr (SAMPLED) {
+        if (sampled_fast) sampled_scratch_init<NW>(smem_raw, fr.n);
+    }
     __syncthreads();                                  // the mbarrier is initialised
 
     // ---- 1. bounding-box scan (pre/tsdf_numba.py:75-116) of the staged crop, which also turns
@@ -1083,12 +1126,12 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     bool sawnan = false;
     if (fr.staged) {
         mbar_wait(&sh->bar, 0);
-        if (sampled) {       // (ends with a barrier: every thread is done reading the crop before it is sanitised)
+        if constexpr (SAMPLED) {   // (ends with a barrier: every thread is done reading the crop before it is sanitised)
             const int iw = __ldg(a.headers + 6 * (size_t)f), ih = __ldg(a.headers + 6 * (size_t)f + 1);
-            const int* idx = a.sample_idx + (size_t)f * a.point_num;
+            const int* idx = idx_staged ? reinterpret_cast<const int*>(crop_s + fr.n_pad) : idx_g;
             bool done = false;
-            if (fr.bw <= COLCAP && fr.bh <= ROWCAP)
-                done = sampled_bbox_fast<NW, true, (int)sizeof(FS), (int)offsetof(FS, red), (int)SCRATCH_BITS>(
+            if (sampled_fast)
+                done = sampled_bbox_fast<NW, true, (int)sizeof(FS), (int)offsetof(FS, red)>(
                     nullptr, fr.n, fr.bw, fr.bh, fr.l, fr.t, iw, ih, a.focal64, idx, a.point_num);
             if (!done)
                 sampled_bbox_general<NW, true, (int)sizeof(FS), (int)offsetof(FS, red), (int)SCRATCH_BITS>(
@@ -1100,12 +1143,12 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     } else if (scan) {
         if (scan_exact) bbox_partial<DEFF, true, false, NW>(fr, const_cast<float*>(fr.crop), a, yf, sh->red);
         else            bbox_partial<DEFF, false, false, NW>(fr, const_cast<float*>(fr.crop), a, yf, sh->red);
-    } else if (sampled) {
+    } else if constexpr (SAMPLED) {
         const int iw = __ldg(a.headers + 6 * (size_t)f), ih = __ldg(a.headers + 6 * (size_t)f + 1);
-        const int* idx = a.sample_idx + (size_t)f * a.point_num;
+        const int* idx = idx_g;
         bool done = false;
-        if (fr.bw <= COLCAP && fr.bh <= ROWCAP)
-            done = sampled_bbox_fast<NW, false, (int)sizeof(FS), (int)offsetof(FS, red), (int)SCRATCH_BITS>(
+        if (sampled_fast)
+            done = sampled_bbox_fast<NW, false, (int)sizeof(FS), (int)offsetof(FS, red)>(
                 fr.crop, fr.n, fr.bw, fr.bh, fr.l, fr.t, iw, ih, a.focal64, idx, a.point_num);
         if (!done)
             sampled_bbox_general<NW, false, (int)sizeof(FS), (int)offsetof(FS, red), (int)SCRATCH_BITS>(
@@ -1269,8 +1312,11 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     }
 }
 
-template <int R, int LAYOUT, bool DEFF>
+template <int R, int LAYOUT, bool DEFF, bool SAMPLED = false>
 cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t stream) {
+    if constexpr (!SAMPLED) {
+        if (args_in.bbox_mode == 3) return launch_fused<R, LAYOUT, DEFF, true>(args_in, max_crop_px, stream);
+    }
     BatchArgs args = args_in;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -1285,13 +1331,14 @@ cudaError_t launch_fused(const BatchArgs& args_in, int max_crop_px, cudaStream_t
     // staging capacity: the largest crop of the batch when known (the occupancy then follows from
     // it: three CTAs per SM up to ~63 KB crops, two up to ~100 KB, one above); oversize crops take the direct path.
     long long want = max_crop_px > 0 ? (((long long)max_crop_px + 3) & ~3ll) * 4 : (long long)smem_optin;
+    if (args.bbox_mode == 3 && max_crop_px > 0) want += (((long long)args.point_num + 3) & ~3ll) * 4;   // the index vector
     long long avail = (long long)smem_optin - fixed - 1024;
     if (want > avail) want = avail;
     if (want < 16) want = 16;
     want &= ~15ll;
     args.cap_floats = (int)(want / 4);
     size_t smem = (size_t)fixed + (size_t)want;
-    auto kern = dtsdf_fused_kernel<R, LAYOUT, DEFF>;
+    auto kern = dtsdf_fused_kernel<R, LAYOUT, DEFF, SAMPLED>;
     static std::atomic<unsigned> smem_ok{0u};
     e = allow_max_smem(kern, dev, smem_optin, smem_ok);
     if (e != cudaSuccess) return e;

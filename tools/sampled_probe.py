@@ -6,6 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as g
 pkg = g.load_package()
+if os.environ.get("PROBE_LIB"):                      # an experimental build (tools/exp_bench.py build NAME ...)
+    pkg.capi.LIB_PATH = os.environ["PROBE_LIB"]
 F, P = 8500, 6000
 headers, depth = pkg.synth.make_uniform_batch(F, seed0=3)
 offsets, packed_len, max_px = pkg.capi.pack_plan(headers)
