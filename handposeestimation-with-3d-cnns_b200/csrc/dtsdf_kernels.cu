@@ -1966,13 +1966,23 @@ cudaError_t launch_aug_t(const BatchArgs& args_in, const float* aug, int max_cro
     if (e != cudaSuccess) return e;
     if ((reinterpret_cast<uintptr_t>(args.vol) & 15) != 0 || (reinterpret_cast<uintptr_t>(args.depth) & 15) != 0)
         return cudaErrorMisalignedAddress;
+    auto kern = dtsdf_aug_kernel<R, LAYOUT>;
+    // what is left for the staged crop beside the kernel's static shared memory (tables, lists: 3.5-7 KB by R)
+    static std::atomic<long long> static_bytes{-1};
+    long long fixed = static_bytes.load(std::memory_order_relaxed);
+    if (fixed < 0) {
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, kern);
+        if (e != cudaSuccess) return e;
+        fixed = (long long)fa.sharedSizeBytes;
+        static_bytes.store(fixed, std::memory_order_relaxed);
+    }
     long long want = max_crop_px > 0 ? (((long long)max_crop_px + 3) & ~3ll) * 4 : (long long)smem_optin;
-    const long long avail = (long long)smem_optin - 2048;
+    const long long avail = (long long)smem_optin - fixed - 1024 - 16;
     if (want > avail) want = avail;
     if (want < 16) want = 16;
     want &= ~15ll;
     args.cap_floats = (int)(want / 4);
-    auto kern = dtsdf_aug_kernel<R, LAYOUT>;
     static std::atomic<unsigned> smem_ok{0u};
     e = allow_max_smem(kern, dev, smem_optin, smem_ok);
     if (e != cudaSuccess) return e;

@@ -265,6 +265,79 @@ def test_sampled_voxeliser_equals_the_cloud_path(R, layout):
     v.close()
 
 
+def test_kernels_stay_inside_their_buffers():
+    """compute-sanitizer is closed on this pool (profiles/r02_sanitizer_refused.txt): every output of every device
+    entry point is carved out of a larger allocation filled with a canary pattern, 4 KB on both sides; after the
+    launches over edge shapes (1-pixel crops, a full frame that is not staged, crops partly outside the image, empty
+    depth) the canaries must be untouched and the results must equal those written into ordinary tensors."""
+    import importlib
+    import torch
+    amod = importlib.import_module(pkg.__name__ + ".augment")
+    cmod = importlib.import_module(pkg.__name__ + ".codec")
+    dev = torch.device("cuda:0")
+    CANARY, PAD = 0x7FC0DEAD, 1024                              # int32 words
+    frames = _sampled_case_frames()
+    headers, offsets, packed, max_px = pkg.pack_frames(frames)
+    n = len(frames)
+    args = (torch.from_numpy(packed).to(dev), torch.from_numpy(offsets).to(dev), torch.from_numpy(headers).to(dev))
+    guards = []
+
+    def guarded(shape, dtype=torch.float32):
+        numel = int(np.prod(shape))
+        assert dtype in (torch.float32, torch.int32)
+        raw = torch.full((numel + 2 * PAD,), CANARY, dtype=torch.int32, device=dev)
+        guards.append((raw, numel))
+        return raw[PAD:PAD + numel].view(dtype).view(*shape)
+
+    def check_guards():
+        torch.cuda.synchronize()
+        for raw, numel in guards:
+            assert bool((raw[:PAD] == CANARY).all()) and bool((raw[PAD + numel:] == CANARY).all())
+        guards.clear()
+
+    n_valid = pkg.count_valid_device(*args, out=guarded((n,), torch.int32))
+    check_guards()
+    nv = n_valid.cpu().numpy()
+    keep = nv > 0
+    rng = np.random.default_rng(5)
+    idx = np.stack([rng.integers(0, max(int(v), 1), size=6000) for v in nv]).astype(np.int32)
+    idx[::3, :7] = [-1, -2 ** 31, 2 ** 31 - 1, 76800, 10 ** 6, 123456789, -5]      # out of range: must select nothing
+    d_idx = torch.from_numpy(idx).to(dev)
+    for R, layout in ((32, 0), (48, 1), (64, 0)):
+        cfg = pkg.capi.default_config(R, layout, pkg.BBOX_PIXELS)
+        for hint in (max_px, 16):
+            out = (guarded((n, 3, R, R, R)), guarded((n,)), guarded((n, 3)))
+            pkg.voxelize_device(*args, hint, cfg, out_vol=out[0], out_max_l=out[1], out_mid_p=out[2])
+            want = pkg.voxelize_device(*args, hint, cfg)
+            torch.cuda.synchronize()
+            assert all(torch.equal(a.view(torch.int32), b.view(torch.int32)) for a, b in zip(out, want))
+            check_guards()
+            out = (guarded((n, 3, R, R, R)), guarded((n,)), guarded((n, 3)))
+            pkg.voxelize_sampled_device(*args, d_idx, hint, cfg, out_vol=out[0], out_max_l=out[1], out_mid_p=out[2])
+            want = pkg.voxelize_sampled_device(*args, d_idx, hint, cfg)
+            torch.cuda.synchronize()
+            sel = torch.from_numpy(keep).to(dev)
+            assert torch.equal(out[0][sel].view(torch.int32), want[0][sel].view(torch.int32))
+            check_guards()
+            aug = torch.from_numpy(amod.make_augmentations(n, np.random.default_rng(R), centers=np.tile([0, 0, -380.0], (n, 1)))).to(dev)
+            out = (guarded((n, 3, R, R, R)), guarded((n,)), guarded((n, 3)))
+            amod.voxelize_aug_device(*args, aug, hint, cfg, out_vol=out[0], out_max_l=out[1], out_mid_p=out[2])
+            check_guards()
+    # the volume codec: packed arrays carved from a guarded byte buffer, expansion into a guarded volume
+    vol, _, _ = pkg.voxelize_device(*args, max_px)
+    nbytes = cmod.PackedVolumes.storage_bytes(n, 32)
+    raw = torch.full((nbytes // 4 + 2 * PAD,), CANARY, dtype=torch.int32, device=dev)
+    store = raw[PAD:PAD + nbytes // 4].view(torch.uint8)
+    pk = cmod.PackedVolumes(n, 32, dev, storage=store)
+    cmod.pack_volumes_device(vol, pk)
+    back = guarded((n, 3, 32, 32, 32))
+    cmod.unpack_volumes_device(pk, out=back)
+    torch.cuda.synchronize()
+    assert bool((raw[:PAD] == CANARY).all()) and bool((raw[PAD + nbytes // 4:] == CANARY).all())
+    assert torch.equal(back.view(torch.int32), vol.view(torch.int32))
+    check_guards()
+
+
 def test_tsdf_for_module(forloop_golden):
     tsdf_for = import_pre("tsdf_for")
     c = forloop_golden[3]
