@@ -523,7 +523,9 @@ def run_secondary(pkg, dev, rank, world, args, max_over_ranks, barrier):
     dt = max_over_ranks(time.perf_counter() - t0) / reps
     barrier()
     # what bounds it: the caller's random stream is ONE sequential MT19937 (each frame's 6000 draws start where
-    # the previous frame's rejection sampling stopped), drawn by one thread whatever the GPU does meanwhile
+    # the previous frame's rejection sampling stopped): one thread has to find those starting points in order
+    # (nothing written), helper threads then produce the draws; beyond that the dense stores of the volumes
+    # into host memory, as for the plain host call (e2e.bound)
     t0 = time.perf_counter()
     for _ in range(reps):
         capi.resample_indices(n_valid[:n_host], P)
@@ -534,8 +536,9 @@ def run_secondary(pkg, dev, rank, world, args, max_over_ranks, barrier):
         "config": "Voxelizer.process_packed(want_points=False) = dtsdf_process_host: host crops in, volumes out (pinned), "
                   "resampling indices drawn in C from the caller's np.random MT19937 state (bit-compatible with the "
                   "reference's per-frame np.random.randint calls, pre/process.py:75-80); dtsdf_count_valid_batch + "
-                  "dtsdf_voxelize_sampled_batch per chunk",
-        "bound": {"what": "the index draw alone (dtsdf_resample_indices, one thread: the stream is sequential)",
+                  "dtsdf_voxelize_sampled_batch per chunk, the crops uploaded and counted chunk by chunk behind the draws",
+        "bound": {"what": "the index draw alone (dtsdf_resample_indices: one thread scans the sequential stream for "
+                          "where each frame's draws begin, up to four helpers write them)",
                   "ms": dt_rng * 1e3, "value": n_host * world / dt_rng, "unit": "frames/s",
                   "ns_per_draw": dt_rng / (n_host * P) * 1e9},
         "frac": dt_rng / dt}

@@ -134,8 +134,9 @@ struct MapBuf {
 // A small persistent thread pool for the host-side expansion of packed volumes.  Jobs are plain records in
 // a fixed ring (no allocation on submit: nothing here can throw once the threads run).
 struct ExpandJob {
-    const void* chunk;          // dtsdf_ctx::ChunkRecord
+    const void* chunk;          // dtsdf_ctx::ChunkRecord, or (draw = true) a DrawRecord
     int32_t f0, f1;             // frames [f0, f1) of the chunk
+    bool draw = false;          // second phase of the resampling index draw instead of an expansion
 };
 void run_expand_job(const ExpandJob& j);
 
@@ -161,6 +162,7 @@ public:
         cv_.notify_one();
         return true;
     }
+    int size() const { return (int)th_.size(); }
     void stop() {
         { std::lock_guard<std::mutex> g(m_); quit_ = true; }
         cv_.notify_all();
@@ -231,7 +233,7 @@ struct dtsdf_packed_host {
 
 struct dtsdf_ctx {
     int device = 0;
-    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr, s_lit = nullptr;
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr, s_lit = nullptr, s_idx = nullptr;
     static const int NSLOT = 4;                 // chunks in flight
     // packed device -> host transfer
     int opt_packed = 1;
@@ -274,6 +276,11 @@ struct dtsdf_ctx {
     int32_t b_n = 0;
     int32_t b_max_px = 0;
     std::vector<int32_t> b_nvalid_h;
+    // dtsdf_process_host without clouds: the crops go up piece by piece (one piece per pipeline chunk) with the
+    // valid-pixel counts of a piece coming back behind it, so the first index draw starts after one piece
+    MapBuf m_nvalid;
+    std::vector<cudaEvent_t> ev_piece;
+    int32_t b_pieces = 0;                        // 0: everything was uploaded and counted synchronously
 };
 
 extern "C" {
@@ -622,6 +629,7 @@ int dtsdf_ctx_create(int32_t device, dtsdf_ctx** out) {
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_lit, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->s_idx, cudaStreamNonBlocking);
     for (int i = 0; i < dtsdf_ctx::NSLOT && err == cudaSuccess; ++i) {
         err = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming);
         // the host waits on ev_run while its cores expand packed volumes: sleep, do not spin
@@ -661,6 +669,9 @@ void dtsdf_ctx_destroy(dtsdf_ctx* c) {
     if (c->s_run) cudaStreamDestroy(c->s_run);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->s_lit) cudaStreamDestroy(c->s_lit);
+    if (c->s_idx) cudaStreamDestroy(c->s_idx);
+    for (cudaEvent_t e : c->ev_piece) cudaEventDestroy(e);
+    c->m_nvalid.release();
     cudaGetLastError();
     delete c;
 }
@@ -731,7 +742,28 @@ static void expand_chunk(const dtsdf_ctx::ChunkRecord* r) {
 }
 
 namespace {
+// Second phase of the index draw of one pipeline chunk (first phase: HostPipeline::scan_chunk): frame i's
+// draws are produced from the snapshot of the stream taken where they begin - any frame on any thread.
+struct DrawRecord {
+    const dtsdf::DrawSpan* spans;      // [frames of the chunk]
+    int32_t point_num;
+    int32_t* out;                      // [frames][point_num], pinned staging of the chunk's slot
+    Latch* latch;
+};
+void run_draw_job(const ExpandJob& j) {
+    const DrawRecord* r = static_cast<const DrawRecord*>(j.chunk);
+    for (int32_t f = j.f0; f < j.f1; ++f) {
+        const dtsdf::DrawSpan& sp = r->spans[f];
+        int32_t* idx = r->out + (size_t)f * r->point_num;
+        const int32_t lead = r->point_num - sp.count;          // pre/process.py:76-79: every point once, then repeats
+        for (int32_t k = 0; k < lead; ++k) idx[k] = k;
+        dtsdf::draw_fill(sp, idx + lead);
+    }
+    r->latch->done();
+}
+
 void run_expand_job(const ExpandJob& j) {
+    if (j.draw) { run_draw_job(j); return; }
     const dtsdf_ctx::ChunkRecord* r = static_cast<const dtsdf_ctx::ChunkRecord*>(j.chunk);
     dtsdf_ctx* c = r->ctx;
     const unsigned char* codes = (const unsigned char*)c->m_codes[r->slot].p;
@@ -813,6 +845,12 @@ struct HostPipeline {
     int* mt_pos = nullptr;
     double* h_pc = nullptr;
     double focal64 = 0.0;
+    // the index draw in two phases (csrc/dtsdf_rng.cpp): this thread finds where every frame's draws begin
+    // (sequential, nothing written), the pool threads produce them; chunk k+1 is scanned while chunk k is on the GPU
+    std::vector<dtsdf::DrawSpan> spans[2];
+    DrawRecord draw_rec[2];
+    Latch draw_latch[2];
+    int scan_chunk(int k);
     // finalizer: takes the chunks in order, polls the event behind each one's last copy, hands the
     // chunk to the expansion threads
     std::mutex qm;
@@ -914,8 +952,45 @@ struct HostPipeline {
     int run();
 };
 
+// Phase one of chunk k's index draw (pre/process.py:70-84, frames in order on the caller's stream), then the
+// pool gets phase two.  With pieces in flight (dtsdf_process_host without clouds) the chunk's valid-pixel counts
+// are waited for first.
+int HostPipeline::scan_chunk(int k) {
+    const int slot = k % dtsdf_ctx::NSLOT, par = k & 1;
+    const int32_t f0 = k * per_chunk;
+    const int32_t nf = std::min(per_chunk, n_frames - f0);
+    if (c->b_pieces > 0) {
+        CK(cudaEventSynchronize(c->ev_piece[(size_t)k]));
+        memcpy(c->b_nvalid_h.data() + f0, (const int32_t*)c->m_nvalid.p + f0, (size_t)nf * 4);
+    }
+    // the staging buffer of the slot was last read by the host -> device copy of chunk k - NSLOT
+    if (k >= dtsdf_ctx::NSLOT) CK(cudaEventSynchronize(c->ev_in[slot]));
+    int rc;
+    if ((rc = c->m_idx[slot].reserve((size_t)nf * point_num * 4)) != DTSDF_OK) return rc;
+    spans[par].resize((size_t)nf);
+    for (int32_t i = 0; i < nf; ++i) {
+        const int32_t nv = c->b_nvalid_h[(size_t)f0 + i];
+        if (nv <= 0) return DTSDF_ERR_EMPTY_CLOUD;       // np.random.randint(0, 0): ValueError; the stream stays here
+        dtsdf::np_legacy_randint_skip(mt_key, mt_pos, (uint32_t)nv, nv < point_num ? point_num - nv : point_num,
+                                      &spans[par][(size_t)i]);
+    }
+    DrawRecord& r = draw_rec[par];
+    r.spans = spans[par].data(); r.point_num = point_num; r.out = (int32_t*)c->m_idx[slot].p; r.latch = &draw_latch[par];
+    const int workers = c->pool.size();
+    const int jobs = std::max(1, std::min<int>(nf, workers));
+    draw_latch[par].add(jobs);
+    for (int j = 0; j < jobs; ++j) {
+        ExpandJob job;
+        job.chunk = &r; job.draw = true;
+        job.f0 = (int32_t)((int64_t)nf * j / jobs);
+        job.f1 = (int32_t)((int64_t)nf * (j + 1) / jobs);
+        if (workers == 0 || !c->pool.submit(job)) run_expand_job(job);
+    }
+    return DTSDF_OK;
+}
+
 int HostPipeline::submit_chunks() {
-    const cudaStream_t st_in = single ? c->s_run : c->s_in;
+    const cudaStream_t st_in = single ? c->s_run : (process_mode ? c->s_idx : c->s_in);
     const cudaStream_t st_out = single ? c->s_run : c->s_out;
     std::vector<int64_t> rebased;
     int rc;
@@ -977,19 +1052,19 @@ int HostPipeline::submit_chunks() {
         } else {
             // pre/process.py:70-84 for the frames of this chunk, in frame order, on the caller's stream
             const size_t ni = (size_t)nf * point_num;
-            if ((rc = c->m_idx[slot].reserve(ni * 4)) != DTSDF_OK) return rc;
             if ((rc = c->p_idx[slot].reserve(ni * 4)) != DTSDF_OK) return rc;
             if ((rc = c->p_ext[slot].reserve((size_t)nf * 24)) != DTSDF_OK) return rc;
             if (h_pc) {
                 if ((rc = c->p_pc[slot].reserve(ni * 24)) != DTSDF_OK) return rc;
                 if (packed && (rc = c->m_pc[slot].reserve(ni * 24)) != DTSDF_OK) return rc;
             }
-            rc = resample_indices(mt_key, mt_pos, nf, c->b_nvalid_h.data() + f0, point_num, (int32_t*)c->m_idx[slot].p);
-            if (rc != DTSDF_OK) return rc;
+            if (k == 0 && (rc = scan_chunk(0)) != DTSDF_OK) return rc;
+            draw_latch[k & 1].wait();
             CK(cudaMemcpyAsync(c->p_idx[slot].p, c->m_idx[slot].p, ni * 4, cudaMemcpyHostToDevice, st_in));
+            if (c->b_pieces > 0) CK(cudaStreamWaitEvent(c->s_run, c->ev_piece[(size_t)k], 0));      // the chunk's crops
         }
         if (!single) {
-            CK(cudaEventRecord(c->ev_in[slot], c->s_in));
+            CK(cudaEventRecord(c->ev_in[slot], st_in));
             CK(cudaStreamWaitEvent(c->s_run, c->ev_in[slot], 0));
         }
 
@@ -1016,6 +1091,8 @@ int HostPipeline::submit_chunks() {
                                           (float*)c->d_mid[slot].p, c->s_run);
         }
         if (rc != DTSDF_OK) return rc;
+        // while the GPU works on this chunk: where the next chunk's draws begin, and its draws on the pool
+        if (process_mode && k + 1 < nchunk && (rc = scan_chunk(k + 1)) != DTSDF_OK) return rc;
 
         if (packed) {
             // pack into device memory on the kernel stream; then, on s_out so that the next chunk's
@@ -1131,7 +1208,9 @@ int HostPipeline::run() {
         rc = no_memory.load() ? DTSDF_ERR_ALLOC : DTSDF_ERR_CUDA;
     }
     for (int i = 0; i < dtsdf_ctx::NSLOT; ++i) c->latch[i].wait();         // expansion jobs that did start
+    draw_latch[0].wait(); draw_latch[1].wait();                            // draw jobs read this object's spans
     if (packed) { cudaStreamSynchronize(c->s_lit); cudaGetLastError(); }
+    if (process_mode) { cudaStreamSynchronize(c->s_idx); cudaGetLastError(); }
     cudaError_t e_out = single ? cudaSuccess : cudaStreamSynchronize(c->s_out);
     cudaError_t e_run = cudaStreamSynchronize(c->s_run);
     cudaError_t e_in = single ? cudaSuccess : cudaStreamSynchronize(c->s_in);
@@ -1321,7 +1400,7 @@ int dtsdf_resample_extrema_host(dtsdf_ctx* c, int32_t point_num, const double* h
 
 static int process_begin_impl(dtsdf_ctx* c, double focal, int32_t n_frames, const float* h_depth,
                               int64_t packed_len, const int64_t* h_off, const int32_t* h_hdr,
-                              int32_t* h_n_valid, bool want_points);
+                              int32_t* h_n_valid, bool want_points, int32_t piece_frames = 0);
 
 int dtsdf_process_begin_host(dtsdf_ctx* c, double focal, int32_t n_frames, const float* h_depth,
                              int64_t packed_len, const int64_t* h_off, const int32_t* h_hdr,
@@ -1331,22 +1410,29 @@ int dtsdf_process_begin_host(dtsdf_ctx* c, double focal, int32_t n_frames, const
 
 // want_points = false: only the valid-pixel counts are needed (the sampled voxeliser finds the box of the
 // resampled cloud from the depth map itself); no cloud is built and none of its memory reserved
+// piece_frames > 0 (only without clouds): nothing is waited for - the crops go up on s_in in pieces of that many
+// frames, each followed by its count kernel, the copy of its counts into pinned memory (m_nvalid) and an event
+// (ev_piece[j]); the caller (HostPipeline, one piece per chunk) synchronises piece by piece.
 static int process_begin_impl(dtsdf_ctx* c, double focal, int32_t n_frames, const float* h_depth,
                               int64_t packed_len, const int64_t* h_off, const int32_t* h_hdr,
-                              int32_t* h_n_valid, bool want_points) {
+                              int32_t* h_n_valid, bool want_points, int32_t piece_frames) {
     if (!c || n_frames < 0 || packed_len < 0 || !(focal > 0.0)) return DTSDF_ERR_INVALID_ARG;
     c->b_n = 0;
+    c->b_pieces = 0;
     if (n_frames == 0) return DTSDF_OK;
     if (!h_depth || !h_off || !h_hdr || !h_n_valid) return DTSDF_ERR_INVALID_ARG;
     std::vector<int64_t> poff(n_frames);
-    int64_t total_px = 0;
+    int64_t total_px = 0, prev_end = 0;
     int32_t max_px = 0;
+    bool in_order = true;                   // every crop starts at or behind the end of the one before it
     for (int32_t i = 0; i < n_frames; ++i) {
         const int32_t* h = h_hdr + 6 * (size_t)i;
         if (!header_ok(h)) return DTSDF_ERR_BAD_HEADER;
         const int64_t n = ((int64_t)h[4] - h[2]) * ((int64_t)h[5] - h[3]);
         if (h_off[i] < 0 || (h_off[i] & 3) || h_off[i] + ((n + 3) & ~(int64_t)3) > packed_len)
             return DTSDF_ERR_INVALID_ARG;
+        in_order = in_order && h_off[i] >= prev_end;
+        prev_end = h_off[i] + ((n + 3) & ~(int64_t)3);
         poff[i] = total_px;                 // room for every pixel of the crop
         total_px += n;
         max_px = std::max<int32_t>(max_px, (int32_t)n);
@@ -1357,6 +1443,35 @@ static int process_begin_impl(dtsdf_ctx* c, double focal, int32_t n_frames, cons
     if ((rc = c->b_off.reserve((size_t)n_frames * 8)) != DTSDF_OK) return rc;
     if ((rc = c->b_hdr.reserve((size_t)n_frames * 24)) != DTSDF_OK) return rc;
     if ((rc = c->b_nvalid.reserve((size_t)n_frames * 4)) != DTSDF_OK) return rc;
+    if (piece_frames > 0 && !want_points && in_order) {
+        const int32_t np = (n_frames + piece_frames - 1) / piece_frames;
+        if ((rc = c->m_nvalid.reserve((size_t)n_frames * 4)) != DTSDF_OK) return rc;
+        while ((int32_t)c->ev_piece.size() < np) {
+            cudaEvent_t e = nullptr;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->ev_piece.push_back(e);
+        }
+        c->b_nvalid_h.assign((size_t)n_frames, 0);
+        cudaStream_t s = c->s_in;
+        CK(cudaMemcpyAsync(c->b_off.p, h_off, (size_t)n_frames * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(c->b_hdr.p, h_hdr, (size_t)n_frames * 24, cudaMemcpyHostToDevice, s));
+        for (int32_t j = 0; j < np; ++j) {
+            const int32_t f0 = j * piece_frames, nf = std::min(piece_frames, n_frames - f0);
+            const int32_t* hl = h_hdr + 6 * (size_t)(f0 + nf - 1);
+            const int64_t nlast = ((int64_t)hl[4] - hl[2]) * ((int64_t)hl[5] - hl[3]);
+            const int64_t e0 = h_off[f0], e1 = h_off[f0 + nf - 1] + ((nlast + 3) & ~(int64_t)3);
+            CK(cudaMemcpyAsync((float*)c->b_depth.p + e0, h_depth + e0, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, s));
+            rc = dtsdf_count_valid_batch(nf, (const float*)c->b_depth.p, (const int64_t*)c->b_off.p + f0,
+                                         (const int32_t*)c->b_hdr.p + 6 * (size_t)f0, (int32_t*)c->b_nvalid.p + f0, s);
+            if (rc != DTSDF_OK) return rc;
+            CK(cudaMemcpyAsync((int32_t*)c->m_nvalid.p + f0, (const int32_t*)c->b_nvalid.p + f0, (size_t)nf * 4,
+                               cudaMemcpyDeviceToHost, s));
+            CK(cudaEventRecord(c->ev_piece[(size_t)j], s));
+        }
+        c->b_pieces = np;
+        c->b_max_px = max_px;
+        return DTSDF_OK;
+    }
     if (want_points) {
         if ((rc = c->b_poff.reserve((size_t)n_frames * 8)) != DTSDF_OK) return rc;
         if ((rc = c->b_points.reserve((size_t)total_px * 24)) != DTSDF_OK) return rc;
@@ -1436,16 +1551,69 @@ int dtsdf_np_randint(uint32_t* mt_key, int32_t* mt_pos, int32_t high, int32_t co
     return DTSDF_OK;
 }
 
+// The same draws in two phases for large batches: this thread finds where every frame's draws begin, block by
+// block of 256 frames (np_legacy_randint_skip: nothing written), and up to four helper threads produce the draws
+// of block b from the snapshots while block b + 1 is being scanned.  Output and final stream state are those of
+// resample_indices (tests/test_host_logic.py checks both against np.random itself).
+static int resample_indices_two_phase(uint32_t* key, int* pos, int32_t n, const int32_t* n_valid, int32_t point_num,
+                                      int32_t* out, int helpers) {
+    constexpr int32_t BLOCK = 256;
+    std::vector<dtsdf::DrawSpan> spans[2];
+    std::vector<std::thread> th[2];
+    auto join = [&](int par) { for (auto& t : th[par]) t.join(); th[par].clear(); };
+    int rc = DTSDF_OK;
+    try {
+        for (int32_t b0 = 0, b = 0; b0 < n && rc == DTSDF_OK; b0 += BLOCK, ++b) {
+            const int par = b & 1;
+            const int32_t nb = std::min(BLOCK, n - b0);
+            join(par);                                    // block b - 2 used these snapshots
+            spans[par].resize((size_t)nb);
+            int32_t ok = 0;
+            for (; ok < nb; ++ok) {
+                const int32_t nv = n_valid[b0 + ok];
+                if (nv <= 0) { rc = DTSDF_ERR_EMPTY_CLOUD; break; }
+                dtsdf::np_legacy_randint_skip(key, pos, (uint32_t)nv, nv < point_num ? point_num - nv : point_num,
+                                              &spans[par][(size_t)ok]);
+            }
+            const int jobs = std::max(1, std::min<int>(helpers, ok));
+            for (int j = 0; j < jobs; ++j) {
+                const int32_t f0 = (int32_t)((int64_t)ok * j / jobs), f1 = (int32_t)((int64_t)ok * (j + 1) / jobs);
+                const dtsdf::DrawSpan* sp = spans[par].data();
+                int32_t* o = out + (size_t)b0 * point_num;
+                th[par].emplace_back([=] {
+                    for (int32_t f = f0; f < f1; ++f) {
+                        int32_t* idx = o + (size_t)f * point_num;
+                        const int32_t lead = point_num - sp[f].count;
+                        for (int32_t k = 0; k < lead; ++k) idx[k] = k;
+                        dtsdf::draw_fill(sp[f], idx + lead);
+                    }
+                });
+            }
+        }
+    } catch (...) {
+        join(0); join(1);
+        throw;
+    }
+    join(0); join(1);
+    return rc;
+}
+
 int dtsdf_resample_indices(uint32_t* mt_key, int32_t* mt_pos, int32_t n_frames, const int32_t* n_valid,
                            int32_t point_num, int32_t* out_idx) {
     if (!mt_key || !mt_pos || n_frames < 0 || point_num <= 0) return DTSDF_ERR_INVALID_ARG;
     if (*mt_pos < 0 || *mt_pos > 624) return DTSDF_ERR_INVALID_ARG;
     if (n_frames == 0) return DTSDF_OK;
     if (!n_valid || !out_idx) return DTSDF_ERR_INVALID_ARG;
-    int pos = *mt_pos;
-    const int rc = resample_indices(mt_key, &pos, n_frames, n_valid, point_num, out_idx);
-    *mt_pos = pos;
-    return rc;
+    return guarded([&]() -> int {
+        int pos = *mt_pos;
+        const int helpers = (int)std::min(4u, std::max(1u, std::thread::hardware_concurrency()) - 1u);
+        // (small requests, one core, DTSDF_RNG_ISA=scalar... : the plain form; same results)
+        const int rc = (n_frames >= 64 && helpers >= 1)
+                           ? resample_indices_two_phase(mt_key, &pos, n_frames, n_valid, point_num, out_idx, helpers)
+                           : resample_indices(mt_key, &pos, n_frames, n_valid, point_num, out_idx);
+        *mt_pos = pos;
+        return rc;
+    });
 }
 
 int dtsdf_process_host(dtsdf_ctx* c, const dtsdf_config* cfg_in, double focal, int32_t n_frames,
@@ -1461,10 +1629,6 @@ int dtsdf_process_host(dtsdf_ctx* c, const dtsdf_config* cfg_in, double focal, i
     if (!h_out_vol) return DTSDF_ERR_INVALID_ARG;
     return guarded([&]() -> int {
         // back-projection + compaction of every frame; crops, tables and clouds stay resident (b_*)
-        std::vector<int32_t> n_valid((size_t)n_frames);
-        int rc2 = process_begin_impl(c, focal, n_frames, h_depth, packed_len, h_off, h_hdr, n_valid.data(),
-                                     h_out_pc != nullptr);
-        if (rc2 != DTSDF_OK) return rc2;
         USE_DEVICE(c->device);
         dtsdf_config cfg = *cfg_in;
         cfg.bbox_mode = DTSDF_BBOX_EXTREMA;
@@ -1476,7 +1640,19 @@ int dtsdf_process_host(dtsdf_ctx* c, const dtsdf_config* cfg_in, double focal, i
         p.process_mode = true; p.point_num = point_num; p.mt_key = mt_key; p.mt_pos = &pos; p.h_pc = h_out_pc;
         p.focal64 = focal;
         p.configure();
+        // with clouds: back-projection + compaction of every frame up front, crops, tables and clouds resident
+        // (b_*); without: the crops go up and are counted one pipeline chunk at a time behind the draws
+        std::vector<int32_t> n_valid((size_t)n_frames);
+        int rc2 = process_begin_impl(c, focal, n_frames, h_depth, packed_len, h_off, h_hdr, n_valid.data(),
+                                     h_out_pc != nullptr, p.nchunk > 1 ? p.per_chunk : 0);
+        if (rc2 != DTSDF_OK) {
+            cudaStreamSynchronize(c->s_in);          // pieces may be in flight from the caller's buffer
+            cudaGetLastError();
+            c->b_pieces = 0;
+            return rc2;
+        }
         rc2 = p.run();
+        c->b_pieces = 0;
         *mt_pos = pos;
         return rc2;
     });

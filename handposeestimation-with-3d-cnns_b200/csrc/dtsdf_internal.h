@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <vector>
 
 namespace dtsdf {
 
@@ -96,6 +97,20 @@ const char* decode_isa();
 // NumPy's legacy global stream (dtsdf_rng.cpp): `count` draws of np.random.randint(0, high) from the MT19937
 // state (key[624], pos as in np.random.get_state()), written to out; the state advances as NumPy's would.
 void np_legacy_randint(uint32_t* key, int* pos, uint32_t high, int count, int32_t* out);
+
+// The same draws in two phases, so that only the cheap half is sequential.  The stream is ONE MT19937 and every
+// frame's draws start where the previous frame's rejection sampling stopped, so WHERE a frame's draws begin must
+// be found in order - but that needs no output: np_legacy_randint_skip steps the generator and counts acceptances
+// (tempering + compare + popcount; no compress-store, nothing written) after leaving a snapshot of the state in the
+// span; draw_fill then produces a frame's draws from its snapshot, any frame on any thread.
+struct DrawSpan {
+    uint32_t key[624];        // the state the request started from
+    int      pos;
+    uint32_t high;            // np.random.randint(0, high, size=count)
+    int32_t  count;
+};
+void np_legacy_randint_skip(uint32_t* key, int* pos, uint32_t high, int count, DrawSpan* span);
+void draw_fill(const DrawSpan& span, int32_t* out);
 
 // kernels launched by this process (claimed in bench.py's gpu_launches)
 extern std::atomic<long long> g_launch_count;

@@ -34,10 +34,34 @@ inline uint32_t twist(uint32_t u, uint32_t v) {
 // mt19937_gen: the next 624 words of state.  The three loops only read words that this pass has not
 // written yet or wrote at least 227 iterations earlier, so the compiler may vectorise them (clones for the
 // wider vector units are picked at load time).
-__attribute__((target_clones("avx512f", "avx2", "default")))
-void mt_generate(uint32_t* key) {
+__attribute__((target_clones("avx2", "default")))
+void mt_generate_auto(uint32_t* key) {
     int i = 0;
     for (; i < MT_N - MT_M; ++i) key[i] = key[i + MT_M] ^ twist(key[i], key[i + 1]);
+    for (; i < MT_N - 1; ++i) key[i] = key[i + (MT_M - MT_N)] ^ twist(key[i], key[i + 1]);
+    key[MT_N - 1] = key[MT_M - 1] ^ twist(key[MT_N - 1], key[0]);
+}
+
+// The same pass written out for AVX-512 (16 words per step: one bit select, one test-and-move, one
+// three-way xor): 0.19 ns per word against 0.3-0.6 for what the compiler makes of the loops above.  A step
+// reads key[i + 1 .. i + 16] before it writes key[i .. i + 15], and key[i - 227 ..] was written 14 steps earlier.
+__attribute__((target("avx512f")))
+inline __m512i twist16(__m512i u, __m512i v, __m512i far) {
+    const __m512i up = _mm512_set1_epi32((int)UPPER), one = _mm512_set1_epi32(1), a = _mm512_set1_epi32((int)MATRIX_A);
+    const __m512i y = _mm512_ternarylogic_epi32(up, u, v, 0xCA);                        // up ? u : v
+    const __m512i mag = _mm512_maskz_mov_epi32(_mm512_test_epi32_mask(v, one), a);
+    return _mm512_ternarylogic_epi32(_mm512_srli_epi32(y, 1), mag, far, 0x96);          // xor of the three
+}
+__attribute__((target("avx512f")))
+void mt_generate_avx512(uint32_t* key) {
+    int i = 0;
+    for (; i + 16 <= MT_N - MT_M; i += 16)
+        _mm512_storeu_si512(key + i, twist16(_mm512_loadu_si512(key + i), _mm512_loadu_si512(key + i + 1),
+                                             _mm512_loadu_si512(key + i + MT_M)));
+    for (; i < MT_N - MT_M; ++i) key[i] = key[i + MT_M] ^ twist(key[i], key[i + 1]);
+    for (; i + 16 <= MT_N - 1; i += 16)
+        _mm512_storeu_si512(key + i, twist16(_mm512_loadu_si512(key + i), _mm512_loadu_si512(key + i + 1),
+                                             _mm512_loadu_si512(key + i + (MT_M - MT_N))));
     for (; i < MT_N - 1; ++i) key[i] = key[i + (MT_M - MT_N)] ^ twist(key[i], key[i + 1]);
     key[MT_N - 1] = key[MT_M - 1] ^ twist(key[MT_N - 1], key[0]);
 }
@@ -70,14 +94,16 @@ int filter_avx512(const uint32_t* key, int n, uint32_t mask, uint32_t rng, int32
     const __m512i vmask = _mm512_set1_epi32((int)mask), vrng = _mm512_set1_epi32((int)rng);
     const __m512i c1 = _mm512_set1_epi32((int)0x9d2c5680u), c2 = _mm512_set1_epi32((int)0xefc60000u);
     int done = 0, k = 0;
-    for (; k + 16 <= n && done < want; k += 16) {
-        __m512i y = _mm512_loadu_si512(key + k);
+    for (; k < n && done < want; k += 16) {
+        // (the last step of a block is a masked load: a block seldom starts on a multiple of 16 words)
+        const __mmask16 live = n - k >= 16 ? (__mmask16)0xffff : (__mmask16)((1u << (n - k)) - 1u);
+        __m512i y = _mm512_maskz_loadu_epi32(live, key + k);
         y = _mm512_xor_si512(y, _mm512_srli_epi32(y, 11));
         y = _mm512_xor_si512(y, _mm512_and_si512(_mm512_slli_epi32(y, 7), c1));
         y = _mm512_xor_si512(y, _mm512_and_si512(_mm512_slli_epi32(y, 15), c2));
         y = _mm512_xor_si512(y, _mm512_srli_epi32(y, 18));
         y = _mm512_and_si512(y, vmask);
-        unsigned m = _mm512_cmple_epu32_mask(y, vrng);
+        unsigned m = _mm512_mask_cmple_epu32_mask(live, y, vrng);
         const int c = __builtin_popcount(m);
         if (done + c >= want) {
             // the step that completes the request: keep the first (want - done) accepted words only
@@ -92,10 +118,64 @@ int filter_avx512(const uint32_t* key, int n, uint32_t mask, uint32_t rng, int32
         _mm512_mask_compressstoreu_epi32(out + done, (__mmask16)m, y);
         done += c;
     }
-    int tail_got = 0;
-    const int tail = filter_scalar(key + k, n - k, mask, rng, out + done, want - done, &tail_got);
-    *got = done + tail_got;
-    return k + tail;
+    *got = done;                    // all n words looked at (or want == 0)
+    return k < n ? k : n;
+}
+
+// The counting half of the filters: how many of key[0..n) are needed for `want` acceptances (up to and including
+// the last accepted word), *got = acceptances found (< want: all n words were looked at).
+size_t count_scalar(const uint32_t* key, size_t n, uint32_t mask, uint32_t rng, int want, int* got) {
+    int done = 0;
+    size_t k = 0;
+    for (; k < n && done < want; ++k) done += ((temper(key[k]) & mask) <= rng);
+    *got = done;
+    return k;
+}
+
+__attribute__((target("avx512f,bmi2")))
+size_t count_avx512(const uint32_t* key, size_t n, uint32_t mask, uint32_t rng, int want, int* got) {
+    const __m512i vmask = _mm512_set1_epi32((int)mask), vrng = _mm512_set1_epi32((int)rng);
+    const __m512i c1 = _mm512_set1_epi32((int)0x9d2c5680u), c2 = _mm512_set1_epi32((int)0xefc60000u);
+    int done = 0;
+    size_t k = 0;
+    for (; k < n && done < want; k += 16) {
+        const __mmask16 live = n - k >= 16 ? (__mmask16)0xffff : (__mmask16)((1u << (n - k)) - 1u);
+        __m512i y = _mm512_maskz_loadu_epi32(live, key + k);
+        y = _mm512_xor_si512(y, _mm512_srli_epi32(y, 11));
+        y = _mm512_xor_si512(y, _mm512_and_si512(_mm512_slli_epi32(y, 7), c1));
+        y = _mm512_xor_si512(y, _mm512_and_si512(_mm512_slli_epi32(y, 15), c2));
+        y = _mm512_xor_si512(y, _mm512_srli_epi32(y, 18));
+        const unsigned m = _mm512_mask_cmple_epu32_mask(live, _mm512_and_si512(y, vmask), vrng);
+        const int c = __builtin_popcount(m);
+        if (done + c >= want) {
+            const unsigned last = _pdep_u32(1u << (want - done - 1), m);       // the last acceptance needed
+            *got = want;
+            return k + (size_t)__builtin_ctz(last) + 1;
+        }
+        done += c;
+    }
+    *got = done;
+    return k < n ? k : n;
+}
+
+// Acceptances among ALL of key[0..n): what the scan uses for every block that cannot complete the request
+// (fewer words left in it than draws still wanted) - no early exit, no mask leaves the vector unit.
+__attribute__((target("avx512f")))
+int count_all_avx512(const uint32_t* key, int n, uint32_t mask, uint32_t rng) {
+    const __m512i vmask = _mm512_set1_epi32((int)mask), vrng = _mm512_set1_epi32((int)rng), one = _mm512_set1_epi32(1);
+    const __m512i c1 = _mm512_set1_epi32((int)0x9d2c5680u), c2 = _mm512_set1_epi32((int)0xefc60000u);
+    __m512i acc = _mm512_setzero_si512();
+    for (int k = 0; k < n; k += 16) {
+        const __mmask16 live = n - k >= 16 ? (__mmask16)0xffff : (__mmask16)((1u << (n - k)) - 1u);
+        __m512i y = _mm512_maskz_loadu_epi32(live, key + k);
+        y = _mm512_xor_si512(y, _mm512_srli_epi32(y, 11));
+        y = _mm512_ternarylogic_epi32(y, _mm512_slli_epi32(y, 7), c1, 0x78);        // y ^ (s & c)
+        y = _mm512_ternarylogic_epi32(y, _mm512_slli_epi32(y, 15), c2, 0x78);
+        y = _mm512_xor_si512(y, _mm512_srli_epi32(y, 18));
+        const __mmask16 m = _mm512_mask_cmple_epu32_mask(live, _mm512_and_si512(y, vmask), vrng);
+        acc = _mm512_mask_add_epi32(acc, m, acc, one);
+    }
+    return _mm512_reduce_add_epi32(acc);
 }
 
 bool has_avx512() {
@@ -106,6 +186,11 @@ bool has_avx512() {
         return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("bmi2");
     }();
     return has;
+}
+
+inline void mt_generate(uint32_t* key) {
+    if (has_avx512()) mt_generate_avx512(key);
+    else mt_generate_auto(key);
 }
 
 }  // namespace
@@ -130,6 +215,40 @@ void np_legacy_randint(uint32_t* key, int* pos, uint32_t high, int count, int32_
         done += got;
     }
     *pos = p;
+}
+
+void np_legacy_randint_skip(uint32_t* key, int* pos, uint32_t high, int count, DrawSpan* span) {
+    memcpy(span->key, key, sizeof(span->key));
+    span->pos = *pos;
+    span->high = high;
+    span->count = count;
+    const uint32_t rng = high - 1u;
+    if (rng == 0u || count <= 0) return;      // random_bounded_uint64_fill: rng == 0 consumes nothing
+    uint32_t mask = rng;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    const bool wide = has_avx512();
+    int p = *pos, done = 0;
+    while (done < count) {
+        if (p >= MT_N) { mt_generate(key); p = 0; }
+        if (wide && count - done > MT_N - p) {             // the block cannot complete the request: count all of it
+            done += count_all_avx512(key + p, MT_N - p, mask, rng);
+            p = MT_N;
+            continue;
+        }
+        int got = 0;
+        const size_t used = wide ? count_avx512(key + p, (size_t)(MT_N - p), mask, rng, count - done, &got)
+                                 : count_scalar(key + p, (size_t)(MT_N - p), mask, rng, count - done, &got);
+        p += (int)used;
+        done += got;
+    }
+    *pos = p;
+}
+
+void draw_fill(const DrawSpan& span, int32_t* out) {
+    uint32_t key[MT_N];
+    memcpy(key, span.key, sizeof(key));
+    int pos = span.pos;
+    np_legacy_randint(key, &pos, span.high, span.count, out);
 }
 
 }  // namespace dtsdf

@@ -226,6 +226,38 @@ for i0 in range(0, n, CH):                              # the library, a chunk o
     bad += int(not np.array_equal(got, want))
     bad += int(not (np.array_equal(mine[1], after[1]) and mine[2] == after[2]))
     state = after
+# a call too small for the two-phase form (the plain form), and a frame without points in the middle of a large
+# call: np.random.randint(0, 0) raises in the reference, the stream has advanced by the frames before it
+def reference_draws(counts):                             # pre/process.py:70-84, verbatim calls
+    rows = np.empty((len(counts), point_num), dtype=np.int32)
+    for i, ps in enumerate(int(v) for v in counts):
+        if ps < point_num:
+            rows[i] = np.arange(0, point_num, 1, dtype=np.int32)
+            rows[i, ps:] = np.random.randint(0, ps, size=point_num - ps)
+        else:
+            rows[i] = np.random.randint(0, ps, size=point_num)
+    return rows
+np.random.set_state(state)
+want = reference_draws(n_valid[100:140])
+after = np.random.get_state()
+np.random.set_state(state)
+got = capi.resample_indices(n_valid[100:140], point_num)
+mine = np.random.get_state()
+bad += int(not np.array_equal(got, want))
+bad += int(not (np.array_equal(mine[1], after[1]) and mine[2] == after[2]))
+nv = n_valid[100:700].copy()
+nv[417] = 0
+np.random.set_state(state)
+reference_draws(nv[:417])
+after = np.random.get_state()
+np.random.set_state(state)
+try:
+    capi.resample_indices(nv, point_num)
+    bad += 1
+except ValueError:
+    pass
+mine = np.random.get_state()
+bad += int(not (np.array_equal(mine[1], after[1]) and mine[2] == after[2]))
 # single calls incl. count 0 and high 1 (which consumes nothing)
 np.random.seed(5)
 a = [np.random.randint(0, h, size=c) for h, c in ((1, 10), (7, 0), (2, 33), (1 << 30, 5), (3, 1000))]
