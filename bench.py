@@ -512,7 +512,10 @@ def run_secondary(pkg, dev, rank, world, args, max_over_ranks, barrier):
     vox = pkg.Voxelizer(device=dev.index, voxel_res=R)
     n_host = min(F, 4000)
     h_out = capi.PinnedBuffer((n_host, 3, R, R, R), np.float32)
-    packed_h = np.ascontiguousarray(depth.reshape(-1)[:int(offsets[n_host]) if n_host < F else depth.size])
+    n_in = int(offsets[n_host]) if n_host < F else depth.size
+    h_in = capi.PinnedBuffer((n_in,), np.float32)              # pinned both ways, like the e2e leg of the main line
+    h_in.array[...] = depth.reshape(-1)[:n_in]
+    packed_h = h_in.array
     np.random.seed(7 + rank)
     vox.process_packed(headers[:n_host], offsets[:n_host], packed_h, P, want_points=False, out_vol=h_out.array)
     barrier()
@@ -533,7 +536,7 @@ def run_secondary(pkg, dev, rank, world, args, max_over_ranks, barrier):
     barrier()
     out["process_semantics_host_call"] = {
         "frames_per_gpu": n_host, "ms": dt * 1e3, "value": n_host * world / dt, "unit": "frames/s",
-        "config": "Voxelizer.process_packed(want_points=False) = dtsdf_process_host: host crops in, volumes out (pinned), "
+        "config": "Voxelizer.process_packed(want_points=False) = dtsdf_process_host: host crops in, volumes out (both pinned), "
                   "resampling indices drawn in C from the caller's np.random MT19937 state (bit-compatible with the "
                   "reference's per-frame np.random.randint calls, pre/process.py:75-80); dtsdf_count_valid_batch + "
                   "dtsdf_voxelize_sampled_batch per chunk, the crops uploaded and counted chunk by chunk behind the draws",
@@ -544,6 +547,7 @@ def run_secondary(pkg, dev, rank, world, args, max_over_ranks, barrier):
         "frac": dt_rng / dt}
     vox.close()
     h_out.free()
+    h_in.free()
 
     # ---- ragged crops (every frame its own 80-150 x 80-140 px bounding box)
     n_r = min(F, 4000)

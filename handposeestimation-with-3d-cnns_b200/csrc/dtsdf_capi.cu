@@ -156,7 +156,12 @@ public:
         {
             std::lock_guard<std::mutex> g(m_);
             if (count_ == CAP) return false;
-            ring_[(head_ + count_) % CAP] = j;
+            if (j.draw) {                        // the submitting thread waits for draws: they go in front of expansions
+                head_ = (head_ + CAP - 1) % CAP;
+                ring_[head_] = j;
+            } else {
+                ring_[(head_ + count_) % CAP] = j;
+            }
             ++count_;
         }
         cv_.notify_one();
@@ -846,11 +851,16 @@ struct HostPipeline {
     double* h_pc = nullptr;
     double focal64 = 0.0;
     // the index draw in two phases (csrc/dtsdf_rng.cpp): this thread finds where every frame's draws begin
-    // (sequential, nothing written), the pool threads produce them; chunk k+1 is scanned while chunk k is on the GPU
-    std::vector<dtsdf::DrawSpan> spans[2];
-    DrawRecord draw_rec[2];
-    Latch draw_latch[2];
+    // (sequential, nothing written), the pool threads produce them; the scan runs AHEAD chunks in front of the
+    // chunk being submitted, so the pool works on chunk k+1's draws while this thread scans chunk k+2
+    static const int AHEAD = 2;                    // chunks scanned ahead of the one being submitted
+    std::vector<dtsdf::DrawSpan> spans[AHEAD + 1];
+    DrawRecord draw_rec[AHEAD + 1];
+    Latch draw_latch[AHEAD + 1];
     int scan_chunk(int k);
+    // DTSDF_TRACE=1: where the submitting thread's time went (seconds), printed to stderr at the end of the call
+    double tr_scan = 0, tr_draw_wait = 0, tr_slot_wait = 0, tr_piece_wait = 0, tr_submit = 0, tr_exit = 0;
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
     // finalizer: takes the chunks in order, polls the event behind each one's last copy, hands the
     // chunk to the expansion threads
     std::mutex qm;
@@ -956,13 +966,15 @@ struct HostPipeline {
 // pool gets phase two.  With pieces in flight (dtsdf_process_host without clouds) the chunk's valid-pixel counts
 // are waited for first.
 int HostPipeline::scan_chunk(int k) {
-    const int slot = k % dtsdf_ctx::NSLOT, par = k & 1;
+    const int slot = k % dtsdf_ctx::NSLOT, par = k % (AHEAD + 1);
     const int32_t f0 = k * per_chunk;
     const int32_t nf = std::min(per_chunk, n_frames - f0);
+    const double t_in = now();
     if (c->b_pieces > 0) {
         CK(cudaEventSynchronize(c->ev_piece[(size_t)k]));
         memcpy(c->b_nvalid_h.data() + f0, (const int32_t*)c->m_nvalid.p + f0, (size_t)nf * 4);
     }
+    tr_piece_wait += now() - t_in;
     // the staging buffer of the slot was last read by the host -> device copy of chunk k - NSLOT
     if (k >= dtsdf_ctx::NSLOT) CK(cudaEventSynchronize(c->ev_in[slot]));
     int rc;
@@ -986,6 +998,7 @@ int HostPipeline::scan_chunk(int k) {
         job.f1 = (int32_t)((int64_t)nf * (j + 1) / jobs);
         if (workers == 0 || !c->pool.submit(job)) run_expand_job(job);
     }
+    tr_scan += now() - t_in;
     return DTSDF_OK;
 }
 
@@ -1016,8 +1029,10 @@ int HostPipeline::submit_chunks() {
         // the slot's buffers are free once its previous chunk has left them: plain mode, its D2H
         // has finished (which implies its kernel has); packed mode, the host threads are done
         // expanding it (its kernels were waited for before they started)
+        const double t_slot = now();
         if (packed) c->latch[slot].wait();
         else if (k >= dtsdf_ctx::NSLOT) CK(cudaEventSynchronize(c->ev_out[slot]));
+        tr_slot_wait += now() - t_slot;
         if (k == c->opt_fail_chunk) CK(cudaErrorUnknown);          // injected failure (DTSDF_OPT_TEST_FAIL_CHUNK)
         if (!process_mode) {
             if ((rc = c->d_depth[slot].reserve((size_t)(e1 - e0) * 4)) != DTSDF_OK) return rc;
@@ -1058,8 +1073,11 @@ int HostPipeline::submit_chunks() {
                 if ((rc = c->p_pc[slot].reserve(ni * 24)) != DTSDF_OK) return rc;
                 if (packed && (rc = c->m_pc[slot].reserve(ni * 24)) != DTSDF_OK) return rc;
             }
-            if (k == 0 && (rc = scan_chunk(0)) != DTSDF_OK) return rc;
-            draw_latch[k & 1].wait();
+            for (int a = 0; k == 0 && a < AHEAD && a < nchunk; ++a)
+                if ((rc = scan_chunk(a)) != DTSDF_OK) return rc;
+            const double t_draw = now();
+            draw_latch[k % (AHEAD + 1)].wait();
+            tr_draw_wait += now() - t_draw;
             CK(cudaMemcpyAsync(c->p_idx[slot].p, c->m_idx[slot].p, ni * 4, cudaMemcpyHostToDevice, st_in));
             if (c->b_pieces > 0) CK(cudaStreamWaitEvent(c->s_run, c->ev_piece[(size_t)k], 0));      // the chunk's crops
         }
@@ -1092,7 +1110,7 @@ int HostPipeline::submit_chunks() {
         }
         if (rc != DTSDF_OK) return rc;
         // while the GPU works on this chunk: where the next chunk's draws begin, and its draws on the pool
-        if (process_mode && k + 1 < nchunk && (rc = scan_chunk(k + 1)) != DTSDF_OK) return rc;
+        if (process_mode && k + AHEAD < nchunk && (rc = scan_chunk(k + AHEAD)) != DTSDF_OK) return rc;
 
         if (packed) {
             // pack into device memory on the kernel stream; then, on s_out so that the next chunk's
@@ -1193,6 +1211,7 @@ int HostPipeline::run() {
         fin = std::thread([this] { finalizer(); });
     }
     int rc;
+    const double t_run = now();
     try {
         rc = submit_chunks();
     } catch (const std::bad_alloc&) {
@@ -1201,6 +1220,7 @@ int HostPipeline::run() {
         rc = DTSDF_ERR_INTERNAL;
     }
     // ---- the one exit path
+    tr_submit = now();
     if (rc != DTSDF_OK) cancel.store(true);
     stop_finalizer();
     if (rc == DTSDF_OK && failed.load()) {
@@ -1208,12 +1228,19 @@ int HostPipeline::run() {
         rc = no_memory.load() ? DTSDF_ERR_ALLOC : DTSDF_ERR_CUDA;
     }
     for (int i = 0; i < dtsdf_ctx::NSLOT; ++i) c->latch[i].wait();         // expansion jobs that did start
-    draw_latch[0].wait(); draw_latch[1].wait();                            // draw jobs read this object's spans
+    for (Latch& l : draw_latch) l.wait();                                  // draw jobs read this object's spans
     if (packed) { cudaStreamSynchronize(c->s_lit); cudaGetLastError(); }
     if (process_mode) { cudaStreamSynchronize(c->s_idx); cudaGetLastError(); }
     cudaError_t e_out = single ? cudaSuccess : cudaStreamSynchronize(c->s_out);
     cudaError_t e_run = cudaStreamSynchronize(c->s_run);
     cudaError_t e_in = single ? cudaSuccess : cudaStreamSynchronize(c->s_in);
+    if (getenv("DTSDF_TRACE")) {
+        const double t_end = now();
+        fprintf(stderr, "[dtsdf trace] frames %d chunks %d x %d: call %.2f ms = submit loop %.2f (scan %.2f of which piece wait "
+                        "%.2f; draw wait %.2f; slot wait %.2f) + exit path %.2f\n", n_frames, nchunk, per_chunk,
+                (t_end - t_run) * 1e3, (tr_submit - t_run) * 1e3, tr_scan * 1e3, tr_piece_wait * 1e3, tr_draw_wait * 1e3,
+                tr_slot_wait * 1e3, (t_end - tr_submit) * 1e3);
+    }
     if (rc != DTSDF_OK) { cudaGetLastError(); return rc; }
     if (e_out != cudaSuccess) return cuda_fail(e_out, "cudaStreamSynchronize(s_out)");
     if (e_run != cudaSuccess) return cuda_fail(e_run, "cudaStreamSynchronize(s_run)");
@@ -1637,7 +1664,10 @@ int dtsdf_process_host(dtsdf_ctx* c, const dtsdf_config* cfg_in, double focal, i
         p.c = c; p.cfg = &cfg; p.n_frames = n_frames; p.h_depth = nullptr; p.h_off = nullptr; p.h_hdr = nullptr;
         p.h_aux = nullptr; p.h_vol = h_out_vol; p.h_maxl = h_out_max_l; p.h_mid = h_out_mid_p;
         p.aux_w = 6;
-        p.process_mode = true; p.point_num = point_num; p.mt_key = mt_key; p.mt_pos = &pos; p.h_pc = h_out_pc;
+        // (a 64-byte aligned working copy of the generator state: its vector steps then never split a cache line)
+        alignas(64) uint32_t key_al[640];
+        memcpy(key_al, mt_key, 624 * sizeof(uint32_t));
+        p.process_mode = true; p.point_num = point_num; p.mt_key = key_al; p.mt_pos = &pos; p.h_pc = h_out_pc;
         p.focal64 = focal;
         p.configure();
         // with clouds: back-projection + compaction of every frame up front, crops, tables and clouds resident
@@ -1653,6 +1683,7 @@ int dtsdf_process_host(dtsdf_ctx* c, const dtsdf_config* cfg_in, double focal, i
         }
         rc2 = p.run();
         c->b_pieces = 0;
+        memcpy(mt_key, key_al, 624 * sizeof(uint32_t));
         *mt_pos = pos;
         return rc2;
     });

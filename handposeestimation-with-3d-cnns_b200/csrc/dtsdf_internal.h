@@ -103,7 +103,7 @@ void np_legacy_randint(uint32_t* key, int* pos, uint32_t high, int count, int32_
 // be found in order - but that needs no output: np_legacy_randint_skip steps the generator and counts acceptances
 // (tempering + compare + popcount; no compress-store, nothing written) after leaving a snapshot of the state in the
 // span; draw_fill then produces a frame's draws from its snapshot, any frame on any thread.
-struct DrawSpan {
+struct alignas(64) DrawSpan {
     uint32_t key[624];        // the state the request started from
     int      pos;
     uint32_t high;            // np.random.randint(0, high, size=count)

@@ -1,0 +1,26 @@
+"""Dev probe: the process() host call (dtsdf_process_host, volumes only, pinned buffers) with DTSDF_TRACE=1 -
+where the submitting thread's time goes.  usage: python tools/process_trace.py [frames]"""
+import os, sys, time
+import numpy as np
+os.environ["DTSDF_TRACE"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g
+pkg = g.load_package()
+capi = pkg.capi
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
+frames = pkg.synth.make_frames(range(n), box=pkg.synth.DEFAULT_BOX)
+hdr, off, pk, _ = pkg.pack_frames(frames)
+pin = capi.PinnedBuffer(pk.shape, np.float32)
+pin.array[...] = pk
+out = capi.PinnedBuffer((n, 3, 32, 32, 32), np.float32)
+vox = pkg.Voxelizer(device=0)
+np.random.seed(3)
+for rep in range(4):
+    t0 = time.perf_counter()
+    vox.process_packed(hdr, off, pin.array, 6000, want_points=False, out_vol=out.array)
+    dt = time.perf_counter() - t0
+    print("call %d: %.2f ms = %.0f frames/s" % (rep, dt * 1e3, n / dt), flush=True)
+nv = np.full(n, 8811, dtype=np.int32)
+t0 = time.perf_counter(); capi.resample_indices(nv, 6000); dt = time.perf_counter() - t0
+print("index draw alone: %.2f ms" % (dt * 1e3))
