@@ -1601,8 +1601,7 @@ __device__ __forceinline__ void aug_camera4(const AugTables<R>* __restrict__ T, 
 // value with |d| < 1 ("no depth": the voxel stays 0) when the projection is not finite or outside the crop.
 // STAGED: the crop is in shared memory and the word right below it is 0.0f - the target of "outside".
 template <bool STAGED>
-__device__ __forceinline__ float aug_lookup_rel(const AugFrame& k, float vx, float vy, float vz, int& px, int& py,
-                                                unsigned& rel) {
+__device__ __forceinline__ float aug_lookup(const AugFrame& k, float vx, float vy, float vz, int& px, int& py) {
     const float coeff = __fdiv_rn(-k.focal, vz);
     const float fpx = __fadd_rn(__fmul_rn(vx, coeff), (float)k.cx);
     const float fpy = __fadd_rn(__fmul_rn(-vy, coeff), (float)k.cy);
@@ -1614,15 +1613,8 @@ __device__ __forceinline__ float aug_lookup_rel(const AugFrame& k, float vx, flo
     const float fs = __fadd_rn(fpx, fpy);
     const bool in = ux < (unsigned)k.bw && uy < (unsigned)k.bh && fs == fs;
     const int idx = in ? (int)uy * k.bw + (int)ux : -1;
-    rel = ux | (uy << 16);               // crop-relative pixel (meaningful inside a staged crop: both below 2^16)
     if (STAGED) return k.crop[idx];
     return in ? __ldg(k.crop + idx) : 0.0f;
-}
-
-template <bool STAGED>
-__device__ __forceinline__ float aug_lookup(const AugFrame& k, float vx, float vy, float vz, int& px, int& py) {
-    unsigned rel;
-    return aug_lookup_rel<STAGED>(k, vx, vy, vz, px, py, rel);
 }
 
 // a / trunc and d / focal of pass 2: the fixed-divisor forms (div_fixed, file header) inside their proven
@@ -1702,8 +1694,8 @@ __device__ __forceinline__ void aug_eval_group(const AugFrame& k, const AugTable
     st_f4(p + 2 * CH, make_float4(o2[0], o2[1], o2[2], o2[3]));
 }
 
-// Both passes over one frame, group-granular (crops too large to stage: the rare path).
-template <int R, int LAYOUT, bool STAGED, int NTH>
+// Both passes over one frame.
+template <int R, int LAYOUT, bool STAGED>
 __device__ __forceinline__ void aug_voxel_passes(const AugFrame& k, const AugTables<R>* __restrict__ T,
                                                  const float* __restrict__ A, const float* __restrict__ c,
                                                  unsigned short* __restrict__ list, float* __restrict__ out) {
@@ -1712,7 +1704,7 @@ __device__ __forceinline__ void aug_voxel_passes(const AugFrame& k, const AugTab
     const unsigned lt = (1u << lane) - 1u;
     int cnt = 0;
 #pragma unroll 1
-    for (int g = tid; g < CH / 4; g += NTH) {
+    for (int g = tid; g < CH / 4; g += NT) {
         float4 val;
         bool near = aug_classify_group<R, LAYOUT, STAGED>(k, T, g, val);
         // a 32-byte sector (an even/odd lane pair) is written once, whole: by pass 1 or by pass 2
@@ -1739,179 +1731,6 @@ __device__ __forceinline__ void aug_voxel_passes(const AugFrame& k, const AugTab
     }
     __syncwarp();
     if (lane < cnt) aug_eval_group<R, LAYOUT, STAGED>(k, T, A, c, (int)list[lane], out);
-}
-
-// ---- Staged crops: pass 2 at VOXEL granularity.
-// Pass 1 classifies four voxels per lane as before.  A 32-byte sector still has to be written once and whole, so
-// a sector with a near-surface voxel cannot be stored by pass 1 - but only its NEAR voxels need the full
-// evaluation (the group-granular form evaluated all eight voxels of the sector: 35 % of all voxels for ~13 % that
-// are near, and pass 2 was 45 % of the kernel's instructions).  Per warp, in shared memory:
-//   * a ring of pending groups: { group | far codes of its four voxels (0, +1, -1) | near mask, end of its voxels
-//     in the voxel ring (monotone count, 16 bits) | ring position of its first voxel };
-//   * a ring of pending near voxels, three words each: { depth, crop-relative pixel, 4 * group + j } - pass 1
-//     has already projected the voxel and looked the depth up, pass 2 does not repeat it - overwritten in place
-//     by the three channel values once evaluated.
-// Whenever 32 voxels are pending they are evaluated, one per lane, all lanes busy; groups whose voxels are all
-// done (a prefix of the ring: voxels enter in group order) are assembled - evaluated values for the near
-// voxels, decoded far codes for the others - and stored, 3 x 16 bytes per lane.  Same arithmetic per voxel as the
-// specification (oracle/dtsdf_oracle.c, oracle_dtsdf_aug_frame): bit-identical results.
-constexpr int AUG_CAPG = 64;        // groups: at most 32 left pending by a step (more forces a drain) + 32 new
-constexpr int AUG_CAPV = 160;       // voxels: at most 31 left pending by a step + 4 x 32 new
-
-template <int NW>
-struct __align__(16) AugRings {
-    uint2 grp[NW][AUG_CAPG];
-    float vd[NW][AUG_CAPV];
-    unsigned vp[NW][AUG_CAPV];
-    unsigned vk[NW][AUG_CAPV];
-};
-
-// One near voxel: the specification's evaluation from the depth and pixel pass 1 found.
-template <int R, int LAYOUT>
-__device__ __forceinline__ void aug_eval_voxel(const AugFrame& k, const AugTables<R>* __restrict__ T,
-                                               const float* __restrict__ A, const float* __restrict__ c,
-                                               unsigned key, float d, unsigned rel, float& t0, float& t1, float& t2) {
-    int f0, m, s;
-    aug_group_index<R, LAYOUT>((int)(key >> 2), f0, m, s);
-    const int j = (int)(key & 3u);
-    const int xi = LAYOUT == 0 ? s : f0 + j, zi = LAYOUT == 0 ? f0 + j : s;
-    const float va0 = T->va[0][xi], va1 = T->va[1][m], va2 = T->va[2][zi];
-    const float vz = __fadd_rn(T->tx[xi].z, __fadd_rn(T->ty[m].z, T->tz[zi].z));      // as aug_camera4 forms it
-    const int dx = (int)(rel & 0xffffu) + k.l - k.cx, dy = (int)(rel >> 16) + k.t - k.cy;
-    const float c1 = aug_div_focal(k, d);
-    float wa[3];
-    xform(__fmul_rn((float)dx, c1), __fmul_rn((float)(-dy), c1), -d, A, c, wa);
-    t0 = fabsf(aug_div_trunc(k, __fsub_rn(va0, wa[0])));          // |a| / b == |a / b| under RN
-    t1 = fabsf(aug_div_trunc(k, __fsub_rn(va1, wa[1])));
-    t2 = fabsf(aug_div_trunc(k, __fsub_rn(va2, wa[2])));
-    const float ss = __fadd_rn(__fadd_rn(__fmul_rn(t0, t0), __fmul_rn(t1, t1)), __fmul_rn(t2, t2));
-    if (ss > THR_SQ) { t0 = 1.0f; t1 = 1.0f; t2 = 1.0f; }        // sqrt_rn(ss) > 1 <=> ss > nextafter(1,2)
-    if (1.0f < t0) t0 = 1.0f;
-    if (1.0f < t1) t1 = 1.0f;
-    if (1.0f < t2) t2 = 1.0f;
-    if (-d > vz) { t0 = -t0; t1 = -t1; t2 = -t2; }
-}
-
-template <int R, int LAYOUT, int NTH>
-__device__ __forceinline__ void aug_voxel_passes_staged(const AugFrame& k, const AugTables<R>* __restrict__ T,
-                                                        const float* __restrict__ A, const float* __restrict__ c,
-                                                        uint2* __restrict__ grp, float* __restrict__ vd,
-                                                        unsigned* __restrict__ vp, unsigned* __restrict__ vk,
-                                                        float* __restrict__ out) {
-    constexpr int CH = R * R * R;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    unsigned g_head = 0, g_tail = 0;            // groups: monotone counts, ring index = count & (AUG_CAPG - 1)
-    unsigned v_head = 0, v_tail = 0;            // voxels: monotone counts ...
-    int vh_w = 0, vt_w = 0;                     // ... and the same positions inside the ring
-
-    // evaluates pending voxels in rounds of 32 (all of them when `all`), then stores the groups that are complete
-    auto flush = [&](bool all) {
-        bool any_round = false;
-        while (v_tail - v_head >= 32u || (all && v_tail != v_head)) {
-            const unsigned n = min(32u, v_tail - v_head);
-            if ((unsigned)lane < n) {
-                int q = vh_w + lane;
-                if (q >= AUG_CAPV) q -= AUG_CAPV;
-                float t0, t1, t2;
-                aug_eval_voxel<R, LAYOUT>(k, T, A, c, vk[q], vd[q], vp[q], t0, t1, t2);
-                vd[q] = t0; vp[q] = __float_as_uint(t1); vk[q] = __float_as_uint(t2);
-            }
-            v_head += n;
-            vh_w += (int)n;
-            if (vh_w >= AUG_CAPV) vh_w -= AUG_CAPV;
-            any_round = true;
-        }
-        if (!any_round && !all) return;
-        __syncwarp();
-#pragma unroll 1
-        for (unsigned base = g_head; (int)(g_tail - base) > 0; base += 32u) {
-            const unsigned sidx = base + (unsigned)lane;
-            bool ready = false;
-            uint2 rec = make_uint2(0u, 0u);
-            if ((int)(g_tail - sidx) > 0) {
-                rec = grp[sidx & (AUG_CAPG - 1)];
-                ready = (short)((v_head & 0xffffu) - (rec.y & 0xffffu)) >= 0;       // all its voxels are evaluated
-            }
-            if (ready) {
-                int q = (int)(rec.y >> 16);
-                float o0[4], o1[4], o2[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const unsigned code = (rec.x >> (16 + 2 * j)) & 3u;
-                    const float far = code == 0u ? 0.0f : (code == 2u ? -1.0f : 1.0f);
-                    o0[j] = far; o1[j] = far; o2[j] = far;
-                    if ((rec.x >> (24 + j)) & 1u) {
-                        o0[j] = vd[q]; o1[j] = __uint_as_float(vp[q]); o2[j] = __uint_as_float(vk[q]);
-                        q = q + 1 == AUG_CAPV ? 0 : q + 1;
-                    }
-                }
-                float* p = out + 4 * (size_t)(rec.x & 0xffffu);
-                st_f4(p, make_float4(o0[0], o0[1], o0[2], o0[3]));
-                st_f4(p + CH, make_float4(o1[0], o1[1], o1[2], o1[3]));
-                st_f4(p + 2 * CH, make_float4(o2[0], o2[1], o2[2], o2[3]));
-            }
-            const unsigned done = __ballot_sync(FULL, ready);
-            g_head += (unsigned)__popc(done);                  // (complete groups are a prefix of the ring)
-            if (done != FULL) break;
-        }
-        __syncwarp();
-    };
-
-#pragma unroll 1
-    for (int g = tid; g < CH / 4; g += NTH) {
-        int f0, m, s;
-        aug_group_index<R, LAYOUT>(g, f0, m, s);
-        float vx[4], vy[4], vz[4], o[4], d[4];
-        unsigned rel[4], nm = 0u, codes = 0u;
-        aug_camera4<R, LAYOUT>(T, f0, m, s, vx, vy, vz);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int px, py;
-            d[j] = aug_lookup_rel<true>(k, vx[j], vy[j], vz[j], px, py, rel[j]);
-            const float sz = __fadd_rn(vz[j], d[j]);                   // v_z - w_z, w_z = -d
-            const bool valid = !(fabsf(d[j]) < 1.0f);
-            const bool far = fabsf(sz) > k.t_far && fabsf(d[j]) < BIG_DEPTH;
-            const bool neg = sz < 0.0f;                                 // (a near voxel's code is not used)
-            o[j] = (valid && far) ? (neg ? -1.0f : 1.0f) : 0.0f;
-            codes |= ((valid && far) ? (neg ? 2u : 1u) : 0u) << (2 * j);
-            nm |= ((valid && !far) ? 1u : 0u) << j;
-        }
-        const unsigned b0 = __ballot_sync(FULL, nm & 1u), b1 = __ballot_sync(FULL, nm & 2u);
-        const unsigned b2 = __ballot_sync(FULL, nm & 4u), b3 = __ballot_sync(FULL, nm & 8u);
-        const unsigned any = b0 | b1 | b2 | b3;
-        // a 32-byte sector (an even/odd lane pair) is written once, whole: here or when its near voxels are done
-        const unsigned listed = any | ((any & 0x55555555u) << 1) | ((any & 0xAAAAAAAAu) >> 1);
-        if (!((listed >> lane) & 1u)) {
-            float* p = out + 4 * (size_t)g;
-            const float4 val = make_float4(o[0], o[1], o[2], o[3]);
-            st_f4(p, val); st_f4(p + CH, val); st_f4(p + 2 * CH, val);
-        } else {
-            const unsigned off = (unsigned)(__popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt));
-            int q = vt_w + (int)off;
-            if (q >= AUG_CAPV) q -= AUG_CAPV;
-            const unsigned vend = v_tail + off + (unsigned)__popc(nm);
-            grp[(g_tail + (unsigned)__popc(listed & lt)) & (AUG_CAPG - 1)] =
-                make_uint2((unsigned)g | (codes << 16) | (nm << 24), (vend & 0xffffu) | ((unsigned)q << 16));
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if ((nm >> j) & 1u) {
-                    vd[q] = d[j]; vp[q] = rel[j]; vk[q] = 4u * (unsigned)g + (unsigned)j;
-                    q = q + 1 == AUG_CAPV ? 0 : q + 1;
-                }
-        }
-        if (any == 0u) continue;                                   // (warp-uniform)
-        const unsigned tot = (unsigned)(__popc(b0) + __popc(b1) + __popc(b2) + __popc(b3));
-        g_tail += (unsigned)__popc(listed);
-        v_tail += tot;
-        vt_w += (int)tot;
-        if (vt_w >= AUG_CAPV) vt_w -= AUG_CAPV;
-        __syncwarp();
-        flush(false);
-        if (g_tail - g_head > 32u) flush(true);                    // (few voxels, many groups: make room)
-    }
-    __syncwarp();
-    flush(true);
 }
 
 // Far-surface shortcut of the augmented path.  In exact arithmetic v' - w' = (v* - w) . A with v* the
@@ -1998,6 +1817,7 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
     __shared__ float aug[21];
     __shared__ unsigned long long bar;
     __shared__ AugTables<R> tab;
+    __shared__ float t_far_s;
     // the staged crop starts 16 bytes into the dynamic shared memory; the word right below it is 0.0f
     // ("no depth"), where lookups that fall outside the crop are pointed
     float* crop_s = reinterpret_cast<float*>(smem_raw + 16);
@@ -2130,8 +1950,10 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
     k.yf = __frcp_rn(focal); k.ytr = __frcp_rn(trunc);
     k.fast_f = __float_as_uint(focal) == DEFAULT_FOCAL_BITS;
     k.fast_t = trunc >= 0x1p-20f && trunc <= 0x1p20f;
-    k.t_far = aug_far_threshold(A, Ainv, c, trunc, max_l, mid0, mid1, mid2);
+    // (one thread, not one of those filling the tables: a few hundred instructions that every thread used to repeat)
+    if (tid == NT - 1) t_far_s = aug_far_threshold(A, Ainv, c, trunc, max_l, mid0, mid1, mid2);
     __syncthreads();          // the tables are complete
+    k.t_far = t_far_s;
     float* out = a.vol + (size_t)f * 3 * CH;
     if (fr.staged) aug_voxel_passes<R, LAYOUT, true>(k, &tab, A, c, glist[warp], out);
     else           aug_voxel_passes<R, LAYOUT, false>(k, &tab, A, c, glist[warp], out);
