@@ -1412,9 +1412,27 @@ __global__ void __launch_bounds__(NT) count_valid_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------- point cloud (f64)
+// a / b in float64 for a per-launch divisor b with y = rcp_rn(b): q = a y and two residual corrections
+// q += fma(-b, q, a) y.  The first brings q within half an ulp (and a hair) of a / b whatever the rounding of a y
+// did; for a faithful q and a correctly rounded reciprocal the correction is the correctly rounded quotient
+// (Markstein 1990; the one divisor class the theorem excepts - a significand of all ones - takes the IEEE path,
+// like every dividend outside 2^-900 .. 2^900, zeros included: their residuals would lose the sign / overflow).
+// tests/native/ddivision_check.c runs the same five operations against the host's IEEE division on 2 x 10^8
+// dividends, half of them built to put the quotient within a few units of 2^-53 ulp of a rounding boundary.
+__device__ __forceinline__ double ddiv_fixed(double a, double b, double y, bool fast_b) {
+    const double m = fabs(a);
+    if (!(fast_b && m >= 0x1p-900 && m <= 0x1p900)) return __ddiv_rn(a, b);
+    double q = __dmul_rn(a, y);
+    q = __fma_rn(__fma_rn(-b, q, a), y, q);
+    q = __fma_rn(__fma_rn(-b, q, a), y, q);
+    return q;
+}
+
 // pre/process.py:30-68: X = ((u+left) - w/2)*d / f, Y = -(((v+top) - h/2)*d) / f, Z = -d in
-// float64, keeping the pixels with d != 0 in row-major order.  One CTA per frame; block-wide
-// stream compaction with ballot + prefix sums.
+// float64, keeping the pixels with d != 0 in row-major order.  One CTA per frame.  Every warp owns a contiguous
+// piece of the crop: it counts its valid pixels, ONE block barrier turns the eight counts into output offsets, and
+// the warps then write their pieces on their own (ballot + popc per 32 pixels) - round 1 synchronised the block
+// three times per 256 pixels and paid two IEEE float64 divisions per point (0.95 TB/s).
 __global__ void __launch_bounds__(NT) point_cloud_kernel(int n_frames, double focal,
                                                          const float* __restrict__ depth,
                                                          const long long* __restrict__ offsets,
@@ -1423,7 +1441,6 @@ __global__ void __launch_bounds__(NT) point_cloud_kernel(int n_frames, double fo
                                                          const long long* __restrict__ point_offsets,
                                                          int* __restrict__ n_valid) {
     __shared__ int warp_cnt[NWARP];
-    __shared__ int base_s;
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int* h = headers + 6 * (size_t)f;
@@ -1432,40 +1449,52 @@ __global__ void __launch_bounds__(NT) point_cloud_kernel(int n_frames, double fo
     const int n = (bw > 0 && bh > 0) ? bw * bh : 0;
     const float* crop = depth + offsets[f];
     double* out = points ? points + 3 * point_offsets[f] : nullptr;
-    const double half_w = (double)w / 2.0, half_h = (double)hh / 2.0;
-    if (tid == 0) base_s = 0;
+    // the warp's piece: steps of 32 pixels [s0, s1)
+    const int steps = (n + 31) >> 5, per_warp = (steps + NWARP - 1) / NWARP;
+    const int s0 = min(warp * per_warp, steps), s1 = min(s0 + per_warp, steps);
+    int cnt = 0;
+    for (int st = s0; st < s1; ++st) {
+        const int pos = 32 * st + lane;
+        const float d = pos < n ? __ldg(crop + pos) : 0.0f;
+        cnt += __popc(__ballot_sync(FULL, d != 0.0f));                   // any(row) of pre/process.py:63
+    }
+    if (lane == 0) warp_cnt[warp] = cnt;
     __syncthreads();
-    for (int p0 = 0; p0 < n; p0 += NT) {
-        const int pos = p0 + tid;
-        float d = 0.0f;
-        if (pos < n) d = __ldg(crop + pos);
-        const bool keep = (pos < n) && (d != 0.0f);            // any(row) of pre/process.py:63
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_cnt[warp] = __popc(m);
-        __syncthreads();
-        int before = base_s;
-        int total = 0;
+    int before = 0, total = 0;
 #pragma unroll
-        for (int i = 0; i < NWARP; ++i) {
-            const int c = warp_cnt[i];
-            if (i < warp) before += c;
-            total += c;
-        }
-        if (keep && out) {
-            const int dst = before + __popc(m & ((1u << lane) - 1u));
-            const int row = pos / bw, col = pos - row * bw;
+    for (int i = 0; i < NWARP; ++i) {
+        const int c = warp_cnt[i];
+        if (i < warp) before += c;
+        total += c;
+    }
+    if (tid == 0) n_valid[f] = total;
+    if (out == nullptr || s0 >= s1) return;
+    const double half_w = (double)w / 2.0, half_h = (double)hh / 2.0;
+    const double yf = __drcp_rn(focal);
+    const unsigned long long fb = (unsigned long long)__double_as_longlong(focal);
+    const int fe = (int)((fb >> 52) & 0x7ff);
+    const bool fast_b = fe > 1023 - 100 && fe < 1023 + 100 && (fb & 0xfffffffffffffull) != 0xfffffffffffffull;
+    const unsigned lt = (1u << lane) - 1u;
+    int pos = 32 * s0 + lane;
+    int row = pos / bw, col = pos - row * bw;
+    for (int st = s0; st < s1; ++st, pos += 32) {
+        const float d = pos < n ? __ldg(crop + pos) : 0.0f;
+        const bool keep = d != 0.0f;
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (keep) {
+            // (staging the 32 points in shared memory and storing them as one contiguous run was measured: no gain)
+            const size_t dst = (size_t)(before + __popc(m & lt));
             const double dd = (double)d;
             const double u = ((double)col + (double)l) - half_w;
             const double v = ((double)row + (double)t) - half_h;
-            out[3 * (size_t)dst + 0] = __ddiv_rn(__dmul_rn(u, dd), focal);
-            out[3 * (size_t)dst + 1] = __ddiv_rn(-__dmul_rn(v, dd), focal);
-            out[3 * (size_t)dst + 2] = -dd;
+            out[3 * dst + 0] = ddiv_fixed(__dmul_rn(u, dd), focal, yf, fast_b);
+            out[3 * dst + 1] = ddiv_fixed(-__dmul_rn(v, dd), focal, yf, fast_b);
+            out[3 * dst + 2] = -dd;
         }
-        __syncthreads();
-        if (tid == 0) base_s += total;
-        __syncthreads();
+        before += __popc(m);
+        col += 32;
+        while (col >= bw) { col -= bw; ++row; }
     }
-    if (tid == 0) n_valid[f] = base_s;
 }
 
 // pre/process.py:82 (gather by the caller's index vector) + :102-120 (per-axis extrema,

@@ -29,3 +29,15 @@ def test_two_correction_division_random(checker):
     out = subprocess.run([checker, "random", "400000000"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "mismatches=0" in out.stdout
+
+
+def test_float64_division_by_a_fixed_divisor(tmp_path):
+    """point_cloud_kernel's X = (u d) / f and Y in float64: reciprocal multiplication + two residual corrections
+    (ddiv_fixed) equals IEEE division on 2 x 10^8 dividends, half of them with the quotient next to a rounding
+    boundary, for the default focal and 258 other divisors (tests/native/ddivision_check.c)."""
+    exe = str(tmp_path / "ddivision_check")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-fopenmp", os.path.join(HERE, "native", "ddivision_check.c"),
+                    "-o", exe, "-lm"], check=True)
+    out = subprocess.run([exe, "200000000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "mismatches=0" in out.stdout
