@@ -1569,6 +1569,15 @@ __device__ __forceinline__ void xform(float px, float py, float pz, const float*
     }
 }
 
+// CTA shape of the augmented kernel: 8 warps, three CTAs per SM (the staged crop allows no more).  Measured on B200,
+// 8,500 default frames: 256 x 3 1.306 ms; 512 x 2 (64 registers, 140 bytes spilled) 1.453 ms; 384 x 2 with the
+// round-2 experiments 1.49 ms - with two CTAs per SM nothing covers a CTA's prologue (crop wait, bounding box, tables).
+#ifndef DTSDF_AUG_NT
+#define DTSDF_AUG_NT 256
+#define DTSDF_AUG_MIN_CTAS 3
+#endif
+constexpr int AUG_NT = DTSDF_AUG_NT, AUG_NW = AUG_NT / 32, AUG_MIN_CTAS = DTSDF_AUG_MIN_CTAS;
+
 // Per-frame constants of the augmented voxel loop.
 struct AugFrame {
     const float* crop;            // staged (shared) or global crop
@@ -1733,7 +1742,7 @@ __device__ __forceinline__ void aug_voxel_passes(const AugFrame& k, const AugTab
     const unsigned lt = (1u << lane) - 1u;
     int cnt = 0;
 #pragma unroll 1
-    for (int g = tid; g < CH / 4; g += NT) {
+    for (int g = tid; g < CH / 4; g += AUG_NT) {
         float4 val;
         bool near = aug_classify_group<R, LAYOUT, STAGED>(k, T, g, val);
         // a 32-byte sector (an even/odd lane pair) is written once, whole: by pass 1 or by pass 2
@@ -1839,10 +1848,10 @@ __device__ __forceinline__ float aug_far_threshold(const float* __restrict__ A, 
 }
 
 template <int R, int LAYOUT>
-__global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ BatchArgs a,
+__global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const __grid_constant__ BatchArgs a,
                                                        const float* __restrict__ aug_all) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ float red[NWARP][8];
+    __shared__ float red[AUG_NW][8];
     __shared__ float aug[21];
     __shared__ unsigned long long bar;
     __shared__ AugTables<R> tab;
@@ -1877,7 +1886,7 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
         const float yf = __frcp_rn(focal);
         const bool deff = __float_as_uint(focal) == DEFAULT_FOCAL_BITS;
         const float2 nc2 = make_float2(-c[2], -c[2]);
-        for (int row = warp; row < fr.bh; row += NWARP) {
+        for (int row = warp; row < fr.bh; row += AUG_NW) {
             const float fy = (float)(row + fr.t - a.center_y);
             for (int col = lane; col < fr.bw; col += 64) {
                 const float d0 = crop[row * fr.bw + col];
@@ -1918,7 +1927,7 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
         *reinterpret_cast<float2*>(&red[warp][4]) = make_float2(mx[1], mx[2]);
     }
     __syncthreads();
-    bbox_reduce<NWARP>(red, mn, mx);
+    bbox_reduce<AUG_NW>(red, mn, mx);
 
     // ---- 2. grid parameters (pre/process.py:91-96)
     const float mid0 = __fmul_rn(__fadd_rn(mx[0], mn[0]), 0.5f);
@@ -1960,7 +1969,7 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
     //      near-surface voxels go to a per-warp list and are evaluated 32 at a time by pass 2 with all lanes
     //      busy (the specification's arithmetic, IEEE divisions).
     constexpr int CH = R * R * R;
-    static_assert((CH / 4) % NT == 0 && CH / 4 <= 65536 && 3 * R <= NT, "groups per frame: whole warps, 16-bit list entries");
+    static_assert((CH / 4) % AUG_NT == 0 && CH / 4 <= 65536 && 3 * R <= AUG_NT, "groups per frame: whole warps, 16-bit list entries");
     if (tid < 3 * R) {
         const int axis = tid / R, i = tid - axis * R;
         const float o = axis == 0 ? ox : (axis == 1 ? oy : oz);
@@ -1972,7 +1981,7 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
         else                tab.tz[i] = make_float4(__fmaf_rn(dd, Ainv[6], c[0]), __fmaf_rn(dd, Ainv[7], c[1]),
                                                     __fmaf_rn(dd, Ainv[8], c[2]), 0.0f);
     }
-    __shared__ unsigned short glist[NWARP][64];
+    __shared__ unsigned short glist[AUG_NW][64];
     AugFrame k;
     k.crop = crop; k.l = fr.l; k.t = fr.t; k.bw = max(fr.bw, 0); k.bh = max(fr.bh, 0);   // bad header: empty crop
     k.cx = a.center_x; k.cy = a.center_y; k.focal = focal; k.trunc = trunc;
@@ -1980,7 +1989,7 @@ __global__ void __launch_bounds__(NT) dtsdf_aug_kernel(const __grid_constant__ B
     k.fast_f = __float_as_uint(focal) == DEFAULT_FOCAL_BITS;
     k.fast_t = trunc >= 0x1p-20f && trunc <= 0x1p20f;
     // (one thread, not one of those filling the tables: a few hundred instructions that every thread used to repeat)
-    if (tid == NT - 1) t_far_s = aug_far_threshold(A, Ainv, c, trunc, max_l, mid0, mid1, mid2);
+    if (tid == AUG_NT - 1) t_far_s = aug_far_threshold(A, Ainv, c, trunc, max_l, mid0, mid1, mid2);
     __syncthreads();          // the tables are complete
     k.t_far = t_far_s;
     float* out = a.vol + (size_t)f * 3 * CH;
@@ -2018,7 +2027,7 @@ cudaError_t launch_aug_t(const BatchArgs& args_in, const float* aug, int max_cro
     static std::atomic<unsigned> smem_ok{0u};
     e = allow_max_smem(kern, dev, smem_optin, smem_ok);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)args.n_frames, NT, (size_t)want + 16, stream>>>(args, aug);          // + the zero word below the crop
+    kern<<<(unsigned)args.n_frames, AUG_NT, (size_t)want + 16, stream>>>(args, aug);          // + the zero word below the crop
     ++g_launch_count;
     return cudaGetLastError();
 }
