@@ -705,11 +705,13 @@ def run_ours(args, rank, local_rank, world):
         # alone, same threads, same destination, all ranks at once), (2) the crops over PCIe (host -> device alone)
         lazy, _, _ = vox.voxelize_packed_lazy(headers, offsets, h_packed.array, layout=args.layout, bbox_mode=pkg.BBOX_PIXELS)
         lazy.expand(out=h_vol.array)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(3):
+        best = float("inf")                            # a bound: the fastest of five repetitions (box noise is one-sided)
+        for _ in range(5):
+            barrier()
+            t0 = time.perf_counter()
             lazy.expand(out=h_vol.array)
-        expand_rate = F * world * 3 / max_over_ranks(time.perf_counter() - t0)
+            best = min(best, max_over_ranks(time.perf_counter() - t0))
+        expand_rate = F * world / best
         barrier()
         packed_host_bytes = lazy.nbytes
         lazy.close()

@@ -223,17 +223,76 @@ struct Latch {
 
 // Volumes left packed in host memory by dtsdf_voxelize_host_packed: per pipeline chunk its code bytes,
 // literal offsets and literal stream exactly as they crossed PCIe (dtsdf_internal.h, compact container).
+namespace {
+// Storage of packed chunks that outlives a handle: a chunk is ~8 MB, and memory fresh from the allocator costs a
+// page fault per 4 KB when the expansion threads first write it (a fresh 400 MB result: more time in the kernel's
+// page-fault path than in the whole GPU pipeline).  Blocks of freed handles wait here - at most 1 GB of them - for
+// the next result; a training loop that packs a set per epoch then never touches fresh memory.
+class BlockCache {
+public:
+    struct Block { unsigned char* p = nullptr; size_t cap = 0; };
+    Block take(size_t need) {                      // may throw std::bad_alloc
+        {
+            std::lock_guard<std::mutex> g(m_);
+            for (size_t i = 0; i < free_.size(); ++i)
+                if (free_[i].cap >= need && free_[i].cap <= 2 * need + 4096) {
+                    Block b = free_[i];
+                    free_[i] = free_.back();
+                    free_.pop_back();
+                    held_ -= b.cap;
+                    return b;
+                }
+        }
+        Block b;
+        b.cap = (need + 4095) & ~(size_t)4095;
+        b.p = new unsigned char[b.cap];
+        return b;
+    }
+    void give(Block b) noexcept {
+        if (!b.p) return;
+        {
+            std::lock_guard<std::mutex> g(m_);
+            if (held_ + b.cap <= LIMIT && free_.size() < free_.capacity()) {
+                free_.push_back(b);
+                held_ += b.cap;
+                return;
+            }
+        }
+        delete[] b.p;
+    }
+    BlockCache() { free_.reserve(4096); }
+private:
+    static constexpr size_t LIMIT = (size_t)1 << 30;
+    std::mutex m_;
+    std::vector<Block> free_;
+    size_t held_ = 0;
+};
+BlockCache& blocks() {                             // (never destroyed: handles may be freed during process exit)
+    static BlockCache* cache = new BlockCache();
+    return *cache;
+}
+}  // namespace
+
 struct dtsdf_packed_host {
     int32_t n_frames = 0, voxel_res = 0, per_chunk = 1;
     size_t r3 = 0;
     struct Chunk {
         int32_t f0 = 0, nf = 0;
-        std::unique_ptr<unsigned char[]> codes;          // [nf][r3/4]
-        std::unique_ptr<unsigned long long[]> loff;      // [nf+1]
-        std::unique_ptr<float[]> lits;                   // [3 * loff[nf]]
+        BlockCache::Block block;                          // one allocation: [loff | codes | lits]
+        unsigned long long* loff = nullptr;               // [nf+1]
+        unsigned char* codes = nullptr;                   // [nf][r3/4]
+        float* lits = nullptr;                            // [3 * loff[nf]]
+        void bind(int32_t frames, size_t r3_, unsigned long long total) {      // may throw std::bad_alloc
+            const size_t b_loff = ((size_t)frames + 1) * 8, b_codes = ((size_t)frames * (r3_ / 4) + 15) & ~(size_t)15;
+            block = blocks().take(b_loff + 8 + b_codes + 12 * (size_t)total + 16);
+            loff = reinterpret_cast<unsigned long long*>(block.p);
+            codes = block.p + ((b_loff + 15) & ~(size_t)15);
+            lits = reinterpret_cast<float*>(codes + b_codes);
+        }
     };
     std::vector<Chunk> chunks;
     std::atomic<long long> bytes{0};
+    ~dtsdf_packed_host() { for (Chunk& ch : chunks) blocks().give(ch.block); }
 };
 
 struct dtsdf_ctx {
@@ -776,9 +835,9 @@ void run_expand_job(const ExpandJob& j) {
     const float* lits = (const float*)c->m_lits[r->slot].p;
     if (r->keep) {                               // packed result: this job's share of the chunk, as it is
         const size_t cb = r->r3 / 4;
-        memcpy(r->keep->codes.get() + (size_t)j.f0 * cb, codes + (size_t)j.f0 * cb, (size_t)(j.f1 - j.f0) * cb);
-        memcpy(r->keep->lits.get() + 3 * loff[j.f0], lits + 3 * loff[j.f0], (size_t)(loff[j.f1] - loff[j.f0]) * 12);
-        if (j.f0 == 0) memcpy(r->keep->loff.get(), loff, (size_t)(r->nf + 1) * 8);
+        memcpy(r->keep->codes + (size_t)j.f0 * cb, codes + (size_t)j.f0 * cb, (size_t)(j.f1 - j.f0) * cb);
+        memcpy(r->keep->lits + 3 * loff[j.f0], lits + 3 * loff[j.f0], (size_t)(loff[j.f1] - loff[j.f0]) * 12);
+        if (j.f0 == 0) memcpy(r->keep->loff, loff, (size_t)(r->nf + 1) * 8);
         c->latch[r->slot].done();
         return;
     }
@@ -909,9 +968,7 @@ struct HostPipeline {
                         const dtsdf_ctx::ChunkRecord& r = c->chunk[slot];
                         const unsigned long long total = ((const unsigned long long*)c->m_loff[slot].p)[r.nf];
                         try {
-                            r.keep->codes.reset(new unsigned char[(size_t)r.nf * (r.r3 / 4)]);
-                            r.keep->loff.reset(new unsigned long long[(size_t)r.nf + 1]);
-                            r.keep->lits.reset(new float[3 * (size_t)total + 4]);
+                            r.keep->bind(r.nf, r.r3, total);
                             result->bytes += (long long)r.nf * (long long)(r.r3 / 4) + 8ll * (r.nf + 1) + 12ll * (long long)total;
                         } catch (...) {
                             ok = false;
@@ -1326,7 +1383,7 @@ int dtsdf_expand_frames(const dtsdf_packed_host* h, int32_t first, int32_t count
         for (int32_t f = a; f < b; ++f) {
             const dtsdf_packed_host::Chunk& ch = h->chunks[(size_t)(f / h->per_chunk)];
             const int32_t i = f - ch.f0;
-            dtsdf::decode_frame(ch.codes.get() + (size_t)i * (r3 / 4), ch.lits.get() + 3 * ch.loff[i],
+            dtsdf::decode_frame(ch.codes + (size_t)i * (r3 / 4), ch.lits + 3 * ch.loff[i],
                                 (size_t)(ch.loff[i + 1] - ch.loff[i]), r3, h_out + (size_t)(f - first) * vol_floats);
         }
     };
