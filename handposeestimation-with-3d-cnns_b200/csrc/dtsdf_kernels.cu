@@ -1432,7 +1432,10 @@ __device__ __forceinline__ double ddiv_fixed(double a, double b, double y, bool 
 // float64, keeping the pixels with d != 0 in row-major order.  One CTA per frame.  Every warp owns a contiguous
 // piece of the crop: it counts its valid pixels, ONE block barrier turns the eight counts into output offsets, and
 // the warps then write their pieces on their own (ballot + popc per 32 pixels) - round 1 synchronised the block
-// three times per 256 pixels and paid two IEEE float64 divisions per point (0.95 TB/s).
+// three times per 256 pixels and paid two IEEE float64 divisions per point (0.95 TB/s).  The crop is read twice
+// (count, then write): a crop of up to PC_STAGE_FLOATS pixels is staged in shared memory by ONE TMA bulk copy (three
+// CTAs per SM) and both passes read it there; larger crops are read from global memory, eight steps of loads in flight.
+constexpr int PC_STAGE_FLOATS = 18 * 1024;          // 72 KB: the MSRA crops (<= 150 x 140) almost always fit
 __global__ void __launch_bounds__(NT) point_cloud_kernel(int n_frames, double focal,
                                                          const float* __restrict__ depth,
                                                          const long long* __restrict__ offsets,
@@ -1440,22 +1443,38 @@ __global__ void __launch_bounds__(NT) point_cloud_kernel(int n_frames, double fo
                                                          double* __restrict__ points,
                                                          const long long* __restrict__ point_offsets,
                                                          int* __restrict__ n_valid) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int warp_cnt[NWARP];
+    __shared__ unsigned long long bar;
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int* h = headers + 6 * (size_t)f;
     const int w = h[0], hh = h[1], l = h[2], t = h[3], r = h[4], b = h[5];
     const int bw = r - l, bh = b - t;
     const int n = (bw > 0 && bh > 0) ? bw * bh : 0;
-    const float* crop = depth + offsets[f];
+    const float* crop_g = depth + offsets[f];                // 16-byte aligned, padded to 4 floats (packed batch)
+    const int n_pad = (n + 3) & ~3;
+    const bool staged = n > 0 && n_pad <= PC_STAGE_FLOATS;   // (CTA-uniform)
+    if (staged) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(&bar, (uint32_t)n_pad * 4u);
+            bulk_g2s(smem_raw, crop_g, (uint32_t)n_pad * 4u, &bar);
+        }
+        __syncthreads();
+        mbar_wait(&bar, 0);
+    }
+    const float* crop = staged ? reinterpret_cast<const float*>(smem_raw) : crop_g;
     double* out = points ? points + 3 * point_offsets[f] : nullptr;
     // the warp's piece: steps of 32 pixels [s0, s1)
     const int steps = (n + 31) >> 5, per_warp = (steps + NWARP - 1) / NWARP;
     const int s0 = min(warp * per_warp, steps), s1 = min(s0 + per_warp, steps);
     int cnt = 0;
+#pragma unroll 8
     for (int st = s0; st < s1; ++st) {
         const int pos = 32 * st + lane;
-        const float d = pos < n ? __ldg(crop + pos) : 0.0f;
+        const float d = pos < n ? crop[pos] : 0.0f;
         cnt += __popc(__ballot_sync(FULL, d != 0.0f));                   // any(row) of pre/process.py:63
     }
     if (lane == 0) warp_cnt[warp] = cnt;
@@ -1477,23 +1496,37 @@ __global__ void __launch_bounds__(NT) point_cloud_kernel(int n_frames, double fo
     const unsigned lt = (1u << lane) - 1u;
     int pos = 32 * s0 + lane;
     int row = pos / bw, col = pos - row * bw;
-    for (int st = s0; st < s1; ++st, pos += 32) {
-        const float d = pos < n ? __ldg(crop + pos) : 0.0f;
-        const bool keep = d != 0.0f;
-        const unsigned m = __ballot_sync(FULL, keep);
-        if (keep) {
-            // (staging the 32 points in shared memory and storing them as one contiguous run was measured: no gain)
-            const size_t dst = (size_t)(before + __popc(m & lt));
-            const double dd = (double)d;
-            const double u = ((double)col + (double)l) - half_w;
-            const double v = ((double)row + (double)t) - half_h;
-            out[3 * dst + 0] = ddiv_fixed(__dmul_rn(u, dd), focal, yf, fast_b);
-            out[3 * dst + 1] = ddiv_fixed(-__dmul_rn(v, dd), focal, yf, fast_b);
-            out[3 * dst + 2] = -dd;
+    // eight steps per iteration, their loads issued together (an unstaged crop: one load per step and nothing else in
+    // flight left the warps waiting on memory 63 % of the time - ncu, long scoreboard)
+    constexpr int U = 8;
+    for (int st = s0; st < s1; st += U) {
+        float dv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = pos + 32 * u;
+            dv[u] = (st + u < s1 && p < n) ? crop[p] : 0.0f;
         }
-        before += __popc(m);
-        col += 32;
-        while (col >= bw) { col -= bw; ++row; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (st + u >= s1) break;                                      // (warp-uniform)
+            const float d = dv[u];
+            const bool keep = d != 0.0f;
+            const unsigned m = __ballot_sync(FULL, keep);
+            if (keep) {
+                // (staging the 32 points in shared memory and storing them as one contiguous run was measured: no gain)
+                const size_t dst = (size_t)(before + __popc(m & lt));
+                const double dd = (double)d;
+                const double uu = ((double)col + (double)l) - half_w;
+                const double vv = ((double)row + (double)t) - half_h;
+                out[3 * dst + 0] = ddiv_fixed(__dmul_rn(uu, dd), focal, yf, fast_b);
+                out[3 * dst + 1] = ddiv_fixed(-__dmul_rn(vv, dd), focal, yf, fast_b);
+                out[3 * dst + 2] = -dd;
+            }
+            before += __popc(m);
+            col += 32;
+            while (col >= bw) { col -= bw; ++row; }
+        }
+        pos += 32 * U;
     }
 }
 
@@ -1513,14 +1546,31 @@ __global__ void __launch_bounds__(NT) resample_extrema_kernel(int point_num,
     const int* idx = indices ? indices + (size_t)f * point_num : nullptr;
     double* dst = out_pc ? out_pc + (size_t)f * point_num * 3 : nullptr;
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int k = tid; k < point_num; k += NT) {
-        const int i = idx ? idx[k] : k;
-        const double x = src[3 * (size_t)i], y = src[3 * (size_t)i + 1], z = src[3 * (size_t)i + 2];
-        if (dst) { dst[3 * (size_t)k] = x; dst[3 * (size_t)k + 1] = y; dst[3 * (size_t)k + 2] = z; }
-        const float xf = __double2float_rn(x), yf = __double2float_rn(y), zf = __double2float_rn(z);
-        mn[0] = fminf(mn[0], xf); mx[0] = fmaxf(mx[0], xf);
-        mn[1] = fminf(mn[1], yf); mx[1] = fmaxf(mx[1], yf);
-        if (z != 0.0) { mn[2] = fminf(mn[2], zf); mx[2] = fmaxf(mx[2], zf); }
+    // four samples per thread and iteration: the four index loads, then the twelve gathers, in flight together (one
+    // sample at a time is a chain of two dependent loads per iteration: latency-bound)
+    constexpr int U = 4;
+    for (int k0 = tid; k0 < point_num; k0 += U * NT) {
+        int i[U];
+        double p[U][3];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = k0 + u * NT;
+            i[u] = k < point_num ? (idx ? idx[k] : k) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i[u] >= 0) { p[u][0] = src[3 * (size_t)i[u]]; p[u][1] = src[3 * (size_t)i[u] + 1]; p[u][2] = src[3 * (size_t)i[u] + 2]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i[u] < 0) continue;
+            const int k = k0 + u * NT;
+            const double x = p[u][0], y = p[u][1], z = p[u][2];
+            if (dst) { dst[3 * (size_t)k] = x; dst[3 * (size_t)k + 1] = y; dst[3 * (size_t)k + 2] = z; }
+            const float xf = __double2float_rn(x), yf = __double2float_rn(y), zf = __double2float_rn(z);
+            mn[0] = fminf(mn[0], xf); mx[0] = fmaxf(mx[0], xf);
+            mn[1] = fminf(mn[1], yf); mx[1] = fmaxf(mx[1], yf);
+            if (z != 0.0) { mn[2] = fminf(mn[2], zf); mx[2] = fmaxf(mx[2], zf); }
+        }
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) { mn[c] = warp_min(mn[c]); mx[c] = warp_max(mx[c]); }
@@ -2082,8 +2132,15 @@ cudaError_t launch_point_cloud(int n_frames, double focal, const float* depth,
                                const long long* point_offsets, int* n_valid,
                                cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    point_cloud_kernel<<<n_frames, NT, 0, stream>>>(n_frames, focal, depth, offsets, headers, points,
-                                                    point_offsets, n_valid);
+    static std::atomic<int> smem_set{0};
+    if (!smem_set.load(std::memory_order_relaxed)) {
+        const cudaError_t e = cudaFuncSetAttribute(point_cloud_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   PC_STAGE_FLOATS * 4);
+        if (e != cudaSuccess) return e;
+        smem_set.store(1, std::memory_order_relaxed);
+    }
+    point_cloud_kernel<<<n_frames, NT, PC_STAGE_FLOATS * 4, stream>>>(n_frames, focal, depth, offsets, headers, points,
+                                                                      point_offsets, n_valid);
     ++g_launch_count;
     return cudaGetLastError();
 }
