@@ -1636,12 +1636,12 @@ int dtsdf_np_randint(uint32_t* mt_key, int32_t* mt_pos, int32_t high, int32_t co
 }
 
 // The same draws in two phases for large batches: this thread finds where every frame's draws begin, block by
-// block of 256 frames (np_legacy_randint_skip: nothing written), and up to four helper threads produce the draws
+// block of 1024 frames (np_legacy_randint_skip: nothing written), and up to four helper threads produce the draws
 // of block b from the snapshots while block b + 1 is being scanned.  Output and final stream state are those of
 // resample_indices (tests/test_host_logic.py checks both against np.random itself).
 static int resample_indices_two_phase(uint32_t* key, int* pos, int32_t n, const int32_t* n_valid, int32_t point_num,
                                       int32_t* out, int helpers) {
-    constexpr int32_t BLOCK = 256;
+    constexpr int32_t BLOCK = 1024;          // (helper threads are started per block: ~30 us each)
     std::vector<dtsdf::DrawSpan> spans[2];
     std::vector<std::thread> th[2];
     auto join = [&](int par) { for (auto& t : th[par]) t.join(); th[par].clear(); };
