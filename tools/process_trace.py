@@ -21,6 +21,14 @@ for rep in range(4):
     vox.process_packed(hdr, off, pin.array, 6000, want_points=False, out_vol=out.array)
     dt = time.perf_counter() - t0
     print("call %d: %.2f ms = %.0f frames/s" % (rep, dt * 1e3, n / dt), flush=True)
+print("pageable input and output (what a caller with plain NumPy arrays gets):")
+out_pg = np.empty((n, 3, 32, 32, 32), dtype=np.float32)
+out_pg[...] = 0
+for rep in range(3):
+    t0 = time.perf_counter()
+    vox.process_packed(hdr, off, pk, 6000, want_points=False, out_vol=out_pg)
+    dt = time.perf_counter() - t0
+    print("call %d: %.2f ms = %.0f frames/s" % (rep, dt * 1e3, n / dt), flush=True)
 nv = np.full(n, 8811, dtype=np.int32)
 t0 = time.perf_counter(); capi.resample_indices(nv, 6000); dt = time.perf_counter() - t0
 print("index draw alone: %.2f ms" % (dt * 1e3))
