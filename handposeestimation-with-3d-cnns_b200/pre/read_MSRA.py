@@ -113,8 +113,7 @@ def _gesture_with_aug(engine, records, joints):
         x, y, z = clouds_aug[i, :, 0], clouds_aug[i, :, 1], clouds_aug[i, :, 2]
         z = z[z != 0]
         extrema[i] = (np.max(x), np.max(y), np.max(z), np.min(x), np.min(y), np.min(z))
-    headers, offsets, packed, _ = _pkg.pack_frames(records)
-    vol_aug, sides_aug, centres_aug = engine.voxelize_packed(headers, offsets, packed, layout=_pkg.LAYOUT_CXYZ,
+    vol_aug, sides_aug, centres_aug = engine.voxelize_frames(records, layout=_pkg.LAYOUT_CXYZ,
                                                              bbox_mode=_pkg.BBOX_EXTREMA, aux=extrema)
     return (clouds, volumes, sides, centres), (clouds_aug, vol_aug, sides_aug, centres_aug, gt_aug)
 

@@ -33,12 +33,14 @@ def frame_depth(frame):
     return frame["data"]
 
 
-def pack_frames(frames, pinned=False):
+def pack_frames(frames, pinned=False, scratch=None):
     """Packs frame records into the batched input format of include/dtsdf_b200.h.
 
     Returns ``(headers int32[n,6], offsets int64[n], packed float32[packed_len], max_crop_px)``;
     crop starts are 16-byte aligned and the tail padding is zero.  With ``pinned=True`` the
     packed buffer is page-locked and a fifth value, its owning ``PinnedBuffer``, is returned.
+    ``scratch``: a callable ``n_floats -> float32 array`` that provides the packed buffer instead
+    (``Voxelizer`` hands out its page-locked staging area this way).
     """
     n = len(frames)
     headers = np.empty((n, 6), dtype=np.int32)
@@ -48,7 +50,11 @@ def pack_frames(frames, pinned=False):
             raise ValueError("frame %d: header needs 6 int32 values" % i)
         headers[i] = h[:6]
     offsets, packed_len, max_px = capi.pack_plan(headers)
-    if pinned:
+    if scratch is not None:
+        buf = None
+        packed = scratch(max(packed_len, 4))
+        packed[:] = 0
+    elif pinned:
         buf = capi.PinnedBuffer(max(packed_len, 4), np.float32)
         packed = buf.array
         packed[:] = 0
@@ -107,12 +113,26 @@ class Voxelizer:
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
             self._lib.dtsdf_ctx_destroy(self._ctx)
             self._ctx = None
+        if getattr(self, "_stage", None) is not None:
+            self._stage.free()
+            self._stage = None
 
     def __del__(self):
         try:
             self.close()
         except Exception:
             pass
+
+    def _staging(self, n_floats):
+        """Page-locked packing area of the frame-level calls, grown when needed and kept: a host -> device copy
+        out of pageable memory is staged by the driver on the calling thread (the process() host call over
+        4,000 frames: 37 ms from a NumPy array, 14 ms from page-locked memory), and page-locking memory per call
+        costs more than it saves.  Valid until the next frame-level call on this instance."""
+        if getattr(self, "_stage", None) is None or self._stage.array.size < n_floats:
+            if getattr(self, "_stage", None) is not None:
+                self._stage.free()
+            self._stage = capi.PinnedBuffer((max(int(n_floats * 1.25), 1 << 20),), np.float32)
+        return self._stage.array[:n_floats]
 
     @_serialised
     def set_option(self, option, value):
@@ -189,9 +209,10 @@ class Voxelizer:
             return None, out_max_l, out_mid_p
         return PackedHostVolumes(handle, self._lib), out_max_l, out_mid_p
 
+    @_serialised
     def voxelize_frames(self, frames, layout=LAYOUT_CXYZ, bbox_mode=BBOX_PIXELS, aux=None, voxel_res=None):
         """Frame records -> (vol float32[n,3,R,R,R], max_l float32[n], mid_p float32[n,3])."""
-        headers, offsets, packed, _ = pack_frames(frames)
+        headers, offsets, packed, _ = pack_frames(frames, scratch=self._staging)
         return self.voxelize_packed(headers, offsets, packed, layout, bbox_mode, aux, voxel_res)
 
     # ------------------------------------------------------------------ process.py pieces
@@ -235,8 +256,9 @@ class Voxelizer:
     def process_frames(self, frames, point_num=6000, want_points=True, layout=LAYOUT_CXYZ, voxel_res=None):
         """``DataProcess(frame, gt, point_num).process()`` (pre/process.py:13-28) for a list of frame
         records: ``pack_frames`` + ``process_packed``."""
-        headers, offsets, packed, _ = pack_frames(frames)
-        return self.process_packed(headers, offsets, packed, point_num, want_points, layout, voxel_res)
+        with self._lock:
+            headers, offsets, packed, _ = pack_frames(frames, scratch=self._staging)
+            return self.process_packed(headers, offsets, packed, point_num, want_points, layout, voxel_res)
 
     @_serialised
     def process_packed(self, headers, offsets, packed, point_num=6000, want_points=True, layout=LAYOUT_CXYZ,

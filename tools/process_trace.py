@@ -29,6 +29,12 @@ for rep in range(3):
     vox.process_packed(hdr, off, pk, 6000, want_points=False, out_vol=out_pg)
     dt = time.perf_counter() - t0
     print("call %d: %.2f ms = %.0f frames/s" % (rep, dt * 1e3, n / dt), flush=True)
+print("frame records in, NumPy arrays out (Voxelizer.process_frames: packs into its page-locked staging area):")
+for rep in range(3):
+    t0 = time.perf_counter()
+    vox.process_frames(frames, 6000, want_points=False)
+    dt = time.perf_counter() - t0
+    print("call %d: %.2f ms = %.0f frames/s" % (rep, dt * 1e3, n / dt), flush=True)
 nv = np.full(n, 8811, dtype=np.int32)
 t0 = time.perf_counter(); capi.resample_indices(nv, 6000); dt = time.perf_counter() - t0
 print("index draw alone: %.2f ms" % (dt * 1e3))
