@@ -180,6 +180,22 @@ def test_process_host_one_call_equals_per_frame_numpy_draws():
     out = v.process_frames(frames[:4], 6000)                              # the context works afterwards
     np.random.seed(1)
     assert _same(out[1], v.process_frames_two_calls(frames[:4], 6000)[1])
+    # the same failure deep inside a pipelined call (two frames per chunk, the index scan two chunks ahead of the
+    # submission, crops uploaded chunk by chunk): the caller's stream ends where the reference's would - advanced by
+    # the draws of the frames before the empty one, nothing more
+    v.set_option(pkg.capi.OPT_CHUNK_MB, 1)
+    v.set_option(pkg.capi.OPT_PACKED_D2H, 1)
+    batch = frames[:23] + [empty] + frames[23:40]
+    np.random.seed(123)
+    with pytest.raises(ValueError):
+        v.process_frames(batch, 6000, want_points=False)
+    mine = np.random.get_state()
+    np.random.seed(123)
+    for fr in batch[:23]:
+        ps = int(np.count_nonzero(fr["depth"]))
+        np.random.randint(0, ps, size=6000 - ps if ps < 6000 else 6000)
+    theirs = np.random.get_state()
+    assert np.array_equal(mine[1], theirs[1]) and mine[2] == theirs[2]
     v.close()
 
 
@@ -530,6 +546,18 @@ def test_packed_host_result_expands_to_the_dense_result():
         with pytest.raises(pkg.DtsdfError):
             lazy.expand(n - 1, 2)
         lazy.close()
+    # the storage of closed results is kept for later ones (no fresh pages per call): results that are alive at
+    # the same time never share it, and a recycled block holds nothing of its previous owner
+    v.set_option(pkg.capi.OPT_CHUNK_MB, 8)
+    want = v.voxelize_packed(headers, offsets, packed)[0]
+    first = v.voxelize_packed_lazy(headers[:200], offsets[:200], packed)[0]
+    second = v.voxelize_packed_lazy(headers[60:260], offsets[60:260], packed)[0]
+    assert _same(first.expand(), want[:200]) and _same(second.expand(), want[60:260])
+    first.close()
+    third = v.voxelize_packed_lazy(headers[100:130], offsets[100:130], packed)[0]       # takes blocks `first` gave back
+    assert _same(third.expand(), want[100:130]) and _same(second.expand(), want[60:260])
+    second.close()
+    third.close()
     v.set_option(pkg.capi.OPT_LITERAL_PUSH, 1)                    # the push route of the dense result, too
     v.set_option(pkg.capi.OPT_CHUNK_MB, 8)
     assert _same(v.voxelize_packed(headers, offsets, packed)[0], c_oracle.dtsdf_batch(headers, offsets, packed)[0])
