@@ -489,6 +489,25 @@ def run_secondary(pkg, dev, rank, world, args, max_over_ranks, barrier):
     del d_points
     torch.cuda.empty_cache()
 
+    # the sampled cloud (what process() returns and read_MSRA.py stores) without the full one: two launches,
+    # hand_points[rand_idx] straight from the depth map + fused kernel in extrema mode
+    d_pc = torch.empty((F, P, 3), dtype=torch.float64, device=dev)
+
+    def process_sampled_cloud():
+        capi.check(lib.dtsdf_sample_cloud_batch(F, ctypes.c_double(241.42), P, d_packed.data_ptr(), d_off.data_ptr(),
+                                                d_hdr.data_ptr(), d_idx.data_ptr(), int(max_px), d_pc.data_ptr(),
+                                                d_ext.data_ptr(), None, stream))
+        pkg.voxelize_device(d_packed, d_off, d_hdr, max_px, cfg_e, aux=d_ext, out_vol=vol, out_max_l=d_maxl, out_mid_p=d_mid)
+    if max_px <= 22528:
+        ms = timed(process_sampled_cloud)
+        entry("process_semantics_device_with_sampled_clouds", F, ms,
+              algorithmic_bytes(headers, R) + int(np.sum(4 * n_px + 0 * n_valid.astype(np.int64) + (4 + 24) * P + 24)),
+              {"config": "bbox from the resampled 6000-point cloud, the SAMPLED clouds written (float64[6000,3] per frame, what "
+                         "process() returns), the full cloud never built: dtsdf_sample_cloud_batch + fused kernel (extrema mode)",
+               "bytes": "fused 455,656 + crop 4 bw bh + index 4 and point 24 per sample + 24"})
+    del d_pc
+    torch.cuda.empty_cache()
+
     # the same semantics in ONE launch when the sampled cloud itself is not wanted (3D_CNN/dataset.py never
     # reads it): ranks of the valid pixels, a bitmap of the sampled ranks and the extrema of the sample inside
     # the voxeliser (DTSDF_BBOX_SAMPLED) - no cloud is ever written

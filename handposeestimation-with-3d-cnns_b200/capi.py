@@ -90,6 +90,7 @@ _SIGNATURES = {
                                                     _vp]),
     "dtsdf_point_cloud_batch": (ctypes.c_int, [_i32, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_resample_extrema_batch": (ctypes.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dtsdf_sample_cloud_batch": (ctypes.c_int, [_i32, ctypes.c_double, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "dtsdf_normalize_joints_batch": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "dtsdf_pack_volumes_batch": (ctypes.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "dtsdf_unpack_volumes_batch": (ctypes.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),

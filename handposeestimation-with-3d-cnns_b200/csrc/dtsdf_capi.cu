@@ -637,6 +637,22 @@ int dtsdf_resample_extrema_batch(int32_t n_frames, int32_t point_num, const doub
     return DTSDF_OK;
 }
 
+int dtsdf_sample_cloud_batch(int32_t n_frames, double focal, int32_t point_num, const float* d_depth_packed,
+                             const int64_t* d_crop_offsets, const int32_t* d_headers, const int32_t* d_indices,
+                             int32_t max_crop_px, double* d_out_pc, float* d_out_extrema, int32_t* d_out_n_valid,
+                             void* stream) {
+    static_assert(DTSDF_SAMPLE_CLOUD_MAX_PX == 22528, "header constant");
+    if (n_frames < 0 || point_num <= 0 || !(focal > 0.0)) return DTSDF_ERR_INVALID_ARG;
+    if (n_frames == 0) return DTSDF_OK;
+    if (!d_depth_packed || !d_crop_offsets || !d_headers || !d_out_extrema) return DTSDF_ERR_INVALID_ARG;
+    if (max_crop_px <= 0 || max_crop_px > dtsdf::sample_cloud_max_pixels()) return DTSDF_ERR_UNSUPPORTED;
+    if (DTSDF_SAMPLE_CLOUD_MAX_PX != dtsdf::sample_cloud_max_pixels()) return DTSDF_ERR_INTERNAL;
+    CK(dtsdf::launch_sample_cloud(n_frames, focal, point_num, d_depth_packed,
+                                  reinterpret_cast<const long long*>(d_crop_offsets), d_headers, d_indices, d_out_pc,
+                                  d_out_extrema, d_out_n_valid, (cudaStream_t)stream));
+    return DTSDF_OK;
+}
+
 int dtsdf_normalize_joints_batch(int32_t n_frames, const float* d_joints, const float* d_max_l,
                                  const float* d_mid_p, int32_t clamp01, float* d_out, void* stream) {
     if (n_frames < 0) return DTSDF_ERR_INVALID_ARG;
@@ -1156,9 +1172,17 @@ int HostPipeline::submit_chunks() {
                                               point_num, c->b_max_px, (float*)c->d_vol[slot].p, (float*)c->d_maxl[slot].p,
                                               (float*)c->d_mid[slot].p, c->s_run);
         } else {
-            rc = dtsdf_resample_extrema_batch(nf, point_num, (const double*)c->b_points.p, (const int64_t*)c->b_poff.p + f0,
-                                              (const int32_t*)c->p_idx[slot].p, h_pc ? (double*)c->p_pc[slot].p : nullptr,
-                                              (float*)c->p_ext[slot].p, c->s_run);
+            // the sampled clouds are wanted: straight from the depth map when the crops allow it (no full cloud was
+            // built then, see dtsdf_process_host), else gathered from the clouds built up front
+            if (c->b_n == 0)
+                rc = dtsdf_sample_cloud_batch(nf, focal64, point_num, (const float*)c->b_depth.p, (const int64_t*)c->b_off.p + f0,
+                                              (const int32_t*)c->b_hdr.p + 6 * (size_t)f0, (const int32_t*)c->p_idx[slot].p,
+                                              c->b_max_px, (double*)c->p_pc[slot].p, (float*)c->p_ext[slot].p, nullptr,
+                                              c->s_run);
+            else
+                rc = dtsdf_resample_extrema_batch(nf, point_num, (const double*)c->b_points.p, (const int64_t*)c->b_poff.p + f0,
+                                                  (const int32_t*)c->p_idx[slot].p, h_pc ? (double*)c->p_pc[slot].p : nullptr,
+                                                  (float*)c->p_ext[slot].p, c->s_run);
             if (rc == DTSDF_OK)
                 rc = dtsdf_voxelize_batch(cfg, nf, (const float*)c->b_depth.p, (const int64_t*)c->b_off.p + f0,
                                           (const int32_t*)c->b_hdr.p + 6 * (size_t)f0, (const float*)c->p_ext[slot].p,
@@ -1730,8 +1754,20 @@ int dtsdf_process_host(dtsdf_ctx* c, const dtsdf_config* cfg_in, double focal, i
         // with clouds: back-projection + compaction of every frame up front, crops, tables and clouds resident
         // (b_*); without: the crops go up and are counted one pipeline chunk at a time behind the draws
         std::vector<int32_t> n_valid((size_t)n_frames);
+        // the full clouds are an intermediate: with crops of at most DTSDF_SAMPLE_CLOUD_MAX_PX pixels the sampled
+        // points come straight from the depth map (dtsdf_sample_cloud_batch) and the call takes the same route
+        // as without clouds
+        bool full_clouds = h_out_pc != nullptr;
+        if (full_clouds) {
+            int64_t biggest = 0;
+            for (int32_t i = 0; i < n_frames; ++i) {
+                const int32_t* hh = h_hdr + 6 * (size_t)i;
+                biggest = std::max<int64_t>(biggest, ((int64_t)hh[4] - hh[2]) * ((int64_t)hh[5] - hh[3]));
+            }
+            full_clouds = biggest > DTSDF_SAMPLE_CLOUD_MAX_PX;
+        }
         int rc2 = process_begin_impl(c, focal, n_frames, h_depth, packed_len, h_off, h_hdr, n_valid.data(),
-                                     h_out_pc != nullptr, p.nchunk > 1 ? p.per_chunk : 0);
+                                     full_clouds, p.nchunk > 1 ? p.per_chunk : 0);
         if (rc2 != DTSDF_OK) {
             cudaStreamSynchronize(c->s_in);          // pieces may be in flight from the caller's buffer
             cudaGetLastError();

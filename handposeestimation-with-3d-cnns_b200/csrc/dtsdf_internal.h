@@ -52,6 +52,12 @@ cudaError_t launch_point_cloud(int n_frames, double focal, const float* depth,
                                const long long* point_offsets, int* n_valid,
                                cudaStream_t stream);
 
+// point_cloud + gather by index + extrema without the full cloud (crops of at most sample_cloud_max_pixels())
+int sample_cloud_max_pixels();
+cudaError_t launch_sample_cloud(int n_frames, double focal, int point_num, const float* depth, const long long* offsets,
+                                const int* headers, const int* indices, double* out_pc, float* out_extrema,
+                                int* n_valid, cudaStream_t stream);
+
 cudaError_t launch_resample_extrema(int n_frames, int point_num, const double* points,
                                     const long long* point_offsets, const int* indices,
                                     double* out_pc, float* out_extrema, cudaStream_t stream);

@@ -1586,6 +1586,194 @@ __global__ void __launch_bounds__(NT) resample_extrema_kernel(int point_num,
     }
 }
 
+// ---------------------------------------------------------------- sampled cloud in one kernel
+// DataProcess.point_cloud() + set_length() + max_min_point() (pre/process.py:30-84, 102-120) when only the SAMPLED
+// cloud is wanted: hand_points[rand_idx] is written straight from the depth map, the full cloud (24 B per valid
+// pixel, written by point_cloud_kernel and gathered from by resample_extrema_kernel: 211 KB + 1.75 sectors per
+// sample) never exists.  One CTA per frame:
+//   0  the crop is staged by one TMA bulk copy (crops beyond the staging area are read in place);
+//   1  per 32-pixel word: the mask of valid pixels (d != 0) and, after one scan by warp 0, the number of valid
+//      pixels before the word - the rank of a pixel is that count plus a popc;
+//   2  sample k wants the pixel of rank idx[k]: its word by a table over the ranks that are multiples of 32 and a
+//      short walk, the rank-th set bit of the word (five halvings), back-projection in float64 exactly as point_cloud_kernel does it, the point goes to
+//      out_pc[k]; extrema as resample_extrema_kernel (float32-rounded, z ignoring exact zeros).
+// Bit for bit what the two kernels produce.  Crops of more than SC_MAX_WORDS * 32 pixels are not handled here
+// (the launcher says so and the caller takes the two-kernel route).
+constexpr int SC_STAGE_FLOATS = 16 * 1024;          // 64 KB staged crop
+constexpr int SC_MAX_WORDS = 704;                   // 22,528 pixels (the MSRA crops are below 150 x 140)
+constexpr int SC_SMEM = SC_STAGE_FLOATS * 4;
+
+__global__ void __launch_bounds__(NT) sample_cloud_kernel(double focal, int point_num,
+                                                          const float* __restrict__ depth,
+                                                          const long long* __restrict__ offsets,
+                                                          const int* __restrict__ headers,
+                                                          const int* __restrict__ indices,
+                                                          double* __restrict__ out_pc,
+                                                          float* __restrict__ out_extrema,
+                                                          int* __restrict__ n_valid_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float red[NWARP][8];
+    __shared__ unsigned long long bar;
+    __shared__ int total_s;
+    __shared__ unsigned vmask[SC_MAX_WORDS];                  // valid pixels of each 32-pixel word
+    __shared__ int wpre[SC_MAX_WORDS + 1];                    // valid pixels before the word
+    __shared__ short start[SC_MAX_WORDS + 2];                 // the word that holds rank 32 q
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* h = headers + 6 * (size_t)f;
+    const int w = h[0], hh = h[1], l = h[2], t = h[3], r = h[4], b = h[5];
+    const int bw = r - l, bh = b - t;
+    const int n = (bw > 0 && bh > 0) ? bw * bh : 0;
+    const int words = (n + 31) >> 5;
+    if (words > SC_MAX_WORDS) {                               // (CTA-uniform) a crop the caller's hint did not announce:
+        if (tid < 6) out_extrema[6 * (size_t)f + tid] = __int_as_float(QNAN_BITS);      // no result, nothing overrun
+        if (tid == 0 && n_valid_out) n_valid_out[f] = -1;
+        return;
+    }
+    const float* crop_g = depth + offsets[f];
+    const int n_pad = (n + 3) & ~3;
+    const bool staged = n > 0 && n_pad <= SC_STAGE_FLOATS;
+    if (staged) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(&bar, (uint32_t)n_pad * 4u);
+            bulk_g2s(smem_raw, crop_g, (uint32_t)n_pad * 4u, &bar);
+        }
+        __syncthreads();
+        mbar_wait(&bar, 0);
+    }
+    const float* crop = staged ? reinterpret_cast<const float*>(smem_raw) : crop_g;
+    // ---- 1. valid masks and counts per word: a THREAD per word (32 pixels = eight 16-byte reads, in a per-lane
+    //      rotated order so that a warp's reads spread over the banks), each thread a run of consecutive words, then
+    //      one block scan of the runs.  (A warp per word - one ballot per 32 pixels - cost 30 % of the kernel's
+    //      instructions: a warp instruction per word where a thread's would do.)
+    __shared__ int wtot[NWARP];
+    const int wpt = (words + NT - 1) / NT;                    // words per thread: 1..3
+    const int w0 = min(tid * wpt, words), w1 = min(w0 + wpt, words);
+    int mine = 0;
+    for (int wd = w0; wd < w1; ++wd) {
+        unsigned m = 0u;
+        const int p0 = 32 * wd;
+        if (staged && p0 + 32 <= n_pad) {                     // whole word inside the staged (16-byte aligned, zero-padded) crop
+            const float4* q4 = reinterpret_cast<const float4*>(smem_raw) + 8 * wd;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int j = (i + lane) & 7;
+                const float4 v = q4[j];
+                const unsigned nib = (v.x != 0.0f ? 1u : 0u) | (v.y != 0.0f ? 2u : 0u) | (v.z != 0.0f ? 4u : 0u) | (v.w != 0.0f ? 8u : 0u);
+                m |= nib << (4 * j);
+            }
+            if (p0 + 32 > n) m &= (1u << (n - p0)) - 1u;      // (padding is zero anyway)
+        } else {
+            for (int i = 0; i < 32 && p0 + i < n; ++i) m |= (crop[p0 + i] != 0.0f ? 1u : 0u) << i;
+        }
+        vmask[wd] = m;                                        // any(row) of pre/process.py:63
+        mine += __popc(m);
+    }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    int run = incl - mine;
+#pragma unroll
+    for (int i = 0; i < NWARP; ++i) run += i < warp ? wtot[i] : 0;
+    for (int wd = w0; wd < w1; ++wd) {
+        const int c = __popc(vmask[wd]);
+        wpre[wd] = run;
+        // a word holds at most 32 valid pixels, hence at most one rank that is a multiple of 32: it starts there
+        const int q = (run + 31) >> 5;
+        if (32 * q < run + c) start[q] = (short)wd;
+        run += c;
+    }
+    if (tid == NT - 1) total_s = run;
+    __syncthreads();
+    const int total = total_s;
+    if (tid == 0 && n_valid_out) n_valid_out[f] = total;
+    // ---- 2. the samples
+    const double half_w = (double)w / 2.0, half_h = (double)hh / 2.0;
+    const double yf = __drcp_rn(focal);
+    const unsigned long long fb = (unsigned long long)__double_as_longlong(focal);
+    const int fe = (int)((fb >> 52) & 0x7ff);
+    const bool fast_b = fe > 1023 - 100 && fe < 1023 + 100 && (fb & 0xfffffffffffffull) != 0xfffffffffffffull;
+    const int* idx = indices ? indices + (size_t)f * point_num : nullptr;
+    double* dst = out_pc ? out_pc + (size_t)f * point_num * 3 : nullptr;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    // four samples per thread and iteration, their index loads issued together: one sample at a time left the warps
+    // waiting on the index load (ncu: long scoreboard)
+    const float inv_bw = __frcp_rn((float)bw);
+    constexpr int U = 8;
+    for (int k0 = tid; k0 < point_num; k0 += U * NT) {
+        int rank[U], wd[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = k0 + u * NT;
+            rank[u] = k < point_num ? (idx ? __ldg(idx + k) : k) : -1;
+            wd[u] = 0;
+        }
+        // the last word with wpre <= rank: from the word that holds the multiple of 32 below the rank, a few words on
+        // (one or two in a hand; a binary search over all words was 24 % of the kernel's instructions)
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if ((unsigned)rank[u] < (unsigned)total) wd[u] = start[rank[u] >> 5];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if ((unsigned)rank[u] < (unsigned)total)
+                while (wd[u] + 1 < words && wpre[wd[u] + 1] <= rank[u]) ++wd[u];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = k0 + u * NT;
+            if (k >= point_num) continue;
+            if ((unsigned)rank[u] >= (unsigned)total) {       // not a point of this frame: nothing to gather
+                if (dst) { dst[3 * (size_t)k] = 0.0; dst[3 * (size_t)k + 1] = 0.0; dst[3 * (size_t)k + 2] = 0.0; }
+                continue;
+            }
+            // the (rank - wpre[word])-th set bit of the word, by halving (__fns is a loop over the bits; a shortcut
+            // for words with all 32 pixels valid only added divergence: 0.642 vs 0.626 ms)
+            unsigned m = vmask[wd[u]];
+            int want = rank[u] - wpre[wd[u]], bit = 0;
+#pragma unroll
+            for (int span = 16; span > 0; span >>= 1) {
+                const int c = __popc(m & ((1u << span) - 1u));
+                if (want >= c) { want -= c; m >>= span; bit += span; }
+            }
+            const int pos = 32 * wd[u] + bit;
+            // pos / bw for pos < 2^15: float quotient, off by at most one
+            int row = __float2int_rz(__fmul_rz((float)pos, inv_bw));
+            if (row * bw > pos) --row;
+            if ((row + 1) * bw <= pos) ++row;
+            const int col = pos - row * bw;
+            const double dd = (double)crop[pos];
+            const double uu = ((double)col + (double)l) - half_w;
+            const double vv = ((double)row + (double)t) - half_h;
+            const double x = ddiv_fixed(__dmul_rn(uu, dd), focal, yf, fast_b);
+            const double y = ddiv_fixed(-__dmul_rn(vv, dd), focal, yf, fast_b);
+            const double z = -dd;
+            if (dst) { dst[3 * (size_t)k] = x; dst[3 * (size_t)k + 1] = y; dst[3 * (size_t)k + 2] = z; }
+            const float xf = __double2float_rn(x), yff = __double2float_rn(y), zf = __double2float_rn(z);
+            mn[0] = fminf(mn[0], xf); mx[0] = fmaxf(mx[0], xf);
+            mn[1] = fminf(mn[1], yff); mx[1] = fmaxf(mx[1], yff);
+            if (z != 0.0) { mn[2] = fminf(mn[2], zf); mx[2] = fmaxf(mx[2], zf); }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { mn[c] = warp_min(mn[c]); mx[c] = warp_max(mx[c]); }
+    if (lane == 0) {
+        red[warp][0] = mx[0]; red[warp][1] = mx[1]; red[warp][2] = mx[2];
+        red[warp][3] = mn[0]; red[warp][4] = mn[1]; red[warp][5] = mn[2];
+    }
+    __syncthreads();
+    if (tid < 6) {
+        float v = red[0][tid];
+        for (int ww = 1; ww < NWARP; ++ww) v = tid < 3 ? fmaxf(v, red[ww][tid]) : fminf(v, red[ww][tid]);
+        out_extrema[6 * (size_t)f + tid] = v;
+    }
+}
+
 // (gt - mid_p)/max_l + 0.5 in float32, optional clamp to [0,1]
 // (pre/joint_nor.py:8-18; 3D_CNN/train.py:236-244 does the same on float32 tensors).
 __global__ void normalize_joints_kernel(int total, const float* __restrict__ joints,
@@ -2141,6 +2329,24 @@ cudaError_t launch_point_cloud(int n_frames, double focal, const float* depth,
     }
     point_cloud_kernel<<<n_frames, NT, PC_STAGE_FLOATS * 4, stream>>>(n_frames, focal, depth, offsets, headers, points,
                                                                       point_offsets, n_valid);
+    ++g_launch_count;
+    return cudaGetLastError();
+}
+
+int sample_cloud_max_pixels() { return SC_MAX_WORDS * 32; }
+
+cudaError_t launch_sample_cloud(int n_frames, double focal, int point_num, const float* depth, const long long* offsets,
+                                const int* headers, const int* indices, double* out_pc, float* out_extrema,
+                                int* n_valid, cudaStream_t stream) {
+    if (n_frames <= 0) return cudaSuccess;
+    static std::atomic<int> smem_set{0};
+    if (!smem_set.load(std::memory_order_relaxed)) {
+        const cudaError_t e = cudaFuncSetAttribute(sample_cloud_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM);
+        if (e != cudaSuccess) return e;
+        smem_set.store(1, std::memory_order_relaxed);
+    }
+    sample_cloud_kernel<<<n_frames, NT, SC_SMEM, stream>>>(focal, point_num, depth, offsets, headers, indices, out_pc,
+                                                           out_extrema, n_valid);
     ++g_launch_count;
     return cudaGetLastError();
 }

@@ -228,6 +228,26 @@ int dtsdf_resample_extrema_batch(int32_t n_frames, int32_t point_num,
                                  const int32_t* d_indices,
                                  double* d_out_pc, float* d_out_extrema, void* stream);
 
+/* The two calls above in one launch when only the SAMPLED cloud is wanted: the points
+ * hand_points[rand_idx] (pre/process.py:30-68 followed by :82) are back-projected straight
+ * from the depth map - the full cloud is never written - and their extrema reduced
+ * (pre/process.py:102-120).  Bit for bit what dtsdf_point_cloud_batch +
+ * dtsdf_resample_extrema_batch produce.
+ *   d_indices      int32[n][point_num]: ranks among the frame's valid pixels (d != 0, row-major);
+ *                  a value outside [0, n_valid_i) yields a zero point and does not enter the extrema
+ *   d_out_pc       double[n][point_num][3]  (may be NULL)
+ *   d_out_extrema  float[n][6] as above
+ *   d_out_n_valid  int32[n] or NULL
+ *   max_crop_px    the largest crop of the batch in pixels; beyond DTSDF_SAMPLE_CLOUD_MAX_PX
+ *                  the call returns DTSDF_ERR_UNSUPPORTED (use the two calls above)
+ */
+#define DTSDF_SAMPLE_CLOUD_MAX_PX 22528
+int dtsdf_sample_cloud_batch(int32_t n_frames, double focal, int32_t point_num,
+                             const float* d_depth_packed, const int64_t* d_crop_offsets,
+                             const int32_t* d_headers, const int32_t* d_indices, int32_t max_crop_px,
+                             double* d_out_pc, float* d_out_extrema, int32_t* d_out_n_valid,
+                             void* stream);
+
 /* ---- lossless volume codec on the device (gather of volumes to a training rank) ----------------
  * A voxel whose three channels are all +0.0, all +1.0 or all -1.0 - outside the crop, no depth, or
  * beyond the truncation distance (pre/process.py:159,167,180-194): about 90 % of a D-TSDF volume -

@@ -281,6 +281,68 @@ def test_sampled_voxeliser_equals_the_cloud_path(R, layout):
     v.close()
 
 
+def test_sampled_cloud_in_one_launch_equals_the_two_kernels():
+    """dtsdf_sample_cloud_batch (hand_points[rand_idx] straight from the depth map: word masks, rank search,
+    back-projection of the sampled pixels only) against dtsdf_point_cloud_batch + dtsdf_resample_extrema_batch, bit
+    for bit: sampled clouds, extrema, valid-pixel counts; hands, random boxes, NaN / huge / negative / sub-unit
+    depths, 1-pixel crops, an odd image size; 6000 and 37 samples; a crop beyond its limit is refused."""
+    import ctypes
+    import torch
+    lib = pkg.capi.load_library()
+    dev = torch.device("cuda:0")
+    frames = [f for f in _sampled_case_frames() if np.asarray(f["depth"]).size <= 22528 and np.count_nonzero(f["depth"])]
+    assert len(frames) > 50
+    headers, offsets, packed, max_px = pkg.pack_frames(frames)
+    n = len(frames)
+    d_packed, d_off, d_hdr = torch.from_numpy(packed).to(dev), torch.from_numpy(offsets).to(dev), torch.from_numpy(headers).to(dev)
+    sizes = (headers[:, 4] - headers[:, 2]).astype(np.int64) * (headers[:, 5] - headers[:, 3])
+    poff = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+    d_poff = torch.from_numpy(poff).to(dev)
+    d_points = torch.zeros((int(sizes.sum()), 3), dtype=torch.float64, device=dev)
+    d_nvalid = torch.zeros((n,), dtype=torch.int32, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    focal = ctypes.c_double(241.42)
+    pkg.capi.check(lib.dtsdf_point_cloud_batch(n, focal, d_packed.data_ptr(), d_off.data_ptr(), d_hdr.data_ptr(),
+                                               d_points.data_ptr(), d_poff.data_ptr(), d_nvalid.data_ptr(), stream))
+    n_valid = d_nvalid.cpu().numpy()
+    rng = np.random.default_rng(99)
+    for point_num in (6000, 37):
+        idx = np.stack([rng.integers(0, int(v), size=point_num) for v in n_valid]).astype(np.int32)
+        idx[:, 0] = 0
+        idx[:, 1] = n_valid - 1                                  # first and last point of every frame
+        d_idx = torch.from_numpy(idx).to(dev)
+        want_pc = torch.zeros((n, point_num, 3), dtype=torch.float64, device=dev)
+        want_ext = torch.zeros((n, 6), dtype=torch.float32, device=dev)
+        pkg.capi.check(lib.dtsdf_resample_extrema_batch(n, point_num, d_points.data_ptr(), d_poff.data_ptr(), d_idx.data_ptr(),
+                                                        want_pc.data_ptr(), want_ext.data_ptr(), stream))
+        got_pc = torch.full((n, point_num, 3), 7.0, dtype=torch.float64, device=dev)
+        got_ext = torch.full((n, 6), 7.0, dtype=torch.float32, device=dev)
+        got_nv = torch.zeros((n,), dtype=torch.int32, device=dev)
+        pkg.capi.check(lib.dtsdf_sample_cloud_batch(n, focal, point_num, d_packed.data_ptr(), d_off.data_ptr(), d_hdr.data_ptr(),
+                                                    d_idx.data_ptr(), int(max_px), got_pc.data_ptr(), got_ext.data_ptr(),
+                                                    got_nv.data_ptr(), stream))
+        torch.cuda.synchronize()
+        assert np.array_equal(got_nv.cpu().numpy(), n_valid)
+        assert torch.equal(got_pc.view(torch.int64), want_pc.view(torch.int64))
+        assert torch.equal(got_ext.view(torch.int32), want_ext.view(torch.int32))
+        # without a cloud output, and with ranks that are not points of the frame
+        idx[::2, 5] = n_valid[::2]
+        idx[1::2, 6] = -3
+        d_idx = torch.from_numpy(idx).to(dev)
+        pkg.capi.check(lib.dtsdf_sample_cloud_batch(n, focal, point_num, d_packed.data_ptr(), d_off.data_ptr(), d_hdr.data_ptr(),
+                                                    d_idx.data_ptr(), int(max_px), got_pc.data_ptr(), got_ext.data_ptr(), None, stream))
+        torch.cuda.synchronize()
+        got = got_pc.cpu().numpy()
+        assert not got[::2, 5].any() and not got[1::2, 6].any()
+        keep = np.ones((n, point_num), bool)
+        keep[::2, 5] = False
+        keep[1::2, 6] = False
+        assert np.array_equal(got.view(np.int64)[keep], want_pc.cpu().numpy().view(np.int64)[keep])
+    rc = lib.dtsdf_sample_cloud_batch(n, focal, 37, d_packed.data_ptr(), d_off.data_ptr(), d_hdr.data_ptr(), d_idx.data_ptr(),
+                                      76800, got_pc.data_ptr(), got_ext.data_ptr(), None, stream)
+    assert rc == pkg.capi.ERR_UNSUPPORTED
+
+
 def test_kernels_stay_inside_their_buffers():
     """compute-sanitizer is closed on this pool (profiles/r02_sanitizer_refused.txt): every output of every device
     entry point is carved out of a larger allocation filled with a canary pattern, 4 KB on both sides; after the

@@ -38,6 +38,11 @@ def timeit(fn, n=10):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
+def sc():
+    capi.check(lib.dtsdf_sample_cloud_batch(F, ctypes.c_double(241.42), P, d_packed.data_ptr(), d_off.data_ptr(), d_hdr.data_ptr(),
+                                            d_idx.data_ptr(), int(max_px), d_pc.data_ptr(), d_ext.data_ptr(), None, stream))
+t_sc = timeit(sc)
+print("sample_cloud_kernel %.3f ms (%.2f TB/s on crop + index + sampled cloud)" % (t_sc, F * (n_px * 4 + P * 28 + 24) / t_sc / 1e9))
 t_pc, t_rs = timeit(pc), timeit(rs)
 nv = float(n_valid.mean())
 b_pc = F * (n_px * 4 + nv * 24)
