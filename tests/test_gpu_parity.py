@@ -171,6 +171,16 @@ def test_process_host_one_call_equals_per_frame_numpy_draws():
         if want_points:
             assert np.array_equal(a[0], b[0])
         assert _same(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    # a crop beyond what dtsdf_sample_cloud_batch takes (a full 320 x 240 frame): the call builds the full clouds
+    # up front and gathers from them, same results
+    big = frames[:5] + [synth.make_frame(1, box=(0, 0, 320, 240))] + frames[5:9]
+    v.set_option(pkg.capi.OPT_CHUNK_MB, 1)
+    v.set_option(pkg.capi.OPT_PACKED_D2H, 1)
+    np.random.seed(7)
+    a = v.process_frames_two_calls(big, 6000, want_points=True)
+    np.random.seed(7)
+    b = v.process_frames(big, 6000, want_points=True)
+    assert np.array_equal(a[0], b[0]) and _same(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
     # a frame without a single point: the reference's np.random.randint(0, 0) raises ValueError
     empty = synth.make_frame(4)
     empty["depth"] = np.zeros_like(empty["depth"])
