@@ -333,11 +333,10 @@ __device__ __forceinline__ bool sanitize_crop(float* crop_s, int n_pad) {
 //     sample (pre/process.py:102-120) are those of P, Q and d, compared as order-preserving integers (-0 < +0,
 //     like the FMNMX of resample_extrema_kernel); NaNs are skipped as fminf/fmaxf skip them.  FOUR float64
 //     divisions per frame remain.
-//   * sampled_bbox_fast: P is monotone in d within a column and Q within a row, so per sampled pixel only the
-//     depth is compared - four shared-memory atomics on its ordered bits (column min/max, row min/max), no
-//     float64 in the loop; u * d and v * d are formed for the column / row extremes only.  This needs finite
-//     depths (0 * inf = NaN would hide a column's finite pixels) and a crop of at most COLCAP x ROWCAP pixels
-//     (the MSRA image is 320 x 240);
+//   * sampled_bbox_fast: per sampled pixel the products u * d and v * d are formed EXACTLY as two floats each
+//     (hi = RN32(u d), lo = fma(u, d, -hi): u, v have at most 11 significant bits, d 24) and compared as 64-bit
+//     integers of their ordered bits; the extremes stay in registers - no float64 in the loop, no atomics.  This
+//     needs finite depths and none so small that lo would underflow (|d| >= 2^-90), and n + 64 bits of bitmap;
 //   * sampled_bbox_general: any other frame; every sampled pixel is multiplied out in float64.
 // Result in shared memory (FrameShared::red[0]): {max x, y, z, min x, y, z} - what resample_extrema_kernel
 // produces from the materialised cloud, bit for bit.  Scratch is the projection-table area of FrameShared (not
@@ -353,8 +352,6 @@ __device__ __forceinline__ int fkey(float x) {
 }
 __device__ __forceinline__ float fkey_inv(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
 
-constexpr int COLCAP = 320, ROWCAP = 240;
-constexpr int KEY_MAX = 0x7fffffff, KEY_MIN = -0x7fffffff - 1;
 
 template <int NW>
 struct SampledScratch {
@@ -362,8 +359,6 @@ struct SampledScratch {
     float     fred[NW][2];        // per warp: min d, max d
     int       wsum[NW];
     int       flag[NW];           // per warp: its piece holds an infinite depth
-    int       colmin[COLCAP], colmax[COLCAP];     // ordered bits of the smallest / largest sampled depth per column
-    int       rowmin[ROWCAP], rowmax[ROWCAP];     // ... per row
     unsigned  bitmap[1];          // ... to the end of the scratch area
 };
 
@@ -431,19 +426,16 @@ __device__ __forceinline__ void mark_samples(const int* idx, int point_num, int 
 }
 
 // what sampled_bbox_fast expects to find (the kernel does this while the crop is still on its way, ahead of a
-// barrier it has anyway): empty column / row extremes and a cleared bitmap for the n ranks a crop of n pixels can
-// have (+ two spare words)
+// barrier it has anyway): a cleared bitmap for the n ranks a crop of n pixels can have (+ two spare words)
 template <int NW>
 __device__ __forceinline__ void sampled_scratch_init(unsigned char* smem_raw, int n) {
     constexpr int NTH = 32 * NW;
     SampledScratch<NW>* sc = reinterpret_cast<SampledScratch<NW>*>(smem_raw);
-    for (int c = threadIdx.x; c < COLCAP; c += NTH) { sc->colmin[c] = KEY_MAX; sc->colmax[c] = KEY_MIN; }
-    for (int c = threadIdx.x; c < ROWCAP; c += NTH) { sc->rowmin[c] = KEY_MAX; sc->rowmax[c] = KEY_MIN; }
     for (int i = threadIdx.x; i < (n + 31) / 32 + 2; i += NTH) sc->bitmap[i] = 0u;
 }
 
-// Needs bw <= COLCAP, bh <= ROWCAP, n + 64 <= CAP_BITS and sampled_scratch_init + a barrier before it.
-// Returns false (CTA-uniform, no result written) when the crop holds an infinite depth.
+// Needs n + 64 <= CAP_BITS and sampled_scratch_init + a barrier before it.
+// Returns false (CTA-uniform, no result written) when the crop holds an infinite or a tiny (< 2^-90) depth.
 template <int NW, bool SMEM, int CROP_OFF, int OUT6_OFF>
 __device__ __noinline__ bool sampled_bbox_fast(const float* __restrict__ crop_g, int n, int bw, int bh,
                                                int l, int t, int w, int h, double focal,
@@ -454,22 +446,26 @@ __device__ __noinline__ bool sampled_bbox_fast(const float* __restrict__ crop_g,
     const float* crop = SMEM ? reinterpret_cast<const float*>(smem_raw + CROP_OFF) : crop_g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
+    if (abs(w) >= (1 << 20) || abs(h) >= (1 << 20)) return false;      // (u, v would not be exact float32 values)
     // the sampled ranks (all below the number of valid pixels, hence below n; anything else marks nothing)
     mark_samples<NTH>(idx, point_num, 0, n, sc->bitmap);
     // a warp owns one contiguous piece of the crop, a whole number of 32-pixel steps
     const int S = ((n + NTH - 1) / NTH) * 32;
     const int s0 = min(n, warp * S), s1 = min(n, s0 + S);
     int cnt = 0;
-    float amax = 0.0f;
+    float amax = 0.0f, amin = INFINITY;
 #pragma unroll 4
     for (int q = s0; q < s1; q += 32) {
         const int p = q + lane;
         const float d = p < s1 ? (SMEM ? crop[p] : __ldg(crop + p)) : 0.0f;
         cnt += d != 0.0f;
         amax = fmaxf(amax, fabsf(d));                          // (skips NaN)
+        amin = fminf(amin, d != 0.0f ? fabsf(d) : INFINITY);
     }
     cnt = __reduce_add_sync(FULL, cnt);
-    const unsigned anyinf = __ballot_sync(FULL, amax == INFINITY);
+    // infinite depths (0 * inf = NaN) and depths so small that the low half of a two-float product would be lost
+    // to underflow go to the general form
+    const unsigned anyinf = __ballot_sync(FULL, amax == INFINITY || amin < 0x1p-90f);
     if (lane == 0) { sc->wsum[warp] = cnt; sc->flag[warp] = anyinf != 0u; }
     __syncthreads();
     int base = 0, inf = 0;
@@ -479,6 +475,18 @@ __device__ __noinline__ bool sampled_bbox_fast(const float* __restrict__ crop_g,
         inf |= sc->flag[i];
     }
     if (inf) return false;
+    // P = u d and Q = v d are exact as TWO floats: u, v are integers or half-integers below 2^10 and d has 24 bits, so
+    // hi = RN32(u d) and lo = fma(u, d, -hi) hold the product exactly (no underflow: |d| >= 2^-90 here), and since
+    // rounding is monotone the order of the exact products is the lexicographic order of (hi, lo) - compared as one
+    // 64-bit integer of their ordered bits (-0 < +0 as in dkey).  The extremes of the sample stay in registers: no
+    // per-column / per-row tables, no atomics (round 2, third form of this pass: four shared-memory atomics per
+    // sampled pixel before, 1.015 ms per 8,500 frames).
+    auto key2 = [](float hi, float lo) -> long long {
+        return (long long)(((unsigned long long)(unsigned)fkey(hi) << 32) | (unsigned)(fkey(lo) ^ (int)0x80000000));
+    };
+    long long kpmin = 0x7fffffffffffffffll, kpmax = -0x7fffffffffffffffll - 1, kqmin = kpmin, kqmax = kpmax;
+    float sdmin = INFINITY, sdmax = -INFINITY;
+    const float half_wf = (float)w * 0.5f, half_hf = (float)h * 0.5f;
     {
         {
             const int w0 = 0, wn = n;
@@ -513,11 +521,12 @@ __device__ __noinline__ bool sampled_bbox_fast(const float* __restrict__ crop_g,
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (((word[u] >> (r[u] & 31)) & 1u) && d[u] == d[u]) {
-                        // (one reduction per row in the warp instead of 32 atomics on the same word was
-                        //  measured: slower, 1.30 vs 1.09 ms per 8,500 frames - same-address shared atomics are cheap)
-                        const int k = fkey(d[u]);
-                        atomicMin(&sc->colmin[col], k); atomicMax(&sc->colmax[col], k);
-                        atomicMin(&sc->rowmin[row], k); atomicMax(&sc->rowmax[row], k);
+                        const float uf = __fsub_rn((float)(col + l), half_wf), vf = __fsub_rn((float)(row + t), half_hf);
+                        const float ph = __fmul_rn(uf, d[u]), qh = __fmul_rn(vf, d[u]);
+                        const long long kp = key2(ph, __fmaf_rn(uf, d[u], -ph)), kq = key2(qh, __fmaf_rn(vf, d[u], -qh));
+                        kpmin = min(kpmin, kp); kpmax = max(kpmax, kp);
+                        kqmin = min(kqmin, kq); kqmax = max(kqmax, kq);
+                        sdmin = fminf(sdmin, d[u]); sdmax = fmaxf(sdmax, d[u]);
                     }
                     col += 32;
                     if (wide) { if (col >= bw) { col -= bw; ++row; } }
@@ -525,26 +534,18 @@ __device__ __noinline__ bool sampled_bbox_fast(const float* __restrict__ crop_g,
                 }
             }
         }
-        __syncthreads();
     }
+    // back to float64: hi + lo is the exact product, which is what RN64(u d) is (35 significant bits)
+    auto exact = [](long long k) -> double {
+        const float hi = fkey_inv((int)(k >> 32)), lo = fkey_inv((int)((unsigned)k ^ 0x80000000u));
+        return lo == 0.0f ? (double)hi : __dadd_rn((double)hi, (double)lo);      // (-0 + +0 would lose the sign of a zero product)
+    };
     KeyRange kr;
     kr.init();
-    const double half_w = (double)w / 2.0, half_h = (double)h / 2.0;
-    for (int c = tid; c < bw; c += NTH) {
-        const int klo = sc->colmin[c], khi = sc->colmax[c];
-        if (klo <= khi) {
-            const double u = ((double)c + (double)l) - half_w;
-            kr.p(__dmul_rn(u, (double)fkey_inv(klo))); kr.p(__dmul_rn(u, (double)fkey_inv(khi)));
-        }
-    }
-    for (int c = tid; c < bh; c += NTH) {
-        const int klo = sc->rowmin[c], khi = sc->rowmax[c];
-        if (klo <= khi) {
-            const double v = ((double)c + (double)t) - half_h;
-            const float lo = fkey_inv(klo), hi = fkey_inv(khi);
-            kr.q(__dmul_rn(v, (double)lo)); kr.q(__dmul_rn(v, (double)hi));
-            kr.dmin = fminf(kr.dmin, lo); kr.dmax = fmaxf(kr.dmax, hi);
-        }
+    if (kpmin <= kpmax) {
+        kr.p(exact(kpmin)); kr.p(exact(kpmax));
+        kr.q(exact(kqmin)); kr.q(exact(kqmax));
+        kr.dmin = sdmin; kr.dmax = sdmax;
     }
     sampled_finish<NW>(kr, sc, reinterpret_cast<float*>(smem_raw + OUT6_OFF), focal);
     return true;
@@ -1114,7 +1115,8 @@ dtsdf_fused_kernel(const __grid_constant__ BatchArgs a) {
     const bool scan_exact = !(DEFF || focal_ok);     // no proven fixed-divisor form for this focal
     // the common shape of a sampled frame: per-column / per-row extremes and one bitmap window (prepared now,
     // while the crop is on its way)
-    const bool sampled_fast = sampled && fr.bw <= COLCAP && fr.bh <= ROWCAP && fr.n + 64 <= (int)SCRATCH_BITS;
+    const bool sampled_fast = sampled && fr.n + 64 <= (int)SCRATCH_BITS && fr.bw < (1 << 20) && fr.bh < (1 << 20) &&
+                              abs(fr.l) < (1 << 20) && abs(fr.t) < (1 << 20);          // (u, v exact in float32)
     if constexpr (SAMPLED) {
         if (sampled_fast) sampled_scratch_init<NW>(smem_raw, fr.n);
     }
