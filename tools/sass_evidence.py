@@ -20,7 +20,7 @@ def demangle(name):
 print("# SASS mnemonics per kernel of lib/libdtsdf_b200.so: cuobjdump -sass of the objects __graft_entry__.build() links\n"
       "# (nvcc 12.9, -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false), counted by tools/sass_evidence.py.\n"
       "# UBLKCP.S.G = cp.async.bulk global->shared (TMA bulk copy); SYNCS.*TRANS64 = mbarrier expect-tx / try_wait;\n"
-      "# FFMA2/FMUL2/FADD2 = Blackwell packed FP32 pipe; CREDUX = redux.sync.{min,max}.f32; ATOMS/DMUL = the sampled bounding\n"
+      "# FFMA2/FMUL2/FADD2 = Blackwell packed FP32 pipe; CREDUX = redux.sync.{min,max}.f32; ATOMS.OR / DMUL = the sampled bounding\n"
       "# box; no HMMA / UTC*MMA anywhere (there is no contraction on this path); STL/LDL = spills.\n"
       "# dtsdf_fused_kernel<R, LAYOUT, DEFF, SAMPLED>, dtsdf_aug_kernel<R, LAYOUT>.")
 for obj in ("dtsdf_kernels.cu.o", "dtsdf_codec.cu.o"):
