@@ -157,8 +157,7 @@ class MSRA_Dataset(data.Dataset):
                 if bbox == 'points':
                     _, v, ml, mp = vox.process_frames(frames, point_num, want_points=False)
                 elif packed_host:
-                    v, ml, mp = vox.voxelize_packed_lazy(*pkg.pack_frames(frames)[:3], layout=pkg.LAYOUT_CXYZ,
-                                                         bbox_mode=pkg.BBOX_PIXELS)
+                    v, ml, mp = vox.voxelize_frames_lazy(frames, layout=pkg.LAYOUT_CXYZ, bbox_mode=pkg.BBOX_PIXELS)
                 else:
                     v, ml, mp = vox.voxelize_frames(frames, layout=pkg.LAYOUT_CXYZ, bbox_mode=pkg.BBOX_PIXELS)
                 tsdf.append(v); max_l.append(ml); mid_p.append(mp)

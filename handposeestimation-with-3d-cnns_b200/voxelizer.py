@@ -209,6 +209,12 @@ class Voxelizer:
             return None, out_max_l, out_mid_p
         return PackedHostVolumes(handle, self._lib), out_max_l, out_mid_p
 
+    def voxelize_frames_lazy(self, frames, layout=LAYOUT_CXYZ, bbox_mode=BBOX_PIXELS, aux=None, voxel_res=None):
+        """Frame records -> (PackedHostVolumes, max_l, mid_p): ``voxelize_packed_lazy`` through the staging area."""
+        with self._lock:
+            headers, offsets, packed, _ = pack_frames(frames, scratch=self._staging)
+            return self.voxelize_packed_lazy(headers, offsets, packed, layout, bbox_mode, aux, voxel_res)
+
     @_serialised
     def voxelize_frames(self, frames, layout=LAYOUT_CXYZ, bbox_mode=BBOX_PIXELS, aux=None, voxel_res=None):
         """Frame records -> (vol float32[n,3,R,R,R], max_l float32[n], mid_p float32[n,3])."""
