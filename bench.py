@@ -569,7 +569,7 @@ def run_secondary(pkg, dev, rank, world, args, max_over_ranks, barrier):
     h_in.free()
 
     # ---- ragged crops (every frame its own 80-150 x 80-140 px bounding box)
-    n_r = min(F, 4000)
+    n_r = F
     frames = pkg.synth.make_frames(range(200000 + n_r * rank, 200000 + n_r * (rank + 1)))
     rh, ro, rp, rmax = pkg.pack_frames(frames)
     del frames

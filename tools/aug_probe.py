@@ -24,3 +24,5 @@ def timeit(fn, n=10):
 t0 = timeit(lambda: pkg.voxelize_device(*args, max_px, out_vol=out[0], out_max_l=out[1], out_mid_p=out[2]))
 t1 = timeit(lambda: amod.voxelize_aug_device(*args, aug, max_px, out_vol=out[0], out_max_l=out[1], out_mid_p=out[2]))
 print("plain %.3f ms (%.2f M volumes/s)   augmented %.3f ms (%.2f M volumes/s)" % (t0, F / t0 / 1e3, t1, F / t1 / 1e3))
+t2 = timeit(lambda: amod.voxelize_aug_device(*args, aug, 16, out_vol=out[0], out_max_l=out[1], out_mid_p=out[2]))
+print("augmented, crop left in global memory (staging hint 16 px: more CTAs per SM, lookups through L1): %.3f ms" % t2)
