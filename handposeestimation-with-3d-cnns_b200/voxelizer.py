@@ -61,12 +61,17 @@ def pack_frames(frames, pinned=False, scratch=None):
     else:
         buf = None
         packed = np.zeros(max(packed_len, 4), dtype=np.float32)
-    for i, fr in enumerate(frames):
-        d = np.asarray(frame_depth(fr), dtype=np.float32).reshape(-1)
-        n_px = int(headers[i, 4] - headers[i, 2]) * int(headers[i, 5] - headers[i, 3])
-        if d.size != n_px:
-            raise ValueError("frame %d: depth has %d values, bounding box has %d pixels" % (i, d.size, n_px))
-        packed[offsets[i]:offsets[i] + n_px] = d
+    sizes = (headers[:, 4] - headers[:, 2]).astype(np.int64) * (headers[:, 5] - headers[:, 3])
+    depths = [np.asarray(frame_depth(fr)).reshape(-1) for fr in frames]
+    for i, d in enumerate(depths):
+        if d.size != sizes[i]:
+            raise ValueError("frame %d: depth has %d values, bounding box has %d pixels" % (i, d.size, sizes[i]))
+    if n and not (sizes & 3).any() and all(d.dtype == np.float32 for d in depths):
+        # no padding between the crops (every crop a multiple of four pixels): one concatenation
+        np.concatenate(depths, out=packed[:int(sizes.sum())])
+    else:
+        for i, d in enumerate(depths):
+            packed[offsets[i]:offsets[i] + d.size] = d
     if pinned:
         return headers, offsets, packed, max_px, buf
     return headers, offsets, packed, max_px
