@@ -2322,13 +2322,13 @@ cudaError_t launch_point_cloud(int n_frames, double focal, const float* depth,
                                const long long* point_offsets, int* n_valid,
                                cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    static std::atomic<int> smem_set{0};
-    if (!smem_set.load(std::memory_order_relaxed)) {
-        const cudaError_t e = cudaFuncSetAttribute(point_cloud_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   PC_STAGE_FLOATS * 4);
-        if (e != cudaSuccess) return e;
-        smem_set.store(1, std::memory_order_relaxed);
-    }
+    // (the opt-in limit is a per-device attribute of the kernel)
+    int dev = 0, smem_optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    static std::atomic<unsigned> smem_ok{0u};
+    if (e == cudaSuccess) e = allow_max_smem(point_cloud_kernel, dev, smem_optin, smem_ok);
+    if (e != cudaSuccess) return e;
     point_cloud_kernel<<<n_frames, NT, PC_STAGE_FLOATS * 4, stream>>>(n_frames, focal, depth, offsets, headers, points,
                                                                       point_offsets, n_valid);
     ++g_launch_count;
@@ -2341,12 +2341,13 @@ cudaError_t launch_sample_cloud(int n_frames, double focal, int point_num, const
                                 const int* headers, const int* indices, double* out_pc, float* out_extrema,
                                 int* n_valid, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    static std::atomic<int> smem_set{0};
-    if (!smem_set.load(std::memory_order_relaxed)) {
-        const cudaError_t e = cudaFuncSetAttribute(sample_cloud_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM);
-        if (e != cudaSuccess) return e;
-        smem_set.store(1, std::memory_order_relaxed);
-    }
+    // (the opt-in limit is a per-device attribute of the kernel)
+    int dev = 0, smem_optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    static std::atomic<unsigned> smem_ok{0u};
+    if (e == cudaSuccess) e = allow_max_smem(sample_cloud_kernel, dev, smem_optin, smem_ok);
+    if (e != cudaSuccess) return e;
     sample_cloud_kernel<<<n_frames, NT, SC_SMEM, stream>>>(focal, point_num, depth, offsets, headers, indices, out_pc,
                                                            out_extrema, n_valid);
     ++g_launch_count;

@@ -683,6 +683,18 @@ def test_host_entry_points_restore_the_current_device():
     x = torch.zeros(4, device="cuda")
     assert x.device.index == 0
     assert _same(got, c_oracle.dtsdf_batch(*pack_simple(frames))[0])
+    # every kernel of the process() path on the second device as well (kernel attributes such as the opt-in shared
+    # memory limit are per device), same results as on the first
+    v0 = pkg.Voxelizer(device=0)
+    for want_points in (True, False):
+        np.random.seed(3)
+        a = v0.process_frames(frames, 6000, want_points=want_points)
+        np.random.seed(3)
+        b = v1.process_frames(frames, 6000, want_points=want_points)
+        assert torch.cuda.current_device() == 0
+        assert (a[0] is None and b[0] is None) or np.array_equal(a[0], b[0])
+        assert _same(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    v0.close()
     v1.close()
     assert torch.cuda.current_device() == 0
 
