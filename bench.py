@@ -371,6 +371,35 @@ def run_gather_legs(pkg, dist, dev, rank, world, F, R, cfg, inputs, d_vol, d_max
                      "matches_nccl_gather_all_frames": all_ok(same), "bytes_pulled_over_nvlink": int(nvlink_bytes),
                      "rank0_ingress_gbs": nvlink_bytes / (ms * 1e-3) / 1e9,
                      "rank0_hbm_write_gbs": world * vol_bytes / (ms * 1e-3) / 1e9}
+    # ---- packed, in two parts: the root expands the first half of every rank while the others voxelise and pack
+    #      their second half
+    PARTS = 2
+
+    def voxelise_rows(out, f0, f1):
+        pkg.voxelize_device(d_packed, d_off[f0:f1], d_hdr[f0:f1], max_px, cfg, out_vol=out[f0:f1], out_max_l=d_maxl[f0:f1],
+                            out_mid_p=d_mid[f0:f1])
+
+    def parts_step():
+        if rank == 0:
+            voxelise(g.mine)
+            for k in range(PARTS):
+                g.gather_part(k, PARTS)
+        else:
+            for k in range(PARTS):
+                f0, f1 = g.part(rank, k, PARTS)
+                voxelise_rows(d_vol, f0, f1)
+                g.gather_part(k, PARTS, d_vol)
+        g.finish_parts()
+    if rank == 0:
+        g.full.zero_()
+    ms = timed(parts_step, reps=5, warm=2)
+    same = True
+    if rank == 0:
+        same = all(bool(torch.equal(g.full[r * F:(r + 1) * F].view(torch.int32), bufs[r].view(torch.int32)))
+                   for r in range(world))
+    res["packed_in_parts"] = {"value": F * world / (ms * 1e-3), "unit": UNIT, "ms": ms, "parts": PARTS,
+                              "matches_nccl_gather_all_frames": all_ok(same),
+                              "rank0_hbm_write_gbs": world * vol_bytes / (ms * 1e-3) / 1e9}
     g.close()
     del g, bufs
     torch.cuda.empty_cache()
@@ -384,8 +413,8 @@ def run_gather_legs(pkg, dist, dev, rank, world, F, R, cfg, inputs, d_vol, d_max
                 "%.0f GB/s): no gather into one GPU can beat ~%.1f M volumes/s, about one GPU's own voxelising rate; "
                 "NVLink ingress at the measured %.0f GB/s peer-copy rate bounds the dense forms far below that"
                 % (world * vol_bytes / 1e9, peak, F * world / hbm_ms / 1e3, NVLINK_PEER_GBS),
-        "packed_frac_of_hbm_write_bound": hbm_ms / res["packed"]["ms"]}
-    res["best"] = max(("nccl", "p2p", "packed"), key=lambda k: res[k]["value"])
+        "packed_frac_of_hbm_write_bound": hbm_ms / min(res["packed"]["ms"], res["packed_in_parts"]["ms"])}
+    res["best"] = max(("nccl", "p2p", "packed", "packed_in_parts"), key=lambda k: res[k]["value"])
     return res
 
 

@@ -43,6 +43,13 @@ class PackedVolumes:
         self.lit_count = storage[offs[1]:offs[1] + sizes[1]].view(torch.int32)
         self.lits = storage[offs[2]:offs[2] + sizes[2]].view(torch.float32).view(n, 3 * r3)
 
+    def rows(self, f0, f1):
+        """The packed form of volumes [f0, f1) as an object of its own (a view: same memory)."""
+        v = object.__new__(PackedVolumes)
+        v.n_frames, v.voxel_res, v.nbytes, v.storage = int(f1) - int(f0), self.voxel_res, self.nbytes, self.storage
+        v.codes, v.lit_count, v.lits = self.codes[f0:f1], self.lit_count[f0:f1], self.lits[f0:f1]
+        return v
+
     @staticmethod
     def storage_bytes(n_frames, voxel_res=32):
         r3 = int(voxel_res) ** 3

@@ -176,6 +176,36 @@ class PackedVolumeGather:
         self._stream_barrier()
         return self.full
 
+    # ---- the same in parts: the root expands part k of every rank while the others produce part k + 1
+    def part(self, r, k, parts):
+        """Frames [f0, f1) of rank r that make up part k of ``parts``."""
+        n = self.counts[r]
+        return n * k // parts, n * (k + 1) // parts
+
+    def gather_part(self, k, parts, vol=None):
+        """Collective, once per part and in order.  Non-root ranks: ``vol`` holds the rank's dense volumes with part
+        k written (current stream); it is packed into the same rows of the shared buffer.  Root: its own part k is
+        enqueued already; after the barrier it expands part k of every other rank.  With two parts the root's
+        expansion of the first half covers the other ranks' voxelising and packing of the second - what is left
+        of the step is the root's own voxelisation plus its expansion of everything.  ``finish_parts()`` after the
+        last part."""
+        if self.rank != self.root and self.packed is not None:
+            f0, f1 = self.part(self.rank, k, parts)
+            if f1 > f0:
+                pack_volumes_device(vol[f0:f1], self.packed.rows(f0, f1))
+        self._stream_barrier()
+        if self.rank == self.root:
+            for r, pk in self.peers.items():
+                f0, f1 = self.part(r, k, parts)
+                if f1 > f0:
+                    s = int(self.starts[r])
+                    unpack_volumes_device(pk.rows(f0, f1), out=self.full[s + f0:s + f1])
+
+    def finish_parts(self):
+        """Collective: the packed buffers may be rewritten once this has been enqueued on every rank."""
+        self._stream_barrier()
+        return self.full
+
     def bytes_on_nvlink(self):
         """Bytes the root pulls from the other ranks per gather (a collective; synchronises)."""
         mine = self.packed.bytes_in_use() if self.packed is not None else 0

@@ -42,16 +42,31 @@ def main():
         full = g.gather()
     nbytes = g.bytes_on_nvlink()
     # every rank sends its local volumes the plain way for the comparison
-    ok = True
+    refs = {}
     for r in range(world):
         if rank == 0:
             ref = local_vol if r == 0 else torch.empty((counts[r], 3, 32, 32, 32), dtype=torch.float32, device=dev)
             if r != 0:
                 dist.recv(ref, src=r)
-            got = full[sum(counts[:r]):sum(counts[:r + 1])]
-            ok = ok and bool(torch.equal(got.view(torch.int32), ref.view(torch.int32)))
+            refs[r] = ref
         elif rank == r:
             dist.send(local_vol, dst=0)
+
+    def equal_everywhere(full):
+        return all(bool(torch.equal(full[sum(counts[:r]):sum(counts[:r + 1])].view(torch.int32), refs[r].view(torch.int32)))
+                   for r in range(world))
+    ok = equal_everywhere(full) if rank == 0 else True
+    # the same in parts (gather_part / finish_parts): one, three and seven parts, the shared buffers reused
+    for parts in (1, 3, 7):
+        if rank == 0:
+            g.full.zero_()
+            pkg.voxelize_device(d[0], d[1], d[2], max_px, out_vol=g.mine)
+        for k in range(parts):
+            g.gather_part(k, parts, None if rank == 0 else local_vol)
+        full = g.finish_parts()
+        torch.cuda.synchronize()
+        if rank == 0:
+            ok = ok and equal_everywhere(full)
     g.close()
     if rank == 0:
         dense = sum(counts[1:]) * 3 * 32 ** 3 * 4
