@@ -96,6 +96,14 @@ __device__ __forceinline__ float div_fixed(float a, float b, float y) {
     return q;
 }
 
+// A 4-byte read of the staged crop through its shared-memory address: where a kernel keeps the crop as a
+// pointer that is shared OR global at run time, the compiler can only emit generic LD.E with 64-bit address arithmetic.
+__device__ __forceinline__ float lds_f32(unsigned saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+
 // ---------------------------------------------------------------- shared memory
 template <int R, int LAYOUT, int NW>
 struct __align__(16) FrameShared {
@@ -1467,6 +1475,7 @@ __global__ void __launch_bounds__(NT) point_cloud_kernel(int n_frames, double fo
         __syncthreads();
         mbar_wait(&bar, 0);
     }
+    // (reads through the generic pointer: explicit shared-space loads were measured here, 0.646 vs 0.578 ms)
     const float* crop = staged ? reinterpret_cast<const float*>(smem_raw) : crop_g;
     double* out = points ? points + 3 * point_offsets[f] : nullptr;
     // the warp's piece: steps of 32 pixels [s0, s1)
@@ -1821,6 +1830,7 @@ constexpr int AUG_NT = DTSDF_AUG_NT, AUG_NW = AUG_NT / 32, AUG_MIN_CTAS = DTSDF_
 // Per-frame constants of the augmented voxel loop.
 struct AugFrame {
     const float* crop;            // staged (shared) or global crop
+    unsigned crop_s32;            // the staged crop's address in the shared window (STAGED only)
     int l, t, bw, bh;
     int cx, cy;
     float focal, trunc;
@@ -1891,7 +1901,7 @@ __device__ __forceinline__ float aug_lookup(const AugFrame& k, float vx, float v
     const float fs = __fadd_rn(fpx, fpy);
     const bool in = ux < (unsigned)k.bw && uy < (unsigned)k.bh && fs == fs;
     const int idx = in ? (int)uy * k.bw + (int)ux : -1;
-    if (STAGED) return k.crop[idx];
+    if (STAGED) return lds_f32(k.crop_s32 + 4u * (unsigned)idx);       // (idx = -1: the zero word below the crop)
     return in ? __ldg(k.crop + idx) : 0.0f;
 }
 
@@ -2115,6 +2125,7 @@ __global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const _
     __syncthreads();
     if (fr.staged) mbar_wait(&bar, 0);
     const float* __restrict__ crop = fr.staged ? crop_s : fr.crop;
+    const unsigned crop_s32 = smem_u32(crop_s);
     const float *A = aug, *Ainv = aug + 9, *c = aug + 18;
     const float focal = a.focal;
 
@@ -2129,8 +2140,9 @@ __global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const _
         for (int row = warp; row < fr.bh; row += AUG_NW) {
             const float fy = (float)(row + fr.t - a.center_y);
             for (int col = lane; col < fr.bw; col += 64) {
-                const float d0 = crop[row * fr.bw + col];
-                const float d1 = col + 32 < fr.bw ? crop[row * fr.bw + col + 32] : 0.0f;
+                const int i0 = row * fr.bw + col;
+                const float d0 = fr.staged ? lds_f32(crop_s32 + 4u * (unsigned)i0) : __ldg(fr.crop + i0);
+                const float d1 = col + 32 < fr.bw ? (fr.staged ? lds_f32(crop_s32 + 4u * (unsigned)(i0 + 32)) : __ldg(fr.crop + i0 + 32)) : 0.0f;
                 const bool v0 = !(fabsf(d0) < 1.0f), v1 = !(fabsf(d1) < 1.0f);
                 if (!(v0 || v1)) continue;
                 float2 q;
@@ -2223,7 +2235,7 @@ __global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const _
     }
     __shared__ unsigned short glist[AUG_NW][64];
     AugFrame k;
-    k.crop = crop; k.l = fr.l; k.t = fr.t; k.bw = max(fr.bw, 0); k.bh = max(fr.bh, 0);   // bad header: empty crop
+    k.crop = crop; k.crop_s32 = smem_u32(crop_s); k.l = fr.l; k.t = fr.t; k.bw = max(fr.bw, 0); k.bh = max(fr.bh, 0);   // bad header: empty crop
     k.cx = a.center_x; k.cy = a.center_y; k.focal = focal; k.trunc = trunc;
     k.yf = __frcp_rn(focal); k.ytr = __frcp_rn(trunc);
     k.fast_f = __float_as_uint(focal) == DEFAULT_FOCAL_BITS;
