@@ -1821,6 +1821,21 @@ __device__ __forceinline__ void xform(float px, float py, float pz, const float*
 // CTA shape of the augmented kernel: 8 warps, three CTAs per SM (the staged crop allows no more).  Measured on B200,
 // 8,500 default frames: 256 x 3 1.306 ms; 512 x 2 (64 registers, 140 bytes spilled) 1.453 ms; 384 x 2 with the
 // round-2 experiments 1.49 ms - with two CTAs per SM nothing covers a CTA's prologue (crop wait, bounding box, tables).
+#ifndef DTSDF_AUGX_SAFE
+#define DTSDF_AUGX_SAFE 1
+#endif
+#ifndef DTSDF_AUGX_MIN3
+#define DTSDF_AUGX_MIN3 1
+#endif
+#ifndef DTSDF_AUGX_TRUNC3
+#define DTSDF_AUGX_TRUNC3 1
+#endif
+#ifndef DTSDF_AUGX_OPAQUE
+#define DTSDF_AUGX_OPAQUE 1
+#endif
+#ifndef DTSDF_AUGX_SELP
+#define DTSDF_AUGX_SELP 1
+#endif
 #ifndef DTSDF_AUG_NT
 #define DTSDF_AUG_NT 256
 #define DTSDF_AUG_MIN_CTAS 3
@@ -1888,21 +1903,50 @@ __device__ __forceinline__ void aug_camera4(const AugTables<R>* __restrict__ T, 
 // Projection and depth lookup of one voxel (pre/process.py:154-167), branch-free.  Returns the depth, or a
 // value with |d| < 1 ("no depth": the voxel stays 0) when the projection is not finite or outside the crop.
 // STAGED: the crop is in shared memory and the word right below it is 0.0f - the target of "outside".
-template <bool STAGED>
+// coeff = -focal / v_z (pre/process.py:154).  SAFE is a per-frame fact (aug_grid_is_safe): every voxel of the frame
+// has 2^-60 <= |v_z| <= 2^60, and 2^-20 <= |focal| <= 2^20.  The division is then the straight-line part of what the
+// compiler emits for __fdiv_rn - reciprocal seed (MUFU.RCP), one Newton step, quotient, one residual correction -
+// without the range check and the branch to a slow path that every IEEE division carries (four per voxel group: the
+// compiler cannot schedule across them).  Equal to __fdiv_rn: tests/native/rcp_division_check.cu runs EVERY divisor
+// of the range on the GPU, for the default focal and 64 other dividends (the seed is a hardware approximation).
+template <bool SAFE>
+__device__ __forceinline__ float aug_div_coeff(float nf, float vz) {
+    if (!SAFE) return __fdiv_rn(nf, vz);
+    const float r0 = rcp_approx(vz);
+    const float r1 = __fmaf_rn(r0, __fmaf_rn(-vz, r0, 1.0f), r0);
+    const float q0 = __fmul_rn(nf, r1);
+    return __fmaf_rn(r1, __fmaf_rn(-vz, q0, nf), q0);
+}
+
+template <bool STAGED, bool SAFE>
 __device__ __forceinline__ float aug_lookup(const AugFrame& k, float vx, float vy, float vz, int& px, int& py) {
-    const float coeff = __fdiv_rn(-k.focal, vz);
+    const float coeff = aug_div_coeff<SAFE>(-k.focal, vz);
     const float fpx = __fadd_rn(__fmul_rn(vx, coeff), (float)k.cx);
     const float fpy = __fadd_rn(__fmul_rn(-vy, coeff), (float)k.cy);
     // the specification drops |fp| >= 2e9 (or NaN) before int(): the conversion saturates, so anything
-    // that large falls outside the crop by itself; only NaN (which converts to 0) needs its own test
+    // that large falls outside the crop by itself; only NaN (which converts to 0) needs its own test -
+    // and in a SAFE frame (finite v, finite non-zero coeff) no NaN can arise
     px = __float2int_rz(fpx);
     py = __float2int_rz(fpy);
     const unsigned ux = (unsigned)(px - k.l), uy = (unsigned)(py - k.t);
-    const float fs = __fadd_rn(fpx, fpy);
-    const bool in = ux < (unsigned)k.bw && uy < (unsigned)k.bh && fs == fs;
-    const int idx = in ? (int)uy * k.bw + (int)ux : -1;
-    if (STAGED) return lds_f32(k.crop_s32 + 4u * (unsigned)idx);       // (idx = -1: the zero word below the crop)
-    return in ? __ldg(k.crop + idx) : 0.0f;
+#if DTSDF_AUGX_SELP
+    if (STAGED && SAFE) {                                               // (outside: the zero word below the crop)
+        int idx;                                                        // one predicate, one select
+        asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\tsetp.lt.and.u32 p, %3, %4, p;\n\tselp.b32 %0, %5, -1, p;\n\t}"
+            : "=r"(idx) : "r"(ux), "r"((unsigned)k.bw), "r"(uy), "r"((unsigned)k.bh), "r"((int)(uy * (unsigned)k.bw + ux)));
+        return lds_f32(k.crop_s32 + 4u * (unsigned)idx);
+    }
+#endif
+    bool in = (ux < (unsigned)k.bw) & (uy < (unsigned)k.bh);
+    if (!SAFE) {
+        const float fs = __fadd_rn(fpx, fpy);
+        in = in & (fs == fs);
+    }
+    if (STAGED) {                                                       // (outside: the zero word below the crop)
+        const unsigned off = in ? 4u * (uy * (unsigned)k.bw + ux) : 0xfffffffcu;
+        return lds_f32(k.crop_s32 + off);
+    }
+    return in ? __ldg(k.crop + ((int)uy * k.bw + (int)ux)) : 0.0f;
 }
 
 // a / trunc and d / focal of pass 2: the fixed-divisor forms (div_fixed, file header) inside their proven
@@ -1919,7 +1963,7 @@ __device__ __forceinline__ float aug_div_focal(const AugFrame& k, float d) {
 }
 
 // Pass 1: every voxel of the group is 0, +-1 by the far-surface shortcut, or "near".
-template <int R, int LAYOUT, bool STAGED>
+template <int R, int LAYOUT, bool STAGED, bool SAFE>
 __device__ __forceinline__ bool aug_classify_group(const AugFrame& k, const AugTables<R>* __restrict__ T, int g, float4& val) {
     int f0, m, s;
     aug_group_index<R, LAYOUT>(g, f0, m, s);
@@ -1929,7 +1973,7 @@ __device__ __forceinline__ bool aug_classify_group(const AugFrame& k, const AugT
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         int px, py;
-        const float d = aug_lookup<STAGED>(k, vx[j], vy[j], vz[j], px, py);
+        const float d = aug_lookup<STAGED, SAFE>(k, vx[j], vy[j], vz[j], px, py);
         const float sz = __fadd_rn(vz[j], d);                      // v_z - w_z, w_z = -d
         const bool valid = !(fabsf(d) < 1.0f);
         const bool far = fabsf(sz) > k.t_far && fabsf(d) < BIG_DEPTH;
@@ -1941,7 +1985,7 @@ __device__ __forceinline__ bool aug_classify_group(const AugFrame& k, const AugT
 }
 
 // Pass 2: the specification's evaluation of all four voxels of a listed group.
-template <int R, int LAYOUT, bool STAGED>
+template <int R, int LAYOUT, bool STAGED, bool SAFE>
 __device__ __forceinline__ void aug_eval_group(const AugFrame& k, const AugTables<R>* __restrict__ T,
                                                const float* __restrict__ A, const float* __restrict__ c,
                                                int g, float* __restrict__ out) {
@@ -1954,7 +1998,7 @@ __device__ __forceinline__ void aug_eval_group(const AugFrame& k, const AugTable
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         int px, py;
-        const float d = aug_lookup<STAGED>(k, vx[j], vy[j], vz[j], px, py);
+        const float d = aug_lookup<STAGED, SAFE>(k, vx[j], vy[j], vz[j], px, py);
         float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
         if (!(fabsf(d) < 1.0f)) {
             const int xi = LAYOUT == 0 ? s : f0 + j, zi = LAYOUT == 0 ? f0 + j : s;
@@ -1962,9 +2006,22 @@ __device__ __forceinline__ void aug_eval_group(const AugFrame& k, const AugTable
             const float c1 = aug_div_focal(k, d);
             float wa[3];
             xform(__fmul_rn((float)(px - k.cx), c1), __fmul_rn((float)(-(py - k.cy)), c1), -d, A, c, wa);
+#if DTSDF_AUGX_TRUNC3
+            // the three divisions by trunc behind ONE range test (aug_div_trunc's, on the smallest and the largest of
+            // the three magnitudes; a zero difference takes the IEEE branch with the rest of its voxel)
+            const float a0 = __fsub_rn(va0, wa[0]), a1 = __fsub_rn(va1, wa[1]), a2 = __fsub_rn(va2, wa[2]);
+            if (k.fast_t && fmin3(fabsf(a0), fabsf(a1), fabsf(a2)) >= 0x1p-60f && fmax3(fabsf(a0), fabsf(a1), fabsf(a2)) <= 0x1p60f) {
+                t0 = fabsf(div_fixed<false>(a0, k.trunc, k.ytr));         // |a| / b == |a / b| under RN
+                t1 = fabsf(div_fixed<false>(a1, k.trunc, k.ytr));
+                t2 = fabsf(div_fixed<false>(a2, k.trunc, k.ytr));
+            } else {
+                t0 = fabsf(__fdiv_rn(a0, k.trunc)); t1 = fabsf(__fdiv_rn(a1, k.trunc)); t2 = fabsf(__fdiv_rn(a2, k.trunc));
+            }
+#else
             t0 = fabsf(aug_div_trunc(k, __fsub_rn(va0, wa[0])));          // |a| / b == |a / b| under RN
             t1 = fabsf(aug_div_trunc(k, __fsub_rn(va1, wa[1])));
             t2 = fabsf(aug_div_trunc(k, __fsub_rn(va2, wa[2])));
+#endif
             const float ss = __fadd_rn(__fadd_rn(__fmul_rn(t0, t0), __fmul_rn(t1, t1)), __fmul_rn(t2, t2));
             // sqrt_rn(ss) > 1 <=> ss > nextafter(1,2); then min(t,1) is the identity below it,
             // except for NaN (kept) - same as the specification's comparisons
@@ -1983,7 +2040,7 @@ __device__ __forceinline__ void aug_eval_group(const AugFrame& k, const AugTable
 }
 
 // Both passes over one frame.
-template <int R, int LAYOUT, bool STAGED>
+template <int R, int LAYOUT, bool STAGED, bool SAFE>
 __device__ __forceinline__ void aug_voxel_passes(const AugFrame& k, const AugTables<R>* __restrict__ T,
                                                  const float* __restrict__ A, const float* __restrict__ c,
                                                  unsigned short* __restrict__ list, float* __restrict__ out) {
@@ -1994,7 +2051,7 @@ __device__ __forceinline__ void aug_voxel_passes(const AugFrame& k, const AugTab
 #pragma unroll 1
     for (int g = tid; g < CH / 4; g += AUG_NT) {
         float4 val;
-        bool near = aug_classify_group<R, LAYOUT, STAGED>(k, T, g, val);
+        bool near = aug_classify_group<R, LAYOUT, STAGED, SAFE>(k, T, g, val);
         // a 32-byte sector (an even/odd lane pair) is written once, whole: by pass 1 or by pass 2
         unsigned bal = __ballot_sync(FULL, near);
         bal |= ((bal & 0x55555555u) << 1) | ((bal & 0xAAAAAAAAu) >> 1);
@@ -2008,7 +2065,7 @@ __device__ __forceinline__ void aug_voxel_passes(const AugFrame& k, const AugTab
         cnt += __popc(bal);
         if (cnt >= 32) {
             __syncwarp();
-            aug_eval_group<R, LAYOUT, STAGED>(k, T, A, c, (int)list[lane], out);
+            aug_eval_group<R, LAYOUT, STAGED, SAFE>(k, T, A, c, (int)list[lane], out);
             const int rem = cnt - 32;
             unsigned short carry = 0;
             if (lane < rem) carry = list[32 + lane];
@@ -2018,7 +2075,7 @@ __device__ __forceinline__ void aug_voxel_passes(const AugFrame& k, const AugTab
         }
     }
     __syncwarp();
-    if (lane < cnt) aug_eval_group<R, LAYOUT, STAGED>(k, T, A, c, (int)list[lane], out);
+    if (lane < cnt) aug_eval_group<R, LAYOUT, STAGED, SAFE>(k, T, A, c, (int)list[lane], out);
 }
 
 // Far-surface shortcut of the augmented path.  In exact arithmetic v' - w' = (v* - w) . A with v* the
@@ -2097,6 +2154,34 @@ __device__ __forceinline__ float aug_far_threshold(const float* __restrict__ A, 
     return ok ? t_far : INFINITY;
 }
 
+// Is the whole grid of the frame inside the range aug_div_coeff<true> is proven for, and free of NaN sources?
+// The per-axis table entries (AugTables) are monotone in the voxel index - every step of their evaluation is a
+// correctly rounded monotone operation - and so is the table sum: the extremes over the grid of each camera-frame
+// component are EXACTLY the sums of the per-axis extremes, which sit at the first and last voxel of each axis.
+template <int R>
+__device__ __forceinline__ bool aug_grid_is_safe(float ox, float oy, float oz, float voxel_len, const float* __restrict__ Ainv,
+                                                 const float* __restrict__ c, float focal) {
+    const float o[3] = {ox, oy, oz};
+    bool ok = fabsf(focal) >= 0x1p-20f && fabsf(focal) <= 0x1p20f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float lo[3], hi[3];
+#pragma unroll
+        for (int axis = 0; axis < 3; ++axis) {
+            const float d0 = __fsub_rn(__fadd_rn(o[axis], __fmul_rn(0.0f, voxel_len)), c[axis]);
+            const float d1 = __fsub_rn(__fadd_rn(o[axis], __fmul_rn((float)(R - 1), voxel_len)), c[axis]);
+            const float e0 = axis < 2 ? __fmul_rn(d0, Ainv[3 * axis + k]) : __fmaf_rn(d0, Ainv[6 + k], c[k]);
+            const float e1 = axis < 2 ? __fmul_rn(d1, Ainv[3 * axis + k]) : __fmaf_rn(d1, Ainv[6 + k], c[k]);
+            ok = ok && e0 == e0 && e1 == e1;
+            lo[axis] = fminf(e0, e1); hi[axis] = fmaxf(e0, e1);
+        }
+        const float vlo = __fadd_rn(lo[0], __fadd_rn(lo[1], lo[2])), vhi = __fadd_rn(hi[0], __fadd_rn(hi[1], hi[2]));
+        ok = ok && fabsf(vlo) <= 0x1p60f && fabsf(vhi) <= 0x1p60f;
+        if (k == 2) ok = ok && (vlo >= 0x1p-60f || vhi <= -0x1p-60f);
+    }
+    return ok;
+}
+
 template <int R, int LAYOUT>
 __global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const __grid_constant__ BatchArgs a,
                                                        const float* __restrict__ aug_all) {
@@ -2106,6 +2191,7 @@ __global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const _
     __shared__ unsigned long long bar;
     __shared__ AugTables<R> tab;
     __shared__ float t_far_s;
+    __shared__ int safe_s;
     // the staged crop starts 16 bytes into the dynamic shared memory; the word right below it is 0.0f
     // ("no depth"), where lookups that fall outside the crop are pointed
     float* crop_s = reinterpret_cast<float*>(smem_raw + 16);
@@ -2145,17 +2231,25 @@ __global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const _
                 const float d1 = col + 32 < fr.bw ? (fr.staged ? lds_f32(crop_s32 + 4u * (unsigned)(i0 + 32)) : __ldg(fr.crop + i0 + 32)) : 0.0f;
                 const bool v0 = !(fabsf(d0) < 1.0f), v1 = !(fabsf(d1) < 1.0f);
                 if (!(v0 || v1)) continue;
+                float fx0 = (float)(col + fr.l - a.center_x), fx1 = (float)(col + 32 + fr.l - a.center_x);
+#if DTSDF_AUGX_MIN3
+                // a pixel without depth takes its partner's place: the pair then holds the valid pixel twice and
+                // the extremes need no per-pixel guard (three-input minimum / maximum over both lanes of the pair)
+                const float e0 = v0 ? d0 : d1, e1 = v1 ? d1 : d0;
+                fx0 = v0 ? fx0 : fx1; fx1 = v1 ? fx1 : fx0;
+#else
+                const float e0 = d0, e1 = d1;
+#endif
                 float2 q;
-                if (deff && fabsf(d0) < BIG_DEPTH && fabsf(d1) < BIG_DEPTH)
-                    q = div_fixed2<true>(make_float2(d0, d1), make_float2(-focal, -focal), make_float2(yf, yf));
+                if (deff && fabsf(e0) < BIG_DEPTH && fabsf(e1) < BIG_DEPTH)
+                    q = div_fixed2<true>(make_float2(e0, e1), make_float2(-focal, -focal), make_float2(yf, yf));
                 else
-                    q = make_float2(__fdiv_rn(d0, focal), __fdiv_rn(d1, focal));
+                    q = make_float2(__fdiv_rn(e0, focal), __fdiv_rn(e1, focal));
                 // X, Y are products that are then added to: scalar mul.rn, scalar add.rn (ptxas contracts the
                 // packed forms, see eval_pair); from dx on, every product is inside a specified fma
-                const float fx0 = (float)(col + fr.l - a.center_x), fx1 = (float)(col + 32 + fr.l - a.center_x);
                 const float2 dx = make_float2(__fsub_rn(__fmul_rn(q.x, fx0), c[0]), __fsub_rn(__fmul_rn(q.y, fx1), c[0]));
                 const float2 dy = make_float2(__fsub_rn(__fmul_rn(-q.x, fy), c[1]), __fsub_rn(__fmul_rn(-q.y, fy), c[1]));
-                const float2 dz = __fadd2_rn(make_float2(-d0, -d1), nc2);
+                const float2 dz = __fadd2_rn(make_float2(-e0, -e1), nc2);
                 float2 pa[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -2166,8 +2260,12 @@ __global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const _
                 }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
+#if DTSDF_AUGX_MIN3
+                    mn[k] = fmin3(mn[k], pa[k].x, pa[k].y); mx[k] = fmax3(mx[k], pa[k].x, pa[k].y);
+#else
                     if (v0) { mn[k] = pa[k].x < mn[k] ? pa[k].x : mn[k]; mx[k] = pa[k].x > mx[k] ? pa[k].x : mx[k]; }
                     if (v1) { mn[k] = pa[k].y < mn[k] ? pa[k].y : mn[k]; mx[k] = pa[k].y > mx[k] ? pa[k].y : mx[k]; }
+#endif
                 }
             }
         }
@@ -2235,18 +2333,26 @@ __global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const _
     }
     __shared__ unsigned short glist[AUG_NW][64];
     AugFrame k;
-    k.crop = crop; k.crop_s32 = smem_u32(crop_s); k.l = fr.l; k.t = fr.t; k.bw = max(fr.bw, 0); k.bh = max(fr.bh, 0);   // bad header: empty crop
+    k.crop = crop; k.crop_s32 = smem_u32(crop_s);
+#if DTSDF_AUGX_OPAQUE
+    asm volatile("" : "+r"(k.crop_s32));      // kept in a register: rebuilt from the CTA's shared window per group otherwise
+#endif
+ k.l = fr.l; k.t = fr.t; k.bw = max(fr.bw, 0); k.bh = max(fr.bh, 0);   // bad header: empty crop
     k.cx = a.center_x; k.cy = a.center_y; k.focal = focal; k.trunc = trunc;
     k.yf = __frcp_rn(focal); k.ytr = __frcp_rn(trunc);
     k.fast_f = __float_as_uint(focal) == DEFAULT_FOCAL_BITS;
     k.fast_t = trunc >= 0x1p-20f && trunc <= 0x1p20f;
     // (one thread, not one of those filling the tables: a few hundred instructions that every thread used to repeat)
-    if (tid == AUG_NT - 1) t_far_s = aug_far_threshold(A, Ainv, c, trunc, max_l, mid0, mid1, mid2);
+    if (tid == AUG_NT - 1) {
+        t_far_s = aug_far_threshold(A, Ainv, c, trunc, max_l, mid0, mid1, mid2);
+        safe_s = aug_grid_is_safe<R>(ox, oy, oz, voxel_len, Ainv, c, focal) ? 1 : 0;
+    }
     __syncthreads();          // the tables are complete
     k.t_far = t_far_s;
     float* out = a.vol + (size_t)f * 3 * CH;
-    if (fr.staged) aug_voxel_passes<R, LAYOUT, true>(k, &tab, A, c, glist[warp], out);
-    else           aug_voxel_passes<R, LAYOUT, false>(k, &tab, A, c, glist[warp], out);
+    if (!fr.staged)                     aug_voxel_passes<R, LAYOUT, false, false>(k, &tab, A, c, glist[warp], out);
+    else if (DTSDF_AUGX_SAFE && safe_s) aug_voxel_passes<R, LAYOUT, true, true>(k, &tab, A, c, glist[warp], out);
+    else                                aug_voxel_passes<R, LAYOUT, true, false>(k, &tab, A, c, glist[warp], out);
 }
 
 template <int R, int LAYOUT>

@@ -55,6 +55,23 @@ __device__ __forceinline__ float warp_max(float v) {
     asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
     return r;
 }
+// Three-input minimum / maximum (FMNMX3, sm_100); a NaN operand is ignored like in the two-input forms.
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// MUFU.RCP alone (no subnormal handling): the seed of aug_div_coeff.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 
 }  // namespace ptx

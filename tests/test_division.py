@@ -41,3 +41,20 @@ def test_float64_division_by_a_fixed_divisor(tmp_path):
     out = subprocess.run([exe, "200000000"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "mismatches=0" in out.stdout
+
+
+@pytest.mark.gpu
+def test_reciprocal_divisions_of_the_augmented_voxeliser_on_the_gpu(tmp_path):
+    """coeff = -focal / v_z of the augmented voxeliser (csrc/dtsdf_kernels.cu: aug_div_coeff) inside the range its
+    per-frame test guarantees: the reciprocal forms equal __fdiv_rn for EVERY divisor with 2^-60 <= |z| <= 2^60 -
+    the five-FMA form for the default focal and 64 other dividends, the three-FMA form for the default focal.
+    Runs on the GPU: the seed (MUFU.RCP) is a hardware approximation (tests/native/rcp_division_check.cu)."""
+    import __graft_entry__ as g
+    exe = g.RCP_CHECK
+    if not os.path.exists(exe):
+        exe = str(tmp_path / "rcp_division_check")
+        subprocess.run([g._find("nvcc"), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false",
+                        os.path.join(HERE, "native", "rcp_division_check.cu"), "-o", exe], check=True)
+    out = subprocess.run([exe, "64"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "five_fma mismatches=0 " in out.stdout and "three_fma mismatches=0 " in out.stdout

@@ -12,11 +12,8 @@ EXP = os.path.join(ROOT, "tools", "_exp")
 def build(name, flags):
     import __graft_entry__ as g
     os.makedirs(EXP, exist_ok=True)
-    srcs = [os.path.join(g.CSRC, "dtsdf_kernels.cu"), os.path.join(g.CSRC, "dtsdf_capi.cu"),
-            os.path.join(g.CSRC, "dtsdf_decode.cpp")]
-    only32 = [] if "--all-res" in flags else ["-DDTSDF_EXP_ONLY32"]
-    flags = [f for f in flags if f != "--all-res"]
-    cmd = [g._find("nvcc")] + g.NVCC_FLAGS + only32 + flags + srcs + ["-o", os.path.join(EXP, name + ".so")]
+    srcs = [os.path.join(g.CSRC, n) for n in g.CUDA_SOURCES]
+    cmd = [g._find("nvcc")] + g.NVCC_FLAGS + flags + srcs + ["-o", os.path.join(EXP, name + ".so")]
     subprocess.run(cmd, check=True, cwd=ROOT)
 
 
