@@ -1802,10 +1802,10 @@ __global__ void normalize_joints_kernel(int total, const float* __restrict__ joi
 // ---------------------------------------------------------------- augmented D-TSDF
 // Specification: oracle/dtsdf_oracle.c, oracle_dtsdf_aug_frame (the
 // reference's own augmentation cannot run, pre/process.py:252).  p' = (p - c) . A + c; the grid is
-// laid over the augmented hand, every voxel centre is taken back to the camera frame with Ainv,
-// projected and looked up as in pre/process.py:150-175, and the distances are measured in the
-// augmented frame.  The projection no longer separates per axis, so this kernel evaluates every
-// voxel directly (IEEE divisions, one pass); it is the training-time path, not the bench's.
+// laid over the augmented hand, every voxel centre is taken back to the camera frame with Ainv
+// (a sum of three per-axis table entries), projected and looked up as in pre/process.py:150-175, and the
+// distance vector is measured in the augmented frame: (v - w) . A.  The projection no longer separates
+// per axis, so pass 1 projects every voxel itself; it is the training-time path, not the bench's.
 __device__ __forceinline__ void xform(float px, float py, float pz, const float* __restrict__ M,
                                       const float* __restrict__ c, float (&q)[3]) {
     const float dx = __fsub_rn(px, c[0]), dy = __fsub_rn(py, c[1]), dz = __fsub_rn(pz, c[2]);
@@ -1821,21 +1821,6 @@ __device__ __forceinline__ void xform(float px, float py, float pz, const float*
 // CTA shape of the augmented kernel: 8 warps, three CTAs per SM (the staged crop allows no more).  Measured on B200,
 // 8,500 default frames: 256 x 3 1.306 ms; 512 x 2 (64 registers, 140 bytes spilled) 1.453 ms; 384 x 2 with the
 // round-2 experiments 1.49 ms - with two CTAs per SM nothing covers a CTA's prologue (crop wait, bounding box, tables).
-#ifndef DTSDF_AUGX_SAFE
-#define DTSDF_AUGX_SAFE 1
-#endif
-#ifndef DTSDF_AUGX_MIN3
-#define DTSDF_AUGX_MIN3 1
-#endif
-#ifndef DTSDF_AUGX_TRUNC3
-#define DTSDF_AUGX_TRUNC3 1
-#endif
-#ifndef DTSDF_AUGX_OPAQUE
-#define DTSDF_AUGX_OPAQUE 1
-#endif
-#ifndef DTSDF_AUGX_SELP
-#define DTSDF_AUGX_SELP 1
-#endif
 #ifndef DTSDF_AUG_NT
 #define DTSDF_AUG_NT 256
 #define DTSDF_AUG_MIN_CTAS 3
@@ -1856,11 +1841,10 @@ struct AugFrame {
 
 // Per-axis tables of the separable voxel -> camera map (specification: oracle/dtsdf_oracle.c, step 3):
 //   v_k = tx[x][k] + (ty[y][k] + tz[z][k]),   tx[i] = (va_x[i] - c_x) * Ainv[0][.],  ty likewise with row 1,
-//   tz[i][k] = fma(va_z[i] - c_z, Ainv[2][k], c_k);   va[axis][i]: the voxel centres in the augmented frame.
+//   tz[i][k] = fma(va_z[i] - c_z, Ainv[2][k], c_k);   va_axis[i]: the voxel centres in the augmented frame.
 template <int R>
 struct __align__(16) AugTables {
     float4 tx[R], ty[R], tz[R];
-    float va[3][R];
 };
 
 template <int R, int LAYOUT>
@@ -1929,14 +1913,12 @@ __device__ __forceinline__ float aug_lookup(const AugFrame& k, float vx, float v
     px = __float2int_rz(fpx);
     py = __float2int_rz(fpy);
     const unsigned ux = (unsigned)(px - k.l), uy = (unsigned)(py - k.t);
-#if DTSDF_AUGX_SELP
     if (STAGED && SAFE) {                                               // (outside: the zero word below the crop)
         int idx;                                                        // one predicate, one select
         asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\tsetp.lt.and.u32 p, %3, %4, p;\n\tselp.b32 %0, %5, -1, p;\n\t}"
             : "=r"(idx) : "r"(ux), "r"((unsigned)k.bw), "r"(uy), "r"((unsigned)k.bh), "r"((int)(uy * (unsigned)k.bw + ux)));
         return lds_f32(k.crop_s32 + 4u * (unsigned)idx);
     }
-#endif
     bool in = (ux < (unsigned)k.bw) & (uy < (unsigned)k.bh);
     if (!SAFE) {
         const float fs = __fadd_rn(fpx, fpy);
@@ -1949,14 +1931,8 @@ __device__ __forceinline__ float aug_lookup(const AugFrame& k, float vx, float v
     return in ? __ldg(k.crop + ((int)uy * k.bw + (int)ux)) : 0.0f;
 }
 
-// a / trunc and d / focal of pass 2: the fixed-divisor forms (div_fixed, file header) inside their proven
-// ranges - dividend 0 or 2^-60 <= |a| <= 2^60 with trunc in [2^-20, 2^20]; 1 <= |d| < 2^40 with the default
-// focal - and IEEE division otherwise.  Bit-identical either way.
-__device__ __forceinline__ float aug_div_trunc(const AugFrame& k, float a) {
-    const float m = fabsf(a);
-    if (k.fast_t && (m == 0.0f || (m >= 0x1p-60f && m <= 0x1p60f))) return div_fixed<false>(a, k.trunc, k.ytr);
-    return __fdiv_rn(a, k.trunc);
-}
+// d / focal of pass 2: the fixed-divisor form (div_fixed, file header) inside its proven range - 1 <= |d| < 2^40
+// with the default focal - and IEEE division otherwise.  Bit-identical either way.
 __device__ __forceinline__ float aug_div_focal(const AugFrame& k, float d) {
     if (k.fast_f && fabsf(d) < BIG_DEPTH) return div_fixed<true>(d, k.focal, k.yf);     // (|d| >= 1: valid depth)
     return __fdiv_rn(d, k.focal);
@@ -1984,11 +1960,47 @@ __device__ __forceinline__ bool aug_classify_group(const AugFrame& k, const AugT
     return near;
 }
 
+// Pass 2, one voxel, any operands: the specification's steps in its own order (oracle/dtsdf_oracle.c), the divisions
+// in their fixed-divisor forms where their range tests allow.
+__device__ __forceinline__ void aug_eval_voxel(const AugFrame& k, const float* __restrict__ A, float vx, float vy, float vz,
+                                               float d, int px, int py, float& t0, float& t1, float& t2) {
+    t0 = 0.0f; t1 = 0.0f; t2 = 0.0f;
+    if (fabsf(d) < 1.0f) return;
+    // the distance vector in the augmented frame: (v - w) . A, the products in the order of xform()
+    const float c1 = aug_div_focal(k, d);
+    const float dx = __fsub_rn(vx, __fmul_rn((float)(px - k.cx), c1));
+    const float dy = __fsub_rn(vy, __fmul_rn((float)(-(py - k.cy)), c1));
+    const float dz = __fadd_rn(vz, d);                                                 // v_z - w_z, w_z = -d
+    float e[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        e[q] = __fmul_rn(dx, A[q]);
+        e[q] = __fmaf_rn(dy, A[3 + q], e[q]);
+        e[q] = __fmaf_rn(dz, A[6 + q], e[q]);
+    }
+    // the three divisions by trunc behind ONE range test (div_fixed's, file header, on the smallest and the
+    // largest of the three magnitudes; a zero component takes the IEEE branch with the rest of its voxel)
+    if (k.fast_t && fmin3(fabsf(e[0]), fabsf(e[1]), fabsf(e[2])) >= 0x1p-60f && fmax3(fabsf(e[0]), fabsf(e[1]), fabsf(e[2])) <= 0x1p60f) {
+        t0 = fabsf(div_fixed<false>(e[0], k.trunc, k.ytr));                 // |a| / b == |a / b| under RN
+        t1 = fabsf(div_fixed<false>(e[1], k.trunc, k.ytr));
+        t2 = fabsf(div_fixed<false>(e[2], k.trunc, k.ytr));
+    } else {
+        t0 = fabsf(__fdiv_rn(e[0], k.trunc)); t1 = fabsf(__fdiv_rn(e[1], k.trunc)); t2 = fabsf(__fdiv_rn(e[2], k.trunc));
+    }
+    const float ss = __fadd_rn(__fadd_rn(__fmul_rn(t0, t0), __fmul_rn(t1, t1)), __fmul_rn(t2, t2));
+    // sqrt_rn(ss) > 1 <=> ss > nextafter(1,2); then min(t,1) is the identity below it,
+    // except for NaN (kept) - same as the specification's comparisons
+    if (ss > THR_SQ) { t0 = 1.0f; t1 = 1.0f; t2 = 1.0f; }
+    if (1.0f < t0) t0 = 1.0f;
+    if (1.0f < t1) t1 = 1.0f;
+    if (1.0f < t2) t2 = 1.0f;
+    if (-d > vz) { t0 = -t0; t1 = -t1; t2 = -t2; }
+}
+
 // Pass 2: the specification's evaluation of all four voxels of a listed group.
 template <int R, int LAYOUT, bool STAGED, bool SAFE>
 __device__ __forceinline__ void aug_eval_group(const AugFrame& k, const AugTables<R>* __restrict__ T,
-                                               const float* __restrict__ A, const float* __restrict__ c,
-                                               int g, float* __restrict__ out) {
+                                               const float* __restrict__ A, int g, float* __restrict__ out) {
     constexpr int CH = R * R * R;
     int f0, m, s;
     aug_group_index<R, LAYOUT>(g, f0, m, s);
@@ -1999,39 +2011,7 @@ __device__ __forceinline__ void aug_eval_group(const AugFrame& k, const AugTable
     for (int j = 0; j < 4; ++j) {
         int px, py;
         const float d = aug_lookup<STAGED, SAFE>(k, vx[j], vy[j], vz[j], px, py);
-        float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
-        if (!(fabsf(d) < 1.0f)) {
-            const int xi = LAYOUT == 0 ? s : f0 + j, zi = LAYOUT == 0 ? f0 + j : s;
-            const float va0 = T->va[0][xi], va1 = T->va[1][m], va2 = T->va[2][zi];
-            const float c1 = aug_div_focal(k, d);
-            float wa[3];
-            xform(__fmul_rn((float)(px - k.cx), c1), __fmul_rn((float)(-(py - k.cy)), c1), -d, A, c, wa);
-#if DTSDF_AUGX_TRUNC3
-            // the three divisions by trunc behind ONE range test (aug_div_trunc's, on the smallest and the largest of
-            // the three magnitudes; a zero difference takes the IEEE branch with the rest of its voxel)
-            const float a0 = __fsub_rn(va0, wa[0]), a1 = __fsub_rn(va1, wa[1]), a2 = __fsub_rn(va2, wa[2]);
-            if (k.fast_t && fmin3(fabsf(a0), fabsf(a1), fabsf(a2)) >= 0x1p-60f && fmax3(fabsf(a0), fabsf(a1), fabsf(a2)) <= 0x1p60f) {
-                t0 = fabsf(div_fixed<false>(a0, k.trunc, k.ytr));         // |a| / b == |a / b| under RN
-                t1 = fabsf(div_fixed<false>(a1, k.trunc, k.ytr));
-                t2 = fabsf(div_fixed<false>(a2, k.trunc, k.ytr));
-            } else {
-                t0 = fabsf(__fdiv_rn(a0, k.trunc)); t1 = fabsf(__fdiv_rn(a1, k.trunc)); t2 = fabsf(__fdiv_rn(a2, k.trunc));
-            }
-#else
-            t0 = fabsf(aug_div_trunc(k, __fsub_rn(va0, wa[0])));          // |a| / b == |a / b| under RN
-            t1 = fabsf(aug_div_trunc(k, __fsub_rn(va1, wa[1])));
-            t2 = fabsf(aug_div_trunc(k, __fsub_rn(va2, wa[2])));
-#endif
-            const float ss = __fadd_rn(__fadd_rn(__fmul_rn(t0, t0), __fmul_rn(t1, t1)), __fmul_rn(t2, t2));
-            // sqrt_rn(ss) > 1 <=> ss > nextafter(1,2); then min(t,1) is the identity below it,
-            // except for NaN (kept) - same as the specification's comparisons
-            if (ss > THR_SQ) { t0 = 1.0f; t1 = 1.0f; t2 = 1.0f; }
-            if (1.0f < t0) t0 = 1.0f;
-            if (1.0f < t1) t1 = 1.0f;
-            if (1.0f < t2) t2 = 1.0f;
-            if (-d > vz[j]) { t0 = -t0; t1 = -t1; t2 = -t2; }
-        }
-        o0[j] = t0; o1[j] = t1; o2[j] = t2;
+        aug_eval_voxel(k, A, vx[j], vy[j], vz[j], d, px, py, o0[j], o1[j], o2[j]);
     }
     float* p = out + 4 * (size_t)g;
     st_f4(p, make_float4(o0[0], o0[1], o0[2], o0[3]));
@@ -2042,7 +2022,7 @@ __device__ __forceinline__ void aug_eval_group(const AugFrame& k, const AugTable
 // Both passes over one frame.
 template <int R, int LAYOUT, bool STAGED, bool SAFE>
 __device__ __forceinline__ void aug_voxel_passes(const AugFrame& k, const AugTables<R>* __restrict__ T,
-                                                 const float* __restrict__ A, const float* __restrict__ c,
+                                                 const float* __restrict__ A,
                                                  unsigned short* __restrict__ list, float* __restrict__ out) {
     constexpr int CH = R * R * R;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -2065,7 +2045,7 @@ __device__ __forceinline__ void aug_voxel_passes(const AugFrame& k, const AugTab
         cnt += __popc(bal);
         if (cnt >= 32) {
             __syncwarp();
-            aug_eval_group<R, LAYOUT, STAGED, SAFE>(k, T, A, c, (int)list[lane], out);
+            aug_eval_group<R, LAYOUT, STAGED, SAFE>(k, T, A, (int)list[lane], out);
             const int rem = cnt - 32;
             unsigned short carry = 0;
             if (lane < rem) carry = list[32 + lane];
@@ -2075,7 +2055,7 @@ __device__ __forceinline__ void aug_voxel_passes(const AugFrame& k, const AugTab
         }
     }
     __syncwarp();
-    if (lane < cnt) aug_eval_group<R, LAYOUT, STAGED, SAFE>(k, T, A, c, (int)list[lane], out);
+    if (lane < cnt) aug_eval_group<R, LAYOUT, STAGED, SAFE>(k, T, A, (int)list[lane], out);
 }
 
 // Far-surface shortcut of the augmented path.  In exact arithmetic v' - w' = (v* - w) . A with v* the
@@ -2232,14 +2212,10 @@ __global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const _
                 const bool v0 = !(fabsf(d0) < 1.0f), v1 = !(fabsf(d1) < 1.0f);
                 if (!(v0 || v1)) continue;
                 float fx0 = (float)(col + fr.l - a.center_x), fx1 = (float)(col + 32 + fr.l - a.center_x);
-#if DTSDF_AUGX_MIN3
                 // a pixel without depth takes its partner's place: the pair then holds the valid pixel twice and
                 // the extremes need no per-pixel guard (three-input minimum / maximum over both lanes of the pair)
                 const float e0 = v0 ? d0 : d1, e1 = v1 ? d1 : d0;
                 fx0 = v0 ? fx0 : fx1; fx1 = v1 ? fx1 : fx0;
-#else
-                const float e0 = d0, e1 = d1;
-#endif
                 float2 q;
                 if (deff && fabsf(e0) < BIG_DEPTH && fabsf(e1) < BIG_DEPTH)
                     q = div_fixed2<true>(make_float2(e0, e1), make_float2(-focal, -focal), make_float2(yf, yf));
@@ -2260,12 +2236,7 @@ __global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const _
                 }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-#if DTSDF_AUGX_MIN3
                     mn[k] = fmin3(mn[k], pa[k].x, pa[k].y); mx[k] = fmax3(mx[k], pa[k].x, pa[k].y);
-#else
-                    if (v0) { mn[k] = pa[k].x < mn[k] ? pa[k].x : mn[k]; mx[k] = pa[k].x > mx[k] ? pa[k].x : mx[k]; }
-                    if (v1) { mn[k] = pa[k].y < mn[k] ? pa[k].y : mn[k]; mx[k] = pa[k].y > mx[k] ? pa[k].y : mx[k]; }
-#endif
                 }
             }
         }
@@ -2325,7 +2296,6 @@ __global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const _
         const float o = axis == 0 ? ox : (axis == 1 ? oy : oz);
         const float va = __fadd_rn(o, __fmul_rn((float)i, voxel_len));
         const float dd = __fsub_rn(va, c[axis]);
-        tab.va[axis][i] = va;
         if (axis == 0)      tab.tx[i] = make_float4(__fmul_rn(dd, Ainv[0]), __fmul_rn(dd, Ainv[1]), __fmul_rn(dd, Ainv[2]), 0.0f);
         else if (axis == 1) tab.ty[i] = make_float4(__fmul_rn(dd, Ainv[3]), __fmul_rn(dd, Ainv[4]), __fmul_rn(dd, Ainv[5]), 0.0f);
         else                tab.tz[i] = make_float4(__fmaf_rn(dd, Ainv[6], c[0]), __fmaf_rn(dd, Ainv[7], c[1]),
@@ -2334,9 +2304,7 @@ __global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const _
     __shared__ unsigned short glist[AUG_NW][64];
     AugFrame k;
     k.crop = crop; k.crop_s32 = smem_u32(crop_s);
-#if DTSDF_AUGX_OPAQUE
     asm volatile("" : "+r"(k.crop_s32));      // kept in a register: rebuilt from the CTA's shared window per group otherwise
-#endif
  k.l = fr.l; k.t = fr.t; k.bw = max(fr.bw, 0); k.bh = max(fr.bh, 0);   // bad header: empty crop
     k.cx = a.center_x; k.cy = a.center_y; k.focal = focal; k.trunc = trunc;
     k.yf = __frcp_rn(focal); k.ytr = __frcp_rn(trunc);
@@ -2350,9 +2318,9 @@ __global__ void __launch_bounds__(AUG_NT, AUG_MIN_CTAS) dtsdf_aug_kernel(const _
     __syncthreads();          // the tables are complete
     k.t_far = t_far_s;
     float* out = a.vol + (size_t)f * 3 * CH;
-    if (!fr.staged)                     aug_voxel_passes<R, LAYOUT, false, false>(k, &tab, A, c, glist[warp], out);
-    else if (DTSDF_AUGX_SAFE && safe_s) aug_voxel_passes<R, LAYOUT, true, true>(k, &tab, A, c, glist[warp], out);
-    else                                aug_voxel_passes<R, LAYOUT, true, false>(k, &tab, A, c, glist[warp], out);
+    if (!fr.staged)                     aug_voxel_passes<R, LAYOUT, false, false>(k, &tab, A, glist[warp], out);
+    else if (safe_s)                    aug_voxel_passes<R, LAYOUT, true, true>(k, &tab, A, glist[warp], out);
+    else                                aug_voxel_passes<R, LAYOUT, true, false>(k, &tab, A, glist[warp], out);
 }
 
 template <int R, int LAYOUT>
