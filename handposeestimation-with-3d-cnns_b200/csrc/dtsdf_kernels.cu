@@ -2058,18 +2058,19 @@ __device__ __forceinline__ void aug_voxel_passes(const AugFrame& k, const AugTab
     if (lane < cnt) aug_eval_group<R, LAYOUT, STAGED, SAFE>(k, T, A, (int)list[lane], out);
 }
 
-// Far-surface shortcut of the augmented path.  In exact arithmetic v' - w' = (v* - w) . A with v* the
-// exact preimage of the voxel centre v' under p -> (p - c).A + c, so |v' - w'| >= smin(A) |v* - w| >=
-// smin(A) (|v_z - w_z| - |v - v*|), where v = (v' - c).Ainv + c is what the specification projects and
-// |v - v*| <= |v' - c| |Ainv.A - I| / smin(A) accounts for a caller's Ainv that is not exactly A^-1.
-// Lower bound for smin(A): |det A| / (s1 s2) >= 2 |det A| / |A|_F^2.  If
+// Far-surface shortcut of the augmented path.  The specification's distance vector is (v - w) . A, v the camera-
+// frame point it projects, and |u . A| >= smin(A) |u| >= smin(A) |u_z| for any u.  Lower bound for smin(A):
+// |det A| / (s1 s2) >= 2 |det A| / |A|_F^2.  If
 //     |v_z - w_z| > t_far = (trunc (1 + 2^-8) + slack) / smin_lo + drift
-// then |v' - w'| / trunc > 1 with a margin far above the float32 rounding of the specification's own
+// then |(v - w) . A| / trunc > 1 with a margin far above the float32 rounding of the specification's own
 // evaluation (slack: absolute rounding of coordinates of the frame's magnitude, 2^-17 relative; the
 // part of the rounding that grows with |d| is relative to |v_z - w_z| itself and below 2^-12 while
 // smin_lo > 2^-6 |A|_F, required here), so the Euclidean truncation fires and the voxel is +-1 by the
-// sign of v_z - w_z (pre/process.py:180-194).  Anything unusual (non-finite or huge entries, a nearly
-// singular A, tiny or huge trunc) switches the shortcut off: t_far = +inf.
+// sign of v_z - w_z (pre/process.py:180-194).  drift and the test on |Ainv.A - I| date from the first form of the
+// specification, which measured from the voxel centre v' itself - v = (v' - c).Ainv + c is its preimage only as far
+// as the caller's Ainv is A^-1; they are kept: more margin, and a map whose Ainv is unrelated to A runs without the
+// shortcut.  Anything unusual (non-finite or huge entries, a nearly singular A, tiny or huge trunc) switches the
+// shortcut off: t_far = +inf.
 __device__ __forceinline__ float aug_far_threshold(const float* __restrict__ A, const float* __restrict__ Ainv,
                                                    const float* __restrict__ c, float trunc, float max_l,
                                                    float mid0, float mid1, float mid2) {

@@ -1057,6 +1057,52 @@ def test_augmented_dtsdf_unusual_transforms():
             assert _same(got[i], cv[i]), "frame %d layout %d" % (i, layout)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("focal", [241.42, 300.0, 1e-7])
+def test_augmented_dtsdf_either_side_of_the_safe_frame_test(focal):
+    """The augmented kernel runs a frame through its straight-line reciprocal division only when the whole grid has
+    2^-60 <= |v_z| <= 2^60 and the focal is inside 2^+-20 (csrc/dtsdf_kernels.cu: aug_grid_is_safe); both
+    instantiations must give the specification's result.  Frames on either side of that test: ordinary maps (safe),
+    an Ainv that stretches the grid across the camera plane z = 0 (v_z of either sign, zero and next to zero:
+    infinite and NaN projections), a grid wholly behind the camera, a crop that starts at pixel (0, 0) (where the
+    pixel of a NaN projection would land) - with the default focal, another one, and one outside the proven range."""
+    import importlib
+    import torch
+    amod = importlib.import_module(pkg.__name__ + ".augment")
+
+    def rec(A, Ainv=None, c=(0, 0, -380.0)):
+        A = np.asarray(A, dtype=np.float64).reshape(3, 3)
+        Ainv = np.linalg.inv(A) if Ainv is None else np.asarray(Ainv, dtype=np.float64).reshape(3, 3)
+        return np.concatenate([A.reshape(-1), Ainv.reshape(-1), np.asarray(c, dtype=np.float64)]).astype(np.float32)
+
+    t = np.deg2rad(25.0)
+    Rz = np.array([[np.cos(t), np.sin(t), 0], [-np.sin(t), np.cos(t), 0], [0, 0, 1.0]])
+    mats = [rec(np.diag([1.2, 0.8, 1.0]) @ Rz),                                  # safe
+            rec(np.eye(3), Ainv=np.diag([1.0, 1.0, 6.0])),                       # the grid crosses z = 0
+            rec(Rz, Ainv=np.diag([1.0, 1.0, 3.5]) @ Rz.T),                       # crosses z = 0, rotated
+            rec(np.eye(3), Ainv=np.diag([1.0, 1.0, -1.0])),                      # grid mirrored to behind the camera (z > 0): safe
+            rec(np.eye(3), Ainv=np.zeros((3, 3)), c=(0, 0, 0)),                  # every voxel at the camera centre: v_z = 0
+            rec(np.diag([0.9, 1.1, 1.0]) @ Rz, c=(3.0, -2.0, -400.0))]           # safe
+    frames = synth.make_frames(range(1300, 1300 + len(mats)), box=(0, 0, 110, 120))   # crops that start at pixel (0, 0)
+    frames += synth.make_frames(range(1400, 1400 + len(mats)))
+    aug = np.stack(mats + mats).astype(np.float32)
+    headers, offsets, packed = pack_simple(frames)
+    dev = torch.device("cuda:0")
+    for layout in (0, 1):
+        cfg = pkg.capi.default_config(32, layout, pkg.BBOX_PIXELS)
+        cfg.focal = focal
+        vol, ml, mp = amod.voxelize_aug_device(torch.from_numpy(packed).to(dev), torch.from_numpy(offsets).to(dev),
+                                               torch.from_numpy(headers).to(dev), torch.from_numpy(aug).to(dev),
+                                               130 * 150, cfg)
+        torch.cuda.synchronize()
+        cv, cml, cmp_ = c_oracle.dtsdf_aug_batch(headers, offsets, packed, aug, R=32, layout=layout, focal=focal)
+        assert _same(ml.cpu().numpy(), cml) and _same(mp.cpu().numpy(), cmp_)
+        got = vol.cpu().numpy()
+        for i in range(len(frames)):
+            assert _same(got[i], cv[i]), "frame %d layout %d" % (i, layout)
+        assert focal < 1.0 or (np.count_nonzero(cv[0]) > 0 and np.count_nonzero(cv[len(mats)]) > 0)
+
+
 def test_identity_augmentation_is_the_plain_path(vox):
     import importlib
     import torch
