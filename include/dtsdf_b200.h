@@ -187,7 +187,7 @@ int dtsdf_voxelize_sampled_batch(const dtsdf_config* cfg, double focal, int32_t 
  * own affine map p' = (p - c) . A + c (row vector times matrix, A = stretch . rotation as in
  * show/visualize.py:106-114): the grid is laid over the AUGMENTED hand, voxel centres are taken back
  * to the camera frame with Ainv, projected and looked up as usual, distances are measured in the
- * augmented frame.  There is no reference behaviour to reproduce (data_aug raises AxisError,
+ * augmented frame ((v - w) . A for the camera-frame voxel centre v and surface point w).  There is no reference behaviour to reproduce (data_aug raises AxisError,
  * pre/process.py:252; cut_version voxelises the un-augmented depth, cut_version/pre/process.py:207):
  * the specification is oracle/dtsdf_oracle.c:oracle_dtsdf_aug_frame, matched bit for bit.
  *   d_aug         float[n][21] = A[3][3], Ainv[3][3], c[3]

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "handposeestimation-with-3d-cnns_b200", "lib", "obj")
 WANT = ["UBLKCP.S.G", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "FFMA2", "FMUL2", "FADD2", "CREDUX.MIN.F32",
         "CREDUX.MAX.F32", "STG.E.128", "LDS.128", "ATOMS.MIN.S32", "ATOMS.MAX.S32", "ATOMS.OR", "DMUL", "MUFU.RCP64H",
-        "REDUX.SUM.S32", "HMMA", "UTCHMMA", "STL", "LDL"]
+        "REDUX.SUM.S32", "FMNMX3", "MUFU.RCP", "FCHK", "HMMA", "UTCHMMA", "STL", "LDL"]
 
 
 def demangle(name):
@@ -22,6 +22,8 @@ print("# SASS mnemonics per kernel of lib/libdtsdf_b200.so: cuobjdump -sass of t
       "# UBLKCP.S.G = cp.async.bulk global->shared (TMA bulk copy); SYNCS.*TRANS64 = mbarrier expect-tx / try_wait;\n"
       "# FFMA2/FMUL2/FADD2 = Blackwell packed FP32 pipe; CREDUX = redux.sync.{min,max}.f32; ATOMS.OR / DMUL = the sampled bounding\n"
       "# box; no HMMA / UTC*MMA anywhere (there is no contraction on this path); STL/LDL = spills.\n"
+      "# FMNMX3 = three-input min / max (sm_100); MUFU.RCP against FCHK: every IEEE division carries one of each, a reciprocal\n"
+      "# sequence without range check (the augmented kernel's safe-frame division, the fixed-divisor forms) only the former.\n"
       "# dtsdf_fused_kernel<R, LAYOUT, DEFF, SAMPLED>, dtsdf_aug_kernel<R, LAYOUT>.")
 for obj in ("dtsdf_kernels.cu.o", "dtsdf_codec.cu.o"):
     sass = subprocess.run(["cuobjdump", "-sass", os.path.join(OBJ, obj)], capture_output=True, text=True, check=True).stdout
