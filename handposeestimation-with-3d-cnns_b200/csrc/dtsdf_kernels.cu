@@ -1884,9 +1884,6 @@ __device__ __forceinline__ void aug_camera4(const AugTables<R>* __restrict__ T, 
     }
 }
 
-// Projection and depth lookup of one voxel (pre/process.py:154-167), branch-free.  Returns the depth, or a
-// value with |d| < 1 ("no depth": the voxel stays 0) when the projection is not finite or outside the crop.
-// STAGED: the crop is in shared memory and the word right below it is 0.0f - the target of "outside".
 // coeff = -focal / v_z (pre/process.py:154).  SAFE is a per-frame fact (aug_grid_is_safe): every voxel of the frame
 // has 2^-60 <= |v_z| <= 2^60, and 2^-20 <= |focal| <= 2^20.  The division is then the straight-line part of what the
 // compiler emits for __fdiv_rn - reciprocal seed (MUFU.RCP), one Newton step, quotient, one residual correction -
@@ -1902,6 +1899,9 @@ __device__ __forceinline__ float aug_div_coeff(float nf, float vz) {
     return __fmaf_rn(r1, __fmaf_rn(-vz, q0, nf), q0);
 }
 
+// Projection and depth lookup of one voxel (pre/process.py:154-167), branch-free.  Returns the depth, or a
+// value with |d| < 1 ("no depth": the voxel stays 0) when the projection is not finite or outside the crop.
+// STAGED: the crop is in shared memory and the word right below it is 0.0f - the target of "outside".
 template <bool STAGED, bool SAFE>
 __device__ __forceinline__ float aug_lookup(const AugFrame& k, float vx, float vy, float vz, int& px, int& py) {
     const float coeff = aug_div_coeff<SAFE>(-k.focal, vz);
