@@ -622,9 +622,14 @@ def run_ours(args, rank, local_rank, world):
         raise RuntimeError("bench.py needs a CUDA device: the D-TSDF path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    stdout_fd = None
     if world > 1:
-        # stdout carries the JSON line only: NCCL's own banner (NCCL_DEBUG=VERSION on some boxes) goes to a file
+        # stdout carries the JSON line only: NCCL's own banner ("NCCL version ...", printed by the library on some
+        # boxes whatever NCCL_DEBUG_FILE says) goes to stderr - file descriptor 1 points there until the line is printed
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/dtsdf_bench_nccl.%h.%p.log")
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     build_cuda()
     pkg = load_package()
@@ -862,6 +867,9 @@ def run_ours(args, rank, local_rank, world):
             if R == 32:
                 line["cpu_baseline"]["reference_numba_kernels_on_this_gpu"] = numba_gpu_rate(
                     headers, offsets, h_packed.array)
+        if stdout_fd is not None:
+            sys.stdout.flush()
+            os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
     barrier()
     vox.close()
