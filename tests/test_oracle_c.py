@@ -65,3 +65,30 @@ def test_identity_augmentation_specification_reduces_to_the_reference_path():
         v0, ml0, mp0, _ = c_oracle.dtsdf_batch(headers, offsets, packed, layout=layout)
         assert np.array_equal(v, v0) and np.array_equal(np.signbit(v), np.signbit(v0))
         assert np.array_equal(ml, ml0) and np.array_equal(mp, mp0)
+
+
+def test_augmentation_specification_is_invariant_under_a_power_of_two_scale():
+    """A size-independent property of the augmented D-TSDF's specification (oracle_dtsdf_aug_frame): with the map A
+    replaced by 2A (Ainv by Ainv / 2, centre 0) every augmented point, the grid, the voxel length and the truncation
+    double EXACTLY, the camera-frame voxel centres stay what they were - so the volume is the same bit for bit, max_l
+    and mid_p double."""
+    import helpers
+    frames = helpers.synth.make_frames(range(60, 64))
+    headers, offsets, packed = helpers.pack_simple(frames)
+    rng = np.random.default_rng(5)
+    aug = np.zeros((len(frames), 21), np.float32)
+    for i in range(len(frames)):
+        t = rng.uniform(-0.6, 0.6)
+        A = np.diag([rng.uniform(0.7, 1.4), rng.uniform(0.7, 1.4), 1.0]) @ np.array(
+            [[np.cos(t), np.sin(t), 0.0], [-np.sin(t), np.cos(t), 0.0], [0.0, 0.0, 1.0]])
+        aug[i, :9] = A.astype(np.float32).reshape(-1)
+        aug[i, 9:18] = np.linalg.inv(A).astype(np.float32).reshape(-1)
+    aug2 = aug.copy()
+    aug2[:, :9] *= np.float32(2.0)
+    aug2[:, 9:18] *= np.float32(0.5)
+    for layout in (0, 1):
+        v, ml, mp = c_oracle.dtsdf_aug_batch(headers, offsets, packed, aug, layout=layout)
+        v2, ml2, mp2 = c_oracle.dtsdf_aug_batch(headers, offsets, packed, aug2, layout=layout)
+        assert np.count_nonzero(v) > 0
+        assert np.array_equal(v, v2) and np.array_equal(np.signbit(v), np.signbit(v2))
+        assert np.array_equal(ml2, np.float32(2.0) * ml) and np.array_equal(mp2, np.float32(2.0) * mp)
